@@ -1,0 +1,240 @@
+"""celda_b200: host-side mirror (Python + ctypes) of celda's hot-path interface over libcelda_cuda.so.
+
+The product is the CUDA library behind include/celda_cuda.h; this package only marshals numpy arrays across the
+C ABI with the reference's names, argument meaning and error behaviour (R/RcppExports.R, R/matrixSums.R,
+R/celda_C.R, R/celda_G.R, R/celda_CG.R).  Matrices are column-major like R (numpy order="F"); labels are 1-based.
+There is no CPU fallback: every call raises CeldaCudaError if the CUDA library or a device is missing.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import CeldaCudaError, build, check, declared_functions, lib  # noqa: F401
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+MODEL_CG, MODEL_C, MODEL_G = 0, 1, 2
+
+
+def _d(a):
+    return np.asfortranarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.asfortranarray(a, dtype=np.int32)
+
+
+def _pd(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _pi(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+class CSC:
+    """A dgCMatrix: Dim, p (int32[ncol+1]), i (int32[nnz], 0-based), x (float64[nnz])  (SURVEY.md L0)."""
+
+    def __init__(self, nrow, ncol, p, i, x):
+        self.nrow, self.ncol = int(nrow), int(ncol)
+        self.p, self.i, self.x = np.ascontiguousarray(p, np.int32), np.ascontiguousarray(i, np.int32), \
+            np.ascontiguousarray(x, np.float64)
+        if self.p.size != self.ncol + 1 or self.i.size != self.x.size or self.p[-1] != self.x.size:
+            raise ValueError("inconsistent dgCMatrix slots")
+
+    @classmethod
+    def from_dense(cls, mat):
+        """methods::as(x, "CsparseMatrix") (R/celda_CG.R:225)."""
+        mat = np.asarray(mat)
+        nr, nc = mat.shape
+        cols, rows = np.nonzero(mat.T)
+        p = np.zeros(nc + 1, dtype=np.int32)
+        np.cumsum(np.bincount(cols, minlength=nc), out=p[1:])
+        return cls(nr, nc, p, rows.astype(np.int32), mat.T[cols, rows].astype(np.float64))
+
+    @property
+    def nnz(self):
+        return int(self.x.size)
+
+
+def device_count():
+    n = C.c_int(0)
+    check(lib().celda_cuda_device_count(C.byref(n)))
+    return n.value
+
+
+def set_device(d):
+    check(lib().celda_cuda_set_device(int(d)))
+
+
+def launch_count():
+    return int(lib().celda_cuda_launch_count())
+
+
+def _vec(fn, x):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty_like(x)
+    check(fn(_pd(x), x.size, _pd(out)))
+    return out
+
+
+def lgamma(x):
+    """lgamma table builder (R/celda_CG.R:428-429,543): device arithmetic, value-identical to the sweeps'."""
+    return _vec(lib().celda_cuda_lgamma, x)
+
+
+def log(x):
+    return _vec(lib().celda_cuda_log, x)
+
+
+def exp(x):
+    return _vec(lib().celda_cuda_exp, x)
+
+
+# ------------------------------------------------------------------ src/matrixSumsSparse.cpp
+def colSumByGroupSparse(counts, group, K):
+    group = _i(group)
+    out = np.zeros((counts.nrow, K), order="F")
+    check(lib().celda_colSumByGroupSparse(counts.nrow, counts.ncol, _pi(counts.p), _pi(counts.i), _pd(counts.x),
+                                          _pi(group), group.size, K, _pd(out)))
+    return out
+
+
+def rowSumByGroupSparse(counts, group, L):
+    group = _i(group)
+    out = np.zeros((L, counts.ncol), order="F")
+    check(lib().celda_rowSumByGroupSparse(counts.nrow, counts.ncol, _pi(counts.p), _pi(counts.i), _pd(counts.x),
+                                          _pi(group), group.size, L, _pd(out)))
+    return out
+
+
+def colSumByGroupChangeSparse(counts, px, group, pgroup, K):
+    """px is updated IN PLACE and returned (reference quirk Q3)."""
+    group, pgroup = _i(group), _i(pgroup)
+    if not (px.flags.f_contiguous and px.dtype == np.float64):
+        raise TypeError("px must be a column-major float64 matrix (it is updated in place)")
+    check(lib().celda_colSumByGroupChangeSparse(counts.nrow, counts.ncol, _pi(counts.p), _pi(counts.i), _pd(counts.x),
+                                                _pd(px), px.shape[0], _pi(group), group.size, _pi(pgroup),
+                                                pgroup.size, K))
+    return px
+
+
+def rowSumByGroupChangeSparse(counts, px, group, pgroup, L):
+    group, pgroup = _i(group), _i(pgroup)
+    if not (px.flags.f_contiguous and px.dtype == np.float64):
+        raise TypeError("px must be a column-major float64 matrix (it is updated in place)")
+    check(lib().celda_rowSumByGroupChangeSparse(counts.nrow, counts.ncol, _pi(counts.p), _pi(counts.i), _pd(counts.x),
+                                                _pd(px), px.shape[1], _pi(group), group.size, _pi(pgroup),
+                                                pgroup.size, L))
+    return px
+
+
+# ------------------------------------------------------------------ device-resident chain
+class Chain:
+    """One chain of .celda_CG / .celda_C / .celda_G with counts and tables resident in HBM (celda_chain_*)."""
+
+    def __init__(self, counts, sampleLabel=None, K=1, L=1, alpha=1.0, beta=1.0, delta=1.0, gamma=1.0,
+                 model=MODEL_CG, device=0):
+        self._h = C.c_void_p()
+        self.counts, self.model, self.K, self.L = counts, model, int(K), int(L)
+        self.nG, self.nM = counts.nrow, counts.ncol
+        s = None
+        self.nS = 1
+        if model != MODEL_G:
+            s = _i(sampleLabel)
+            self.nS = int(s.max())
+        self.s = s
+        check(lib().celda_chain_create(C.byref(self._h), device, model, counts.nrow, counts.ncol, _pi(counts.p),
+                                       _pi(counts.i), _pd(counts.x), _pi(s), self.nS, self.K, self.L, alpha, beta,
+                                       delta, gamma))
+
+    def close(self):
+        if self._h:
+            lib().celda_chain_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_state(self, z=None, y=None):
+        z = None if z is None else _i(z)
+        y = None if y is None else _i(y)
+        check(lib().celda_chain_set_state(self._h, _pi(z), _pi(y)))
+
+    def get_state(self):
+        z = np.zeros(self.nM, np.int32) if self.model != MODEL_G else None
+        y = np.zeros(self.nG, np.int32) if self.model != MODEL_C else None
+        check(lib().celda_chain_get_state(self._h, _pi(z), _pi(y)))
+        return z, y
+
+    def sweep_y(self, ix, u, doSample=True):
+        ix, u = _i(ix), _d(u)
+        check(lib().celda_chain_sweep_y(self._h, _pi(ix), _pd(u), int(doSample)))
+
+    def sweep_z_gibbs(self, ix, u, doSample=True):
+        ix, u = _i(ix), _d(u)
+        check(lib().celda_chain_sweep_z_gibbs(self._h, _pi(ix), _pd(u), int(doSample)))
+
+    def iterate(self, ix_y, u_y, ix_z, u_z):
+        """One iteration of R/celda_CG.R:543-602 (no split heuristics); returns the log-likelihood."""
+        ll = C.c_double(0)
+        check(lib().celda_chain_iterate(self._h, _pi(ix_y), _pd(u_y), _pi(ix_z), _pd(u_z), C.byref(ll)))
+        return ll.value
+
+    def stage_draws(self, ix_y, u_y, ix_z, u_z):
+        """ix_y/u_y: [n_iter, nG]; ix_z/u_z: [n_iter, nM] (C-contiguous)."""
+        ix_y, u_y = np.ascontiguousarray(ix_y, np.int32), np.ascontiguousarray(u_y, np.float64)
+        ix_z, u_z = np.ascontiguousarray(ix_z, np.int32), np.ascontiguousarray(u_z, np.float64)
+        check(lib().celda_chain_stage_draws(self._h, ix_y.shape[0], _pi(ix_y), _pd(u_y), _pi(ix_z), _pd(u_z)))
+
+    def iterate_staged(self, it):
+        ll = C.c_double(0)
+        check(lib().celda_chain_iterate_staged(self._h, int(it), C.byref(ll)))
+        return ll.value
+
+    def loglik(self):
+        ll = C.c_double(0)
+        check(lib().celda_chain_loglik(self._h, C.byref(ll)))
+        return ll.value
+
+    def tables(self):
+        """The sufficient statistics as R holds them (.cCGDecomposeCounts, R/celda_CG.R:902-934)."""
+        K, L, nG, nM, nS = self.K, self.L, self.nG, self.nM, self.nS
+        t = dict(mCPByS=np.zeros((K, nS), np.int32, order="F"), nTSByC=np.zeros((L, nM), order="F"),
+                 nTSByCP=np.zeros((L, K), order="F"), nGByCP=np.zeros((nG, K), order="F"), nCP=np.zeros(K),
+                 nByC=np.zeros(nM), nByG=np.zeros(nG), nByTS=np.zeros(L), nGByTS=np.zeros(L, np.int32))
+        check(lib().celda_chain_get_tables(self._h, _pi(t["mCPByS"]), _pd(t["nTSByC"]), _pd(t["nTSByCP"]),
+                                           _pd(t["nGByCP"]), _pd(t["nCP"]), _pd(t["nByC"]), _pd(t["nByG"]),
+                                           _pd(t["nByTS"]), _pi(t["nGByTS"])))
+        return t
+
+    def probs(self):
+        pz = np.zeros((self.K, self.nM), order="F") if self.model != MODEL_G else None
+        py = np.zeros((self.L, self.nG), order="F") if self.model != MODEL_C else None
+        check(lib().celda_chain_get_probs(self._h, _pd(pz), _pd(py)))
+        return pz, py
+
+    def timer_start(self):
+        check(lib().celda_chain_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float(0)
+        check(lib().celda_chain_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def profile(self, enable=True):
+        check(lib().celda_chain_profile(self._h, int(enable)))
+
+    def profile_get(self):
+        names = ["sweep_y", "rowSumByGroupChange", "sweep_z", "colSumByGroupChange", "loglik"]
+        out = {}
+        for w, n in enumerate(names):
+            ms, nl = C.c_double(0), C.c_longlong(0)
+            st = (C.c_longlong * 3)()
+            check(lib().celda_chain_profile_get(self._h, w, C.byref(ms), C.byref(nl), st))
+            out[n] = dict(ms=ms.value, launches=nl.value, rounds=st[0], units=st[1], movers=st[2])
+        return out

@@ -1,0 +1,783 @@
+// libcelda_cuda: C ABI (include/celda_cuda.h) over the sm_100a kernels.  Host side of the drop-in boundary.
+#include "../../include/celda_cuda.h"
+
+#include <algorithm>
+#include <cmath>
+#include <memory>
+
+#include "common.cuh"
+#include "kernels.cuh"
+#include "sweeps.cuh"
+
+using namespace celda;
+
+namespace {
+
+int g_device = 0;
+
+inline int grid_for(long long n, int threads, int sms, int per_sm = 8) {
+    long long b = (n + threads - 1) / threads;
+    return (int)std::max<long long>(1, std::min<long long>(b, (long long)sms * per_sm));
+}
+
+struct LabelCheck {
+    DevBuf<int> flag;
+    int init(cudaStream_t st) {
+        CELDA_TRY(flag.alloc(1));
+        return flag.zero(st);
+    }
+};
+
+int check_labels_host(const int* g, long long n, int K, const char* what, const char* kname) {
+    for (long long i = 0; i < n; ++i)
+        if (g[i] < 1 || g[i] > K) return fail("The entries in '%s' need to be between 1 and '%s'.", what, kname);
+    return 0;
+}
+
+}  // namespace
+
+// ================================================================================================ chain
+struct celda_chain {
+    int device = 0, model = 0, nG = 0, nM = 0, nS = 0, K = 0, L = 0, sms = 148;
+    long long Z = 0;
+    double alpha = 1, beta = 1, delta = 1, gamma = 1;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool has_state = false;
+    DevBuf<int> cp, ci, cx, s, z, y, zprev, yprev;
+    DevBuf<int> nTSByC, nGByCP, nTSByCP, nByC, nGByTS, mCPByS;
+    DevBuf<long long> nCP, nByG, nByTS;
+    DevBuf<double> probsZ, probsY;
+    // sweep work space
+    DevBuf<double> bufP, bufA, colsum, lgnCP;
+    DevBuf<int> spec, status;
+    DevBuf<unsigned> barrier;
+    DevBuf<long long> stats;  // [which][3]
+    DevBuf<int> ixy, ixz;
+    DevBuf<double> uy, uz;
+    DevBuf<double> llPartial, llOut;
+    // staged draws
+    int staged_iters = 0;
+    DevBuf<int> st_ixy, st_ixz;
+    DevBuf<double> st_uy, st_uz;
+    int Wmax = 8192, Wmin = 128, lgT = 2048;
+    int npG = 0;
+    // profiling
+    bool profile = false;
+    double prof_ms[5] = {0, 0, 0, 0, 0};
+    long long prof_launches[5] = {0, 0, 0, 0, 0};
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+
+    ~celda_chain() {
+        cudaSetDevice(device);
+        for (auto& pe : pending) {
+            cudaEventDestroy(pe.second.first);
+            cudaEventDestroy(pe.second.second);
+        }
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (st) cudaStreamDestroy(st);
+    }
+};
+
+namespace {
+
+struct ProfScope {
+    celda_chain* h;
+    int which;
+    cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(celda_chain* h_, int w) : h(h_), which(w) {
+        if (h->profile) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, h->st);
+        }
+    }
+    ~ProfScope() {
+        if (h->profile) {
+            cudaEventRecord(b, h->st);
+            h->pending.push_back({which, {a, b}});
+        }
+    }
+};
+
+void prof_collect(celda_chain* h) {
+    for (auto& pe : h->pending) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, pe.second.first, pe.second.second) == cudaSuccess) {
+            h->prof_ms[pe.first] += ms;
+            h->prof_launches[pe.first] += 1;
+        }
+        cudaEventDestroy(pe.second.first);
+        cudaEventDestroy(pe.second.second);
+    }
+    h->pending.clear();
+}
+
+int chain_sync(celda_chain* h) {
+    CELDA_CUDA_OK(cudaStreamSynchronize(h->st));
+    prof_collect(h);
+    return 0;
+}
+
+int chain_check_status(celda_chain* h) {
+    int stv = 0;
+    CELDA_CUDA_OK(cudaMemcpyAsync(&stv, h->status.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CELDA_TRY(chain_sync(h));
+    if (stv == -1) return fail("sample.int would take the Walker alias branch (> 200 likely categories): not supported");
+    if (stv == -2) return fail("NA in probability vector");
+    if (stv == -3) return fail("too few positive probabilities");
+    if (stv) return fail("sweep failed with status %d", stv);
+    return 0;
+}
+
+// ---- decompose (R/celda_CG.R:902-934, R/celda_C.R:800-822, R/celda_G.R:712-733)
+int chain_decompose(celda_chain* h) {
+    cudaStream_t st = h->st;
+    const int sms = h->sms;
+    if (h->model != CELDA_MODEL_C) {  // nTSByC = rowSumByGroup(counts, y, L)
+        const int threads = 256, nwarp = threads / 32;
+        k_rowsum_csc<int><<<std::min((h->nM + nwarp - 1) / nwarp, sms * 8), threads, sizeof(int) * nwarp * h->L, st>>>(
+            h->nM, h->cp.p, h->ci.p, h->cx.p, h->y.p, h->L, h->nTSByC.p, nullptr);
+        count_launch();
+        CELDA_TRY(h->nByTS.zero(st));
+        k_fill_int<<<1, 256, 0, st>>>(h->nGByTS.p, h->L, 1);
+        k_module_totals<<<grid_for(h->nG, 256, sms), 256, 0, st>>>(h->y.p, h->nByG.p, h->nG,
+                                                                    (unsigned long long*)h->nByTS.p, h->nGByTS.p);
+        count_launch(2);
+    }
+    if (h->model != CELDA_MODEL_G) {  // nGByCP = colSumByGroup(counts, z, K); mCPByS = table(z, s)
+        const int threads = 256, nwarp = threads / 32;
+        CELDA_TRY(h->nGByCP.zero(st));
+        k_colsum_csc<int><<<std::min((h->nM + nwarp - 1) / nwarp, sms * 16), threads, 0, st>>>(
+            h->nM, h->cp.p, h->ci.p, h->cx.p, h->z.p, h->K, h->nGByCP.p);
+        CELDA_TRY(h->mCPByS.zero(st));
+        k_table_zs<<<grid_for(h->nM, 256, sms), 256, 0, st>>>(h->z.p, h->s.p, h->nM, h->K, h->mCPByS.p);
+        count_launch(2);
+    }
+    if (h->model == CELDA_MODEL_CG) {  // nTSByCP = colSumByGroup(nTSByC, z, K); nCP = colSums(nTSByCP)
+        CELDA_TRY(h->nTSByCP.zero(st));
+        k_colsum_dense<<<std::min(sms * 2, std::max(1, h->nM / 64)), 512, sizeof(int) * h->L * h->K, st>>>(
+            h->nTSByC.p, h->L, h->nM, h->z.p, h->K, h->nTSByCP.p);
+        k_colsums_small<<<1, 256, 0, st>>>(h->nTSByCP.p, h->L, h->K, h->nCP.p);
+        count_launch(2);
+    } else if (h->model == CELDA_MODEL_C) {
+        CELDA_TRY(h->nCP.zero(st));
+        k_colsums_genemajor<<<grid_for((long long)h->nG * h->K, 256, sms), 256, 0, st>>>(
+            h->nGByCP.p, h->nG, h->K, (unsigned long long*)h->nCP.p);
+        count_launch();
+    }
+    CELDA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int chain_loglik_async(celda_chain* h) {
+    ProfScope ps(h, 4);
+    cudaStream_t st = h->st;
+    LLArgs a{};
+    a.model = h->model;
+    a.K = h->K;
+    a.L = h->L;
+    a.nS = h->nS;
+    a.nG = h->nG;
+    a.nM = h->nM;
+    a.mCPByS = h->mCPByS.p;
+    a.phiTab = h->nTSByCP.p;
+    a.nByTS = h->nByTS.p;
+    a.nGByTS = h->nGByTS.p;
+    a.partial = h->llPartial.p;
+    a.alpha = h->alpha;
+    a.beta = h->beta;
+    a.delta = h->delta;
+    a.gamma = h->gamma;
+    a.out = h->llOut.p;
+    const int NB = 64;  // fixed partial-block count => deterministic order
+    int off = 0;
+    if (h->model != CELDA_MODEL_C) {
+        k_sum_lgamma<long long><<<NB, 256, 0, st>>>(h->nByG.p, h->nG, h->delta, h->llPartial.p);
+        count_launch();
+        a.npG = NB;
+        off = NB;
+    }
+    if (h->model == CELDA_MODEL_G) {
+        const int NBG = 256;
+        k_sum_lgamma<int><<<NBG, 256, 0, st>>>(h->nTSByC.p, (long long)h->L * h->nM, h->beta, h->llPartial.p + off);
+        k_sum_lgamma_colsums<<<NBG, 256, 0, st>>>(h->nTSByC.p, h->L, h->nM, h->beta, h->llPartial.p + off + NBG);
+        a.npPhiB = NBG;
+        a.npPhiD = NBG;
+        count_launch(2);
+    }
+    k_loglik_final<<<1, 256, 0, st>>>(a);
+    count_launch();
+    CELDA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_sweep_z(celda_chain* h, const int* d_ix, const double* d_u, int doSample, int which) {
+    ProfScope ps(h, which);
+    const int threads = 512, nwarp = threads / 32;
+    ZArgs a{};
+    a.R = h->L;
+    a.K = h->K;
+    a.nS = h->nS;
+    a.nM = h->nM;
+    a.counts = h->nTSByC.p;
+    a.nByC = h->nByC.p;
+    a.s = h->s.p;
+    a.z = h->z.p;
+    a.nTab = h->nTSByCP.p;
+    a.nCP = h->nCP.p;
+    a.mCPByS = h->mCPByS.p;
+    a.alpha = h->alpha;
+    a.beta = h->beta;
+    a.ix = d_ix;
+    a.u = d_u;
+    a.doSample = doSample;
+    a.probs = h->probsZ.p;
+    a.w = SweepWork{h->bufP.p, h->bufA.p, h->spec.p, h->colsum.p, h->lgnCP.p, h->barrier.p, h->status.p,
+                    h->stats.p + 3 * which, h->Wmax, h->Wmin, h->lgT};
+    const size_t smem = z_sweep_smem(a.R, a.K, a.nS, h->lgT, nwarp);
+    if (smem > 220 * 1024) return fail("z sweep: K=%d x R=%d tables need %zu bytes of shared memory (> 220 KB)", a.K, a.R, smem);
+    CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CELDA_CUDA_OK(cudaMemsetAsync(h->barrier.p, 0, sizeof(unsigned), h->st));
+    void* args[] = {&a};
+    CELDA_CUDA_OK(cudaLaunchCooperativeKernel((void*)k_sweep_z, dim3(h->sms), dim3(threads), args, smem, h->st));
+    count_launch();
+    return 0;
+}
+
+int launch_sweep_y(celda_chain* h, const int* d_ix, const double* d_u, int doSample, int which) {
+    ProfScope ps(h, which);
+    const int threads = 512, nwarp = threads / 32;
+    YArgs a{};
+    a.nG = h->nG;
+    a.ncol = h->K;
+    a.L = h->L;
+    a.counts = h->nGByCP.p;
+    a.nByG = h->nByG.p;
+    a.y = h->y.p;
+    a.tTab = h->nTSByCP.p;
+    a.nByTS = h->nByTS.p;
+    a.nGByTS = h->nGByTS.p;
+    a.beta = h->beta;
+    a.gamma = h->gamma;
+    a.delta = h->delta;
+    a.ix = d_ix;
+    a.u = d_u;
+    a.doSample = doSample;
+    a.probs = h->probsY.p;
+    a.w = SweepWork{h->bufP.p, h->bufA.p, h->spec.p, h->colsum.p, h->lgnCP.p, h->barrier.p, h->status.p,
+                    h->stats.p + 3 * which, h->Wmax, h->Wmin, h->lgT};
+    const size_t smem = y_sweep_smem(a.L, a.ncol, h->lgT, nwarp);
+    if (smem > 220 * 1024) return fail("y sweep: L=%d x K=%d tables need %zu bytes of shared memory (> 220 KB)", a.L, a.ncol, smem);
+    CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CELDA_CUDA_OK(cudaMemsetAsync(h->barrier.p, 0, sizeof(unsigned), h->st));
+    void* args[] = {&a};
+    CELDA_CUDA_OK(cudaLaunchCooperativeKernel((void*)k_sweep_y, dim3(h->sms), dim3(threads), args, smem, h->st));
+    count_launch();
+    return 0;
+}
+
+// y sweep + rowSumByGroupChange (R/celda_CG.R:544-564)
+int chain_step_y(celda_chain* h, const int* d_ix, const double* d_u, int doSample) {
+    if (h->model != CELDA_MODEL_CG) return fail("sweep_y: only the celda_CG chain is implemented on this handle");
+    CELDA_CUDA_OK(cudaMemcpyAsync(h->yprev.p, h->y.p, sizeof(int) * h->nG, cudaMemcpyDeviceToDevice, h->st));
+    CELDA_TRY(launch_sweep_y(h, d_ix, d_u, doSample, 0));
+    if (doSample) {
+        ProfScope ps(h, 1);
+        const int threads = 256, nwarp = threads / 32;
+        k_rowsum_change_csc<int><<<std::min((h->nM + nwarp - 1) / nwarp, h->sms * 16), threads, 0, h->st>>>(
+            h->nM, h->cp.p, h->ci.p, h->cx.p, h->y.p, h->yprev.p, h->L, h->nTSByC.p);
+        count_launch();
+    }
+    CELDA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// z sweep + colSumByGroupChange (R/celda_CG.R:567-585)
+int chain_step_z(celda_chain* h, const int* d_ix, const double* d_u, int doSample) {
+    if (h->model != CELDA_MODEL_CG) return fail("sweep_z_gibbs: only the celda_CG chain is implemented on this handle");
+    CELDA_CUDA_OK(cudaMemcpyAsync(h->zprev.p, h->z.p, sizeof(int) * h->nM, cudaMemcpyDeviceToDevice, h->st));
+    CELDA_TRY(launch_sweep_z(h, d_ix, d_u, doSample, 2));
+    if (doSample) {
+        ProfScope ps(h, 3);
+        const int threads = 256, nwarp = threads / 32;
+        k_colsum_change_csc<int><<<std::min((h->nM + nwarp - 1) / nwarp, h->sms * 16), threads, 0, h->st>>>(
+            h->nM, h->cp.p, h->ci.p, h->cx.p, h->z.p, h->zprev.p, h->K, h->nGByCP.p);
+        count_launch();
+    }
+    CELDA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int validate_order(const int* ix, long long n, const char* what) {
+    std::vector<unsigned char> seen((size_t)n, 0);
+    for (long long i = 0; i < n; ++i) {
+        const int v = ix[i];
+        if (v < 1 || v > n || seen[v - 1]) return fail("%s must be a permutation of 1..%lld", what, n);
+        seen[v - 1] = 1;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* celda_cuda_last_error(void) { return g_err; }
+
+int celda_cuda_device_count(int* n) {
+    CELDA_CUDA_OK(cudaGetDeviceCount(n));
+    return 0;
+}
+
+int celda_cuda_set_device(int device) {
+    CELDA_CUDA_OK(cudaSetDevice(device));
+    g_device = device;
+    return 0;
+}
+
+long long celda_cuda_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------ math
+static int math_vec(int op, const double* x, long long n, double* out) {
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    DevBuf<double> dx, dout;
+    CELDA_TRY(dx.upload(x, (size_t)n));
+    CELDA_TRY(dout.alloc((size_t)n));
+    const int grid = grid_for(n, 256, num_sms(g_device));
+    if (op == 0) k_math_vec<0><<<grid, 256>>>(dx.p, n, dout.p);
+    else if (op == 1) k_math_vec<1><<<grid, 256>>>(dx.p, n, dout.p);
+    else k_math_vec<2><<<grid, 256>>>(dx.p, n, dout.p);
+    count_launch();
+    CELDA_CUDA_OK(cudaGetLastError());
+    CELDA_TRY(dout.download(out, (size_t)n));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+int celda_cuda_lgamma(const double* x, long long n, double* out) { return math_vec(0, x, n, out); }
+int celda_cuda_log(const double* x, long long n, double* out) { return math_vec(1, x, n, out); }
+int celda_cuda_exp(const double* x, long long n, double* out) { return math_vec(2, x, n, out); }
+
+// ------------------------------------------------------------------------------------------------ sparse aggregation
+// The stateless entry points compute in double like the reference (NumericMatrix): sums of integer-valued
+// doubles are exact and order-independent, so atomics reproduce the reference bit for bit.
+struct CscDev {
+    DevBuf<int> p, i;
+    DevBuf<double> x;
+    int upload(int ncol, const int* hp, const int* hi, const double* hx) {
+        const long long nnz = hp[ncol];
+        CELDA_TRY(p.upload(hp, (size_t)ncol + 1));
+        CELDA_TRY(i.upload(hi, (size_t)nnz));
+        CELDA_TRY(x.upload(hx, (size_t)nnz));
+        return 0;
+    }
+};
+
+int celda_colSumByGroupSparse(int nrow, int ncol, const int* p, const int* i, const double* x, const int* group,
+                              long long ngroup, int K, double* out) {
+    if (ncol != ngroup) return fail("Length of 'group' must be equal to the number of columns in 'counts'.");
+    CELDA_TRY(check_labels_host(group, ngroup, K, "group", "K"));
+    if (K > ncol) return fail("'K' cannot be bigger than the number of columns in 'counts'.");
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    const int sms = num_sms(g_device);
+    CscDev m;
+    DevBuf<int> g;
+    DevBuf<double> acc, res;
+    CELDA_TRY(m.upload(ncol, p, i, x));
+    CELDA_TRY(g.upload(group, (size_t)ngroup));
+    CELDA_TRY(acc.alloc((size_t)nrow * K));
+    CELDA_TRY(acc.zero());
+    CELDA_TRY(res.alloc((size_t)nrow * K));
+    k_colsum_csc<double><<<std::min((ncol + 7) / 8, sms * 16), 256>>>(ncol, m.p.p, m.i.p, m.x.p, g.p, K, acc.p);
+    k_transpose_convert<double, double><<<grid_for((long long)nrow * K, 256, sms), 256>>>(acc.p, nrow, K, res.p, true);
+    count_launch(2);
+    CELDA_CUDA_OK(cudaGetLastError());
+    CELDA_TRY(res.download(out, (size_t)nrow * K));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
+int celda_rowSumByGroupSparse(int nrow, int ncol, const int* p, const int* i, const double* x, const int* group,
+                              long long ngroup, int L, double* out) {
+    if (nrow != ngroup) return fail("Length of 'group' must be equal to the number of rows in 'counts'.");
+    CELDA_TRY(check_labels_host(group, ngroup, L, "group", "L"));
+    if (L > nrow) return fail("'L' cannot be bigger than the number of rows in 'counts'.");
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    const int sms = num_sms(g_device);
+    CscDev m;
+    DevBuf<int> g;
+    DevBuf<double> res;
+    CELDA_TRY(m.upload(ncol, p, i, x));
+    CELDA_TRY(g.upload(group, (size_t)ngroup));
+    CELDA_TRY(res.alloc((size_t)L * ncol));
+    const int threads = (sizeof(double) * 8 * L <= 96 * 1024) ? 256 : 32, nwarp = threads / 32;
+    const size_t smem = sizeof(double) * nwarp * L;
+    if (smem > 200 * 1024) return fail("'L' = %d is too large for the aggregation kernel", L);
+    CELDA_CUDA_OK(cudaFuncSetAttribute(k_rowsum_csc<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_rowsum_csc<double><<<std::min((ncol + nwarp - 1) / nwarp, sms * 8), threads, smem>>>(ncol, m.p.p, m.i.p, m.x.p, g.p, L,
+                                                                                          res.p, nullptr);
+    count_launch();
+    CELDA_CUDA_OK(cudaGetLastError());
+    CELDA_TRY(res.download(out, (size_t)L * ncol));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
+int celda_colSumByGroupChangeSparse(int nrow, int ncol, const int* p, const int* i, const double* x, double* px,
+                                    int px_nrow, const int* group, long long ngroup, const int* pgroup,
+                                    long long npgroup, int K) {
+    if (ncol != ngroup) return fail("Length of 'group' must be equal to the number of columns in 'counts'.");
+    if (ngroup != npgroup) return fail("Length of 'group' must equal 'pgroup'.");
+    CELDA_TRY(check_labels_host(group, ngroup, K, "group", "K"));
+    CELDA_TRY(check_labels_host(pgroup, npgroup, K, "pgroup", "K"));
+    if (px_nrow != nrow) return fail("'px' and 'counts' must have the same number of rows.");
+    if (K > ncol) return fail("'K' cannot be bigger than the number of columns in 'counts'.");
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    const int sms = num_sms(g_device);
+    CscDev m;
+    DevBuf<int> g, pg;
+    DevBuf<double> dpx, acc;
+    CELDA_TRY(m.upload(ncol, p, i, x));
+    CELDA_TRY(g.upload(group, (size_t)ngroup));
+    CELDA_TRY(pg.upload(pgroup, (size_t)npgroup));
+    CELDA_TRY(dpx.upload(px, (size_t)nrow * K));
+    CELDA_TRY(acc.alloc((size_t)nrow * K));
+    const int grid = grid_for((long long)nrow * K, 256, sms);
+    k_transpose_convert<double, double><<<grid, 256>>>(dpx.p, nrow, K, acc.p, false);
+    k_colsum_change_csc<double><<<std::min((ncol + 7) / 8, sms * 16), 256>>>(ncol, m.p.p, m.i.p, m.x.p, g.p, pg.p, K, acc.p);
+    k_transpose_convert<double, double><<<grid, 256>>>(acc.p, nrow, K, dpx.p, true);
+    count_launch(3);
+    CELDA_CUDA_OK(cudaGetLastError());
+    CELDA_TRY(dpx.download(px, (size_t)nrow * K));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
+int celda_rowSumByGroupChangeSparse(int nrow, int ncol, const int* p, const int* i, const double* x, double* px,
+                                    int px_ncol, const int* group, long long ngroup, const int* pgroup,
+                                    long long npgroup, int L) {
+    if (nrow != ngroup) return fail("Length of 'group' must be equal to the number of rows in 'counts'.");
+    if (ngroup != npgroup) return fail("Length of 'group' must equal 'pgroup'.");
+    CELDA_TRY(check_labels_host(group, ngroup, L, "group", "L"));
+    CELDA_TRY(check_labels_host(pgroup, npgroup, L, "pgroup", "L"));
+    if (px_ncol != ncol) return fail("'px' and 'counts' must have the same number of rows.");
+    if (L > nrow) return fail("'L' cannot be bigger than the number of rows in 'counts'.");
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    const int sms = num_sms(g_device);
+    CscDev m;
+    DevBuf<int> g, pg;
+    DevBuf<double> dpx;
+    CELDA_TRY(m.upload(ncol, p, i, x));
+    CELDA_TRY(g.upload(group, (size_t)ngroup));
+    CELDA_TRY(pg.upload(pgroup, (size_t)npgroup));
+    CELDA_TRY(dpx.upload(px, (size_t)L * ncol));
+    k_rowsum_change_csc<double><<<std::min((ncol + 7) / 8, sms * 16), 256>>>(ncol, m.p.p, m.i.p, m.x.p, g.p, pg.p, L, dpx.p);
+    count_launch();
+    CELDA_CUDA_OK(cudaGetLastError());
+    CELDA_TRY(dpx.download(px, (size_t)L * ncol));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ chain
+int celda_chain_create(celda_chain** out, int device, int model, int nG, int nM, const int* p, const int* i,
+                       const double* x, const int* s, int nS, int K, int L, double alpha, double beta, double delta,
+                       double gamma) {
+    *out = nullptr;
+    if (model < 0 || model > 2) return fail("unknown model %d", model);
+    if (nG < 1 || nM < 1) return fail("counts must have at least one row and one column");
+    if (model != CELDA_MODEL_G && (K < 1 || K > nM)) return fail("'K' must be between 1 and the number of cells");
+    if (model != CELDA_MODEL_C && (L < 1 || L > nG)) return fail("'L' must be between 1 and the number of features");
+    if (K > 32767 || L > 32767) return fail("K and L must be below 32768");
+    if (model != CELDA_MODEL_G) {
+        if (!s) return fail("sample labels are required");
+        CELDA_TRY(check_labels_host(s, nM, nS, "s", "nS"));
+    }
+    const long long Z = p[nM];
+    for (int c = 0; c < nM; ++c)
+        if (p[c + 1] < p[c]) return fail("column pointers of 'counts' must be non-decreasing");
+    CELDA_CUDA_OK(cudaSetDevice(device));
+    std::unique_ptr<celda_chain> h(new celda_chain());
+    h->device = device;
+    h->model = model;
+    h->nG = nG;
+    h->nM = nM;
+    h->nS = (model == CELDA_MODEL_G) ? 1 : nS;
+    h->K = (model == CELDA_MODEL_G) ? 1 : K;
+    h->L = (model == CELDA_MODEL_C) ? 1 : L;
+    h->Z = Z;
+    h->alpha = alpha;
+    h->beta = beta;
+    h->delta = delta;
+    h->gamma = gamma;
+    h->sms = num_sms(device);
+    CELDA_CUDA_OK(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    CELDA_CUDA_OK(cudaEventCreate(&h->ev0));
+    CELDA_CUDA_OK(cudaEventCreate(&h->ev1));
+    cudaStream_t st = h->st;
+    // ---- a1: GPU-resident CSC copy, values narrowed to int32 after an integrality check
+    CELDA_TRY(h->cp.upload(p, (size_t)nM + 1, st));
+    CELDA_TRY(h->ci.upload(i, (size_t)Z, st));
+    CELDA_TRY(h->cx.alloc((size_t)Z));
+    {
+        DevBuf<double> dx;
+        DevBuf<int> flag;
+        CELDA_TRY(dx.upload(x, (size_t)Z, st));
+        CELDA_TRY(flag.alloc(1));
+        CELDA_TRY(flag.zero(st));
+        k_narrow<<<grid_for(Z, 256, h->sms), 256, 0, st>>>(dx.p, Z, h->cx.p, flag.p);
+        count_launch();
+        int f = 0;
+        CELDA_CUDA_OK(cudaMemcpyAsync(&f, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CELDA_CUDA_OK(cudaStreamSynchronize(st));
+        if (f) return fail("counts must be integer-valued and below 2^31 (found a non-integer entry)");
+    }
+    for (long long t = 0; t < Z; ++t)
+        if (i[t] < 0 || i[t] >= nG) return fail("row index out of range in 'counts'");
+    if (model != CELDA_MODEL_G) CELDA_TRY(h->s.upload(s, (size_t)nM, st));
+    CELDA_TRY(h->z.alloc(nM));
+    CELDA_TRY(h->zprev.alloc(nM));
+    CELDA_TRY(h->y.alloc(nG));
+    CELDA_TRY(h->yprev.alloc(nG));
+    CELDA_TRY(h->nByC.alloc(nM));
+    CELDA_TRY(h->nByG.alloc(nG));
+    CELDA_TRY(h->nByG.zero(st));
+    k_rowtotals_csc<<<grid_for(Z, 256, h->sms), 256, 0, st>>>(Z, h->ci.p, h->cx.p, (unsigned long long*)h->nByG.p);
+    {
+        // nByC (Matrix::colSums): reuse the row-sum kernel with a single group
+        DevBuf<int> ones, tmp;
+        CELDA_TRY(ones.alloc(nG));
+        CELDA_TRY(tmp.alloc(nM));
+        k_fill_int<<<grid_for(nG, 256, h->sms), 256, 0, st>>>(ones.p, nG, 1);
+        k_rowsum_csc<int><<<std::min((nM + 7) / 8, h->sms * 8), 256, sizeof(int) * 8, st>>>(nM, h->cp.p, h->ci.p, h->cx.p,
+                                                                                         ones.p, 1, tmp.p, h->nByC.p);
+        count_launch(3);
+        CELDA_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    if (model != CELDA_MODEL_C) {
+        CELDA_TRY(h->nTSByC.alloc((size_t)h->L * nM));
+        CELDA_TRY(h->nByTS.alloc(h->L));
+        CELDA_TRY(h->nGByTS.alloc(h->L));
+        CELDA_TRY(h->probsY.alloc((size_t)h->L * nG));
+    }
+    if (model != CELDA_MODEL_G) {
+        CELDA_TRY(h->nGByCP.alloc((size_t)nG * h->K));
+        CELDA_TRY(h->mCPByS.alloc((size_t)h->K * h->nS));
+        CELDA_TRY(h->nCP.alloc(h->K));
+        CELDA_TRY(h->probsZ.alloc((size_t)h->K * nM));
+    }
+    if (model == CELDA_MODEL_CG) CELDA_TRY(h->nTSByCP.alloc((size_t)h->L * h->K));
+    const int ncand = std::max(h->K, h->L);
+    CELDA_TRY(h->bufP.alloc((size_t)h->Wmax * ncand));
+    CELDA_TRY(h->bufA.alloc((size_t)h->Wmax * ncand));
+    CELDA_TRY(h->spec.alloc(h->Wmax));
+    CELDA_TRY(h->colsum.alloc(ncand));
+    CELDA_TRY(h->lgnCP.alloc(ncand));
+    CELDA_TRY(h->status.alloc(1));
+    CELDA_TRY(h->status.zero(st));
+    CELDA_TRY(h->barrier.alloc(1));
+    CELDA_TRY(h->stats.alloc(15));
+    CELDA_TRY(h->stats.zero(st));
+    CELDA_TRY(h->ixy.alloc(nG));
+    CELDA_TRY(h->uy.alloc(nG));
+    CELDA_TRY(h->ixz.alloc(nM));
+    CELDA_TRY(h->uz.alloc(nM));
+    CELDA_TRY(h->llPartial.alloc(1024));
+    CELDA_TRY(h->llOut.alloc(1));
+    CELDA_CUDA_OK(cudaStreamSynchronize(st));
+    CELDA_CUDA_OK(cudaGetLastError());
+    *out = h.release();
+    return 0;
+}
+
+void celda_chain_destroy(celda_chain* h) { delete h; }
+
+int celda_chain_set_state(celda_chain* h, const int* z, const int* y) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (h->model != CELDA_MODEL_G) {
+        if (!z) return fail("z labels are required");
+        for (int c = 0; c < h->nM; ++c)
+            if (z[c] < 1 || z[c] > h->K)
+                return fail("Assigned value of cell cluster greater than the total number of cell clusters!");
+        CELDA_CUDA_OK(cudaMemcpyAsync(h->z.p, z, sizeof(int) * h->nM, cudaMemcpyHostToDevice, h->st));
+    }
+    if (h->model != CELDA_MODEL_C) {
+        if (!y) return fail("y labels are required");
+        for (int g = 0; g < h->nG; ++g)
+            if (y[g] < 1 || y[g] > h->L)
+                return fail("Assigned value of feature module greater than the total number of feature modules!");
+        CELDA_CUDA_OK(cudaMemcpyAsync(h->y.p, y, sizeof(int) * h->nG, cudaMemcpyHostToDevice, h->st));
+    }
+    CELDA_TRY(chain_decompose(h));
+    CELDA_TRY(chain_sync(h));
+    h->has_state = true;
+    return 0;
+}
+
+int celda_chain_get_state(celda_chain* h, int* z, int* y) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (z && h->model != CELDA_MODEL_G) CELDA_TRY(h->z.download(z, h->nM, h->st));
+    if (y && h->model != CELDA_MODEL_C) CELDA_TRY(h->y.download(y, h->nG, h->st));
+    return chain_sync(h);
+}
+
+int celda_chain_sweep_y(celda_chain* h, const int* ix, const double* u, int doSample) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (!h->has_state) return fail("set_state must be called first");
+    CELDA_TRY(validate_order(ix, h->nG, "ix"));
+    CELDA_CUDA_OK(cudaMemcpyAsync(h->ixy.p, ix, sizeof(int) * h->nG, cudaMemcpyHostToDevice, h->st));
+    CELDA_CUDA_OK(cudaMemcpyAsync(h->uy.p, u, sizeof(double) * h->nG, cudaMemcpyHostToDevice, h->st));
+    CELDA_TRY(chain_step_y(h, h->ixy.p, h->uy.p, doSample));
+    return chain_check_status(h);
+}
+
+int celda_chain_sweep_z_gibbs(celda_chain* h, const int* ix, const double* u, int doSample) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (!h->has_state) return fail("set_state must be called first");
+    CELDA_TRY(validate_order(ix, h->nM, "ix"));
+    CELDA_CUDA_OK(cudaMemcpyAsync(h->ixz.p, ix, sizeof(int) * h->nM, cudaMemcpyHostToDevice, h->st));
+    CELDA_CUDA_OK(cudaMemcpyAsync(h->uz.p, u, sizeof(double) * h->nM, cudaMemcpyHostToDevice, h->st));
+    CELDA_TRY(chain_step_z(h, h->ixz.p, h->uz.p, doSample));
+    return chain_check_status(h);
+}
+
+int celda_chain_loglik(celda_chain* h, double* ll) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (!h->has_state) return fail("set_state must be called first");
+    if (h->model == CELDA_MODEL_C) return fail("loglik: celda_C chain not implemented yet");
+    CELDA_TRY(chain_loglik_async(h));
+    CELDA_CUDA_OK(cudaMemcpyAsync(ll, h->llOut.p, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    return chain_sync(h);
+}
+
+int celda_chain_iterate(celda_chain* h, const int* ix_y, const double* u_y, const int* ix_z, const double* u_z,
+                        double* ll) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (!h->has_state) return fail("set_state must be called first");
+    if (!ix_y || !u_y || !ix_z || !u_z) return fail("iterate: injected order and uniforms are required");
+    CELDA_TRY(validate_order(ix_y, h->nG, "ix_y"));
+    CELDA_TRY(validate_order(ix_z, h->nM, "ix_z"));
+    cudaStream_t st = h->st;
+    CELDA_CUDA_OK(cudaMemcpyAsync(h->ixy.p, ix_y, sizeof(int) * h->nG, cudaMemcpyHostToDevice, st));
+    CELDA_CUDA_OK(cudaMemcpyAsync(h->uy.p, u_y, sizeof(double) * h->nG, cudaMemcpyHostToDevice, st));
+    CELDA_CUDA_OK(cudaMemcpyAsync(h->ixz.p, ix_z, sizeof(int) * h->nM, cudaMemcpyHostToDevice, st));
+    CELDA_CUDA_OK(cudaMemcpyAsync(h->uz.p, u_z, sizeof(double) * h->nM, cudaMemcpyHostToDevice, st));
+    CELDA_TRY(chain_step_y(h, h->ixy.p, h->uy.p, 1));
+    CELDA_TRY(chain_step_z(h, h->ixz.p, h->uz.p, 1));
+    CELDA_TRY(chain_loglik_async(h));
+    CELDA_CUDA_OK(cudaMemcpyAsync(ll, h->llOut.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    return chain_check_status(h);
+}
+
+int celda_chain_stage_draws(celda_chain* h, int n_iter, const int* ix_y, const double* u_y, const int* ix_z,
+                            const double* u_z) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    for (int it = 0; it < n_iter; ++it) {
+        CELDA_TRY(validate_order(ix_y + (size_t)it * h->nG, h->nG, "ix_y"));
+        CELDA_TRY(validate_order(ix_z + (size_t)it * h->nM, h->nM, "ix_z"));
+    }
+    CELDA_TRY(h->st_ixy.upload(ix_y, (size_t)n_iter * h->nG, h->st));
+    CELDA_TRY(h->st_uy.upload(u_y, (size_t)n_iter * h->nG, h->st));
+    CELDA_TRY(h->st_ixz.upload(ix_z, (size_t)n_iter * h->nM, h->st));
+    CELDA_TRY(h->st_uz.upload(u_z, (size_t)n_iter * h->nM, h->st));
+    h->staged_iters = n_iter;
+    return chain_sync(h);
+}
+
+int celda_chain_iterate_staged(celda_chain* h, int iter, double* ll) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (!h->has_state) return fail("set_state must be called first");
+    if (iter < 0 || iter >= h->staged_iters) return fail("iterate_staged: iteration %d was not staged", iter);
+    CELDA_TRY(chain_step_y(h, h->st_ixy.p + (size_t)iter * h->nG, h->st_uy.p + (size_t)iter * h->nG, 1));
+    CELDA_TRY(chain_step_z(h, h->st_ixz.p + (size_t)iter * h->nM, h->st_uz.p + (size_t)iter * h->nM, 1));
+    CELDA_TRY(chain_loglik_async(h));
+    CELDA_CUDA_OK(cudaMemcpyAsync(ll, h->llOut.p, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    return chain_check_status(h);
+}
+
+int celda_chain_get_tables(celda_chain* h, int* mCPByS, double* nTSByC, double* nTSByCP, double* nGByCP, double* nCP,
+                           double* nByC, double* nByG, double* nByTS, int* nGByTS) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    cudaStream_t st = h->st;
+    const int sms = h->sms;
+    DevBuf<double> tmp;
+    auto out_d = [&](auto* src, long long n, double* dst) -> int {
+        CELDA_TRY(tmp.alloc((size_t)n));
+        using T = std::remove_pointer_t<decltype(src)>;
+        k_convert<T, double><<<grid_for(n, 256, sms), 256, 0, st>>>(src, n, tmp.p);
+        count_launch();
+        CELDA_TRY(tmp.download(dst, (size_t)n, st));
+        CELDA_CUDA_OK(cudaStreamSynchronize(st));
+        return 0;
+    };
+    if (mCPByS && h->model != CELDA_MODEL_G) CELDA_TRY(h->mCPByS.download(mCPByS, (size_t)h->K * h->nS, st));
+    if (nTSByC && h->model != CELDA_MODEL_C) CELDA_TRY(out_d(h->nTSByC.p, (long long)h->L * h->nM, nTSByC));
+    if (nTSByCP && h->model == CELDA_MODEL_CG) CELDA_TRY(out_d(h->nTSByCP.p, (long long)h->L * h->K, nTSByCP));
+    if (nGByCP && h->model != CELDA_MODEL_G) {
+        const long long n = (long long)h->nG * h->K;
+        CELDA_TRY(tmp.alloc((size_t)n));
+        k_transpose_convert<int, double><<<grid_for(n, 256, sms), 256, 0, st>>>(h->nGByCP.p, h->nG, h->K, tmp.p, true);
+        count_launch();
+        CELDA_TRY(tmp.download(nGByCP, (size_t)n, st));
+        CELDA_CUDA_OK(cudaStreamSynchronize(st));
+    }
+    if (nCP && h->model != CELDA_MODEL_G) CELDA_TRY(out_d(h->nCP.p, h->K, nCP));
+    if (nByC) CELDA_TRY(out_d(h->nByC.p, h->nM, nByC));
+    if (nByG) CELDA_TRY(out_d(h->nByG.p, h->nG, nByG));
+    if (nByTS && h->model != CELDA_MODEL_C) CELDA_TRY(out_d(h->nByTS.p, h->L, nByTS));
+    if (nGByTS && h->model != CELDA_MODEL_C) CELDA_TRY(h->nGByTS.download(nGByTS, h->L, st));
+    CELDA_CUDA_OK(cudaGetLastError());
+    return chain_sync(h);
+}
+
+int celda_chain_get_probs(celda_chain* h, double* probsZ, double* probsY) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (probsZ && h->model != CELDA_MODEL_G) CELDA_TRY(h->probsZ.download(probsZ, (size_t)h->K * h->nM, h->st));
+    if (probsY && h->model != CELDA_MODEL_C) CELDA_TRY(h->probsY.download(probsY, (size_t)h->L * h->nG, h->st));
+    return chain_sync(h);
+}
+
+int celda_chain_timer_start(celda_chain* h) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    CELDA_CUDA_OK(cudaEventRecord(h->ev0, h->st));
+    return 0;
+}
+
+int celda_chain_timer_stop(celda_chain* h, float* ms) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    CELDA_CUDA_OK(cudaEventRecord(h->ev1, h->st));
+    CELDA_CUDA_OK(cudaEventSynchronize(h->ev1));
+    CELDA_CUDA_OK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+    return 0;
+}
+
+int celda_chain_profile(celda_chain* h, int enable) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    CELDA_TRY(chain_sync(h));
+    h->profile = enable != 0;
+    for (int q = 0; q < 5; ++q) {
+        h->prof_ms[q] = 0;
+        h->prof_launches[q] = 0;
+    }
+    CELDA_TRY(h->stats.zero(h->st));
+    return chain_sync(h);
+}
+
+int celda_chain_profile_get(celda_chain* h, int which, double* ms, long long* launches, long long* rounds) {
+    if (which < 0 || which > 4) return fail("profile_get: which must be 0..4");
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    CELDA_TRY(chain_sync(h));
+    long long stats[3] = {0, 0, 0};
+    CELDA_CUDA_OK(cudaMemcpy(stats, h->stats.p + 3 * which, sizeof(stats), cudaMemcpyDeviceToHost));
+    if (ms) *ms = h->prof_ms[which];
+    if (launches) *launches = h->prof_launches[which];
+    if (rounds) {
+        rounds[0] = stats[0];
+        rounds[1] = stats[1];
+        rounds[2] = stats[2];
+    }
+    return 0;
+}
+
+}  // extern "C"

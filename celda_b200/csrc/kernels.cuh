@@ -1,0 +1,361 @@
+// Aggregation, contingency-table, log-likelihood and element-wise kernels (sm_100a).
+// All count data on the device is int32 (values) / int64 (totals); sums of integer-valued doubles in the
+// reference (src/matrixSumsSparse.cpp, src/matrixSums.c) are exact, so integer arithmetic reproduces them bit
+// for bit and is order-independent (atomics are safe).
+#pragma once
+#include "celda_math.cuh"
+
+namespace celda {
+
+// ---------------------------------------------------------------------------------------------- element-wise
+template <int OP>
+__global__ void k_math_vec(const double* __restrict__ x, long long n, double* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        out[i] = OP == 0 ? dlgamma(v) : (OP == 1 ? dlog(v) : dexp(v));
+    }
+}
+
+// double -> int32 with an integrality / range check (flag[0] |= 1 when a value is not an int32 integer)
+__global__ void k_narrow(const double* __restrict__ x, long long n, int* __restrict__ out, int* flag) {
+    int bad = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        const int iv = (int)v;
+        bad |= !((double)iv == v);
+        out[i] = iv;
+    }
+    if (bad) atomicOr(flag, 1);
+}
+
+template <typename TI, typename TO>
+__global__ void k_convert(const TI* __restrict__ x, long long n, TO* __restrict__ out) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = (TO)x[i];
+}
+
+// out[r + c*nr] = in[c + r*nc]  (gene-major [nr][nc] <-> column-major nr x nc)
+template <typename TI, typename TO>
+__global__ void k_transpose_convert(const TI* __restrict__ in, int nr, int nc, TO* __restrict__ out, bool in_is_rowmajor) {
+    const long long n = (long long)nr * nc;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(q % nr), c = (int)(q / nr);  // q indexes the column-major side
+        if (in_is_rowmajor) out[q] = (TO)in[(size_t)r * nc + c];
+        else out[(size_t)r * nc + c] = (TO)in[q];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- CSC aggregation
+// rowSumByGroup (src/matrixSumsSparse.cpp:44-73): out[L x nc] column-major; one warp per column, per-warp shared
+// accumulator so every HBM byte of (i, x) is read once, coalesced, and the output is written once.
+template <typename T>
+__global__ void k_rowsum_csc(int nc, const int* __restrict__ p, const int* __restrict__ ri, const T* __restrict__ xv,
+                             const int* __restrict__ group, int L, T* __restrict__ out, T* __restrict__ nByC) {
+    extern __shared__ __align__(8) unsigned char acc_raw[];
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    T* acc = reinterpret_cast<T*>(acc_raw) + warp * L;
+    for (int c = blockIdx.x * nwarp + warp; c < nc; c += gridDim.x * nwarp) {
+        for (int l = lane; l < L; l += 32) acc[l] = 0;
+        __syncwarp();
+        T tot = 0;
+        const int e = p[c + 1];
+        for (int t = p[c] + lane; t < e; t += 32) {
+            const T v = xv[t];
+            atomicAdd(&acc[group[ri[t]] - 1], v);
+            tot += v;
+        }
+        __syncwarp();
+        for (int l = lane; l < L; l += 32) out[(size_t)c * L + l] = acc[l];
+        if (nByC) {  // integer instantiation only (order of a shuffle tree is irrelevant for integers)
+            for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            if (lane == 0) nByC[c] = tot;
+        }
+        __syncwarp();
+    }
+}
+
+// colSumByGroup (src/matrixSumsSparse.cpp:9-38): out gene-major [nr][K] (pre-zeroed), integer atomics into L2.
+template <typename T>
+__global__ void k_colsum_csc(int nc, const int* __restrict__ p, const int* __restrict__ ri, const T* __restrict__ xv,
+                             const int* __restrict__ group, int K, T* __restrict__ out) {
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = blockIdx.x * nwarp + warp; c < nc; c += gridDim.x * nwarp) {
+        const int g = group[c] - 1, e = p[c + 1];
+        for (int t = p[c] + lane; t < e; t += 32) atomicAdd(&out[(size_t)ri[t] * K + g], xv[t]);
+    }
+}
+
+// colSumByGroupChange (src/matrixSumsSparse.cpp:85-131): only columns whose label changed are walked.
+template <typename T>
+__global__ void k_colsum_change_csc(int nc, const int* __restrict__ p, const int* __restrict__ ri,
+                                    const T* __restrict__ xv, const int* __restrict__ group,
+                                    const int* __restrict__ pgroup, int K, T* __restrict__ out) {
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = blockIdx.x * nwarp + warp; c < nc; c += gridDim.x * nwarp) {
+        const int g = group[c] - 1, pg = pgroup[c] - 1;
+        if (g == pg) continue;
+        const int e = p[c + 1];
+        for (int t = p[c] + lane; t < e; t += 32) {
+            const T v = xv[t];
+            atomicAdd(&out[(size_t)ri[t] * K + g], v);
+            atomicAdd(&out[(size_t)ri[t] * K + pg], -v);
+        }
+    }
+}
+
+// rowSumByGroupChange (src/matrixSumsSparse.cpp:141-187): like the reference, every stored entry is inspected
+// (the row index stream is read once, coalesced; values only for rows whose label changed).  px: L x nc.
+template <typename T>
+__global__ void k_rowsum_change_csc(int nc, const int* __restrict__ p, const int* __restrict__ ri,
+                                    const T* __restrict__ xv, const int* __restrict__ group,
+                                    const int* __restrict__ pgroup, int L, T* __restrict__ px) {
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = blockIdx.x * nwarp + warp; c < nc; c += gridDim.x * nwarp) {
+        const int e = p[c + 1];
+        for (int t = p[c] + lane; t < e; t += 32) {
+            const int r = ri[t];
+            const int g = group[r], pg = pgroup[r];
+            if (g != pg) {
+                const T v = xv[t];
+                atomicAdd(&px[(size_t)c * L + g - 1], v);
+                atomicAdd(&px[(size_t)c * L + pg - 1], -v);
+            }
+        }
+    }
+}
+
+// per-row totals of a CSC matrix (Matrix::rowSums, R/celda_CG.R:913): int64 atomics
+__global__ void k_rowtotals_csc(long long nnz, const int* __restrict__ ri, const int* __restrict__ xv,
+                                unsigned long long* __restrict__ nByG) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nnz; t += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&nByG[ri[t]], (unsigned long long)(long long)xv[t]);
+}
+
+// ---------------------------------------------------------------------------------------------- dense aggregation
+// colSumByGroup on a dense int32 R x nc column-major matrix (nTSByC -> nTSByCP, R/celda_CG.R:910): out R x K.
+__global__ void k_colsum_dense(const int* __restrict__ x, int R, long long nc, const int* __restrict__ group, int K,
+                               int* __restrict__ out) {
+    extern __shared__ int acc[];  // R x K
+    for (int q = threadIdx.x; q < R * K; q += blockDim.x) acc[q] = 0;
+    __syncthreads();
+    const long long per = (nc + gridDim.x - 1) / gridDim.x;
+    const long long c0 = blockIdx.x * per, c1 = min(nc, c0 + per);
+    const long long n = (c1 > c0) ? (c1 - c0) * R : 0;
+    for (long long q = threadIdx.x; q < n; q += blockDim.x) {
+        const long long c = c0 + q / R;
+        const int r = (int)(q % R);
+        const int v = x[c * R + r];
+        if (v) atomicAdd(&acc[(group[c] - 1) * R + r], v);
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < R * K; q += blockDim.x)
+        if (acc[q]) atomicAdd(&out[q], acc[q]);
+}
+
+// colSumByGroupChange on the same dense layout, in place on out (R x K)
+__global__ void k_colsum_change_dense(const int* __restrict__ x, int R, long long nc, const int* __restrict__ group,
+                                      const int* __restrict__ pgroup, int* __restrict__ out) {
+    const long long n = nc * R;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const long long c = q / R;
+        const int g = group[c], pg = pgroup[c];
+        if (g == pg) continue;
+        const int r = (int)(q % R);
+        const int v = x[q];
+        if (v) {
+            atomicAdd(&out[(size_t)(g - 1) * R + r], v);
+            atomicSub(&out[(size_t)(pg - 1) * R + r], v);
+        }
+    }
+}
+
+// table(factor(z, 1:K), s) (R/celda_CG.R:904): K x nS
+__global__ void k_table_zs(const int* __restrict__ z, const int* __restrict__ s, long long n, int K, int* __restrict__ m) {
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n; c += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&m[(size_t)(s[c] - 1) * K + z[c] - 1], 1);
+}
+
+// nByTS = rowSumByGroup(nByG, y), nGByTS = tabulate(y, L) + 1  (R/celda_CG.R:914-916); nGByTS pre-set to 1
+__global__ void k_module_totals(const int* __restrict__ y, const long long* __restrict__ nByG, int nG,
+                                unsigned long long* __restrict__ nByTS, int* __restrict__ nGByTS) {
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < nG; g += gridDim.x * blockDim.x) {
+        atomicAdd(&nByTS[y[g] - 1], (unsigned long long)nByG[g]);
+        atomicAdd(&nGByTS[y[g] - 1], 1);
+    }
+}
+
+__global__ void k_fill_int(int* p, long long n, int v) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// nCP = colSums(table) for an int32 R x K column-major table (one thread per column; K is small)
+__global__ void k_colsums_small(const int* __restrict__ t, int R, int K, long long* __restrict__ out) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+        long long s = 0;
+        for (int r = 0; r < R; ++r) s += t[(size_t)k * R + r];
+        out[k] = s;
+    }
+}
+
+// column totals of a gene-major [nG][K] table (nCP for celda_C)
+__global__ void k_colsums_genemajor(const int* __restrict__ t, int nG, int K, unsigned long long* __restrict__ out) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < (long long)nG * K;
+         q += (long long)gridDim.x * blockDim.x)
+        if (t[q]) atomicAdd(&out[q % K], (unsigned long long)(long long)t[q]);
+}
+
+// ---------------------------------------------------------------------------------------------- label checks
+// flag bit 0: label outside [1, K]
+__global__ void k_check_labels(const int* __restrict__ g, long long n, int K, int* flag) {
+    int bad = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        bad |= (g[i] < 1 || g[i] > K);
+    if (bad) atomicOr(flag, 1);
+}
+
+// ---------------------------------------------------------------------------------------------- log-likelihood
+// Deterministic block reduction (fixed tree), result on thread 0.
+__device__ double block_sum(double v, double* red) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < nw; ++w) s += red[w];
+    return s;
+}
+
+// Partial sums of lgamma(x + add) over an integer array, one partial per block (grid fixed => deterministic).
+template <typename T>
+__global__ void k_sum_lgamma(const T* __restrict__ x, long long n, double add, double* __restrict__ partial) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        acc += dlgamma((double)x[i] + add);
+    const double s = block_sum(acc, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// Partial sums of lgamma(colSum(x[, c] + add)) for an int32 R x nc column-major matrix (one thread per column,
+// the column is added serially like R's colSums of (x + add)).
+__global__ void k_sum_lgamma_colsums(const int* __restrict__ x, int R, long long nc, double add,
+                                     double* __restrict__ partial) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < nc; c += (long long)gridDim.x * blockDim.x) {
+        double cs = 0.0;
+        for (int r = 0; r < R; ++r) cs += (double)x[c * R + r] + add;
+        acc += dlgamma(cs);
+    }
+    const double s = block_sum(acc, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+struct LLArgs {
+    int model;  // 0 CG, 1 C, 2 G
+    int K, L, nS, nG;
+    long long nM;
+    const int* mCPByS;        // K x nS
+    const int* phiTab;        // CG: nTSByCP (L x K); C/G: unused (partials)
+    const long long* nByTS;   // L
+    const int* nGByTS;        // L
+    const double* partial;    // [0..np): sum lgamma(nByG + delta); then model-specific partial blocks
+    int npG, npPhiB, npPhiD;  // partial counts: genes, phi numerator, phi denominator (C and G models)
+    double alpha, beta, delta, gamma;
+    double* out;
+};
+
+// Final assembly in the reference's order: a + b + c + d per component, then theta + phi + psi + eta
+// (R/celda_CG.R:854-887, R/celda_C.R:771-787, R/celda_G.R:677-701).  One block.
+__global__ void k_loglik_final(LLArgs a) {
+    __shared__ double red[32];
+    __shared__ double comp[4];
+    const int K = a.K, L = a.L, nS = a.nS;
+    const double* part = a.partial;
+    // ---- theta (CG, C)
+    if (a.model != 2) {
+        double acc = 0.0;
+        for (int q = threadIdx.x; q < K * nS; q += blockDim.x) acc += dlgamma((double)a.mCPByS[q] + a.alpha);
+        const double b = block_sum(acc, red);
+        acc = 0.0;
+        for (int s = threadIdx.x; s < nS; s += blockDim.x) {
+            double cs = 0.0;
+            for (int k = 0; k < K; ++k) cs += (double)a.mCPByS[(size_t)s * K + k] + a.alpha;
+            acc += dlgamma(cs);
+        }
+        const double d = block_sum(acc, red);
+        if (threadIdx.x == 0) {
+            const double aa = (double)nS * dlgamma((double)K * a.alpha);
+            const double c = (double)(-nS * K) * dlgamma(a.alpha);
+            comp[0] = aa + b + c + -d;
+        }
+    }
+    // ---- phi
+    {
+        double b = 0.0, d = 0.0;
+        int R;
+        long long ncols;
+        if (a.model == 0) {
+            R = L;
+            ncols = K;
+            double acc = 0.0;
+            for (int q = threadIdx.x; q < L * K; q += blockDim.x) acc += dlgamma((double)a.phiTab[q] + a.beta);
+            b = block_sum(acc, red);
+            acc = 0.0;
+            for (int k = threadIdx.x; k < K; k += blockDim.x) {
+                double cs = 0.0;
+                for (int l = 0; l < L; ++l) cs += (double)a.phiTab[(size_t)k * L + l] + a.beta;
+                acc += dlgamma(cs);
+            }
+            d = block_sum(acc, red);
+        } else {
+            R = (a.model == 1) ? a.nG : L;
+            ncols = (a.model == 1) ? K : a.nM;
+            if (threadIdx.x == 0) {
+                for (int q = 0; q < a.npPhiB; ++q) b += part[a.npG + q];
+                for (int q = 0; q < a.npPhiD; ++q) d += part[a.npG + a.npPhiB + q];
+            }
+        }
+        if (threadIdx.x == 0) {
+            const double aa = (double)ncols * dlgamma((double)R * a.beta);
+            const double c = -(double)ncols * (double)R * dlgamma(a.beta);
+            comp[1] = aa + b + c + -d;
+        }
+    }
+    // ---- psi, eta (CG, G)
+    if (a.model != 1) {
+        double acc = 0.0, acc2 = 0.0, acc3 = 0.0;
+        for (int l = threadIdx.x; l < L; l += blockDim.x) {
+            const double g = (double)a.nGByTS[l];
+            acc += dlgamma(g * a.delta);
+            acc2 += dlgamma((double)a.nByTS[l] + (g * a.delta));
+            acc3 += dlgamma(g + a.gamma);
+        }
+        const double pa = block_sum(acc, red);
+        const double pd = block_sum(acc2, red);
+        const double eb = block_sum(acc3, red);
+        if (threadIdx.x == 0) {
+            double pb = 0.0;
+            for (int q = 0; q < a.npG; ++q) pb += part[q];
+            double nGs = 0.0, es = 0.0;
+            for (int l = 0; l < L; ++l) {
+                nGs += (double)a.nGByTS[l];
+                es += (double)a.nGByTS[l] + a.gamma;
+            }
+            const double pc = -nGs * dlgamma(a.delta);
+            comp[2] = pa + pb + pc + -pd;
+            const double ea = dlgamma((double)L * a.gamma);
+            const double ec = (double)(-L) * dlgamma(a.gamma);
+            comp[3] = ea + eb + ec + -dlgamma(es);
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (a.model == 0) *a.out = comp[0] + comp[1] + comp[2] + comp[3];
+        else if (a.model == 1) *a.out = comp[0] + comp[1];
+        else *a.out = comp[1] + comp[2] + comp[3];
+    }
+}
+
+}  // namespace celda

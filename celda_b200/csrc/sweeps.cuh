@@ -1,0 +1,657 @@
+// Sequential Gibbs sweeps as persistent cooperative kernels (sm_100a).
+//
+// The reference visits cells (R/celda_C.R:637-705) or genes (R/celda_G.R:620-651) strictly in order; step i
+// reads the count tables step i-1 may have changed.  Two facts make an exact parallel schedule possible:
+//   (1) the log-probability of candidate j for an item depends only on column j of the table (plus the
+//       per-candidate scalars), and on whether j is the item's current label;
+//   (2) an item that does not move changes nothing.
+// So a window of upcoming items is evaluated speculatively by the whole grid against the current tables, the
+// first item (in visiting order) whose draw differs from its label is committed, and for the items behind it
+// only the two candidates the move touched are re-evaluated ("patch units") before they are drawn again.
+// Every floating-point value is produced by the same operations in the same order as a sequential sweep, so
+// labels, tables and probabilities are bit-identical to it.
+//
+// Work decomposition: one warp per (item, candidate) "unit": lanes evaluate the lgamma terms in parallel into
+// shared memory, lane 0 adds them in the reference's serial order.  One warp per item draws.
+#pragma once
+#include "celda_math.cuh"
+
+namespace celda {
+
+// ------------------------------------------------------------------------------------------------ helpers
+__device__ __forceinline__ void grid_sync(unsigned* counter, unsigned& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*((volatile unsigned*)counter) < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+
+// R sort.c revsort semantics (descending heapsort carrying the index permutation; not stable), 1 thread.
+__device__ __noinline__ void revsort_serial(double* a, int* ib, int n) {
+    if (n <= 1) return;
+    a--;
+    ib--;
+    int l = (n >> 1) + 1, ir = n, i, j, ii;
+    double ra;
+    for (;;) {
+        if (l > 1) {
+            l = l - 1;
+            ra = a[l];
+            ii = ib[l];
+        } else {
+            ra = a[ir];
+            ii = ib[ir];
+            a[ir] = a[1];
+            ib[ir] = ib[1];
+            if (--ir == 1) {
+                a[1] = ra;
+                ib[1] = ii;
+                return;
+            }
+        }
+        i = l;
+        j = l << 1;
+        while (j <= ir) {
+            if (j < ir && a[j] > a[j + 1]) ++j;
+            if (ra > a[j]) {
+                a[i] = a[j];
+                ib[i] = ib[j];
+                j += (i = j);
+            } else
+                j = ir + 1;
+        }
+        a[i] = ra;
+        ib[i] = ii;
+    }
+}
+
+// Ordered (ascending index) sum of the positive entries of r[0..n), identical on every lane.
+// Adding +0.0 to a non-negative partial sum is the identity, so skipping zeros is exact.
+__device__ __forceinline__ double warp_ordered_sum_pos(const double* r, int n, int lane) {
+    double s = 0.0;
+    for (int base = 0; base < n; base += 32) {
+        const double v = (base + lane < n) ? r[base + lane] : 0.0;
+        unsigned m = __ballot_sync(0xffffffffu, v > 0.0);
+        while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1;
+            s += shfl_d(v, b);
+        }
+    }
+    return s;
+}
+
+// .sampleLl (R/celda_functions.R:1-11) + sample.int(n, 1, TRUE, prob) with the uniform supplied.
+// pl: n log-probabilities in shared memory.  r, hs: n doubles of warp scratch; perm: n ints.
+// Returns the 0-based label, or <0: -1 Walker-alias branch (>200 likely categories), -2 non-finite
+// probability, -3 no positive probability.  Warp-cooperative; all lanes return the same value.
+__device__ int warp_sample_ll(const double* pl, int n, double u, double* r, double* hs, int* perm, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    double mx = -__longlong_as_double(0x7ff0000000000000LL);
+    for (int i = lane; i < n; i += 32) mx = fmax(mx, pl[i]);
+    for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
+    int bad = 0;
+    for (int i = lane; i < n; i += 32) {
+        const double e = dexp(pl[i] - mx);
+        r[i] = e;
+        bad |= !(e >= 0.0) || (e > 1.7976931348623157e308);
+    }
+    __syncwarp();
+    if (__any_sync(FULL, bad)) return -2;
+    const double s1 = warp_ordered_sum_pos(r, n, lane);
+    for (int i = lane; i < n; i += 32) r[i] = r[i] / s1;
+    __syncwarp();
+    const double s2 = warp_ordered_sum_pos(r, n, lane);  // FixupProb: plain-double sum of the positive entries
+    if (!(s2 > 0.0)) return -3;
+    int nc = 0, nzero = 0;
+    for (int i = lane; i < n; i += 32) {
+        const double q = r[i] / s2;
+        r[i] = q;
+        hs[i] = q;
+        nc += ((double)n * q > 0.1);
+        nzero += (q == 0.0);
+    }
+    for (int o = 16; o; o >>= 1) {
+        nc += __shfl_xor_sync(FULL, nc, o);
+        nzero += __shfl_xor_sync(FULL, nzero, o);
+    }
+    __syncwarp();
+    if (nc > 200) return -1;
+    if (n == 1) return 0;
+    // Scan the values in descending order (the order revsort produces is unique up to ties).
+    double cum = 0.0;
+    int result = -1;
+    bool slow = false;
+    for (int k = 0; k < n; ++k) {
+        double bv = -1.0;
+        int bi = 0x7fffffff;
+        for (int i = lane; i < n; i += 32) {
+            const double v = hs[i];
+            if (v > bv) {
+                bv = v;
+                bi = i;
+            }
+        }
+        for (int o = 16; o; o >>= 1) {
+            const double ov = __shfl_xor_sync(FULL, bv, o);
+            const int oi = __shfl_xor_sync(FULL, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) {
+                bv = ov;
+                bi = oi;
+            }
+        }
+        const int rem = n - k;
+        bool select;
+        if (bv == 0.0) {
+            // only zero-probability entries remain: the cumulative sum no longer moves, so no earlier position
+            // can satisfy u <= cum and R falls through to the last sorted position.
+            if (nzero == 1) {
+                result = bi;
+            } else
+                slow = true;
+            break;
+        }
+        cum = (k == 0) ? bv : bv + cum;
+        select = (rem == 1) || (u <= cum);
+        if (select) {
+            int mult = 0;
+            for (int i = lane; i < n; i += 32) mult += (r[i] == bv);
+            for (int o = 16; o; o >>= 1) mult += __shfl_xor_sync(FULL, mult, o);
+            if (mult == 1)
+                result = bi;
+            else
+                slow = true;  // the label inside a group of exactly equal probabilities depends on heapsort order
+            break;
+        }
+        if (lane == 0) hs[bi] = -1.0;
+        __syncwarp();
+    }
+    if (!slow) return result;
+    // Exact emulation of ProbSampleReplace on one lane (rare: exact ties, or u beyond the total mass).
+    __syncwarp();
+    if (lane == 0) {
+        for (int i = 0; i < n; ++i) {
+            hs[i] = r[i];
+            perm[i] = i;
+        }
+        revsort_serial(hs, perm, n);
+        for (int i = 1; i < n; ++i) hs[i] += hs[i - 1];
+        int j;
+        for (j = 0; j < n - 1; ++j)
+            if (u <= hs[j]) break;
+        result = perm[j];
+    }
+    result = __shfl_sync(FULL, result, 0);
+    __syncwarp();
+    return result;
+}
+
+// Block-wide: smallest index c in [0, nwin) with spec[c] >= 0, or -1.  Result valid on all threads.
+__device__ int block_first_mover(const int* spec, int nwin, int* s_first) {
+    if (threadIdx.x == 0) *s_first = 0x7fffffff;
+    __syncthreads();
+    int best = 0x7fffffff;
+    for (int c = threadIdx.x; c < nwin; c += blockDim.x) {
+        if (__ldcg(spec + c) >= 0) {
+            best = c;
+            break;  // ascending per thread
+        }
+    }
+    for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best != 0x7fffffff) atomicMin(s_first, best);
+    __syncthreads();
+    const int f = *s_first;
+    __syncthreads();
+    return f == 0x7fffffff ? -1 : f;
+}
+
+struct SweepWork {
+    double* bufP;       // [Wmax * ncand] per-(item, candidate) partial results
+    double* bufA;       // [Wmax * ncand] second per-candidate scalar (z sweep only)
+    int* spec;          // [Wmax] packed (old << 16 | new) for movers, -1 otherwise
+    double* colsum;     // [K]  (z sweep)
+    double* lgnCP;      // [K]  (z sweep)
+    unsigned* barrier;  // zeroed before launch
+    int* status;        // 0 ok, else sampler error code
+    long long* stats;   // [0] rounds, [1] units, [2] movers
+    int Wmax;           // ring capacity (items)
+    int Wmin;
+    int lgT;            // entries of the shared-memory lgamma(k + beta) table
+};
+
+// ------------------------------------------------------------------------------------------------ z sweep
+// .cCCalcGibbsProbZ (R/celda_C.R:620-714) on a dense R x nM int32 count matrix (nTSByC in celda_CG).
+struct ZArgs {
+    int R, K, nS;
+    long long nM;
+    const int* counts;  // R x nM column-major
+    const int* nByC;    // [nM]
+    const int* s;       // [nM] 1-based
+    int* z;             // [nM] 1-based, updated
+    int* nTab;          // R x K column-major (nGByCP argument), updated
+    long long* nCP;     // [K], updated
+    int* mCPByS;        // K x nS, updated
+    double alpha, beta;
+    const int* ix;      // visiting order, 1-based
+    const double* u;    // one uniform per visited item
+    int doSample;
+    double* probs;      // K x nM or null
+    SweepWork w;
+};
+
+__device__ __forceinline__ double lg_tab(const double* lgtab, int T, long long k, double beta) {
+    return (k < T) ? lgtab[k] : dlgamma((double)k + beta);
+}
+
+__global__ void __launch_bounds__(512, 1) k_sweep_z(ZArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int R = a.R, K = a.K, nS = a.nS, T = a.w.lgT;
+    const int Rp = R | 1;  // odd stride: candidate-major rows, conflict-free across lanes of r
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int scratchD = max(R, 3 * K + (K + 1) / 2) + 2;
+    double* lgtab = reinterpret_cast<double*>(smem_raw);
+    double* scratch_all = lgtab + T;
+    long long* nCP_s = reinterpret_cast<long long*>(scratch_all + (size_t)nwarp * scratchD);
+    int* n_s = reinterpret_cast<int*>(nCP_s + K);
+    int* m_s = n_s + (size_t)K * Rp;
+    int* s_misc = m_s + K * nS;  // [0] first mover
+    double* scr = scratch_all + (size_t)warp * scratchD;
+
+    const double Rbeta = (double)R * a.beta;
+    const int gwarp = blockIdx.x * nwarp + warp, tw = gridDim.x * nwarp;
+
+    for (int q = threadIdx.x; q < R * K; q += blockDim.x) n_s[(q / R) * Rp + (q % R)] = a.nTab[q];
+    for (int q = threadIdx.x; q < K; q += blockDim.x) nCP_s[q] = a.nCP[q];
+    for (int q = threadIdx.x; q < K * nS; q += blockDim.x) m_s[q] = a.mCPByS[q];
+    for (int q = threadIdx.x; q < T; q += blockDim.x) lgtab[q] = dlgamma((double)q + a.beta);
+    __syncthreads();
+
+    long long pos = 0, hi = 0;
+    int W = a.w.Wmax, nd = K, da = -1, db = -1;  // nd == K: every column's cached sum is still to be computed
+    bool have_spec = false;
+    long long prev_end = 0;
+    unsigned bar_target = 0;
+    long long rounds = 0, units_done = 0, movers = 0;
+
+    while (true) {
+        // ---- commit the first mover of the previous window (every CTA updates its own copy of the tables)
+        if (have_spec) {
+            const int nwin = (int)(prev_end - pos);
+            const int first = block_first_mover(a.w.spec, nwin, s_misc);
+            if (first < 0) {
+                pos = prev_end;
+                hi = pos;
+                nd = 0;
+                W = min(2 * W, a.w.Wmax);
+            } else {
+                const long long t = pos + first;
+                const long long i = a.ix[t] - 1;
+                const int packed = __ldcg(a.w.spec + first);
+                da = packed >> 16;
+                db = packed & 0xffff;
+                const int* x = a.counts + i * R;
+                for (int r = threadIdx.x; r < R; r += blockDim.x) {
+                    const int xv = x[r];
+                    n_s[da * Rp + r] -= xv;
+                    n_s[db * Rp + r] += xv;
+                }
+                if (threadIdx.x == 0) {
+                    const int Ni = a.nByC[i], si = a.s[i] - 1;
+                    nCP_s[da] -= Ni;
+                    nCP_s[db] += Ni;
+                    m_s[si * K + da] -= 1;
+                    m_s[si * K + db] += 1;
+                    if (blockIdx.x == 0) a.z[i] = db + 1;
+                }
+                ++movers;
+                pos = t + 1;
+                hi = prev_end;
+                nd = 2;
+                W = min(a.w.Wmax, max(a.w.Wmin, min(4 * (first + 1), 1024)));
+                __syncthreads();
+            }
+        }
+        if (pos >= a.nM) break;
+        const long long end = max(hi, min(pos + (long long)W, a.nM));
+        const int nwin = (int)(end - pos);
+        const long long nPatch = (hi - pos) * (nd == K ? 0 : nd);  // nd == K only on the first round (hi == pos)
+        const long long nFresh = (end - hi) * K;
+        const long long total = nd + nPatch + nFresh;
+        ++rounds;
+        // ---- A1: units
+        for (long long uidx = gwarp; uidx < total; uidx += tw) {
+            int j;
+            long long t = -1;
+            if (uidx < nd) {
+                j = (nd == K) ? (int)uidx : (uidx == 0 ? da : db);
+            } else if (uidx < nd + nPatch) {
+                const long long q = uidx - nd;
+                t = pos + q / 2;
+                j = (q & 1) ? db : da;
+            } else {
+                const long long q = uidx - nd - nPatch;
+                t = hi + q / K;
+                j = (int)(q % K);
+            }
+            const int* ncol = n_s + j * Rp;
+            if (t < 0) {
+                for (int r = lane; r < R; r += 32) scr[r] = lg_tab(lgtab, T, ncol[r], a.beta);
+                __syncwarp();
+                if (lane == 0) {
+                    double S = 0.0;
+                    for (int r = 0; r < R; ++r) S += scr[r];
+                    a.w.colsum[j] = S;
+                    a.w.lgnCP[j] = dlgamma((double)nCP_s[j] + Rbeta);
+                }
+                __syncwarp();
+            } else {
+                const long long i = a.ix[t] - 1;
+                const int zi = a.z[i] - 1;
+                const int sgn = (j == zi) ? -1 : 1;
+                const int* x = a.counts + i * R;
+                for (int r = lane; r < R; r += 32) scr[r] = lg_tab(lgtab, T, (long long)ncol[r] + sgn * x[r], a.beta);
+                __syncwarp();
+                if (lane == 0) {
+                    double S = 0.0;
+                    for (int r = 0; r < R; ++r) S += scr[r];
+                    const size_t o = (size_t)(t % a.w.Wmax) * K + j;
+                    a.w.bufP[o] = S;
+                    a.w.bufA[o] = dlgamma((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
+                }
+                __syncwarp();
+            }
+        }
+        units_done += total;
+        grid_sync(a.w.barrier, bar_target);
+        // ---- A2: combine in the reference's order, draw
+        double* pl = scr;
+        double* rr = scr + K;
+        double* hs = scr + 2 * K;
+        int* perm = reinterpret_cast<int*>(scr + 3 * K);
+        for (int c = gwarp; c < nwin; c += tw) {
+            const long long t = pos + c;
+            const long long i = a.ix[t] - 1;
+            const int zi = a.z[i] - 1, si = a.s[i] - 1;
+            const size_t o = (size_t)(t % a.w.Wmax) * K;
+            for (int j = lane; j < K; j += 32) {
+                const double S = __ldcg(a.w.bufP + o + j), A = __ldcg(a.w.bufA + o + j);
+                const double cs = __ldcg(a.w.colsum + j), lc = __ldcg(a.w.lgnCP + j);
+                double p = dlog((double)(m_s[si * K + j] - (j == zi)) + a.alpha);
+                if (j != zi) {
+                    p = p + S;
+                    p = p - A;
+                    p = p - cs;
+                    p = p + lc;
+                } else {
+                    p = p + cs;
+                    p = p - lc;
+                    p = p - S;
+                    p = p + A;
+                }
+                pl[j] = p;
+                if (a.probs) a.probs[i * K + j] = p;
+            }
+            __syncwarp();
+            int znew = zi;
+            if (a.doSample) {
+                znew = warp_sample_ll(pl, K, a.u[t], rr, hs, perm, lane);
+                if (znew < 0) {
+                    if (lane == 0) atomicCAS(a.w.status, 0, znew);
+                    znew = zi;
+                }
+            }
+            if (lane == 0) a.w.spec[c] = (znew != zi) ? ((zi << 16) | znew) : -1;
+            __syncwarp();
+        }
+        prev_end = end;
+        have_spec = true;
+        grid_sync(a.w.barrier, bar_target);
+    }
+    // ---- write the tables back (CTA 0's copy; all copies are identical)
+    if (blockIdx.x == 0) {
+        for (int q = threadIdx.x; q < R * K; q += blockDim.x) a.nTab[q] = n_s[(q / R) * Rp + (q % R)];
+        for (int q = threadIdx.x; q < K; q += blockDim.x) a.nCP[q] = nCP_s[q];
+        for (int q = threadIdx.x; q < K * nS; q += blockDim.x) a.mCPByS[q] = m_s[q];
+        if (threadIdx.x == 0) {
+            a.w.stats[0] += rounds;
+            a.w.stats[1] += units_done;
+            a.w.stats[2] += movers;
+        }
+    }
+}
+
+inline size_t z_sweep_smem(int R, int K, int nS, int T, int nwarp) {
+    const int Rp = R | 1;
+    const size_t scratchD = (size_t)std::max(R, 3 * K + (K + 1) / 2) + 2;
+    return sizeof(double) * (T + nwarp * scratchD) + sizeof(long long) * K + sizeof(int) * ((size_t)K * Rp + K * nS + 4);
+}
+
+// ------------------------------------------------------------------------------------------------ y sweep
+// .cGCalcGibbsProbY (R/celda_G.R:602-660) + cG_CalcGibbsProbY (src/cG_calcGibbsProbY.cpp:187-249) on a dense
+// gene-major int32 count table (nGByCP in celda_CG; ncol = K).
+struct YArgs {
+    int nG, ncol, L;
+    const int* counts;      // [nG][ncol] gene-major
+    const long long* nByG;  // [nG]
+    int* y;                 // [nG] 1-based, updated
+    int* tTab;              // L x ncol column-major (nTSByC argument), updated
+    long long* nByTS;       // [L], updated
+    int* nGByTS;            // [L] (includes the +1 pseudo-gene), updated
+    double beta, gamma, delta;
+    const int* ix;
+    const double* u;
+    int doSample;
+    double* probs;  // L x nG or null
+    SweepWork w;
+};
+
+__global__ void __launch_bounds__(512, 1) k_sweep_y(YArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L = a.L, C = a.ncol, T = a.w.lgT;
+    const int Cp = C | 1;
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int scratchD = max(2 * C + 8, 3 * L + (L + 1) / 2) + 2;
+    double* lgtab = reinterpret_cast<double*>(smem_raw);
+    double* lgt_s = lgtab + T;                          // [L][Cp] lgamma(t + beta)
+    double* scratch_all = lgt_s + (size_t)L * Cp;
+    long long* T_s = reinterpret_cast<long long*>(scratch_all + (size_t)nwarp * scratchD);
+    int* t_s = reinterpret_cast<int*>(T_s + L);         // [L][Cp]
+    int* g_s = t_s + (size_t)L * Cp;
+    int* s_misc = g_s + L;
+    double* scr = scratch_all + (size_t)warp * scratchD;
+    const int gwarp = blockIdx.x * nwarp + warp, tw = gridDim.x * nwarp;
+
+    for (int q = threadIdx.x; q < T; q += blockDim.x) lgtab[q] = dlgamma((double)q + a.beta);
+    for (int q = threadIdx.x; q < L * C; q += blockDim.x) t_s[(q % L) * Cp + (q / L)] = a.tTab[q];
+    for (int q = threadIdx.x; q < L; q += blockDim.x) {
+        T_s[q] = a.nByTS[q];
+        g_s[q] = a.nGByTS[q];
+    }
+    __syncthreads();
+    for (int q = threadIdx.x; q < L * C; q += blockDim.x) {
+        const int l = q / C, c = q % C;
+        lgt_s[l * Cp + c] = lg_tab(lgtab, T, t_s[l * Cp + c], a.beta);
+    }
+    __syncthreads();
+
+    long long pos = 0, hi = 0, prev_end = 0;
+    int W = a.w.Wmax, nd = 0, da = -1, db = -1;
+    bool have_spec = false;
+    unsigned bar_target = 0;
+    long long rounds = 0, units_done = 0, movers = 0;
+
+    while (true) {
+        if (have_spec) {
+            const int nwin = (int)(prev_end - pos);
+            const int first = block_first_mover(a.w.spec, nwin, s_misc);
+            if (first < 0) {
+                pos = prev_end;
+                hi = pos;
+                nd = 0;
+                W = min(2 * W, a.w.Wmax);
+            } else {
+                const long long t = pos + first;
+                const int i = a.ix[t] - 1;
+                const int packed = __ldcg(a.w.spec + first);
+                da = packed >> 16;
+                db = packed & 0xffff;
+                const int* x = a.counts + (size_t)i * C;
+                for (int c = threadIdx.x; c < C; c += blockDim.x) {
+                    const int xv = x[c];
+                    t_s[da * Cp + c] -= xv;
+                    t_s[db * Cp + c] += xv;
+                    lgt_s[da * Cp + c] = lg_tab(lgtab, T, t_s[da * Cp + c], a.beta);
+                    lgt_s[db * Cp + c] = lg_tab(lgtab, T, t_s[db * Cp + c], a.beta);
+                }
+                if (threadIdx.x == 0) {
+                    const long long Ni = a.nByG[i];
+                    g_s[da] -= 1;
+                    g_s[db] += 1;
+                    T_s[da] -= Ni;
+                    T_s[db] += Ni;
+                    if (blockIdx.x == 0) a.y[i] = db + 1;
+                }
+                ++movers;
+                pos = t + 1;
+                hi = prev_end;
+                nd = 2;
+                W = min(a.w.Wmax, max(a.w.Wmin, min(4 * (first + 1), 1024)));
+                __syncthreads();
+            }
+        }
+        if (pos >= a.nG) break;
+        const long long end = max(hi, min(pos + (long long)W, (long long)a.nG));
+        const int nwin = (int)(end - pos);
+        const long long nPatch = (hi - pos) * nd;
+        const long long nFresh = (end - hi) * L;
+        const long long total = nPatch + nFresh;
+        ++rounds;
+        for (long long uidx = gwarp; uidx < total; uidx += tw) {
+            long long t;
+            int l;
+            if (uidx < nPatch) {
+                t = pos + uidx / 2;
+                l = (uidx & 1) ? db : da;
+            } else {
+                const long long q = uidx - nPatch;
+                t = hi + q / L;
+                l = (int)(q % L);
+            }
+            const int i = a.ix[t] - 1;
+            const int cur = a.y[i] - 1;
+            const bool isCur = (l == cur);
+            const int* x = a.counts + (size_t)i * C;
+            const int* trow = t_s + l * Cp;
+            const double* lrow = lgt_s + l * Cp;
+            // first loop of cG_CalcGibbsProbY (:212-225): per column one fresh lgamma and one cached one
+            for (int c = lane; c < C; c += 32) {
+                const double fresh = lg_tab(lgtab, T, (long long)trow[c] + (isCur ? -x[c] : x[c]), a.beta);
+                const double cached = lrow[c];
+                scr[2 * c] = isCur ? cached : fresh;      // added
+                scr[2 * c + 1] = isCur ? fresh : cached;  // subtracted
+            }
+            // second loop (:230-246): six per-module terms, evaluated by six lanes
+            if (lane < 6) {
+                const int g = g_s[l];
+                const double Tl = (double)T_s[l], Ni = (double)a.nByG[i];
+                double v;
+                if (isCur) {
+                    switch (lane) {
+                        case 0: v = dlgamma((double)g + a.gamma); break;
+                        case 1: v = dlgamma((double)(g - 1) + a.gamma); break;
+                        case 2: v = dlgamma((double)g * a.delta); break;
+                        case 3: v = dlgamma((double)(g - 1) * a.delta); break;
+                        case 4: v = dlgamma(Tl - Ni + (double)(g - 1) * a.delta); break;
+                        default: v = dlgamma(Tl + (double)g * a.delta); break;
+                    }
+                } else {
+                    switch (lane) {
+                        case 0: v = dlgamma((double)(g + 1) + a.gamma); break;
+                        case 1: v = dlgamma((double)g + a.gamma); break;
+                        case 2: v = dlgamma((double)(g + 1) * a.delta); break;
+                        case 3: v = dlgamma((double)g * a.delta); break;
+                        case 4: v = dlgamma(Tl + (double)g * a.delta); break;
+                        default: v = dlgamma(Tl + Ni + (double)(g + 1) * a.delta); break;
+                    }
+                }
+                scr[2 * C + lane] = v;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                double p = 0.0;
+                for (int c = 0; c < C; ++c) {
+                    p += scr[2 * c];
+                    p -= scr[2 * c + 1];
+                }
+                p += scr[2 * C + 0];
+                p -= scr[2 * C + 1];
+                p += scr[2 * C + 2];
+                p -= scr[2 * C + 3];
+                p += scr[2 * C + 4];
+                p -= scr[2 * C + 5];
+                a.w.bufP[(size_t)(t % a.w.Wmax) * L + l] = p;
+            }
+            __syncwarp();
+        }
+        units_done += total;
+        grid_sync(a.w.barrier, bar_target);
+        double* pl = scr;
+        double* rr = scr + L;
+        double* hs = scr + 2 * L;
+        int* perm = reinterpret_cast<int*>(scr + 3 * L);
+        for (int c = gwarp; c < nwin; c += tw) {
+            const long long t = pos + c;
+            const int i = a.ix[t] - 1;
+            const int cur = a.y[i] - 1;
+            const size_t o = (size_t)(t % a.w.Wmax) * L;
+            for (int l = lane; l < L; l += 32) {
+                const double p = __ldcg(a.w.bufP + o + l);
+                pl[l] = p;
+                if (a.probs) a.probs[(size_t)i * L + l] = p;
+            }
+            __syncwarp();
+            int ynew = cur;
+            if (a.doSample) {
+                ynew = warp_sample_ll(pl, L, a.u[t], rr, hs, perm, lane);
+                if (ynew < 0) {
+                    if (lane == 0) atomicCAS(a.w.status, 0, ynew);
+                    ynew = cur;
+                }
+            }
+            if (lane == 0) a.w.spec[c] = (ynew != cur) ? ((cur << 16) | ynew) : -1;
+            __syncwarp();
+        }
+        prev_end = end;
+        have_spec = true;
+        grid_sync(a.w.barrier, bar_target);
+    }
+    if (blockIdx.x == 0) {
+        for (int q = threadIdx.x; q < L * C; q += blockDim.x) a.tTab[q] = t_s[(q % L) * Cp + (q / L)];
+        for (int q = threadIdx.x; q < L; q += blockDim.x) {
+            a.nByTS[q] = T_s[q];
+            a.nGByTS[q] = g_s[q];
+        }
+        if (threadIdx.x == 0) {
+            a.w.stats[0] += rounds;
+            a.w.stats[1] += units_done;
+            a.w.stats[2] += movers;
+        }
+    }
+}
+
+inline size_t y_sweep_smem(int L, int C, int T, int nwarp) {
+    const int Cp = C | 1;
+    const size_t scratchD = (size_t)std::max(2 * C + 8, 3 * L + (L + 1) / 2) + 2;
+    return sizeof(double) * (T + (size_t)L * Cp + nwarp * scratchD) + sizeof(long long) * L +
+           sizeof(int) * ((size_t)L * Cp + L + 4);
+}
+
+}  // namespace celda

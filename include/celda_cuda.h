@@ -1,0 +1,176 @@
+/*
+ * celda_cuda.h -- C ABI of libcelda_cuda.so (B200 / sm_100a), the drop-in boundary for celda's
+ * collapsed-Gibbs hot path.  Plain pointers and sizes only; every call is synchronous; every
+ * function returns 0 on success or a non-zero status whose text is celda_cuda_last_error().
+ *
+ * Conventions follow R: matrices are column-major, labels are 1-based int32, a dgCMatrix is
+ * (p int32[ncol+1], i int32[nnz] 0-based, x double[nnz]).  All pointers are HOST pointers; the
+ * library owns device memory.  `*Change` routines update `px` IN PLACE (reference quirk Q3).
+ *
+ * Each entry point names the reference interface it replaces (paths relative to the celda
+ * source tree, campbio/celda 1.18.2).  The R-side binding (.Call shim) is shown in INTEGRATION.md.
+ */
+#ifndef CELDA_CUDA_H
+#define CELDA_CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- library ------------------------------------------------------------------------------- */
+const char *celda_cuda_last_error(void);
+int celda_cuda_device_count(int *n);
+/* Select the device used by the stateless entry points below (chain handles carry their own). */
+int celda_cuda_set_device(int device);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+long long celda_cuda_launch_count(void);
+
+/* ---- a12: lgamma tables  (R/celda_CG.R:428-429,543; R/celda_G.R:329-332) --------------------
+ * out[k] = lgamma(x[k]) / log / exp with the library's device arithmetic (DESIGN.md "arithmetic"). */
+int celda_cuda_lgamma(const double *x, long long n, double *out);
+int celda_cuda_log(const double *x, long long n, double *out);
+int celda_cuda_exp(const double *x, long long n, double *out);
+
+/* ---- a2-a5: by-group aggregation on a dgCMatrix  (src/matrixSumsSparse.cpp) ------------------
+ * replaces colSumByGroupSparse(counts, group, K)                  src/matrixSumsSparse.cpp:9-38   */
+int celda_colSumByGroupSparse(int nrow, int ncol, const int *p, const int *i, const double *x,
+                              const int *group, long long ngroup, int K, double *out /* nrow x K */);
+/* replaces rowSumByGroupSparse(counts, group, L)                  src/matrixSumsSparse.cpp:44-73  */
+int celda_rowSumByGroupSparse(int nrow, int ncol, const int *p, const int *i, const double *x,
+                              const int *group, long long ngroup, int L, double *out /* L x ncol */);
+/* replaces colSumByGroupChangeSparse(counts, px, group, pgroup, K) src/matrixSumsSparse.cpp:85-131 */
+int celda_colSumByGroupChangeSparse(int nrow, int ncol, const int *p, const int *i, const double *x,
+                                    double *px, int px_nrow, const int *group, long long ngroup,
+                                    const int *pgroup, long long npgroup, int K);
+/* replaces rowSumByGroupChangeSparse(counts, px, group, pgroup, L) src/matrixSumsSparse.cpp:141-187 */
+int celda_rowSumByGroupChangeSparse(int nrow, int ncol, const int *p, const int *i, const double *x,
+                                    double *px, int px_ncol, const int *group, long long ngroup,
+                                    const int *pgroup, long long npgroup, int L);
+
+#ifdef CELDA_CUDA_PLANNED /* declared for the next milestone; not exported yet */
+/* ---- a2-a5 dense twins  (src/matrixSums.c) ---------------------------------------------------
+ * `nlevels` stands for nlevels(group); pass a negative value for "group is not a factor".
+ * replaces _rowSumByGroup / _rowSumByGroup_numeric                 src/matrixSums.c:5-48,198-236   */
+int celda_rowSumByGroup_int(const int *x, int nr, int nc, const int *group, long long ngroup, int nlevels, int *ans);
+int celda_rowSumByGroup_numeric(const double *x, int nr, int nc, const int *group, long long ngroup, int nlevels,
+                                double *ans);
+/* replaces _colSumByGroup / _colSumByGroup_numeric                 src/matrixSums.c:50-93,240-278  */
+int celda_colSumByGroup_int(const int *x, int nr, int nc, const int *group, long long ngroup, int nlevels, int *ans);
+int celda_colSumByGroup_numeric(const double *x, int nr, int nc, const int *group, long long ngroup, int nlevels,
+                                double *ans);
+/* replaces _rowSumByGroupChange[_numeric]                          src/matrixSums.c:97-143,282-327 */
+int celda_rowSumByGroupChange_int(const int *x, int nr, int nc, int *px, int px_nr, int px_nc, const int *group,
+                                  long long ngroup, int nlevels, const int *pgroup, long long npgroup, int pnlevels);
+int celda_rowSumByGroupChange_numeric(const double *x, int nr, int nc, double *px, int px_nr, int px_nc,
+                                      const int *group, long long ngroup, int nlevels, const int *pgroup,
+                                      long long npgroup, int pnlevels);
+/* replaces _colSumByGroupChange[_numeric]                          src/matrixSums.c:147-194,331-379 */
+int celda_colSumByGroupChange_int(const int *x, int nr, int nc, int *px, int px_nr, int px_nc, const int *group,
+                                  long long ngroup, int nlevels, const int *pgroup, long long npgroup, int pnlevels);
+int celda_colSumByGroupChange_numeric(const double *x, int nr, int nc, double *px, int px_nr, int px_nc,
+                                      const int *group, long long ngroup, int nlevels, const int *pgroup,
+                                      long long npgroup, int pnlevels);
+
+/* ---- a10: one gene's module log-probabilities -----------------------------------------------
+ * replaces cG_CalcGibbsProbY(index, counts, nTSbyC, nbyTS, nGbyTS, nbyG, y, L, nG, lg_beta, lg_gamma,
+ * lg_delta, delta)                                                src/cG_calcGibbsProbY.cpp:187-249
+ * The three lgamma tables of the reference are value-identical to direct evaluation and are not taken. */
+int celda_cG_CalcGibbsProbY(int index, const double *counts, int ncol, const double *nTSbyC, const double *nbyTS,
+                            const int *nGbyTS, const double *nbyG, const int *y, int L, int nG, double beta,
+                            double gamma, double delta, double *probs /* L */);
+
+/* ---- a9 helpers -----------------------------------------------------------------------------
+ * replaces fastNormPropLog(R_counts, R_alpha)                     src/matrixNorm.cpp:36-52        */
+int celda_fastNormPropLog(const double *counts, int nr, int nc, double alpha, double *res);
+/* replaces eigenMatMultInt(A, B) / eigenMatMultNumeric(A, B): C = t(A) %*% B   src/eigenMatMultInt.cpp:11-26 */
+int celda_eigenMatMultInt(const double *A, int n, int k, const int *B, int m, double *C /* k x m */);
+int celda_eigenMatMultNumeric(const double *A, int n, int k, const double *B, int m, double *C);
+/* replaces _perplexityG(x, phi, psi, group)                       src/perplexity.c:5-62           */
+int celda_perplexityG(const int *x, int nr, int nc, const double *phi, int phi_nr, int phi_nc, const double *psi,
+                      int psi_nr, int psi_nc, const int *group, long long ngroup, int nlevels, double *ans);
+
+/* ---- a13: collapsed log-likelihoods -----------------------------------------------------------
+ * replaces .cCGCalcLL  R/celda_CG.R:839-888 ; .cCCalcLL  R/celda_C.R:760-788 ; .cGCalcLL  R/celda_G.R:664-702 */
+int celda_cCGCalcLL(int K, int L, const int *mCPByS, const double *nTSByCP, const double *nByG, int nGenes,
+                    const double *nByTS, const int *nGByTS, int nS, double alpha, double beta, double delta,
+                    double gamma, double *ll);
+int celda_cCCalcLL(const int *mCPByS, const double *nGByCP, int K, int nS, int nG, double alpha, double beta,
+                   double *ll);
+int celda_cGCalcLL(const double *nTSByC, const double *nByTS, const double *nByG, int nGenes, const int *nGByTS,
+                   long long nM, int L, double beta, double delta, double gamma, double *ll);
+
+/* ---- a8/a9/a10 at sweep granularity, R-closure signatures ------------------------------------
+ * replaces .cCCalcGibbsProbZ(counts, mCPByS, nGByCP, nByC, nCP, z, s, K, nG, nM, alpha, beta, doSample)
+ *                                                                 R/celda_C.R:620-714
+ * counts: dense nG x nM (nTSByC in celda_CG).  ix/u: injected visiting order (1-based) and uniforms
+ * (SURVEY.md App. C).  mCPByS, nGByCP, nCP, z are updated in place; probs (K x nM) may be NULL. */
+int celda_cCCalcGibbsProbZ(const double *counts, int *mCPByS, int nS, double *nGByCP, const double *nByC, double *nCP,
+                           int *z, const int *s, int K, int nG, long long nM, double alpha, double beta, int doSample,
+                           const int *ix, const double *u, double *probs);
+/* replaces .cGCalcGibbsProbY(counts, nTSByC, nByTS, nGByTS, nByG, y, L, nG, beta, delta, gamma, lgbeta,
+ * lggamma, lgdelta, doSample)                                     R/celda_G.R:602-660
+ * counts: dense nG x ncol (nGByCP in celda_CG).  nTSByC (L x ncol), nByTS, nGByTS, y updated in place. */
+int celda_cGCalcGibbsProbY(const double *counts, int ncol, double *nTSByC, double *nByTS, int *nGByTS,
+                           const double *nByG, int *y, int L, int nG, double beta, double delta, double gamma,
+                           int doSample, const int *ix, const double *u, double *probs);
+/* replaces .cCCalcEMProbZ (same arguments as the Gibbs closure)   R/celda_C.R:717-756
+ * counts as a dgCMatrix (p != NULL) or dense nG x nM double (p == NULL, x = the matrix). */
+int celda_cCCalcEMProbZ(int nG, long long nM, const int *p, const int *i, const double *x, int *mCPByS, int nS,
+                        double *nGByCP, double *nCP, int *z, const int *s, int K, double alpha, double beta,
+                        int doSample, double *probs);
+
+#endif /* CELDA_CUDA_PLANNED */
+
+/* ---- device-resident chain (a1, a6, a7, a15): counts and tables stay in HBM -------------------
+ * One handle = one chain of .celda_CG / .celda_C / .celda_G (R/celda_CG.R:367-835, R/celda_C.R:306-616,
+ * R/celda_G.R:286-583) on one device.  */
+typedef struct celda_chain celda_chain;
+enum { CELDA_MODEL_CG = 0, CELDA_MODEL_C = 1, CELDA_MODEL_G = 2 };
+
+/* Upload the count matrix (integrality-checked, narrowed to int32) and build its gene-major twin. */
+int celda_chain_create(celda_chain **out, int device, int model, int nG, int nM, const int *p, const int *i,
+                       const double *x, const int *s /* 1-based sample labels, NULL for celda_G */, int nS, int K,
+                       int L, double alpha, double beta, double delta, double gamma);
+void celda_chain_destroy(celda_chain *h);
+/* .cCGDecomposeCounts / .cCDecomposeCounts / .cGDecomposeCounts from labels (z or y may be NULL per model). */
+int celda_chain_set_state(celda_chain *h, const int *z, const int *y);
+int celda_chain_get_state(celda_chain *h, int *z, int *y);
+/* Sweeps with injected order/uniforms (host pointers) ... */
+int celda_chain_sweep_y(celda_chain *h, const int *ix, const double *u, int doSample);
+int celda_chain_sweep_z_gibbs(celda_chain *h, const int *ix, const double *u, int doSample);
+#ifdef CELDA_CUDA_PLANNED
+int celda_chain_sweep_z_em(celda_chain *h, int doSample);
+/* ... or with the device Philox4x32-10 generator: order = argsort of Philox keys, one uniform per step. */
+int celda_chain_seed(celda_chain *h, unsigned long long seed, unsigned long long stream);
+int celda_chain_sweep_y_philox(celda_chain *h, int doSample);
+int celda_chain_sweep_z_gibbs_philox(celda_chain *h, int doSample);
+#endif /* CELDA_CUDA_PLANNED */
+/* One iteration of the chain loop without split heuristics (R/celda_CG.R:543-602): y sweep, rowSumByGroupChange,
+ * z sweep (Gibbs), colSumByGroupChange, log-likelihood.  ix/u NULL => Philox. */
+int celda_chain_iterate(celda_chain *h, const int *ix_y, const double *u_y, const int *ix_z, const double *u_z,
+                        double *ll);
+/* Pre-stage injected draws for n_iter iterations in HBM, then run them without host traffic. */
+int celda_chain_stage_draws(celda_chain *h, int n_iter, const int *ix_y, const double *u_y, const int *ix_z,
+                            const double *u_z);
+int celda_chain_iterate_staged(celda_chain *h, int iter, double *ll);
+int celda_chain_loglik(celda_chain *h, double *ll);
+#ifdef CELDA_CUDA_PLANNED
+int celda_chain_perplexity(celda_chain *h, double *perplexity);
+#endif /* CELDA_CUDA_PLANNED */
+/* Tables as R holds them (double, column-major); any pointer may be NULL. */
+int celda_chain_get_tables(celda_chain *h, int *mCPByS, double *nTSByC, double *nTSByCP, double *nGByCP, double *nCP,
+                           double *nByC, double *nByG, double *nByTS, int *nGByTS);
+int celda_chain_get_probs(celda_chain *h, double *probsZ /* K x nM */, double *probsY /* L x nG */);
+/* CUDA-event timing on the chain's stream (bench.py): start, then stop returns elapsed ms. */
+int celda_chain_timer_start(celda_chain *h);
+int celda_chain_timer_stop(celda_chain *h, float *ms);
+/* Per-kernel accumulated device time (ms) and launch counts since the last reset, for roofline accounting:
+ * which = 0 y sweep, 1 rowSumByGroupChange, 2 z sweep, 3 colSumByGroupChange, 4 log-likelihood. */
+int celda_chain_profile(celda_chain *h, int enable);
+int celda_chain_profile_get(celda_chain *h, int which, double *ms, long long *launches,
+                            long long *rounds_units_movers /* [3] */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
