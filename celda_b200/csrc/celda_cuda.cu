@@ -339,6 +339,32 @@ int celda_cuda_set_device(int device) {
 
 long long celda_cuda_launch_count(void) { return g_launches.load(); }
 
+int celda_cuda_fp64_peak(double* tflops) {
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    DevBuf<double> out;
+    CELDA_TRY(out.alloc(1));
+    const int sms = num_sms(g_device), blocks = sms * 4, threads = 512, iters = 20000;
+    cudaEvent_t e0, e1;
+    CELDA_CUDA_OK(cudaEventCreate(&e0));
+    CELDA_CUDA_OK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        k_fp64_peak<<<blocks, threads>>>(out.p, iters);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+        count_launch();
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    CELDA_CUDA_OK(cudaGetLastError());
+    *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ math
 static int math_vec(int op, const double* x, long long n, double* out) {
     CELDA_CUDA_OK(cudaSetDevice(g_device));

@@ -16,6 +16,17 @@ __global__ void k_math_vec(const double* __restrict__ x, long long n, double* __
     }
 }
 
+// FP64 FMA peak probe: 8 independent chains per thread, fma() is explicit so -fmad=false does not split it.
+__global__ void k_fp64_peak(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, b, c); a1 = fma(a1, b, c); a2 = fma(a2, b, c); a3 = fma(a3, b, c);
+        a4 = fma(a4, b, c); a5 = fma(a5, b, c); a6 = fma(a6, b, c); a7 = fma(a7, b, c);
+    }
+    if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 12345.678) out[0] = a0;
+}
+
 // double -> int32 with an integrality / range check (flag[0] |= 1 when a value is not an int32 integer)
 __global__ void k_narrow(const double* __restrict__ x, long long n, int* __restrict__ out, int* flag) {
     int bad = 0;

@@ -25,6 +25,10 @@ int celda_cuda_set_device(int device);
 /* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
 long long celda_cuda_launch_count(void);
 
+/* Measured FP64 FMA throughput of the current device in TFLOP/s (2 flop per FMA; independent register chains on
+ * every SM).  The roofline denominator for the FP64-bound sweep kernels: MEASURED_PEAKS.json has no FP64 entry. */
+int celda_cuda_fp64_peak(double *tflops);
+
 /* ---- a12: lgamma tables  (R/celda_CG.R:428-429,543; R/celda_G.R:329-332) --------------------
  * out[k] = lgamma(x[k]) / log / exp with the library's device arithmetic (DESIGN.md "arithmetic"). */
 int celda_cuda_lgamma(const double *x, long long n, double *out);
