@@ -213,6 +213,16 @@ int chain_loglik_async(celda_chain* h) {
     return 0;
 }
 
+// Steady-state window (items): the largest count <= Wmax whose units (items x candidates) fill a whole number of
+// grid-wide lane passes, so that the lane-per-unit rounds leave no thread idle.
+int full_window(const celda_chain* h, int threads, int ncand) {
+    const long long lanes = (long long)h->sms * threads;
+    const long long m = std::max<long long>(1, (long long)h->Wmax * ncand / lanes);
+    long long w = m * lanes / ncand;
+    if (w > h->Wmax) w = h->Wmax;
+    return (int)std::max<long long>(w, h->Wmin);
+}
+
 int launch_sweep_z(celda_chain* h, const int* d_ix, const double* d_u, int doSample, int which) {
     ProfScope ps(h, which);
     const int threads = 512, nwarp = threads / 32;
@@ -235,7 +245,7 @@ int launch_sweep_z(celda_chain* h, const int* d_ix, const double* d_u, int doSam
     a.doSample = doSample;
     a.probs = h->probsZ.p;
     a.w = SweepWork{h->bufP.p, h->bufA.p, h->spec.p, h->colsum.p, h->lgnCP.p, h->barrier.p, h->status.p,
-                    h->stats.p + 3 * which, h->Wmax, h->Wmin, h->lgT};
+                    h->stats.p + 3 * which, h->Wmax, full_window(h, threads, a.K), h->Wmin, h->lgT};
     const size_t smem = z_sweep_smem(a.R, a.K, a.nS, h->lgT, nwarp);
     if (smem > 220 * 1024) return fail("z sweep: K=%d x R=%d tables need %zu bytes of shared memory (> 220 KB)", a.K, a.R, smem);
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -267,7 +277,7 @@ int launch_sweep_y(celda_chain* h, const int* d_ix, const double* d_u, int doSam
     a.doSample = doSample;
     a.probs = h->probsY.p;
     a.w = SweepWork{h->bufP.p, h->bufA.p, h->spec.p, h->colsum.p, h->lgnCP.p, h->barrier.p, h->status.p,
-                    h->stats.p + 3 * which, h->Wmax, h->Wmin, h->lgT};
+                    h->stats.p + 3 * which, h->Wmax, full_window(h, threads, a.L), h->Wmin, h->lgT};
     const size_t smem = y_sweep_smem(a.L, a.ncol, h->lgT, nwarp);
     if (smem > 220 * 1024) return fail("y sweep: L=%d x K=%d tables need %zu bytes of shared memory (> 220 KB)", a.L, a.ncol, smem);
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

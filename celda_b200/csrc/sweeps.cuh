@@ -223,6 +223,7 @@ struct SweepWork {
     int* status;        // 0 ok, else sampler error code
     long long* stats;   // [0] rounds, [1] units, [2] movers
     int Wmax;           // ring capacity (items)
+    int Wfull;          // steady-state window: units per round = a whole number of grid-wide lane passes
     int Wmin;
     int lgT;            // entries of the shared-memory lgamma(k + beta) table
 };
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_z(ZArgs a) {
     __syncthreads();
 
     long long pos = 0, hi = 0;
-    int W = a.w.Wmax, nd = K, da = -1, db = -1;  // nd == K: every column's cached sum is still to be computed
+    int W = a.w.Wfull, nd = K, da = -1, db = -1;  // nd == K: every column's cached sum is still to be computed
     bool have_spec = false;
     long long prev_end = 0;
     unsigned bar_target = 0;
@@ -290,7 +291,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_z(ZArgs a) {
                 pos = prev_end;
                 hi = pos;
                 nd = 0;
-                W = min(2 * W, a.w.Wmax);
+                W = min(2 * W, a.w.Wfull);
             } else {
                 const long long t = pos + first;
                 const long long i = a.ix[t] - 1;
@@ -326,10 +327,11 @@ __global__ void __launch_bounds__(512, 1) k_sweep_z(ZArgs a) {
         const long long nFresh = (end - hi) * K;
         const long long total = nd + nPatch + nFresh;
         ++rounds;
-        // ---- A1: units
-        for (long long uidx = gwarp; uidx < total; uidx += tw) {
-            int j;
-            long long t = -1;
+        // ---- A1: units.  Large rounds: one LANE per unit (the lane evaluates and adds its unit's terms serially, no
+        // staging, no single-lane phases).  Small rounds (churn): one WARP per unit for latency.  Both orders of
+        // evaluation are the reference's, so the results are identical.
+        auto decode = [&](long long uidx, long long& t, int& j) {
+            t = -1;
             if (uidx < nd) {
                 j = (nd == K) ? (int)uidx : (uidx == 0 ? da : db);
             } else if (uidx < nd + nPatch) {
@@ -341,32 +343,64 @@ __global__ void __launch_bounds__(512, 1) k_sweep_z(ZArgs a) {
                 t = hi + q / K;
                 j = (int)(q % K);
             }
-            const int* ncol = n_s + j * Rp;
-            if (t < 0) {
-                for (int r = lane; r < R; r += 32) scr[r] = lg_tab(lgtab, T, ncol[r], a.beta);
-                __syncwarp();
-                if (lane == 0) {
+        };
+        if (total >= (long long)tw * 16) {
+            for (long long uidx = (long long)gwarp * 32 + lane; uidx < total; uidx += (long long)tw * 32) {
+                int j;
+                long long t;
+                decode(uidx, t, j);
+                const int* ncol = n_s + j * Rp;
+                if (t < 0) {
                     double S = 0.0;
-                    for (int r = 0; r < R; ++r) S += scr[r];
+                    for (int r = 0; r < R; ++r) S += lg_tab(lgtab, T, ncol[r], a.beta);
                     a.w.colsum[j] = S;
                     a.w.lgnCP[j] = dlgamma((double)nCP_s[j] + Rbeta);
-                }
-                __syncwarp();
-            } else {
-                const long long i = a.ix[t] - 1;
-                const int zi = a.z[i] - 1;
-                const int sgn = (j == zi) ? -1 : 1;
-                const int* x = a.counts + i * R;
-                for (int r = lane; r < R; r += 32) scr[r] = lg_tab(lgtab, T, (long long)ncol[r] + sgn * x[r], a.beta);
-                __syncwarp();
-                if (lane == 0) {
+                } else {
+                    const long long i = a.ix[t] - 1;
+                    const int zi = a.z[i] - 1;
+                    const int sgn = (j == zi) ? -1 : 1;
+                    const int* x = a.counts + i * R;
                     double S = 0.0;
-                    for (int r = 0; r < R; ++r) S += scr[r];
+#pragma unroll 2
+                    for (int r = 0; r < R; ++r) S += lg_tab(lgtab, T, (long long)ncol[r] + sgn * __ldg(x + r), a.beta);
                     const size_t o = (size_t)(t % a.w.Wmax) * K + j;
                     a.w.bufP[o] = S;
                     a.w.bufA[o] = dlgamma((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
                 }
-                __syncwarp();
+            }
+        } else {
+            for (long long uidx = gwarp; uidx < total; uidx += tw) {
+                int j;
+                long long t;
+                decode(uidx, t, j);
+                const int* ncol = n_s + j * Rp;
+                if (t < 0) {
+                    for (int r = lane; r < R; r += 32) scr[r] = lg_tab(lgtab, T, ncol[r], a.beta);
+                    __syncwarp();
+                    if (lane == 0) {
+                        double S = 0.0;
+                        for (int r = 0; r < R; ++r) S += scr[r];
+                        a.w.colsum[j] = S;
+                        a.w.lgnCP[j] = dlgamma((double)nCP_s[j] + Rbeta);
+                    }
+                    __syncwarp();
+                } else {
+                    const long long i = a.ix[t] - 1;
+                    const int zi = a.z[i] - 1;
+                    const int sgn = (j == zi) ? -1 : 1;
+                    const int* x = a.counts + i * R;
+                    for (int r = lane; r < R; r += 32)
+                        scr[r] = lg_tab(lgtab, T, (long long)ncol[r] + sgn * x[r], a.beta);
+                    __syncwarp();
+                    if (lane == 0) {
+                        double S = 0.0;
+                        for (int r = 0; r < R; ++r) S += scr[r];
+                        const size_t o = (size_t)(t % a.w.Wmax) * K + j;
+                        a.w.bufP[o] = S;
+                        a.w.bufA[o] = dlgamma((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
+                    }
+                    __syncwarp();
+                }
             }
         }
         units_done += total;
@@ -483,7 +517,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_y(YArgs a) {
     __syncthreads();
 
     long long pos = 0, hi = 0, prev_end = 0;
-    int W = a.w.Wmax, nd = 0, da = -1, db = -1;
+    int W = a.w.Wfull, nd = 0, da = -1, db = -1;
     bool have_spec = false;
     unsigned bar_target = 0;
     long long rounds = 0, units_done = 0, movers = 0;
@@ -496,7 +530,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_y(YArgs a) {
                 pos = prev_end;
                 hi = pos;
                 nd = 0;
-                W = min(2 * W, a.w.Wmax);
+                W = min(2 * W, a.w.Wfull);
             } else {
                 const long long t = pos + first;
                 const int i = a.ix[t] - 1;
@@ -534,72 +568,125 @@ __global__ void __launch_bounds__(512, 1) k_sweep_y(YArgs a) {
         const long long nFresh = (end - hi) * L;
         const long long total = nPatch + nFresh;
         ++rounds;
-        for (long long uidx = gwarp; uidx < total; uidx += tw) {
-            long long t;
-            int l;
-            if (uidx < nPatch) {
-                t = pos + uidx / 2;
-                l = (uidx & 1) ? db : da;
-            } else {
-                const long long q = uidx - nPatch;
-                t = hi + q / L;
-                l = (int)(q % L);
-            }
-            const int i = a.ix[t] - 1;
-            const int cur = a.y[i] - 1;
-            const bool isCur = (l == cur);
-            const int* x = a.counts + (size_t)i * C;
-            const int* trow = t_s + l * Cp;
-            const double* lrow = lgt_s + l * Cp;
-            // first loop of cG_CalcGibbsProbY (:212-225): per column one fresh lgamma and one cached one
-            for (int c = lane; c < C; c += 32) {
-                const double fresh = lg_tab(lgtab, T, (long long)trow[c] + (isCur ? -x[c] : x[c]), a.beta);
-                const double cached = lrow[c];
-                scr[2 * c] = isCur ? cached : fresh;      // added
-                scr[2 * c + 1] = isCur ? fresh : cached;  // subtracted
-            }
-            // second loop (:230-246): six per-module terms, evaluated by six lanes
-            if (lane < 6) {
-                const int g = g_s[l];
-                const double Tl = (double)T_s[l], Ni = (double)a.nByG[i];
-                double v;
+        if (total >= (long long)tw * 16) {
+            // one lane per (gene, module) unit: the whole cG_CalcGibbsProbY term sequence in one thread
+            for (long long uidx = (long long)gwarp * 32 + lane; uidx < total; uidx += (long long)tw * 32) {
+                long long t;
+                int l;
+                if (uidx < nPatch) {
+                    t = pos + uidx / 2;
+                    l = (uidx & 1) ? db : da;
+                } else {
+                    const long long q = uidx - nPatch;
+                    t = hi + q / L;
+                    l = (int)(q % L);
+                }
+                const int i = a.ix[t] - 1;
+                const int cur = a.y[i] - 1;
+                const bool isCur = (l == cur);
+                const int* x = a.counts + (size_t)i * C;
+                const int* trow = t_s + l * Cp;
+                const double* lrow = lgt_s + l * Cp;
+                double p = 0.0;
                 if (isCur) {
-                    switch (lane) {
-                        case 0: v = dlgamma((double)g + a.gamma); break;
-                        case 1: v = dlgamma((double)(g - 1) + a.gamma); break;
-                        case 2: v = dlgamma((double)g * a.delta); break;
-                        case 3: v = dlgamma((double)(g - 1) * a.delta); break;
-                        case 4: v = dlgamma(Tl - Ni + (double)(g - 1) * a.delta); break;
-                        default: v = dlgamma(Tl + (double)g * a.delta); break;
+                    for (int c = 0; c < C; ++c) {
+                        p += lrow[c];
+                        p -= lg_tab(lgtab, T, (long long)trow[c] - __ldg(x + c), a.beta);
                     }
                 } else {
-                    switch (lane) {
-                        case 0: v = dlgamma((double)(g + 1) + a.gamma); break;
-                        case 1: v = dlgamma((double)g + a.gamma); break;
-                        case 2: v = dlgamma((double)(g + 1) * a.delta); break;
-                        case 3: v = dlgamma((double)g * a.delta); break;
-                        case 4: v = dlgamma(Tl + (double)g * a.delta); break;
-                        default: v = dlgamma(Tl + Ni + (double)(g + 1) * a.delta); break;
+#pragma unroll 2
+                    for (int c = 0; c < C; ++c) {
+                        p += lg_tab(lgtab, T, (long long)trow[c] + __ldg(x + c), a.beta);
+                        p -= lrow[c];
                     }
                 }
-                scr[2 * C + lane] = v;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                double p = 0.0;
-                for (int c = 0; c < C; ++c) {
-                    p += scr[2 * c];
-                    p -= scr[2 * c + 1];
+                const int g = g_s[l];
+                const double Tl = (double)T_s[l], Ni = (double)a.nByG[i];
+                if (isCur) {
+                    p += dlgamma((double)g + a.gamma);
+                    p -= dlgamma((double)(g - 1) + a.gamma);
+                    p += dlgamma((double)g * a.delta);
+                    p -= dlgamma((double)(g - 1) * a.delta);
+                    p += dlgamma(Tl - Ni + (double)(g - 1) * a.delta);
+                    p -= dlgamma(Tl + (double)g * a.delta);
+                } else {
+                    p += dlgamma((double)(g + 1) + a.gamma);
+                    p -= dlgamma((double)g + a.gamma);
+                    p += dlgamma((double)(g + 1) * a.delta);
+                    p -= dlgamma((double)g * a.delta);
+                    p += dlgamma(Tl + (double)g * a.delta);
+                    p -= dlgamma(Tl + Ni + (double)(g + 1) * a.delta);
                 }
-                p += scr[2 * C + 0];
-                p -= scr[2 * C + 1];
-                p += scr[2 * C + 2];
-                p -= scr[2 * C + 3];
-                p += scr[2 * C + 4];
-                p -= scr[2 * C + 5];
                 a.w.bufP[(size_t)(t % a.w.Wmax) * L + l] = p;
             }
-            __syncwarp();
+        } else {
+            for (long long uidx = gwarp; uidx < total; uidx += tw) {
+                long long t;
+                int l;
+                if (uidx < nPatch) {
+                    t = pos + uidx / 2;
+                    l = (uidx & 1) ? db : da;
+                } else {
+                    const long long q = uidx - nPatch;
+                    t = hi + q / L;
+                    l = (int)(q % L);
+                }
+                const int i = a.ix[t] - 1;
+                const int cur = a.y[i] - 1;
+                const bool isCur = (l == cur);
+                const int* x = a.counts + (size_t)i * C;
+                const int* trow = t_s + l * Cp;
+                const double* lrow = lgt_s + l * Cp;
+                // first loop of cG_CalcGibbsProbY (:212-225): per column one fresh lgamma and one cached one
+                for (int c = lane; c < C; c += 32) {
+                    const double fresh = lg_tab(lgtab, T, (long long)trow[c] + (isCur ? -x[c] : x[c]), a.beta);
+                    const double cached = lrow[c];
+                    scr[2 * c] = isCur ? cached : fresh;      // added
+                    scr[2 * c + 1] = isCur ? fresh : cached;  // subtracted
+                }
+                // second loop (:230-246): six per-module terms, evaluated by six lanes
+                if (lane < 6) {
+                    const int g = g_s[l];
+                    const double Tl = (double)T_s[l], Ni = (double)a.nByG[i];
+                    double v;
+                    if (isCur) {
+                        switch (lane) {
+                            case 0: v = dlgamma((double)g + a.gamma); break;
+                            case 1: v = dlgamma((double)(g - 1) + a.gamma); break;
+                            case 2: v = dlgamma((double)g * a.delta); break;
+                            case 3: v = dlgamma((double)(g - 1) * a.delta); break;
+                            case 4: v = dlgamma(Tl - Ni + (double)(g - 1) * a.delta); break;
+                            default: v = dlgamma(Tl + (double)g * a.delta); break;
+                        }
+                    } else {
+                        switch (lane) {
+                            case 0: v = dlgamma((double)(g + 1) + a.gamma); break;
+                            case 1: v = dlgamma((double)g + a.gamma); break;
+                            case 2: v = dlgamma((double)(g + 1) * a.delta); break;
+                            case 3: v = dlgamma((double)g * a.delta); break;
+                            case 4: v = dlgamma(Tl + (double)g * a.delta); break;
+                            default: v = dlgamma(Tl + Ni + (double)(g + 1) * a.delta); break;
+                        }
+                    }
+                    scr[2 * C + lane] = v;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    double p = 0.0;
+                    for (int c = 0; c < C; ++c) {
+                        p += scr[2 * c];
+                        p -= scr[2 * c + 1];
+                    }
+                    p += scr[2 * C + 0];
+                    p -= scr[2 * C + 1];
+                    p += scr[2 * C + 2];
+                    p -= scr[2 * C + 3];
+                    p += scr[2 * C + 4];
+                    p -= scr[2 * C + 5];
+                    a.w.bufP[(size_t)(t % a.w.Wmax) * L + l] = p;
+                }
+                __syncwarp();
+            }
         }
         units_done += total;
         grid_sync(a.w.barrier, bar_target);
