@@ -162,6 +162,66 @@ __device__ __forceinline__ double dlgamma_large(double x) {
     return ln_sqrt_2pi + (x - 0.5) * dlog(x) - x + dlgammacor(x);
 }
 
+// Generic lgamma kept out of line: the sweeps call it only off the hot range.
+__device__ __noinline__ double dlgamma_generic(double x) {
+    if (!(x > 0.0))
+        return (x == 0.0) ? __longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double(0x7ff8000000000000LL);
+    if (x <= 10.0) {
+        if (x < 1e-306) return -dlog(x);
+        return dlog(fabs(dgamma_small(x)));
+    }
+    return dlgamma_large(x);
+}
+
+// Hot-range lgamma: 10 < x <= 4934720 (a count plus a prior), straight-line code.  Performs exactly the
+// operations of dlgamma_large()/dlog() for such x (x is normal, exponent k >= 3, Stirling correction below its
+// large-x cut-off); the two data-dependent forms of the log tail are both evaluated and selected, which costs a
+// few flops but keeps the warp converged.  Arguments within 2^-20 of a power of two (e.g. 63 + 1) take the
+// generic routine.
+__device__ __constant__ double kHot[20] = {
+    6.93147180369123816490e-01, 1.90821492927058770002e-10,                                   // 0 ln2_hi, 1 ln2_lo
+    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01,             // 2.. Lg1..Lg7
+    2.222219843214978396e-01, 1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01,
+    +.6221098041892605227126015543416e-13, -.1809129475572494194263306266719e-10,             // 9.. algmcs[4..0]
+    +.9810825646924729426157171547487e-8, -.1384948176067563840732986059135e-4, +.1666389480451863247205729650822e+0,
+    0.918938533204672741780329736406, 0.0, 0.0, 0.0, 0.0, 0.0};
+
+__device__ __forceinline__ double dlgamma_hot(double x) {
+    if (!(x > 10.0 && x <= 4934720.0)) return dlgamma_generic(x);
+    int hx = __double2hiint(x);
+    const int lx = __double2loint(x);
+    int k = (hx >> 20) - 1023;
+    hx &= 0x000fffff;
+    if ((0x000fffff & (2 + hx)) < 3) return dlgamma_generic(x);
+    const int i = (hx + 0x95f64) & 0x100000;
+    const double xm = __hiloint2double(hx | (i ^ 0x3ff00000), lx);
+    k += (i >> 20);
+    const double f = xm - 1.0;
+    const double dk = (double)k;
+    const double s = f / (2.0 + f);
+    const double z = s * s;
+    const double w = z * z;
+    const double t1 = w * (kHot[3] + w * (kHot[5] + w * kHot[7]));
+    const double t2 = z * (kHot[2] + w * (kHot[4] + w * (kHot[6] + w * kHot[8])));
+    const double R = t2 + t1;
+    const double hfsq = 0.5 * f * f;
+    const double dkhi = dk * kHot[0], dklo = dk * kHot[1];
+    const double la = dkhi - ((hfsq - (s * (hfsq + R) + dklo)) - f);
+    const double lb = dkhi - ((s * (f - R) - dklo) - f);
+    const double lg = (((hx - 0x6147a) | (0x6b851 - hx)) > 0) ? la : lb;
+    // Stirling correction, x < 94906265.6
+    const double t = 10.0 / x;
+    const double tx = (t * t * 2.0 - 1.0) * 2.0;
+    double b0 = 0.0, b1 = 0.0, b2 = 0.0;
+    b2 = b1; b1 = b0; b0 = tx * b1 - b2 + kHot[9];
+    b2 = b1; b1 = b0; b0 = tx * b1 - b2 + kHot[10];
+    b2 = b1; b1 = b0; b0 = tx * b1 - b2 + kHot[11];
+    b2 = b1; b1 = b0; b0 = tx * b1 - b2 + kHot[12];
+    b2 = b1; b1 = b0; b0 = tx * b1 - b2 + kHot[13];
+    const double cor = ((b0 - b2) * 0.5) / x;
+    return kHot[14] + (x - 0.5) * lg - x + cor;
+}
+
 __device__ __forceinline__ double dlgamma(double x) {
     if (!(x > 0.0))
         return (x == 0.0) ? __longlong_as_double(0x7ff0000000000000LL) : __longlong_as_double(0x7ff8000000000000LL);

@@ -12,7 +12,7 @@ template <int OP>
 __global__ void k_math_vec(const double* __restrict__ x, long long n, double* __restrict__ out) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const double v = x[i];
-        out[i] = OP == 0 ? dlgamma(v) : (OP == 1 ? dlog(v) : dexp(v));
+        out[i] = OP == 0 ? dlgamma_hot(v) : (OP == 1 ? dlog(v) : dexp(v));  // hot lgamma falls back to the generic one off range
     }
 }
 

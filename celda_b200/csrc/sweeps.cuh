@@ -249,7 +249,7 @@ struct ZArgs {
 };
 
 __device__ __forceinline__ double lg_tab(const double* lgtab, int T, long long k, double beta) {
-    return (k < T) ? lgtab[k] : dlgamma((double)k + beta);
+    return (k < T) ? lgtab[k] : dlgamma_hot((double)k + beta);
 }
 
 __global__ void __launch_bounds__(512, 1) k_sweep_z(ZArgs a) {
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_z(ZArgs a) {
                     for (int r = 0; r < R; ++r) S += lg_tab(lgtab, T, (long long)ncol[r] + sgn * __ldg(x + r), a.beta);
                     const size_t o = (size_t)(t % a.w.Wmax) * K + j;
                     a.w.bufP[o] = S;
-                    a.w.bufA[o] = dlgamma((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
+                    a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
                 }
             }
         } else {
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_z(ZArgs a) {
                         for (int r = 0; r < R; ++r) S += scr[r];
                         const size_t o = (size_t)(t % a.w.Wmax) * K + j;
                         a.w.bufP[o] = S;
-                        a.w.bufA[o] = dlgamma((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
+                        a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
                     }
                     __syncwarp();
                 }
@@ -588,34 +588,25 @@ __global__ void __launch_bounds__(512, 1) k_sweep_y(YArgs a) {
                 const int* trow = t_s + l * Cp;
                 const double* lrow = lgt_s + l * Cp;
                 double p = 0.0;
-                if (isCur) {
-                    for (int c = 0; c < C; ++c) {
-                        p += lrow[c];
-                        p -= lg_tab(lgtab, T, (long long)trow[c] - __ldg(x + c), a.beta);
-                    }
-                } else {
+                const int sgn = isCur ? -1 : 1;
 #pragma unroll 2
-                    for (int c = 0; c < C; ++c) {
-                        p += lg_tab(lgtab, T, (long long)trow[c] + __ldg(x + c), a.beta);
-                        p -= lrow[c];
-                    }
+                for (int c = 0; c < C; ++c) {
+                    const double fresh = lg_tab(lgtab, T, (long long)trow[c] + sgn * __ldg(x + c), a.beta);
+                    const double cached = lrow[c];
+                    p += isCur ? cached : fresh;
+                    p -= isCur ? fresh : cached;
                 }
                 const int g = g_s[l];
                 const double Tl = (double)T_s[l], Ni = (double)a.nByG[i];
-                if (isCur) {
-                    p += dlgamma((double)g + a.gamma);
-                    p -= dlgamma((double)(g - 1) + a.gamma);
-                    p += dlgamma((double)g * a.delta);
-                    p -= dlgamma((double)(g - 1) * a.delta);
-                    p += dlgamma(Tl - Ni + (double)(g - 1) * a.delta);
-                    p -= dlgamma(Tl + (double)g * a.delta);
-                } else {
-                    p += dlgamma((double)(g + 1) + a.gamma);
-                    p -= dlgamma((double)g + a.gamma);
-                    p += dlgamma((double)(g + 1) * a.delta);
-                    p -= dlgamma((double)g * a.delta);
-                    p += dlgamma(Tl + (double)g * a.delta);
-                    p -= dlgamma(Tl + Ni + (double)(g + 1) * a.delta);
+                {
+                    // second loop of cG_CalcGibbsProbY (:230-246); (g0, g1) = (g, g-1) for the current module else (g+1, g)
+                    const int g1 = isCur ? g - 1 : g, g0 = g1 + 1;
+                    p += dlgamma_hot((double)g0 + a.gamma);
+                    p -= dlgamma_hot((double)g1 + a.gamma);
+                    p += dlgamma_hot((double)g0 * a.delta);
+                    p -= dlgamma_hot((double)g1 * a.delta);
+                    p += dlgamma_hot(isCur ? Tl - Ni + (double)g1 * a.delta : Tl + (double)g1 * a.delta);
+                    p -= dlgamma_hot(isCur ? Tl + (double)g0 * a.delta : Tl + Ni + (double)g0 * a.delta);
                 }
                 a.w.bufP[(size_t)(t % a.w.Wmax) * L + l] = p;
             }
