@@ -291,7 +291,10 @@ def main():
                                        "ms_per_launch": rc_ms}
         out["kernel_ms_per_step"] = {k: v["ms"] / K for k, v in prof.items()}
         out["sweep_stats_per_step"] = {k: {"rounds": prof[k]["rounds"] / K, "units": prof[k]["units"] / K,
-                                           "movers": prof[k]["movers"] / K} for k in ("sweep_y", "sweep_z")}
+                                           "movers": prof[k]["movers"] / K,
+                                           "cta0_mclk": {q: prof[k]["clk_" + q] / K / 1e6 for q in
+                                                         ("commit", "units", "draw", "barrier")}}
+                                       for k in ("sweep_y", "sweep_z")}
         if world == 1 and not a.no_cpu_baseline:
             zc, yc = ch.get_state()
             c_ixy, c_uy, c_ixz, c_uz = draw_inputs(rng, 1, nG, nM)

@@ -213,19 +213,21 @@ int chain_loglik_async(celda_chain* h) {
     return 0;
 }
 
-// Steady-state window (items): the largest count <= Wmax whose units (items x candidates) fill a whole number of
-// grid-wide lane passes, so that the lane-per-unit rounds leave no thread idle.
-int full_window(const celda_chain* h, int threads, int ncand) {
+// Window sizes (items).  unit: the item count whose units (items x candidates) fill one grid-wide lane pass;
+// full: the largest multiple of it that fits the ring buffer, so lane-per-unit rounds leave no thread idle.
+void window_sizes(const celda_chain* h, int threads, int ncand, int* full, int* unit) {
     const long long lanes = (long long)h->sms * threads;
-    const long long m = std::max<long long>(1, (long long)h->Wmax * ncand / lanes);
-    long long w = m * lanes / ncand;
-    if (w > h->Wmax) w = h->Wmax;
-    return (int)std::max<long long>(w, h->Wmin);
+    long long u = std::max<long long>(lanes / ncand, h->Wmin);
+    if (u > h->Wmax) u = h->Wmax;
+    *unit = (int)u;
+    *full = (int)(std::max<long long>(1, h->Wmax / u) * u);
 }
 
 int launch_sweep_z(celda_chain* h, const int* d_ix, const double* d_u, int doSample, int which) {
     ProfScope ps(h, which);
-    const int threads = 512, nwarp = threads / 32;
+    int threads = 1024;
+    if (z_sweep_smem(h->L, h->K, h->nS, h->lgT, threads / 32) > 220 * 1024) threads = 512;
+    const int nwarp = threads / 32;
     ZArgs a{};
     a.R = h->L;
     a.K = h->K;
@@ -244,8 +246,10 @@ int launch_sweep_z(celda_chain* h, const int* d_ix, const double* d_u, int doSam
     a.u = d_u;
     a.doSample = doSample;
     a.probs = h->probsZ.p;
+    int wfull, wunit;
+    window_sizes(h, threads, a.K, &wfull, &wunit);
     a.w = SweepWork{h->bufP.p, h->bufA.p, h->spec.p, h->colsum.p, h->lgnCP.p, h->barrier.p, h->status.p,
-                    h->stats.p + 3 * which, h->Wmax, full_window(h, threads, a.K), h->Wmin, h->lgT};
+                    h->stats.p + 8 * which, h->Wmax, wfull, wunit, h->Wmin, h->lgT};
     const size_t smem = z_sweep_smem(a.R, a.K, a.nS, h->lgT, nwarp);
     if (smem > 220 * 1024) return fail("z sweep: K=%d x R=%d tables need %zu bytes of shared memory (> 220 KB)", a.K, a.R, smem);
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -258,7 +262,9 @@ int launch_sweep_z(celda_chain* h, const int* d_ix, const double* d_u, int doSam
 
 int launch_sweep_y(celda_chain* h, const int* d_ix, const double* d_u, int doSample, int which) {
     ProfScope ps(h, which);
-    const int threads = 512, nwarp = threads / 32;
+    int threads = 1024;
+    if (y_sweep_smem(h->L, h->K, h->lgT, threads / 32) > 220 * 1024) threads = 512;
+    const int nwarp = threads / 32;
     YArgs a{};
     a.nG = h->nG;
     a.ncol = h->K;
@@ -276,8 +282,10 @@ int launch_sweep_y(celda_chain* h, const int* d_ix, const double* d_u, int doSam
     a.u = d_u;
     a.doSample = doSample;
     a.probs = h->probsY.p;
+    int wfull, wunit;
+    window_sizes(h, threads, a.L, &wfull, &wunit);
     a.w = SweepWork{h->bufP.p, h->bufA.p, h->spec.p, h->colsum.p, h->lgnCP.p, h->barrier.p, h->status.p,
-                    h->stats.p + 3 * which, h->Wmax, full_window(h, threads, a.L), h->Wmin, h->lgT};
+                    h->stats.p + 8 * which, h->Wmax, wfull, wunit, h->Wmin, h->lgT};
     const size_t smem = y_sweep_smem(a.L, a.ncol, h->lgT, nwarp);
     if (smem > 220 * 1024) return fail("y sweep: L=%d x K=%d tables need %zu bytes of shared memory (> 220 KB)", a.L, a.ncol, smem);
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -613,7 +621,7 @@ int celda_chain_create(celda_chain** out, int device, int model, int nG, int nM,
     CELDA_TRY(h->status.alloc(1));
     CELDA_TRY(h->status.zero(st));
     CELDA_TRY(h->barrier.alloc(1));
-    CELDA_TRY(h->stats.alloc(15));
+    CELDA_TRY(h->stats.alloc(40));
     CELDA_TRY(h->stats.zero(st));
     CELDA_TRY(h->ixy.alloc(nG));
     CELDA_TRY(h->uy.alloc(nG));
@@ -804,14 +812,12 @@ int celda_chain_profile_get(celda_chain* h, int which, double* ms, long long* la
     if (which < 0 || which > 4) return fail("profile_get: which must be 0..4");
     CELDA_CUDA_OK(cudaSetDevice(h->device));
     CELDA_TRY(chain_sync(h));
-    long long stats[3] = {0, 0, 0};
-    CELDA_CUDA_OK(cudaMemcpy(stats, h->stats.p + 3 * which, sizeof(stats), cudaMemcpyDeviceToHost));
+    long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CELDA_CUDA_OK(cudaMemcpy(stats, h->stats.p + 8 * which, sizeof(stats), cudaMemcpyDeviceToHost));
     if (ms) *ms = h->prof_ms[which];
     if (launches) *launches = h->prof_launches[which];
     if (rounds) {
-        rounds[0] = stats[0];
-        rounds[1] = stats[1];
-        rounds[2] = stats[2];
+        for (int q = 0; q < 7; ++q) rounds[q] = stats[q];
     }
     return 0;
 }

@@ -90,10 +90,12 @@ __device__ __forceinline__ double warp_ordered_sum_pos(const double* r, int n, i
 }
 
 // .sampleLl (R/celda_functions.R:1-11) + sample.int(n, 1, TRUE, prob) with the uniform supplied.
-// pl: n log-probabilities in shared memory.  r, hs: n doubles of warp scratch; perm: n ints.
+// pl: n log-probabilities in shared memory (overwritten on the rare exact path).  r: n doubles of warp scratch;
+// hs may alias pl; perm: n ints.  n <= 1024.
 // Returns the 0-based label, or <0: -1 Walker-alias branch (>200 likely categories), -2 non-finite
 // probability, -3 no positive probability.  Warp-cooperative; all lanes return the same value.
-__device__ int warp_sample_ll(const double* pl, int n, double u, double* r, double* hs, int* perm, int lane) {
+__device__ int warp_sample_ll(double* pl, int n, double u, double* r, int* perm, int lane) {
+    double* hs = pl;
     const unsigned FULL = 0xffffffffu;
     double mx = -__longlong_as_double(0x7ff0000000000000LL);
     for (int i = lane; i < n; i += 32) mx = fmax(mx, pl[i]);
@@ -115,7 +117,6 @@ __device__ int warp_sample_ll(const double* pl, int n, double u, double* r, doub
     for (int i = lane; i < n; i += 32) {
         const double q = r[i] / s2;
         r[i] = q;
-        hs[i] = q;
         nc += ((double)n * q > 0.1);
         nzero += (q == 0.0);
     }
@@ -130,11 +131,12 @@ __device__ int warp_sample_ll(const double* pl, int n, double u, double* r, doub
     double cum = 0.0;
     int result = -1;
     bool slow = false;
+    unsigned taken = 0;  // bit q: entry lane + 32 q of this lane has been consumed (n <= 1024)
     for (int k = 0; k < n; ++k) {
         double bv = -1.0;
         int bi = 0x7fffffff;
-        for (int i = lane; i < n; i += 32) {
-            const double v = hs[i];
+        for (int i = lane, q = 0; i < n; i += 32, ++q) {
+            const double v = ((taken >> q) & 1u) ? -1.0 : r[i];
             if (v > bv) {
                 bv = v;
                 bi = i;
@@ -171,8 +173,7 @@ __device__ int warp_sample_ll(const double* pl, int n, double u, double* r, doub
                 slow = true;  // the label inside a group of exactly equal probabilities depends on heapsort order
             break;
         }
-        if (lane == 0) hs[bi] = -1.0;
-        __syncwarp();
+        if ((bi & 31) == lane) taken |= 1u << (bi >> 5);
     }
     if (!slow) return result;
     // Exact emulation of ProbSampleReplace on one lane (rare: exact ties, or u beyond the total mass).
@@ -221,9 +222,10 @@ struct SweepWork {
     double* lgnCP;      // [K]  (z sweep)
     unsigned* barrier;  // zeroed before launch
     int* status;        // 0 ok, else sampler error code
-    long long* stats;   // [0] rounds, [1] units, [2] movers
+    long long* stats;   // [0] rounds, [1] units, [2] movers, [3..6] CTA-0 clocks in commit / units / draw / barriers
     int Wmax;           // ring capacity (items)
     int Wfull;          // steady-state window: units per round = a whole number of grid-wide lane passes
+    int Wunit;          // items whose units fill one grid-wide lane pass
     int Wmin;
     int lgT;            // entries of the shared-memory lgamma(k + beta) table
 };
@@ -252,12 +254,12 @@ __device__ __forceinline__ double lg_tab(const double* lgtab, int T, long long k
     return (k < T) ? lgtab[k] : dlgamma_hot((double)k + beta);
 }
 
-__global__ void __launch_bounds__(512, 1) k_sweep_z(ZArgs a) {
+__global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int R = a.R, K = a.K, nS = a.nS, T = a.w.lgT;
     const int Rp = R | 1;  // odd stride: candidate-major rows, conflict-free across lanes of r
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int scratchD = max(R, 3 * K + (K + 1) / 2) + 2;
+    const int scratchD = max(R, 2 * K + (K + 1) / 2) + 2;
     double* lgtab = reinterpret_cast<double*>(smem_raw);
     double* scratch_all = lgtab + T;
     long long* nCP_s = reinterpret_cast<long long*>(scratch_all + (size_t)nwarp * scratchD);
@@ -281,6 +283,8 @@ __global__ void __launch_bounds__(512, 1) k_sweep_z(ZArgs a) {
     long long prev_end = 0;
     unsigned bar_target = 0;
     long long rounds = 0, units_done = 0, movers = 0;
+    long long ck_commit = 0, ck_units = 0, ck_draw = 0, ck_bar = 0, ck0 = clock64(), ck1;
+#define CELDA_TICK(acc) do { ck1 = clock64(); acc += ck1 - ck0; ck0 = ck1; } while (0)
 
     while (true) {
         // ---- commit the first mover of the previous window (every CTA updates its own copy of the tables)
@@ -291,7 +295,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_z(ZArgs a) {
                 pos = prev_end;
                 hi = pos;
                 nd = 0;
-                W = min(2 * W, a.w.Wfull);
+                W = (2 * W <= a.w.Wunit) ? 2 * W : min(max(2 * W / a.w.Wunit, 1) * a.w.Wunit, a.w.Wfull);
             } else {
                 const long long t = pos + first;
                 const long long i = a.ix[t] - 1;
@@ -316,11 +320,12 @@ __global__ void __launch_bounds__(512, 1) k_sweep_z(ZArgs a) {
                 pos = t + 1;
                 hi = prev_end;
                 nd = 2;
-                W = min(a.w.Wmax, max(a.w.Wmin, min(4 * (first + 1), 1024)));
+                W = max(a.w.Wmin, min(4 * (first + 1), a.w.Wunit));
                 __syncthreads();
             }
         }
         if (pos >= a.nM) break;
+        CELDA_TICK(ck_commit);
         const long long end = max(hi, min(pos + (long long)W, a.nM));
         const int nwin = (int)(end - pos);
         const long long nPatch = (hi - pos) * (nd == K ? 0 : nd);  // nd == K only on the first round (hi == pos)
@@ -404,12 +409,13 @@ __global__ void __launch_bounds__(512, 1) k_sweep_z(ZArgs a) {
             }
         }
         units_done += total;
+        CELDA_TICK(ck_units);
         grid_sync(a.w.barrier, bar_target);
+        CELDA_TICK(ck_bar);
         // ---- A2: combine in the reference's order, draw
         double* pl = scr;
         double* rr = scr + K;
-        double* hs = scr + 2 * K;
-        int* perm = reinterpret_cast<int*>(scr + 3 * K);
+        int* perm = reinterpret_cast<int*>(scr + 2 * K);
         for (int c = gwarp; c < nwin; c += tw) {
             const long long t = pos + c;
             const long long i = a.ix[t] - 1;
@@ -436,7 +442,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_z(ZArgs a) {
             __syncwarp();
             int znew = zi;
             if (a.doSample) {
-                znew = warp_sample_ll(pl, K, a.u[t], rr, hs, perm, lane);
+                znew = warp_sample_ll(pl, K, a.u[t], rr, perm, lane);
                 if (znew < 0) {
                     if (lane == 0) atomicCAS(a.w.status, 0, znew);
                     znew = zi;
@@ -447,7 +453,9 @@ __global__ void __launch_bounds__(512, 1) k_sweep_z(ZArgs a) {
         }
         prev_end = end;
         have_spec = true;
+        CELDA_TICK(ck_draw);
         grid_sync(a.w.barrier, bar_target);
+        CELDA_TICK(ck_bar);
     }
     // ---- write the tables back (CTA 0's copy; all copies are identical)
     if (blockIdx.x == 0) {
@@ -458,13 +466,17 @@ __global__ void __launch_bounds__(512, 1) k_sweep_z(ZArgs a) {
             a.w.stats[0] += rounds;
             a.w.stats[1] += units_done;
             a.w.stats[2] += movers;
+            a.w.stats[3] += ck_commit;
+            a.w.stats[4] += ck_units;
+            a.w.stats[5] += ck_draw;
+            a.w.stats[6] += ck_bar;
         }
     }
 }
 
 inline size_t z_sweep_smem(int R, int K, int nS, int T, int nwarp) {
     const int Rp = R | 1;
-    const size_t scratchD = (size_t)std::max(R, 3 * K + (K + 1) / 2) + 2;
+    const size_t scratchD = (size_t)std::max(R, 2 * K + (K + 1) / 2) + 2;
     return sizeof(double) * (T + nwarp * scratchD) + sizeof(long long) * K + sizeof(int) * ((size_t)K * Rp + K * nS + 4);
 }
 
@@ -487,12 +499,12 @@ struct YArgs {
     SweepWork w;
 };
 
-__global__ void __launch_bounds__(512, 1) k_sweep_y(YArgs a) {
+__global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int L = a.L, C = a.ncol, T = a.w.lgT;
     const int Cp = C | 1;
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int scratchD = max(2 * C + 8, 3 * L + (L + 1) / 2) + 2;
+    const int scratchD = max(2 * C + 8, 2 * L + (L + 1) / 2) + 2;
     double* lgtab = reinterpret_cast<double*>(smem_raw);
     double* lgt_s = lgtab + T;                          // [L][Cp] lgamma(t + beta)
     double* scratch_all = lgt_s + (size_t)L * Cp;
@@ -521,6 +533,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_y(YArgs a) {
     bool have_spec = false;
     unsigned bar_target = 0;
     long long rounds = 0, units_done = 0, movers = 0;
+    long long ck_commit = 0, ck_units = 0, ck_draw = 0, ck_bar = 0, ck0 = clock64(), ck1;
 
     while (true) {
         if (have_spec) {
@@ -530,7 +543,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_y(YArgs a) {
                 pos = prev_end;
                 hi = pos;
                 nd = 0;
-                W = min(2 * W, a.w.Wfull);
+                W = (2 * W <= a.w.Wunit) ? 2 * W : min(max(2 * W / a.w.Wunit, 1) * a.w.Wunit, a.w.Wfull);
             } else {
                 const long long t = pos + first;
                 const int i = a.ix[t] - 1;
@@ -557,11 +570,12 @@ __global__ void __launch_bounds__(512, 1) k_sweep_y(YArgs a) {
                 pos = t + 1;
                 hi = prev_end;
                 nd = 2;
-                W = min(a.w.Wmax, max(a.w.Wmin, min(4 * (first + 1), 1024)));
+                W = max(a.w.Wmin, min(4 * (first + 1), a.w.Wunit));
                 __syncthreads();
             }
         }
         if (pos >= a.nG) break;
+        CELDA_TICK(ck_commit);
         const long long end = max(hi, min(pos + (long long)W, (long long)a.nG));
         const int nwin = (int)(end - pos);
         const long long nPatch = (hi - pos) * nd;
@@ -680,11 +694,12 @@ __global__ void __launch_bounds__(512, 1) k_sweep_y(YArgs a) {
             }
         }
         units_done += total;
+        CELDA_TICK(ck_units);
         grid_sync(a.w.barrier, bar_target);
+        CELDA_TICK(ck_bar);
         double* pl = scr;
         double* rr = scr + L;
-        double* hs = scr + 2 * L;
-        int* perm = reinterpret_cast<int*>(scr + 3 * L);
+        int* perm = reinterpret_cast<int*>(scr + 2 * L);
         for (int c = gwarp; c < nwin; c += tw) {
             const long long t = pos + c;
             const int i = a.ix[t] - 1;
@@ -698,7 +713,7 @@ __global__ void __launch_bounds__(512, 1) k_sweep_y(YArgs a) {
             __syncwarp();
             int ynew = cur;
             if (a.doSample) {
-                ynew = warp_sample_ll(pl, L, a.u[t], rr, hs, perm, lane);
+                ynew = warp_sample_ll(pl, L, a.u[t], rr, perm, lane);
                 if (ynew < 0) {
                     if (lane == 0) atomicCAS(a.w.status, 0, ynew);
                     ynew = cur;
@@ -709,7 +724,9 @@ __global__ void __launch_bounds__(512, 1) k_sweep_y(YArgs a) {
         }
         prev_end = end;
         have_spec = true;
+        CELDA_TICK(ck_draw);
         grid_sync(a.w.barrier, bar_target);
+        CELDA_TICK(ck_bar);
     }
     if (blockIdx.x == 0) {
         for (int q = threadIdx.x; q < L * C; q += blockDim.x) a.tTab[q] = t_s[(q % L) * Cp + (q / L)];
@@ -721,13 +738,17 @@ __global__ void __launch_bounds__(512, 1) k_sweep_y(YArgs a) {
             a.w.stats[0] += rounds;
             a.w.stats[1] += units_done;
             a.w.stats[2] += movers;
+            a.w.stats[3] += ck_commit;
+            a.w.stats[4] += ck_units;
+            a.w.stats[5] += ck_draw;
+            a.w.stats[6] += ck_bar;
         }
     }
 }
 
 inline size_t y_sweep_smem(int L, int C, int T, int nwarp) {
     const int Cp = C | 1;
-    const size_t scratchD = (size_t)std::max(2 * C + 8, 3 * L + (L + 1) / 2) + 2;
+    const size_t scratchD = (size_t)std::max(2 * C + 8, 2 * L + (L + 1) / 2) + 2;
     return sizeof(double) * (T + (size_t)L * Cp + nwarp * scratchD) + sizeof(long long) * L +
            sizeof(int) * ((size_t)L * Cp + L + 4);
 }

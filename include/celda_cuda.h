@@ -172,7 +172,7 @@ int celda_chain_timer_stop(celda_chain *h, float *ms);
  * which = 0 y sweep, 1 rowSumByGroupChange, 2 z sweep, 3 colSumByGroupChange, 4 log-likelihood. */
 int celda_chain_profile(celda_chain *h, int enable);
 int celda_chain_profile_get(celda_chain *h, int which, double *ms, long long *launches,
-                            long long *rounds_units_movers /* [3] */);
+                            long long *stats /* [7]: rounds, units, movers, CTA-0 clocks in commit / units / draw / barriers */);
 
 #ifdef __cplusplus
 }
