@@ -60,7 +60,7 @@ struct celda_chain {
     int staged_iters = 0;
     DevBuf<int> st_ixy, st_ixz;
     DevBuf<double> st_uy, st_uz;
-    int Wmax = 8192, Wmin = 128, lgT = 2048;
+    int Wmax = 8192, Wmin = 32, lgT = 2048;
     int npG = 0;
     // profiling
     bool profile = false;

@@ -73,17 +73,24 @@ __device__ __noinline__ void revsort_serial(double* a, int* ib, int n) {
     }
 }
 
-// Ordered (ascending index) sum of the positive entries of r[0..n), identical on every lane.
-// Adding +0.0 to a non-negative partial sum is the identity, so skipping zeros is exact.
+// Ordered (ascending index) sum of r[0..n), identical on every lane: the serial order of R's sum().  Entries are
+// >= +0 and adding +0.0 to a non-negative partial sum is the identity, so zeros are skipped: a chunk of 32 with few
+// positive entries is added through shuffles, a dense chunk by a serial loop over shared memory (broadcast reads).
 __device__ __forceinline__ double warp_ordered_sum_pos(const double* r, int n, int lane) {
     double s = 0.0;
     for (int base = 0; base < n; base += 32) {
         const double v = (base + lane < n) ? r[base + lane] : 0.0;
         unsigned m = __ballot_sync(0xffffffffu, v > 0.0);
-        while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1;
-            s += shfl_d(v, b);
+        if (__popc(m) <= 6) {
+            while (m) {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                s += shfl_d(v, b);
+            }
+        } else {
+            const int e = min(n, base + 32);
+#pragma unroll 4
+            for (int i = base; i < e; ++i) s += r[i];
         }
     }
     return s;
@@ -278,7 +285,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
     __syncthreads();
 
     long long pos = 0, hi = 0;
-    int W = a.w.Wfull, nd = K, da = -1, db = -1;  // nd == K: every column's cached sum is still to be computed
+    int W = a.w.Wfull, nd = K, da = -1, db = -1, gavg = a.w.Wfull;  // nd == K: every column's cached sum is still to be computed
     bool have_spec = false;
     long long prev_end = 0;
     unsigned bar_target = 0;
@@ -295,6 +302,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                 pos = prev_end;
                 hi = pos;
                 nd = 0;
+                gavg = min(2 * gavg + nwin, 1 << 24);
                 W = (2 * W <= a.w.Wunit) ? 2 * W : min(max(2 * W / a.w.Wunit, 1) * a.w.Wunit, a.w.Wfull);
             } else {
                 const long long t = pos + first;
@@ -317,10 +325,15 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                     if (blockIdx.x == 0) a.z[i] = db + 1;
                 }
                 ++movers;
+                // gavg: running estimate of the items between movers.  Under churn the window (and with it the
+                // patch + redraw work of every round) shrinks to a few gaps; results already computed beyond it
+                // are dropped and recomputed when the sweep gets there.
+                gavg = max(1, (3 * gavg + first + 1) / 4);
+                W = (4LL * gavg >= a.w.Wunit) ? (int)min((4LL * gavg / a.w.Wunit) * a.w.Wunit, (long long)a.w.Wfull)
+                                              : max(a.w.Wmin, 4 * gavg);
                 pos = t + 1;
-                hi = prev_end;
+                hi = min(prev_end, pos + W);
                 nd = 2;
-                W = max(a.w.Wmin, min(4 * (first + 1), a.w.Wunit));
                 __syncthreads();
             }
         }
@@ -529,7 +542,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
     __syncthreads();
 
     long long pos = 0, hi = 0, prev_end = 0;
-    int W = a.w.Wfull, nd = 0, da = -1, db = -1;
+    int W = a.w.Wfull, nd = 0, da = -1, db = -1, gavg = a.w.Wfull;
     bool have_spec = false;
     unsigned bar_target = 0;
     long long rounds = 0, units_done = 0, movers = 0;
@@ -543,6 +556,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                 pos = prev_end;
                 hi = pos;
                 nd = 0;
+                gavg = min(2 * gavg + nwin, 1 << 24);
                 W = (2 * W <= a.w.Wunit) ? 2 * W : min(max(2 * W / a.w.Wunit, 1) * a.w.Wunit, a.w.Wfull);
             } else {
                 const long long t = pos + first;
@@ -567,10 +581,15 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                     if (blockIdx.x == 0) a.y[i] = db + 1;
                 }
                 ++movers;
+                // gavg: running estimate of the items between movers.  Under churn the window (and with it the
+                // patch + redraw work of every round) shrinks to a few gaps; results already computed beyond it
+                // are dropped and recomputed when the sweep gets there.
+                gavg = max(1, (3 * gavg + first + 1) / 4);
+                W = (4LL * gavg >= a.w.Wunit) ? (int)min((4LL * gavg / a.w.Wunit) * a.w.Wunit, (long long)a.w.Wfull)
+                                              : max(a.w.Wmin, 4 * gavg);
                 pos = t + 1;
-                hi = prev_end;
+                hi = min(prev_end, pos + W);
                 nd = 2;
-                W = max(a.w.Wmin, min(4 * (first + 1), a.w.Wunit));
                 __syncthreads();
             }
         }
