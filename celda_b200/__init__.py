@@ -130,6 +130,118 @@ def rowSumByGroupChangeSparse(counts, px, group, pgroup, L):
     return px
 
 
+# ------------------------------------------------------------------ src/matrixSums.c (dense twins)
+def _dense_kind(x):
+    x = np.asarray(x)
+    if np.issubdtype(x.dtype, np.integer):
+        return "int", np.int32, _pi
+    return "numeric", np.float64, _pd
+
+
+def _dense_sum(name, x, group, nlevels):
+    kind, dt, ptr = _dense_kind(x)
+    x, group = np.asfortranarray(x, dtype=dt), _i(group)
+    nr, nc = x.shape
+    nl = max(int(nlevels), 0)
+    out = np.zeros((nl, nc) if name == "rowSumByGroup" else (nr, nl), dtype=dt, order="F")
+    check(getattr(lib(), f"celda_{name}_{kind}")(ptr(x), nr, nc, _pi(group), group.size, int(nlevels), ptr(out)))
+    return out
+
+
+def rowSumByGroup_dense(x, group, nlevels):
+    """_rowSumByGroup / _rowSumByGroup_numeric (src/matrixSums.c:5-48,198-236); nlevels < 0 == not a factor."""
+    return _dense_sum("rowSumByGroup", x, group, nlevels)
+
+
+def colSumByGroup_dense(x, group, nlevels):
+    """_colSumByGroup / _colSumByGroup_numeric (src/matrixSums.c:50-93,240-278)."""
+    return _dense_sum("colSumByGroup", x, group, nlevels)
+
+
+def _dense_change(name, x, px, group, pgroup, nlevels, pnlevels):
+    kind, dt, ptr = _dense_kind(x)
+    x, group, pgroup = np.asfortranarray(x, dtype=dt), _i(group), _i(pgroup)
+    if not (px.flags.f_contiguous and px.dtype == dt):
+        raise TypeError("px must be a column-major matrix of the same type as x (it is updated in place)")
+    pnlevels = nlevels if pnlevels is None else pnlevels
+    check(getattr(lib(), f"celda_{name}_{kind}")(ptr(x), x.shape[0], x.shape[1], ptr(px), px.shape[0], px.shape[1],
+                                                 _pi(group), group.size, int(nlevels), _pi(pgroup), pgroup.size,
+                                                 int(pnlevels)))
+    return px
+
+
+def rowSumByGroupChange_dense(x, px, group, pgroup, nlevels, pnlevels=None):
+    """_rowSumByGroupChange[_numeric] (src/matrixSums.c:97-143,282-327); px updated in place."""
+    return _dense_change("rowSumByGroupChange", x, px, group, pgroup, nlevels, pnlevels)
+
+
+def colSumByGroupChange_dense(x, px, group, pgroup, nlevels, pnlevels=None):
+    """_colSumByGroupChange[_numeric] (src/matrixSums.c:147-194,331-379); px updated in place."""
+    return _dense_change("colSumByGroupChange", x, px, group, pgroup, nlevels, pnlevels)
+
+
+# ------------------------------------------------------------------ R/matrixSums.R:1-51 type dispatchers
+def rowSumByGroup(counts, group, L):
+    """.rowSumByGroup: int matrix / numeric matrix -> factor(group, levels = seq(L)) + dense native; dgCMatrix -> sparse."""
+    return rowSumByGroupSparse(counts, group, L) if isinstance(counts, CSC) else rowSumByGroup_dense(counts, group, L)
+
+
+def colSumByGroup(counts, group, K):
+    return colSumByGroupSparse(counts, group, K) if isinstance(counts, CSC) else colSumByGroup_dense(counts, group, K)
+
+
+def rowSumByGroupChange(counts, pcounts, group, pgroup, L):
+    if isinstance(counts, CSC):
+        return rowSumByGroupChangeSparse(counts, pcounts, group, pgroup, L)
+    return rowSumByGroupChange_dense(counts, pcounts, group, pgroup, L)
+
+
+def colSumByGroupChange(counts, pcounts, group, pgroup, K):
+    if isinstance(counts, CSC):
+        return colSumByGroupChangeSparse(counts, pcounts, group, pgroup, K)
+    return colSumByGroupChange_dense(counts, pcounts, group, pgroup, K)
+
+
+# ------------------------------------------------------------------ R/RcppExports.R stubs
+def cG_CalcGibbsProbY(index, counts, nTSbyC, nbyTS, nGbyTS, nbyG, y, L, nG, beta, gamma, delta):
+    """cG_CalcGibbsProbY (src/cG_calcGibbsProbY.cpp:187-249); the lgamma tables are evaluated on the device."""
+    c, t, ts, gt, g, y = _d(counts), _d(nTSbyC), _d(nbyTS), _i(nGbyTS), _d(nbyG), _i(y)
+    out = np.zeros(L)
+    check(lib().celda_cG_CalcGibbsProbY(int(index), _pd(c), c.size, _pd(t), _pd(ts), _pi(gt), _pd(g), _pi(y), L, nG,
+                                        beta, gamma, delta, _pd(out)))
+    return out
+
+
+def fastNormPropLog(counts, alpha):
+    x = _d(counts)
+    out = np.empty_like(x, order="F")
+    check(lib().celda_fastNormPropLog(_pd(x), x.shape[0], x.shape[1], alpha, _pd(out)))
+    return out
+
+
+def eigenMatMultInt(A, B):
+    A, B = _d(A), _i(B)
+    out = np.empty((A.shape[1], B.shape[1]), order="F")
+    check(lib().celda_eigenMatMultInt(_pd(A), A.shape[0], A.shape[1], _pi(B), B.shape[1], _pd(out)))
+    return out
+
+
+def eigenMatMultNumeric(A, B):
+    A, B = _d(A), _d(B)
+    out = np.empty((A.shape[1], B.shape[1]), order="F")
+    check(lib().celda_eigenMatMultNumeric(_pd(A), A.shape[0], A.shape[1], _pd(B), B.shape[1], _pd(out)))
+    return out
+
+
+def perplexityG(x, phi, psi, group, nlevels):
+    """_perplexityG (src/perplexity.c:5-62): sum x log(phi[g(i), j] psi[i, g(i)])."""
+    x, phi, psi, group = _i(x), _d(phi), _d(psi), _i(group)
+    ans = C.c_double(0)
+    check(lib().celda_perplexityG(_pi(x), x.shape[0], x.shape[1], _pd(phi), phi.shape[0], phi.shape[1], _pd(psi),
+                                  psi.shape[0], psi.shape[1], _pi(group), group.size, int(nlevels), C.byref(ans)))
+    return ans.value
+
+
 # ------------------------------------------------------------------ device-resident chain
 class Chain:
     """One chain of .celda_CG / .celda_C / .celda_G with counts and tables resident in HBM (celda_chain_*)."""

@@ -524,6 +524,220 @@ int celda_rowSumByGroupChangeSparse(int nrow, int ncol, const int* p, const int*
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ dense twins
+#define NA_INT_ (-2147483647 - 1)
+static int has_na(const int* g, long long n) {
+    for (long long i = 0; i < n; ++i)
+        if (g[i] == NA_INT_) return 1;
+    return 0;
+}
+static int in_levels(const int* g, long long n, int nl) {
+    for (long long i = 0; i < n; ++i)
+        if (g[i] < 1 || g[i] > nl) return 0;
+    return 1;
+}
+
+}  // extern "C"
+template <typename T>
+static int dense_sum(bool byRow, const T* x, int nr, int nc, const int* group, long long ngroup, int nl, T* ans) {
+    if (nl < 0) return fail("The grouping argument must be a factor");
+    if (byRow && ngroup != nr)
+        return fail("The length of the grouping argument must match the number of rows in the matrix");
+    if (!byRow && ngroup != nc)
+        return fail("The length of the grouping argument must match the number of columns in the matrix");
+    if (has_na(group, ngroup)) return fail("Labels in group and pgroup must not be NA.");
+    if (!in_levels(group, ngroup, nl)) return fail("factor codes of the grouping argument exceed its number of levels");
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    const int sms = num_sms(g_device);
+    const size_t nout = byRow ? (size_t)nl * nc : (size_t)nr * nl;
+    DevBuf<T> dx, dout;
+    DevBuf<int> dg;
+    CELDA_TRY(dx.upload(x, (size_t)nr * nc));
+    CELDA_TRY(dg.upload(group, (size_t)ngroup));
+    CELDA_TRY(dout.alloc(nout));
+    if (byRow) k_dense_rowsum<T><<<grid_for((long long)nout, 128, sms, 16), 128>>>(dx.p, nr, nc, dg.p, nl, dout.p);
+    else k_dense_colsum<T><<<grid_for((long long)nout, 128, sms, 16), 128>>>(dx.p, nr, nc, dg.p, nl, dout.p);
+    count_launch();
+    CELDA_CUDA_OK(cudaGetLastError());
+    CELDA_TRY(dout.download(ans, nout));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+extern "C" {
+
+}  // extern "C"
+template <typename T>
+static int dense_change(bool byRow, const T* x, int nr, int nc, T* px, int px_nr, int px_nc, const int* group,
+                        long long ngroup, int nl, const int* pgroup, long long npgroup, int nlp) {
+    if (nl < 0 || nlp < 0) return fail("The grouping arguments must be factors");
+    if (byRow) {
+        if (nl != nlp || nl != px_nr)
+            return fail("group and pgroup must have the same number of levels equal to row number of px");
+        if (nc != px_nc) return fail("x and the previously summed matrix, px, must have the same number of columns.");
+        if (ngroup != npgroup || ngroup != nr)
+            return fail("group label and previous group label must be the same length as the number of rows in x.");
+    } else {
+        if (nl != nlp || nl != px_nc)
+            return fail("group and pgroup must have the same number of levels equal to column number of px");
+        if (nr != px_nr) return fail("x and the previously summed matrix, pxc must have the same number of rows");
+        if (ngroup != npgroup || ngroup != nc)
+            return fail("group label and previous group label must be the same length as the number of columns in x.");
+    }
+    if (has_na(group, ngroup) || has_na(pgroup, npgroup)) return fail("Labels in group and pgroup must not be NA.");
+    if (!in_levels(group, ngroup, nl) || !in_levels(pgroup, npgroup, nl))
+        return fail("factor codes of the grouping arguments exceed their number of levels");
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    const int sms = num_sms(g_device);
+    const size_t nout = (size_t)px_nr * px_nc;
+    DevBuf<T> dx, dpx;
+    DevBuf<int> dg, dpg;
+    CELDA_TRY(dx.upload(x, (size_t)nr * nc));
+    CELDA_TRY(dpx.upload(px, nout));
+    CELDA_TRY(dg.upload(group, (size_t)ngroup));
+    CELDA_TRY(dpg.upload(pgroup, (size_t)npgroup));
+    if (byRow) k_dense_rowsum_change<T><<<grid_for((long long)nout, 128, sms, 16), 128>>>(dx.p, nr, nc, dpx.p, dg.p, dpg.p, nl);
+    else k_dense_colsum_change<T><<<grid_for((long long)nout, 128, sms, 16), 128>>>(dx.p, nr, nc, dpx.p, dg.p, dpg.p, nl);
+    count_launch();
+    CELDA_CUDA_OK(cudaGetLastError());
+    CELDA_TRY(dpx.download(px, nout));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+extern "C" {
+
+int celda_rowSumByGroup_int(const int* x, int nr, int nc, const int* group, long long ngroup, int nlevels, int* ans) {
+    return dense_sum<int>(true, x, nr, nc, group, ngroup, nlevels, ans);
+}
+int celda_rowSumByGroup_numeric(const double* x, int nr, int nc, const int* group, long long ngroup, int nlevels,
+                                double* ans) {
+    return dense_sum<double>(true, x, nr, nc, group, ngroup, nlevels, ans);
+}
+int celda_colSumByGroup_int(const int* x, int nr, int nc, const int* group, long long ngroup, int nlevels, int* ans) {
+    return dense_sum<int>(false, x, nr, nc, group, ngroup, nlevels, ans);
+}
+int celda_colSumByGroup_numeric(const double* x, int nr, int nc, const int* group, long long ngroup, int nlevels,
+                                double* ans) {
+    return dense_sum<double>(false, x, nr, nc, group, ngroup, nlevels, ans);
+}
+int celda_rowSumByGroupChange_int(const int* x, int nr, int nc, int* px, int px_nr, int px_nc, const int* group,
+                                  long long ngroup, int nlevels, const int* pgroup, long long npgroup, int pnlevels) {
+    return dense_change<int>(true, x, nr, nc, px, px_nr, px_nc, group, ngroup, nlevels, pgroup, npgroup, pnlevels);
+}
+int celda_rowSumByGroupChange_numeric(const double* x, int nr, int nc, double* px, int px_nr, int px_nc,
+                                      const int* group, long long ngroup, int nlevels, const int* pgroup,
+                                      long long npgroup, int pnlevels) {
+    return dense_change<double>(true, x, nr, nc, px, px_nr, px_nc, group, ngroup, nlevels, pgroup, npgroup, pnlevels);
+}
+int celda_colSumByGroupChange_int(const int* x, int nr, int nc, int* px, int px_nr, int px_nc, const int* group,
+                                  long long ngroup, int nlevels, const int* pgroup, long long npgroup, int pnlevels) {
+    return dense_change<int>(false, x, nr, nc, px, px_nr, px_nc, group, ngroup, nlevels, pgroup, npgroup, pnlevels);
+}
+int celda_colSumByGroupChange_numeric(const double* x, int nr, int nc, double* px, int px_nr, int px_nc,
+                                      const int* group, long long ngroup, int nlevels, const int* pgroup,
+                                      long long npgroup, int pnlevels) {
+    return dense_change<double>(false, x, nr, nc, px, px_nr, px_nc, group, ngroup, nlevels, pgroup, npgroup, pnlevels);
+}
+
+// ------------------------------------------------------------------------------------------------ a10 / a9 helpers
+int celda_cG_CalcGibbsProbY(int index, const double* counts, int ncol, const double* nTSbyC, const double* nbyTS,
+                            const int* nGbyTS, const double* nbyG, const int* y, int L, int nG, double beta,
+                            double gamma, double delta, double* probs) {
+    if (index < 1 || index > nG) return fail("'index' must be between 1 and nG");
+    if (y[index - 1] < 1 || y[index - 1] > L) return fail("module label of the indexed feature is out of range");
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    DevBuf<double> dc, dt, dts, dg, dp;
+    DevBuf<int> dgt, dy;
+    CELDA_TRY(dc.upload(counts, ncol));
+    CELDA_TRY(dt.upload(nTSbyC, (size_t)L * ncol));
+    CELDA_TRY(dts.upload(nbyTS, L));
+    CELDA_TRY(dgt.upload(nGbyTS, L));
+    CELDA_TRY(dg.upload(nbyG, nG));
+    CELDA_TRY(dy.upload(y, nG));
+    CELDA_TRY(dp.alloc(L));
+    k_cG_CalcGibbsProbY<<<(L + 63) / 64, 64>>>(index - 1, dc.p, ncol, dt.p, dts.p, dgt.p, dg.p, dy.p, L, beta, gamma,
+                                                delta, dp.p);
+    count_launch();
+    CELDA_CUDA_OK(cudaGetLastError());
+    CELDA_TRY(dp.download(probs, L));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
+int celda_fastNormPropLog(const double* counts, int nr, int nc, double alpha, double* res) {
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    DevBuf<double> dx, dr;
+    DevBuf<int> flag;
+    CELDA_TRY(dx.upload(counts, (size_t)nr * nc));
+    CELDA_TRY(dr.alloc((size_t)nr * nc));
+    CELDA_TRY(flag.alloc(1));
+    CELDA_TRY(flag.zero());
+    k_fastNormPropLog<<<std::max(1, std::min(nc, num_sms(g_device) * 8)), 256>>>(dx.p, nr, nc, alpha, dr.p, flag.p);
+    count_launch();
+    CELDA_CUDA_OK(cudaGetLastError());
+    int f = 0;
+    CELDA_CUDA_OK(cudaMemcpy(&f, flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (f)
+        return fail("Division by 0. Make sure colSums of counts does not contain 0 after rounding counts to integers.");
+    CELDA_TRY(dr.download(res, (size_t)nr * nc));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
+}  // extern "C"
+template <typename TB>
+static int mat_mult_t(const double* A, int n, int k, const TB* B, int m, double* Cm) {
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    DevBuf<double> dA, dC;
+    DevBuf<TB> dB;
+    CELDA_TRY(dA.upload(A, (size_t)n * k));
+    CELDA_TRY(dB.upload(B, (size_t)n * m));
+    CELDA_TRY(dC.alloc((size_t)k * m));
+    k_matMultT<TB><<<grid_for((long long)k * m, 128, num_sms(g_device), 16), 128>>>(dA.p, n, k, dB.p, m, dC.p);
+    count_launch();
+    CELDA_CUDA_OK(cudaGetLastError());
+    CELDA_TRY(dC.download(Cm, (size_t)k * m));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+extern "C" {
+int celda_eigenMatMultInt(const double* A, int n, int k, const int* B, int m, double* Cm) {
+    return mat_mult_t<int>(A, n, k, B, m, Cm);
+}
+int celda_eigenMatMultNumeric(const double* A, int n, int k, const double* B, int m, double* Cm) {
+    return mat_mult_t<double>(A, n, k, B, m, Cm);
+}
+
+int celda_perplexityG(const int* x, int nr, int nc, const double* phi, int phi_nr, int phi_nc, const double* psi,
+                      int psi_nr, int psi_nc, const int* group, long long ngroup, int nlevels, double* ans) {
+    const int nl = nlevels;
+    if (nl < 0) return fail("The grouping argument must be a factor");
+    if (ngroup != nr) return fail("The length of the grouping argument must match the number of rows in the matrix.");
+    if (phi_nc != nc) return fail("The R_phi and R_x must have the same number of colums.");
+    if (phi_nr != nl) return fail("R_phi must have the same number of rows as the number of levels in R_group.");
+    if (psi_nr != nr) return fail("The R_psi and R_x must have the same number of rows.");
+    if (psi_nc != nl) return fail("R_phi must have the same number of columns as the number of levels in R_group.");
+    for (long long i = 0; i < ngroup; ++i)
+        if (group[i] == NA_INT_ || group[i] < 1 || group[i] > nl)
+            return fail("Labels in group and pgroup must not be NA and must less than or equal to the number of rows in the matrix.");
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    DevBuf<int> dx, dg;
+    DevBuf<double> dphi, dpsi, part, out;
+    CELDA_TRY(dx.upload(x, (size_t)nr * nc));
+    CELDA_TRY(dg.upload(group, (size_t)ngroup));
+    CELDA_TRY(dphi.upload(phi, (size_t)phi_nr * phi_nc));
+    CELDA_TRY(dpsi.upload(psi, (size_t)psi_nr * psi_nc));
+    const int NB = 128;
+    CELDA_TRY(part.alloc(NB));
+    CELDA_TRY(out.alloc(1));
+    k_perplexityG<<<NB, 256>>>(dx.p, nr, nc, dphi.p, dpsi.p, dg.p, nl, part.p);
+    k_sum_partials<<<1, 32>>>(part.p, NB, out.p);
+    count_launch(2);
+    CELDA_CUDA_OK(cudaGetLastError());
+    CELDA_TRY(out.download(ans, 1));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ chain
 int celda_chain_create(celda_chain** out, int device, int model, int nG, int nM, const int* p, const int* i,
                        const double* x, const int* s, int nS, int K, int L, double alpha, double beta, double delta,

@@ -370,3 +370,188 @@ __global__ void k_loglik_final(LLArgs a) {
 }
 
 }  // namespace celda
+
+namespace celda {
+
+// ---------------------------------------------------------------------------------------------- dense twins
+// src/matrixSums.c.  One thread per OUTPUT element, gathering its contributions in the reference's loop order
+// (ascending row / column index), so results are bit-identical for arbitrary doubles, not only integer-valued
+// ones, and the int32 variants wrap like the reference's int arithmetic.
+template <typename T> struct AccOf { using type = T; };
+template <> struct AccOf<int> { using type = unsigned; };
+
+// _rowSumByGroup[_numeric] (:5-48, :198-236): ans[nl x nc], ans[g(i), j] += x[i, j]
+template <typename T>
+__global__ void k_dense_rowsum(const T* __restrict__ x, int nr, int nc, const int* __restrict__ group, int nl,
+                               T* __restrict__ ans) {
+    using A = typename AccOf<T>::type;
+    const long long n = (long long)nl * nc;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)(q % nl) + 1;
+        const long long j = q / nl;
+        A acc = 0;
+        for (int i = 0; i < nr; ++i)
+            if (group[i] == l) acc += (A)x[j * nr + i];
+        ans[q] = (T)acc;
+    }
+}
+
+// _colSumByGroup[_numeric] (:50-93, :240-278): ans[nr x nl], ans[i, g(j)] += x[i, j]
+template <typename T>
+__global__ void k_dense_colsum(const T* __restrict__ x, int nr, int nc, const int* __restrict__ group, int nl,
+                               T* __restrict__ ans) {
+    using A = typename AccOf<T>::type;
+    const long long n = (long long)nr * nl;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(q % nr), l = (int)(q / nr) + 1;
+        A acc = 0;
+        for (int j = 0; j < nc; ++j)
+            if (group[j] == l) acc += (A)x[(long long)j * nr + i];
+        ans[q] = (T)acc;
+    }
+}
+
+// _rowSumByGroupChange[_numeric] (:97-143, :282-327): px[nl x nc] in place
+template <typename T>
+__global__ void k_dense_rowsum_change(const T* __restrict__ x, int nr, int nc, T* __restrict__ px,
+                                      const int* __restrict__ group, const int* __restrict__ pgroup, int nl) {
+    using A = typename AccOf<T>::type;
+    const long long n = (long long)nl * nc;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const int l = (int)(q % nl) + 1;
+        const long long j = q / nl;
+        A acc = (A)px[q];
+        for (int i = 0; i < nr; ++i) {
+            const int g = group[i], pg = pgroup[i];
+            if (g != pg) {
+                if (pg == l) acc -= (A)x[j * nr + i];
+                if (g == l) acc += (A)x[j * nr + i];
+            }
+        }
+        px[q] = (T)acc;
+    }
+}
+
+// _colSumByGroupChange[_numeric] (:147-194, :331-379): px[nr x nl] in place
+template <typename T>
+__global__ void k_dense_colsum_change(const T* __restrict__ x, int nr, int nc, T* __restrict__ px,
+                                      const int* __restrict__ group, const int* __restrict__ pgroup, int nl) {
+    using A = typename AccOf<T>::type;
+    const long long n = (long long)nr * nl;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(q % nr), l = (int)(q / nr) + 1;
+        A acc = (A)px[q];
+        for (int j = 0; j < nc; ++j) {
+            const int g = group[j], pg = pgroup[j];
+            if (g != pg) {
+                if (g == l) acc += (A)x[(long long)j * nr + i];
+                if (pg == l) acc -= (A)x[(long long)j * nr + i];
+            }
+        }
+        px[q] = (T)acc;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- a10 single gene
+// cG_CalcGibbsProbY (src/cG_calcGibbsProbY.cpp:187-249) for one gene: one thread per module, the column loop
+// and the six trailing terms in the reference's order.  Table look-ups lg_beta[k] etc. are evaluated directly.
+__global__ void k_cG_CalcGibbsProbY(int index0, const double* __restrict__ counts, int ncol,
+                                    const double* __restrict__ nTSbyC, const double* __restrict__ nbyTS,
+                                    const int* __restrict__ nGbyTS, const double* __restrict__ nbyG,
+                                    const int* __restrict__ y, int L, double beta, double gamma, double delta,
+                                    double* __restrict__ probs) {
+    const int cur = y[index0] - 1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) {
+        double p = 0.0;
+        for (int col = 0; col < ncol; ++col) {
+            const double t = nTSbyC[(size_t)col * L + i], c = counts[col];
+            if (i == cur) {
+                p += dlgamma_hot((double)(long long)t + beta);
+                p -= dlgamma_hot((double)(long long)(t - c) + beta);
+            } else {
+                p += dlgamma_hot((double)(long long)(t + c) + beta);
+                p -= dlgamma_hot((double)(long long)t + beta);
+            }
+        }
+        const int g = nGbyTS[i];
+        if (i == cur) {
+            p += dlgamma_hot((double)g + gamma);
+            p -= dlgamma_hot((double)(g - 1) + gamma);
+            p += dlgamma_hot((double)g * delta);
+            p -= dlgamma_hot((double)(g - 1) * delta);
+            p += dlgamma_hot(nbyTS[i] - nbyG[index0] + (double)(g - 1) * delta);
+            p -= dlgamma_hot(nbyTS[i] + (double)g * delta);
+        } else {
+            p += dlgamma_hot((double)(g + 1) + gamma);
+            p -= dlgamma_hot((double)g + gamma);
+            p += dlgamma_hot((double)(g + 1) * delta);
+            p -= dlgamma_hot((double)g * delta);
+            p += dlgamma_hot(nbyTS[i] + (double)g * delta);
+            p -= dlgamma_hot(nbyTS[i] + nbyG[index0] + (double)(g + 1) * delta);
+        }
+        probs[i] = p;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- a9 helpers
+// fastNormPropLog (src/matrixNorm.cpp:36-52): res = log((x + a) / (colSum + nrow a)); one block per column,
+// the column sum added serially by thread 0 (Rcpp sugar colSums order).  flag |= 1 on a zero denominator.
+__global__ void k_fastNormPropLog(const double* __restrict__ x, int nr, int nc, double a, double* __restrict__ res,
+                                  int* flag) {
+    __shared__ double s_den;
+    for (int j = blockIdx.x; j < nc; j += gridDim.x) {
+        if (threadIdx.x == 0) {
+            double cs = 0.0;
+            for (int i = 0; i < nr; ++i) cs += x[(size_t)j * nr + i];
+            s_den = cs + (double)nr * a;
+            if (s_den == 0.0) atomicOr(flag, 1);
+        }
+        __syncthreads();
+        const double den = s_den;
+        for (int i = threadIdx.x; i < nr; i += blockDim.x)
+            res[(size_t)j * nr + i] = dlog((x[(size_t)j * nr + i] + a) / den);
+        __syncthreads();
+    }
+}
+
+// eigenMatMultInt / eigenMatMultNumeric (src/eigenMatMultInt.cpp:11-26): C = t(A) %*% B, A n x k, B n x m, C k x m.
+// One thread per output element, serial dot product over n (unfused multiply-add).
+template <typename TB>
+__global__ void k_matMultT(const double* __restrict__ A, int n, int k, const TB* __restrict__ B, int m,
+                           double* __restrict__ Cm) {
+    const long long tot = (long long)k * m;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < tot; q += (long long)gridDim.x * blockDim.x) {
+        const int a = (int)(q % k);
+        const long long c = q / k;
+        double acc = 0.0;
+        for (int r = 0; r < n; ++r) acc += A[(size_t)a * n + r] * (double)B[c * n + r];
+        Cm[q] = acc;
+    }
+}
+
+// _perplexityG (src/perplexity.c:51-55): sum_ij x[i,j] log(phi[g(i), j] psi[i, g(i)]); per-block partials
+__global__ void k_perplexityG(const int* __restrict__ x, int nr, int nc, const double* __restrict__ phi,
+                              const double* __restrict__ psi, const int* __restrict__ group, int nl,
+                              double* __restrict__ partial) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    const long long n = (long long)nr * nc;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(q % nr);
+        const long long j = q / nr;
+        const int g = group[i] - 1;
+        acc += (double)x[q] * dlog(phi[j * nl + g] * psi[(size_t)nr * g + i]);
+    }
+    const double s = block_sum(acc, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__global__ void k_sum_partials(const double* __restrict__ partial, int n, double* out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < n; ++i) s += partial[i];
+        *out = s;
+    }
+}
+
+}  // namespace celda

@@ -51,7 +51,6 @@ int celda_rowSumByGroupChangeSparse(int nrow, int ncol, const int *p, const int 
                                     double *px, int px_ncol, const int *group, long long ngroup,
                                     const int *pgroup, long long npgroup, int L);
 
-#ifdef CELDA_CUDA_PLANNED /* declared for the next milestone; not exported yet */
 /* ---- a2-a5 dense twins  (src/matrixSums.c) ---------------------------------------------------
  * `nlevels` stands for nlevels(group); pass a negative value for "group is not a factor".
  * replaces _rowSumByGroup / _rowSumByGroup_numeric                 src/matrixSums.c:5-48,198-236   */
@@ -93,6 +92,7 @@ int celda_eigenMatMultNumeric(const double *A, int n, int k, const double *B, in
 int celda_perplexityG(const int *x, int nr, int nc, const double *phi, int phi_nr, int phi_nc, const double *psi,
                       int psi_nr, int psi_nc, const int *group, long long ngroup, int nlevels, double *ans);
 
+#ifdef CELDA_CUDA_PLANNED /* declared for the next milestone; not exported yet */
 /* ---- a13: collapsed log-likelihoods -----------------------------------------------------------
  * replaces .cCGCalcLL  R/celda_CG.R:839-888 ; .cCCalcLL  R/celda_C.R:760-788 ; .cGCalcLL  R/celda_G.R:664-702 */
 int celda_cCGCalcLL(int K, int L, const int *mCPByS, const double *nTSByCP, const double *nByG, int nGenes,
