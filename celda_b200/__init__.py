@@ -291,6 +291,18 @@ class Chain:
         ix, u = _i(ix), _d(u)
         check(lib().celda_chain_sweep_z_gibbs(self._h, _pi(ix), _pd(u), int(doSample)))
 
+    def sweep_z_em(self, doSample=True):
+        """.cCCalcEMProbZ (R/celda_C.R:717-756) + re-decomposition."""
+        check(lib().celda_chain_sweep_z_em(self._h, int(doSample)))
+
+    def iterate_em(self, ix_y=None, u_y=None):
+        """One iteration with algorithm = "EM" (celda_C: EM z + LL; celda_CG: y Gibbs sweep + EM z + LL)."""
+        ll = C.c_double(0)
+        ix_y = None if ix_y is None else _i(ix_y)
+        u_y = None if u_y is None else _d(u_y)
+        check(lib().celda_chain_iterate_em(self._h, _pi(ix_y), _pd(u_y), C.byref(ll)))
+        return ll.value
+
     def iterate(self, ix_y, u_y, ix_z, u_z):
         """One iteration of R/celda_CG.R:543-602 (no split heuristics); returns the log-likelihood."""
         ll = C.c_double(0)

@@ -56,6 +56,8 @@ struct celda_chain {
     DevBuf<int> ixy, ixz;
     DevBuf<double> uy, uz;
     DevBuf<double> llPartial, llOut;
+    DevBuf<double> phiBuf, thetaBuf;  // EM step
+    DevBuf<int> emFlag;
     // staged draws
     int staged_iters = 0;
     DevBuf<int> st_ixy, st_ixz;
@@ -199,6 +201,14 @@ int chain_loglik_async(celda_chain* h) {
         a.npG = NB;
         off = NB;
     }
+    if (h->model == CELDA_MODEL_C) {
+        // phi over nGByCP (gene-major [nG][K]): numerator in fixed blocks, denominator one serial column sum per k
+        k_sum_lgamma<int><<<NB, 256, 0, st>>>(h->nGByCP.p, (long long)h->nG * h->K, h->beta, h->llPartial.p + off);
+        k_ll_phi_den_genemajor<<<1, 256, 0, st>>>(h->nGByCP.p, h->nG, h->K, h->beta, h->llPartial.p + off + NB);
+        a.npPhiB = NB;
+        a.npPhiD = 1;
+        count_launch(2);
+    }
     if (h->model == CELDA_MODEL_G) {
         const int NBG = 256;
         k_sum_lgamma<int><<<NBG, 256, 0, st>>>(h->nTSByC.p, (long long)h->L * h->nM, h->beta, h->llPartial.p + off);
@@ -325,6 +335,60 @@ int chain_step_z(celda_chain* h, const int* d_ix, const double* d_u, int doSampl
         count_launch();
     }
     CELDA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+// EM z step (.cCCalcEMProbZ, R/celda_C.R:717-756) + re-decomposition (.cCReDecomposeCounts :825-839; in celda_CG
+// additionally nGByCP <- colSumByGroupChange, R/celda_CG.R:584).  celda_C: counts = the CSC; celda_CG: counts =
+// nTSByC (dense L x nM) against nTSByCP.
+int chain_step_z_em(celda_chain* h, int doSample) {
+    if (h->model == CELDA_MODEL_G) return fail("sweep_z_em: celda_G has no cell populations");
+    ProfScope ps(h, 2);
+    cudaStream_t st = h->st;
+    const bool isC = h->model == CELDA_MODEL_C;
+    const int R = isC ? h->nG : h->L, K = h->K;
+    CELDA_TRY(h->emFlag.zero(st));
+    k_em_phi<<<grid_for((long long)R * K, 256, h->sms), 256, 0, st>>>(isC ? h->nGByCP.p : h->nTSByCP.p, isC, R, K, h->nCP.p,
+                                                                      h->beta, h->phiBuf.p, h->emFlag.p);
+    k_em_theta<<<std::min(h->nS, 1024), 64, 0, st>>>(h->mCPByS.p, K, h->nS, h->alpha, h->thetaBuf.p, h->emFlag.p);
+    CELDA_CUDA_OK(cudaMemcpyAsync(h->zprev.p, h->z.p, sizeof(int) * h->nM, cudaMemcpyDeviceToDevice, st));
+    const int threads = 256, nwarp = threads / 32;
+    const int grid = (int)std::min<long long>(((long long)h->nM + nwarp - 1) / nwarp, (long long)h->sms * 32);
+    if (isC)
+        k_em_probs<true><<<grid, threads, 0, st>>>(R, h->nM, K, h->cp.p, h->ci.p, h->cx.p, h->phiBuf.p, h->thetaBuf.p, h->s.p,
+                                                  h->probsZ.p, doSample ? h->z.p : nullptr);
+    else
+        k_em_probs<false><<<grid, threads, 0, st>>>(R, h->nM, K, nullptr, nullptr, h->nTSByC.p, h->phiBuf.p, h->thetaBuf.p,
+                                                   h->s.p, h->probsZ.p, doSample ? h->z.p : nullptr);
+    count_launch(3);
+    if (doSample) {
+        if (!isC) {
+            k_colsum_change_dense<<<grid_for((long long)h->L * h->nM, 256, h->sms), 256, 0, st>>>(h->nTSByC.p, h->L, h->nM, h->z.p,
+                                                                                               h->zprev.p, h->nTSByCP.p);
+            k_colsums_small<<<1, 256, 0, st>>>(h->nTSByCP.p, h->L, K, h->nCP.p);
+            count_launch(2);
+        }
+        k_colsum_change_csc<int><<<std::min((h->nM + nwarp - 1) / nwarp, h->sms * 16), threads, 0, st>>>(
+            h->nM, h->cp.p, h->ci.p, h->cx.p, h->z.p, h->zprev.p, K, h->nGByCP.p);
+        if (isC) {
+            CELDA_TRY(h->nCP.zero(st));
+            k_colsums_genemajor<<<grid_for((long long)h->nG * K, 256, h->sms), 256, 0, st>>>(h->nGByCP.p, h->nG, K,
+                                                                                          (unsigned long long*)h->nCP.p);
+            count_launch();
+        }
+        CELDA_TRY(h->mCPByS.zero(st));
+        k_table_zs<<<grid_for(h->nM, 256, h->sms), 256, 0, st>>>(h->z.p, h->s.p, h->nM, K, h->mCPByS.p);
+        count_launch(2);
+    }
+    CELDA_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int chain_check_em_flag(celda_chain* h) {
+    int f = 0;
+    CELDA_CUDA_OK(cudaMemcpyAsync(&f, h->emFlag.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CELDA_TRY(chain_sync(h));
+    if (f) return fail("Division by 0. Make sure colSums of counts does not contain 0 after rounding counts to integers.");
     return 0;
 }
 
@@ -842,6 +906,9 @@ int celda_chain_create(celda_chain** out, int device, int model, int nG, int nM,
     CELDA_TRY(h->ixz.alloc(nM));
     CELDA_TRY(h->uz.alloc(nM));
     CELDA_TRY(h->llPartial.alloc(1024));
+    CELDA_TRY(h->phiBuf.alloc((size_t)std::max(nG, h->L) * h->K));
+    CELDA_TRY(h->thetaBuf.alloc((size_t)h->K * h->nS));
+    CELDA_TRY(h->emFlag.alloc(1));
     CELDA_TRY(h->llOut.alloc(1));
     CELDA_CUDA_OK(cudaStreamSynchronize(st));
     CELDA_CUDA_OK(cudaGetLastError());
@@ -903,7 +970,6 @@ int celda_chain_sweep_z_gibbs(celda_chain* h, const int* ix, const double* u, in
 int celda_chain_loglik(celda_chain* h, double* ll) {
     CELDA_CUDA_OK(cudaSetDevice(h->device));
     if (!h->has_state) return fail("set_state must be called first");
-    if (h->model == CELDA_MODEL_C) return fail("loglik: celda_C chain not implemented yet");
     CELDA_TRY(chain_loglik_async(h));
     CELDA_CUDA_OK(cudaMemcpyAsync(ll, h->llOut.p, sizeof(double), cudaMemcpyDeviceToHost, h->st));
     return chain_sync(h);
@@ -925,6 +991,33 @@ int celda_chain_iterate(celda_chain* h, const int* ix_y, const double* u_y, cons
     CELDA_TRY(chain_step_z(h, h->ixz.p, h->uz.p, 1));
     CELDA_TRY(chain_loglik_async(h));
     CELDA_CUDA_OK(cudaMemcpyAsync(ll, h->llOut.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    return chain_check_status(h);
+}
+
+int celda_chain_sweep_z_em(celda_chain* h, int doSample) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (!h->has_state) return fail("set_state must be called first");
+    CELDA_TRY(chain_step_z_em(h, doSample));
+    return chain_check_em_flag(h);
+}
+
+// One iteration with the EM z step (algorithm = "EM"): celda_C -- .cCCalcEMProbZ then .cCCalcLL (R/celda_C.R:427-449);
+// celda_CG -- y Gibbs sweep, rowSumByGroupChange, EM z step, colSumByGroupChange, .cCGCalcLL (R/celda_CG.R:543-602).
+int celda_chain_iterate_em(celda_chain* h, const int* ix_y, const double* u_y, double* ll) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (!h->has_state) return fail("set_state must be called first");
+    if (h->model == CELDA_MODEL_G) return fail("iterate_em: celda_G has no cell populations");
+    if (h->model == CELDA_MODEL_CG) {
+        if (!ix_y || !u_y) return fail("iterate_em: injected order and uniforms are required for the y sweep");
+        CELDA_TRY(validate_order(ix_y, h->nG, "ix_y"));
+        CELDA_CUDA_OK(cudaMemcpyAsync(h->ixy.p, ix_y, sizeof(int) * h->nG, cudaMemcpyHostToDevice, h->st));
+        CELDA_CUDA_OK(cudaMemcpyAsync(h->uy.p, u_y, sizeof(double) * h->nG, cudaMemcpyHostToDevice, h->st));
+        CELDA_TRY(chain_step_y(h, h->ixy.p, h->uy.p, 1));
+    }
+    CELDA_TRY(chain_step_z_em(h, 1));
+    CELDA_TRY(chain_loglik_async(h));
+    CELDA_CUDA_OK(cudaMemcpyAsync(ll, h->llOut.p, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CELDA_TRY(chain_check_em_flag(h));
     return chain_check_status(h);
 }
 

@@ -555,3 +555,113 @@ __global__ void k_sum_partials(const double* __restrict__ partial, int n, double
 }
 
 }  // namespace celda
+
+namespace celda {
+
+// ---------------------------------------------------------------------------------------------- EM z step (a9)
+// .cCCalcEMProbZ (R/celda_C.R:717-756).  phi is laid out [R][K] (row r's K log-probabilities contiguous) so that
+// the lanes of a warp (one lane per population) read it coalesced.
+
+// phi[r][k] = log((n[r,k] + beta) / (nCP[k] + R beta)); n is gene-major [R][K] (rowMajor) or column-major R x K.
+// flag |= 1 on a zero denominator (fastNormPropLog's "Division by 0" error, src/matrixNorm.cpp:44-46).
+__global__ void k_em_phi(const int* __restrict__ n, bool rowMajor, int R, int K, const long long* __restrict__ nCP,
+                         double beta, double* __restrict__ phi, int* flag) {
+    const long long tot = (long long)R * K;
+    const double atot = (double)R * beta;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < tot; q += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(q / K), k = (int)(q % K);
+        const double den = (double)nCP[k] + atot;
+        if (den == 0.0) atomicOr(flag, 1);
+        const int v = rowMajor ? n[q] : n[(size_t)k * R + r];
+        phi[q] = dlog(((double)v + beta) / den);
+    }
+}
+
+// theta[k, s] = log((m[k,s] + alpha) / (colSum_s + K alpha)), K x nS column-major
+__global__ void k_em_theta(const int* __restrict__ m, int K, int nS, double alpha, double* __restrict__ theta, int* flag) {
+    for (int s = blockIdx.x; s < nS; s += gridDim.x) {
+        double cs = 0.0;
+        for (int k = 0; k < K; ++k) cs += (double)m[(size_t)s * K + k];
+        const double den = cs + (double)K * alpha;
+        if (den == 0.0 && threadIdx.x == 0) atomicOr(flag, 1);
+        for (int k = threadIdx.x; k < K; k += blockDim.x) theta[(size_t)s * K + k] = dlog(((double)m[(size_t)s * K + k] + alpha) / den);
+    }
+}
+
+// probs[, c] = t(phi) %*% counts[, c] + theta[, s_c] and which.max (first maximum), one warp per cell, lane k (+32q)
+// per population, the stored entries of the column added serially in storage order (unfused multiply, add).
+// SPARSE: counts is the CSC (ri, xv); else a dense int32 R x nM column-major matrix.
+template <bool SPARSE>
+__global__ void k_em_probs(int R, long long nM, int K, const int* __restrict__ p, const int* __restrict__ ri,
+                           const int* __restrict__ xv, const double* __restrict__ phi, const double* __restrict__ theta,
+                           const int* __restrict__ s, double* __restrict__ probs, int* __restrict__ znew) {
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int KPL = 8;  // populations per lane: K <= 256
+    for (long long c = blockIdx.x * (long long)nwarp + warp; c < nM; c += (long long)gridDim.x * nwarp) {
+        double acc[KPL];
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) acc[q] = 0.0;
+        if (SPARSE) {
+            const int e = p[c + 1];
+            for (int t = p[c]; t < e; ++t) {
+                const double x = (double)xv[t];
+                const double* row = phi + (size_t)ri[t] * K;
+#pragma unroll
+                for (int q = 0; q < KPL; ++q) {
+                    const int k = lane + 32 * q;
+                    if (k < K) acc[q] += row[k] * x;
+                }
+            }
+        } else {
+            const int* col = xv + c * R;
+            for (int r = 0; r < R; ++r) {
+                const double x = (double)col[r];
+                const double* row = phi + (size_t)r * K;
+#pragma unroll
+                for (int q = 0; q < KPL; ++q) {
+                    const int k = lane + 32 * q;
+                    if (k < K) acc[q] += row[k] * x;
+                }
+            }
+        }
+        const double* th = theta + (size_t)(s[c] - 1) * K;
+        double bv = -__longlong_as_double(0x7ff0000000000000LL);
+        int bi = 0x7fffffff;
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) {
+            const int k = lane + 32 * q;
+            if (k < K) {
+                const double v = acc[q] + th[k];
+                if (probs) probs[c * K + k] = v;
+                if (v > bv) {  // ascending k within the lane: strict > keeps the first maximum
+                    bv = v;
+                    bi = k;
+                }
+            }
+        }
+        for (int o = 16; o; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > bv || (ov == bv && oi < bi)) {
+                bv = ov;
+                bi = oi;
+            }
+        }
+        if (znew && lane == 0) znew[c] = (bi == 0x7fffffff ? 0 : bi) + 1;
+    }
+}
+
+// sum over k of lgamma(colSum_k(n + beta)) for a gene-major [R][K] table, columns added serially (R/celda_C.R:783)
+__global__ void k_ll_phi_den_genemajor(const int* __restrict__ n, int R, int K, double beta, double* __restrict__ out) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        double cs = 0.0;
+        for (int r = 0; r < R; ++r) cs += (double)n[(size_t)r * K + k] + beta;
+        acc += dlgamma(cs);
+    }
+    const double s = block_sum(acc, red);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+}  // namespace celda

@@ -142,8 +142,10 @@ int celda_chain_get_state(celda_chain *h, int *z, int *y);
 /* Sweeps with injected order/uniforms (host pointers) ... */
 int celda_chain_sweep_y(celda_chain *h, const int *ix, const double *u, int doSample);
 int celda_chain_sweep_z_gibbs(celda_chain *h, const int *ix, const double *u, int doSample);
-#ifdef CELDA_CUDA_PLANNED
+/* EM z step (.cCCalcEMProbZ, R/celda_C.R:717-756) and one EM-mode iteration of the chain loop. */
 int celda_chain_sweep_z_em(celda_chain *h, int doSample);
+int celda_chain_iterate_em(celda_chain *h, const int *ix_y, const double *u_y, double *ll);
+#ifdef CELDA_CUDA_PLANNED
 /* ... or with the device Philox4x32-10 generator: order = argsort of Philox keys, one uniform per step. */
 int celda_chain_seed(celda_chain *h, unsigned long long seed, unsigned long long stream);
 int celda_chain_sweep_y_philox(celda_chain *h, int doSample);
