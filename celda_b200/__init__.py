@@ -242,6 +242,71 @@ def perplexityG(x, phi, psi, group, nlevels):
     return ans.value
 
 
+# ------------------------------------------------------------------ R closures at sweep granularity
+def cCCalcGibbsProbZ(counts, mCPByS, nGByCP, nByC, nCP, z, s, K, nG, nM, alpha, beta, ix, u, doSample=True):
+    """.cCCalcGibbsProbZ (R/celda_C.R:620-714) on a dense nG x nM matrix (nTSByC in celda_CG) with the visiting order
+    `ix` and uniforms `u` injected.  Returns list(mCPByS, nGByCP, nCP, z, probs) like the reference (inputs copied)."""
+    counts = _d(counts)
+    m, n, nbc, ncp, z, s = _i(mCPByS).copy(order="F"), _d(nGByCP).copy(order="F"), _d(nByC), _d(nCP).copy(), \
+        _i(z).copy(), _i(s)
+    ix, u = _i(ix), _d(u)
+    probs = np.full((K, nM), np.nan, order="F")
+    check(lib().celda_cCCalcGibbsProbZ(_pd(counts), _pi(m), m.shape[1], _pd(n), _pd(nbc), _pd(ncp), _pi(z), _pi(s), K, nG,
+                                       nM, alpha, beta, int(doSample), _pi(ix), _pd(u), _pd(probs)))
+    return dict(mCPByS=m, nGByCP=n, nCP=ncp, z=z, probs=probs)
+
+
+def cCCalcEMProbZ(counts, mCPByS, nGByCP, nByC, nCP, z, s, K, nG, nM, alpha, beta, doSample=True):
+    """.cCCalcEMProbZ (R/celda_C.R:717-756); counts: CSC (dgCMatrix) or a dense matrix."""
+    m, n, ncp, z, s = _i(mCPByS).copy(order="F"), _d(nGByCP).copy(order="F"), _d(nCP).copy(), _i(z).copy(), _i(s)
+    probs = np.zeros((K, nM), order="F")
+    if isinstance(counts, CSC):
+        args = (_pi(counts.p), _pi(counts.i), _pd(counts.x))
+    else:
+        dense = _d(counts)
+        args = (None, None, _pd(dense))
+    check(lib().celda_cCCalcEMProbZ(nG, nM, *args, _pi(m), m.shape[1], _pd(n), _pd(ncp), _pi(z), _pi(s), K, alpha, beta,
+                                    int(doSample), _pd(probs)))
+    return dict(mCPByS=m, nGByCP=n, nCP=ncp, z=z, probs=probs)
+
+
+def cGCalcGibbsProbY(counts, nTSByC, nByTS, nGByTS, nByG, y, L, nG, beta, delta, gamma, ix, u, doSample=True):
+    """.cGCalcGibbsProbY (R/celda_G.R:602-660) on a dense nG x ncol matrix (nGByCP in celda_CG).  The lgbeta /
+    lggamma / lgdelta tables of the reference are evaluated on the device (value-identical)."""
+    counts = _d(counts)
+    t, ts, gt, g, y = _d(nTSByC).copy(order="F"), _d(nByTS).copy(), _i(nGByTS).copy(), _d(nByG), _i(y).copy()
+    ix, u = _i(ix), _d(u)
+    probs = np.full((L, nG), np.nan, order="F")
+    check(lib().celda_cGCalcGibbsProbY(_pd(counts), counts.shape[1], _pd(t), _pd(ts), _pi(gt), _pd(g), _pi(y), L, nG,
+                                       beta, delta, gamma, int(doSample), _pi(ix), _pd(u), _pd(probs)))
+    return dict(nTSByC=t, nGByTS=gt, nByTS=ts, y=y, probs=probs)
+
+
+def cCGCalcLL(K, L, mCPByS, nTSByCP, nByG, nByTS, nGByTS, nS, nG, alpha, beta, delta, gamma):
+    """.cCGCalcLL (R/celda_CG.R:839-888)."""
+    m, t, g, ts, gt = _i(mCPByS), _d(nTSByCP), _d(nByG), _d(nByTS), _i(nGByTS)
+    ll = C.c_double(0)
+    check(lib().celda_cCGCalcLL(K, L, _pi(m), _pd(t), _pd(g), g.size, _pd(ts), _pi(gt), nS, alpha, beta, delta, gamma,
+                                C.byref(ll)))
+    return ll.value
+
+
+def cCCalcLL(mCPByS, nGByCP, s, z, K, nS, nG, alpha, beta):
+    """.cCCalcLL (R/celda_C.R:760-788); s and z are unused by the reference formula, kept for the signature."""
+    m, n = _i(mCPByS), _d(nGByCP)
+    ll = C.c_double(0)
+    check(lib().celda_cCCalcLL(_pi(m), _pd(n), K, nS, nG, alpha, beta, C.byref(ll)))
+    return ll.value
+
+
+def cGCalcLL(nTSByC, nByTS, nByG, nGByTS, nM, nG, L, beta, delta, gamma):
+    """.cGCalcLL (R/celda_G.R:664-702)."""
+    t, ts, g, gt = _d(nTSByC), _d(nByTS), _d(nByG), _i(nGByTS)
+    ll = C.c_double(0)
+    check(lib().celda_cGCalcLL(_pd(t), _pd(ts), _pd(g), g.size, _pi(gt), nM, L, beta, delta, gamma, C.byref(ll)))
+    return ll.value
+
+
 # ------------------------------------------------------------------ device-resident chain
 class Chain:
     """One chain of .celda_CG / .celda_C / .celda_G with counts and tables resident in HBM (celda_chain_*)."""

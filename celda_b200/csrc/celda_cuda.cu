@@ -36,6 +36,28 @@ int check_labels_host(const int* g, long long n, int K, const char* what, const 
 
 }  // namespace
 
+// Work space of the sweep kernels (ring buffers, speculation flags, barrier, status, statistics).
+struct SweepBufs {
+    DevBuf<double> bufP, bufA, colsum, lgnCP;
+    DevBuf<int> spec, status;
+    DevBuf<unsigned> barrier;
+    DevBuf<long long> stats;  // [which][8]
+    int Wmax = 8192, Wmin = 32, lgT = 2048;
+    int alloc(int ncand, cudaStream_t st) {
+        CELDA_TRY(bufP.alloc((size_t)Wmax * ncand));
+        CELDA_TRY(bufA.alloc((size_t)Wmax * ncand));
+        CELDA_TRY(spec.alloc(Wmax));
+        CELDA_TRY(colsum.alloc(ncand));
+        CELDA_TRY(lgnCP.alloc(ncand));
+        CELDA_TRY(status.alloc(1));
+        CELDA_TRY(status.zero(st));
+        CELDA_TRY(barrier.alloc(1));
+        CELDA_TRY(stats.alloc(40));
+        CELDA_TRY(stats.zero(st));
+        return 0;
+    }
+};
+
 // ================================================================================================ chain
 struct celda_chain {
     int device = 0, model = 0, nG = 0, nM = 0, nS = 0, K = 0, L = 0, sms = 148;
@@ -48,11 +70,7 @@ struct celda_chain {
     DevBuf<int> nTSByC, nGByCP, nTSByCP, nByC, nGByTS, mCPByS;
     DevBuf<long long> nCP, nByG, nByTS;
     DevBuf<double> probsZ, probsY;
-    // sweep work space
-    DevBuf<double> bufP, bufA, colsum, lgnCP;
-    DevBuf<int> spec, status;
-    DevBuf<unsigned> barrier;
-    DevBuf<long long> stats;  // [which][3]
+    SweepBufs wb;  // sweep work space
     DevBuf<int> ixy, ixz;
     DevBuf<double> uy, uz;
     DevBuf<double> llPartial, llOut;
@@ -62,7 +80,6 @@ struct celda_chain {
     int staged_iters = 0;
     DevBuf<int> st_ixy, st_ixz;
     DevBuf<double> st_uy, st_uz;
-    int Wmax = 8192, Wmin = 32, lgT = 2048;
     int npG = 0;
     // profiling
     bool profile = false;
@@ -122,15 +139,13 @@ int chain_sync(celda_chain* h) {
     return 0;
 }
 
+int sweep_status(int stv);
+
 int chain_check_status(celda_chain* h) {
     int stv = 0;
-    CELDA_CUDA_OK(cudaMemcpyAsync(&stv, h->status.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CELDA_CUDA_OK(cudaMemcpyAsync(&stv, h->wb.status.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CELDA_TRY(chain_sync(h));
-    if (stv == -1) return fail("sample.int would take the Walker alias branch (> 200 likely categories): not supported");
-    if (stv == -2) return fail("NA in probability vector");
-    if (stv == -3) return fail("too few positive probabilities");
-    if (stv) return fail("sweep failed with status %d", stv);
-    return 0;
+    return sweep_status(stv);
 }
 
 // ---- decompose (R/celda_CG.R:902-934, R/celda_C.R:800-822, R/celda_G.R:712-733)
@@ -173,46 +188,53 @@ int chain_decompose(celda_chain* h) {
     return 0;
 }
 
-int chain_loglik_async(celda_chain* h) {
-    ProfScope ps(h, 4);
-    cudaStream_t st = h->st;
+// Log-likelihood from device-resident integer tables (shared by the chain handle and the stateless entry points).
+struct LLIn {
+    int model, K, L, nS, nG;
+    long long nM;
+    const int *mCPByS, *nTSByCP, *nGByCP /* gene-major */, *nTSByC, *nGByTS;
+    const long long *nByG, *nByTS;
+    double alpha, beta, delta, gamma;
+};
+
+int run_loglik(const LLIn& in, double* partial /* >= 1024 */, double* out, cudaStream_t st) {
     LLArgs a{};
-    a.model = h->model;
-    a.K = h->K;
-    a.L = h->L;
-    a.nS = h->nS;
-    a.nG = h->nG;
-    a.nM = h->nM;
-    a.mCPByS = h->mCPByS.p;
-    a.phiTab = h->nTSByCP.p;
-    a.nByTS = h->nByTS.p;
-    a.nGByTS = h->nGByTS.p;
-    a.partial = h->llPartial.p;
-    a.alpha = h->alpha;
-    a.beta = h->beta;
-    a.delta = h->delta;
-    a.gamma = h->gamma;
-    a.out = h->llOut.p;
-    const int NB = 64;  // fixed partial-block count => deterministic order
+    a.model = in.model;
+    a.K = in.K;
+    a.L = in.L;
+    a.nS = in.nS;
+    a.nG = in.nG;
+    a.nM = in.nM;
+    a.mCPByS = in.mCPByS;
+    a.phiTab = in.nTSByCP;
+    a.nByTS = in.nByTS;
+    a.nGByTS = in.nGByTS;
+    a.partial = partial;
+    a.alpha = in.alpha;
+    a.beta = in.beta;
+    a.delta = in.delta;
+    a.gamma = in.gamma;
+    a.out = out;
+    const int NB = 64;  // fixed partial-block counts => deterministic summation order
     int off = 0;
-    if (h->model != CELDA_MODEL_C) {
-        k_sum_lgamma<long long><<<NB, 256, 0, st>>>(h->nByG.p, h->nG, h->delta, h->llPartial.p);
+    if (in.model != CELDA_MODEL_C) {
+        k_sum_lgamma<long long><<<NB, 256, 0, st>>>(in.nByG, in.nG, in.delta, partial);
         count_launch();
         a.npG = NB;
         off = NB;
     }
-    if (h->model == CELDA_MODEL_C) {
+    if (in.model == CELDA_MODEL_C) {
         // phi over nGByCP (gene-major [nG][K]): numerator in fixed blocks, denominator one serial column sum per k
-        k_sum_lgamma<int><<<NB, 256, 0, st>>>(h->nGByCP.p, (long long)h->nG * h->K, h->beta, h->llPartial.p + off);
-        k_ll_phi_den_genemajor<<<1, 256, 0, st>>>(h->nGByCP.p, h->nG, h->K, h->beta, h->llPartial.p + off + NB);
+        k_sum_lgamma<int><<<NB, 256, 0, st>>>(in.nGByCP, (long long)in.nG * in.K, in.beta, partial + off);
+        k_ll_phi_den_genemajor<<<1, 256, 0, st>>>(in.nGByCP, in.nG, in.K, in.beta, partial + off + NB);
         a.npPhiB = NB;
         a.npPhiD = 1;
         count_launch(2);
     }
-    if (h->model == CELDA_MODEL_G) {
+    if (in.model == CELDA_MODEL_G) {
         const int NBG = 256;
-        k_sum_lgamma<int><<<NBG, 256, 0, st>>>(h->nTSByC.p, (long long)h->L * h->nM, h->beta, h->llPartial.p + off);
-        k_sum_lgamma_colsums<<<NBG, 256, 0, st>>>(h->nTSByC.p, h->L, h->nM, h->beta, h->llPartial.p + off + NBG);
+        k_sum_lgamma<int><<<NBG, 256, 0, st>>>(in.nTSByC, (long long)in.L * in.nM, in.beta, partial + off);
+        k_sum_lgamma_colsums<<<NBG, 256, 0, st>>>(in.nTSByC, in.L, in.nM, in.beta, partial + off + NBG);
         a.npPhiB = NBG;
         a.npPhiD = NBG;
         count_launch(2);
@@ -223,21 +245,69 @@ int chain_loglik_async(celda_chain* h) {
     return 0;
 }
 
+int chain_loglik_async(celda_chain* h) {
+    ProfScope ps(h, 4);
+    LLIn in{h->model, h->K, h->L, h->nS, h->nG, h->nM, h->mCPByS.p, h->nTSByCP.p, h->nGByCP.p, h->nTSByC.p,
+            h->nGByTS.p, h->nByG.p, h->nByTS.p, h->alpha, h->beta, h->delta, h->gamma};
+    return run_loglik(in, h->llPartial.p, h->llOut.p, h->st);
+}
+
 // Window sizes (items).  unit: the item count whose units (items x candidates) fill one grid-wide lane pass;
 // full: the largest multiple of it that fits the ring buffer, so lane-per-unit rounds leave no thread idle.
-void window_sizes(const celda_chain* h, int threads, int ncand, int* full, int* unit) {
-    const long long lanes = (long long)h->sms * threads;
-    long long u = std::max<long long>(lanes / ncand, h->Wmin);
-    if (u > h->Wmax) u = h->Wmax;
+void window_sizes(const SweepBufs& b, int sms, int threads, int ncand, int* full, int* unit) {
+    const long long lanes = (long long)sms * threads;
+    long long u = std::max<long long>(lanes / ncand, b.Wmin);
+    if (u > b.Wmax) u = b.Wmax;
     *unit = (int)u;
-    *full = (int)(std::max<long long>(1, h->Wmax / u) * u);
+    *full = (int)(std::max<long long>(1, b.Wmax / u) * u);
+}
+
+SweepWork make_work(SweepBufs& b, int sms, int threads, int ncand, int which) {
+    int wfull, wunit;
+    window_sizes(b, sms, threads, ncand, &wfull, &wunit);
+    return SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
+                     b.stats.p + 8 * which, b.Wmax, wfull, wunit, b.Wmin, b.lgT};
+}
+
+// a: data pointers and sizes filled by the caller; work space, window policy and launch geometry set here.
+int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
+    int threads = 1024;
+    if (z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32) > 220 * 1024) threads = 512;
+    a.w = make_work(b, sms, threads, a.K, which);
+    const size_t smem = z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32);
+    if (smem > 220 * 1024) return fail("z sweep: K=%d x R=%d tables need %zu bytes of shared memory (> 220 KB)", a.K, a.R, smem);
+    CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CELDA_CUDA_OK(cudaMemsetAsync(b.barrier.p, 0, sizeof(unsigned), st));
+    void* args[] = {&a};
+    CELDA_CUDA_OK(cudaLaunchCooperativeKernel((void*)k_sweep_z, dim3(sms), dim3(threads), args, smem, st));
+    count_launch();
+    return 0;
+}
+
+int run_sweep_y(YArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
+    int threads = 1024;
+    if (y_sweep_smem(a.L, a.ncol, b.lgT, threads / 32) > 220 * 1024) threads = 512;
+    a.w = make_work(b, sms, threads, a.L, which);
+    const size_t smem = y_sweep_smem(a.L, a.ncol, b.lgT, threads / 32);
+    if (smem > 220 * 1024) return fail("y sweep: L=%d x K=%d tables need %zu bytes of shared memory (> 220 KB)", a.L, a.ncol, smem);
+    CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CELDA_CUDA_OK(cudaMemsetAsync(b.barrier.p, 0, sizeof(unsigned), st));
+    void* args[] = {&a};
+    CELDA_CUDA_OK(cudaLaunchCooperativeKernel((void*)k_sweep_y, dim3(sms), dim3(threads), args, smem, st));
+    count_launch();
+    return 0;
+}
+
+int sweep_status(int stv) {
+    if (stv == -1) return fail("sample.int would take the Walker alias branch (> 200 likely categories): not supported");
+    if (stv == -2) return fail("NA in probability vector");
+    if (stv == -3) return fail("too few positive probabilities");
+    if (stv) return fail("sweep failed with status %d", stv);
+    return 0;
 }
 
 int launch_sweep_z(celda_chain* h, const int* d_ix, const double* d_u, int doSample, int which) {
     ProfScope ps(h, which);
-    int threads = 1024;
-    if (z_sweep_smem(h->L, h->K, h->nS, h->lgT, threads / 32) > 220 * 1024) threads = 512;
-    const int nwarp = threads / 32;
     ZArgs a{};
     a.R = h->L;
     a.K = h->K;
@@ -256,25 +326,11 @@ int launch_sweep_z(celda_chain* h, const int* d_ix, const double* d_u, int doSam
     a.u = d_u;
     a.doSample = doSample;
     a.probs = h->probsZ.p;
-    int wfull, wunit;
-    window_sizes(h, threads, a.K, &wfull, &wunit);
-    a.w = SweepWork{h->bufP.p, h->bufA.p, h->spec.p, h->colsum.p, h->lgnCP.p, h->barrier.p, h->status.p,
-                    h->stats.p + 8 * which, h->Wmax, wfull, wunit, h->Wmin, h->lgT};
-    const size_t smem = z_sweep_smem(a.R, a.K, a.nS, h->lgT, nwarp);
-    if (smem > 220 * 1024) return fail("z sweep: K=%d x R=%d tables need %zu bytes of shared memory (> 220 KB)", a.K, a.R, smem);
-    CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CELDA_CUDA_OK(cudaMemsetAsync(h->barrier.p, 0, sizeof(unsigned), h->st));
-    void* args[] = {&a};
-    CELDA_CUDA_OK(cudaLaunchCooperativeKernel((void*)k_sweep_z, dim3(h->sms), dim3(threads), args, smem, h->st));
-    count_launch();
-    return 0;
+    return run_sweep_z(a, h->wb, h->sms, which, h->st);
 }
 
 int launch_sweep_y(celda_chain* h, const int* d_ix, const double* d_u, int doSample, int which) {
     ProfScope ps(h, which);
-    int threads = 1024;
-    if (y_sweep_smem(h->L, h->K, h->lgT, threads / 32) > 220 * 1024) threads = 512;
-    const int nwarp = threads / 32;
     YArgs a{};
     a.nG = h->nG;
     a.ncol = h->K;
@@ -292,18 +348,7 @@ int launch_sweep_y(celda_chain* h, const int* d_ix, const double* d_u, int doSam
     a.u = d_u;
     a.doSample = doSample;
     a.probs = h->probsY.p;
-    int wfull, wunit;
-    window_sizes(h, threads, a.L, &wfull, &wunit);
-    a.w = SweepWork{h->bufP.p, h->bufA.p, h->spec.p, h->colsum.p, h->lgnCP.p, h->barrier.p, h->status.p,
-                    h->stats.p + 8 * which, h->Wmax, wfull, wunit, h->Wmin, h->lgT};
-    const size_t smem = y_sweep_smem(a.L, a.ncol, h->lgT, nwarp);
-    if (smem > 220 * 1024) return fail("y sweep: L=%d x K=%d tables need %zu bytes of shared memory (> 220 KB)", a.L, a.ncol, smem);
-    CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CELDA_CUDA_OK(cudaMemsetAsync(h->barrier.p, 0, sizeof(unsigned), h->st));
-    void* args[] = {&a};
-    CELDA_CUDA_OK(cudaLaunchCooperativeKernel((void*)k_sweep_y, dim3(h->sms), dim3(threads), args, smem, h->st));
-    count_launch();
-    return 0;
+    return run_sweep_y(a, h->wb, h->sms, which, h->st);
 }
 
 // y sweep + rowSumByGroupChange (R/celda_CG.R:544-564)
@@ -802,6 +847,279 @@ int celda_perplexityG(const int* x, int nr, int nc, const double* phi, int phi_n
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ stateless LL / sweeps
+}  // extern "C"
+namespace {
+// host double array (integer-valued) -> device int32 / int64, with an integrality check
+int up_int(const double* h, size_t n, DevBuf<int>& out, const char* what) {
+    DevBuf<double> d;
+    DevBuf<int> flag;
+    CELDA_TRY(d.upload(h, n));
+    CELDA_TRY(out.alloc(n));
+    CELDA_TRY(flag.alloc(1));
+    CELDA_TRY(flag.zero());
+    k_narrow<<<grid_for((long long)n, 256, num_sms(g_device)), 256>>>(d.p, (long long)n, out.p, flag.p);
+    count_launch();
+    int f = 0;
+    CELDA_CUDA_OK(cudaMemcpy(&f, flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (f) return fail("'%s' must hold integer-valued counts below 2^31", what);
+    return 0;
+}
+int up_ll(const double* h, size_t n, DevBuf<long long>& out, const char* what) {
+    std::vector<long long> v(n);
+    for (size_t i = 0; i < n; ++i) {
+        v[i] = (long long)h[i];
+        if ((double)v[i] != h[i]) return fail("'%s' must hold integer-valued counts", what);
+    }
+    return out.upload(v.data(), n);
+}
+template <typename T>
+int down_d(const T* dev, size_t n, double* host) {
+    DevBuf<double> tmp;
+    CELDA_TRY(tmp.alloc(n));
+    k_convert<T, double><<<grid_for((long long)n, 256, num_sms(g_device)), 256>>>(dev, (long long)n, tmp.p);
+    count_launch();
+    CELDA_CUDA_OK(cudaGetLastError());
+    CELDA_TRY(tmp.download(host, n));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+int ll_finish(const LLIn& in, double* ll) {
+    DevBuf<double> partial, out;
+    CELDA_TRY(partial.alloc(1024));
+    CELDA_TRY(out.alloc(1));
+    CELDA_TRY(run_loglik(in, partial.p, out.p, 0));
+    CELDA_TRY(out.download(ll, 1));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+}  // namespace
+extern "C" {
+
+int celda_cCGCalcLL(int K, int L, const int* mCPByS, const double* nTSByCP, const double* nByG, int nGenes,
+                    const double* nByTS, const int* nGByTS, int nS, double alpha, double beta, double delta,
+                    double gamma, double* ll) {
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    DevBuf<int> m, t, gt;
+    DevBuf<long long> g, ts;
+    CELDA_TRY(m.upload(mCPByS, (size_t)K * nS));
+    CELDA_TRY(up_int(nTSByCP, (size_t)L * K, t, "nTSByCP"));
+    CELDA_TRY(up_ll(nByG, nGenes, g, "nByG"));
+    CELDA_TRY(up_ll(nByTS, L, ts, "nByTS"));
+    CELDA_TRY(gt.upload(nGByTS, L));
+    LLIn in{CELDA_MODEL_CG, K, L, nS, nGenes, 0, m.p, t.p, nullptr, nullptr, gt.p, g.p, ts.p, alpha, beta, delta, gamma};
+    return ll_finish(in, ll);
+}
+
+int celda_cCCalcLL(const int* mCPByS, const double* nGByCP, int K, int nS, int nG, double alpha, double beta,
+                   double* ll) {
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    DevBuf<int> m, ncm, n;
+    CELDA_TRY(m.upload(mCPByS, (size_t)K * nS));
+    CELDA_TRY(up_int(nGByCP, (size_t)nG * K, ncm, "nGByCP"));
+    CELDA_TRY(n.alloc((size_t)nG * K));
+    k_transpose_convert<int, int><<<grid_for((long long)nG * K, 256, num_sms(g_device)), 256>>>(ncm.p, nG, K, n.p, false);
+    count_launch();
+    LLIn in{CELDA_MODEL_C, K, 1, nS, nG, 0, m.p, nullptr, n.p, nullptr, nullptr, nullptr, nullptr, alpha, beta, 1.0, 1.0};
+    return ll_finish(in, ll);
+}
+
+int celda_cGCalcLL(const double* nTSByC, const double* nByTS, const double* nByG, int nGenes, const int* nGByTS,
+                   long long nM, int L, double beta, double delta, double gamma, double* ll) {
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    DevBuf<int> t, gt;
+    DevBuf<long long> g, ts;
+    CELDA_TRY(up_int(nTSByC, (size_t)L * nM, t, "nTSByC"));
+    CELDA_TRY(up_ll(nByG, nGenes, g, "nByG"));
+    CELDA_TRY(up_ll(nByTS, L, ts, "nByTS"));
+    CELDA_TRY(gt.upload(nGByTS, L));
+    LLIn in{CELDA_MODEL_G, 1, L, 1, nGenes, nM, nullptr, nullptr, nullptr, t.p, gt.p, g.p, ts.p, 1.0, beta, delta, gamma};
+    return ll_finish(in, ll);
+}
+
+int celda_cCCalcGibbsProbZ(const double* counts, int* mCPByS, int nS, double* nGByCP, const double* nByC, double* nCP,
+                           int* z, const int* s, int K, int nG, long long nM, double alpha, double beta, int doSample,
+                           const int* ix, const double* u, double* probs) {
+    if (K < 1 || K > 32767) return fail("'K' must be between 1 and 32767");
+    CELDA_TRY(check_labels_host(z, nM, K, "z", "K"));
+    CELDA_TRY(check_labels_host(s, nM, nS, "s", "nS"));
+    CELDA_TRY(validate_order(ix, nM, "ix"));
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    const int sms = num_sms(g_device);
+    DevBuf<int> dc, dm, dn, dbc, dz, ds, dix;
+    DevBuf<long long> dcp;
+    DevBuf<double> du, dprobs;
+    SweepBufs wb;
+    CELDA_TRY(up_int(counts, (size_t)nG * nM, dc, "counts"));
+    CELDA_TRY(dm.upload(mCPByS, (size_t)K * nS));
+    CELDA_TRY(up_int(nGByCP, (size_t)nG * K, dn, "nGByCP"));
+    CELDA_TRY(up_int(nByC, (size_t)nM, dbc, "nByC"));
+    CELDA_TRY(up_ll(nCP, K, dcp, "nCP"));
+    CELDA_TRY(dz.upload(z, (size_t)nM));
+    CELDA_TRY(ds.upload(s, (size_t)nM));
+    CELDA_TRY(dix.upload(ix, (size_t)nM));
+    CELDA_TRY(du.upload(u, (size_t)nM));
+    if (probs) CELDA_TRY(dprobs.alloc((size_t)K * nM));
+    CELDA_TRY(wb.alloc(K, 0));
+    ZArgs a{};
+    a.R = nG;
+    a.K = K;
+    a.nS = nS;
+    a.nM = nM;
+    a.counts = dc.p;
+    a.nByC = dbc.p;
+    a.s = ds.p;
+    a.z = dz.p;
+    a.nTab = dn.p;
+    a.nCP = dcp.p;
+    a.mCPByS = dm.p;
+    a.alpha = alpha;
+    a.beta = beta;
+    a.ix = dix.p;
+    a.u = du.p;
+    a.doSample = doSample;
+    a.probs = probs ? dprobs.p : nullptr;
+    CELDA_TRY(run_sweep_z(a, wb, sms, 0, 0));
+    int stv = 0;
+    CELDA_CUDA_OK(cudaMemcpy(&stv, wb.status.p, sizeof(int), cudaMemcpyDeviceToHost));
+    CELDA_TRY(sweep_status(stv));
+    CELDA_TRY(dz.download(z, (size_t)nM));
+    CELDA_TRY(dm.download(mCPByS, (size_t)K * nS));
+    CELDA_TRY(down_d<int>(dn.p, (size_t)nG * K, nGByCP));
+    CELDA_TRY(down_d<long long>(dcp.p, K, nCP));
+    if (probs) CELDA_TRY(dprobs.download(probs, (size_t)K * nM));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
+int celda_cGCalcGibbsProbY(const double* counts, int ncol, double* nTSByC, double* nByTS, int* nGByTS,
+                           const double* nByG, int* y, int L, int nG, double beta, double delta, double gamma,
+                           int doSample, const int* ix, const double* u, double* probs) {
+    if (L < 1 || L > 32767) return fail("'L' must be between 1 and 32767");
+    CELDA_TRY(check_labels_host(y, nG, L, "y", "L"));
+    CELDA_TRY(validate_order(ix, nG, "ix"));
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    const int sms = num_sms(g_device);
+    DevBuf<int> dcm, dc, dt, dgt, dy, dix;
+    DevBuf<long long> dts, dg;
+    DevBuf<double> du, dprobs;
+    SweepBufs wb;
+    CELDA_TRY(up_int(counts, (size_t)nG * ncol, dcm, "counts"));
+    CELDA_TRY(dc.alloc((size_t)nG * ncol));
+    k_transpose_convert<int, int><<<grid_for((long long)nG * ncol, 256, sms), 256>>>(dcm.p, nG, ncol, dc.p, false);
+    count_launch();
+    CELDA_TRY(up_int(nTSByC, (size_t)L * ncol, dt, "nTSByC"));
+    CELDA_TRY(up_ll(nByTS, L, dts, "nByTS"));
+    CELDA_TRY(dgt.upload(nGByTS, L));
+    CELDA_TRY(up_ll(nByG, nG, dg, "nByG"));
+    CELDA_TRY(dy.upload(y, nG));
+    CELDA_TRY(dix.upload(ix, nG));
+    CELDA_TRY(du.upload(u, nG));
+    if (probs) CELDA_TRY(dprobs.alloc((size_t)L * nG));
+    CELDA_TRY(wb.alloc(L, 0));
+    YArgs a{};
+    a.nG = nG;
+    a.ncol = ncol;
+    a.L = L;
+    a.counts = dc.p;
+    a.nByG = dg.p;
+    a.y = dy.p;
+    a.tTab = dt.p;
+    a.nByTS = dts.p;
+    a.nGByTS = dgt.p;
+    a.beta = beta;
+    a.gamma = gamma;
+    a.delta = delta;
+    a.ix = dix.p;
+    a.u = du.p;
+    a.doSample = doSample;
+    a.probs = probs ? dprobs.p : nullptr;
+    CELDA_TRY(run_sweep_y(a, wb, sms, 0, 0));
+    int stv = 0;
+    CELDA_CUDA_OK(cudaMemcpy(&stv, wb.status.p, sizeof(int), cudaMemcpyDeviceToHost));
+    CELDA_TRY(sweep_status(stv));
+    CELDA_TRY(dy.download(y, nG));
+    CELDA_TRY(dgt.download(nGByTS, L));
+    CELDA_TRY(down_d<int>(dt.p, (size_t)L * ncol, nTSByC));
+    CELDA_TRY(down_d<long long>(dts.p, L, nByTS));
+    if (probs) CELDA_TRY(dprobs.download(probs, (size_t)L * nG));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
+int celda_cCCalcEMProbZ(int nG, long long nM, const int* p, const int* i, const double* x, int* mCPByS, int nS,
+                        double* nGByCP, double* nCP, int* z, const int* s, int K, double alpha, double beta,
+                        int doSample, double* probs) {
+    if (K < 1 || K > 256) return fail("'K' must be between 1 and 256 for the EM step");
+    CELDA_TRY(check_labels_host(z, nM, K, "z", "K"));
+    CELDA_TRY(check_labels_host(s, nM, nS, "s", "nS"));
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    const int sms = num_sms(g_device);
+    const bool sparse = p != nullptr;
+    DevBuf<int> dp, di, dx, dm, dncm, dn, dz, dzp, ds, flag;
+    DevBuf<long long> dcp;
+    DevBuf<double> phi, theta, dprobs;
+    if (sparse) {
+        CELDA_TRY(dp.upload(p, (size_t)nM + 1));
+        CELDA_TRY(di.upload(i, (size_t)p[nM]));
+        CELDA_TRY(up_int(x, (size_t)p[nM], dx, "counts"));
+    } else {
+        CELDA_TRY(up_int(x, (size_t)nG * nM, dx, "counts"));
+    }
+    CELDA_TRY(dm.upload(mCPByS, (size_t)K * nS));
+    CELDA_TRY(up_int(nGByCP, (size_t)nG * K, dncm, "nGByCP"));
+    CELDA_TRY(up_ll(nCP, K, dcp, "nCP"));
+    CELDA_TRY(dz.upload(z, (size_t)nM));
+    CELDA_TRY(dzp.upload(z, (size_t)nM));
+    CELDA_TRY(ds.upload(s, (size_t)nM));
+    CELDA_TRY(phi.alloc((size_t)nG * K));
+    CELDA_TRY(theta.alloc((size_t)K * nS));
+    CELDA_TRY(dprobs.alloc((size_t)K * nM));
+    CELDA_TRY(flag.alloc(1));
+    CELDA_TRY(flag.zero());
+    k_em_phi<<<grid_for((long long)nG * K, 256, sms), 256>>>(dncm.p, false, nG, K, dcp.p, beta, phi.p, flag.p);
+    k_em_theta<<<std::min(nS, 1024), 64>>>(dm.p, K, nS, alpha, theta.p, flag.p);
+    const int threads = 256, nwarp = threads / 32;
+    const int grid = (int)std::min<long long>((nM + nwarp - 1) / nwarp, (long long)sms * 32);
+    if (sparse)
+        k_em_probs<true><<<grid, threads>>>(nG, nM, K, dp.p, di.p, dx.p, phi.p, theta.p, ds.p, dprobs.p,
+                                            doSample ? dz.p : nullptr);
+    else
+        k_em_probs<false><<<grid, threads>>>(nG, nM, K, nullptr, nullptr, dx.p, phi.p, theta.p, ds.p, dprobs.p,
+                                             doSample ? dz.p : nullptr);
+    count_launch(3);
+    int f = 0;
+    CELDA_CUDA_OK(cudaMemcpy(&f, flag.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (f) return fail("Division by 0. Make sure colSums of counts does not contain 0 after rounding counts to integers.");
+    if (doSample) {
+        if (sparse) {
+            // gene-major working copy for the sparse change kernel
+            CELDA_TRY(dn.alloc((size_t)nG * K));
+            k_transpose_convert<int, int><<<grid_for((long long)nG * K, 256, sms), 256>>>(dncm.p, nG, K, dn.p, false);
+            k_colsum_change_csc<int><<<(int)std::min<long long>((nM + nwarp - 1) / nwarp, (long long)sms * 16), threads>>>(
+                (int)nM, dp.p, di.p, dx.p, dz.p, dzp.p, K, dn.p);
+            k_transpose_convert<int, int><<<grid_for((long long)nG * K, 256, sms), 256>>>(dn.p, nG, K, dncm.p, true);
+            count_launch(3);
+        } else {
+            k_colsum_change_dense<<<grid_for((long long)nG * nM, 256, sms), 256>>>(dx.p, nG, nM, dz.p, dzp.p, dncm.p);
+            count_launch();
+        }
+        k_colsums_small<<<1, 256>>>(dncm.p, nG, K, dcp.p);
+        CELDA_TRY(dm.zero());
+        k_table_zs<<<grid_for(nM, 256, sms), 256>>>(dz.p, ds.p, nM, K, dm.p);
+        count_launch(2);
+        CELDA_CUDA_OK(cudaGetLastError());
+        CELDA_TRY(dz.download(z, (size_t)nM));
+        CELDA_TRY(dm.download(mCPByS, (size_t)K * nS));
+        CELDA_TRY(down_d<int>(dncm.p, (size_t)nG * K, nGByCP));
+        CELDA_TRY(down_d<long long>(dcp.p, K, nCP));
+    }
+    CELDA_CUDA_OK(cudaGetLastError());
+    if (probs) CELDA_TRY(dprobs.download(probs, (size_t)K * nM));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------ chain
 int celda_chain_create(celda_chain** out, int device, int model, int nG, int nM, const int* p, const int* i,
                        const double* x, const int* s, int nS, int K, int L, double alpha, double beta, double delta,
@@ -890,17 +1208,7 @@ int celda_chain_create(celda_chain** out, int device, int model, int nG, int nM,
         CELDA_TRY(h->probsZ.alloc((size_t)h->K * nM));
     }
     if (model == CELDA_MODEL_CG) CELDA_TRY(h->nTSByCP.alloc((size_t)h->L * h->K));
-    const int ncand = std::max(h->K, h->L);
-    CELDA_TRY(h->bufP.alloc((size_t)h->Wmax * ncand));
-    CELDA_TRY(h->bufA.alloc((size_t)h->Wmax * ncand));
-    CELDA_TRY(h->spec.alloc(h->Wmax));
-    CELDA_TRY(h->colsum.alloc(ncand));
-    CELDA_TRY(h->lgnCP.alloc(ncand));
-    CELDA_TRY(h->status.alloc(1));
-    CELDA_TRY(h->status.zero(st));
-    CELDA_TRY(h->barrier.alloc(1));
-    CELDA_TRY(h->stats.alloc(40));
-    CELDA_TRY(h->stats.zero(st));
+    CELDA_TRY(h->wb.alloc(std::max(h->K, h->L), st));
     CELDA_TRY(h->ixy.alloc(nG));
     CELDA_TRY(h->uy.alloc(nG));
     CELDA_TRY(h->ixz.alloc(nM));
@@ -1111,7 +1419,7 @@ int celda_chain_profile(celda_chain* h, int enable) {
         h->prof_ms[q] = 0;
         h->prof_launches[q] = 0;
     }
-    CELDA_TRY(h->stats.zero(h->st));
+    CELDA_TRY(h->wb.stats.zero(h->st));
     return chain_sync(h);
 }
 
@@ -1120,7 +1428,7 @@ int celda_chain_profile_get(celda_chain* h, int which, double* ms, long long* la
     CELDA_CUDA_OK(cudaSetDevice(h->device));
     CELDA_TRY(chain_sync(h));
     long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    CELDA_CUDA_OK(cudaMemcpy(stats, h->stats.p + 8 * which, sizeof(stats), cudaMemcpyDeviceToHost));
+    CELDA_CUDA_OK(cudaMemcpy(stats, h->wb.stats.p + 8 * which, sizeof(stats), cudaMemcpyDeviceToHost));
     if (ms) *ms = h->prof_ms[which];
     if (launches) *launches = h->prof_launches[which];
     if (rounds) {

@@ -92,7 +92,6 @@ int celda_eigenMatMultNumeric(const double *A, int n, int k, const double *B, in
 int celda_perplexityG(const int *x, int nr, int nc, const double *phi, int phi_nr, int phi_nc, const double *psi,
                       int psi_nr, int psi_nc, const int *group, long long ngroup, int nlevels, double *ans);
 
-#ifdef CELDA_CUDA_PLANNED /* declared for the next milestone; not exported yet */
 /* ---- a13: collapsed log-likelihoods -----------------------------------------------------------
  * replaces .cCGCalcLL  R/celda_CG.R:839-888 ; .cCCalcLL  R/celda_C.R:760-788 ; .cGCalcLL  R/celda_G.R:664-702 */
 int celda_cCGCalcLL(int K, int L, const int *mCPByS, const double *nTSByCP, const double *nByG, int nGenes,
@@ -123,7 +122,6 @@ int celda_cCCalcEMProbZ(int nG, long long nM, const int *p, const int *i, const 
                         double *nGByCP, double *nCP, int *z, const int *s, int K, double alpha, double beta,
                         int doSample, double *probs);
 
-#endif /* CELDA_CUDA_PLANNED */
 
 /* ---- device-resident chain (a1, a6, a7, a15): counts and tables stay in HBM -------------------
  * One handle = one chain of .celda_CG / .celda_C / .celda_G (R/celda_CG.R:367-835, R/celda_C.R:306-616,

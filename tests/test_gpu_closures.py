@@ -1,0 +1,77 @@
+"""GPU parity for the sweep-granularity entry points that keep the R closures' signatures and the
+stateless log-likelihoods."""
+import numpy as np
+import pytest
+
+import celda_b200 as cb
+from oracle.oracle import dense_to_csc
+
+pytestmark = pytest.mark.gpu
+
+
+def test_stateless_loglik_goldens(oracle, gold_cg, gold_c, gold_g):
+    O = dense_to_csc(gold_cg["counts"])
+    p = oracle.cCGDecomposeCounts(O, gold_cg["s_mod"], gold_cg["z"], gold_cg["y"], 5, 10)
+    ll = cb.cCGCalcLL(5, 10, p["mCPByS"], p["nTSByCP"], p["nByG"], p["nByTS"], p["nGByTS"], p["nS"], p["nG"], 1.0, 1.0,
+                      1.0, 1.0)
+    assert abs(ll - (-1215541.0958389007)) <= 1e-12 * abs(ll)
+    assert ll < 0  # tests/testthat/test-celda_CG.R:60-94
+    O = dense_to_csc(gold_c["counts"])
+    p = oracle.cCDecomposeCounts(O, gold_c["s_mod"], gold_c["z"], 10)
+    ll = cb.cCCalcLL(p["mCPByS"], p["nGByCP"], gold_c["s_mod"], gold_c["z"], 10, p["nS"], p["nG"], 1.0, 1.0)
+    assert abs(ll - (-1273077.9330206949)) <= 1e-12 * abs(ll)
+    O = dense_to_csc(gold_g["counts"])
+    p = oracle.cGDecomposeCounts(O, gold_g["y"], 10)
+    ll = cb.cGCalcLL(p["nTSByC"], p["nByTS"], p["nByG"], p["nGByTS"], p["nM"], p["nG"], 10, 1.0, 1.0, 1.0)
+    assert abs(ll - (-290669.0461321392)) <= 1e-12 * abs(ll)
+    # non-default hyper-parameters against the oracle
+    ll = cb.cGCalcLL(p["nTSByC"], p["nByTS"], p["nByG"], p["nGByTS"], p["nM"], p["nG"], 10, 0.3, 2.5, 4.0)
+    ref = oracle.cGCalcLL(p["nTSByC"], p["nByTS"], p["nByG"], p["nGByTS"], p["nM"], p["nG"], 10, 0.3, 2.5, 4.0)
+    assert abs(ll - ref) <= 1e-12 * abs(ref)
+
+
+def test_closure_signature_sweeps_bit_exact(oracle, gold_cg):
+    counts, s, K, L = gold_cg["counts"], gold_cg["s"], 5, 10
+    nG, nM = counts.shape
+    rng = np.random.default_rng(31)
+    z, y = rng.integers(1, K + 1, nM).astype(np.int32), rng.integers(1, L + 1, nG).astype(np.int32)
+    p = oracle.cCGDecomposeCounts(dense_to_csc(counts), s, z, y, K, L)
+    ixy, uy = rng.permutation(nG).astype(np.int32) + 1, rng.random(nG)
+    ixz, uz = rng.permutation(nM).astype(np.int32) + 1, rng.random(nM)
+    got = cb.cGCalcGibbsProbY(p["nGByCP"], p["nTSByCP"], p["nByTS"], p["nGByTS"], p["nByG"], y, L, nG, 1.0, 1.0, 1.0,
+                              ixy, uy)
+    ref = oracle.cGCalcGibbsProbY(p["nGByCP"], p["nTSByCP"], p["nByTS"], p["nGByTS"], p["nByG"], y, L, nG, 1.0, 1.0,
+                                  1.0, ixy, uy)
+    for k in ("nTSByC", "nGByTS", "nByTS", "y", "probs"):
+        assert np.array_equal(got[k], ref[k]), k
+    got = cb.cCCalcGibbsProbZ(p["nTSByC"], p["mCPByS"], p["nTSByCP"], p["nByC"], p["nCP"], z, s, K, L, nM, 1.0, 1.0,
+                              ixz, uz)
+    ref = oracle.cCCalcGibbsProbZ(p["nTSByC"], p["mCPByS"], p["nTSByCP"], p["nByC"], p["nCP"], z, s, K, L, nM, 1.0, 1.0,
+                                  ixz, uz)
+    for k in ("mCPByS", "nGByCP", "nCP", "z", "probs"):
+        assert np.array_equal(got[k], ref[k]), k
+    # inputs are not modified (R copy semantics)
+    assert np.array_equal(p["nTSByCP"], oracle.colSumByGroup(p["nTSByC"], z, K))
+    # celda_C form of the z sweep: the raw (densified) count matrix against nGByCP, R = nG
+    dense = counts.astype(np.float64)
+    got = cb.cCCalcGibbsProbZ(dense, p["mCPByS"], p["nGByCP"], p["nByC"], p["nGByCP"].sum(0), z, s, K, nG, nM, 0.5, 0.2,
+                              ixz, uz)
+    ref = oracle.cCCalcGibbsProbZ(dense, p["mCPByS"], p["nGByCP"], p["nByC"], p["nGByCP"].sum(0), z, s, K, nG, nM, 0.5,
+                                  0.2, ixz, uz)
+    for k in ("mCPByS", "nGByCP", "nCP", "z", "probs"):
+        assert np.array_equal(got[k], ref[k]), k
+
+
+def test_closure_signature_em(oracle, gold_c):
+    counts, s, z, K = gold_c["counts"], gold_c["s_mod"], gold_c["sim_z"], 10
+    O = dense_to_csc(counts)
+    p = oracle.cCDecomposeCounts(O, s, z, K)
+    ref = oracle.cCCalcEMProbZ(O, p["mCPByS"], p["nGByCP"], p["nByC"], p["nCP"], z, s, K, p["nG"], p["nM"], 1.0, 1.0)
+    for cnt in (cb.CSC.from_dense(counts), counts.astype(np.float64)):
+        got = cb.cCCalcEMProbZ(cnt, p["mCPByS"], p["nGByCP"], p["nByC"], p["nCP"], z, s, K, p["nG"], p["nM"], 1.0, 1.0)
+        for k in ("mCPByS", "nGByCP", "nCP", "z"):
+            assert np.array_equal(got[k], ref[k]), k
+        assert np.allclose(got["probs"], ref["probs"], rtol=1e-12, atol=0)
+    with pytest.raises(cb.CeldaCudaError, match="Division by 0"):
+        cb.cCCalcEMProbZ(counts.astype(np.float64), p["mCPByS"] * 0, p["nGByCP"], p["nByC"], p["nCP"], z, s, K, p["nG"],
+                         p["nM"], 0.0, 1.0)
