@@ -390,6 +390,12 @@ class Chain:
         check(lib().celda_chain_loglik(self._h, C.byref(ll)))
         return ll.value
 
+    def perplexity(self):
+        """perplexity(x) on the model's own counts (R/perplexity.R:233-325)."""
+        v = C.c_double(0)
+        check(lib().celda_chain_perplexity(self._h, C.byref(v)))
+        return v.value
+
     def tables(self):
         """The sufficient statistics as R holds them (.cCGDecomposeCounts, R/celda_CG.R:902-934)."""
         K, L, nG, nM, nS = self.K, self.L, self.nG, self.nM, self.nS

@@ -1329,6 +1329,50 @@ int celda_chain_iterate_em(celda_chain* h, const int* ix_y, const double* u_y, d
     return chain_check_status(h);
 }
 
+// perplexity(x) on the model's own counts (R/perplexity.R:233-325, newCounts = NULL).
+int celda_chain_perplexity(celda_chain* h, double* perplexity) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (!h->has_state) return fail("set_state must be called first");
+    cudaStream_t st = h->st;
+    const int sms = h->sms, K = h->K, L = h->L, nG = h->nG;
+    DevBuf<double> psiDen, colDen, M, theta, percell, partial, out;
+    CELDA_TRY(percell.alloc(h->nM));
+    const int NB = 256;
+    CELDA_TRY(partial.alloc(NB));
+    CELDA_TRY(out.alloc(2));
+    const int threads = 256, nwarp = threads / 32;
+    const int grid = (int)std::min<long long>(((long long)h->nM + nwarp - 1) / nwarp, (long long)sms * 32);
+    if (h->model != CELDA_MODEL_C) {
+        CELDA_TRY(psiDen.alloc(L));
+        k_perp_psi_den<<<(L + 63) / 64, 64, 0, st>>>(h->nByG.p, h->y.p, nG, L, h->delta, psiDen.p);
+        count_launch();
+    }
+    if (h->model == CELDA_MODEL_G) {
+        k_perp_cells_G<<<grid, threads, 0, st>>>(h->nM, L, h->cp.p, h->ci.p, h->cx.p, h->nTSByC.p, h->y.p, h->nByG.p, psiDen.p,
+                                                h->beta, h->delta, percell.p);
+        count_launch();
+    } else {
+        if (K > 256) return fail("perplexity: K must be <= 256");
+        CELDA_TRY(colDen.alloc(K));
+        CELDA_TRY(M.alloc((size_t)nG * K));
+        CELDA_TRY(theta.alloc((size_t)K * h->nS));
+        if (h->model == CELDA_MODEL_CG) k_perp_col_den<<<1, 256, 0, st>>>(h->nTSByCP.p, false, L, K, h->beta, colDen.p);
+        else k_perp_col_den<<<1, 256, 0, st>>>(h->nGByCP.p, true, nG, K, h->beta, colDen.p);
+        k_perp_M<<<grid_for((long long)nG * K, 256, sms), 256, 0, st>>>(h->model, nG, K, L, h->y.p, h->nByG.p, psiDen.p,
+                                                                       h->nTSByCP.p, h->nGByCP.p, colDen.p, h->beta,
+                                                                       h->delta, M.p);
+        k_perp_theta<<<(h->nS + 63) / 64, 64, 0, st>>>(h->mCPByS.p, K, h->nS, h->alpha, theta.p);
+        k_perp_cells<<<grid, threads, 0, st>>>(h->nM, K, h->cp.p, h->ci.p, h->cx.p, M.p, theta.p, h->s.p, percell.p);
+        count_launch(4);
+    }
+    k_sum_array<<<NB, 256, 0, st>>>(percell.p, h->nM, partial.p);
+    k_perp_final<<<1, 256, 0, st>>>(partial.p, NB, h->nByC.p, h->nM, out.p);
+    count_launch(2);
+    CELDA_CUDA_OK(cudaGetLastError());
+    CELDA_CUDA_OK(cudaMemcpyAsync(perplexity, out.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    return chain_sync(h);
+}
+
 int celda_chain_stage_draws(celda_chain* h, int n_iter, const int* ix_y, const double* u_y, const int* ix_z,
                             const double* u_z) {
     CELDA_CUDA_OK(cudaSetDevice(h->device));

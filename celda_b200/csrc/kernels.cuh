@@ -665,3 +665,148 @@ __global__ void k_ll_phi_den_genemajor(const int* __restrict__ n, int R, int K, 
 }
 
 }  // namespace celda
+
+namespace celda {
+
+// ---------------------------------------------------------------------------------------------- perplexity (a14)
+// R/perplexity.R:233-325 with the posterior factors of R/factorizeMatrix.R:280-296.
+
+// den[l] = sum over genes of module l of (nByG + delta), genes added in ascending order (one thread per module)
+__global__ void k_perp_psi_den(const long long* __restrict__ nByG, const int* __restrict__ y, int nG, int L, double delta,
+                               double* __restrict__ den) {
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < L; l += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int g = 0; g < nG; ++g)
+            if (y[g] == l + 1) s += (double)nByG[g] + delta;
+        den[l] = s;
+    }
+}
+
+// column denominators of (table + add): tab is R x K column-major (rowMajor = false) or [R][K] (rowMajor = true)
+__global__ void k_perp_col_den(const int* __restrict__ tab, bool rowMajor, int R, int K, double add, double* __restrict__ den) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int r = 0; r < R; ++r) s += (double)(rowMajor ? tab[(size_t)r * K + k] : tab[(size_t)k * R + r]) + add;
+        den[k] = s;
+    }
+}
+
+// M[g][k] (gene-major): celda_CG log(psi[g] phi[y_g, k]) ; celda_C log((nGByCP[g,k] + beta) / colden[k])
+__global__ void k_perp_M(int model, int nG, int K, int L, const int* __restrict__ y, const long long* __restrict__ nByG,
+                         const double* __restrict__ psiDen, const int* __restrict__ nTSByCP /* L x K col-major */,
+                         const int* __restrict__ nGByCP /* [nG][K] */, const double* __restrict__ colDen, double beta,
+                         double delta, double* __restrict__ M) {
+    const long long tot = (long long)nG * K;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < tot; q += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(q / K), k = (int)(q % K);
+        if (model == 0) {
+            const int l = y[g] - 1;
+            const double psi = ((double)nByG[g] + delta) / psiDen[l];
+            const double phi = ((double)nTSByCP[(size_t)k * L + l] + beta) / colDen[k];
+            M[q] = dlog(psi * phi);
+        } else {
+            M[q] = dlog(((double)nGByCP[q] + beta) / colDen[k]);
+        }
+    }
+}
+
+// theta[k, s] = log((m + alpha) / colSum(m + alpha))
+__global__ void k_perp_theta(const int* __restrict__ m, int K, int nS, double alpha, double* __restrict__ theta) {
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < nS; s += gridDim.x * blockDim.x) {
+        double cs = 0.0;
+        for (int k = 0; k < K; ++k) cs += (double)m[(size_t)s * K + k] + alpha;
+        for (int k = 0; k < K; ++k) theta[(size_t)s * K + k] = dlog(((double)m[(size_t)s * K + k] + alpha) / cs);
+    }
+}
+
+// per cell: logSumExp_k( sum_nz M[i][k] x + theta[k, s_c] ) -> lse[c]; column total -> tot[c].  One warp per cell.
+__global__ void k_perp_cells(long long nM, int K, const int* __restrict__ p, const int* __restrict__ ri,
+                             const int* __restrict__ xv, const double* __restrict__ M, const double* __restrict__ theta,
+                             const int* __restrict__ s, double* __restrict__ lse) {
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int KPL = 8;
+    for (long long c = blockIdx.x * (long long)nwarp + warp; c < nM; c += (long long)gridDim.x * nwarp) {
+        double acc[KPL];
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) acc[q] = 0.0;
+        const int e = p[c + 1];
+        for (int t = p[c]; t < e; ++t) {
+            const double x = (double)xv[t];
+            const double* row = M + (size_t)ri[t] * K;
+#pragma unroll
+            for (int q = 0; q < KPL; ++q) {
+                const int k = lane + 32 * q;
+                if (k < K) acc[q] += row[k] * x;
+            }
+        }
+        const double* th = theta + (size_t)(s[c] - 1) * K;
+        double mx = -__longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) {
+            const int k = lane + 32 * q;
+            if (k < K) {
+                acc[q] += th[k];
+                mx = fmax(mx, acc[q]);
+            }
+        }
+        for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        double se = 0.0;
+#pragma unroll
+        for (int q = 0; q < KPL; ++q) {
+            const int k = lane + 32 * q;
+            if (k < K) se += dexp(acc[q] - mx);
+        }
+        for (int o = 16; o; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+        if (lane == 0) lse[c] = mx + dlog(se);  // the maximum contributes exp(0) = 1, so se >= 1
+    }
+}
+
+// celda_G: per cell sum_nz x log(psi[g] phi_cell[y_g, c]), phi_cell = (nTSByC[, c] + beta) / colSum
+__global__ void k_perp_cells_G(long long nM, int L, const int* __restrict__ p, const int* __restrict__ ri,
+                               const int* __restrict__ xv, const int* __restrict__ nTSByC, const int* __restrict__ y,
+                               const long long* __restrict__ nByG, const double* __restrict__ psiDen, double beta,
+                               double delta, double* __restrict__ out) {
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long long c = blockIdx.x * (long long)nwarp + warp; c < nM; c += (long long)gridDim.x * nwarp) {
+        const int* col = nTSByC + c * L;
+        double den = 0.0;
+        for (int l = 0; l < L; ++l) den += (double)col[l] + beta;  // every lane, same order
+        double acc = 0.0;
+        const int e = p[c + 1];
+        for (int t = p[c] + lane; t < e; t += 32) {
+            const int g = ri[t], l = y[g] - 1;
+            const double psi = ((double)nByG[g] + delta) / psiDen[l];
+            acc += (double)xv[t] * dlog(psi * (((double)col[l] + beta) / den));
+        }
+        for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) out[c] = acc;
+    }
+}
+
+// Deterministic sum of a double array and of an int32 array (fixed blocks) -> partial[blockIdx], totals[blockIdx]
+__global__ void k_sum_array(const double* __restrict__ v, long long n, double* __restrict__ partial) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) acc += v[i];
+    const double s = block_sum(acc, red);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+__global__ void k_perp_final(const double* __restrict__ partial, int np, const int* __restrict__ nByC, long long nM,
+                             double* out) {
+    __shared__ unsigned long long tot;
+    if (threadIdx.x == 0) tot = 0;
+    __syncthreads();
+    unsigned long long t = 0;
+    for (long long c = threadIdx.x; c < nM; c += blockDim.x) t += (unsigned long long)nByC[c];
+    atomicAdd(&tot, t);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double logPx = 0.0;
+        for (int i = 0; i < np; ++i) logPx += partial[i];
+        out[0] = dexp(-(logPx / (double)tot));
+        out[1] = logPx;
+    }
+}
+
+}  // namespace celda

@@ -158,9 +158,9 @@ int celda_chain_stage_draws(celda_chain *h, int n_iter, const int *ix_y, const d
                             const double *u_z);
 int celda_chain_iterate_staged(celda_chain *h, int iter, double *ll);
 int celda_chain_loglik(celda_chain *h, double *ll);
-#ifdef CELDA_CUDA_PLANNED
+/* perplexity(x) of the current state on the model's own counts: .perplexityCelda_CG / _C / _G
+ * (R/perplexity.R:233-325) over the posterior factors of R/factorizeMatrix.R:280-296. */
 int celda_chain_perplexity(celda_chain *h, double *perplexity);
-#endif /* CELDA_CUDA_PLANNED */
 /* Tables as R holds them (double, column-major); any pointer may be NULL. */
 int celda_chain_get_tables(celda_chain *h, int *mCPByS, double *nTSByC, double *nTSByCP, double *nGByCP, double *nCP,
                            double *nByC, double *nByG, double *nByTS, int *nGByTS);
