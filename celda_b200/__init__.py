@@ -79,6 +79,16 @@ def _vec(fn, x):
     return out
 
 
+def philox4x32(counters, key):
+    """Raw Philox4x32-10 blocks (uint32 words) for known-answer tests."""
+    c = np.ascontiguousarray(counters, dtype=np.uint32).reshape(-1, 4)
+    k = np.ascontiguousarray(key, dtype=np.uint32)
+    out = np.zeros_like(c)
+    check(lib().celda_cuda_philox4x32(c.view(np.int32).ctypes.data_as(_ip), k.view(np.int32).ctypes.data_as(_ip),
+                                      c.shape[0], out.view(np.int32).ctypes.data_as(_ip)))
+    return out
+
+
 def lgamma(x):
     """lgamma table builder (R/celda_CG.R:428-429,543): device arithmetic, value-identical to the sweeps'."""
     return _vec(lib().celda_cuda_lgamma, x)
@@ -355,6 +365,27 @@ class Chain:
     def sweep_z_gibbs(self, ix, u, doSample=True):
         ix, u = _i(ix), _d(u)
         check(lib().celda_chain_sweep_z_gibbs(self._h, _pi(ix), _pd(u), int(doSample)))
+
+    def seed(self, seed, stream=0):
+        """Philox mode: key = seed, stream = chain index (R/celdaGridSearch.R:294 uses seed + chain - 1)."""
+        check(lib().celda_chain_seed(self._h, int(seed), int(stream)))
+
+    def sweep_y_philox(self, doSample=True):
+        check(lib().celda_chain_sweep_y_philox(self._h, int(doSample)))
+
+    def sweep_z_gibbs_philox(self, doSample=True):
+        check(lib().celda_chain_sweep_z_gibbs_philox(self._h, int(doSample)))
+
+    def iterate_philox(self):
+        ll = C.c_double(0)
+        check(lib().celda_chain_iterate(self._h, None, None, None, None, C.byref(ll)))
+        return ll.value
+
+    def get_draws(self, which):
+        n = self.nG if which in (0, "y") else self.nM
+        ix, u = np.zeros(n, np.int32), np.zeros(n)
+        check(lib().celda_chain_get_draws(self._h, 0 if which in (0, "y") else 1, _pi(ix), _pd(u)))
+        return ix, u
 
     def sweep_z_em(self, doSample=True):
         """.cCCalcEMProbZ (R/celda_C.R:717-756) + re-decomposition."""

@@ -5,6 +5,8 @@
 #include <cmath>
 #include <memory>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "sweeps.cuh"
@@ -75,6 +77,14 @@ struct celda_chain {
     DevBuf<double> uy, uz;
     DevBuf<double> llPartial, llOut;
     DevBuf<double> phiBuf, thetaBuf;  // EM step
+    // Philox mode
+    unsigned long long ph_seed = 0, ph_stream = 0;
+    unsigned ph_sweep = 0;
+    bool ph_seeded = false;
+    DevBuf<unsigned long long> ph_keys, ph_keys_out;
+    DevBuf<int> ph_iota;
+    DevBuf<unsigned char> ph_tmp;
+    int last_draw_n[2] = {0, 0};  // for get_draws: y, z
     DevBuf<int> emFlag;
     // staged draws
     int staged_iters = 0;
@@ -434,6 +444,30 @@ int chain_check_em_flag(celda_chain* h) {
     CELDA_CUDA_OK(cudaMemcpyAsync(&f, h->emFlag.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
     CELDA_TRY(chain_sync(h));
     if (f) return fail("Division by 0. Make sure colSums of counts does not contain 0 after rounding counts to integers.");
+    return 0;
+}
+
+// Philox mode: visiting order (argsort of per-item 64-bit keys) and one uniform per visited item, generated on
+// the device into the chain's ix / u staging buffers.
+int chain_philox_draws(celda_chain* h, long long n, int* d_ix, double* d_u) {
+    if (!h->ph_seeded) return fail("philox mode: call celda_chain_seed first");
+    cudaStream_t st = h->st;
+    if (h->ph_keys.n < (size_t)n) {
+        CELDA_TRY(h->ph_keys.alloc((size_t)n));
+        CELDA_TRY(h->ph_keys_out.alloc((size_t)n));
+        CELDA_TRY(h->ph_iota.alloc((size_t)n));
+    }
+    k_philox_draws<<<grid_for(n, 256, h->sms), 256, 0, st>>>(n, (unsigned)h->ph_seed, (unsigned)(h->ph_seed >> 32), h->ph_sweep,
+                                                             (unsigned)h->ph_stream, h->ph_keys.p, h->ph_iota.p, d_u);
+    count_launch();
+    size_t bytes = 0;
+    CELDA_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->ph_keys.p, h->ph_keys_out.p, h->ph_iota.p, d_ix, (int)n, 0,
+                                                  64, st));
+    if (h->ph_tmp.n < bytes) CELDA_TRY(h->ph_tmp.alloc(bytes));
+    CELDA_CUDA_OK(cub::DeviceRadixSort::SortPairs(h->ph_tmp.p, bytes, h->ph_keys.p, h->ph_keys_out.p, h->ph_iota.p, d_ix, (int)n,
+                                                  0, 64, st));
+    count_launch(8);  // radix sort passes
+    h->ph_sweep += 1;
     return 0;
 }
 
@@ -1275,6 +1309,57 @@ int celda_chain_sweep_z_gibbs(celda_chain* h, const int* ix, const double* u, in
     return chain_check_status(h);
 }
 
+int celda_chain_seed(celda_chain* h, unsigned long long seed, unsigned long long stream) {
+    h->ph_seed = seed;
+    h->ph_stream = stream;
+    h->ph_sweep = 0;
+    h->ph_seeded = true;
+    return 0;
+}
+
+int celda_chain_sweep_y_philox(celda_chain* h, int doSample) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (!h->has_state) return fail("set_state must be called first");
+    CELDA_TRY(chain_philox_draws(h, h->nG, h->ixy.p, h->uy.p));
+    CELDA_TRY(chain_step_y(h, h->ixy.p, h->uy.p, doSample));
+    return chain_check_status(h);
+}
+
+int celda_chain_sweep_z_gibbs_philox(celda_chain* h, int doSample) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (!h->has_state) return fail("set_state must be called first");
+    CELDA_TRY(chain_philox_draws(h, h->nM, h->ixz.p, h->uz.p));
+    CELDA_TRY(chain_step_z(h, h->ixz.p, h->uz.p, doSample));
+    return chain_check_status(h);
+}
+
+// The order and uniforms the last sweep of each kind consumed (injected or generated): which = 0 y, 1 z.
+int celda_chain_get_draws(celda_chain* h, int which, int* ix, double* u) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (which == 0) {
+        CELDA_TRY(h->ixy.download(ix, h->nG, h->st));
+        CELDA_TRY(h->uy.download(u, h->nG, h->st));
+    } else {
+        CELDA_TRY(h->ixz.download(ix, h->nM, h->st));
+        CELDA_TRY(h->uz.download(u, h->nM, h->st));
+    }
+    return chain_sync(h);
+}
+
+int celda_cuda_philox4x32(const int* counters, const int* key, int n, int* out) {
+    CELDA_CUDA_OK(cudaSetDevice(g_device));
+    DevBuf<unsigned> dc, dk, dout;
+    CELDA_TRY(dc.upload(reinterpret_cast<const unsigned*>(counters), (size_t)4 * n));
+    CELDA_TRY(dk.upload(reinterpret_cast<const unsigned*>(key), 2));
+    CELDA_TRY(dout.alloc((size_t)4 * n));
+    k_philox_raw<<<grid_for(n, 128, num_sms(g_device)), 128>>>(dc.p, dk.p, n, dout.p);
+    count_launch();
+    CELDA_CUDA_OK(cudaGetLastError());
+    CELDA_TRY(dout.download(reinterpret_cast<unsigned*>(out), (size_t)4 * n));
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
 int celda_chain_loglik(celda_chain* h, double* ll) {
     CELDA_CUDA_OK(cudaSetDevice(h->device));
     if (!h->has_state) return fail("set_state must be called first");
@@ -1287,14 +1372,19 @@ int celda_chain_iterate(celda_chain* h, const int* ix_y, const double* u_y, cons
                         double* ll) {
     CELDA_CUDA_OK(cudaSetDevice(h->device));
     if (!h->has_state) return fail("set_state must be called first");
-    if (!ix_y || !u_y || !ix_z || !u_z) return fail("iterate: injected order and uniforms are required");
-    CELDA_TRY(validate_order(ix_y, h->nG, "ix_y"));
-    CELDA_TRY(validate_order(ix_z, h->nM, "ix_z"));
     cudaStream_t st = h->st;
-    CELDA_CUDA_OK(cudaMemcpyAsync(h->ixy.p, ix_y, sizeof(int) * h->nG, cudaMemcpyHostToDevice, st));
-    CELDA_CUDA_OK(cudaMemcpyAsync(h->uy.p, u_y, sizeof(double) * h->nG, cudaMemcpyHostToDevice, st));
-    CELDA_CUDA_OK(cudaMemcpyAsync(h->ixz.p, ix_z, sizeof(int) * h->nM, cudaMemcpyHostToDevice, st));
-    CELDA_CUDA_OK(cudaMemcpyAsync(h->uz.p, u_z, sizeof(double) * h->nM, cudaMemcpyHostToDevice, st));
+    if (!ix_y && !u_y && !ix_z && !u_z) {  // Philox mode
+        CELDA_TRY(chain_philox_draws(h, h->nG, h->ixy.p, h->uy.p));
+        CELDA_TRY(chain_philox_draws(h, h->nM, h->ixz.p, h->uz.p));
+    } else {
+        if (!ix_y || !u_y || !ix_z || !u_z) return fail("iterate: pass all four of ix_y, u_y, ix_z, u_z or none (Philox)");
+        CELDA_TRY(validate_order(ix_y, h->nG, "ix_y"));
+        CELDA_TRY(validate_order(ix_z, h->nM, "ix_z"));
+        CELDA_CUDA_OK(cudaMemcpyAsync(h->ixy.p, ix_y, sizeof(int) * h->nG, cudaMemcpyHostToDevice, st));
+        CELDA_CUDA_OK(cudaMemcpyAsync(h->uy.p, u_y, sizeof(double) * h->nG, cudaMemcpyHostToDevice, st));
+        CELDA_CUDA_OK(cudaMemcpyAsync(h->ixz.p, ix_z, sizeof(int) * h->nM, cudaMemcpyHostToDevice, st));
+        CELDA_CUDA_OK(cudaMemcpyAsync(h->uz.p, u_z, sizeof(double) * h->nM, cudaMemcpyHostToDevice, st));
+    }
     CELDA_TRY(chain_step_y(h, h->ixy.p, h->uy.p, 1));
     CELDA_TRY(chain_step_z(h, h->ixz.p, h->uz.p, 1));
     CELDA_TRY(chain_loglik_async(h));

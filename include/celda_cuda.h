@@ -143,14 +143,17 @@ int celda_chain_sweep_z_gibbs(celda_chain *h, const int *ix, const double *u, in
 /* EM z step (.cCCalcEMProbZ, R/celda_C.R:717-756) and one EM-mode iteration of the chain loop. */
 int celda_chain_sweep_z_em(celda_chain *h, int doSample);
 int celda_chain_iterate_em(celda_chain *h, const int *ix_y, const double *u_y, double *ll);
-#ifdef CELDA_CUDA_PLANNED
-/* ... or with the device Philox4x32-10 generator: order = argsort of Philox keys, one uniform per step. */
+/* ... or with the device Philox4x32-10 generator (key = seed; counter = item, sweep number, stream): the visiting
+ * order is the argsort of per-item 64-bit keys, one uniform in (0,1) per visited item.  get_draws returns the order
+ * and uniforms the last sweep consumed (which = 0 y, 1 z), so a Philox run can be replayed in injection mode. */
 int celda_chain_seed(celda_chain *h, unsigned long long seed, unsigned long long stream);
 int celda_chain_sweep_y_philox(celda_chain *h, int doSample);
 int celda_chain_sweep_z_gibbs_philox(celda_chain *h, int doSample);
-#endif /* CELDA_CUDA_PLANNED */
+int celda_chain_get_draws(celda_chain *h, int which, int *ix, double *u);
+/* Raw generator (known-answer tests): out[4 i ..] = philox4x32_10(counters[4 i ..], key[0..1]) as 32-bit words. */
+int celda_cuda_philox4x32(const int *counters, const int *key, int n, int *out);
 /* One iteration of the chain loop without split heuristics (R/celda_CG.R:543-602): y sweep, rowSumByGroupChange,
- * z sweep (Gibbs), colSumByGroupChange, log-likelihood.  ix/u NULL => Philox. */
+ * z sweep (Gibbs), colSumByGroupChange, log-likelihood.  All four of ix/u NULL => Philox mode. */
 int celda_chain_iterate(celda_chain *h, const int *ix_y, const double *u_y, const int *ix_z, const double *u_z,
                         double *ll);
 /* Pre-stage injected draws for n_iter iterations in HBM, then run them without host traffic. */
