@@ -15,7 +15,8 @@ _TYPES = {
     "int": C.c_int, "double": C.c_double, "long long": C.c_longlong, "unsigned long long": C.c_ulonglong,
     "const int *": _ip, "int *": _ip, "const double *": _dp, "double *": _dp, "long long *": _llp,
     "float *": C.POINTER(C.c_float), "celda_chain *": C.c_void_p, "celda_chain **": C.POINTER(C.c_void_p),
-    "const char *": C.c_char_p, "void": None,
+    "const char *": C.c_char_p, "char *": C.c_char_p, "void": None, "celda_comm *": C.c_void_p,
+    "celda_comm **": C.POINTER(C.c_void_p),
 }
 
 

@@ -6,6 +6,8 @@
 #include <memory>
 
 #include <cub/device/device_radix_sort.cuh>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -37,6 +39,41 @@ int check_labels_host(const int* g, long long n, int K, const char* what, const 
 }
 
 }  // namespace
+
+// NCCL is resolved at run time (dlopen by SONAME): a host process that already carries an NCCL (e.g. a Python
+// process that imported torch) shares that copy, a plain R process loads the system one.  No link-time dependency.
+struct NcclApi {
+    void* so = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    int load() {
+        if (so) return 0;
+        so = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!so) return fail("cannot load libnccl.so.2: %s", dlerror());
+        GetUniqueId = (decltype(GetUniqueId))dlsym(so, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(so, "ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))dlsym(so, "ncclCommDestroy");
+        AllReduce = (decltype(AllReduce))dlsym(so, "ncclAllReduce");
+        GetErrorString = (decltype(GetErrorString))dlsym(so, "ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !GetErrorString)
+            return fail("libnccl.so.2 lacks an expected symbol");
+        return 0;
+    }
+};
+static NcclApi g_nccl;
+#define CELDA_NCCL_OK(expr)                                                                              \
+    do {                                                                                                 \
+        ncclResult_t r__ = (expr);                                                                       \
+        if (r__ != ncclSuccess) return celda::fail("NCCL error %s at %s:%d", g_nccl.GetErrorString(r__), __FILE__, __LINE__); \
+    } while (0)
+
+struct celda_comm {
+    ncclComm_t comm = nullptr;
+    int nranks = 1, rank = 0, device = 0;
+};
 
 // Work space of the sweep kernels (ring buffers, speculation flags, barrier, status, statistics).
 struct SweepBufs {
@@ -73,6 +110,10 @@ struct celda_chain {
     DevBuf<long long> nCP, nByG, nByTS;
     DevBuf<double> probsZ, probsY;
     SweepBufs wb;  // sweep work space
+    // cell-sharded mode (EM z step + aggregation): this handle holds a column range of the counts;
+    // *_loc are this shard's partial tables, the plain names hold the all-reduced (global) tables.
+    celda_comm* comm = nullptr;
+    DevBuf<int> nGByCP_loc, mCPByS_loc;
     DevBuf<int> ixy, ixz;
     DevBuf<double> uy, uz;
     DevBuf<double> llPartial, llOut;
@@ -158,6 +199,16 @@ int chain_check_status(celda_chain* h) {
     return sweep_status(stv);
 }
 
+// Cell-sharded mode: combine the shards' partial G x K and K x S tables with one all-reduce each (int32 sums are
+// exact and order-independent, so every rank ends up with the bit-identical global tables).
+int chain_reduce_tables(celda_chain* h) {
+    if (!h->comm) return 0;
+    CELDA_NCCL_OK(g_nccl.AllReduce(h->nGByCP_loc.p, h->nGByCP.p, (size_t)h->nG * h->K, ncclInt32, ncclSum, h->comm->comm, h->st));
+    CELDA_NCCL_OK(g_nccl.AllReduce(h->mCPByS_loc.p, h->mCPByS.p, (size_t)h->K * h->nS, ncclInt32, ncclSum, h->comm->comm, h->st));
+    count_launch(2);
+    return 0;
+}
+
 // ---- decompose (R/celda_CG.R:902-934, R/celda_C.R:800-822, R/celda_G.R:712-733)
 int chain_decompose(celda_chain* h) {
     cudaStream_t st = h->st;
@@ -175,12 +226,15 @@ int chain_decompose(celda_chain* h) {
     }
     if (h->model != CELDA_MODEL_G) {  // nGByCP = colSumByGroup(counts, z, K); mCPByS = table(z, s)
         const int threads = 256, nwarp = threads / 32;
-        CELDA_TRY(h->nGByCP.zero(st));
+        DevBuf<int>& ng = h->comm ? h->nGByCP_loc : h->nGByCP;
+        DevBuf<int>& mm = h->comm ? h->mCPByS_loc : h->mCPByS;
+        CELDA_TRY(ng.zero(st));
         k_colsum_csc<int><<<std::min((h->nM + nwarp - 1) / nwarp, sms * 16), threads, 0, st>>>(
-            h->nM, h->cp.p, h->ci.p, h->cx.p, h->z.p, h->K, h->nGByCP.p);
-        CELDA_TRY(h->mCPByS.zero(st));
-        k_table_zs<<<grid_for(h->nM, 256, sms), 256, 0, st>>>(h->z.p, h->s.p, h->nM, h->K, h->mCPByS.p);
+            h->nM, h->cp.p, h->ci.p, h->cx.p, h->z.p, h->K, ng.p);
+        CELDA_TRY(mm.zero(st));
+        k_table_zs<<<grid_for(h->nM, 256, sms), 256, 0, st>>>(h->z.p, h->s.p, h->nM, h->K, mm.p);
         count_launch(2);
+        CELDA_TRY(chain_reduce_tables(h));
     }
     if (h->model == CELDA_MODEL_CG) {  // nTSByCP = colSumByGroup(nTSByC, z, K); nCP = colSums(nTSByCP)
         CELDA_TRY(h->nTSByCP.zero(st));
@@ -424,16 +478,20 @@ int chain_step_z_em(celda_chain* h, int doSample) {
             count_launch(2);
         }
         k_colsum_change_csc<int><<<std::min((h->nM + nwarp - 1) / nwarp, h->sms * 16), threads, 0, st>>>(
-            h->nM, h->cp.p, h->ci.p, h->cx.p, h->z.p, h->zprev.p, K, h->nGByCP.p);
+            h->nM, h->cp.p, h->ci.p, h->cx.p, h->z.p, h->zprev.p, K, h->comm ? h->nGByCP_loc.p : h->nGByCP.p);
+        {
+            DevBuf<int>& mm = h->comm ? h->mCPByS_loc : h->mCPByS;
+            CELDA_TRY(mm.zero(st));
+            k_table_zs<<<grid_for(h->nM, 256, h->sms), 256, 0, st>>>(h->z.p, h->s.p, h->nM, K, mm.p);
+            count_launch(2);
+        }
+        CELDA_TRY(chain_reduce_tables(h));
         if (isC) {
             CELDA_TRY(h->nCP.zero(st));
             k_colsums_genemajor<<<grid_for((long long)h->nG * K, 256, h->sms), 256, 0, st>>>(h->nGByCP.p, h->nG, K,
                                                                                           (unsigned long long*)h->nCP.p);
             count_launch();
         }
-        CELDA_TRY(h->mCPByS.zero(st));
-        k_table_zs<<<grid_for(h->nM, 256, h->sms), 256, 0, st>>>(h->z.p, h->s.p, h->nM, K, h->mCPByS.p);
-        count_launch(2);
     }
     CELDA_CUDA_OK(cudaGetLastError());
     return 0;
@@ -1309,6 +1367,51 @@ int celda_chain_sweep_z_gibbs(celda_chain* h, const int* ix, const double* u, in
     return chain_check_status(h);
 }
 
+// ---- cell-sharded EM: one process per GPU, one NCCL communicator
+int celda_comm_unique_id(char* id128) {
+    CELDA_TRY(g_nccl.load());
+    ncclUniqueId id;
+    CELDA_NCCL_OK(g_nccl.GetUniqueId(&id));
+    static_assert(sizeof(id) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+int celda_comm_create(celda_comm** out, const char* id128, int nranks, int rank, int device) {
+    *out = nullptr;
+    CELDA_TRY(g_nccl.load());
+    CELDA_CUDA_OK(cudaSetDevice(device));
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    std::unique_ptr<celda_comm> c(new celda_comm());
+    c->nranks = nranks;
+    c->rank = rank;
+    c->device = device;
+    CELDA_NCCL_OK(g_nccl.CommInitRank(&c->comm, nranks, id, rank));
+    *out = c.release();
+    return 0;
+}
+
+void celda_comm_destroy(celda_comm* c) {
+    if (!c) return;
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    delete c;
+}
+
+// Turn a celda_C chain into one shard of a cell-sharded chain: its counts are a column range of the full matrix,
+// its partial nGByCP / mCPByS tables are all-reduced over `comm` after every (re-)decomposition.  Call before
+// set_state; every rank must make the same sequence of calls.
+int celda_chain_attach_comm(celda_chain* h, celda_comm* comm) {
+    if (h->model != CELDA_MODEL_C) return fail("attach_comm: only the celda_C (EM) chain shards cells");
+    if (comm->device != h->device) return fail("attach_comm: communicator and chain live on different devices");
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    CELDA_TRY(h->nGByCP_loc.alloc((size_t)h->nG * h->K));
+    CELDA_TRY(h->mCPByS_loc.alloc((size_t)h->K * h->nS));
+    h->comm = comm;
+    h->has_state = false;
+    return 0;
+}
+
 int celda_chain_seed(celda_chain* h, unsigned long long seed, unsigned long long stream) {
     h->ph_seed = seed;
     h->ph_stream = stream;
@@ -1429,7 +1532,7 @@ int celda_chain_perplexity(celda_chain* h, double* perplexity) {
     CELDA_TRY(percell.alloc(h->nM));
     const int NB = 256;
     CELDA_TRY(partial.alloc(NB));
-    CELDA_TRY(out.alloc(2));
+    CELDA_TRY(out.alloc(3));
     const int threads = 256, nwarp = threads / 32;
     const int grid = (int)std::min<long long>(((long long)h->nM + nwarp - 1) / nwarp, (long long)sms * 32);
     if (h->model != CELDA_MODEL_C) {
@@ -1459,6 +1562,14 @@ int celda_chain_perplexity(celda_chain* h, double* perplexity) {
     k_perp_final<<<1, 256, 0, st>>>(partial.p, NB, h->nByC.p, h->nM, out.p);
     count_launch(2);
     CELDA_CUDA_OK(cudaGetLastError());
+    if (h->comm) {  // shards: all-reduce (logPx, total counts); the sum order differs from one GPU: 1e-9, not bit-exact
+        CELDA_NCCL_OK(g_nccl.AllReduce(out.p + 1, out.p + 1, 2, ncclDouble, ncclSum, h->comm->comm, st));
+        double v[2];
+        CELDA_CUDA_OK(cudaMemcpyAsync(v, out.p + 1, sizeof(v), cudaMemcpyDeviceToHost, st));
+        CELDA_TRY(chain_sync(h));
+        *perplexity = std::exp(-(v[0] / v[1]));
+        return 0;
+    }
     CELDA_CUDA_OK(cudaMemcpyAsync(perplexity, out.p, sizeof(double), cudaMemcpyDeviceToHost, st));
     return chain_sync(h);
 }

@@ -1,0 +1,172 @@
+"""Host-side chain drivers over the device-resident chain handle: the reference's `while` loops
+(.celda_CG R/celda_CG.R:432-835, .celda_C R/celda_C.R:370-616) without the split heuristics, and the chain
+partitioning of celdaGridSearch (R/celdaGridSearch.R:290-391) over GPUs: one chain per GPU at a time, no
+collective on the data path.
+
+Randomness: `draws="philox"` uses the device generator seeded with (seed, chain); `draws=callable` injects
+(ix_y, u_y, ix_z, u_z) per iteration, which is how a run is reproduced seed for seed from R.
+Label initialisation: "predefined" (zInit / yInit) follows the reference exactly; "random" restates
+.initializeCluster (R/initialize_clusters.R:1-57) with numpy's generator (R's RNG stream is not available).
+"""
+import itertools
+
+import numpy as np
+
+from . import MODEL_C, MODEL_CG, Chain
+
+
+def initialize_cluster(N, length, initial=None, rng=None):
+    """.initializeCluster(N, len, initial = ...) without `fixed` (R/initialize_clusters.R:1-57)."""
+    if initial is not None:
+        initial = np.asarray(initial)
+        vals = np.unique(initial)
+        if vals.size != N or initial.size != length or not np.all(np.isin(vals, np.arange(1, N + 1))):
+            raise ValueError("'initial' needs to be a vector of length 'len' containing N unique values.")
+        return (np.searchsorted(vals, initial) + 1).astype(np.int32)
+    z = rng.integers(1, N + 1, length).astype(np.int32)
+    for i in np.setdiff1d(np.arange(1, N + 1), z):
+        cnt = np.bincount(z, minlength=N + 1)
+        top = int(cnt.argmax())
+        if cnt[top] == 1:
+            raise ValueError("'len' is not long enough to accomodate 'N' unique values")
+        ix = np.flatnonzero(z == top)
+        z[rng.choice(ix)] = i
+    return z
+
+
+def _run_chain(ch, algorithm, maxIter, stopIter, draws, rng, nG, nM, model):
+    """The iteration / best-so-far / stopping logic of R/celda_CG.R:521-755 (splitOnIter = -1, splitOnLast = FALSE)."""
+    ll = [ch.loglik()]
+    z, y = ch.get_state()
+    zBest, yBest, llBest = z, y, ll[0]
+    it, noImp = 1, 0
+    while it <= maxIter and noImp <= stopIter:
+        if draws == "philox":
+            if model == MODEL_CG and algorithm == "Gibbs":
+                temp = ch.iterate_philox()
+            else:
+                if model == MODEL_CG:
+                    ch.sweep_y_philox()
+                ch.sweep_z_em()
+                temp = ch.loglik()
+        else:
+            ixy, uy, ixz, uz = draws(it, rng, nG, nM)
+            temp = ch.iterate(ixy, uy, ixz, uz) if algorithm == "Gibbs" else ch.iterate_em(ixy, uy)
+        if all(temp > v for v in ll) or it == 1:  # R/celda_CG.R:734
+            zBest, yBest = ch.get_state()
+            llBest = temp
+            noImp = 1
+        else:
+            noImp += 1
+        ll.append(temp)
+        it += 1
+    return dict(z=zBest, y=yBest, completeLogLik=np.asarray(ll), finalLogLik=llBest)
+
+
+def celda_CG(counts, sampleLabel, K, L, alpha=1.0, beta=1.0, delta=1.0, gamma=1.0, algorithm="EM", stopIter=10,
+             maxIter=200, seed=12345, nchains=3, zInitialize="random", yInitialize="random", zInit=None, yInit=None,
+             draws="philox", device=0):
+    """celda_CG(x, sampleLabel, K, L, ...) (R/celda_CG.R:85-261) on a CSC count matrix, split heuristics off.
+    Returns the per-chain results and `model`, built like the reference from the LAST chain (quirk Q1,
+    R/celda_CG.R:796-811)."""
+    if algorithm not in ("EM", "Gibbs"):
+        raise ValueError("'algorithm' must be 'EM' or 'Gibbs'")
+    chains = []
+    ch = Chain(counts, sampleLabel, K=K, L=L, alpha=alpha, beta=beta, delta=delta, gamma=gamma, model=MODEL_CG,
+               device=device)
+    try:
+        for c in range(1, nchains + 1):
+            rng = np.random.Generator(np.random.PCG64(seed + c - 1))
+            z = initialize_cluster(K, counts.ncol, zInit if zInitialize == "predefined" else None, rng)
+            y = initialize_cluster(L, counts.nrow, yInit if yInitialize == "predefined" else None, rng)
+            ch.set_state(z, y)
+            ch.seed(seed, stream=c - 1)
+            chains.append(_run_chain(ch, algorithm, maxIter, stopIter, draws, rng, counts.nrow, counts.ncol, MODEL_CG))
+    finally:
+        ch.close()
+    best = max(range(nchains), key=lambda i: chains[i]["finalLogLik"])
+    return dict(chains=chains, model=chains[-1], bestChain=best + 1,
+                params=dict(K=K, L=L, alpha=alpha, beta=beta, delta=delta, gamma=gamma, algorithm=algorithm, seed=seed))
+
+
+def celda_C(counts, sampleLabel, K, alpha=1.0, beta=1.0, algorithm="EM", stopIter=10, maxIter=200, seed=12345,
+            nchains=3, zInitialize="random", zInit=None, device=0):
+    """celda_C with the EM z step (R/celda_C.R:306-616; EM forces stopIter <- 1, :351-353).  The best chain is
+    returned (R/celda_C.R:577-589 does this correctly)."""
+    if algorithm != "EM":
+        raise NotImplementedError("celda_C Gibbs on raw counts is served by cCCalcGibbsProbZ on densified input only")
+    stopIter = 1
+    chains = []
+    ch = Chain(counts, sampleLabel, K=K, alpha=alpha, beta=beta, model=MODEL_C, device=device)
+    try:
+        for c in range(1, nchains + 1):
+            rng = np.random.Generator(np.random.PCG64(seed + c - 1))
+            z = initialize_cluster(K, counts.ncol, zInit if zInitialize == "predefined" else None, rng)
+            ch.set_state(z=z)
+            chains.append(_run_chain(ch, "EM", maxIter, stopIter, "philox", rng, counts.nrow, counts.ncol, MODEL_C))
+    finally:
+        ch.close()
+    best = max(range(nchains), key=lambda i: chains[i]["finalLogLik"])
+    return dict(chains=chains, model=chains[best], bestChain=best + 1, params=dict(K=K, alpha=alpha, beta=beta, seed=seed))
+
+
+# ------------------------------------------------------------------ celdaGridSearch chain partitioning
+def expand_grid(paramsTest, nchains):
+    """base::expand.grid(chain = seq_len(nchains), paramsTest...) (R/celdaGridSearch.R:298-310): the first factor
+    (chain) varies fastest.  Returns a list of dicts with a 1-based 'index'."""
+    names = list(paramsTest)
+    rows = []
+    for combo in itertools.product(*[paramsTest[n] for n in reversed(names)]):
+        vals = dict(zip(reversed(names), combo))
+        for chain in range(1, nchains + 1):
+            rows.append(dict(chain=chain, **{n: vals[n] for n in names}))
+    for i, r in enumerate(rows):
+        r["index"] = i + 1
+    return rows
+
+
+def chain_seed(seed, index, nchains):
+    """allSeeds[ifelse(i %% nchains == 0, nchains, i %% nchains)] with allSeeds = seed + 0..nchains-1
+    (R/celdaGridSearch.R:291-295,381-383)."""
+    k = index % nchains
+    return seed + (nchains if k == 0 else k) - 1
+
+
+def partition_runs(runs, nranks, cost=lambda r: r.get("K", 1) * r.get("L", 1)):
+    """Longest-processing-time-first assignment of grid-search runs to ranks (one chain per GPU at a time).
+    Deterministic; returns a list (per rank) of run lists.  Cost defaults to K * L (work per sweep)."""
+    order = sorted(range(len(runs)), key=lambda i: (-cost(runs[i]), i))
+    load = [0.0] * nranks
+    out = [[] for _ in range(nranks)]
+    for i in order:
+        r = min(range(nranks), key=lambda q: (load[q], q))
+        out[r].append(runs[i])
+        load[r] += cost(runs[i])
+    return out
+
+
+def celdaGridSearch(counts, sampleLabel, paramsTest, maxIter=200, nchains=3, seed=12345, algorithm="Gibbs",
+                    rank=0, nranks=1, device=0, runner=None, gather=None, **fixed):
+    """celdaGridSearch(x, model = "celda_CG", paramsTest, nchains, ...) (R/celdaGridSearch.R:214-439): every
+    (chain, K, L) run is an independent single-chain celda_CG; runs are partitioned over `nranks` GPUs (this rank
+    executes its share), then gathered.  `runner(run, seed)` -> result dict can be injected (tests); `gather` is a
+    callable all-gathering picklable objects across ranks (torch.distributed.all_gather_object in bench/tests)."""
+    runs = expand_grid(paramsTest, nchains)
+    mine = partition_runs(runs, nranks)[rank]
+
+    def default_runner(run, sd):
+        res = celda_CG(counts, sampleLabel, run["K"], run["L"], maxIter=maxIter, nchains=1, seed=sd,
+                       algorithm=algorithm, device=device, **fixed)
+        return res["model"]
+
+    runner = runner or default_runner
+    local = []
+    for run in mine:
+        sd = chain_seed(seed, run["index"], nchains)
+        res = runner(run, sd)
+        local.append(dict(index=run["index"], chain=run["chain"], K=run.get("K"), L=run.get("L"), seed=sd,
+                          logLikelihood=float(res["finalLogLik"]), result=res))
+    everything = [local] if gather is None else gather(local)
+    flat = sorted((r for part in everything for r in part), key=lambda r: r["index"])
+    return dict(runParams=[{k: r[k] for k in ("index", "chain", "K", "L", "seed", "logLikelihood")} for r in flat],
+                resList=[r["result"] for r in flat])

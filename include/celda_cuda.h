@@ -168,6 +168,15 @@ int celda_chain_perplexity(celda_chain *h, double *perplexity);
 int celda_chain_get_tables(celda_chain *h, int *mCPByS, double *nTSByC, double *nTSByCP, double *nGByCP, double *nCP,
                            double *nByC, double *nByG, double *nByTS, int *nGByTS);
 int celda_chain_get_probs(celda_chain *h, double *probsZ /* K x nM */, double *probsY /* L x nG */);
+/* ---- a9 / a2-a7 across GPUs: cells sharded over ranks (one process per GPU), the partial G x K and K x S count
+ * tables combined with an NCCL all-reduce.  id128: a 128-byte ncclUniqueId made on one rank and
+ * distributed by the host (R: a file or socket; bench.py: torch.distributed).  NCCL is dlopen'ed at run time. */
+typedef struct celda_comm celda_comm;
+int celda_comm_unique_id(char *id128);
+int celda_comm_create(celda_comm **out, const char *id128, int nranks, int rank, int device);
+void celda_comm_destroy(celda_comm *c);
+int celda_chain_attach_comm(celda_chain *h, celda_comm *comm);
+
 /* CUDA-event timing on the chain's stream (bench.py): start, then stop returns elapsed ms. */
 int celda_chain_timer_start(celda_chain *h);
 int celda_chain_timer_stop(celda_chain *h, float *ms);
