@@ -806,6 +806,7 @@ __global__ void k_perp_final(const double* __restrict__ partial, int np, const i
         for (int i = 0; i < np; ++i) logPx += partial[i];
         out[0] = dexp(-(logPx / (double)tot));
         out[1] = logPx;
+        out[2] = (double)tot;
     }
 }
 
