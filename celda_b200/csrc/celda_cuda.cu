@@ -106,6 +106,9 @@ struct celda_chain {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool has_state = false;
     DevBuf<int> cp, ci, cx, s, z, y, zprev, yprev;
+    // gene-major twin of the counts (rows sorted by column), built on the device at create for celda_CG / celda_G
+    DevBuf<long long> trp;
+    DevBuf<int> tcol, tx, changed, nchanged;
     DevBuf<int> nTSByC, nGByCP, nTSByCP, nByC, nGByTS, mCPByS;
     DevBuf<long long> nCP, nByG, nByTS;
     DevBuf<double> probsZ, probsY;
@@ -422,10 +425,11 @@ int chain_step_y(celda_chain* h, const int* d_ix, const double* d_u, int doSampl
     CELDA_TRY(launch_sweep_y(h, d_ix, d_u, doSample, 0));
     if (doSample) {
         ProfScope ps(h, 1);
-        const int threads = 256, nwarp = threads / 32;
-        k_rowsum_change_csc<int><<<std::min((h->nM + nwarp - 1) / nwarp, h->sms * 16), threads, 0, h->st>>>(
-            h->nM, h->cp.p, h->ci.p, h->cx.p, h->y.p, h->yprev.p, h->L, h->nTSByC.p);
-        count_launch();
+        CELDA_TRY(h->nchanged.zero(h->st));
+        k_list_changed<<<grid_for(h->nG, 256, h->sms), 256, 0, h->st>>>(h->y.p, h->yprev.p, h->nG, h->changed.p, h->nchanged.p);
+        k_rowsum_change_twin<<<h->sms * 4, 256, 0, h->st>>>(h->changed.p, h->nchanged.p, h->trp.p, h->tcol.p, h->tx.p, h->y.p,
+                                                          h->yprev.p, h->L, h->nTSByC.p);
+        count_launch(2);
     }
     CELDA_CUDA_OK(cudaGetLastError());
     return 0;
@@ -1288,6 +1292,37 @@ int celda_chain_create(celda_chain** out, int device, int model, int nG, int nM,
         CELDA_CUDA_OK(cudaStreamSynchronize(st));
     }
     if (model != CELDA_MODEL_C) {
+        // gene-major twin: stable radix sort of (row index, position) pairs keeps each gene's entries in ascending
+        // column order; row pointers from a histogram scanned on the host (nG values).
+        DevBuf<int> colOf, iota, keysOut, perm, cnt;
+        DevBuf<unsigned char> tmp;
+        CELDA_TRY(colOf.alloc((size_t)Z));
+        CELDA_TRY(iota.alloc((size_t)Z));
+        CELDA_TRY(keysOut.alloc((size_t)Z));
+        CELDA_TRY(perm.alloc((size_t)Z));
+        CELDA_TRY(cnt.alloc(nG));
+        CELDA_TRY(cnt.zero(st));
+        k_csc_cols<<<std::min((nM + 7) / 8, h->sms * 16), 256, 0, st>>>(nM, h->cp.p, colOf.p, iota.p);
+        k_row_counts<<<grid_for(Z, 256, h->sms), 256, 0, st>>>(Z, h->ci.p, cnt.p);
+        int bits = 1;
+        while ((1LL << bits) < nG) ++bits;
+        size_t bytes = 0;
+        CELDA_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->ci.p, keysOut.p, iota.p, perm.p, (int)Z, 0, bits, st));
+        CELDA_TRY(tmp.alloc(bytes));
+        CELDA_CUDA_OK(cub::DeviceRadixSort::SortPairs(tmp.p, bytes, h->ci.p, keysOut.p, iota.p, perm.p, (int)Z, 0, bits, st));
+        CELDA_TRY(h->tcol.alloc((size_t)Z));
+        CELDA_TRY(h->tx.alloc((size_t)Z));
+        k_gather_twin<<<grid_for(Z, 256, h->sms), 256, 0, st>>>(Z, perm.p, colOf.p, h->cx.p, h->tcol.p, h->tx.p);
+        count_launch(7);
+        std::vector<int> hc(nG);
+        CELDA_TRY(cnt.download(hc.data(), nG, st));
+        CELDA_CUDA_OK(cudaStreamSynchronize(st));
+        std::vector<long long> rp((size_t)nG + 1, 0);
+        for (int g = 0; g < nG; ++g) rp[g + 1] = rp[g] + hc[g];
+        CELDA_TRY(h->trp.upload(rp.data(), (size_t)nG + 1, st));
+        CELDA_TRY(h->changed.alloc(nG));
+        CELDA_TRY(h->nchanged.alloc(1));
+        CELDA_CUDA_OK(cudaStreamSynchronize(st));
         CELDA_TRY(h->nTSByC.alloc((size_t)h->L * nM));
         CELDA_TRY(h->nByTS.alloc(h->L));
         CELDA_TRY(h->nGByTS.alloc(h->L));

@@ -859,3 +859,61 @@ __global__ void k_philox_draws(long long n, unsigned k0, unsigned k1, unsigned s
 }
 
 }  // namespace celda
+
+namespace celda {
+
+// ---------------------------------------------------------------------------------------------- gene-major twin
+// column index of every stored entry of a CSC matrix (input of the stable sort that builds the gene-major twin)
+__global__ void k_csc_cols(int nc, const int* __restrict__ p, int* __restrict__ colOf, int* __restrict__ iota) {
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int c = blockIdx.x * nwarp + warp; c < nc; c += gridDim.x * nwarp) {
+        const int e = p[c + 1];
+        for (int t = p[c] + lane; t < e; t += 32) {
+            colOf[t] = c;
+            iota[t] = t;
+        }
+    }
+}
+
+__global__ void k_gather_twin(long long nnz, const int* __restrict__ perm, const int* __restrict__ colOf,
+                              const int* __restrict__ xv, int* __restrict__ tcol, int* __restrict__ tx) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nnz; q += (long long)gridDim.x * blockDim.x) {
+        const int t = perm[q];
+        tcol[q] = colOf[t];
+        tx[q] = xv[t];
+    }
+}
+
+__global__ void k_row_counts(long long nnz, const int* __restrict__ ri, int* __restrict__ cnt) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < nnz; t += (long long)gridDim.x * blockDim.x)
+        atomicAdd(&cnt[ri[t]], 1);
+}
+
+// list[0 .. *count) = indices g with group[g] != pgroup[g]
+__global__ void k_list_changed(const int* __restrict__ group, const int* __restrict__ pgroup, int n, int* __restrict__ list,
+                               int* __restrict__ count) {
+    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n; g += gridDim.x * blockDim.x)
+        if (group[g] != pgroup[g]) list[atomicAdd(count, 1)] = g;
+}
+
+// rowSumByGroupChange (src/matrixSumsSparse.cpp:141-187) through the gene-major twin: only the stored entries of
+// genes whose label changed are visited (the reference scans all of them).  One block per changed gene (strided).
+__global__ void k_rowsum_change_twin(const int* __restrict__ list, const int* __restrict__ count,
+                                     const long long* __restrict__ rp, const int* __restrict__ tcol,
+                                     const int* __restrict__ tx, const int* __restrict__ group,
+                                     const int* __restrict__ pgroup, int L, int* __restrict__ px) {
+    const int n = *count;
+    for (int q = blockIdx.x; q < n; q += gridDim.x) {
+        const int g = list[q];
+        const int a = pgroup[g] - 1, b = group[g] - 1;
+        const long long e = rp[g + 1];
+        for (long long t = rp[g] + threadIdx.x; t < e; t += blockDim.x) {
+            const int v = tx[t];
+            const size_t base = (size_t)tcol[t] * L;
+            atomicAdd(&px[base + b], v);
+            atomicSub(&px[base + a], v);
+        }
+    }
+}
+
+}  // namespace celda
