@@ -456,7 +456,8 @@ class Chain:
         check(lib().celda_chain_profile(self._h, int(enable)))
 
     def profile_get(self):
-        names = ["sweep_y", "rowSumByGroupChange", "sweep_z", "colSumByGroupChange", "loglik"]
+        names = ["sweep_y", "rowSumByGroupChange", "sweep_z", "colSumByGroupChange", "loglik", "rowSumByGroup",
+                 "colSumByGroup"]
         out = {}
         for w, n in enumerate(names):
             ms, nl = C.c_double(0), C.c_longlong(0)

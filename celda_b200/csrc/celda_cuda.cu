@@ -137,8 +137,8 @@ struct celda_chain {
     int npG = 0;
     // profiling
     bool profile = false;
-    double prof_ms[5] = {0, 0, 0, 0, 0};
-    long long prof_launches[5] = {0, 0, 0, 0, 0};
+    double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long prof_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
 
     ~celda_chain() {
@@ -218,8 +218,11 @@ int chain_decompose(celda_chain* h) {
     const int sms = h->sms;
     if (h->model != CELDA_MODEL_C) {  // nTSByC = rowSumByGroup(counts, y, L)
         const int threads = 256, nwarp = threads / 32;
-        k_rowsum_csc<int><<<std::min((h->nM + nwarp - 1) / nwarp, sms * 8), threads, sizeof(int) * nwarp * h->L, st>>>(
-            h->nM, h->cp.p, h->ci.p, h->cx.p, h->y.p, h->L, h->nTSByC.p, nullptr);
+        {
+            ProfScope ps(h, 5);
+            k_rowsum_csc<int><<<std::min((h->nM + nwarp - 1) / nwarp, sms * 8), threads, sizeof(int) * nwarp * h->L, st>>>(
+                h->nM, h->cp.p, h->ci.p, h->cx.p, h->y.p, h->L, h->nTSByC.p, nullptr);
+        }
         count_launch();
         CELDA_TRY(h->nByTS.zero(st));
         k_fill_int<<<1, 256, 0, st>>>(h->nGByTS.p, h->L, 1);
@@ -232,8 +235,11 @@ int chain_decompose(celda_chain* h) {
         DevBuf<int>& ng = h->comm ? h->nGByCP_loc : h->nGByCP;
         DevBuf<int>& mm = h->comm ? h->mCPByS_loc : h->mCPByS;
         CELDA_TRY(ng.zero(st));
-        k_colsum_csc<int><<<std::min((h->nM + nwarp - 1) / nwarp, sms * 16), threads, 0, st>>>(
-            h->nM, h->cp.p, h->ci.p, h->cx.p, h->z.p, h->K, ng.p);
+        {
+            ProfScope ps(h, 6);
+            k_colsum_csc<int><<<std::min((h->nM + nwarp - 1) / nwarp, sms * 16), threads, 0, st>>>(
+                h->nM, h->cp.p, h->ci.p, h->cx.p, h->z.p, h->K, ng.p);
+        }
         CELDA_TRY(mm.zero(st));
         k_table_zs<<<grid_for(h->nM, 256, sms), 256, 0, st>>>(h->z.p, h->s.p, h->nM, h->K, mm.p);
         count_launch(2);
@@ -1695,7 +1701,7 @@ int celda_chain_profile(celda_chain* h, int enable) {
     CELDA_CUDA_OK(cudaSetDevice(h->device));
     CELDA_TRY(chain_sync(h));
     h->profile = enable != 0;
-    for (int q = 0; q < 5; ++q) {
+    for (int q = 0; q < 8; ++q) {
         h->prof_ms[q] = 0;
         h->prof_launches[q] = 0;
     }
@@ -1704,11 +1710,11 @@ int celda_chain_profile(celda_chain* h, int enable) {
 }
 
 int celda_chain_profile_get(celda_chain* h, int which, double* ms, long long* launches, long long* rounds) {
-    if (which < 0 || which > 4) return fail("profile_get: which must be 0..4");
+    if (which < 0 || which > 6) return fail("profile_get: which must be 0..6");
     CELDA_CUDA_OK(cudaSetDevice(h->device));
     CELDA_TRY(chain_sync(h));
     long long stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    CELDA_CUDA_OK(cudaMemcpy(stats, h->wb.stats.p + 8 * which, sizeof(stats), cudaMemcpyDeviceToHost));
+    if (which < 5) CELDA_CUDA_OK(cudaMemcpy(stats, h->wb.stats.p + 8 * which, sizeof(stats), cudaMemcpyDeviceToHost));
     if (ms) *ms = h->prof_ms[which];
     if (launches) *launches = h->prof_launches[which];
     if (rounds) {

@@ -70,7 +70,18 @@ __global__ void k_rowsum_csc(int nc, const int* __restrict__ p, const int* __res
         __syncwarp();
         T tot = 0;
         const int e = p[c + 1];
-        for (int t = p[c] + lane; t < e; t += 32) {
+        int t = p[c] + lane;
+        for (; t + 96 < e; t += 128) {  // four independent index/value/label loads in flight per lane
+            const int r0 = ri[t], r1 = ri[t + 32], r2 = ri[t + 64], r3 = ri[t + 96];
+            const T v0 = xv[t], v1 = xv[t + 32], v2 = xv[t + 64], v3 = xv[t + 96];
+            const int g0 = group[r0], g1 = group[r1], g2 = group[r2], g3 = group[r3];
+            atomicAdd(&acc[g0 - 1], v0);
+            atomicAdd(&acc[g1 - 1], v1);
+            atomicAdd(&acc[g2 - 1], v2);
+            atomicAdd(&acc[g3 - 1], v3);
+            tot += v0 + v1 + v2 + v3;
+        }
+        for (; t < e; t += 32) {
             const T v = xv[t];
             atomicAdd(&acc[group[ri[t]] - 1], v);
             tot += v;
@@ -92,7 +103,16 @@ __global__ void k_colsum_csc(int nc, const int* __restrict__ p, const int* __res
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int c = blockIdx.x * nwarp + warp; c < nc; c += gridDim.x * nwarp) {
         const int g = group[c] - 1, e = p[c + 1];
-        for (int t = p[c] + lane; t < e; t += 32) atomicAdd(&out[(size_t)ri[t] * K + g], xv[t]);
+        int t = p[c] + lane;
+        for (; t + 96 < e; t += 128) {
+            const int r0 = ri[t], r1 = ri[t + 32], r2 = ri[t + 64], r3 = ri[t + 96];
+            const T v0 = xv[t], v1 = xv[t + 32], v2 = xv[t + 64], v3 = xv[t + 96];
+            atomicAdd(&out[(size_t)r0 * K + g], v0);
+            atomicAdd(&out[(size_t)r1 * K + g], v1);
+            atomicAdd(&out[(size_t)r2 * K + g], v2);
+            atomicAdd(&out[(size_t)r3 * K + g], v3);
+        }
+        for (; t < e; t += 32) atomicAdd(&out[(size_t)ri[t] * K + g], xv[t]);
     }
 }
 

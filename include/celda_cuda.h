@@ -181,7 +181,8 @@ int celda_chain_attach_comm(celda_chain *h, celda_comm *comm);
 int celda_chain_timer_start(celda_chain *h);
 int celda_chain_timer_stop(celda_chain *h, float *ms);
 /* Per-kernel accumulated device time (ms) and launch counts since the last reset, for roofline accounting:
- * which = 0 y sweep, 1 rowSumByGroupChange, 2 z sweep, 3 colSumByGroupChange, 4 log-likelihood. */
+ * which = 0 y sweep, 1 rowSumByGroupChange, 2 z sweep (Gibbs or EM), 3 colSumByGroupChange, 4 log-likelihood,
+ * 5 rowSumByGroup (decompose), 6 colSumByGroup (decompose). */
 int celda_chain_profile(celda_chain *h, int enable);
 int celda_chain_profile_get(celda_chain *h, int which, double *ms, long long *launches,
                             long long *stats /* [7]: rounds, units, movers, CTA-0 clocks in commit / units / draw / barriers */);
