@@ -43,7 +43,7 @@ static inline int alias_draw(const alias_t *t, uint64_t *s)
 static int cmp_int(const void *a, const void *b) { return (*(const int *)a > *(const int *)b) - (*(const int *)a < *(const int *)b); }
 
 typedef struct {
-    int nG, tid, nthreads; long long nM; const int *z, *N, *mod_off, *mod_genes; const alias_t *aphi, *apsi;
+    int nG, tid, nthreads; long long nM, cell_offset; const int *z, *N, *mod_off, *mod_genes; const alias_t *aphi, *apsi;
     uint64_t seed; int **crow, **cval, *cnnz;
 } job_t;
 
@@ -53,7 +53,7 @@ static void *worker(void *arg)
     int nG = j->nG;
     int *dense = calloc(nG, sizeof(int)), *touched = malloc(sizeof(int) * nG);
     for (long long c = j->tid; c < j->nM; c += j->nthreads) {
-        uint64_t sm = j->seed ^ (0xd1342543de82ef95ULL * (uint64_t)(c + 1)), s[4];
+        uint64_t sm = j->seed ^ (0xd1342543de82ef95ULL * (uint64_t)(c + j->cell_offset + 1)), s[4];
         for (int q = 0; q < 4; q++) s[q] = splitmix(&sm);
         const alias_t *ap = &j->aphi[j->z[c] - 1];
         int nt = 0;
@@ -74,10 +74,11 @@ static void *worker(void *arg)
 /* phi: K x L row-major (cell population -> module distribution); psi: concatenated per-module gene
  * distributions, genes of module l are mod_genes[mod_off[l] .. mod_off[l+1]) with probabilities psi[same range].
  * Output: CSC. colptr int64[nM+1]; *rows_out / *vals_out malloc'd (free with sim_free). Returns nnz.
- * The result depends only on (seed, inputs), not on nthreads: one RNG stream per cell. */
+ * The result depends only on (seed, inputs), not on nthreads: one RNG stream per cell, keyed by the global cell
+ * index cell_offset + c, so a rank can generate just its own cell range of a larger matrix. */
 long long sim_counts(int nG, long long nM, int K, int L, const int *z /* 1-based */, const int *N, const double *phi,
                      const int *mod_off, const int *mod_genes, const double *psi, uint64_t seed, int nthreads,
-                     long long *colptr, int **rows_out, int **vals_out)
+                     long long cell_offset, long long *colptr, int **rows_out, int **vals_out)
 {
     alias_t *aphi = malloc(sizeof(alias_t) * K), *apsi = malloc(sizeof(alias_t) * L);
     for (int k = 0; k < K; k++) alias_build(&aphi[k], phi + (size_t)k * L, L);
@@ -88,7 +89,7 @@ long long sim_counts(int nG, long long nM, int K, int L, const int *z /* 1-based
     if (nthreads > 64) nthreads = 64;
     pthread_t th[64]; job_t jobs[64];
     for (int t = 0; t < nthreads; t++) {
-        jobs[t] = (job_t){nG, t, nthreads, nM, z, N, mod_off, mod_genes, aphi, apsi, seed, crow, cval, cnnz};
+        jobs[t] = (job_t){nG, t, nthreads, nM, cell_offset, z, N, mod_off, mod_genes, aphi, apsi, seed, crow, cval, cnnz};
         pthread_create(&th[t], NULL, worker, &jobs[t]);
     }
     for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);

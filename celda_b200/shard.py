@@ -54,24 +54,27 @@ class Comm:
 
 
 class ShardedChainC:
-    """celda_C chain over this rank's cell range; the tables it exposes are the global ones."""
+    """celda_C chain over this rank's cell range; the tables it exposes are the global (all-reduced) ones."""
 
-    def __init__(self, counts, sampleLabel, K, comm, alpha=1.0, beta=1.0, nS=None):
-        self.bounds = partition_columns_by_nnz(counts.p, comm.nranks)
-        self.lo, self.hi = self.bounds[comm.rank], self.bounds[comm.rank + 1]
-        s = np.asarray(sampleLabel, dtype=np.int32)
-        self.nS = int(s.max()) if nS is None else nS
-        local = shard_csc(counts, self.lo, self.hi)
-        self.chain = Chain(local, s[self.lo:self.hi], K=K, alpha=alpha, beta=beta, model=MODEL_C, device=comm.device)
-        # every rank must size its K x S table for ALL samples, not only those present in its shard
-        if self.chain.nS != self.nS:
-            self.chain.close()
-            s_loc = s[self.lo:self.hi].copy()
-            self.chain = _chain_with_ns(local, s_loc, K, alpha, beta, comm.device, self.nS)
+    def __init__(self, local_counts, s_local, K, comm, nS, alpha=1.0, beta=1.0, lo=0):
+        """local_counts: this rank's columns; s_local: their sample labels; nS: number of samples over ALL ranks
+        (every rank sizes its K x S table for all samples, not only those present in its shard)."""
+        self.lo, self.hi = lo, lo + local_counts.ncol
+        s_loc = np.ascontiguousarray(s_local, dtype=np.int32)
+        self.chain = _chain_with_ns(local_counts, s_loc, K, alpha, beta, comm.device, int(nS))
         check(lib().celda_chain_attach_comm(self.chain._h, comm._c))
 
-    def set_state(self, z):
-        self.chain.set_state(z=np.asarray(z, dtype=np.int32)[self.lo:self.hi])
+    @classmethod
+    def from_full(cls, counts, sampleLabel, K, comm, alpha=1.0, beta=1.0):
+        """Split a full matrix into column ranges balanced by stored entries and keep this rank's."""
+        b = partition_columns_by_nnz(counts.p, comm.nranks)
+        lo, hi = b[comm.rank], b[comm.rank + 1]
+        s = np.asarray(sampleLabel, dtype=np.int32)
+        return cls(shard_csc(counts, lo, hi), s[lo:hi], K, comm, int(s.max()), alpha, beta, lo=lo)
+
+    def set_state(self, z_full=None, z_local=None):
+        z = np.asarray(z_full, dtype=np.int32)[self.lo:self.hi] if z_local is None else z_local
+        self.chain.set_state(z=z)
 
     def iterate_em(self):
         return self.chain.iterate_em()

@@ -26,7 +26,7 @@ def main():
     ids = [shard.Comm.unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     comm = shard.Comm(ids[0], world, rank, local)
-    sh = shard.ShardedChainC(A, s, K, comm)
+    sh = shard.ShardedChainC.from_full(A, s, K, comm)
     sh.set_state(z0)
     ref = cb.Chain(A, s, K=K, model=cb.MODEL_C, device=local)
     ref.set_state(z=z0)
