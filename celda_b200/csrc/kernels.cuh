@@ -622,14 +622,34 @@ __global__ void k_em_probs(int R, long long nM, int K, const int* __restrict__ p
 #pragma unroll
         for (int q = 0; q < KPL; ++q) acc[q] = 0.0;
         if (SPARSE) {
+            // The column's (row, value) pairs are fetched 32 at a time, coalesced, one per lane, and handed round by
+            // shuffles; four phi rows are requested before they are consumed so several L2 requests are in flight.
+            // The products are still added in storage order.
             const int e = p[c + 1];
-            for (int t = p[c]; t < e; ++t) {
-                const double x = (double)xv[t];
-                const double* row = phi + (size_t)ri[t] * K;
+            for (int t0 = p[c]; t0 < e; t0 += 32) {
+                const int cnt = min(32, e - t0);
+                const int myr = (lane < cnt) ? ri[t0 + lane] : 0;
+                const double myx = (lane < cnt) ? (double)xv[t0 + lane] : 0.0;
+                for (int u = 0; u < cnt; u += 4) {
+                    const double* row[4];
+                    double x[4];
 #pragma unroll
-                for (int q = 0; q < KPL; ++q) {
-                    const int k = lane + 32 * q;
-                    if (k < K) acc[q] += row[k] * x;
+                    for (int j = 0; j < 4; ++j) {
+                        row[j] = phi + (size_t)__shfl_sync(0xffffffffu, myr, (u + j) & 31) * K;
+                        x[j] = __shfl_sync(0xffffffffu, myx, (u + j) & 31);
+                    }
+#pragma unroll
+                    for (int q = 0; q < KPL; ++q) {
+                        const int k = lane + 32 * q;
+                        if (k < K) {
+                            double v[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) v[j] = row[j][k];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                if (u + j < cnt) acc[q] += v[j] * x[j];
+                        }
+                    }
                 }
             }
         } else {
