@@ -624,8 +624,10 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                 const int sgn = isCur ? -1 : 1;
 #pragma unroll 2
                 for (int c = 0; c < C; ++c) {
-                    const double fresh = lg_tab(lgtab, T, (long long)trow[c] + sgn * __ldg(x + c), a.beta);
+                    const int xc = __ldg(x + c);  // same gene on (almost) every lane of the warp: a uniform branch
                     const double cached = lrow[c];
+                    // a zero count leaves the argument at t + beta, whose lgamma is the cached entry (same bits)
+                    const double fresh = (xc == 0) ? cached : lg_tab(lgtab, T, (long long)trow[c] + sgn * xc, a.beta);
                     p += isCur ? cached : fresh;
                     p -= isCur ? fresh : cached;
                 }
@@ -663,8 +665,9 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                 const double* lrow = lgt_s + l * Cp;
                 // first loop of cG_CalcGibbsProbY (:212-225): per column one fresh lgamma and one cached one
                 for (int c = lane; c < C; c += 32) {
-                    const double fresh = lg_tab(lgtab, T, (long long)trow[c] + (isCur ? -x[c] : x[c]), a.beta);
                     const double cached = lrow[c];
+                    const double fresh =
+                        (x[c] == 0) ? cached : lg_tab(lgtab, T, (long long)trow[c] + (isCur ? -x[c] : x[c]), a.beta);
                     scr[2 * c] = isCur ? cached : fresh;      // added
                     scr[2 * c + 1] = isCur ? fresh : cached;  // subtracted
                 }
