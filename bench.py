@@ -165,7 +165,7 @@ def run_reference(a):
         ixy, uy, ixz, uz = draw_inputs(rng, 1, d["nG"], d["nM"])
 
         def one(_):
-            t = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in tables.items()}
+            t = {k: (v.copy(order="F") if isinstance(v, np.ndarray) else v) for k, v in tables.items()}
             return cpu_iteration_sample(d, a, z, y, ixy[0], uy[0], ixz[0], uz[0], 1000, 200, t)
 
         t0 = time.perf_counter()

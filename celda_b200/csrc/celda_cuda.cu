@@ -81,7 +81,7 @@ struct SweepBufs {
     DevBuf<int> spec, status;
     DevBuf<unsigned> barrier;
     DevBuf<long long> stats;  // [which][8]
-    int Wmax = 8192, Wmin = 32, lgT = 2048;
+    int Wmax = 16384, Wmin = 32, lgT = 2048;
     int alloc(int ncand, cudaStream_t st) {
         CELDA_TRY(bufP.alloc((size_t)Wmax * ncand));
         CELDA_TRY(bufA.alloc((size_t)Wmax * ncand));
