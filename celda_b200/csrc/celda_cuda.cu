@@ -327,17 +327,19 @@ int chain_loglik_async(celda_chain* h) {
 
 // Window sizes (items).  unit: the item count whose units (items x candidates) fill one grid-wide lane pass;
 // full: the largest multiple of it that fits the ring buffer, so lane-per-unit rounds leave no thread idle.
-void window_sizes(const SweepBufs& b, int sms, int threads, int ncand, int* full, int* unit) {
+void window_sizes(const SweepBufs& b, int sms, int threads, int ncand, int cap, int* full, int* unit) {
     const long long lanes = (long long)sms * threads;
     long long u = std::max<long long>(lanes / ncand, b.Wmin);
-    if (u > b.Wmax) u = b.Wmax;
+    if (u > cap) u = cap;
     *unit = (int)u;
-    *full = (int)(std::max<long long>(1, b.Wmax / u) * u);
+    *full = (int)(std::max<long long>(1, cap / u) * u);
 }
 
-SweepWork make_work(SweepBufs& b, int sms, int threads, int ncand, int which) {
+// cap: largest steady-state window.  Items behind a mover are patched and redrawn every round, so a sweep whose
+// items keep moving (genes of low count in the y sweep) wants a smaller window than one that is quiet.
+SweepWork make_work(SweepBufs& b, int sms, int threads, int ncand, int which, int cap) {
     int wfull, wunit;
-    window_sizes(b, sms, threads, ncand, &wfull, &wunit);
+    window_sizes(b, sms, threads, ncand, std::min(cap, b.Wmax), &wfull, &wunit);
     return SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
                      b.stats.p + 8 * which, b.Wmax, wfull, wunit, b.Wmin, b.lgT};
 }
@@ -346,7 +348,7 @@ SweepWork make_work(SweepBufs& b, int sms, int threads, int ncand, int which) {
 int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     int threads = 1024;
     if (z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32) > 220 * 1024) threads = 512;
-    a.w = make_work(b, sms, threads, a.K, which);
+    a.w = make_work(b, sms, threads, a.K, which, 16384);
     const size_t smem = z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32);
     if (smem > 220 * 1024) return fail("z sweep: K=%d x R=%d tables need %zu bytes of shared memory (> 220 KB)", a.K, a.R, smem);
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -360,7 +362,7 @@ int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
 int run_sweep_y(YArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     int threads = 1024;
     if (y_sweep_smem(a.L, a.ncol, b.lgT, threads / 32) > 220 * 1024) threads = 512;
-    a.w = make_work(b, sms, threads, a.L, which);
+    a.w = make_work(b, sms, threads, a.L, which, 8192);
     const size_t smem = y_sweep_smem(a.L, a.ncol, b.lgT, threads / 32);
     if (smem > 220 * 1024) return fail("y sweep: L=%d x K=%d tables need %zu bytes of shared memory (> 220 KB)", a.L, a.ncol, smem);
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
