@@ -121,6 +121,7 @@ struct celda_chain {
     DevBuf<double> uy, uz;
     DevBuf<double> llPartial, llOut;
     DevBuf<double> phiBuf, thetaBuf;  // EM step
+    DevBuf<double> lgt;               // celda_G: lgamma(nTSByC + beta), maintained by the y sweep
     // Philox mode
     unsigned long long ph_seed = 0, ph_stream = 0;
     unsigned ph_sweep = 0;
@@ -224,6 +225,11 @@ int chain_decompose(celda_chain* h) {
                 h->nM, h->cp.p, h->ci.p, h->cx.p, h->y.p, h->L, h->nTSByC.p, nullptr);
         }
         count_launch();
+        if (h->model == CELDA_MODEL_G) {
+            k_lgt_fill<<<grid_for((long long)h->L * h->nM, 256, sms), 256, 0, st>>>(h->nTSByC.p, (long long)h->L * h->nM, h->beta,
+                                                                                 h->lgt.p);
+            count_launch();
+        }
         CELDA_TRY(h->nByTS.zero(st));
         k_fill_int<<<1, 256, 0, st>>>(h->nGByTS.p, h->L, 1);
         k_module_totals<<<grid_for(h->nG, 256, sms), 256, 0, st>>>(h->y.p, h->nByG.p, h->nG,
@@ -373,6 +379,28 @@ int run_sweep_y(YArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     return 0;
 }
 
+int run_sweep_yg(YGArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
+    int threads = 1024;
+    if (yg_sweep_smem(a.L, b.lgT, threads / 32) > 220 * 1024) threads = 512;
+    if (yg_sweep_smem(a.L, b.lgT, threads / 32) > 220 * 1024) threads = 256;
+    const size_t smem = yg_sweep_smem(a.L, b.lgT, threads / 32);
+    if (smem > 220 * 1024) return fail("celda_G y sweep: L=%d needs %zu bytes of shared memory (> 220 KB)", a.L, smem);
+    // window: whole waves of (gene group) x (module chunk) tasks over the grid
+    const int nwarp = threads / 32, nchunk = (a.L + 31) / 32;
+    long long unit = std::max<long long>(nwarp, (long long)nwarp * sms / nchunk / nwarp * nwarp);
+    const long long cap = std::min<long long>(b.Wmax, 8192);
+    if (unit > cap) unit = cap / nwarp * nwarp;
+    const long long full = std::max<long long>(1, cap / unit) * unit;
+    a.w = SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
+                    b.stats.p + 8 * which, b.Wmax, (int)full, (int)unit, std::max(b.Wmin, nwarp), b.lgT};
+    CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_yg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CELDA_CUDA_OK(cudaMemsetAsync(b.barrier.p, 0, sizeof(unsigned), st));
+    void* args[] = {&a};
+    CELDA_CUDA_OK(cudaLaunchCooperativeKernel((void*)k_sweep_yg, dim3(sms), dim3(threads), args, smem, st));
+    count_launch();
+    return 0;
+}
+
 int sweep_status(int stv) {
     if (stv == -1) return fail("sample.int would take the Walker alias branch (> 200 likely categories): not supported");
     if (stv == -2) return fail("NA in probability vector");
@@ -428,7 +456,31 @@ int launch_sweep_y(celda_chain* h, const int* d_ix, const double* d_u, int doSam
 
 // y sweep + rowSumByGroupChange (R/celda_CG.R:544-564)
 int chain_step_y(celda_chain* h, const int* d_ix, const double* d_u, int doSample) {
-    if (h->model != CELDA_MODEL_CG) return fail("sweep_y: only the celda_CG chain is implemented on this handle");
+    if (h->model == CELDA_MODEL_C) return fail("sweep_y: celda_C has no feature modules");
+    if (h->model == CELDA_MODEL_G) {  // raw counts against nTSByC (L x nM); the kernel keeps nTSByC itself current
+        ProfScope ps(h, 0);
+        YGArgs a{};
+        a.nG = h->nG;
+        a.L = h->L;
+        a.nM = h->nM;
+        a.rp = h->trp.p;
+        a.tcol = h->tcol.p;
+        a.tx = h->tx.p;
+        a.nByG = h->nByG.p;
+        a.y = h->y.p;
+        a.t = h->nTSByC.p;
+        a.lgt = h->lgt.p;
+        a.nByTS = h->nByTS.p;
+        a.nGByTS = h->nGByTS.p;
+        a.beta = h->beta;
+        a.gamma = h->gamma;
+        a.delta = h->delta;
+        a.ix = d_ix;
+        a.u = d_u;
+        a.doSample = doSample;
+        a.probs = h->probsY.p;
+        return run_sweep_yg(a, h->wb, h->sms, 0, h->st);
+    }
     CELDA_CUDA_OK(cudaMemcpyAsync(h->yprev.p, h->y.p, sizeof(int) * h->nG, cudaMemcpyDeviceToDevice, h->st));
     CELDA_TRY(launch_sweep_y(h, d_ix, d_u, doSample, 0));
     if (doSample) {
@@ -1332,6 +1384,7 @@ int celda_chain_create(celda_chain** out, int device, int model, int nG, int nM,
         CELDA_TRY(h->nchanged.alloc(1));
         CELDA_CUDA_OK(cudaStreamSynchronize(st));
         CELDA_TRY(h->nTSByC.alloc((size_t)h->L * nM));
+        if (model == CELDA_MODEL_G) CELDA_TRY(h->lgt.alloc((size_t)h->L * nM));
         CELDA_TRY(h->nByTS.alloc(h->L));
         CELDA_TRY(h->nGByTS.alloc(h->L));
         CELDA_TRY(h->probsY.alloc((size_t)h->L * nG));
@@ -1519,6 +1572,20 @@ int celda_chain_iterate(celda_chain* h, const int* ix_y, const double* u_y, cons
     CELDA_CUDA_OK(cudaSetDevice(h->device));
     if (!h->has_state) return fail("set_state must be called first");
     cudaStream_t st = h->st;
+    if (h->model == CELDA_MODEL_C) return fail("iterate: the celda_C chain iterates with celda_chain_iterate_em");
+    if (h->model == CELDA_MODEL_G) {  // .celda_G loop body (R/celda_G.R:400-424): y sweep, log-likelihood
+        if (ix_y && u_y) {
+            CELDA_TRY(validate_order(ix_y, h->nG, "ix_y"));
+            CELDA_CUDA_OK(cudaMemcpyAsync(h->ixy.p, ix_y, sizeof(int) * h->nG, cudaMemcpyHostToDevice, st));
+            CELDA_CUDA_OK(cudaMemcpyAsync(h->uy.p, u_y, sizeof(double) * h->nG, cudaMemcpyHostToDevice, st));
+        } else {
+            CELDA_TRY(chain_philox_draws(h, h->nG, h->ixy.p, h->uy.p));
+        }
+        CELDA_TRY(chain_step_y(h, h->ixy.p, h->uy.p, 1));
+        CELDA_TRY(chain_loglik_async(h));
+        CELDA_CUDA_OK(cudaMemcpyAsync(ll, h->llOut.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        return chain_check_status(h);
+    }
     if (!ix_y && !u_y && !ix_z && !u_z) {  // Philox mode
         CELDA_TRY(chain_philox_draws(h, h->nG, h->ixy.p, h->uy.p));
         CELDA_TRY(chain_philox_draws(h, h->nM, h->ixz.p, h->uz.p));

@@ -775,4 +775,243 @@ inline size_t y_sweep_smem(int L, int C, int T, int nwarp) {
            sizeof(int) * ((size_t)L * Cp + L + 4);
 }
 
+// ------------------------------------------------------------------------------------------------ y sweep, celda_G
+// .cGCalcGibbsProbY on the RAW counts (R/celda_G.R:401-415, 602-660): every gene's row is scanned over ALL cells
+// against nTSByC (L x nM), zero counts included -- cG_CalcGibbsProbY adds and subtracts the same table entry for
+// them (src/cG_calcGibbsProbY.cpp:218-222), which is not a floating-point no-op, so bit parity needs the full
+// column scan.  Layout: nTSByC (t) and its cached lgamma (lgt) stay in HBM; one CTA task = (one gene per warp of the
+// CTA, consecutive in the window) x (32 consecutive modules): warp <-> gene, lane <-> module.  The lgt tile of a column range is staged
+// in shared memory once and shared by the 32 genes, each warp walks it in column order with its gene's
+// gene-major twin row as a cursor (a warp-uniform test), evaluating a fresh lgamma only where the count is > 0.
+struct YGArgs {
+    int nG, L;
+    long long nM;
+    const long long* rp;   // gene-major twin: row pointers [nG + 1]
+    const int* tcol;       //   column of each stored entry, ascending within a gene
+    const int* tx;         //   value
+    const long long* nByG;
+    int* y;                // [nG] 1-based, updated
+    int* t;                // nTSByC, L x nM column-major, updated
+    double* lgt;           // lgamma(t + beta), same layout, maintained
+    long long* nByTS;      // [L], updated
+    int* nGByTS;           // [L], updated
+    double beta, gamma, delta;
+    const int* ix;
+    const double* u;
+    int doSample;
+    double* probs;         // L x nG or null
+    SweepWork w;
+};
+
+constexpr int YG_TILE = 128;  // columns per staged tile
+
+__global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int L = a.L, T = a.w.lgT;
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int scratchD = 2 * L + (L + 1) / 2 + 2;
+    double* lgtab = reinterpret_cast<double*>(smem_raw);
+    double* tile = lgtab + T;                             // [YG_TILE][32]
+    double* scratch_all = tile + YG_TILE * 32;
+    long long* T_s = reinterpret_cast<long long*>(scratch_all + (size_t)nwarp * scratchD);
+    int* g_s = reinterpret_cast<int*>(T_s + L);
+    int* s_misc = g_s + L;
+    double* scr = scratch_all + (size_t)warp * scratchD;
+    const int gwarp = blockIdx.x * nwarp + warp, tw = gridDim.x * nwarp;
+    const long long nM = a.nM;
+    const int nchunk = (L + 31) / 32;
+
+    for (int q = threadIdx.x; q < T; q += blockDim.x) lgtab[q] = dlgamma((double)q + a.beta);
+    for (int q = threadIdx.x; q < L; q += blockDim.x) {
+        T_s[q] = a.nByTS[q];
+        g_s[q] = a.nGByTS[q];
+    }
+    __syncthreads();
+
+    long long pos = 0, hi = 0, prev_end = 0;
+    int W = a.w.Wfull, nd = 0, da = -1, db = -1, gavg = a.w.Wfull;
+    bool have_spec = false;
+    unsigned bar_target = 0;
+    long long rounds = 0, units_done = 0, movers = 0;
+
+    while (true) {
+        bool committed = false;
+        if (have_spec) {
+            const int nwin = (int)(prev_end - pos);
+            const int first = block_first_mover(a.w.spec, nwin, s_misc);
+            if (first < 0) {
+                pos = prev_end;
+                hi = pos;
+                nd = 0;
+                gavg = min(2 * gavg + nwin, 1 << 24);
+                W = min(2 * W, a.w.Wfull);
+            } else {
+                const long long tt = pos + first;
+                const int i = a.ix[tt] - 1;
+                const int packed = __ldcg(a.w.spec + first);
+                da = packed >> 16;
+                db = packed & 0xffff;
+                // the two table rows change only where the gene has counts: the grid shares the gene's entries
+                const long long e0 = a.rp[i], e1 = a.rp[i + 1];
+                for (long long e = e0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < e1;
+                     e += (long long)gridDim.x * blockDim.x) {
+                    const size_t base = (size_t)a.tcol[e] * L;
+                    const int xv = a.tx[e];
+                    const int na = __ldcg(a.t + base + da) - xv, nb = __ldcg(a.t + base + db) + xv;
+                    a.t[base + da] = na;
+                    a.t[base + db] = nb;
+                    a.lgt[base + da] = lg_tab(lgtab, T, na, a.beta);
+                    a.lgt[base + db] = lg_tab(lgtab, T, nb, a.beta);
+                }
+                if (threadIdx.x == 0) {
+                    const long long Ni = a.nByG[i];
+                    g_s[da] -= 1;
+                    g_s[db] += 1;
+                    T_s[da] -= Ni;
+                    T_s[db] += Ni;
+                    if (blockIdx.x == 0) a.y[i] = db + 1;
+                }
+                ++movers;
+                gavg = max(1, (3 * gavg + first + 1) / 4);
+                W = (int)max((long long)a.w.Wmin, min(4LL * gavg, (long long)a.w.Wfull));
+                W = ((W + 31) / 32) * 32;
+                pos = tt + 1;
+                hi = min(prev_end, pos + W);
+                nd = 2;
+                committed = true;
+            }
+        }
+        if (pos >= a.nG) break;
+        if (committed) grid_sync(a.w.barrier, bar_target);  // table rows a, b are visible before they are read
+        const long long end = max(hi, min(pos + (long long)W, (long long)a.nG));
+        const int nwin = (int)(end - pos);
+        // ---- tasks: patch = (32 carried genes) x {da, db}; fresh = (32 new genes) x (32-module chunk)
+        const long long nPatchGrp = (nd == 2) ? (hi - pos + nwarp - 1) / nwarp : 0;
+        const long long nFreshGrp = (end - hi + nwarp - 1) / nwarp;
+        const long long ntask = nPatchGrp + nFreshGrp * nchunk;
+        ++rounds;
+        for (long long task = blockIdx.x; task < ntask; task += gridDim.x) {
+            long long tgene;   // visiting position of this warp's gene
+            int l;             // this lane's module, -1 = inactive lane
+            bool valid;
+            if (task < nPatchGrp) {
+                tgene = pos + task * nwarp + warp;
+                valid = tgene < hi;
+                l = (lane == 0) ? da : (lane == 1 ? db : -1);
+            } else {
+                const long long q = task - nPatchGrp;
+                tgene = hi + (q / nchunk) * nwarp + warp;
+                valid = tgene < end;
+                l = (int)(q % nchunk) * 32 + lane;
+                if (l >= L) l = -1;
+            }
+            const int i = valid ? a.ix[tgene] - 1 : 0;
+            const int cur = valid ? a.y[i] - 1 : -1;
+            const bool active = valid && l >= 0;
+            const bool isCur = active && (l == cur);
+            const int lsafe = (l >= 0) ? l : 0;
+            // module of lane `lane` inside the staged tile: patch tasks stage rows da, db in slots 0, 1
+            long long nz = valid ? a.rp[i] : 0;
+            const long long nzEnd = valid ? a.rp[i + 1] : 0;
+            long long nextcol = (nz < nzEnd) ? a.tcol[nz] : (1LL << 60);
+            double p = 0.0;
+            for (long long c0 = 0; c0 < nM; c0 += YG_TILE) {
+                const int tc = (int)min((long long)YG_TILE, nM - c0);
+                __syncthreads();
+                // stage lgt[c0 .. c0 + tc) for this task's 32 modules: warp w loads columns w, w + 32, ...
+                for (int cc = warp; cc < tc; cc += nwarp)
+                    tile[cc * 32 + lane] = (l >= 0) ? __ldcg(a.lgt + (size_t)(c0 + cc) * L + lsafe) : 0.0;
+                __syncthreads();
+                if (active) {
+                    for (int cc = 0; cc < tc; ++cc) {
+                        const double cached = tile[cc * 32 + lane];
+                        double fresh = cached;
+                        if (c0 + cc == nextcol) {  // warp-uniform: all lanes of the warp follow the same gene
+                            const int xv = a.tx[nz];
+                            const int tv = __ldcg(a.t + (size_t)(c0 + cc) * L + l);
+                            fresh = lg_tab(lgtab, T, (long long)tv + (isCur ? -xv : xv), a.beta);
+                            ++nz;
+                            nextcol = (nz < nzEnd) ? a.tcol[nz] : (1LL << 60);
+                        }
+                        p += isCur ? cached : fresh;
+                        p -= isCur ? fresh : cached;
+                    }
+                } else if (valid) {
+                    // inactive lanes keep the cursor in step so the test above stays warp-uniform
+                    while (nextcol < c0 + tc) {
+                        ++nz;
+                        nextcol = (nz < nzEnd) ? a.tcol[nz] : (1LL << 60);
+                    }
+                }
+            }
+            if (active) {
+                const int g = g_s[l];
+                const double Tl = (double)T_s[l], Ni = (double)a.nByG[i];
+                const int g1 = isCur ? g - 1 : g, g0 = g1 + 1;
+                p += dlgamma_hot((double)g0 + a.gamma);
+                p -= dlgamma_hot((double)g1 + a.gamma);
+                p += dlgamma_hot((double)g0 * a.delta);
+                p -= dlgamma_hot((double)g1 * a.delta);
+                p += dlgamma_hot(isCur ? Tl - Ni + (double)g1 * a.delta : Tl + (double)g1 * a.delta);
+                p -= dlgamma_hot(isCur ? Tl + (double)g0 * a.delta : Tl + Ni + (double)g0 * a.delta);
+                a.w.bufP[(size_t)(tgene % a.w.Wmax) * L + l] = p;
+            }
+        }
+        units_done += ntask;
+        grid_sync(a.w.barrier, bar_target);
+        double* pl = scr;
+        double* rr = scr + L;
+        int* perm = reinterpret_cast<int*>(scr + 2 * L);
+        for (int c = gwarp; c < nwin; c += tw) {
+            const long long tt = pos + c;
+            const int i = a.ix[tt] - 1;
+            const int cur = a.y[i] - 1;
+            const size_t o = (size_t)(tt % a.w.Wmax) * L;
+            for (int l = lane; l < L; l += 32) {
+                const double p = __ldcg(a.w.bufP + o + l);
+                pl[l] = p;
+                if (a.probs) a.probs[(size_t)i * L + l] = p;
+            }
+            __syncwarp();
+            int ynew = cur;
+            if (a.doSample) {
+                ynew = warp_sample_ll(pl, L, a.u[tt], rr, perm, lane);
+                if (ynew < 0) {
+                    if (lane == 0) atomicCAS(a.w.status, 0, ynew);
+                    ynew = cur;
+                }
+            }
+            if (lane == 0) a.w.spec[c] = (ynew != cur) ? ((cur << 16) | ynew) : -1;
+            __syncwarp();
+        }
+        prev_end = end;
+        have_spec = true;
+        grid_sync(a.w.barrier, bar_target);
+    }
+    if (blockIdx.x == 0) {
+        for (int q = threadIdx.x; q < L; q += blockDim.x) {
+            a.nByTS[q] = T_s[q];
+            a.nGByTS[q] = g_s[q];
+        }
+        if (threadIdx.x == 0) {
+            a.w.stats[0] += rounds;
+            a.w.stats[1] += units_done;
+            a.w.stats[2] += movers;
+        }
+    }
+}
+
+inline size_t yg_sweep_smem(int L, int T, int nwarp) {
+    const size_t scratchD = (size_t)2 * L + (L + 1) / 2 + 2;
+    return sizeof(double) * (T + YG_TILE * 32 + nwarp * scratchD) + sizeof(long long) * L + sizeof(int) * (L + 4);
+}
+
+// lgt = lgamma(t + beta) for the whole L x nM table (at set_state; the sweep keeps it current afterwards)
+__global__ void k_lgt_fill(const int* __restrict__ t, long long n, double beta, double* __restrict__ lgt) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const int v = t[q];
+        lgt[q] = dlgamma_hot((double)v + beta);
+    }
+}
+
 }  // namespace celda
