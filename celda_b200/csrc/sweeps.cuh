@@ -811,11 +811,12 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int scratchD = 2 * L + (L + 1) / 2 + 2;
     double* lgtab = reinterpret_cast<double*>(smem_raw);
-    double* tile = lgtab + T;                             // [YG_TILE][32]
+    double* tile = lgtab + T;                             // [YG_TILE][32] lgamma(t + beta)
     double* scratch_all = tile + YG_TILE * 32;
     long long* T_s = reinterpret_cast<long long*>(scratch_all + (size_t)nwarp * scratchD);
     int* g_s = reinterpret_cast<int*>(T_s + L);
-    int* s_misc = g_s + L;
+    int* ttile = g_s + L;                                 // [YG_TILE][32] t
+    int* s_misc = ttile + YG_TILE * 32;
     double* scr = scratch_all + (size_t)warp * scratchD;
     const int gwarp = blockIdx.x * nwarp + warp, tw = gridDim.x * nwarp;
     const long long nM = a.nM;
@@ -833,6 +834,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
     bool have_spec = false;
     unsigned bar_target = 0;
     long long rounds = 0, units_done = 0, movers = 0;
+    long long ck_commit = 0, ck_units = 0, ck_draw = 0, ck_bar = 0, ck0 = clock64(), ck1;
 
     while (true) {
         bool committed = false;
@@ -883,6 +885,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
         }
         if (pos >= a.nG) break;
         if (committed) grid_sync(a.w.barrier, bar_target);  // table rows a, b are visible before they are read
+        CELDA_TICK(ck_commit);
         const long long end = max(hi, min(pos + (long long)W, (long long)a.nG));
         const int nwin = (int)(end - pos);
         // ---- tasks: patch = (32 carried genes) x {da, db}; fresh = (32 new genes) x (32-module chunk)
@@ -911,36 +914,54 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
             const bool isCur = active && (l == cur);
             const int lsafe = (l >= 0) ? l : 0;
             // module of lane `lane` inside the staged tile: patch tasks stage rows da, db in slots 0, 1
+            // cursor into the gene's twin row; the next entry (column, count) is fetched one step ahead so that its
+            // latency is hidden behind the columns in between
             long long nz = valid ? a.rp[i] : 0;
             const long long nzEnd = valid ? a.rp[i + 1] : 0;
-            long long nextcol = (nz < nzEnd) ? a.tcol[nz] : (1LL << 60);
+            const long long NONE = 1LL << 60;
+            long long nextcol = (nz < nzEnd) ? a.tcol[nz] : NONE;
+            int nextx = (nz < nzEnd) ? a.tx[nz] : 0;
             double p = 0.0;
             for (long long c0 = 0; c0 < nM; c0 += YG_TILE) {
                 const int tc = (int)min((long long)YG_TILE, nM - c0);
                 __syncthreads();
-                // stage lgt[c0 .. c0 + tc) for this task's 32 modules: warp w loads columns w, w + 32, ...
-                for (int cc = warp; cc < tc; cc += nwarp)
-                    tile[cc * 32 + lane] = (l >= 0) ? __ldcg(a.lgt + (size_t)(c0 + cc) * L + lsafe) : 0.0;
+                // stage t and lgt of columns [c0, c0 + tc) for this task's 32 modules: warp w loads columns w, w + nwarp, ...
+                for (int cc = warp; cc < tc; cc += nwarp) {
+                    const size_t g = (size_t)(c0 + cc) * L + lsafe;
+                    tile[cc * 32 + lane] = (l >= 0) ? __ldcg(a.lgt + g) : 0.0;
+                    ttile[cc * 32 + lane] = (l >= 0) ? __ldcg(a.t + g) : 0;
+                }
                 __syncthreads();
                 if (active) {
-                    for (int cc = 0; cc < tc; ++cc) {
-                        const double cached = tile[cc * 32 + lane];
-                        double fresh = cached;
-                        if (c0 + cc == nextcol) {  // warp-uniform: all lanes of the warp follow the same gene
-                            const int xv = a.tx[nz];
-                            const int tv = __ldcg(a.t + (size_t)(c0 + cc) * L + l);
-                            fresh = lg_tab(lgtab, T, (long long)tv + (isCur ? -xv : xv), a.beta);
-                            ++nz;
-                            nextcol = (nz < nzEnd) ? a.tcol[nz] : (1LL << 60);
+                    // runs of columns where the gene has no count: (p + cached) - cached, a tight loop; then the
+                    // column with a count (warp-uniform: all lanes of the warp follow the same gene)
+                    int cc = 0;
+                    while (cc < tc) {
+                        const int stop = (nextcol - c0 < tc) ? (int)(nextcol - c0) : tc;
+#pragma unroll 4
+                        for (; cc < stop; ++cc) {
+                            const double cached = tile[cc * 32 + lane];
+                            p += cached;
+                            p -= cached;
                         }
-                        p += isCur ? cached : fresh;
-                        p -= isCur ? fresh : cached;
+                        if (cc < tc) {
+                            const double cached = tile[cc * 32 + lane];
+                            const int xv = nextx;
+                            const double fresh =
+                                lg_tab(lgtab, T, (long long)ttile[cc * 32 + lane] + (isCur ? -xv : xv), a.beta);
+                            ++nz;
+                            nextcol = (nz < nzEnd) ? a.tcol[nz] : NONE;
+                            nextx = (nz < nzEnd) ? a.tx[nz] : 0;
+                            p += isCur ? cached : fresh;
+                            p -= isCur ? fresh : cached;
+                            ++cc;
+                        }
                     }
-                } else if (valid) {
-                    // inactive lanes keep the cursor in step so the test above stays warp-uniform
+                } else {
+                    // inactive lanes keep the cursor in step so the tests above stay warp-uniform
                     while (nextcol < c0 + tc) {
                         ++nz;
-                        nextcol = (nz < nzEnd) ? a.tcol[nz] : (1LL << 60);
+                        nextcol = (nz < nzEnd) ? a.tcol[nz] : NONE;
                     }
                 }
             }
@@ -958,7 +979,9 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
             }
         }
         units_done += ntask;
+        CELDA_TICK(ck_units);
         grid_sync(a.w.barrier, bar_target);
+        CELDA_TICK(ck_bar);
         double* pl = scr;
         double* rr = scr + L;
         int* perm = reinterpret_cast<int*>(scr + 2 * L);
@@ -986,7 +1009,9 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
         }
         prev_end = end;
         have_spec = true;
+        CELDA_TICK(ck_draw);
         grid_sync(a.w.barrier, bar_target);
+        CELDA_TICK(ck_bar);
     }
     if (blockIdx.x == 0) {
         for (int q = threadIdx.x; q < L; q += blockDim.x) {
@@ -997,13 +1022,18 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
             a.w.stats[0] += rounds;
             a.w.stats[1] += units_done;
             a.w.stats[2] += movers;
+            a.w.stats[3] += ck_commit;
+            a.w.stats[4] += ck_units;
+            a.w.stats[5] += ck_draw;
+            a.w.stats[6] += ck_bar;
         }
     }
 }
 
 inline size_t yg_sweep_smem(int L, int T, int nwarp) {
     const size_t scratchD = (size_t)2 * L + (L + 1) / 2 + 2;
-    return sizeof(double) * (T + YG_TILE * 32 + nwarp * scratchD) + sizeof(long long) * L + sizeof(int) * (L + 4);
+    return sizeof(double) * (T + YG_TILE * 32 + nwarp * scratchD) + sizeof(long long) * L +
+           sizeof(int) * (L + YG_TILE * 32 + 4);
 }
 
 // lgt = lgamma(t + beta) for the whole L x nM table (at set_state; the sweep keeps it current afterwards)
