@@ -274,8 +274,14 @@ def main():
         z_ms = pz["ms"] / max(1, pz["launches"])
         z_flop = FLOP_PER_LGAMMA * (float(nM) * a.K * a.L + 2.0 * nM * a.K)  # algorithmic: C*K*L sums + 2 scalars/cand
         ach = z_flop / (z_ms * 1e-3) / 1e12
+        # DRAM traffic of k_sweep_z per launch from the committed ncu --set full capture of this same command
+        # (profiles/r1_ncu_full_sweeps_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum), default config only
+        default_cfg = (a.cells, a.genes, a.K, a.L) == (100000, 20000, 30, 150)
+        traffic = (63.262976 + 6.542080) * 1e6 if default_cfg else None
         out["roofline"] = {"bound": "fp64", "kernel": "k_sweep_z", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                           "frac": ach / peak if peak else None, "traffic": None,
+                           "frac": ach / peak if peak else None, "traffic": traffic,
+                           "traffic_note": "bytes; algorithmic HBM bytes are 4*L*C (nTSByC) + 8*K*C (probs) = 84 MB, "
+                                           "the kernel is FP64-pipe bound (ncu: 62 % fp64 pipe, 0.26 % DRAM)",
                            "note": "peak = DFMA rate measured live (2 flop/FMA); the sweep arithmetic is unfused "
                                    "(-fmad=false, bit-reproducible), so 0.5 is its ceiling; not in MEASURED_PEAKS.json",
                            "ms_per_launch": z_ms}
