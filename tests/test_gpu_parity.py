@@ -289,3 +289,25 @@ def test_staged_iterations_match_host_fed(oracle, gold_cg):
     assert np.array_equal(za, zb) and np.array_equal(ya, yb)
     a.close()
     b.close()
+
+
+def test_cg_iteration_more_than_32_populations(oracle):
+    """K = 40 > 32 and L = 70: several candidates per lane in the draw and in the warp-mode units."""
+    rng = np.random.default_rng(77)
+    G, C, K, L, S = 300, 900, 40, 70, 3
+    counts, s, z_true, y_true = simulate_cg(rng, G, C, K, L, S, nrange=(200, 400))
+    A, O = _csc(counts)
+    z, y = z_true.copy(), y_true.copy()
+    fz, fy = rng.random(C) < 0.3, rng.random(G) < 0.3
+    z[fz] = rng.integers(1, K + 1, fz.sum())
+    y[fy] = rng.integers(1, L + 1, fy.sum())
+    ch = cb.Chain(A, s, K=K, L=L)
+    ch.set_state(z, y)
+    for it in range(2):
+        ixy, uy = rng.permutation(G).astype(np.int32) + 1, rng.random(G)
+        ixz, uz = rng.permutation(C).astype(np.int32) + 1, rng.random(C)
+        ref = _oracle_iteration(oracle, O, s, z, y, K, L, ixy, uy, ixz, uz)
+        ll = ch.iterate(ixy, uy, ixz, uz)
+        _check_iteration(ch, ref, ll)
+        z, y = ref["z"], ref["y"]
+    ch.close()
