@@ -16,6 +16,12 @@ def build():
     return so
 
 
+def _threads():
+    """Generator threads: all host cores divided among the ranks of a torchrun launch."""
+    world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+    return max(1, (os.cpu_count() or 1) // max(1, world))
+
+
 def simulate_cells_cg(seed, S, cells_per_sample, G, K, L, nrange, alpha=1.0, beta=1.0, gamma=5.0, delta=1.0):
     """.simulateCellscelda_CG (R/simulateCells.R:302-435): theta_s ~ Dir(alpha), z_c ~ Cat(theta_s);
     phi_k ~ Dir(beta 1_L); eta ~ Dir(gamma 1_L), y_g ~ Cat(eta); psi_l ~ Dir(delta) over the genes of module l;
@@ -45,7 +51,7 @@ def simulate_cells_cg(seed, S, cells_per_sample, G, K, L, nrange, alpha=1.0, bet
     nnz = lib.sim_counts(C.c_int(G), C.c_longlong(nM), C.c_int(K), C.c_int(L), z.ctypes.data_as(ip),
                          N.ctypes.data_as(ip), np.ascontiguousarray(phi).ctypes.data_as(dp),
                          mod_off.ctypes.data_as(ip), order.ctypes.data_as(ip), psi.ctypes.data_as(dp),
-                         C.c_uint64(seed), C.c_int(os.cpu_count() or 1), C.c_longlong(0), colptr.ctypes.data_as(C.POINTER(C.c_longlong)), C.byref(rows), C.byref(vals))
+                         C.c_uint64(seed), C.c_int(_threads()), C.c_longlong(0), colptr.ctypes.data_as(C.POINTER(C.c_longlong)), C.byref(rows), C.byref(vals))
     ri = np.ctypeslib.as_array(rows, shape=(max(nnz, 1),))[:nnz].copy()
     xv = np.ctypeslib.as_array(vals, shape=(max(nnz, 1),))[:nnz].astype(np.float64)
     lib.sim_free(rows)
@@ -91,7 +97,7 @@ def simulate_cells_c(seed, S, cells_per_sample, G, K, nrange, alpha=1.0, beta=1.
                          Nl.ctypes.data_as(ip), np.ascontiguousarray(onehot).ctypes.data_as(dp),
                          mod_off.ctypes.data_as(ip), mod_genes.ctypes.data_as(ip),
                          np.ascontiguousarray(phi).ravel().ctypes.data_as(dp), C.c_uint64(seed),
-                         C.c_int(os.cpu_count() or 1), C.c_longlong(lo), colptr.ctypes.data_as(C.POINTER(C.c_longlong)),
+                         C.c_int(_threads()), C.c_longlong(lo), colptr.ctypes.data_as(C.POINTER(C.c_longlong)),
                          C.byref(rows), C.byref(vals))
     ri = np.ctypeslib.as_array(rows, shape=(max(nnz, 1),))[:nnz].copy()
     xv = np.ctypeslib.as_array(vals, shape=(max(nnz, 1),))[:nnz].astype(np.float64)
