@@ -527,7 +527,16 @@ int chain_step_z_em(celda_chain* h, int doSample) {
     CELDA_CUDA_OK(cudaMemcpyAsync(h->zprev.p, h->z.p, sizeof(int) * h->nM, cudaMemcpyDeviceToDevice, st));
     const int threads = 256, nwarp = threads / 32;
     const int grid = (int)std::min<long long>(((long long)h->nM + nwarp - 1) / nwarp, (long long)h->sms * 32);
-    if (isC)
+    if (isC && K <= 64 && (long long)h->nM >= 4096) {
+        // large celda_C problems: phi streamed through shared memory in gene tiles shared by a block of cells
+        const int GT = std::min(R, (int)(200 * 1024 / (sizeof(double) * K)));
+        const size_t smem = sizeof(double) * (size_t)GT * K;
+        CELDA_CUDA_OK(cudaFuncSetAttribute(k_em_probs_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const long long cpb = 32LL * EM_CPW;
+        const int tgrid = (int)std::min<long long>((h->nM + cpb - 1) / cpb, (long long)h->sms);
+        k_em_probs_tiled<<<tgrid, 1024, smem, st>>>(R, h->nM, K, GT, h->cp.p, h->ci.p, h->cx.p, h->phiBuf.p, h->thetaBuf.p,
+                                                   h->s.p, h->probsZ.p, doSample ? h->z.p : nullptr);
+    } else if (isC)
         k_em_probs<true><<<grid, threads, 0, st>>>(R, h->nM, K, h->cp.p, h->ci.p, h->cx.p, h->phiBuf.p, h->thetaBuf.p, h->s.p,
                                                   h->probsZ.p, doSample ? h->z.p : nullptr);
     else

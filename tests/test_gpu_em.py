@@ -100,3 +100,38 @@ def test_celda_CG_em_iteration(oracle, gold_cg):
         assert abs(ll - want) <= 1e-9 * abs(want)
         z, y = oz["z"], oy["y"]
     ch.close()
+
+
+@pytest.mark.parametrize("K", [20, 45])
+def test_celda_C_em_tiled_kernel_large(oracle, K):
+    """>= 4096 cells takes the shared-memory-tiled contraction (several gene tiles when G*K*8 > 200 KB)."""
+    rng = np.random.default_rng(100 + K)
+    G, C, S = 1500, 6000, 4
+    phi = rng.dirichlet(np.ones(G) * 0.05, K)
+    z_true = rng.integers(1, K + 1, C)
+    counts = np.zeros((G, C), dtype=np.int32)
+    for c in range(C):
+        counts[:, c] = rng.multinomial(rng.integers(100, 400), phi[z_true[c] - 1])
+    counts[counts.sum(1) == 0, 0] = 1
+    s = rng.integers(1, S + 1, C).astype(np.int32)
+    s[:S] = np.arange(1, S + 1)
+    z = z_true.astype(np.int32).copy()
+    flip = rng.random(C) < 0.3
+    z[flip] = rng.integers(1, K + 1, int(flip.sum()))
+    z[:K] = np.arange(1, K + 1)
+    A, O = cb.CSC.from_dense(counts), dense_to_csc(counts)
+    ch = cb.Chain(A, s, K=K, model=cb.MODEL_C, alpha=0.7, beta=0.4)
+    ch.set_state(z=z)
+    p = oracle.cCDecomposeCounts(O, s, z, K)
+    m, n, ncp = p["mCPByS"], p["nGByCP"], p["nCP"]
+    for it in range(2):
+        ref = oracle.cCCalcEMProbZ(O, m, n, p["nByC"], ncp, z, s, K, G, C, 0.7, 0.4)
+        ch.iterate_em()
+        zg, _ = ch.get_state()
+        assert np.array_equal(zg, ref["z"]), (it, (zg != ref["z"]).sum())
+        pz, _ = ch.probs()
+        assert np.array_equal(pz, ref["probs"])
+        t = ch.tables()
+        assert np.array_equal(t["nGByCP"], ref["nGByCP"]) and np.array_equal(t["mCPByS"], ref["mCPByS"])
+        z, m, n, ncp = ref["z"], ref["mCPByS"], ref["nGByCP"], ref["nCP"]
+    ch.close()
