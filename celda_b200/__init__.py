@@ -326,6 +326,7 @@ class Chain:
         self._h = C.c_void_p()
         self.counts, self.model, self.K, self.L = counts, model, int(K), int(L)
         self.nG, self.nM = counts.nrow, counts.ncol
+        self.hyper = (float(alpha), float(beta), float(delta), float(gamma))
         s = None
         self.nS = 1
         if model != MODEL_G:

@@ -24,14 +24,6 @@ inline int grid_for(long long n, int threads, int sms, int per_sm = 8) {
     return (int)std::max<long long>(1, std::min<long long>(b, (long long)sms * per_sm));
 }
 
-struct LabelCheck {
-    DevBuf<int> flag;
-    int init(cudaStream_t st) {
-        CELDA_TRY(flag.alloc(1));
-        return flag.zero(st);
-    }
-};
-
 int check_labels_host(const int* g, long long n, int K, const char* what, const char* kname) {
     for (long long i = 0; i < n; ++i)
         if (g[i] < 1 || g[i] > K) return fail("The entries in '%s' need to be between 1 and '%s'.", what, kname);
@@ -135,7 +127,6 @@ struct celda_chain {
     int staged_iters = 0;
     DevBuf<int> st_ixy, st_ixz;
     DevBuf<double> st_uy, st_uz;
-    int npG = 0;
     // profiling
     bool profile = false;
     double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -170,3 +170,68 @@ def celdaGridSearch(counts, sampleLabel, paramsTest, maxIter=200, nchains=3, see
     flat = sorted((r for part in everything for r in part), key=lambda r: r["index"])
     return dict(runParams=[{k: r[k] for k in ("index", "chain", "K", "L", "seed", "logLikelihood")} for r in flat],
                 resList=[r["result"] for r in flat])
+
+
+# ------------------------------------------------------------------ cold callers of the hot path
+def clusterProbability(chain, log=False):
+    """clusterProbability(x) (R/clusterProbability.R:117-252): the sweeps with doSample = FALSE, then each row of
+    probabilities normalised with the log-sum-exp trick (.normalizeLogProbs).  Returns dict(zProbability [nM, K],
+    yProbability [nG, L]) for the chain's model; the chain state is left unchanged."""
+    from . import MODEL_C as _C, MODEL_G as _G
+    out = {}
+    if chain.model != _G:
+        ix = np.arange(1, chain.nM + 1, dtype=np.int32)
+        if chain.model == _C:
+            chain.sweep_z_em(doSample=False)
+        else:
+            chain.sweep_z_gibbs(ix, np.zeros(chain.nM), doSample=False)
+    if chain.model != _C:
+        chain.sweep_y(np.arange(1, chain.nG + 1, dtype=np.int32), np.zeros(chain.nG), doSample=False)
+    pz, py = chain.probs()
+
+    def norm(p):
+        p = p.T  # items x candidates
+        mx = p.max(axis=1, keepdims=True)
+        lse = mx + np.log(np.exp(p - mx).sum(axis=1, keepdims=True))
+        return p - lse if log else np.exp(p - lse)
+
+    if pz is not None:
+        out["zProbability"] = norm(pz)
+    if py is not None:
+        out["yProbability"] = norm(py)
+    return out
+
+
+def factorizeMatrix(chain, type=("counts", "proportion", "posterior")):
+    """.factorizeMatrixCG (R/factorizeMatrix.R:193-299) from the chain's device-resident tables: counts /
+    proportions / posterior of sample (K x S), cellPopulation (L x K), cell (L x C), module (G x L),
+    geneDistribution (L, the +1 pseudo-gene included exactly like the reference)."""
+    t = chain.tables()
+    z, y = chain.get_state()
+    a, b, d, g = chain.hyper
+    G, L = chain.nG, chain.L
+    GByTS = np.zeros((G, L))
+    GByTS[np.arange(G), y - 1] = t["nByG"]
+    nGByTS = t["nGByTS"].astype(np.float64)
+    nGByTS[nGByTS == 0] = 1.0  # :221
+    res = {}
+
+    def colnorm(m):  # normalizeCounts(m, normalize = "proportion")
+        return m / m.sum(axis=0, keepdims=True)
+
+    if "counts" in type:
+        res["counts"] = dict(sample=t["mCPByS"].astype(np.float64), cellPopulation=t["nTSByCP"], cell=t["nTSByC"],
+                             module=GByTS, geneDistribution=nGByTS)
+    if "proportion" in type:
+        uz, uy = np.unique(z) - 1, np.unique(y) - 1  # only populated populations / modules are normalised (:255-266)
+        cp, mod = t["nTSByCP"].copy(), GByTS.copy()
+        cp[:, uz] = colnorm(cp[:, uz])
+        mod[:, uy] = colnorm(mod[:, uy])
+        res["proportions"] = dict(sample=colnorm(t["mCPByS"].astype(np.float64)), cellPopulation=cp,
+                                  cell=colnorm(t["nTSByC"]), module=mod, geneDistribution=nGByTS / nGByTS.sum())
+    if "posterior" in type:
+        gs = GByTS.copy()
+        gs[np.arange(G), y - 1] += d
+        res["posterior"] = dict(sample=colnorm(t["mCPByS"] + a), cellPopulation=colnorm(t["nTSByCP"] + b),
+                                module=colnorm(gs), geneDistribution=(nGByTS + g) / (nGByTS + g).sum())
+    return res

@@ -135,3 +135,30 @@ def test_celda_C_em_tiled_kernel_large(oracle, K):
         assert np.array_equal(t["nGByCP"], ref["nGByCP"]) and np.array_equal(t["mCPByS"], ref["mCPByS"])
         z, m, n, ncp = ref["z"], ref["mCPByS"], ref["nGByCP"], ref["nCP"]
     ch.close()
+
+
+def test_cluster_probability_and_factorize(oracle, gold_cg):
+    """Cold callers of the hot path on the fitted fixture model: tests/testthat/test-celda_CG.R
+    :22-41 -- factorizeMatrix self-consistency and dimensions, clusterProbability rows summing to 1."""
+    from celda_b200 import model
+    counts, s, z, y = gold_cg["counts"], gold_cg["s_mod"], gold_cg["z"], gold_cg["y"]
+    K, L = 5, 10
+    ch = cb.Chain(cb.CSC.from_dense(counts), s, K=K, L=L)
+    ch.set_state(z, y)
+    cp = model.clusterProbability(ch)
+    assert cp["zProbability"].shape == (counts.shape[1], K) and cp["yProbability"].shape == (counts.shape[0], L)
+    assert np.allclose(cp["zProbability"].sum(1), 1.0, atol=1e-10) and np.allclose(cp["yProbability"].sum(1), 1.0, atol=1e-10)
+    z2, y2 = ch.get_state()
+    assert np.array_equal(z2, z) and np.array_equal(y2, y)
+    f = model.factorizeMatrix(ch)
+    assert f["counts"]["cellPopulation"].shape == (L, K) and f["counts"]["module"].shape == (counts.shape[0], L)
+    assert f["counts"]["cell"].sum() == counts.sum() and f["counts"]["module"].sum() == counts.sum()
+    assert np.allclose(f["proportions"]["cell"].sum(0), 1.0) and np.allclose(f["posterior"]["module"].sum(0), 1.0)
+    assert np.allclose(f["counts"]["cell"], f["proportions"]["cell"] * counts.sum(0)[None, :])
+    # the posterior factors are exactly what the perplexity kernel uses
+    M = np.log(f["posterior"]["module"] @ f["posterior"]["cellPopulation"])
+    inner = M.T @ counts + np.log(f["posterior"]["sample"])[:, s - 1]
+    mx = inner.max(0)
+    px = np.exp(-((mx + np.log(np.exp(inner - mx).sum(0))).sum() / counts.sum()))
+    assert abs(px - ch.perplexity()) <= 1e-9 * px
+    ch.close()
