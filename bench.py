@@ -299,7 +299,7 @@ def main():
         bytes_alg = {"rowSumByGroup": 8 * Z + 4 * (nM + 1) + 4 * nG + 4.0 * a.L * nM,
                      "colSumByGroup": 8 * Z + 4 * (nM + 1) + 4 * nM + 4.0 * nG * a.K}
         out["roofline_aggregation"] = {}
-        for kname, kern in (("rowSumByGroup", "k_rowsum_csc<int>"), ("colSumByGroup", "k_colsum_csc<int>")):
+        for kname, kern in (("rowSumByGroup", "k_rowsum_csc<int>"), ("colSumByGroup", "k_colsum_twin")):
             ms1 = agg[kname]["ms"] / max(1, agg[kname]["launches"])
             out["roofline_aggregation"][kname] = {
                 "bound": "hbm", "kernel": kern, "achieved": bytes_alg[kname] / (ms1 * 1e-3) / 1e9, "peak": hbm,

@@ -231,8 +231,12 @@ int chain_decompose(celda_chain* h) {
         const int threads = 256, nwarp = threads / 32;
         DevBuf<int>& ng = h->comm ? h->nGByCP_loc : h->nGByCP;
         DevBuf<int>& mm = h->comm ? h->mCPByS_loc : h->mCPByS;
-        CELDA_TRY(ng.zero(st));
-        {
+        if (h->tcol.n) {  // gene-major twin available (celda_CG): no global atomics
+            ProfScope ps(h, 6);
+            k_colsum_twin<<<std::min(h->nG, sms * 8), 256, sizeof(int) * 8 * h->K, st>>>(h->nG, h->trp.p, h->tcol.p, h->tx.p,
+                                                                                       h->z.p, h->K, ng.p);
+        } else {
+            CELDA_TRY(ng.zero(st));
             ProfScope ps(h, 6);
             k_colsum_csc<int><<<std::min((h->nM + nwarp - 1) / nwarp, sms * 16), threads, 0, st>>>(
                 h->nM, h->cp.p, h->ci.p, h->cx.p, h->z.p, h->K, ng.p);

@@ -71,7 +71,23 @@ __global__ void k_rowsum_csc(int nc, const int* __restrict__ p, const int* __res
         T tot = 0;
         const int e = p[c + 1];
         int t = p[c] + lane;
-        for (; t + 96 < e; t += 128) {  // four independent index/value/label loads in flight per lane
+        for (; t + 224 < e; t += 256) {  // eight independent index/value/label loads in flight per lane
+            int r[8];
+            T v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                r[q] = ri[t + 32 * q];
+                v[q] = xv[t + 32 * q];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) r[q] = group[r[q]];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                atomicAdd(&acc[r[q] - 1], v[q]);
+                tot += v[q];
+            }
+        }
+        for (; t + 96 < e; t += 128) {
             const int r0 = ri[t], r1 = ri[t + 32], r2 = ri[t + 64], r3 = ri[t + 96];
             const T v0 = xv[t], v1 = xv[t + 32], v2 = xv[t + 64], v3 = xv[t + 96];
             const int g0 = group[r0], g1 = group[r1], g2 = group[r2], g3 = group[r3];
@@ -1045,6 +1061,44 @@ k_em_probs_tiled(int R, long long nM, int K, int GT, const int* __restrict__ p, 
             }
             if (znew && lane == 0) znew[c] = (bi == 0x7fffffff ? 0 : bi) + 1;
         }
+    }
+}
+
+}  // namespace celda
+
+namespace celda {
+
+// colSumByGroup (src/matrixSumsSparse.cpp:9-38) over the gene-major twin: one block per gene (strided), per-warp
+// shared accumulators (K counters), no global atomics; every HBM byte of the twin is read once, coalesced, the
+// G x K table is written once.  out: gene-major [nG][K].
+__global__ void k_colsum_twin(int nG, const long long* __restrict__ rp, const int* __restrict__ tcol,
+                              const int* __restrict__ tx, const int* __restrict__ group, int K, int* __restrict__ out) {
+    extern __shared__ int acc_tw[];  // [nwarp][K]
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* acc = acc_tw + warp * K;
+    for (int g = blockIdx.x; g < nG; g += gridDim.x) {
+        for (int k = lane; k < K; k += 32) acc[k] = 0;
+        __syncwarp();
+        const long long e = rp[g + 1];
+        long long t = rp[g] + threadIdx.x;
+        const long long step = blockDim.x;
+        for (; t + 3 * step < e; t += 4 * step) {
+            const int c0 = tcol[t], c1 = tcol[t + step], c2 = tcol[t + 2 * step], c3 = tcol[t + 3 * step];
+            const int v0 = tx[t], v1 = tx[t + step], v2 = tx[t + 2 * step], v3 = tx[t + 3 * step];
+            const int g0 = group[c0], g1 = group[c1], g2 = group[c2], g3 = group[c3];
+            atomicAdd(&acc[g0 - 1], v0);
+            atomicAdd(&acc[g1 - 1], v1);
+            atomicAdd(&acc[g2 - 1], v2);
+            atomicAdd(&acc[g3 - 1], v3);
+        }
+        for (; t < e; t += step) atomicAdd(&acc[group[tcol[t]] - 1], tx[t]);
+        __syncthreads();
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            int sum = 0;
+            for (int w = 0; w < nwarp; ++w) sum += acc_tw[w * K + k];
+            out[(size_t)g * K + k] = sum;
+        }
+        __syncthreads();
     }
 }
 
