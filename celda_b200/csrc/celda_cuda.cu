@@ -73,7 +73,9 @@ struct SweepBufs {
     DevBuf<int> spec, status;
     DevBuf<unsigned> barrier;
     DevBuf<long long> stats;  // [which][8]
-    int Wmax = 16384, Wmin = 32, lgT = 2048;
+    // value tables of the z sweep (k_sweep_z): row histogram, per-row offsets, per-CTA global tables
+    DevBuf<int> ztHist, ztOffg, ztGrp, ztTmp, ztXT;
+    int Wmax = 32768, Wmin = 32, lgT = 2048;
     int alloc(int ncand, cudaStream_t st) {
         CELDA_TRY(bufP.alloc((size_t)Wmax * ncand));
         CELDA_TRY(bufA.alloc((size_t)Wmax * ncand));
@@ -349,8 +351,33 @@ SweepWork make_work(SweepBufs& b, int sms, int threads, int ncand, int which, in
 int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     int threads = 1024;
     if (z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32) > 220 * 1024) threads = 512;
-    a.w = make_work(b, sms, threads, a.K, which, 16384);
-    const size_t smem = z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32);
+    a.w = make_work(b, sms, threads, a.K, which, 32768);
+    // value tables: the shared memory left over holds the heads; sized from this sweep's count distribution
+    a.EsCap = 0;
+    {
+        const size_t base = z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32);
+        const long long room = ((long long)200 * 1024 - (long long)base) / (long long)sizeof(double);  // ~28 KB stays L1
+        if (sms >= a.K && room >= 8LL * a.R && a.nM >= 4096) {
+            a.EsCap = (int)std::min<long long>(room, 1 << 20);
+            if (b.ztHist.n < (size_t)a.R * ZT_BINS) CELDA_TRY(b.ztHist.alloc((size_t)a.R * ZT_BINS));
+            if (b.ztOffg.n < (size_t)a.R + 1) {
+                CELDA_TRY(b.ztOffg.alloc((size_t)a.R + 1));
+                CELDA_TRY(b.ztGrp.alloc(ZT_MAXGRP + 2));
+                CELDA_TRY(b.ztTmp.alloc((size_t)a.R));
+            }
+            CELDA_TRY(b.ztHist.zero(st));
+            k_row_hist<<<grid_for((long long)a.R * a.nM, 256, sms), 256, 0, st>>>(a.counts, a.R, a.nM, b.ztHist.p);
+            k_pick_rowV<<<1, 256, 0, st>>>(b.ztHist.p, a.R, a.EsCap, b.ztOffg.p, b.ztGrp.p, b.ztTmp.p);
+            if (b.ztXT.n < (size_t)a.R * a.nM) CELDA_TRY(b.ztXT.alloc((size_t)a.R * a.nM));
+            k_permute_transpose<<<(int)std::min<long long>((a.nM + 31) / 32, (long long)sms * 8), 256, 0, st>>>(
+                a.counts, a.R, a.nM, a.ix, b.ztXT.p);
+            count_launch(3);
+            a.offg = b.ztOffg.p;
+            a.grp = b.ztGrp.p;
+            a.xT = b.ztXT.p;
+        }
+    }
+    const size_t smem = z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32, a.EsCap);
     if (smem > 220 * 1024) return fail("z sweep: K=%d x R=%d tables need %zu bytes of shared memory (> 220 KB)", a.K, a.R, smem);
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CELDA_CUDA_OK(cudaMemsetAsync(b.barrier.p, 0, sizeof(unsigned), st));

@@ -239,6 +239,8 @@ struct SweepWork {
 
 // ------------------------------------------------------------------------------------------------ z sweep
 // .cCCalcGibbsProbZ (R/celda_C.R:620-714) on a dense R x nM int32 count matrix (nTSByC in celda_CG).
+constexpr int ZT_MAXGRP = 30;  // row groups of the value tables
+
 struct ZArgs {
     int R, K, nS;
     long long nM;
@@ -254,6 +256,11 @@ struct ZArgs {
     const double* u;    // one uniform per visited item
     int doSample;
     double* probs;      // K x nM or null
+    // value tables of the lane-per-unit rounds (see k_sweep_z)
+    const int* offg;    // [R + 1] row r tabulates counts v in [0, offg[r+1] - offg[r])
+    const int* grp;     // [ZT_MAXGRP + 2]: grp[0] = number of row groups, then the group boundaries (rows)
+    int EsCap;          // shared-memory table capacity in entries; 0 disables the tables
+    const int* xT;      // [R][nM]: xT[r][t] = counts[r, ix[t] - 1], the counts in visiting order, cell-minor
     SweepWork w;
 };
 
@@ -270,10 +277,22 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
     double* lgtab = reinterpret_cast<double*>(smem_raw);
     double* scratch_all = lgtab + T;
     long long* nCP_s = reinterpret_cast<long long*>(scratch_all + (size_t)nwarp * scratchD);
-    int* n_s = reinterpret_cast<int*>(nCP_s + K);
+    double* vt_s = reinterpret_cast<double*>(nCP_s + K);  // [EsCap] value table head of this CTA's candidate
+    int* n_s = reinterpret_cast<int*>(vt_s + a.EsCap);
     int* m_s = n_s + (size_t)K * Rp;
-    int* s_misc = m_s + K * nS;  // [0] first mover
+    int* offg_s = m_s + K * nS;     // [R + 1]
+    int* grp_s = offg_s + R + 1;    // [ZT_MAXGRP + 2]
+    int* s_misc = grp_s + ZT_MAXGRP + 2;  // [0] first mover
     double* scr = scratch_all + (size_t)warp * scratchD;
+    // Lane-per-unit rounds: CTA b owns candidate b % K (replica b / K) and tabulates
+    // lgamma(n[r][j] + v + beta) over the counts v that occur in row r, one group of rows at a time (as many rows
+    // as fit the shared-memory table).  A unit then is R look-ups added in the reference's order instead of R
+    // lgamma evaluations; its partial sum waits in the ring buffer between row groups.  The tables hold exactly
+    // the values lg_tab() returns, and a count beyond a row's table is evaluated directly.
+    const int myCand = blockIdx.x % K, myRep = blockIdx.x / K;
+    // replicas of my candidate: CTAs myCand, myCand + K, ... (every CTA owns one candidate when gridDim >= K)
+    const int nrep = (a.EsCap > 0 && (int)gridDim.x >= K) ? ((int)gridDim.x - myCand + K - 1) / K : 0;
+    const bool tabCTA = nrep > 0;
 
     const double Rbeta = (double)R * a.beta;
     const int gwarp = blockIdx.x * nwarp + warp, tw = gridDim.x * nwarp;
@@ -282,6 +301,10 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
     for (int q = threadIdx.x; q < K; q += blockDim.x) nCP_s[q] = a.nCP[q];
     for (int q = threadIdx.x; q < K * nS; q += blockDim.x) m_s[q] = a.mCPByS[q];
     for (int q = threadIdx.x; q < T; q += blockDim.x) lgtab[q] = dlgamma((double)q + a.beta);
+    if (nrep > 0) {
+        for (int q = threadIdx.x; q <= R; q += blockDim.x) offg_s[q] = a.offg[q];
+        for (int q = threadIdx.x; q < ZT_MAXGRP + 2; q += blockDim.x) grp_s[q] = a.grp[q];
+    }
     __syncthreads();
 
     long long pos = 0, hi = 0;
@@ -362,7 +385,107 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                 j = (int)(q % K);
             }
         };
-        if (total >= (long long)tw * 16) {
+        // one warp per unit: lanes evaluate the lgamma terms into shared memory, lane 0 adds them serially
+        auto warp_unit = [&](long long t, int j) {
+            const int* ncol = n_s + j * Rp;
+            if (t < 0) {
+                for (int r = lane; r < R; r += 32) scr[r] = lg_tab(lgtab, T, ncol[r], a.beta);
+                __syncwarp();
+                if (lane == 0) {
+                    double S = 0.0;
+                    for (int r = 0; r < R; ++r) S += scr[r];
+                    a.w.colsum[j] = S;
+                    a.w.lgnCP[j] = dlgamma((double)nCP_s[j] + Rbeta);
+                }
+                __syncwarp();
+            } else {
+                const long long i = a.ix[t] - 1;
+                const int zi = a.z[i] - 1;
+                const int sgn = (j == zi) ? -1 : 1;
+                const int* x = a.counts + i * R;
+                for (int r = lane; r < R; r += 32) scr[r] = lg_tab(lgtab, T, (long long)ncol[r] + sgn * x[r], a.beta);
+                __syncwarp();
+                if (lane == 0) {
+                    double S = 0.0;
+                    for (int r = 0; r < R; ++r) S += scr[r];
+                    const size_t o = (size_t)(t % a.w.Wmax) * K + j;
+                    a.w.bufP[o] = S;
+                    a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
+                }
+                __syncwarp();
+            }
+        };
+        const bool bigRound = total >= (long long)tw * 16;
+        if (bigRound && nrep > 0) {
+            // (1) cached column sums and patch units: few, one warp each
+            for (long long uidx = gwarp; uidx < nd + nPatch; uidx += tw) {
+                int j;
+                long long t;
+                decode(uidx, t, j);
+                warp_unit(t, j);
+            }
+            const long long nFreshCells = end - hi;
+            // (2) fresh cells x candidates other than the cell's own: table look-ups on the candidate's CTAs
+            if (tabCTA) {
+                const int j = myCand;
+                const int* ncol = n_s + j * Rp;
+                const int ngrp = grp_s[0];
+                const long long nchunk = (nFreshCells + 31) / 32;
+                for (int gI = 0; gI < ngrp; ++gI) {
+                    const int r0 = grp_s[1 + gI], r1 = grp_s[2 + gI];
+                    const int e0 = offg_s[r0], ne = offg_s[r1] - e0;
+                    __syncthreads();
+                    for (int q = threadIdx.x; q < ne; q += blockDim.x) {
+                        int lo = r0, hi2 = r1;  // largest r with offg[r] - e0 <= q
+                        while (hi2 - lo > 1) {
+                            const int mid = (lo + hi2) >> 1;
+                            if (offg_s[mid] - e0 <= q) lo = mid;
+                            else hi2 = mid;
+                        }
+                        vt_s[q] = lg_tab(lgtab, T, (long long)ncol[lo] + (q - (offg_s[lo] - e0)), a.beta);
+                    }
+                    __syncthreads();
+                    for (long long ch = myRep + (long long)nrep * warp; ch < nchunk; ch += (long long)nrep * nwarp) {
+                        const long long q = ch * 32 + lane;
+                        if (q >= nFreshCells) continue;
+                        const long long t = hi + q;
+                        const long long i = a.ix[t] - 1;
+                        if (a.z[i] - 1 == j) continue;  // the cell's own population: step (3)
+                        const int* x = a.xT + t;  // lanes hold consecutive t: one coalesced load per row
+                        const size_t o = (size_t)(t % a.w.Wmax) * K + j;
+                        double S = (gI == 0) ? 0.0 : a.w.bufP[o];
+                        int r = r0;
+                        for (; r + 8 <= r1; r += 8) {  // eight row loads in flight, then eight look-ups in row order
+                            int v[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) v[k] = __ldg(x + (size_t)(r + k) * a.nM);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const int og = offg_s[r + k];
+                                const double val = (v[k] < offg_s[r + k + 1] - og)
+                                                       ? vt_s[og - e0 + v[k]]
+                                                       : lg_tab(lgtab, T, (long long)ncol[r + k] + v[k], a.beta);
+                                S += val;
+                            }
+                        }
+                        for (; r < r1; ++r) {
+                            const int v = __ldg(x + (size_t)r * a.nM);
+                            const int og = offg_s[r];
+                            const double val = (v < offg_s[r + 1] - og) ? vt_s[og - e0 + v]
+                                                                       : lg_tab(lgtab, T, (long long)ncol[r] + v, a.beta);
+                            S += val;
+                        }
+                        a.w.bufP[o] = S;
+                        if (gI == ngrp - 1) a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)a.nByC[i]) + Rbeta);
+                    }
+                }
+            }
+            // (3) each fresh cell against its own population (counts removed): direct evaluation, one warp each
+            for (long long q = gwarp; q < nFreshCells; q += tw) {
+                const long long t = hi + q;
+                warp_unit(t, a.z[a.ix[t] - 1] - 1);
+            }
+        } else if (bigRound) {
             for (long long uidx = (long long)gwarp * 32 + lane; uidx < total; uidx += (long long)tw * 32) {
                 int j;
                 long long t;
@@ -391,34 +514,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                 int j;
                 long long t;
                 decode(uidx, t, j);
-                const int* ncol = n_s + j * Rp;
-                if (t < 0) {
-                    for (int r = lane; r < R; r += 32) scr[r] = lg_tab(lgtab, T, ncol[r], a.beta);
-                    __syncwarp();
-                    if (lane == 0) {
-                        double S = 0.0;
-                        for (int r = 0; r < R; ++r) S += scr[r];
-                        a.w.colsum[j] = S;
-                        a.w.lgnCP[j] = dlgamma((double)nCP_s[j] + Rbeta);
-                    }
-                    __syncwarp();
-                } else {
-                    const long long i = a.ix[t] - 1;
-                    const int zi = a.z[i] - 1;
-                    const int sgn = (j == zi) ? -1 : 1;
-                    const int* x = a.counts + i * R;
-                    for (int r = lane; r < R; r += 32)
-                        scr[r] = lg_tab(lgtab, T, (long long)ncol[r] + sgn * x[r], a.beta);
-                    __syncwarp();
-                    if (lane == 0) {
-                        double S = 0.0;
-                        for (int r = 0; r < R; ++r) S += scr[r];
-                        const size_t o = (size_t)(t % a.w.Wmax) * K + j;
-                        a.w.bufP[o] = S;
-                        a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
-                    }
-                    __syncwarp();
-                }
+                warp_unit(t, j);
             }
         }
         units_done += total;
@@ -487,10 +583,83 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
     }
 }
 
-inline size_t z_sweep_smem(int R, int K, int nS, int T, int nwarp) {
+inline size_t z_sweep_smem(int R, int K, int nS, int T, int nwarp, int EsCap = 0) {
     const int Rp = R | 1;
     const size_t scratchD = (size_t)std::max(R, 2 * K + (K + 1) / 2) + 2;
-    return sizeof(double) * (T + nwarp * scratchD) + sizeof(long long) * K + sizeof(int) * ((size_t)K * Rp + K * nS + 4);
+    return sizeof(double) * (T + nwarp * scratchD + EsCap) + sizeof(long long) * K +
+           sizeof(int) * ((size_t)K * Rp + K * nS + (R + 1) + ZT_MAXGRP + 2 + 4);
+}
+
+// xT[r][t] = counts[r, ix[t] - 1]: the count matrix in visiting order, transposed, so that lanes holding
+// consecutive visiting positions read one row coalesced.  32 cells per block, tile transposed through shared memory.
+__global__ void k_permute_transpose(const int* __restrict__ counts, int R, long long nM, const int* __restrict__ ix,
+                                    int* __restrict__ xT) {
+    __shared__ int tile[32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (long long t0 = (long long)blockIdx.x * 32; t0 < nM; t0 += (long long)gridDim.x * 32) {
+        for (int r0 = 0; r0 < R; r0 += 32) {
+            for (int c = w; c < 32; c += nw) {  // warp c reads rows r0.. of cell t0 + c (coalesced)
+                const long long t = t0 + c;
+                tile[c][lane] = (t < nM && r0 + lane < R) ? counts[(size_t)(ix[t] - 1) * R + r0 + lane] : 0;
+            }
+            __syncthreads();
+            for (int rr = w; rr < 32; rr += nw) {  // warp rr writes row r0 + rr for 32 consecutive t (coalesced)
+                if (r0 + rr < R && t0 + lane < nM) xT[(size_t)(r0 + rr) * nM + t0 + lane] = tile[lane][rr];
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// ---- per-row statistics of the count matrix behind the value tables
+constexpr int ZT_BINS = 2048;
+
+// hist[r][min(x, ZT_BINS - 1)] += 1 over an int32 R x nM column-major matrix
+__global__ void k_row_hist(const int* __restrict__ x, int R, long long nM, int* __restrict__ hist) {
+    const long long n = (long long)R * nM;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(q % R);
+        const int v = min(max(x[q], 0), ZT_BINS - 1);
+        atomicAdd(&hist[r * ZT_BINS + v], 1);
+    }
+}
+
+// Table length per row: the largest count seen (+ margin), then rows are packed greedily into groups of at most
+// EsCap entries.  Any length is CORRECT (a count beyond a row's table is evaluated directly); the choice only
+// decides how often that happens.  One block.
+__global__ void k_pick_rowV(const int* __restrict__ hist, int R, int EsCap, int* __restrict__ offg, int* __restrict__ grp,
+                            int* __restrict__ tmpV) {
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+        const int* h = hist + r * ZT_BINS;
+        int mx = 0;
+        for (int v = 0; v < ZT_BINS; ++v)
+            if (h[v]) mx = v;
+        tmpV[r] = min(min(ZT_BINS, mx + 1 + 8), EsCap);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int og = 0, ngrp = 0, inGrp = 0;
+        grp[1] = 0;
+        for (int r = 0; r < R; ++r) {
+            int v = tmpV[r];
+            if (inGrp + v > EsCap) {
+                if (ngrp + 1 < ZT_MAXGRP) {  // close the group before this row
+                    ++ngrp;
+                    grp[1 + ngrp] = r;
+                    inGrp = 0;
+                } else {
+                    v = max(0, EsCap - inGrp);  // out of groups: shorten the remaining rows' tables
+                }
+            }
+            offg[r] = og;
+            og += v;
+            inGrp += v;
+        }
+        offg[R] = og;
+        ++ngrp;
+        grp[1 + ngrp] = R;
+        grp[0] = ngrp;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ y sweep

@@ -311,3 +311,32 @@ def test_cg_iteration_more_than_32_populations(oracle):
         _check_iteration(ch, ref, ll)
         z, y = ref["z"], ref["y"]
     ch.close()
+
+
+@pytest.mark.parametrize("start", ["truth10", "random"])
+def test_cg_iteration_value_tables_large_windows(oracle, start):
+    """>= 4096 cells: the z sweep's lane-per-unit rounds run on candidate-owned value tables (shared-memory head +
+    global tail + direct fall-back) and must still equal the sequential oracle bit for bit; a few huge counts force
+    the fall-back paths."""
+    rng = np.random.default_rng(91)
+    G, C, K, L, S = 240, 6000, 9, 24, 3
+    counts, s, z_true, y_true = simulate_cg(rng, G, C, K, L, S, nrange=(300, 900))
+    counts[:8, rng.integers(0, C, 40)] += rng.integers(500, 4000, (8, 40)).astype(np.int32)  # beyond every table
+    A, O = _csc(counts)
+    if start == "random":
+        z, y = rng.integers(1, K + 1, C).astype(np.int32), rng.integers(1, L + 1, G).astype(np.int32)
+    else:
+        z, y = z_true.copy(), y_true.copy()
+        fz, fy = rng.random(C) < 0.1, rng.random(G) < 0.1
+        z[fz] = rng.integers(1, K + 1, fz.sum())
+        y[fy] = rng.integers(1, L + 1, fy.sum())
+    ch = cb.Chain(A, s, K=K, L=L)
+    ch.set_state(z, y)
+    for it in range(3):
+        ixy, uy = rng.permutation(G).astype(np.int32) + 1, rng.random(G)
+        ixz, uz = rng.permutation(C).astype(np.int32) + 1, rng.random(C)
+        ref = _oracle_iteration(oracle, O, s, z, y, K, L, ixy, uy, ixz, uz)
+        ll = ch.iterate(ixy, uy, ixz, uz)
+        _check_iteration(ch, ref, ll)
+        z, y = ref["z"], ref["y"]
+    ch.close()
