@@ -359,19 +359,18 @@ int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
         const long long room = ((long long)200 * 1024 - (long long)base) / (long long)sizeof(double);  // ~28 KB stays L1
         if (sms >= a.K && room >= 8LL * a.R && a.nM >= 4096) {
             a.EsCap = (int)std::min<long long>(room, 1 << 20);
-            if (b.ztHist.n < (size_t)a.R * ZT_BINS) CELDA_TRY(b.ztHist.alloc((size_t)a.R * ZT_BINS));
             if (b.ztOffg.n < (size_t)a.R + 1) {
+                CELDA_TRY(b.ztHist.alloc((size_t)a.R));  // per-row maximum count
                 CELDA_TRY(b.ztOffg.alloc((size_t)a.R + 1));
                 CELDA_TRY(b.ztGrp.alloc(ZT_MAXGRP + 2));
                 CELDA_TRY(b.ztTmp.alloc((size_t)a.R));
             }
-            CELDA_TRY(b.ztHist.zero(st));
-            k_row_hist<<<grid_for((long long)a.R * a.nM, 256, sms), 256, 0, st>>>(a.counts, a.R, a.nM, b.ztHist.p);
-            k_pick_rowV<<<1, 256, 0, st>>>(b.ztHist.p, a.R, a.EsCap, b.ztOffg.p, b.ztGrp.p, b.ztTmp.p);
             if (b.ztXT.n < (size_t)a.R * a.nM) CELDA_TRY(b.ztXT.alloc((size_t)a.R * a.nM));
+            CELDA_TRY(b.ztHist.zero(st));
             k_permute_transpose<<<(int)std::min<long long>((a.nM + 31) / 32, (long long)sms * 8), 256, 0, st>>>(
-                a.counts, a.R, a.nM, a.ix, b.ztXT.p);
-            count_launch(3);
+                a.counts, a.R, a.nM, a.ix, b.ztXT.p, b.ztHist.p);
+            k_pick_rowV<<<1, 256, 0, st>>>(b.ztHist.p, a.R, a.EsCap, b.ztOffg.p, b.ztGrp.p, b.ztTmp.p);
+            count_launch(2);
             a.offg = b.ztOffg.p;
             a.grp = b.ztGrp.p;
             a.xT = b.ztXT.p;

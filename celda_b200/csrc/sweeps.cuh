@@ -593,7 +593,7 @@ inline size_t z_sweep_smem(int R, int K, int nS, int T, int nwarp, int EsCap = 0
 // xT[r][t] = counts[r, ix[t] - 1]: the count matrix in visiting order, transposed, so that lanes holding
 // consecutive visiting positions read one row coalesced.  32 cells per block, tile transposed through shared memory.
 __global__ void k_permute_transpose(const int* __restrict__ counts, int R, long long nM, const int* __restrict__ ix,
-                                    int* __restrict__ xT) {
+                                    int* __restrict__ xT, int* __restrict__ rowMax /* [R], zeroed */) {
     __shared__ int tile[32][33];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
     for (long long t0 = (long long)blockIdx.x * 32; t0 < nM; t0 += (long long)gridDim.x * 32) {
@@ -604,38 +604,24 @@ __global__ void k_permute_transpose(const int* __restrict__ counts, int R, long 
             }
             __syncthreads();
             for (int rr = w; rr < 32; rr += nw) {  // warp rr writes row r0 + rr for 32 consecutive t (coalesced)
-                if (r0 + rr < R && t0 + lane < nM) xT[(size_t)(r0 + rr) * nM + t0 + lane] = tile[lane][rr];
+                int v = tile[lane][rr];
+                if (r0 + rr < R && t0 + lane < nM) xT[(size_t)(r0 + rr) * nM + t0 + lane] = v;
+                for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+                if (lane == 0 && r0 + rr < R && v > 0) atomicMax(&rowMax[r0 + rr], v);
             }
             __syncthreads();
         }
     }
 }
 
-// ---- per-row statistics of the count matrix behind the value tables
-constexpr int ZT_BINS = 2048;
-
-// hist[r][min(x, ZT_BINS - 1)] += 1 over an int32 R x nM column-major matrix
-__global__ void k_row_hist(const int* __restrict__ x, int R, long long nM, int* __restrict__ hist) {
-    const long long n = (long long)R * nM;
-    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) {
-        const int r = (int)(q % R);
-        const int v = min(max(x[q], 0), ZT_BINS - 1);
-        atomicAdd(&hist[r * ZT_BINS + v], 1);
-    }
-}
+constexpr int ZT_VMAX = 1 << 16;  // longest table of one row
 
 // Table length per row: the largest count seen (+ margin), then rows are packed greedily into groups of at most
 // EsCap entries.  Any length is CORRECT (a count beyond a row's table is evaluated directly); the choice only
 // decides how often that happens.  One block.
-__global__ void k_pick_rowV(const int* __restrict__ hist, int R, int EsCap, int* __restrict__ offg, int* __restrict__ grp,
+__global__ void k_pick_rowV(const int* __restrict__ rowMax, int R, int EsCap, int* __restrict__ offg, int* __restrict__ grp,
                             int* __restrict__ tmpV) {
-    for (int r = threadIdx.x; r < R; r += blockDim.x) {
-        const int* h = hist + r * ZT_BINS;
-        int mx = 0;
-        for (int v = 0; v < ZT_BINS; ++v)
-            if (h[v]) mx = v;
-        tmpV[r] = min(min(ZT_BINS, mx + 1 + 8), EsCap);
-    }
+    for (int r = threadIdx.x; r < R; r += blockDim.x) tmpV[r] = min(min(ZT_VMAX, rowMax[r] + 1), EsCap);
     __syncthreads();
     if (threadIdx.x == 0) {
         int og = 0, ngrp = 0, inGrp = 0;
