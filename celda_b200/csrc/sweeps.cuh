@@ -435,14 +435,12 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                     const int r0 = grp_s[1 + gI], r1 = grp_s[2 + gI];
                     const int e0 = offg_s[r0], ne = offg_s[r1] - e0;
                     __syncthreads();
-                    for (int q = threadIdx.x; q < ne; q += blockDim.x) {
-                        int lo = r0, hi2 = r1;  // largest r with offg[r] - e0 <= q
-                        while (hi2 - lo > 1) {
-                            const int mid = (lo + hi2) >> 1;
-                            if (offg_s[mid] - e0 <= q) lo = mid;
-                            else hi2 = mid;
+                    {
+                        int rr = r0;  // a thread's entries ascend, so its row only moves forward
+                        for (int q = threadIdx.x; q < ne; q += blockDim.x) {
+                            while (offg_s[rr + 1] - e0 <= q) ++rr;
+                            vt_s[q] = lg_tab(lgtab, T, (long long)ncol[rr] + (q - (offg_s[rr] - e0)), a.beta);
                         }
-                        vt_s[q] = lg_tab(lgtab, T, (long long)ncol[lo] + (q - (offg_s[lo] - e0)), a.beta);
                     }
                     __syncthreads();
                     for (long long ch = myRep + (long long)nrep * warp; ch < nchunk; ch += (long long)nrep * nwarp) {
@@ -455,21 +453,27 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                         const size_t o = (size_t)(t % a.w.Wmax) * K + j;
                         double S = (gI == 0) ? 0.0 : a.w.bufP[o];
                         int r = r0;
+                        const int* xp = x + (size_t)r0 * a.nM;  // walks down the rows: + nM per row
                         for (; r + 8 <= r1; r += 8) {  // eight row loads in flight, then eight look-ups in row order
                             int v[8];
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) v[k] = __ldg(x + (size_t)(r + k) * a.nM);
+                            for (int k = 0; k < 8; ++k) {
+                                v[k] = __ldg(xp);
+                                xp += a.nM;
+                            }
+                            int og = offg_s[r];
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
-                                const int og = offg_s[r + k];
-                                const double val = (v[k] < offg_s[r + k + 1] - og)
-                                                       ? vt_s[og - e0 + v[k]]
-                                                       : lg_tab(lgtab, T, (long long)ncol[r + k] + v[k], a.beta);
+                                const int ogn = offg_s[r + k + 1];
+                                const double val = (v[k] < ogn - og) ? vt_s[og - e0 + v[k]]
+                                                                    : lg_tab(lgtab, T, (long long)ncol[r + k] + v[k], a.beta);
                                 S += val;
+                                og = ogn;
                             }
                         }
                         for (; r < r1; ++r) {
-                            const int v = __ldg(x + (size_t)r * a.nM);
+                            const int v = __ldg(xp);
+                            xp += a.nM;
                             const int og = offg_s[r];
                             const double val = (v < offg_s[r + 1] - og) ? vt_s[og - e0 + v]
                                                                        : lg_tab(lgtab, T, (long long)ncol[r] + v, a.beta);
