@@ -274,17 +274,27 @@ def main():
         z_ms = pz["ms"] / max(1, pz["launches"])
         z_flop = FLOP_PER_LGAMMA * (float(nM) * a.K * a.L + 2.0 * nM * a.K)  # algorithmic: C*K*L sums + 2 scalars/cand
         ach = z_flop / (z_ms * 1e-3) / 1e12
-        # DRAM traffic of k_sweep_z per launch from the committed ncu --set full capture of this same command
+        # DRAM traffic per launch from the committed ncu --set full capture of this same command
         # (profiles/r1_ncu_full_sweeps_summary.csv: dram__bytes_read.sum + dram__bytes_write.sum), default config only
         default_cfg = (a.cells, a.genes, a.K, a.L) == (100000, 20000, 30, 150)
-        traffic = (63.262976 + 6.542080) * 1e6 if default_cfg else None
-        out["roofline"] = {"bound": "fp64", "kernel": "k_sweep_z", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                           "frac": ach / peak if peak else None, "traffic": traffic,
-                           "traffic_note": "bytes; algorithmic HBM bytes are 4*L*C (nTSByC) + 8*K*C (probs) = 84 MB, "
-                                           "the kernel is FP64-pipe bound (ncu: 62 % fp64 pipe, 0.26 % DRAM)",
-                           "note": "peak = DFMA rate measured live (2 flop/FMA); the sweep arithmetic is unfused "
-                                   "(-fmad=false, bit-reproducible), so 0.5 is its ceiling; not in MEASURED_PEAKS.json",
-                           "ms_per_launch": z_ms}
+        out["roofline"] = {
+            "bound": "fp64", "kernel": "k_sweep_z", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+            "frac": ach / peak if peak else None,
+            "traffic": (128.946944 + 20.384256) * 1e6 if default_cfg else None,
+            "traffic_note": "bytes; algorithmic HBM bytes are 4*L*C (nTSByC) + 4*L*C (visiting-order copy, written and read) "
+                            "+ 8*K*C (probs) = 144 MB",
+            "note": "achieved = ALGORITHMIC flops (C*K*L + 2*C*K lgamma at 56 flop, the reference's work) / device time; "
+                    "peak = DFMA rate measured live (2 flop/FMA; MEASURED_PEAKS.json has no FP64 entry).  In large rounds "
+                    "the kernel serves most lgamma terms from shared-memory value tables (bit-identical values), so the "
+                    "FP64 pipe itself is only ~20 % busy (ncu) and the limit is issue / shared-memory latency",
+            "ms_per_launch": z_ms}
+        y_ms = py["ms"] / max(1, py["launches"])
+        y_flop = FLOP_PER_LGAMMA * (float(nG) * a.L * a.K + 6.0 * nG * a.L)
+        out["roofline_y"] = {"bound": "fp64", "kernel": "k_sweep_y", "achieved": y_flop / (y_ms * 1e-3) / 1e12, "peak": peak,
+                             "unit": "TFLOP/s", "frac": y_flop / (y_ms * 1e-3) / 1e12 / peak if peak else None,
+                             "traffic": (3.136768 + 4.524800) * 1e6 if default_cfg else None, "ms_per_launch": y_ms,
+                             "note": "unfused bit-reproducible arithmetic: 0.5 of the FMA peak is the ceiling; ncu: fp64 "
+                                     "pipe 44 % busy; ~11 movers per sweep each cost a grid-wide round"}
         # ---- HBM-bound aggregation kernels: the full decomposition (set_state), timed separately from the step
         zc, yc = ch.get_state()
         ch.profile(True)

@@ -679,7 +679,8 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
     const int scratchD = max(2 * C + 8, 2 * L + (L + 1) / 2) + 2;
     double* lgtab = reinterpret_cast<double*>(smem_raw);
     double* lgt_s = lgtab + T;                          // [L][Cp] lgamma(t + beta)
-    double* scratch_all = lgt_s + (size_t)L * Cp;
+    double* tail_s = lgt_s + (size_t)L * Cp;             // [L][7] module-only terms of the second loop
+    double* scratch_all = tail_s + (size_t)L * 7;
     long long* T_s = reinterpret_cast<long long*>(scratch_all + (size_t)nwarp * scratchD);
     int* t_s = reinterpret_cast<int*>(T_s + L);         // [L][Cp]
     int* g_s = t_s + (size_t)L * Cp;
@@ -698,6 +699,25 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
         const int l = q / C, c = q % C;
         lgt_s[l * Cp + c] = lg_tab(lgtab, T, t_s[l * Cp + c], a.beta);
     }
+    __syncthreads();
+    // Module-only terms of cG_CalcGibbsProbY's second loop (:230-246), cached per module and refreshed when a
+    // gene enters or leaves it: lgamma(g-1+gamma), (g+gamma), (g+1+gamma), ((g-1) delta), (g delta), ((g+1) delta),
+    // (T + g delta) -- the same expressions the per-unit code evaluated, so the values are identical.
+    auto tail_fill = [&](int l, int k) {
+        const int g = g_s[l];
+        double v;
+        switch (k) {
+            case 0: v = dlgamma_hot((double)(g - 1) + a.gamma); break;
+            case 1: v = dlgamma_hot((double)g + a.gamma); break;
+            case 2: v = dlgamma_hot((double)(g + 1) + a.gamma); break;
+            case 3: v = dlgamma_hot((double)(g - 1) * a.delta); break;
+            case 4: v = dlgamma_hot((double)g * a.delta); break;
+            case 5: v = dlgamma_hot((double)(g + 1) * a.delta); break;
+            default: v = dlgamma_hot((double)T_s[l] + (double)g * a.delta); break;
+        }
+        tail_s[l * 7 + k] = v;
+    };
+    for (int q = threadIdx.x; q < L * 7; q += blockDim.x) tail_fill(q / 7, q % 7);
     __syncthreads();
 
     long long pos = 0, hi = 0, prev_end = 0;
@@ -739,6 +759,8 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                     T_s[db] += Ni;
                     if (blockIdx.x == 0) a.y[i] = db + 1;
                 }
+                __syncthreads();
+                if (threadIdx.x < 14) tail_fill(threadIdx.x < 7 ? da : db, threadIdx.x % 7);
                 ++movers;
                 // gavg: running estimate of the items between movers.  Under churn the window (and with it the
                 // patch + redraw work of every round) shrinks to a few gaps; results already computed beyond it
@@ -793,14 +815,16 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                 const int g = g_s[l];
                 const double Tl = (double)T_s[l], Ni = (double)a.nByG[i];
                 {
-                    // second loop of cG_CalcGibbsProbY (:230-246); (g0, g1) = (g, g-1) for the current module else (g+1, g)
+                    // second loop of cG_CalcGibbsProbY (:230-246); (g0, g1) = (g, g-1) for the current module else
+                    // (g+1, g): five of the six terms depend on the module only and come from the cache
+                    const double* tl = tail_s + l * 7;
                     const int g1 = isCur ? g - 1 : g, g0 = g1 + 1;
-                    p += dlgamma_hot((double)g0 + a.gamma);
-                    p -= dlgamma_hot((double)g1 + a.gamma);
-                    p += dlgamma_hot((double)g0 * a.delta);
-                    p -= dlgamma_hot((double)g1 * a.delta);
-                    p += dlgamma_hot(isCur ? Tl - Ni + (double)g1 * a.delta : Tl + (double)g1 * a.delta);
-                    p -= dlgamma_hot(isCur ? Tl + (double)g0 * a.delta : Tl + Ni + (double)g0 * a.delta);
+                    p += tl[isCur ? 1 : 2];
+                    p -= tl[isCur ? 0 : 1];
+                    p += tl[isCur ? 4 : 5];
+                    p -= tl[isCur ? 3 : 4];
+                    p += isCur ? dlgamma_hot(Tl - Ni + (double)g1 * a.delta) : tl[6];
+                    p -= isCur ? tl[6] : dlgamma_hot(Tl + Ni + (double)g0 * a.delta);
                 }
                 a.w.bufP[(size_t)(t % a.w.Wmax) * L + l] = p;
             }
@@ -930,7 +954,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
 inline size_t y_sweep_smem(int L, int C, int T, int nwarp) {
     const int Cp = C | 1;
     const size_t scratchD = (size_t)std::max(2 * C + 8, 2 * L + (L + 1) / 2) + 2;
-    return sizeof(double) * (T + (size_t)L * Cp + nwarp * scratchD) + sizeof(long long) * L +
+    return sizeof(double) * (T + (size_t)L * Cp + (size_t)L * 7 + nwarp * scratchD) + sizeof(long long) * L +
            sizeof(int) * ((size_t)L * Cp + L + 4);
 }
 
