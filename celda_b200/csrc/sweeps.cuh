@@ -134,12 +134,16 @@ __device__ int warp_sample_ll(double* pl, int n, double u, double* r, int* perm,
     __syncwarp();
     if (nc > 200) return -1;
     if (n == 1) return 0;
-    // Scan the values in descending order (the order revsort produces is unique up to ties).
+    // Scan the values in descending order (the order revsort produces is unique up to ties).  Peaked
+    // distributions end within a few warp arg-max steps; a diffuse one (more than 16 positive entries) switches to a rank sort after two.
     double cum = 0.0;
     int result = -1;
     bool slow = false;
     unsigned taken = 0;  // bit q: entry lane + 32 q of this lane has been consumed (n <= 1024)
-    for (int k = 0; k < n; ++k) {
+    const int P = n - nzero;
+    const int klimit = (P > 16) ? 2 : n;
+    int k = 0;
+    for (; k < klimit; ++k) {
         double bv = -1.0;
         int bi = 0x7fffffff;
         for (int i = lane, q = 0; i < n; i += 32, ++q) {
@@ -181,6 +185,48 @@ __device__ int warp_sample_ll(double* pl, int n, double u, double* r, int* perm,
             break;
         }
         if ((bi & 31) == lane) taken |= 1u << (bi >> 5);
+    }
+    if (!slow && result < 0) {
+        // Rank sort of the positive entries (hs aliases pl, which is no longer needed): position = number of larger
+        // values.  Any exact tie among positive entries leaves the order to heapsort => exact path.
+        bool tie = false;
+        for (int i = lane; i < n; i += 32) {
+            const double ri = r[i];
+            if (ri > 0.0) {
+                int gt = 0, eq = 0;
+                for (int j = 0; j < n; ++j) {
+                    const double v = r[j];
+                    gt += (v > ri);
+                    eq += (v == ri);
+                }
+                tie |= (eq > 1);
+                hs[gt] = ri;
+                perm[gt] = i;
+            }
+        }
+        __syncwarp();
+        if (__any_sync(FULL, tie)) {
+            slow = true;
+        } else {
+            for (; k < P; ++k) {  // continue the scan where the arg-max steps stopped; every lane, same order
+                cum = (k == 0) ? hs[k] : hs[k] + cum;
+                if (k == n - 1 || u <= cum) {
+                    result = perm[k];
+                    break;
+                }
+            }
+            if (result < 0) {  // every positive entry passed: R falls through to the last (zero) position
+                if (nzero == 1) {
+                    int zi = 0x7fffffff;
+                    for (int i = lane; i < n; i += 32)
+                        if (r[i] == 0.0) zi = i;
+                    for (int o = 16; o; o >>= 1) zi = min(zi, __shfl_xor_sync(FULL, zi, o));
+                    result = zi;
+                } else
+                    slow = true;
+            }
+        }
+        __syncwarp();
     }
     if (!slow) return result;
     // Exact emulation of ProbSampleReplace on one lane (rare: exact ties, or u beyond the total mass).
@@ -296,6 +342,9 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
 
     const double Rbeta = (double)R * a.beta;
     const int gwarp = blockIdx.x * nwarp + warp, tw = gridDim.x * nwarp;
+    // warp-granular work goes round the CTAs first (item c -> CTA c mod grid), so a short list of items lands on
+    // many SMs with one warp each instead of filling a few SMs
+    const int gwarpT = warp * gridDim.x + blockIdx.x;
 
     for (int q = threadIdx.x; q < R * K; q += blockDim.x) n_s[(q / R) * Rp + (q % R)] = a.nTab[q];
     for (int q = threadIdx.x; q < K; q += blockDim.x) nCP_s[q] = a.nCP[q];
@@ -393,7 +442,8 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                 __syncwarp();
                 if (lane == 0) {
                     double S = 0.0;
-                    for (int r = 0; r < R; ++r) S += scr[r];
+#pragma unroll 8
+                    for (int r = 0; r < R; ++r) S += scr[r];  // loads run ahead of the serial adds
                     a.w.colsum[j] = S;
                     a.w.lgnCP[j] = dlgamma((double)nCP_s[j] + Rbeta);
                 }
@@ -407,7 +457,8 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                 __syncwarp();
                 if (lane == 0) {
                     double S = 0.0;
-                    for (int r = 0; r < R; ++r) S += scr[r];
+#pragma unroll 8
+                    for (int r = 0; r < R; ++r) S += scr[r];  // loads run ahead of the serial adds
                     const size_t o = (size_t)(t % a.w.Wmax) * K + j;
                     a.w.bufP[o] = S;
                     a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
@@ -418,7 +469,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
         const bool bigRound = total >= (long long)tw * 16;
         if (bigRound && nrep > 0) {
             // (1) cached column sums and patch units: few, one warp each
-            for (long long uidx = gwarp; uidx < nd + nPatch; uidx += tw) {
+            for (long long uidx = gwarpT; uidx < nd + nPatch; uidx += tw) {
                 int j;
                 long long t;
                 decode(uidx, t, j);
@@ -485,7 +536,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                 }
             }
             // (3) each fresh cell against its own population (counts removed): direct evaluation, one warp each
-            for (long long q = gwarp; q < nFreshCells; q += tw) {
+            for (long long q = gwarpT; q < nFreshCells; q += tw) {
                 const long long t = hi + q;
                 warp_unit(t, a.z[a.ix[t] - 1] - 1);
             }
@@ -514,7 +565,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                 }
             }
         } else {
-            for (long long uidx = gwarp; uidx < total; uidx += tw) {
+            for (long long uidx = gwarpT; uidx < total; uidx += tw) {
                 int j;
                 long long t;
                 decode(uidx, t, j);
@@ -529,7 +580,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
         double* pl = scr;
         double* rr = scr + K;
         int* perm = reinterpret_cast<int*>(scr + 2 * K);
-        for (int c = gwarp; c < nwin; c += tw) {
+        for (int c = gwarpT; c < nwin; c += tw) {
             const long long t = pos + c;
             const long long i = a.ix[t] - 1;
             const int zi = a.z[i] - 1, si = a.s[i] - 1;
@@ -687,6 +738,9 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
     int* s_misc = g_s + L;
     double* scr = scratch_all + (size_t)warp * scratchD;
     const int gwarp = blockIdx.x * nwarp + warp, tw = gridDim.x * nwarp;
+    // warp-granular work goes round the CTAs first (item c -> CTA c mod grid), so a short list of items lands on
+    // many SMs with one warp each instead of filling a few SMs
+    const int gwarpT = warp * gridDim.x + blockIdx.x;
 
     for (int q = threadIdx.x; q < T; q += blockDim.x) lgtab[q] = dlgamma((double)q + a.beta);
     for (int q = threadIdx.x; q < L * C; q += blockDim.x) t_s[(q % L) * Cp + (q / L)] = a.tTab[q];
@@ -718,6 +772,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
         tail_s[l * 7 + k] = v;
     };
     for (int q = threadIdx.x; q < L * 7; q += blockDim.x) tail_fill(q / 7, q % 7);
+    bool tail_stale = false;
     __syncthreads();
 
     long long pos = 0, hi = 0, prev_end = 0;
@@ -759,8 +814,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                     T_s[db] += Ni;
                     if (blockIdx.x == 0) a.y[i] = db + 1;
                 }
-                __syncthreads();
-                if (threadIdx.x < 14) tail_fill(threadIdx.x < 7 ? da : db, threadIdx.x % 7);
+                tail_stale = true;  // the cached module terms are refreshed lazily, before the next lane-per-unit round
                 ++movers;
                 // gavg: running estimate of the items between movers.  Under churn the window (and with it the
                 // patch + redraw work of every round) shrinks to a few gaps; results already computed beyond it
@@ -783,6 +837,12 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
         const long long total = nPatch + nFresh;
         ++rounds;
         if (total >= (long long)tw * 16) {
+            if (tail_stale) {
+                __syncthreads();
+                for (int q = threadIdx.x; q < L * 7; q += blockDim.x) tail_fill(q / 7, q % 7);
+                tail_stale = false;
+                __syncthreads();
+            }
             // one lane per (gene, module) unit: the whole cG_CalcGibbsProbY term sequence in one thread
             for (long long uidx = (long long)gwarp * 32 + lane; uidx < total; uidx += (long long)tw * 32) {
                 long long t;
@@ -829,7 +889,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                 a.w.bufP[(size_t)(t % a.w.Wmax) * L + l] = p;
             }
         } else {
-            for (long long uidx = gwarp; uidx < total; uidx += tw) {
+            for (long long uidx = gwarpT; uidx < total; uidx += tw) {
                 long long t;
                 int l;
                 if (uidx < nPatch) {
@@ -883,6 +943,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                 __syncwarp();
                 if (lane == 0) {
                     double p = 0.0;
+#pragma unroll 8
                     for (int c = 0; c < C; ++c) {
                         p += scr[2 * c];
                         p -= scr[2 * c + 1];
@@ -905,7 +966,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
         double* pl = scr;
         double* rr = scr + L;
         int* perm = reinterpret_cast<int*>(scr + 2 * L);
-        for (int c = gwarp; c < nwin; c += tw) {
+        for (int c = gwarpT; c < nwin; c += tw) {
             const long long t = pos + c;
             const int i = a.ix[t] - 1;
             const int cur = a.y[i] - 1;
@@ -1002,6 +1063,9 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
     int* s_misc = ttile + YG_TILE * 32;
     double* scr = scratch_all + (size_t)warp * scratchD;
     const int gwarp = blockIdx.x * nwarp + warp, tw = gridDim.x * nwarp;
+    // warp-granular work goes round the CTAs first (item c -> CTA c mod grid), so a short list of items lands on
+    // many SMs with one warp each instead of filling a few SMs
+    const int gwarpT = warp * gridDim.x + blockIdx.x;
     const long long nM = a.nM;
     const int nchunk = (L + 31) / 32;
 
@@ -1168,7 +1232,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
         double* pl = scr;
         double* rr = scr + L;
         int* perm = reinterpret_cast<int*>(scr + 2 * L);
-        for (int c = gwarp; c < nwin; c += tw) {
+        for (int c = gwarpT; c < nwin; c += tw) {
             const long long tt = pos + c;
             const int i = a.ix[tt] - 1;
             const int cur = a.y[i] - 1;
