@@ -422,6 +422,29 @@ int run_sweep_yg(YGArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     return 0;
 }
 
+// celda_C Gibbs z sweep on the raw counts (k_sweep_zc): windows are whole waves of (cell group) x (population chunk)
+int run_sweep_zc(ZCArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
+    int threads = 1024;
+    if (zc_sweep_smem(a.K, a.nS, b.lgT, threads / 32) > 220 * 1024) threads = 512;
+    if (zc_sweep_smem(a.K, a.nS, b.lgT, threads / 32) > 220 * 1024) threads = 256;
+    const size_t smem = zc_sweep_smem(a.K, a.nS, b.lgT, threads / 32);
+    if (smem > 220 * 1024)
+        return fail("celda_C z sweep: K=%d, %d samples need %zu bytes of shared memory (> 220 KB)", a.K, a.nS, smem);
+    const int nwarp = threads / 32, nchunk = (a.K + 31) / 32;
+    long long unit = std::max<long long>(nwarp, (long long)nwarp * sms / nchunk / nwarp * nwarp);
+    const long long cap = std::min<long long>(b.Wmax, 8192);
+    if (unit > cap) unit = cap / nwarp * nwarp;
+    const long long full = std::max<long long>(1, cap / unit) * unit;
+    a.w = SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
+                    b.stats.p + 8 * which, b.Wmax, (int)full, (int)unit, std::max(b.Wmin, nwarp), b.lgT};
+    CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_zc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CELDA_CUDA_OK(cudaMemsetAsync(b.barrier.p, 0, sizeof(unsigned), st));
+    void* args[] = {&a};
+    CELDA_CUDA_OK(cudaLaunchCooperativeKernel((void*)k_sweep_zc, dim3(sms), dim3(threads), args, smem, st));
+    count_launch();
+    return 0;
+}
+
 int sweep_status(int stv) {
     if (stv == -1) return fail("sample.int would take the Walker alias branch (> 200 likely categories): not supported");
     if (stv == -2) return fail("NA in probability vector");
@@ -518,7 +541,36 @@ int chain_step_y(celda_chain* h, const int* d_ix, const double* d_u, int doSampl
 
 // z sweep + colSumByGroupChange (R/celda_CG.R:567-585)
 int chain_step_z(celda_chain* h, const int* d_ix, const double* d_u, int doSample) {
-    if (h->model != CELDA_MODEL_CG) return fail("sweep_z_gibbs: only the celda_CG chain is implemented on this handle");
+    if (h->model == CELDA_MODEL_G) return fail("sweep_z_gibbs: celda_G has no cell populations");
+    if (h->model == CELDA_MODEL_C) {  // raw counts against nGByCP (R/celda_C.R:427-440); the kernel keeps the tables current
+        if (h->comm) return fail("sweep_z_gibbs: a cell-sharded celda_C chain runs the EM z step only");
+        ProfScope ps(h, 2);
+        const long long nt = (long long)h->nG * h->K;
+        k_lgt_fill<<<grid_for(nt, 256, h->sms), 256, 0, h->st>>>(h->nGByCP.p, nt, h->beta, h->lgt.p);
+        count_launch();
+        ZCArgs a{};
+        a.nG = h->nG;
+        a.K = h->K;
+        a.nS = h->nS;
+        a.nM = h->nM;
+        a.cp = h->cp.p;
+        a.ci = h->ci.p;
+        a.cx = h->cx.p;
+        a.nByC = h->nByC.p;
+        a.s = h->s.p;
+        a.z = h->z.p;
+        a.n = h->nGByCP.p;
+        a.lgn = h->lgt.p;
+        a.nCP = h->nCP.p;
+        a.mCPByS = h->mCPByS.p;
+        a.alpha = h->alpha;
+        a.beta = h->beta;
+        a.ix = d_ix;
+        a.u = d_u;
+        a.doSample = doSample;
+        a.probs = h->probsZ.p;
+        return run_sweep_zc(a, h->wb, h->sms, 2, h->st);
+    }
     CELDA_CUDA_OK(cudaMemcpyAsync(h->zprev.p, h->z.p, sizeof(int) * h->nM, cudaMemcpyDeviceToDevice, h->st));
     CELDA_TRY(launch_sweep_z(h, d_ix, d_u, doSample, 2));
     if (doSample) {
@@ -1426,6 +1478,7 @@ int celda_chain_create(celda_chain** out, int device, int model, int nG, int nM,
         CELDA_TRY(h->probsZ.alloc((size_t)h->K * nM));
     }
     if (model == CELDA_MODEL_CG) CELDA_TRY(h->nTSByCP.alloc((size_t)h->L * h->K));
+    if (model == CELDA_MODEL_C) CELDA_TRY(h->lgt.alloc((size_t)nG * h->K));  // lgamma(nGByCP + beta), Gibbs z sweep
     CELDA_TRY(h->wb.alloc(std::max(h->K, h->L), st));
     CELDA_TRY(h->ixy.alloc(nG));
     CELDA_TRY(h->uy.alloc(nG));
@@ -1602,7 +1655,19 @@ int celda_chain_iterate(celda_chain* h, const int* ix_y, const double* u_y, cons
     CELDA_CUDA_OK(cudaSetDevice(h->device));
     if (!h->has_state) return fail("set_state must be called first");
     cudaStream_t st = h->st;
-    if (h->model == CELDA_MODEL_C) return fail("iterate: the celda_C chain iterates with celda_chain_iterate_em");
+    if (h->model == CELDA_MODEL_C) {  // .celda_C loop body, algorithm = "Gibbs" (R/celda_C.R:427-470): z sweep, log-likelihood
+        if (ix_z && u_z) {
+            CELDA_TRY(validate_order(ix_z, h->nM, "ix_z"));
+            CELDA_CUDA_OK(cudaMemcpyAsync(h->ixz.p, ix_z, sizeof(int) * h->nM, cudaMemcpyHostToDevice, st));
+            CELDA_CUDA_OK(cudaMemcpyAsync(h->uz.p, u_z, sizeof(double) * h->nM, cudaMemcpyHostToDevice, st));
+        } else {
+            CELDA_TRY(chain_philox_draws(h, h->nM, h->ixz.p, h->uz.p));
+        }
+        CELDA_TRY(chain_step_z(h, h->ixz.p, h->uz.p, 1));
+        CELDA_TRY(chain_loglik_async(h));
+        CELDA_CUDA_OK(cudaMemcpyAsync(ll, h->llOut.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        return chain_check_status(h);
+    }
     if (h->model == CELDA_MODEL_G) {  // .celda_G loop body (R/celda_G.R:400-424): y sweep, log-likelihood
         if (ix_y && u_y) {
             CELDA_TRY(validate_order(ix_y, h->nG, "ix_y"));

@@ -1260,6 +1260,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
         grid_sync(a.w.barrier, bar_target);
         CELDA_TICK(ck_bar);
     }
+    __syncthreads();  // thread 0's last commit (a mover in the final position) precedes the write-back
     if (blockIdx.x == 0) {
         for (int q = threadIdx.x; q < L; q += blockDim.x) {
             a.nByTS[q] = T_s[q];
@@ -1290,5 +1291,267 @@ __global__ void k_lgt_fill(const int* __restrict__ t, long long n, double beta, 
         lgt[q] = dlgamma_hot((double)v + beta);
     }
 }
+
+// ------------------------------------------------------------------------------------------------ z sweep, celda_C
+// .cCCalcGibbsProbZ on the RAW counts (celda_C: R/celda_C.R:427-440 with algorithm = "Gibbs"): per (cell,
+// population) the reference sums lgamma over ALL nG genes, zeros included (sum(lgamma(nGByCP[, j] + counts[, i] +
+// beta)), :664-687) -- a serial chain of nG adds whose order fixes the bits.  Same structure as k_sweep_yg with the
+// roles swapped: nGByCP (gene-major [nG][K]) and its cached lgamma stay in HBM; one CTA task = (one cell per warp)
+// x (32 populations, one per lane); the cached-lgamma tile of 128 genes is staged in shared memory once for the
+// CTA's cells; each warp walks it in gene order with the cell's CSC column as a cursor, adding the cached value
+// where the cell has no count and a fresh lgamma where it has one.
+struct ZCArgs {
+    int nG, K, nS;
+    long long nM;
+    const int* cp;      // CSC column pointers [nM + 1]
+    const int* ci;      //   row of each stored entry, ascending within a column
+    const int* cx;      //   value
+    const int* nByC;
+    const int* s;
+    int* z;             // [nM] 1-based, updated
+    int* n;             // nGByCP gene-major [nG][K], updated
+    double* lgn;        // lgamma(n + beta), same layout, maintained
+    long long* nCP;     // [K], updated
+    int* mCPByS;        // K x nS, updated
+    double alpha, beta;
+    const int* ix;
+    const double* u;
+    int doSample;
+    double* probs;      // K x nM or null
+    SweepWork w;
+};
+
+__global__ void __launch_bounds__(1024, 1) k_sweep_zc(ZCArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int K = a.K, nS = a.nS, T = a.w.lgT, R = a.nG;
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int scratchD = 2 * K + (K + 1) / 2 + 2;
+    double* lgtab = reinterpret_cast<double*>(smem_raw);
+    double* tile = lgtab + T;                             // [YG_TILE][32] lgamma(n + beta)
+    double* scratch_all = tile + YG_TILE * 32;
+    long long* nCP_s = reinterpret_cast<long long*>(scratch_all + (size_t)nwarp * scratchD);
+    int* ntile = reinterpret_cast<int*>(nCP_s + K);       // [YG_TILE][32] n
+    int* m_s = ntile + YG_TILE * 32;
+    int* s_misc = m_s + K * nS;
+    double* scr = scratch_all + (size_t)warp * scratchD;
+    const int tw = gridDim.x * nwarp;
+    const int gwarpT = warp * gridDim.x + blockIdx.x;
+    const int nchunk = (K + 31) / 32;
+    const double Rbeta = (double)R * a.beta;
+
+    for (int q = threadIdx.x; q < T; q += blockDim.x) lgtab[q] = dlgamma((double)q + a.beta);
+    for (int q = threadIdx.x; q < K; q += blockDim.x) nCP_s[q] = a.nCP[q];
+    for (int q = threadIdx.x; q < K * nS; q += blockDim.x) m_s[q] = a.mCPByS[q];
+    __syncthreads();
+
+    long long pos = 0, hi = 0, prev_end = 0;
+    int W = a.w.Wfull, nd = K, da = -1, db = -1, gavg = a.w.Wfull;  // nd == K: every cached column sum is due
+    bool have_spec = false;
+    unsigned bar_target = 0;
+    long long rounds = 0, units_done = 0, movers = 0;
+
+    while (true) {
+        bool committed = false;
+        if (have_spec) {
+            const int nwin = (int)(prev_end - pos);
+            const int first = block_first_mover(a.w.spec, nwin, s_misc);
+            if (first < 0) {
+                pos = prev_end;
+                hi = pos;
+                nd = 0;
+                gavg = min(2 * gavg + nwin, 1 << 24);
+                W = min(2 * W, a.w.Wfull);
+            } else {
+                const long long tt = pos + first;
+                const long long i = a.ix[tt] - 1;
+                const int packed = __ldcg(a.w.spec + first);
+                da = packed >> 16;
+                db = packed & 0xffff;
+                // the two table columns change only where the cell has counts: the grid shares the cell's entries
+                const int e0 = a.cp[i], e1 = a.cp[i + 1];
+                for (int e = e0 + blockIdx.x * blockDim.x + threadIdx.x; e < e1; e += gridDim.x * blockDim.x) {
+                    const size_t base = (size_t)a.ci[e] * K;
+                    const int xv = a.cx[e];
+                    const int na = __ldcg(a.n + base + da) - xv, nb = __ldcg(a.n + base + db) + xv;
+                    a.n[base + da] = na;
+                    a.n[base + db] = nb;
+                    a.lgn[base + da] = lg_tab(lgtab, T, na, a.beta);
+                    a.lgn[base + db] = lg_tab(lgtab, T, nb, a.beta);
+                }
+                if (threadIdx.x == 0) {
+                    const int Ni = a.nByC[i], si = a.s[i] - 1;
+                    nCP_s[da] -= Ni;
+                    nCP_s[db] += Ni;
+                    m_s[si * K + da] -= 1;
+                    m_s[si * K + db] += 1;
+                    if (blockIdx.x == 0) a.z[i] = db + 1;
+                }
+                ++movers;
+                gavg = max(1, (3 * gavg + first + 1) / 4);
+                W = (int)max((long long)a.w.Wmin, min(4LL * gavg, (long long)a.w.Wfull));
+                W = ((W + nwarp - 1) / nwarp) * nwarp;
+                pos = tt + 1;
+                hi = min(prev_end, pos + W);
+                nd = 2;
+                committed = true;
+            }
+        }
+        if (pos >= a.nM) break;
+        if (committed || rounds == 0) grid_sync(a.w.barrier, bar_target);  // table columns visible before they are read
+        const long long end = max(hi, min(pos + (long long)W, a.nM));
+        const int nwin = (int)(end - pos);
+        // ---- tasks: cached column sums of the changed columns (one warp, lane = column); patch = (nwarp carried
+        // cells) x {da, db}; fresh = (nwarp new cells) x (32-population chunk)
+        const long long nSumTask = (nd == K) ? nchunk : (nd == 2 ? 1 : 0);
+        const long long nPatchGrp = (nd == 2) ? (hi - pos + nwarp - 1) / nwarp : 0;
+        const long long nFreshGrp = (end - hi + nwarp - 1) / nwarp;
+        const long long ntask = nSumTask + nPatchGrp + nFreshGrp * nchunk;
+        ++rounds;
+        for (long long task = blockIdx.x; task < ntask; task += gridDim.x) {
+            if (task < nSumTask) {
+                // sum(lgamma(nGByCP[, j] + beta)) added serially over the genes, one lane per column
+                if (warp == 0) {
+                    int j;
+                    if (nd == K) {
+                        j = (int)task * 32 + lane;
+                        if (j >= K) j = -1;
+                    } else {
+                        j = (lane == 0) ? da : (lane == 1 ? db : -1);
+                    }
+                    if (j >= 0) {
+                        double S = 0.0;
+#pragma unroll 8
+                        for (int r = 0; r < R; ++r) S += __ldcg(a.lgn + (size_t)r * K + j);
+                        a.w.colsum[j] = S;
+                        a.w.lgnCP[j] = dlgamma((double)nCP_s[j] + Rbeta);
+                    }
+                }
+                continue;
+            }
+            long long tcell;
+            int j;
+            bool valid;
+            if (task < nSumTask + nPatchGrp) {
+                tcell = pos + (task - nSumTask) * nwarp + warp;
+                valid = tcell < hi;
+                j = (lane == 0) ? da : (lane == 1 ? db : -1);
+            } else {
+                const long long q = task - nSumTask - nPatchGrp;
+                tcell = hi + (q / nchunk) * nwarp + warp;
+                valid = tcell < end;
+                j = (int)(q % nchunk) * 32 + lane;
+                if (j >= K) j = -1;
+            }
+            const long long i = valid ? a.ix[tcell] - 1 : 0;
+            const int zi = valid ? a.z[i] - 1 : -1;
+            const bool active = valid && j >= 0;
+            const int sgn = (active && j == zi) ? -1 : 1;
+            const int jsafe = (j >= 0) ? j : 0;
+            int nz = valid ? a.cp[i] : 0;
+            const int nzEnd = valid ? a.cp[i + 1] : 0;
+            const int NONE = 0x7fffffff;
+            int nextrow = (nz < nzEnd) ? a.ci[nz] : NONE;
+            int nextx = (nz < nzEnd) ? a.cx[nz] : 0;
+            double S = 0.0;
+            for (int r0 = 0; r0 < R; r0 += YG_TILE) {
+                const int tc = min(YG_TILE, R - r0);
+                __syncthreads();
+                for (int rr = warp; rr < tc; rr += nwarp) {
+                    const size_t g = (size_t)(r0 + rr) * K + jsafe;
+                    tile[rr * 32 + lane] = (j >= 0) ? __ldcg(a.lgn + g) : 0.0;
+                    ntile[rr * 32 + lane] = (j >= 0) ? __ldcg(a.n + g) : 0;
+                }
+                __syncthreads();
+                if (active) {
+                    int rr = 0;
+                    while (rr < tc) {
+                        const int stop = (nextrow - r0 < tc) ? nextrow - r0 : tc;
+#pragma unroll 4
+                        for (; rr < stop; ++rr) S += tile[rr * 32 + lane];
+                        if (rr < tc) {
+                            S += lg_tab(lgtab, T, (long long)ntile[rr * 32 + lane] + sgn * nextx, a.beta);
+                            ++nz;
+                            nextrow = (nz < nzEnd) ? a.ci[nz] : NONE;
+                            nextx = (nz < nzEnd) ? a.cx[nz] : 0;
+                            ++rr;
+                        }
+                    }
+                } else {
+                    while (nextrow < r0 + tc) {
+                        ++nz;
+                        nextrow = (nz < nzEnd) ? a.ci[nz] : NONE;
+                    }
+                }
+            }
+            if (active) {
+                const size_t o = (size_t)(tcell % a.w.Wmax) * K + j;
+                a.w.bufP[o] = S;
+                a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
+            }
+        }
+        units_done += ntask;
+        grid_sync(a.w.barrier, bar_target);
+        // ---- combine in the reference's order (R/celda_C.R:664-687), draw
+        double* pl = scr;
+        double* rr2 = scr + K;
+        int* perm = reinterpret_cast<int*>(scr + 2 * K);
+        for (int c = gwarpT; c < nwin; c += tw) {
+            const long long tt = pos + c;
+            const long long i = a.ix[tt] - 1;
+            const int zi = a.z[i] - 1, si = a.s[i] - 1;
+            const size_t o = (size_t)(tt % a.w.Wmax) * K;
+            for (int j = lane; j < K; j += 32) {
+                const double S = __ldcg(a.w.bufP + o + j), A = __ldcg(a.w.bufA + o + j);
+                const double cs = __ldcg(a.w.colsum + j), lc = __ldcg(a.w.lgnCP + j);
+                double p = dlog((double)(m_s[si * K + j] - (j == zi)) + a.alpha);
+                if (j != zi) {
+                    p = p + S;
+                    p = p - A;
+                    p = p - cs;
+                    p = p + lc;
+                } else {
+                    p = p + cs;
+                    p = p - lc;
+                    p = p - S;
+                    p = p + A;
+                }
+                pl[j] = p;
+                if (a.probs) a.probs[i * K + j] = p;
+            }
+            __syncwarp();
+            int znew = zi;
+            if (a.doSample) {
+                znew = warp_sample_ll(pl, K, a.u[tt], rr2, perm, lane);
+                if (znew < 0) {
+                    if (lane == 0) atomicCAS(a.w.status, 0, znew);
+                    znew = zi;
+                }
+            }
+            if (lane == 0) a.w.spec[c] = (znew != zi) ? ((zi << 16) | znew) : -1;
+            __syncwarp();
+        }
+        prev_end = end;
+        have_spec = true;
+        grid_sync(a.w.barrier, bar_target);
+    }
+    __syncthreads();  // thread 0's last commit (a mover in the final position) precedes the write-back
+    if (blockIdx.x == 0) {
+        for (int q = threadIdx.x; q < K; q += blockDim.x) a.nCP[q] = nCP_s[q];
+        for (int q = threadIdx.x; q < K * nS; q += blockDim.x) a.mCPByS[q] = m_s[q];
+        if (threadIdx.x == 0) {
+            a.w.stats[0] += rounds;
+            a.w.stats[1] += units_done;
+            a.w.stats[2] += movers;
+        }
+    }
+}
+
+inline size_t zc_sweep_smem(int K, int nS, int T, int nwarp) {
+    const size_t scratchD = (size_t)2 * K + (K + 1) / 2 + 2;
+    return sizeof(double) * (T + YG_TILE * 32 + nwarp * scratchD) + sizeof(long long) * K +
+           sizeof(int) * (YG_TILE * 32 + (size_t)K * nS + 4);
+}
+
+// lgn = lgamma(n + beta) over a gene-major [nG][K] table (k_lgt_fill serves: layout-agnostic)
 
 }  // namespace celda
