@@ -12,7 +12,7 @@ import itertools
 
 import numpy as np
 
-from . import MODEL_C, MODEL_CG, Chain
+from . import MODEL_C, MODEL_CG, MODEL_G, Chain
 
 
 def initialize_cluster(N, length, initial=None, rng=None):
@@ -42,7 +42,7 @@ def _run_chain(ch, algorithm, maxIter, stopIter, draws, rng, nG, nM, model):
     it, noImp = 1, 0
     while it <= maxIter and noImp <= stopIter:
         if draws == "philox":
-            if model == MODEL_CG and algorithm == "Gibbs":
+            if algorithm == "Gibbs":  # celda_CG: y + z sweeps; celda_C: z sweep; celda_G: y sweep; then the LL
                 temp = ch.iterate_philox()
             else:
                 if model == MODEL_CG:
@@ -91,11 +91,12 @@ def celda_CG(counts, sampleLabel, K, L, alpha=1.0, beta=1.0, delta=1.0, gamma=1.
 
 def celda_C(counts, sampleLabel, K, alpha=1.0, beta=1.0, algorithm="EM", stopIter=10, maxIter=200, seed=12345,
             nchains=3, zInitialize="random", zInit=None, device=0):
-    """celda_C with the EM z step (R/celda_C.R:306-616; EM forces stopIter <- 1, :351-353).  The best chain is
-    returned (R/celda_C.R:577-589 does this correctly)."""
-    if algorithm != "EM":
-        raise NotImplementedError("celda_C Gibbs on raw counts is served by cCCalcGibbsProbZ on densified input only")
-    stopIter = 1
+    """celda_C (R/celda_C.R:306-616), algorithm = "EM" (forces stopIter <- 1, :351-353) or "Gibbs" (the z sweep on
+    the raw counts, :427-440).  The best chain is returned (R/celda_C.R:577-589 does this correctly)."""
+    if algorithm not in ("EM", "Gibbs"):
+        raise ValueError("'algorithm' must be 'EM' or 'Gibbs'")
+    if algorithm == "EM":
+        stopIter = 1
     chains = []
     ch = Chain(counts, sampleLabel, K=K, alpha=alpha, beta=beta, model=MODEL_C, device=device)
     try:
@@ -103,11 +104,33 @@ def celda_C(counts, sampleLabel, K, alpha=1.0, beta=1.0, algorithm="EM", stopIte
             rng = np.random.Generator(np.random.PCG64(seed + c - 1))
             z = initialize_cluster(K, counts.ncol, zInit if zInitialize == "predefined" else None, rng)
             ch.set_state(z=z)
-            chains.append(_run_chain(ch, "EM", maxIter, stopIter, "philox", rng, counts.nrow, counts.ncol, MODEL_C))
+            ch.seed(seed, stream=c - 1)
+            chains.append(_run_chain(ch, algorithm, maxIter, stopIter, "philox", rng, counts.nrow, counts.ncol, MODEL_C))
     finally:
         ch.close()
     best = max(range(nchains), key=lambda i: chains[i]["finalLogLik"])
-    return dict(chains=chains, model=chains[best], bestChain=best + 1, params=dict(K=K, alpha=alpha, beta=beta, seed=seed))
+    return dict(chains=chains, model=chains[best], bestChain=best + 1,
+                params=dict(K=K, alpha=alpha, beta=beta, algorithm=algorithm, seed=seed))
+
+
+def celda_G(counts, L, beta=1.0, delta=1.0, gamma=1.0, stopIter=10, maxIter=200, seed=12345, nchains=3,
+            yInitialize="random", yInit=None, device=0):
+    """celda_G (R/celda_G.R:268-520): Gibbs y sweeps on the raw counts, split heuristics off; best chain returned
+    (R/celda_G.R:483-494)."""
+    chains = []
+    ch = Chain(counts, None, L=L, beta=beta, delta=delta, gamma=gamma, model=MODEL_G, device=device)
+    try:
+        for c in range(1, nchains + 1):
+            rng = np.random.Generator(np.random.PCG64(seed + c - 1))
+            y = initialize_cluster(L, counts.nrow, yInit if yInitialize == "predefined" else None, rng)
+            ch.set_state(y=y)
+            ch.seed(seed, stream=c - 1)
+            chains.append(_run_chain(ch, "Gibbs", maxIter, stopIter, "philox", rng, counts.nrow, counts.ncol, MODEL_G))
+    finally:
+        ch.close()
+    best = max(range(nchains), key=lambda i: chains[i]["finalLogLik"])
+    return dict(chains=chains, model=chains[best], bestChain=best + 1,
+                params=dict(L=L, beta=beta, delta=delta, gamma=gamma, seed=seed))
 
 
 # ------------------------------------------------------------------ celdaGridSearch chain partitioning

@@ -106,3 +106,28 @@ def test_celda_C_gibbs_philox_replay(oracle, gold_c):
         assert abs(ll - ll_ref) <= 1e-9 * abs(ll_ref)
         z = ref["z"]
     ch.close()
+
+
+def test_model_drivers_celda_C_gibbs_and_celda_G(oracle, gold_c, gold_g):
+    """celda_C(algorithm = "Gibbs") and celda_G chain loops: the reported best log-likelihood is the oracle's
+    log-likelihood of the returned labels, and it improves on the random start."""
+    from celda_b200 import model
+    counts, s, K = gold_c["counts"], gold_c["s_mod"], 10
+    A, O = cb.CSC.from_dense(counts), dense_to_csc(counts)
+    res = model.celda_C(A, s, K, algorithm="Gibbs", maxIter=12, nchains=2, seed=7)
+    m = res["model"]
+    p = oracle.cCDecomposeCounts(O, s, m["z"], K)
+    want = oracle.cCCalcLL(p["mCPByS"], p["nGByCP"], K, p["nS"], p["nG"], 1.0, 1.0)
+    assert abs(m["finalLogLik"] - want) <= 1e-9 * abs(want)
+    assert m["finalLogLik"] > m["completeLogLik"][0]
+    assert m["finalLogLik"] == max(c["finalLogLik"] for c in res["chains"])
+
+    counts, L = gold_g["counts"], 10
+    A, O = cb.CSC.from_dense(counts), dense_to_csc(counts)
+    res = model.celda_G(A, L, maxIter=8, nchains=2, seed=7)
+    m = res["model"]
+    p = oracle.cGDecomposeCounts(O, m["y"], L)
+    want = oracle.cGCalcLL(p["nTSByC"], p["nByTS"], p["nByG"], p["nGByTS"], counts.shape[1], counts.shape[0], L,
+                           1.0, 1.0, 1.0)
+    assert abs(m["finalLogLik"] - want) <= 1e-9 * abs(want)
+    assert m["finalLogLik"] > m["completeLogLik"][0]
