@@ -69,17 +69,19 @@ struct celda_comm {
 
 // Work space of the sweep kernels (ring buffers, speculation flags, barrier, status, statistics).
 struct SweepBufs {
-    DevBuf<double> bufP, bufA, colsum, lgnCP;
-    DevBuf<int> spec, status;
+    DevBuf<double> bufP, bufA, colsum, lgnCP, drawMx;
+    DevBuf<int> spec, status, drawNz;
     DevBuf<unsigned> barrier;
     DevBuf<long long> stats;  // [which][8]
     // value tables of the z sweep (k_sweep_z): row histogram, per-row offsets, per-CTA global tables
     DevBuf<int> ztHist, ztOffg, ztGrp, ztTmp, ztXT;
-    int Wmax = 32768, Wmin = 32, lgT = 2048;
+    int Wmax = 32768, Wmin = 32, lgT = 2048;  // Wmax: ring capacity, a power of two (ring_slot)
     int alloc(int ncand, cudaStream_t st) {
         CELDA_TRY(bufP.alloc((size_t)Wmax * ncand));
         CELDA_TRY(bufA.alloc((size_t)Wmax * ncand));
         CELDA_TRY(spec.alloc(Wmax));
+        CELDA_TRY(drawMx.alloc(Wmax));
+        CELDA_TRY(drawNz.alloc((size_t)4 * Wmax));
         CELDA_TRY(colsum.alloc(ncand));
         CELDA_TRY(lgnCP.alloc(ncand));
         CELDA_TRY(status.alloc(1));
@@ -328,6 +330,13 @@ int chain_loglik_async(celda_chain* h) {
     return run_loglik(in, h->llPartial.p, h->llOut.p, h->st);
 }
 
+// Steady-state window caps (items); CELDA_CUDA_YCAP / CELDA_CUDA_ZCAP override them for tuning runs.
+int window_cap(const char* env, int dflt) {
+    const char* v = getenv(env);
+    const int c = v ? atoi(v) : 0;
+    return c > 0 ? c : dflt;
+}
+
 // Window sizes (items).  unit: the item count whose units (items x candidates) fill one grid-wide lane pass;
 // full: the largest multiple of it that fits the ring buffer, so lane-per-unit rounds leave no thread idle.
 void window_sizes(const SweepBufs& b, int sms, int threads, int ncand, int cap, int* full, int* unit) {
@@ -343,7 +352,7 @@ void window_sizes(const SweepBufs& b, int sms, int threads, int ncand, int cap, 
 SweepWork make_work(SweepBufs& b, int sms, int threads, int ncand, int which, int cap) {
     int wfull, wunit;
     window_sizes(b, sms, threads, ncand, std::min(cap, b.Wmax), &wfull, &wunit);
-    return SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
+    return SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.drawMx.p, b.drawNz.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
                      b.stats.p + 8 * which, b.Wmax, wfull, wunit, b.Wmin, b.lgT};
 }
 
@@ -351,7 +360,7 @@ SweepWork make_work(SweepBufs& b, int sms, int threads, int ncand, int which, in
 int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     int threads = 1024;
     if (z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32) > 220 * 1024) threads = 512;
-    a.w = make_work(b, sms, threads, a.K, which, 32768);
+    a.w = make_work(b, sms, threads, a.K, which, window_cap("CELDA_CUDA_ZCAP", 32768));
     // value tables: the shared memory left over holds the heads; sized from this sweep's count distribution
     a.EsCap = 0;
     {
@@ -389,7 +398,7 @@ int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
 int run_sweep_y(YArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     int threads = 1024;
     if (y_sweep_smem(a.L, a.ncol, b.lgT, threads / 32) > 220 * 1024) threads = 512;
-    a.w = make_work(b, sms, threads, a.L, which, 8192);
+    a.w = make_work(b, sms, threads, a.L, which, window_cap("CELDA_CUDA_YCAP", 8192));
     const size_t smem = y_sweep_smem(a.L, a.ncol, b.lgT, threads / 32);
     if (smem > 220 * 1024) return fail("y sweep: L=%d x K=%d tables need %zu bytes of shared memory (> 220 KB)", a.L, a.ncol, smem);
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -412,7 +421,7 @@ int run_sweep_yg(YGArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     const long long cap = std::min<long long>(b.Wmax, 8192);
     if (unit > cap) unit = cap / nwarp * nwarp;
     const long long full = std::max<long long>(1, cap / unit) * unit;
-    a.w = SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
+    a.w = SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.drawMx.p, b.drawNz.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
                     b.stats.p + 8 * which, b.Wmax, (int)full, (int)unit, std::max(b.Wmin, nwarp), b.lgT};
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_yg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CELDA_CUDA_OK(cudaMemsetAsync(b.barrier.p, 0, sizeof(unsigned), st));
@@ -435,7 +444,7 @@ int run_sweep_zc(ZCArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     const long long cap = std::min<long long>(b.Wmax, 8192);
     if (unit > cap) unit = cap / nwarp * nwarp;
     const long long full = std::max<long long>(1, cap / unit) * unit;
-    a.w = SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
+    a.w = SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.drawMx.p, b.drawNz.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
                     b.stats.p + 8 * which, b.Wmax, (int)full, (int)unit, std::max(b.Wmin, nwarp), b.lgT};
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_zc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CELDA_CUDA_OK(cudaMemsetAsync(b.barrier.p, 0, sizeof(unsigned), st));

@@ -173,10 +173,11 @@ __device__ __noinline__ double dlgamma_generic(double x) {
     return dlgamma_large(x);
 }
 
-// Hot-range lgamma: 10 < x <= 4934720 (a count plus a prior), straight-line code.  Performs exactly the
-// operations of dlgamma_large()/dlog() for such x (x is normal, exponent k >= 3, Stirling correction below its
-// large-x cut-off); the two data-dependent forms of the log tail are both evaluated and selected, which costs a
-// few flops but keeps the warp converged.  Arguments within 2^-20 of a power of two (e.g. 63 + 1) take the
+// Hot-range lgamma: 10 < x <= 1e17 (a count plus a prior), straight-line code.  Performs exactly the
+// operations of dlgamma_large()/dlog() for such x (x is normal, exponent k >= 3; the Stirling correction is
+// evaluated always and dropped above lgammafn's 4934720 cut-off, so table totals in the millions stay converged);
+// the two data-dependent forms of the log tail are both evaluated and selected, which costs a few flops but keeps
+// the warp converged.  Arguments within 2^-20 of a power of two (e.g. 63 + 1) take the
 // generic routine.
 __device__ __constant__ double kHot[20] = {
     6.93147180369123816490e-01, 1.90821492927058770002e-10,                                   // 0 ln2_hi, 1 ln2_lo
@@ -187,7 +188,7 @@ __device__ __constant__ double kHot[20] = {
     0.918938533204672741780329736406, 0.0, 0.0, 0.0, 0.0, 0.0};
 
 __device__ __forceinline__ double dlgamma_hot(double x) {
-    if (!(x > 10.0 && x <= 4934720.0)) return dlgamma_generic(x);
+    if (!(x > 10.0 && x <= 1e17)) return dlgamma_generic(x);
     int hx = __double2hiint(x);
     const int lx = __double2loint(x);
     int k = (hx >> 20) - 1023;
@@ -219,7 +220,8 @@ __device__ __forceinline__ double dlgamma_hot(double x) {
     b2 = b1; b1 = b0; b0 = tx * b1 - b2 + kHot[12];
     b2 = b1; b1 = b0; b0 = tx * b1 - b2 + kHot[13];
     const double cor = ((b0 - b2) * 0.5) / x;
-    return kHot[14] + (x - 0.5) * lg - x + cor;
+    const double base = kHot[14] + (x - 0.5) * lg - x;
+    return (x > 4934720.0) ? base : base + cor;  // above the cut-off lgammafn drops the correction term
 }
 
 __device__ __forceinline__ double dlgamma(double x) {

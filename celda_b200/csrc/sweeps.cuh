@@ -101,9 +101,12 @@ __device__ __forceinline__ double warp_ordered_sum_pos(const double* r, int n, i
 // hs may alias pl; perm: n ints.  n <= 1024.
 // Returns the 0-based label, or <0: -1 Walker-alias branch (>200 likely categories), -2 non-finite
 // probability, -3 no positive probability.  Warp-cooperative; all lanes return the same value.
-__device__ int warp_sample_ll(double* pl, int n, double u, double* r, int* perm, int lane) {
+// mx_out / nz_out describe the vector the draw was made from: the maximum log-probability and the (up to four)
+// entries whose exp(pl - max) is positive, x = -2 when there are more (see draw_unchanged).
+__device__ int warp_sample_ll(double* pl, int n, double u, double* r, int* perm, int lane, double& mx_out, int4& nz_out) {
     double* hs = pl;
     const unsigned FULL = 0xffffffffu;
+    nz_out = make_int4(-2, -1, -1, -1);
     double mx = -__longlong_as_double(0x7ff0000000000000LL);
     for (int i = lane; i < n; i += 32) mx = fmax(mx, pl[i]);
     for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
@@ -114,7 +117,24 @@ __device__ int warp_sample_ll(double* pl, int n, double u, double* r, int* perm,
         bad |= !(e >= 0.0) || (e > 1.7976931348623157e308);
     }
     __syncwarp();
+    mx_out = mx;
     if (__any_sync(FULL, bad)) return -2;
+    {
+        int np = 0, i0 = -1, i1 = -1, i2 = -1, i3 = -1;
+        for (int base = 0; base < n && np <= 4; base += 32) {
+            unsigned m = __ballot_sync(FULL, base + lane < n && r[base + lane] > 0.0);
+            np += __popc(m);
+            if (np > 4) break;
+            for (int q = np - __popc(m); m; m &= m - 1, ++q) {
+                const int b = base + __ffs(m) - 1;
+                i0 = (q == 0) ? b : i0;
+                i1 = (q == 1) ? b : i1;
+                i2 = (q == 2) ? b : i2;
+                i3 = (q == 3) ? b : i3;
+            }
+        }
+        if (np <= 4) nz_out = make_int4(i0, i1, i2, i3);
+    }
     const double s1 = warp_ordered_sum_pos(r, n, lane);
     for (int i = lane; i < n; i += 32) r[i] = r[i] / s1;
     __syncwarp();
@@ -248,13 +268,14 @@ __device__ int warp_sample_ll(double* pl, int n, double u, double* r, int* perm,
     return result;
 }
 
-// Block-wide: smallest index c in [0, nwin) with spec[c] >= 0, or -1.  Result valid on all threads.
-__device__ int block_first_mover(const int* spec, int nwin, int* s_first) {
+// Block-wide: smallest c in [0, nwin) whose ring slot spec[ring_slot(pos + c)] holds a mover, or -1.  Result valid on
+// all threads.
+__device__ int block_first_mover(const int* spec, long long pos, int Wmax, int nwin, int* s_first) {
     if (threadIdx.x == 0) *s_first = 0x7fffffff;
     __syncthreads();
     int best = 0x7fffffff;
     for (int c = threadIdx.x; c < nwin; c += blockDim.x) {
-        if (__ldcg(spec + c) >= 0) {
+        if (__ldcg(spec + ((pos + c) & (long long)(Wmax - 1))) >= 0) {
             best = c;
             break;  // ascending per thread
         }
@@ -267,10 +288,15 @@ __device__ int block_first_mover(const int* spec, int nwin, int* s_first) {
     return f == 0x7fffffff ? -1 : f;
 }
 
+// Ring slot of item position t; the ring capacity is a power of two (SweepBufs).
+__device__ __forceinline__ size_t ring_slot(long long t, int Wmax) { return (size_t)(t & (long long)(Wmax - 1)); }
+
 struct SweepWork {
     double* bufP;       // [Wmax * ncand] per-(item, candidate) partial results
     double* bufA;       // [Wmax * ncand] second per-candidate scalar (z sweep only)
-    int* spec;          // [Wmax] packed (old << 16 | new) for movers, -1 otherwise
+    int* spec;          // [Wmax] ring: packed (old << 16 | new) for movers, -1 otherwise
+    double* drawMx;     // [Wmax] ring: max log-probability of the item's last draw
+    int* drawNz;        // [Wmax][4] ring: its positive entries (see warp_sample_ll)
     double* colsum;     // [K]  (z sweep)
     double* lgnCP;      // [K]  (z sweep)
     unsigned* barrier;  // zeroed before launch
@@ -282,6 +308,26 @@ struct SweepWork {
     int Wmin;
     int lgT;            // entries of the shared-memory lgamma(k + beta) table
 };
+
+// A carried item after the commit (da, db): its draw is a function of e = exp(pl - max) and u alone, and only the
+// entries da and db of pl changed.  If both had e == 0 at the item's last draw (neither is among its recorded positive
+// entries) and both still have, the vector e is bit-identical and so is the outcome: the recorded draw stands.
+// The test is tried only while movers are sparse (gap estimate gavg >= 32): in a churning sweep nearly every item has
+// many positive entries and the failed test would only add latency to the round.
+// Two steps so that an item that fails the list test costs one 16-byte load: draw_recorded_zero() -- neither da nor
+// db was a positive entry at the last draw (mx = that draw's maximum); then the caller evaluates the two new
+// log-probabilities and asks draw_still_zero().
+__device__ __forceinline__ bool draw_recorded_zero(const SweepWork& w, size_t slot, int da, int db, double& mx) {
+    const int4 nz = __ldcg(reinterpret_cast<const int4*>(w.drawNz) + slot);
+    if (nz.x == -2) return false;
+    if (nz.x == da || nz.y == da || nz.z == da || nz.w == da) return false;
+    if (nz.x == db || nz.y == db || nz.z == db || nz.w == db) return false;
+    mx = __ldcg(w.drawMx + slot);
+    return true;
+}
+__device__ __forceinline__ bool draw_still_zero(double mx, double pa, double pb) {
+    return dexp(pa - mx) == 0.0 && dexp(pb - mx) == 0.0;
+}
 
 // ------------------------------------------------------------------------------------------------ z sweep
 // .cCCalcGibbsProbZ (R/celda_C.R:620-714) on a dense R x nM int32 count matrix (nTSByC in celda_CG).
@@ -369,7 +415,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
         // ---- commit the first mover of the previous window (every CTA updates its own copy of the tables)
         if (have_spec) {
             const int nwin = (int)(prev_end - pos);
-            const int first = block_first_mover(a.w.spec, nwin, s_misc);
+            const int first = block_first_mover(a.w.spec, pos, a.w.Wmax, nwin, s_misc);
             if (first < 0) {
                 pos = prev_end;
                 hi = pos;
@@ -379,7 +425,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
             } else {
                 const long long t = pos + first;
                 const long long i = a.ix[t] - 1;
-                const int packed = __ldcg(a.w.spec + first);
+                const int packed = __ldcg(a.w.spec + ring_slot(pos + first, a.w.Wmax));
                 da = packed >> 16;
                 db = packed & 0xffff;
                 const int* x = a.counts + i * R;
@@ -411,7 +457,10 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
         }
         if (pos >= a.nM) break;
         CELDA_TICK(ck_commit);
-        const long long end = max(hi, min(pos + (long long)W, a.nM));
+        // after a commit the window is topped up with fresh items only once it is less than half full: carried items
+        // cost two patch units and a check (draw_unchanged), fresh ones a full evaluation and draw, cheaper in batches
+        const bool topup = nd != 2 || (hi - pos) * 2 < W;
+        const long long end = topup ? max(hi, min(pos + (long long)W, a.nM)) : hi;
         const int nwin = (int)(end - pos);
         const long long nPatch = (hi - pos) * (nd == K ? 0 : nd);  // nd == K only on the first round (hi == pos)
         const long long nFresh = (end - hi) * K;
@@ -459,7 +508,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                     double S = 0.0;
 #pragma unroll 8
                     for (int r = 0; r < R; ++r) S += scr[r];  // loads run ahead of the serial adds
-                    const size_t o = (size_t)(t % a.w.Wmax) * K + j;
+                    const size_t o = ring_slot(t, a.w.Wmax) * K + j;
                     a.w.bufP[o] = S;
                     a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
                 }
@@ -501,7 +550,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                         const long long i = a.ix[t] - 1;
                         if (a.z[i] - 1 == j) continue;  // the cell's own population: step (3)
                         const int* x = a.xT + t;  // lanes hold consecutive t: one coalesced load per row
-                        const size_t o = (size_t)(t % a.w.Wmax) * K + j;
+                        const size_t o = ring_slot(t, a.w.Wmax) * K + j;
                         double S = (gI == 0) ? 0.0 : a.w.bufP[o];
                         int r = r0;
                         const int* xp = x + (size_t)r0 * a.nM;  // walks down the rows: + nM per row
@@ -559,7 +608,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                     double S = 0.0;
 #pragma unroll 2
                     for (int r = 0; r < R; ++r) S += lg_tab(lgtab, T, (long long)ncol[r] + sgn * __ldg(x + r), a.beta);
-                    const size_t o = (size_t)(t % a.w.Wmax) * K + j;
+                    const size_t o = ring_slot(t, a.w.Wmax) * K + j;
                     a.w.bufP[o] = S;
                     a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
                 }
@@ -584,8 +633,8 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
             const long long t = pos + c;
             const long long i = a.ix[t] - 1;
             const int zi = a.z[i] - 1, si = a.s[i] - 1;
-            const size_t o = (size_t)(t % a.w.Wmax) * K;
-            for (int j = lane; j < K; j += 32) {
+            const size_t slot = ring_slot(t, a.w.Wmax), o = slot * K;
+            auto combine = [&](int j) {
                 const double S = __ldcg(a.w.bufP + o + j), A = __ldcg(a.w.bufA + o + j);
                 const double cs = __ldcg(a.w.colsum + j), lc = __ldcg(a.w.lgnCP + j);
                 double p = dlog((double)(m_s[si * K + j] - (j == zi)) + a.alpha);
@@ -600,19 +649,40 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                     p = p - S;
                     p = p + A;
                 }
+                return p;
+            };
+            double mxOld;
+            if (a.doSample && nd == 2 && t < hi && gavg >= 32 && draw_recorded_zero(a.w, slot, da, db, mxOld)) {
+                const double pa = combine(da), pb = combine(db);
+                if (draw_still_zero(mxOld, pa, pb)) {  // carried over the commit (da, db) with an unchanged draw
+                    if (a.probs && lane == 0) {
+                        a.probs[i * K + da] = pa;
+                        a.probs[i * K + db] = pb;
+                    }
+                    continue;
+                }
+            }
+            for (int j = lane; j < K; j += 32) {
+                const double p = combine(j);
                 pl[j] = p;
                 if (a.probs) a.probs[i * K + j] = p;
             }
             __syncwarp();
             int znew = zi;
             if (a.doSample) {
-                znew = warp_sample_ll(pl, K, a.u[t], rr, perm, lane);
+                double mx;
+                int4 nz;
+                znew = warp_sample_ll(pl, K, a.u[t], rr, perm, lane, mx, nz);
                 if (znew < 0) {
                     if (lane == 0) atomicCAS(a.w.status, 0, znew);
                     znew = zi;
                 }
+                if (lane == 0) {
+                    a.w.drawMx[slot] = mx;
+                    reinterpret_cast<int4*>(a.w.drawNz)[slot] = nz;
+                }
             }
-            if (lane == 0) a.w.spec[c] = (znew != zi) ? ((zi << 16) | znew) : -1;
+            if (lane == 0) a.w.spec[slot] = (znew != zi) ? ((zi << 16) | znew) : -1;
             __syncwarp();
         }
         prev_end = end;
@@ -785,7 +855,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
     while (true) {
         if (have_spec) {
             const int nwin = (int)(prev_end - pos);
-            const int first = block_first_mover(a.w.spec, nwin, s_misc);
+            const int first = block_first_mover(a.w.spec, pos, a.w.Wmax, nwin, s_misc);
             if (first < 0) {
                 pos = prev_end;
                 hi = pos;
@@ -795,7 +865,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
             } else {
                 const long long t = pos + first;
                 const int i = a.ix[t] - 1;
-                const int packed = __ldcg(a.w.spec + first);
+                const int packed = __ldcg(a.w.spec + ring_slot(pos + first, a.w.Wmax));
                 da = packed >> 16;
                 db = packed & 0xffff;
                 const int* x = a.counts + (size_t)i * C;
@@ -830,7 +900,10 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
         }
         if (pos >= a.nG) break;
         CELDA_TICK(ck_commit);
-        const long long end = max(hi, min(pos + (long long)W, (long long)a.nG));
+        // after a commit the window is topped up with fresh items only once it is less than half full: carried items
+        // cost two patch units and a check (draw_unchanged), fresh ones a full evaluation and draw, cheaper in batches
+        const bool topup = nd != 2 || (hi - pos) * 2 < W;
+        const long long end = topup ? max(hi, min(pos + (long long)W, (long long)a.nG)) : hi;
         const int nwin = (int)(end - pos);
         const long long nPatch = (hi - pos) * nd;
         const long long nFresh = (end - hi) * L;
@@ -886,7 +959,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                     p += isCur ? dlgamma_hot(Tl - Ni + (double)g1 * a.delta) : tl[6];
                     p -= isCur ? tl[6] : dlgamma_hot(Tl + Ni + (double)g0 * a.delta);
                 }
-                a.w.bufP[(size_t)(t % a.w.Wmax) * L + l] = p;
+                a.w.bufP[ring_slot(t, a.w.Wmax) * L + l] = p;
             }
         } else {
             for (long long uidx = gwarpT; uidx < total; uidx += tw) {
@@ -954,7 +1027,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                     p -= scr[2 * C + 3];
                     p += scr[2 * C + 4];
                     p -= scr[2 * C + 5];
-                    a.w.bufP[(size_t)(t % a.w.Wmax) * L + l] = p;
+                    a.w.bufP[ring_slot(t, a.w.Wmax) * L + l] = p;
                 }
                 __syncwarp();
             }
@@ -970,7 +1043,18 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
             const long long t = pos + c;
             const int i = a.ix[t] - 1;
             const int cur = a.y[i] - 1;
-            const size_t o = (size_t)(t % a.w.Wmax) * L;
+            const size_t slot = ring_slot(t, a.w.Wmax), o = slot * L;
+            double mxOld;
+            if (a.doSample && nd == 2 && t < hi && gavg >= 32 && draw_recorded_zero(a.w, slot, da, db, mxOld)) {
+                const double pa = __ldcg(a.w.bufP + o + da), pb = __ldcg(a.w.bufP + o + db);
+                if (draw_still_zero(mxOld, pa, pb)) {  // carried over the commit (da, db) with an unchanged draw
+                    if (a.probs && lane == 0) {
+                        a.probs[(size_t)i * L + da] = pa;
+                        a.probs[(size_t)i * L + db] = pb;
+                    }
+                    continue;
+                }
+            }
             for (int l = lane; l < L; l += 32) {
                 const double p = __ldcg(a.w.bufP + o + l);
                 pl[l] = p;
@@ -979,13 +1063,19 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
             __syncwarp();
             int ynew = cur;
             if (a.doSample) {
-                ynew = warp_sample_ll(pl, L, a.u[t], rr, perm, lane);
+                double mx;
+                int4 nz;
+                ynew = warp_sample_ll(pl, L, a.u[t], rr, perm, lane, mx, nz);
                 if (ynew < 0) {
                     if (lane == 0) atomicCAS(a.w.status, 0, ynew);
                     ynew = cur;
                 }
+                if (lane == 0) {
+                    a.w.drawMx[slot] = mx;
+                    reinterpret_cast<int4*>(a.w.drawNz)[slot] = nz;
+                }
             }
-            if (lane == 0) a.w.spec[c] = (ynew != cur) ? ((cur << 16) | ynew) : -1;
+            if (lane == 0) a.w.spec[slot] = (ynew != cur) ? ((cur << 16) | ynew) : -1;
             __syncwarp();
         }
         prev_end = end;
@@ -1087,7 +1177,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
         bool committed = false;
         if (have_spec) {
             const int nwin = (int)(prev_end - pos);
-            const int first = block_first_mover(a.w.spec, nwin, s_misc);
+            const int first = block_first_mover(a.w.spec, pos, a.w.Wmax, nwin, s_misc);
             if (first < 0) {
                 pos = prev_end;
                 hi = pos;
@@ -1097,7 +1187,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
             } else {
                 const long long tt = pos + first;
                 const int i = a.ix[tt] - 1;
-                const int packed = __ldcg(a.w.spec + first);
+                const int packed = __ldcg(a.w.spec + ring_slot(pos + first, a.w.Wmax));
                 da = packed >> 16;
                 db = packed & 0xffff;
                 // the two table rows change only where the gene has counts: the grid shares the gene's entries
@@ -1133,7 +1223,10 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
         if (pos >= a.nG) break;
         if (committed) grid_sync(a.w.barrier, bar_target);  // table rows a, b are visible before they are read
         CELDA_TICK(ck_commit);
-        const long long end = max(hi, min(pos + (long long)W, (long long)a.nG));
+        // after a commit the window is topped up with fresh items only once it is less than half full: carried items
+        // cost two patch units and a check (draw_unchanged), fresh ones a full evaluation and draw, cheaper in batches
+        const bool topup = nd != 2 || (hi - pos) * 2 < W;
+        const long long end = topup ? max(hi, min(pos + (long long)W, (long long)a.nG)) : hi;
         const int nwin = (int)(end - pos);
         // ---- tasks: patch = (32 carried genes) x {da, db}; fresh = (32 new genes) x (32-module chunk)
         const long long nPatchGrp = (nd == 2) ? (hi - pos + nwarp - 1) / nwarp : 0;
@@ -1222,7 +1315,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
                 p -= dlgamma_hot((double)g1 * a.delta);
                 p += dlgamma_hot(isCur ? Tl - Ni + (double)g1 * a.delta : Tl + (double)g1 * a.delta);
                 p -= dlgamma_hot(isCur ? Tl + (double)g0 * a.delta : Tl + Ni + (double)g0 * a.delta);
-                a.w.bufP[(size_t)(tgene % a.w.Wmax) * L + l] = p;
+                a.w.bufP[ring_slot(tgene, a.w.Wmax) * L + l] = p;
             }
         }
         units_done += ntask;
@@ -1236,7 +1329,18 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
             const long long tt = pos + c;
             const int i = a.ix[tt] - 1;
             const int cur = a.y[i] - 1;
-            const size_t o = (size_t)(tt % a.w.Wmax) * L;
+            const size_t slot = ring_slot(tt, a.w.Wmax), o = slot * L;
+            double mxOld;
+            if (a.doSample && nd == 2 && tt < hi && gavg >= 32 && draw_recorded_zero(a.w, slot, da, db, mxOld)) {
+                const double pa = __ldcg(a.w.bufP + o + da), pb = __ldcg(a.w.bufP + o + db);
+                if (draw_still_zero(mxOld, pa, pb)) {  // carried over the commit (da, db) with an unchanged draw
+                    if (a.probs && lane == 0) {
+                        a.probs[(size_t)i * L + da] = pa;
+                        a.probs[(size_t)i * L + db] = pb;
+                    }
+                    continue;
+                }
+            }
             for (int l = lane; l < L; l += 32) {
                 const double p = __ldcg(a.w.bufP + o + l);
                 pl[l] = p;
@@ -1245,13 +1349,19 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
             __syncwarp();
             int ynew = cur;
             if (a.doSample) {
-                ynew = warp_sample_ll(pl, L, a.u[tt], rr, perm, lane);
+                double mx;
+                int4 nz;
+                ynew = warp_sample_ll(pl, L, a.u[tt], rr, perm, lane, mx, nz);
                 if (ynew < 0) {
                     if (lane == 0) atomicCAS(a.w.status, 0, ynew);
                     ynew = cur;
                 }
+                if (lane == 0) {
+                    a.w.drawMx[slot] = mx;
+                    reinterpret_cast<int4*>(a.w.drawNz)[slot] = nz;
+                }
             }
-            if (lane == 0) a.w.spec[c] = (ynew != cur) ? ((cur << 16) | ynew) : -1;
+            if (lane == 0) a.w.spec[slot] = (ynew != cur) ? ((cur << 16) | ynew) : -1;
             __syncwarp();
         }
         prev_end = end;
@@ -1354,7 +1464,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_zc(ZCArgs a) {
         bool committed = false;
         if (have_spec) {
             const int nwin = (int)(prev_end - pos);
-            const int first = block_first_mover(a.w.spec, nwin, s_misc);
+            const int first = block_first_mover(a.w.spec, pos, a.w.Wmax, nwin, s_misc);
             if (first < 0) {
                 pos = prev_end;
                 hi = pos;
@@ -1364,7 +1474,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_zc(ZCArgs a) {
             } else {
                 const long long tt = pos + first;
                 const long long i = a.ix[tt] - 1;
-                const int packed = __ldcg(a.w.spec + first);
+                const int packed = __ldcg(a.w.spec + ring_slot(pos + first, a.w.Wmax));
                 da = packed >> 16;
                 db = packed & 0xffff;
                 // the two table columns change only where the cell has counts: the grid shares the cell's entries
@@ -1398,7 +1508,10 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_zc(ZCArgs a) {
         }
         if (pos >= a.nM) break;
         if (committed || rounds == 0) grid_sync(a.w.barrier, bar_target);  // table columns visible before they are read
-        const long long end = max(hi, min(pos + (long long)W, a.nM));
+        // after a commit the window is topped up with fresh items only once it is less than half full: carried items
+        // cost two patch units and a check (draw_unchanged), fresh ones a full evaluation and draw, cheaper in batches
+        const bool topup = nd != 2 || (hi - pos) * 2 < W;
+        const long long end = topup ? max(hi, min(pos + (long long)W, a.nM)) : hi;
         const int nwin = (int)(end - pos);
         // ---- tasks: cached column sums of the changed columns (one warp, lane = column); patch = (nwarp carried
         // cells) x {da, db}; fresh = (nwarp new cells) x (32-population chunk)
@@ -1484,7 +1597,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_zc(ZCArgs a) {
                 }
             }
             if (active) {
-                const size_t o = (size_t)(tcell % a.w.Wmax) * K + j;
+                const size_t o = ring_slot(tcell, a.w.Wmax) * K + j;
                 a.w.bufP[o] = S;
                 a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
             }
@@ -1499,8 +1612,8 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_zc(ZCArgs a) {
             const long long tt = pos + c;
             const long long i = a.ix[tt] - 1;
             const int zi = a.z[i] - 1, si = a.s[i] - 1;
-            const size_t o = (size_t)(tt % a.w.Wmax) * K;
-            for (int j = lane; j < K; j += 32) {
+            const size_t slot = ring_slot(tt, a.w.Wmax), o = slot * K;
+            auto combine = [&](int j) {
                 const double S = __ldcg(a.w.bufP + o + j), A = __ldcg(a.w.bufA + o + j);
                 const double cs = __ldcg(a.w.colsum + j), lc = __ldcg(a.w.lgnCP + j);
                 double p = dlog((double)(m_s[si * K + j] - (j == zi)) + a.alpha);
@@ -1515,19 +1628,40 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_zc(ZCArgs a) {
                     p = p - S;
                     p = p + A;
                 }
+                return p;
+            };
+            double mxOld;
+            if (a.doSample && nd == 2 && tt < hi && gavg >= 32 && draw_recorded_zero(a.w, slot, da, db, mxOld)) {
+                const double pa = combine(da), pb = combine(db);
+                if (draw_still_zero(mxOld, pa, pb)) {  // carried over the commit (da, db) with an unchanged draw
+                    if (a.probs && lane == 0) {
+                        a.probs[i * K + da] = pa;
+                        a.probs[i * K + db] = pb;
+                    }
+                    continue;
+                }
+            }
+            for (int j = lane; j < K; j += 32) {
+                const double p = combine(j);
                 pl[j] = p;
                 if (a.probs) a.probs[i * K + j] = p;
             }
             __syncwarp();
             int znew = zi;
             if (a.doSample) {
-                znew = warp_sample_ll(pl, K, a.u[tt], rr2, perm, lane);
+                double mx;
+                int4 nz;
+                znew = warp_sample_ll(pl, K, a.u[tt], rr2, perm, lane, mx, nz);
                 if (znew < 0) {
                     if (lane == 0) atomicCAS(a.w.status, 0, znew);
                     znew = zi;
                 }
+                if (lane == 0) {
+                    a.w.drawMx[slot] = mx;
+                    reinterpret_cast<int4*>(a.w.drawNz)[slot] = nz;
+                }
             }
-            if (lane == 0) a.w.spec[c] = (znew != zi) ? ((zi << 16) | znew) : -1;
+            if (lane == 0) a.w.spec[slot] = (znew != zi) ? ((zi << 16) | znew) : -1;
             __syncwarp();
         }
         prev_end = end;
