@@ -317,7 +317,7 @@ int run_loglik(const LLIn& in, double* partial /* >= 1024 */, double* out, cudaS
         a.npPhiD = NBG;
         count_launch(2);
     }
-    k_loglik_final<<<1, 256, 0, st>>>(a);
+    k_loglik_final<<<1, 1024, 0, st>>>(a);
     count_launch();
     CELDA_CUDA_OK(cudaGetLastError());
     return 0;
@@ -376,8 +376,11 @@ int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
             }
             if (b.ztXT.n < (size_t)a.R * a.nM) CELDA_TRY(b.ztXT.alloc((size_t)a.R * a.nM));
             CELDA_TRY(b.ztHist.zero(st));
-            k_permute_transpose<<<(int)std::min<long long>((a.nM + 31) / 32, (long long)sms * 8), 256, 0, st>>>(
-                a.counts, a.R, a.nM, a.ix, b.ztXT.p, b.ztHist.p);
+            const int RC = std::min(a.R, 1024);
+            const size_t ptSmem = sizeof(int) * ((size_t)32 * (RC | 1) + RC);
+            CELDA_CUDA_OK(cudaFuncSetAttribute(k_permute_transpose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ptSmem));
+            k_permute_transpose<<<(int)std::min<long long>((a.nM + 31) / 32, (long long)sms * 8), 256, ptSmem, st>>>(
+                a.counts, a.R, RC, a.nM, a.ix, b.ztXT.p, b.ztHist.p);
             k_pick_rowV<<<1, 256, 0, st>>>(b.ztHist.p, a.R, a.EsCap, b.ztOffg.p, b.ztGrp.p, b.ztTmp.p);
             count_launch(2);
             a.offg = b.ztOffg.p;

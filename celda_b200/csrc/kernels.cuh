@@ -315,94 +315,119 @@ struct LLArgs {
 };
 
 // Final assembly in the reference's order: a + b + c + d per component, then theta + phi + psi + eta
-// (R/celda_CG.R:854-887, R/celda_C.R:771-787, R/celda_G.R:677-701).  One block.
+// (R/celda_CG.R:854-887, R/celda_C.R:771-787, R/celda_G.R:677-701).  One block; every thread first accumulates its
+// share of all seven table sums, then ONE block reduction combines them (a chain of seven would cost seven
+// barrier round trips on a kernel that is pure latency).
 __global__ void k_loglik_final(LLArgs a) {
-    __shared__ double red[32];
-    __shared__ double comp[4];
+    __shared__ double red[7][32];
     const int K = a.K, L = a.L, nS = a.nS;
     const double* part = a.partial;
-    // ---- theta (CG, C)
-    if (a.model != 2) {
-        double acc = 0.0;
-        for (int q = threadIdx.x; q < K * nS; q += blockDim.x) acc += dlgamma((double)a.mCPByS[q] + a.alpha);
-        const double b = block_sum(acc, red);
-        acc = 0.0;
-        for (int s = threadIdx.x; s < nS; s += blockDim.x) {
+    const int tid = threadIdx.x, nt = blockDim.x, rev = nt - 1 - tid;  // column sums start from the last thread
+    double acc[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (a.model != 2) {  // theta (CG, C)
+        for (int q = tid; q < K * nS; q += nt) acc[0] += dlgamma((double)a.mCPByS[q] + a.alpha);
+        for (int s = rev; s < nS; s += nt) {
             double cs = 0.0;
             for (int k = 0; k < K; ++k) cs += (double)a.mCPByS[(size_t)s * K + k] + a.alpha;
-            acc += dlgamma(cs);
-        }
-        const double d = block_sum(acc, red);
-        if (threadIdx.x == 0) {
-            const double aa = (double)nS * dlgamma((double)K * a.alpha);
-            const double c = (double)(-nS * K) * dlgamma(a.alpha);
-            comp[0] = aa + b + c + -d;
+            acc[1] += dlgamma(cs);
         }
     }
-    // ---- phi
+    if (a.model == 0) {  // phi over nTSByCP (L x K)
+        for (int q = tid; q < L * K; q += nt) acc[2] += dlgamma((double)a.phiTab[q] + a.beta);
+        for (int k = rev; k < K; k += nt) {
+            double cs = 0.0;
+#pragma unroll 8
+            for (int l = 0; l < L; ++l) cs += (double)a.phiTab[(size_t)k * L + l] + a.beta;
+            acc[3] += dlgamma(cs);
+        }
+    }
+    if (a.model != 1) {  // psi, eta (CG, G)
+        for (int l = tid; l < L; l += nt) {
+            const double g = (double)a.nGByTS[l];
+            acc[4] += dlgamma(g * a.delta);
+            acc[5] += dlgamma((double)a.nByTS[l] + (g * a.delta));
+            acc[6] += dlgamma(g + a.gamma);
+        }
+    }
+    const int warp = tid >> 5, lane = tid & 31, nw = nt >> 5;
+    // what thread 0 needs afterwards, fetched / evaluated in parallel: the per-block partials, the module sizes and
+    // the seven scalar lgamma terms (lane 0 of warps 1..7; dlgamma() is a few hundred dependent instructions)
+    __shared__ double sp[640];
+    __shared__ int sG[1024];
+    __shared__ double sc[8];
+    const int np = min(640, a.npG + a.npPhiB + a.npPhiD);
+    for (int q = tid; q < np; q += nt) sp[q] = part[q];
+    const bool gS = a.model != 1 && L <= 1024;
+    if (gS)
+        for (int l = tid; l < L; l += nt) sG[l] = a.nGByTS[l];
+    if (lane == 0 && warp >= 1 && warp <= 7) {
+        const int Rr = (a.model == 0) ? L : ((a.model == 1) ? a.nG : L);
+        double x;
+        switch (warp) {
+            case 1: x = (double)K * a.alpha; break;
+            case 2: x = a.alpha; break;
+            case 3: x = (double)Rr * a.beta; break;
+            case 4: x = a.beta; break;
+            case 5: x = a.delta; break;
+            case 6: x = (double)L * a.gamma; break;
+            default: x = a.gamma; break;
+        }
+        sc[warp] = dlgamma(x);
+    }
+#pragma unroll
+    for (int c = 0; c < 7; ++c) {
+        double v = acc[c];
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[c][warp] = v;
+    }
+    __syncthreads();
+    if (tid < 7) {
+        double sres = 0.0;
+        for (int w = 0; w < nw; ++w) sres += red[tid][w];
+        red[tid][0] = sres;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    double comp[4] = {0.0, 0.0, 0.0, 0.0};
+    if (a.model != 2) {
+        const double aa = (double)nS * sc[1];
+        const double c = (double)(-nS * K) * sc[2];
+        comp[0] = aa + red[0][0] + c + -red[1][0];
+    }
     {
-        double b = 0.0, d = 0.0;
-        int R;
-        long long ncols;
-        if (a.model == 0) {
-            R = L;
-            ncols = K;
-            double acc = 0.0;
-            for (int q = threadIdx.x; q < L * K; q += blockDim.x) acc += dlgamma((double)a.phiTab[q] + a.beta);
-            b = block_sum(acc, red);
-            acc = 0.0;
-            for (int k = threadIdx.x; k < K; k += blockDim.x) {
-                double cs = 0.0;
-                for (int l = 0; l < L; ++l) cs += (double)a.phiTab[(size_t)k * L + l] + a.beta;
-                acc += dlgamma(cs);
-            }
-            d = block_sum(acc, red);
-        } else {
+        double b = red[2][0], d = red[3][0];
+        int R = L;
+        long long ncols = K;
+        if (a.model != 0) {
             R = (a.model == 1) ? a.nG : L;
             ncols = (a.model == 1) ? K : a.nM;
-            if (threadIdx.x == 0) {
-                for (int q = 0; q < a.npPhiB; ++q) b += part[a.npG + q];
-                for (int q = 0; q < a.npPhiD; ++q) d += part[a.npG + a.npPhiB + q];
-            }
+            b = 0.0;
+            d = 0.0;
+            for (int q = 0; q < a.npPhiB; ++q) b += sp[a.npG + q];
+            for (int q = 0; q < a.npPhiD; ++q) d += sp[a.npG + a.npPhiB + q];
         }
-        if (threadIdx.x == 0) {
-            const double aa = (double)ncols * dlgamma((double)R * a.beta);
-            const double c = -(double)ncols * (double)R * dlgamma(a.beta);
-            comp[1] = aa + b + c + -d;
-        }
+        const double aa = (double)ncols * sc[3];
+        const double c = -(double)ncols * (double)R * sc[4];
+        comp[1] = aa + b + c + -d;
     }
-    // ---- psi, eta (CG, G)
     if (a.model != 1) {
-        double acc = 0.0, acc2 = 0.0, acc3 = 0.0;
-        for (int l = threadIdx.x; l < L; l += blockDim.x) {
-            const double g = (double)a.nGByTS[l];
-            acc += dlgamma(g * a.delta);
-            acc2 += dlgamma((double)a.nByTS[l] + (g * a.delta));
-            acc3 += dlgamma(g + a.gamma);
+        double pb = 0.0;
+        for (int q = 0; q < a.npG; ++q) pb += sp[q];
+        double nGs = 0.0, es = 0.0;
+        for (int l = 0; l < L; ++l) {
+            const double g = (double)(gS ? sG[l] : a.nGByTS[l]);
+            nGs += g;
+            es += g + a.gamma;
         }
-        const double pa = block_sum(acc, red);
-        const double pd = block_sum(acc2, red);
-        const double eb = block_sum(acc3, red);
-        if (threadIdx.x == 0) {
-            double pb = 0.0;
-            for (int q = 0; q < a.npG; ++q) pb += part[q];
-            double nGs = 0.0, es = 0.0;
-            for (int l = 0; l < L; ++l) {
-                nGs += (double)a.nGByTS[l];
-                es += (double)a.nGByTS[l] + a.gamma;
-            }
-            const double pc = -nGs * dlgamma(a.delta);
-            comp[2] = pa + pb + pc + -pd;
-            const double ea = dlgamma((double)L * a.gamma);
-            const double ec = (double)(-L) * dlgamma(a.gamma);
-            comp[3] = ea + eb + ec + -dlgamma(es);
-        }
+        const double pc = -nGs * sc[5];
+        comp[2] = red[4][0] + pb + pc + -red[5][0];
+        const double ea = sc[6];
+        const double ec = (double)(-L) * sc[7];
+        comp[3] = ea + red[6][0] + ec + -dlgamma(es);
     }
-    if (threadIdx.x == 0) {
-        if (a.model == 0) *a.out = comp[0] + comp[1] + comp[2] + comp[3];
-        else if (a.model == 1) *a.out = comp[0] + comp[1];
-        else *a.out = comp[1] + comp[2] + comp[3];
-    }
+    if (a.model == 0) *a.out = comp[0] + comp[1] + comp[2] + comp[3];
+    else if (a.model == 1) *a.out = comp[0] + comp[1];
+    else *a.out = comp[1] + comp[2] + comp[3];
 }
 
 }  // namespace celda

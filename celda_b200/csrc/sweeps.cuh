@@ -716,26 +716,43 @@ inline size_t z_sweep_smem(int R, int K, int nS, int T, int nwarp, int EsCap = 0
 }
 
 // xT[r][t] = counts[r, ix[t] - 1]: the count matrix in visiting order, transposed, so that lanes holding
-// consecutive visiting positions read one row coalesced.  32 cells per block, tile transposed through shared memory.
-__global__ void k_permute_transpose(const int* __restrict__ counts, int R, long long nM, const int* __restrict__ ix,
+// consecutive visiting positions read one row coalesced.  A block moves 32 cells x RC rows per step through shared
+// memory: each warp has a cell's whole column slice in flight (RC / 32 independent 128-byte loads), the rows go out
+// as 128-byte stores, and the per-row maxima are kept per block and merged with one atomic per row at the end.
+__global__ void k_permute_transpose(const int* __restrict__ counts, int R, int RC, long long nM, const int* __restrict__ ix,
                                     int* __restrict__ xT, int* __restrict__ rowMax /* [R], zeroed */) {
-    __shared__ int tile[32][33];
+    extern __shared__ int pt_smem[];
+    const int RCp = RC | 1;
+    int* tile = pt_smem;             // [32][RCp]
+    int* bmax = pt_smem + 32 * RCp;  // [RC]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (long long t0 = (long long)blockIdx.x * 32; t0 < nM; t0 += (long long)gridDim.x * 32) {
-        for (int r0 = 0; r0 < R; r0 += 32) {
-            for (int c = w; c < 32; c += nw) {  // warp c reads rows r0.. of cell t0 + c (coalesced)
+    for (int rb = 0; rb < R; rb += RC) {
+        const int rc = min(RC, R - rb);
+        __syncthreads();
+        for (int r = threadIdx.x; r < rc; r += blockDim.x) bmax[r] = 0;
+        for (long long t0 = (long long)blockIdx.x * 32; t0 < nM; t0 += (long long)gridDim.x * 32) {
+            __syncthreads();
+            for (int c = w; c < 32; c += nw) {
                 const long long t = t0 + c;
-                tile[c][lane] = (t < nM && r0 + lane < R) ? counts[(size_t)(ix[t] - 1) * R + r0 + lane] : 0;
+                if (t < nM) {
+                    const int* src = counts + (size_t)(ix[t] - 1) * R + rb;
+#pragma unroll 4
+                    for (int r = lane; r < rc; r += 32) tile[c * RCp + r] = __ldg(src + r);
+                } else {
+                    for (int r = lane; r < rc; r += 32) tile[c * RCp + r] = 0;
+                }
             }
             __syncthreads();
-            for (int rr = w; rr < 32; rr += nw) {  // warp rr writes row r0 + rr for 32 consecutive t (coalesced)
-                int v = tile[lane][rr];
-                if (r0 + rr < R && t0 + lane < nM) xT[(size_t)(r0 + rr) * nM + t0 + lane] = v;
+            for (int rr = w; rr < rc; rr += nw) {  // row rb + rr always falls to this warp: bmax needs no atomics
+                int v = tile[lane * RCp + rr];
+                if (t0 + lane < nM) xT[(size_t)(rb + rr) * nM + t0 + lane] = v;
                 for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-                if (lane == 0 && r0 + rr < R && v > 0) atomicMax(&rowMax[r0 + rr], v);
+                if (lane == 0 && v > bmax[rr]) bmax[rr] = v;
             }
-            __syncthreads();
         }
+        __syncthreads();
+        for (int r = threadIdx.x; r < rc; r += blockDim.x)
+            if (bmax[r] > 0) atomicMax(&rowMax[rb + r], bmax[r]);
     }
 }
 
