@@ -75,6 +75,7 @@ struct SweepBufs {
     DevBuf<long long> stats;  // [which][8]
     // value tables of the z sweep (k_sweep_z): row histogram, per-row offsets, per-CTA global tables
     DevBuf<int> ztHist, ztOffg, ztGrp, ztTmp, ztXT;
+    DevBuf<double> ztVal;  // [K][ZT_MAXGRP * EsCap] the round's value tables, shared by the grid
     int Wmax = 32768, Wmin = 32, lgT = 2048;  // Wmax: ring capacity, a power of two (ring_slot)
     int alloc(int ncand, cudaStream_t st) {
         CELDA_TRY(bufP.alloc((size_t)Wmax * ncand));
@@ -366,7 +367,7 @@ int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     {
         const size_t base = z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32);
         const long long room = ((long long)200 * 1024 - (long long)base) / (long long)sizeof(double);  // ~28 KB stays L1
-        if (sms >= a.K && room >= 8LL * a.R && a.nM >= 4096) {
+        if (room >= 8LL * a.R && a.nM >= 4096) {
             a.EsCap = (int)std::min<long long>(room, 1 << 20);
             if (b.ztOffg.n < (size_t)a.R + 1) {
                 CELDA_TRY(b.ztHist.alloc((size_t)a.R));  // per-row maximum count
@@ -375,6 +376,9 @@ int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
                 CELDA_TRY(b.ztTmp.alloc((size_t)a.R));
             }
             if (b.ztXT.n < (size_t)a.R * a.nM) CELDA_TRY(b.ztXT.alloc((size_t)a.R * a.nM));
+            a.vtStride = (long long)ZT_MAXGRP * a.EsCap;  // k_pick_rowV never lets the rows' tables exceed this
+            if (b.ztVal.n < (size_t)a.K * a.vtStride) CELDA_TRY(b.ztVal.alloc((size_t)a.K * a.vtStride));
+            a.vtg = b.ztVal.p;
             CELDA_TRY(b.ztHist.zero(st));
             const int RC = std::min(a.R, 1024);
             const size_t ptSmem = sizeof(int) * ((size_t)32 * (RC | 1) + RC);
@@ -386,6 +390,23 @@ int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
             a.offg = b.ztOffg.p;
             a.grp = b.ztGrp.p;
             a.xT = b.ztXT.p;
+            // Steady-state window for table rounds: the sweep is cut into nr equal windows such that the (candidate,
+            // 32-cell chunk) tasks and the draws fill whole grid-wide warp passes (a 32768-cell cap on 100k cells would
+            // run 3 windows of 6.5 passes, each rounded up to 7, plus a remainder)
+            const long long tw = (long long)sms * (threads / 32), cap = a.w.Wfull;
+            long long bestW = cap;
+            double bestCost = 1e300;
+            for (long long nr = (a.nM + cap - 1) / cap, q = 0; q < 4; ++q, ++nr) {
+                const long long W = std::min<long long>(cap, (((a.nM + nr - 1) / nr + 31) / 32) * 32);
+                const long long tablePasses = ((long long)a.K * (W / 32) + tw - 1) / tw, drawPasses = (W + tw - 1) / tw;
+                const double cost = (double)((a.nM + W - 1) / W) * (6.5 * (double)tablePasses + (double)drawPasses + 1.0);
+                if (cost < bestCost) {
+                    bestCost = cost;
+                    bestW = W;
+                }
+            }
+            a.w.Wfull = (int)bestW;
+            a.w.Wunit = std::min(a.w.Wunit, a.w.Wfull);
         }
     }
     const size_t smem = z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32, a.EsCap);

@@ -353,6 +353,8 @@ struct ZArgs {
     const int* grp;     // [ZT_MAXGRP + 2]: grp[0] = number of row groups, then the group boundaries (rows)
     int EsCap;          // shared-memory table capacity in entries; 0 disables the tables
     const int* xT;      // [R][nM]: xT[r][t] = counts[r, ix[t] - 1], the counts in visiting order, cell-minor
+    double* vtg;        // [K][vtStride] the value tables of a round, built once by the whole grid, copied by the users
+    long long vtStride; // entries per candidate (>= offg[R])
     SweepWork w;
 };
 
@@ -376,15 +378,12 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
     int* grp_s = offg_s + R + 1;    // [ZT_MAXGRP + 2]
     int* s_misc = grp_s + ZT_MAXGRP + 2;  // [0] first mover
     double* scr = scratch_all + (size_t)warp * scratchD;
-    // Lane-per-unit rounds: CTA b owns candidate b % K (replica b / K) and tabulates
+    // Lane-per-unit rounds: a CTA tabulates, for the candidate j it is serving,
     // lgamma(n[r][j] + v + beta) over the counts v that occur in row r, one group of rows at a time (as many rows
     // as fit the shared-memory table).  A unit then is R look-ups added in the reference's order instead of R
     // lgamma evaluations; its partial sum waits in the ring buffer between row groups.  The tables hold exactly
     // the values lg_tab() returns, and a count beyond a row's table is evaluated directly.
-    const int myCand = blockIdx.x % K, myRep = blockIdx.x / K;
-    // replicas of my candidate: CTAs myCand, myCand + K, ... (every CTA owns one candidate when gridDim >= K)
-    const int nrep = (a.EsCap > 0 && (int)gridDim.x >= K) ? ((int)gridDim.x - myCand + K - 1) / K : 0;
-    const bool tabCTA = nrep > 0;
+    const bool useTab = a.EsCap > 0;
 
     const double Rbeta = (double)R * a.beta;
     const int gwarp = blockIdx.x * nwarp + warp, tw = gridDim.x * nwarp;
@@ -396,7 +395,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
     for (int q = threadIdx.x; q < K; q += blockDim.x) nCP_s[q] = a.nCP[q];
     for (int q = threadIdx.x; q < K * nS; q += blockDim.x) m_s[q] = a.mCPByS[q];
     for (int q = threadIdx.x; q < T; q += blockDim.x) lgtab[q] = dlgamma((double)q + a.beta);
-    if (nrep > 0) {
+    if (useTab) {
         for (int q = threadIdx.x; q <= R; q += blockDim.x) offg_s[q] = a.offg[q];
         for (int q = threadIdx.x; q < ZT_MAXGRP + 2; q += blockDim.x) grp_s[q] = a.grp[q];
     }
@@ -516,7 +515,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
             }
         };
         const bool bigRound = total >= (long long)tw * 16;
-        if (bigRound && nrep > 0) {
+        if (bigRound && useTab) {
             // (1) cached column sums and patch units: few, one warp each
             for (long long uidx = gwarpT; uidx < nd + nPatch; uidx += tw) {
                 int j;
@@ -525,62 +524,87 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                 warp_unit(t, j);
             }
             const long long nFreshCells = end - hi;
-            // (2) fresh cells x candidates other than the cell's own: table look-ups on the candidate's CTAs
-            if (tabCTA) {
-                const int j = myCand;
-                const int* ncol = n_s + j * Rp;
+            // (1b) this round's value tables, every entry once: vtg[j][e] = lgamma(n[r][j] + v + beta) for the e-th
+            // (row, count) pair; the CTAs that serve candidate j copy the row group they need into shared memory
+            {
+                const int Etot = offg_s[R];
+                const long long nEnt = (long long)K * Etot;
+                for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < nEnt;
+                     idx += (long long)gridDim.x * blockDim.x) {
+                    const int j = (int)(idx / Etot), e = (int)(idx - (long long)j * Etot);
+                    int lo = 0, hiR = R;  // row with offg[row] <= e < offg[row + 1]
+                    while (hiR - lo > 1) {
+                        const int mid = (lo + hiR) >> 1;
+                        if (offg_s[mid] <= e) lo = mid; else hiR = mid;
+                    }
+                    a.vtg[(size_t)j * a.vtStride + e] = lg_tab(lgtab, T, (long long)n_s[j * Rp + lo] + (e - offg_s[lo]), a.beta);
+                }
+                grid_sync(a.w.barrier, bar_target);
+            }
+            // (2) fresh cells x candidates other than the cell's own: table look-ups.  The K x nchunk (candidate,
+            // 32-cell chunk) tasks are cut into gridDim equal contiguous runs, candidate-major, so a CTA serves one
+            // candidate or the tail of one and the head of the next, building that candidate's table first.
+            {
                 const int ngrp = grp_s[0];
                 const long long nchunk = (nFreshCells + 31) / 32;
-                for (int gI = 0; gI < ngrp; ++gI) {
-                    const int r0 = grp_s[1 + gI], r1 = grp_s[2 + gI];
-                    const int e0 = offg_s[r0], ne = offg_s[r1] - e0;
-                    __syncthreads();
-                    {
-                        int rr = r0;  // a thread's entries ascend, so its row only moves forward
-                        for (int q = threadIdx.x; q < ne; q += blockDim.x) {
-                            while (offg_s[rr + 1] - e0 <= q) ++rr;
-                            vt_s[q] = lg_tab(lgtab, T, (long long)ncol[rr] + (q - (offg_s[rr] - e0)), a.beta);
+                const long long totalCh = (long long)K * nchunk;
+                const long long c0 = totalCh * blockIdx.x / gridDim.x, c1 = totalCh * (blockIdx.x + 1) / gridDim.x;
+                for (long long cs = c0; cs < c1;) {
+                    const int j = (int)(cs / nchunk);
+                    const long long segEnd = min(c1, (long long)(j + 1) * nchunk);
+                    const long long chLo = cs - (long long)j * nchunk, chHi = segEnd - (long long)j * nchunk;
+                    cs = segEnd;
+                    const int* ncol = n_s + j * Rp;
+                    for (int gI = 0; gI < ngrp; ++gI) {
+                        const int r0 = grp_s[1 + gI], r1 = grp_s[2 + gI];
+                        const int e0 = offg_s[r0], ne = offg_s[r1] - e0;
+                        __syncthreads();
+                        {
+                            const double* src = a.vtg + (size_t)j * a.vtStride + e0;
+                            for (int q = threadIdx.x; q < ne; q += blockDim.x) vt_s[q] = __ldcg(src + q);
                         }
-                    }
-                    __syncthreads();
-                    for (long long ch = myRep + (long long)nrep * warp; ch < nchunk; ch += (long long)nrep * nwarp) {
-                        const long long q = ch * 32 + lane;
-                        if (q >= nFreshCells) continue;
-                        const long long t = hi + q;
-                        const long long i = a.ix[t] - 1;
-                        if (a.z[i] - 1 == j) continue;  // the cell's own population: step (3)
-                        const int* x = a.xT + t;  // lanes hold consecutive t: one coalesced load per row
-                        const size_t o = ring_slot(t, a.w.Wmax) * K + j;
-                        double S = (gI == 0) ? 0.0 : a.w.bufP[o];
-                        int r = r0;
-                        const int* xp = x + (size_t)r0 * a.nM;  // walks down the rows: + nM per row
-                        for (; r + 8 <= r1; r += 8) {  // eight row loads in flight, then eight look-ups in row order
-                            int v[8];
+                        __syncthreads();
+                        for (long long ch = chLo + warp; ch < chHi; ch += nwarp) {
+                            const long long q = ch * 32 + lane;
+                            if (q >= nFreshCells) continue;
+                            const long long t = hi + q;
+                            const long long i = a.ix[t] - 1;
+                            if (a.z[i] - 1 == j) continue;  // the cell's own population: step (3)
+                            const int* x = a.xT + t;  // lanes hold consecutive t: one coalesced load per row
+                            const size_t o = ring_slot(t, a.w.Wmax) * K + j;
+                            double S = (gI == 0) ? 0.0 : a.w.bufP[o];
+                            int r = r0;
+                            const int* xp = x + (size_t)r0 * a.nM;  // walks down the rows: + nM per row
+                            for (; r + 8 <= r1; r += 8) {  // eight row loads in flight, then eight look-ups in row order
+                                int v[8];
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                v[k] = __ldg(xp);
+                                for (int k = 0; k < 8; ++k) {
+                                    v[k] = __ldg(xp);
+                                    xp += a.nM;
+                                }
+                                int og = offg_s[r];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    const int ogn = offg_s[r + k + 1];
+                                    const double val = (v[k] < ogn - og)
+                                                           ? vt_s[og - e0 + v[k]]
+                                                           : lg_tab(lgtab, T, (long long)ncol[r + k] + v[k], a.beta);
+                                    S += val;
+                                    og = ogn;
+                                }
+                            }
+                            for (; r < r1; ++r) {
+                                const int v = __ldg(xp);
                                 xp += a.nM;
-                            }
-                            int og = offg_s[r];
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                const int ogn = offg_s[r + k + 1];
-                                const double val = (v[k] < ogn - og) ? vt_s[og - e0 + v[k]]
-                                                                    : lg_tab(lgtab, T, (long long)ncol[r + k] + v[k], a.beta);
+                                const int og = offg_s[r];
+                                const double val = (v < offg_s[r + 1] - og) ? vt_s[og - e0 + v]
+                                                                           : lg_tab(lgtab, T, (long long)ncol[r] + v, a.beta);
                                 S += val;
-                                og = ogn;
                             }
+                            a.w.bufP[o] = S;
+                            if (gI == ngrp - 1)
+                                a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)a.nByC[i]) + Rbeta);
                         }
-                        for (; r < r1; ++r) {
-                            const int v = __ldg(xp);
-                            xp += a.nM;
-                            const int og = offg_s[r];
-                            const double val = (v < offg_s[r + 1] - og) ? vt_s[og - e0 + v]
-                                                                       : lg_tab(lgtab, T, (long long)ncol[r] + v, a.beta);
-                            S += val;
-                        }
-                        a.w.bufP[o] = S;
-                        if (gI == ngrp - 1) a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)a.nByC[i]) + Rbeta);
                     }
                 }
             }
