@@ -74,7 +74,7 @@ struct SweepBufs {
     DevBuf<unsigned> barrier;
     DevBuf<long long> stats;  // [which][8]
     // value tables of the z sweep (k_sweep_z): row histogram, per-row offsets, per-CTA global tables
-    DevBuf<int> ztHist, ztOffg, ztGrp, ztTmp, ztXT;
+    DevBuf<int> ztHist, ztOffg, ztGrp, ztTmp, ztXT, ztZT, ztNT;
     DevBuf<double> ztVal;  // [K][ZT_MAXGRP * EsCap] the round's value tables, shared by the grid
     int Wmax = 32768, Wmin = 32, lgT = 2048;  // Wmax: ring capacity, a power of two (ring_slot)
     int alloc(int ncand, cudaStream_t st) {
@@ -376,6 +376,10 @@ int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
                 CELDA_TRY(b.ztTmp.alloc((size_t)a.R));
             }
             if (b.ztXT.n < (size_t)a.R * a.nM) CELDA_TRY(b.ztXT.alloc((size_t)a.R * a.nM));
+            if (b.ztZT.n < (size_t)a.nM) {
+                CELDA_TRY(b.ztZT.alloc((size_t)a.nM));
+                CELDA_TRY(b.ztNT.alloc((size_t)a.nM));
+            }
             a.vtStride = (long long)ZT_MAXGRP * a.EsCap;  // k_pick_rowV never lets the rows' tables exceed this
             if (b.ztVal.n < (size_t)a.K * a.vtStride) CELDA_TRY(b.ztVal.alloc((size_t)a.K * a.vtStride));
             a.vtg = b.ztVal.p;
@@ -384,12 +388,14 @@ int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
             const size_t ptSmem = sizeof(int) * ((size_t)32 * (RC | 1) + RC);
             CELDA_CUDA_OK(cudaFuncSetAttribute(k_permute_transpose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ptSmem));
             k_permute_transpose<<<(int)std::min<long long>((a.nM + 31) / 32, (long long)sms * 8), 256, ptSmem, st>>>(
-                a.counts, a.R, RC, a.nM, a.ix, b.ztXT.p, b.ztHist.p);
+                a.counts, a.R, RC, a.nM, a.ix, b.ztXT.p, b.ztHist.p, a.z, a.nByC, b.ztZT.p, b.ztNT.p);
             k_pick_rowV<<<1, 256, 0, st>>>(b.ztHist.p, a.R, a.EsCap, b.ztOffg.p, b.ztGrp.p, b.ztTmp.p);
             count_launch(2);
             a.offg = b.ztOffg.p;
             a.grp = b.ztGrp.p;
             a.xT = b.ztXT.p;
+            a.zT = b.ztZT.p;
+            a.nT = b.ztNT.p;
             // Steady-state window for table rounds: the sweep is cut into nr equal windows such that the (candidate,
             // 32-cell chunk) tasks and the draws fill whole grid-wide warp passes (a 32768-cell cap on 100k cells would
             // run 3 windows of 6.5 passes, each rounded up to 7, plus a remainder)

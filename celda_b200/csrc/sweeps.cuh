@@ -353,6 +353,8 @@ struct ZArgs {
     const int* grp;     // [ZT_MAXGRP + 2]: grp[0] = number of row groups, then the group boundaries (rows)
     int EsCap;          // shared-memory table capacity in entries; 0 disables the tables
     const int* xT;      // [R][nM]: xT[r][t] = counts[r, ix[t] - 1], the counts in visiting order, cell-minor
+    const int* zT;      // [nM] zT[t] = z[ix[t] - 1] at the start of the sweep (a cell's label changes only at its own visit)
+    const int* nT;      // [nM] nT[t] = nByC[ix[t] - 1]
     double* vtg;        // [K][vtStride] the value tables of a round, built once by the whole grid, copied by the users
     long long vtStride; // entries per candidate (>= offg[R])
     SweepWork w;
@@ -561,15 +563,26 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                         __syncthreads();
                         {
                             const double* src = a.vtg + (size_t)j * a.vtStride + e0;
-                            for (int q = threadIdx.x; q < ne; q += blockDim.x) vt_s[q] = __ldcg(src + q);
+                            for (int q0 = threadIdx.x; q0 < ne; q0 += 8 * blockDim.x) {  // eight loads in flight per thread
+                                double v[8];
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    const int q = q0 + k * blockDim.x;
+                                    v[k] = (q < ne) ? __ldcg(src + q) : 0.0;
+                                }
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    const int q = q0 + k * blockDim.x;
+                                    if (q < ne) vt_s[q] = v[k];
+                                }
+                            }
                         }
                         __syncthreads();
                         for (long long ch = chLo + warp; ch < chHi; ch += nwarp) {
                             const long long q = ch * 32 + lane;
                             if (q >= nFreshCells) continue;
                             const long long t = hi + q;
-                            const long long i = a.ix[t] - 1;
-                            if (a.z[i] - 1 == j) continue;  // the cell's own population: step (3)
+                            if (__ldg(a.zT + t) - 1 == j) continue;  // the cell's own population: step (3)
                             const int* x = a.xT + t;  // lanes hold consecutive t: one coalesced load per row
                             const size_t o = ring_slot(t, a.w.Wmax) * K + j;
                             double S = (gI == 0) ? 0.0 : a.w.bufP[o];
@@ -603,7 +616,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                             }
                             a.w.bufP[o] = S;
                             if (gI == ngrp - 1)
-                                a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)a.nByC[i]) + Rbeta);
+                                a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)__ldg(a.nT + t)) + Rbeta);
                         }
                     }
                 }
@@ -744,12 +757,19 @@ inline size_t z_sweep_smem(int R, int K, int nS, int T, int nwarp, int EsCap = 0
 // memory: each warp has a cell's whole column slice in flight (RC / 32 independent 128-byte loads), the rows go out
 // as 128-byte stores, and the per-row maxima are kept per block and merged with one atomic per row at the end.
 __global__ void k_permute_transpose(const int* __restrict__ counts, int R, int RC, long long nM, const int* __restrict__ ix,
-                                    int* __restrict__ xT, int* __restrict__ rowMax /* [R], zeroed */) {
+                                    int* __restrict__ xT, int* __restrict__ rowMax /* [R], zeroed */,
+                                    const int* __restrict__ z, const int* __restrict__ nByC, int* __restrict__ zT,
+                                    int* __restrict__ nT) {
     extern __shared__ int pt_smem[];
     const int RCp = RC | 1;
     int* tile = pt_smem;             // [32][RCp]
     int* bmax = pt_smem + 32 * RCp;  // [RC]
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < nM; t += (long long)gridDim.x * blockDim.x) {
+        const int i = ix[t] - 1;
+        zT[t] = z[i];
+        nT[t] = nByC[i];
+    }
     for (int rb = 0; rb < R; rb += RC) {
         const int rc = min(RC, R - rb);
         __syncthreads();
