@@ -372,7 +372,7 @@ int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
             if (b.ztOffg.n < (size_t)a.R + 1) {
                 CELDA_TRY(b.ztHist.alloc((size_t)a.R));  // per-row maximum count
                 CELDA_TRY(b.ztOffg.alloc((size_t)a.R + 1));
-                CELDA_TRY(b.ztGrp.alloc(ZT_MAXGRP + 2));
+                CELDA_TRY(b.ztGrp.alloc(ZT_MAXGRP + 3));
                 CELDA_TRY(b.ztTmp.alloc((size_t)a.R));
             }
             if (b.ztXT.n < (size_t)a.R * a.nM) CELDA_TRY(b.ztXT.alloc((size_t)a.R * a.nM));

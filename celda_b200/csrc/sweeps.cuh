@@ -350,7 +350,8 @@ struct ZArgs {
     double* probs;      // K x nM or null
     // value tables of the lane-per-unit rounds (see k_sweep_z)
     const int* offg;    // [R + 1] row r tabulates counts v in [0, offg[r+1] - offg[r])
-    const int* grp;     // [ZT_MAXGRP + 2]: grp[0] = number of row groups, then the group boundaries (rows)
+    const int* grp;     // [ZT_MAXGRP + 3]: grp[0] = number of row groups, then the group boundaries (rows); last entry = 1 when
+                        // every row's table covers all its counts (no look-up can miss)
     int EsCap;          // shared-memory table capacity in entries; 0 disables the tables
     const int* xT;      // [R][nM]: xT[r][t] = counts[r, ix[t] - 1], the counts in visiting order, cell-minor
     const int* zT;      // [nM] zT[t] = z[ix[t] - 1] at the start of the sweep (a cell's label changes only at its own visit)
@@ -362,6 +363,48 @@ struct ZArgs {
 
 __device__ __forceinline__ double lg_tab(const double* lgtab, int T, long long k, double beta) {
     return (k < T) ? lgtab[k] : dlgamma_hot((double)k + beta);
+}
+
+// One (candidate, cell) partial sum over the rows [r0, r1) of a row group: S += table[row][count], rows in order.
+// xp points at the cell's count in row r0 (stride nM per row); a row's table starts at vt_s[offg_s[row] - e0].
+// CHECK = false when every table covers all the counts of its row.
+template <bool CHECK>
+__device__ __forceinline__ double z_table_rows(const int* xp, long long nM, int r0, int r1, const int* offg_s, int e0,
+                                               const double* vt_s, const int* ncol, const double* lgtab, int T,
+                                               double beta, double S) {
+    int r = r0;
+    for (; r + 8 <= r1; r += 8) {  // eight row loads in flight, then eight look-ups in row order
+        int v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v[k] = __ldg(xp);
+            xp += nM;
+        }
+        int og = offg_s[r];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int ogn = offg_s[r + k + 1];
+            double val;
+            if (CHECK)
+                val = (v[k] < ogn - og) ? vt_s[og - e0 + v[k]] : lg_tab(lgtab, T, (long long)ncol[r + k] + v[k], beta);
+            else
+                val = vt_s[og - e0 + v[k]];
+            S += val;
+            og = ogn;
+        }
+    }
+    for (; r < r1; ++r) {
+        const int v = __ldg(xp);
+        xp += nM;
+        const int og = offg_s[r];
+        double val;
+        if (CHECK)
+            val = (v < offg_s[r + 1] - og) ? vt_s[og - e0 + v] : lg_tab(lgtab, T, (long long)ncol[r] + v, beta);
+        else
+            val = vt_s[og - e0 + v];
+        S += val;
+    }
+    return S;
 }
 
 __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
@@ -377,8 +420,8 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
     int* n_s = reinterpret_cast<int*>(vt_s + a.EsCap);
     int* m_s = n_s + (size_t)K * Rp;
     int* offg_s = m_s + K * nS;     // [R + 1]
-    int* grp_s = offg_s + R + 1;    // [ZT_MAXGRP + 2]
-    int* s_misc = grp_s + ZT_MAXGRP + 2;  // [0] first mover
+    int* grp_s = offg_s + R + 1;    // [ZT_MAXGRP + 3]
+    int* s_misc = grp_s + ZT_MAXGRP + 3;  // [0] first mover
     double* scr = scratch_all + (size_t)warp * scratchD;
     // Lane-per-unit rounds: a CTA tabulates, for the candidate j it is serving,
     // lgamma(n[r][j] + v + beta) over the counts v that occur in row r, one group of rows at a time (as many rows
@@ -399,7 +442,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
     for (int q = threadIdx.x; q < T; q += blockDim.x) lgtab[q] = dlgamma((double)q + a.beta);
     if (useTab) {
         for (int q = threadIdx.x; q <= R; q += blockDim.x) offg_s[q] = a.offg[q];
-        for (int q = threadIdx.x; q < ZT_MAXGRP + 2; q += blockDim.x) grp_s[q] = a.grp[q];
+        for (int q = threadIdx.x; q < ZT_MAXGRP + 3; q += blockDim.x) grp_s[q] = a.grp[q];
     }
     __syncthreads();
 
@@ -548,6 +591,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
             // candidate or the tail of one and the head of the next, building that candidate's table first.
             {
                 const int ngrp = grp_s[0];
+                const bool complete = grp_s[ZT_MAXGRP + 2] != 0;
                 const long long nchunk = (nFreshCells + 31) / 32;
                 const long long totalCh = (long long)K * nchunk;
                 const long long c0 = totalCh * blockIdx.x / gridDim.x, c1 = totalCh * (blockIdx.x + 1) / gridDim.x;
@@ -586,34 +630,9 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                             const int* x = a.xT + t;  // lanes hold consecutive t: one coalesced load per row
                             const size_t o = ring_slot(t, a.w.Wmax) * K + j;
                             double S = (gI == 0) ? 0.0 : a.w.bufP[o];
-                            int r = r0;
                             const int* xp = x + (size_t)r0 * a.nM;  // walks down the rows: + nM per row
-                            for (; r + 8 <= r1; r += 8) {  // eight row loads in flight, then eight look-ups in row order
-                                int v[8];
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) {
-                                    v[k] = __ldg(xp);
-                                    xp += a.nM;
-                                }
-                                int og = offg_s[r];
-#pragma unroll
-                                for (int k = 0; k < 8; ++k) {
-                                    const int ogn = offg_s[r + k + 1];
-                                    const double val = (v[k] < ogn - og)
-                                                           ? vt_s[og - e0 + v[k]]
-                                                           : lg_tab(lgtab, T, (long long)ncol[r + k] + v[k], a.beta);
-                                    S += val;
-                                    og = ogn;
-                                }
-                            }
-                            for (; r < r1; ++r) {
-                                const int v = __ldg(xp);
-                                xp += a.nM;
-                                const int og = offg_s[r];
-                                const double val = (v < offg_s[r + 1] - og) ? vt_s[og - e0 + v]
-                                                                           : lg_tab(lgtab, T, (long long)ncol[r] + v, a.beta);
-                                S += val;
-                            }
+                            S = complete ? z_table_rows<false>(xp, a.nM, r0, r1, offg_s, e0, vt_s, ncol, lgtab, T, a.beta, S)
+                                         : z_table_rows<true>(xp, a.nM, r0, r1, offg_s, e0, vt_s, ncol, lgtab, T, a.beta, S);
                             a.w.bufP[o] = S;
                             if (gI == ngrp - 1)
                                 a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)__ldg(a.nT + t)) + Rbeta);
@@ -749,7 +768,7 @@ inline size_t z_sweep_smem(int R, int K, int nS, int T, int nwarp, int EsCap = 0
     const int Rp = R | 1;
     const size_t scratchD = (size_t)std::max(R, 2 * K + (K + 1) / 2) + 2;
     return sizeof(double) * (T + nwarp * scratchD + EsCap) + sizeof(long long) * K +
-           sizeof(int) * ((size_t)K * Rp + K * nS + (R + 1) + ZT_MAXGRP + 2 + 4);
+           sizeof(int) * ((size_t)K * Rp + K * nS + (R + 1) + ZT_MAXGRP + 3 + 4);
 }
 
 // xT[r][t] = counts[r, ix[t] - 1]: the count matrix in visiting order, transposed, so that lanes holding
@@ -831,6 +850,9 @@ __global__ void k_pick_rowV(const int* __restrict__ rowMax, int R, int EsCap, in
         ++ngrp;
         grp[1 + ngrp] = R;
         grp[0] = ngrp;
+        int complete = 1;
+        for (int r = 0; r < R; ++r) complete &= (offg[r + 1] - offg[r] == rowMax[r] + 1);
+        grp[ZT_MAXGRP + 2] = complete;
     }
 }
 

@@ -314,15 +314,19 @@ def test_cg_iteration_more_than_32_populations(oracle):
     ch.close()
 
 
-@pytest.mark.parametrize("start", ["truth10", "random"])
+@pytest.mark.parametrize("start", ["truth10", "random", "truth10-truncated"])
 def test_cg_iteration_value_tables_large_windows(oracle, start):
-    """>= 4096 cells: the z sweep's lane-per-unit rounds run on candidate-owned value tables (shared-memory head +
-    global tail + direct fall-back) and must still equal the sequential oracle bit for bit; a few huge counts force
-    the fall-back paths."""
+    """>= 4096 cells: the z sweep's lane-per-unit rounds run on per-candidate value tables (built once per round by the
+    grid, staged in shared memory one row group at a time) and must still equal the sequential oracle bit for bit.
+    A few large counts stretch some rows' tables; in the 'truncated' case one module count exceeds the shared-memory
+    capacity, so its row's table is cut short and look-ups beyond it are evaluated directly."""
     rng = np.random.default_rng(91)
     G, C, K, L, S = 240, 6000, 9, 24, 3
     counts, s, z_true, y_true = simulate_cg(rng, G, C, K, L, S, nrange=(300, 900))
-    counts[:8, rng.integers(0, C, 40)] += rng.integers(500, 4000, (8, 40)).astype(np.int32)  # beyond every table
+    counts[:8, rng.integers(0, C, 40)] += rng.integers(500, 4000, (8, 40)).astype(np.int32)
+    if start.endswith("truncated"):
+        counts[3, rng.integers(0, C, 5)] += rng.integers(40000, 90000, 5).astype(np.int32)
+        start = "truth10"
     A, O = _csc(counts)
     if start == "random":
         z, y = rng.integers(1, K + 1, C).astype(np.int32), rng.integers(1, L + 1, G).astype(np.int32)
