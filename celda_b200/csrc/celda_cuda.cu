@@ -119,6 +119,7 @@ struct celda_chain {
     DevBuf<double> llPartial, llOut;
     DevBuf<double> phiBuf, thetaBuf;  // EM step
     DevBuf<double> lgt;               // celda_G: lgamma(nTSByC + beta), maintained by the y sweep
+    DevBuf<double> lgG;               // celda_CG: lgamma(k + beta), k < 2^22, read through L2 by the y sweep
     // Philox mode
     unsigned long long ph_seed = 0, ph_stream = 0;
     unsigned ph_sweep = 0;
@@ -338,6 +339,11 @@ int window_cap(const char* env, int dflt) {
     return c > 0 ? c : dflt;
 }
 
+unsigned env_u32(const char* env, unsigned dflt) {
+    const char* v = getenv(env);
+    return v ? (unsigned)strtoul(v, nullptr, 0) : dflt;
+}
+
 // Window sizes (items).  unit: the item count whose units (items x candidates) fill one grid-wide lane pass;
 // full: the largest multiple of it that fits the ring buffer, so lane-per-unit rounds leave no thread idle.
 void window_sizes(const SweepBufs& b, int sms, int threads, int ncand, int cap, int* full, int* unit) {
@@ -512,6 +518,8 @@ int launch_sweep_z(celda_chain* h, const int* d_ix, const double* d_u, int doSam
     a.u = d_u;
     a.doSample = doSample;
     a.probs = h->probsZ.p;
+    a.lgG = h->lgG.p;
+    a.TG = (int)h->lgG.n;
     return run_sweep_z(a, h->wb, h->sms, which, h->st);
 }
 
@@ -534,6 +542,9 @@ int launch_sweep_y(celda_chain* h, const int* d_ix, const double* d_u, int doSam
     a.u = d_u;
     a.doSample = doSample;
     a.probs = h->probsY.p;
+    a.lgG = h->lgG.p;
+    a.TG = (int)h->lgG.n;
+    a.lgMask = env_u32("CELDA_CUDA_LGMASK", 0x77777777u);
     return run_sweep_y(a, h->wb, h->sms, which, h->st);
 }
 
@@ -1518,6 +1529,12 @@ int celda_chain_create(celda_chain** out, int device, int model, int nG, int nM,
     }
     if (model == CELDA_MODEL_CG) CELDA_TRY(h->nTSByCP.alloc((size_t)h->L * h->K));
     if (model == CELDA_MODEL_C) CELDA_TRY(h->lgt.alloc((size_t)nG * h->K));  // lgamma(nGByCP + beta), Gibbs z sweep
+    if (model == CELDA_MODEL_CG) {
+        const long long TG = 1LL << 22;
+        CELDA_TRY(h->lgG.alloc((size_t)TG));
+        k_lgG_fill<<<grid_for(TG, 256, h->sms), 256, 0, st>>>(h->beta, TG, h->lgG.p);
+        count_launch();
+    }
     CELDA_TRY(h->wb.alloc(std::max(h->K, h->L), st));
     CELDA_TRY(h->ixy.alloc(nG));
     CELDA_TRY(h->uy.alloc(nG));

@@ -356,6 +356,8 @@ struct ZArgs {
     const int* xT;      // [R][nM]: xT[r][t] = counts[r, ix[t] - 1], the counts in visiting order, cell-minor
     const int* zT;      // [nM] zT[t] = z[ix[t] - 1] at the start of the sweep (a cell's label changes only at its own visit)
     const int* nT;      // [nM] nT[t] = nByC[ix[t] - 1]
+    const double* lgG;  // lgamma(k + beta), k < TG, L2-resident (see lg_tab2); null / 0 without a chain
+    int TG;
     double* vtg;        // [K][vtStride] the value tables of a round, built once by the whole grid, copied by the users
     long long vtStride; // entries per candidate (>= offg[R])
     SweepWork w;
@@ -363,6 +365,14 @@ struct ZArgs {
 
 __device__ __forceinline__ double lg_tab(const double* lgtab, int T, long long k, double beta) {
     return (k < T) ? lgtab[k] : dlgamma_hot((double)k + beta);
+}
+// The same value with a second, L2-resident level lgG[k] = lgamma(k + beta), k < TG (built once per chain by
+// k_lgG_fill with the same routine, so the bits agree); TG = 0 without a chain.
+__device__ __forceinline__ double lg_tab2(const double* lgtab, int T, const double* __restrict__ lgG, int TG, long long k,
+                                          double beta) {
+    if (k < T) return lgtab[k];
+    if (k < TG) return __ldg(lgG + k);
+    return dlgamma_hot((double)k + beta);
 }
 
 // One (candidate, cell) partial sum over the rows [r0, r1) of a row group: S += table[row][count], rows in order.
@@ -531,7 +541,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
         auto warp_unit = [&](long long t, int j) {
             const int* ncol = n_s + j * Rp;
             if (t < 0) {
-                for (int r = lane; r < R; r += 32) scr[r] = lg_tab(lgtab, T, ncol[r], a.beta);
+                for (int r = lane; r < R; r += 32) scr[r] = lg_tab2(lgtab, T, a.lgG, a.TG, ncol[r], a.beta);
                 __syncwarp();
                 if (lane == 0) {
                     double S = 0.0;
@@ -546,7 +556,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                 const int zi = a.z[i] - 1;
                 const int sgn = (j == zi) ? -1 : 1;
                 const int* x = a.counts + i * R;
-                for (int r = lane; r < R; r += 32) scr[r] = lg_tab(lgtab, T, (long long)ncol[r] + sgn * x[r], a.beta);
+                for (int r = lane; r < R; r += 32) scr[r] = lg_tab2(lgtab, T, a.lgG, a.TG, (long long)ncol[r] + sgn * x[r], a.beta);
                 __syncwarp();
                 if (lane == 0) {
                     double S = 0.0;
@@ -582,7 +592,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                         const int mid = (lo + hiR) >> 1;
                         if (offg_s[mid] <= e) lo = mid; else hiR = mid;
                     }
-                    a.vtg[(size_t)j * a.vtStride + e] = lg_tab(lgtab, T, (long long)n_s[j * Rp + lo] + (e - offg_s[lo]), a.beta);
+                    a.vtg[(size_t)j * a.vtStride + e] = lg_tab2(lgtab, T, a.lgG, a.TG, (long long)n_s[j * Rp + lo] + (e - offg_s[lo]), a.beta);
                 }
                 grid_sync(a.w.barrier, bar_target);
             }
@@ -653,7 +663,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                 const int* ncol = n_s + j * Rp;
                 if (t < 0) {
                     double S = 0.0;
-                    for (int r = 0; r < R; ++r) S += lg_tab(lgtab, T, ncol[r], a.beta);
+                    for (int r = 0; r < R; ++r) S += lg_tab2(lgtab, T, a.lgG, a.TG, ncol[r], a.beta);
                     a.w.colsum[j] = S;
                     a.w.lgnCP[j] = dlgamma((double)nCP_s[j] + Rbeta);
                 } else {
@@ -663,7 +673,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                     const int* x = a.counts + i * R;
                     double S = 0.0;
 #pragma unroll 2
-                    for (int r = 0; r < R; ++r) S += lg_tab(lgtab, T, (long long)ncol[r] + sgn * __ldg(x + r), a.beta);
+                    for (int r = 0; r < R; ++r) S += lg_tab2(lgtab, T, a.lgG, a.TG, (long long)ncol[r] + sgn * __ldg(x + r), a.beta);
                     const size_t o = ring_slot(t, a.w.Wmax) * K + j;
                     a.w.bufP[o] = S;
                     a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
@@ -872,8 +882,20 @@ struct YArgs {
     const double* u;
     int doSample;
     double* probs;  // L x nG or null
+    // lgG[k] = lgamma(k + beta) for k < TG, resident in L2 (same bits as lg_tab): lane-per-unit rounds fetch the terms
+    // of the columns selected by lgMask from it and evaluate the others, which keeps the FP64 pipe and the L2 busy
+    // side by side.  Null / 0 disables.
+    const double* lgG;
+    int TG;
+    unsigned lgMask;  // bit (c & 31): column c reads the table
     SweepWork w;
 };
+
+// lgG[k] = lgamma(k + beta) over k < n (built once per chain)
+__global__ void k_lgG_fill(double beta, long long n, double* __restrict__ out) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+        out[k] = dlgamma_hot((double)k + beta);
+}
 
 __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -904,7 +926,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
     __syncthreads();
     for (int q = threadIdx.x; q < L * C; q += blockDim.x) {
         const int l = q / C, c = q % C;
-        lgt_s[l * Cp + c] = lg_tab(lgtab, T, t_s[l * Cp + c], a.beta);
+        lgt_s[l * Cp + c] = lg_tab2(lgtab, T, a.lgG, a.TG, t_s[l * Cp + c], a.beta);
     }
     __syncthreads();
     // Module-only terms of cG_CalcGibbsProbY's second loop (:230-246), cached per module and refreshed when a
@@ -956,8 +978,8 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                     const int xv = x[c];
                     t_s[da * Cp + c] -= xv;
                     t_s[db * Cp + c] += xv;
-                    lgt_s[da * Cp + c] = lg_tab(lgtab, T, t_s[da * Cp + c], a.beta);
-                    lgt_s[db * Cp + c] = lg_tab(lgtab, T, t_s[db * Cp + c], a.beta);
+                    lgt_s[da * Cp + c] = lg_tab2(lgtab, T, a.lgG, a.TG, t_s[da * Cp + c], a.beta);
+                    lgt_s[db * Cp + c] = lg_tab2(lgtab, T, a.lgG, a.TG, t_s[db * Cp + c], a.beta);
                 }
                 if (threadIdx.x == 0) {
                     const long long Ni = a.nByG[i];
@@ -1024,7 +1046,16 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                     const int xc = __ldg(x + c);  // same gene on (almost) every lane of the warp: a uniform branch
                     const double cached = lrow[c];
                     // a zero count leaves the argument at t + beta, whose lgamma is the cached entry (same bits)
-                    const double fresh = (xc == 0) ? cached : lg_tab(lgtab, T, (long long)trow[c] + sgn * xc, a.beta);
+                    const long long kk = (long long)trow[c] + sgn * xc;
+                    double fresh;
+                    if (xc == 0)
+                        fresh = cached;
+                    else if (kk < T)
+                        fresh = lgtab[kk];
+                    else if (((a.lgMask >> (c & 31)) & 1u) && kk < a.TG)
+                        fresh = __ldg(a.lgG + kk);  // one 32-byte sector per lane: bound by L2 sector throughput
+                    else
+                        fresh = dlgamma_hot((double)kk + a.beta);
                     p += isCur ? cached : fresh;
                     p -= isCur ? fresh : cached;
                 }
@@ -1066,7 +1097,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                 for (int c = lane; c < C; c += 32) {
                     const double cached = lrow[c];
                     const double fresh =
-                        (x[c] == 0) ? cached : lg_tab(lgtab, T, (long long)trow[c] + (isCur ? -x[c] : x[c]), a.beta);
+                        (x[c] == 0) ? cached : lg_tab2(lgtab, T, a.lgG, a.TG, (long long)trow[c] + (isCur ? -x[c] : x[c]), a.beta);
                     scr[2 * c] = isCur ? cached : fresh;      // added
                     scr[2 * c + 1] = isCur ? fresh : cached;  // subtracted
                 }
