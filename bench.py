@@ -362,7 +362,7 @@ def main():
                 "algorithmic_bytes": bytes_alg[kname], "where": "decomposition (set_state), outside the timed step"}
         out["kernel_ms_per_step"] = {k: v["ms"] / K for k, v in prof.items()}
         out["sweep_stats_per_step"] = {k: {"rounds": prof[k]["rounds"] / K, "units": prof[k]["units"] / K,
-                                           "movers": prof[k]["movers"] / K,
+                                           "movers": prof[k]["movers"] / K, "carried_redraws": prof[k]["redraws"] / K,
                                            "cta0_mclk": {q: prof[k]["clk_" + q] / K / 1e6 for q in
                                                          ("commit", "units", "draw", "barrier")}}
                                        for k in ("sweep_y", "sweep_z")}

@@ -462,8 +462,8 @@ class Chain:
         out = {}
         for w, n in enumerate(names):
             ms, nl = C.c_double(0), C.c_longlong(0)
-            st = (C.c_longlong * 7)()
+            st = (C.c_longlong * 8)()
             check(lib().celda_chain_profile_get(self._h, w, C.byref(ms), C.byref(nl), st))
             out[n] = dict(ms=ms.value, launches=nl.value, rounds=st[0], units=st[1], movers=st[2],
-                          clk_commit=st[3], clk_units=st[4], clk_draw=st[5], clk_barrier=st[6])
+                          clk_commit=st[3], clk_units=st[4], clk_draw=st[5], clk_barrier=st[6], redraws=st[7])
         return out

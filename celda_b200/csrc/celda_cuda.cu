@@ -1929,6 +1929,23 @@ int celda_chain_profile(celda_chain* h, int enable) {
     return chain_sync(h);
 }
 
+#ifdef CELDA_DEBUG_STATS
+int celda_cuda_debug_counters(long long* out8, int reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    CELDA_CUDA_OK(cudaMemcpyFromSymbol(out8, g_dbg, sizeof(z)));
+    if (reset) CELDA_CUDA_OK(cudaMemcpyToSymbol(g_dbg, z, sizeof(z)));
+    return 0;
+}
+int celda_cuda_debug_segments(long long* out8, int reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CELDA_CUDA_OK(cudaDeviceSynchronize());
+    CELDA_CUDA_OK(cudaMemcpyFromSymbol(out8, g_dbg2, sizeof(z)));
+    if (reset) CELDA_CUDA_OK(cudaMemcpyToSymbol(g_dbg2, z, sizeof(z)));
+    return 0;
+}
+#endif
+
 int celda_chain_profile_get(celda_chain* h, int which, double* ms, long long* launches, long long* rounds) {
     if (which < 0 || which > 6) return fail("profile_get: which must be 0..6");
     CELDA_CUDA_OK(cudaSetDevice(h->device));
@@ -1938,7 +1955,7 @@ int celda_chain_profile_get(celda_chain* h, int which, double* ms, long long* la
     if (ms) *ms = h->prof_ms[which];
     if (launches) *launches = h->prof_launches[which];
     if (rounds) {
-        for (int q = 0; q < 7; ++q) rounds[q] = stats[q];
+        for (int q = 0; q < 8; ++q) rounds[q] = stats[q];
     }
     return 0;
 }

@@ -96,6 +96,16 @@ __device__ __forceinline__ double warp_ordered_sum_pos(const double* r, int n, i
     return s;
 }
 
+#ifdef CELDA_DEBUG_STATS
+__device__ unsigned long long g_dbg2[8];  // clocks by sampler segment (general path), lane 0
+#define CELDA_DBG_SEG(k) do { if (lane == 0) { const long long c_ = clock64(); atomicAdd(&g_dbg2[k], (unsigned long long)(c_ - dbg_c0)); dbg_c0 = c_; } } while (0)
+__device__ unsigned long long g_dbg[8];  // 0 draws, 1 compact hits, 2 general path, 3 rank sort, 4 exact path, 5 max clocks of one draw
+#define CELDA_DBG_ADD(k) do { if (lane == 0) atomicAdd(&g_dbg[k], 1ull); } while (0)
+#else
+#define CELDA_DBG_ADD(k) do { } while (0)
+#define CELDA_DBG_SEG(k) do { } while (0)
+#endif
+
 // .sampleLl (R/celda_functions.R:1-11) + sample.int(n, 1, TRUE, prob) with the uniform supplied.
 // pl: n log-probabilities in shared memory (overwritten on the rare exact path).  r: n doubles of warp scratch;
 // hs may alias pl; perm: n ints.  n <= 1024.
@@ -107,6 +117,10 @@ __device__ int warp_sample_ll(double* pl, int n, double u, double* r, int* perm,
     double* hs = pl;
     const unsigned FULL = 0xffffffffu;
     nz_out = make_int4(-2, -1, -1, -1);
+    CELDA_DBG_ADD(0);
+#ifdef CELDA_DEBUG_STATS
+    long long dbg_c0 = clock64();
+#endif
     double mx = -__longlong_as_double(0x7ff0000000000000LL);
     for (int i = lane; i < n; i += 32) mx = fmax(mx, pl[i]);
     for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(FULL, mx, o));
@@ -135,10 +149,83 @@ __device__ int warp_sample_ll(double* pl, int n, double u, double* r, int* perm,
         }
         if (np <= 4) nz_out = make_int4(i0, i1, i2, i3);
     }
+    // Compact path: at most 32 entries have exp() > 0 (the usual case once a chain has settled).  Lane k takes the k-th
+    // of them in index order and the whole pipeline -- the two ordered sums, the two normalisations, the descending
+    // order and the cumulative walk -- runs on one entry per lane.  Zero entries contribute +0.0 to the sums, fail
+    // n * q > 0.1 and sort behind every positive entry, so the arithmetic is the one the general path below performs.
+    // Anything unusual (exact ties, u beyond the total mass, an all-zero vector) falls through to the general path.
+    if (n > 1) {
+        int P = 0;
+        for (int base = 0; base < n; base += 32) {
+            const int i = base + lane;
+            const double v = (i < n) ? r[i] : 0.0;
+            const unsigned m = __ballot_sync(FULL, v > 0.0);
+            if (v > 0.0) {
+                const int at = P + __popc(m & ((1u << lane) - 1u));
+                if (at < 32) {
+                    perm[at] = i;
+                    hs[at] = v;
+                }
+            }
+            P += __popc(m);
+        }
+        __syncwarp();
+        if (P >= 1 && P <= 32) {
+            const int myIdx = (lane < P) ? perm[lane] : -1;
+            const double myE = (lane < P) ? hs[lane] : 0.0;
+            __syncwarp();
+            double c1 = 0.0;
+            for (int k = 0; k < P; ++k) c1 += shfl_d(myE, k);
+            const double r1 = myE / c1;
+            double c2 = 0.0;
+            for (int k = 0; k < P; ++k) {
+                const double v = shfl_d(r1, k);
+                if (v > 0.0) c2 += v;
+            }
+            if (c2 > 0.0) {
+                const double q = r1 / c2;
+                const int Ppos = __popc(__ballot_sync(FULL, q > 0.0));
+                int gt = 0, eq = 0;
+                for (int k = 0; k < P; ++k) {
+                    const double v = shfl_d(q, k);
+                    gt += (v > q);
+                    eq += (v == q);
+                }
+                const bool tie = __any_sync(FULL, q > 0.0 && eq > 1);
+                if (!tie) {
+                    if (q > 0.0) {
+                        hs[gt] = q;
+                        perm[gt] = myIdx;
+                    }
+                    __syncwarp();
+                    double cumc = 0.0;
+                    int res = -1;
+                    for (int k = 0; k < Ppos; ++k) {  // every lane, same order
+                        cumc = (k == 0) ? hs[k] : hs[k] + cumc;
+                        if (k == n - 1 || u <= cumc) {
+                            res = perm[k];
+                            break;
+                        }
+                    }
+                    __syncwarp();
+                    if (res >= 0) {
+                        CELDA_DBG_ADD(1);
+                        return res;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    }
+    CELDA_DBG_ADD(2);
+    CELDA_DBG_SEG(0);  // max, exp, list, compact attempt
     const double s1 = warp_ordered_sum_pos(r, n, lane);
+    CELDA_DBG_SEG(1);
     for (int i = lane; i < n; i += 32) r[i] = r[i] / s1;
     __syncwarp();
+    CELDA_DBG_SEG(2);
     const double s2 = warp_ordered_sum_pos(r, n, lane);  // FixupProb: plain-double sum of the positive entries
+    CELDA_DBG_SEG(3);
     if (!(s2 > 0.0)) return -3;
     int nc = 0, nzero = 0;
     for (int i = lane; i < n; i += 32) {
@@ -152,6 +239,7 @@ __device__ int warp_sample_ll(double* pl, int n, double u, double* r, int* perm,
         nzero += __shfl_xor_sync(FULL, nzero, o);
     }
     __syncwarp();
+    CELDA_DBG_SEG(4);
     if (nc > 200) return -1;
     if (n == 1) return 0;
     // Scan the values in descending order (the order revsort produces is unique up to ties).  Peaked
@@ -206,7 +294,9 @@ __device__ int warp_sample_ll(double* pl, int n, double u, double* r, int* perm,
         }
         if ((bi & 31) == lane) taken |= 1u << (bi >> 5);
     }
+    CELDA_DBG_SEG(5);  // arg-max steps
     if (!slow && result < 0) {
+        CELDA_DBG_ADD(3);
         // Rank sort of the positive entries (hs aliases pl, which is no longer needed): position = number of larger
         // values.  Any exact tie among positive entries leaves the order to heapsort => exact path.
         bool tie = false;
@@ -247,9 +337,11 @@ __device__ int warp_sample_ll(double* pl, int n, double u, double* r, int* perm,
             }
         }
         __syncwarp();
+        CELDA_DBG_SEG(6);  // rank sort + walk
     }
     if (!slow) return result;
     // Exact emulation of ProbSampleReplace on one lane (rare: exact ties, or u beyond the total mass).
+    CELDA_DBG_ADD(4);
     __syncwarp();
     if (lane == 0) {
         for (int i = 0; i < n; ++i) {
@@ -301,7 +393,8 @@ struct SweepWork {
     double* lgnCP;      // [K]  (z sweep)
     unsigned* barrier;  // zeroed before launch
     int* status;        // 0 ok, else sampler error code
-    long long* stats;   // [0] rounds, [1] units, [2] movers, [3..6] CTA-0 clocks in commit / units / draw / barriers
+    long long* stats;   // [0] rounds, [1] units, [2] movers, [3..6] CTA-0 clocks in commit / units / draw / barriers,
+                        // [7] carried items drawn again in full (all CTAs)
     int Wmax;           // ring capacity (items)
     int Wfull;          // steady-state window: units per round = a whole number of grid-wide lane passes
     int Wunit;          // items whose units fill one grid-wide lane pass
@@ -462,6 +555,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
     long long prev_end = 0;
     unsigned bar_target = 0;
     long long rounds = 0, units_done = 0, movers = 0;
+    long long redraws = 0;  // carried items drawn again in full (this thread's share)
     long long ck_commit = 0, ck_units = 0, ck_draw = 0, ck_bar = 0, ck0 = clock64(), ck1;
 #define CELDA_TICK(acc) do { ck1 = clock64(); acc += ck1 - ck0; ck0 = ck1; } while (0)
 
@@ -728,6 +822,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                     continue;
                 }
             }
+            if (lane == 0 && nd == 2 && t < hi) ++redraws;
             for (int j = lane; j < K; j += 32) {
                 const double p = combine(j);
                 pl[j] = p;
@@ -757,6 +852,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
         grid_sync(a.w.barrier, bar_target);
         CELDA_TICK(ck_bar);
     }
+    if (redraws) atomicAdd(reinterpret_cast<unsigned long long*>(a.w.stats + 7), (unsigned long long)redraws);
     // ---- write the tables back (CTA 0's copy; all copies are identical)
     if (blockIdx.x == 0) {
         for (int q = threadIdx.x; q < R * K; q += blockDim.x) a.nTab[q] = n_s[(q / R) * Rp + (q % R)];
@@ -766,11 +862,13 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
             a.w.stats[0] += rounds;
             a.w.stats[1] += units_done;
             a.w.stats[2] += movers;
-            a.w.stats[3] += ck_commit;
-            a.w.stats[4] += ck_units;
-            a.w.stats[5] += ck_draw;
-            a.w.stats[6] += ck_bar;
         }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.w.stats[3] += ck_commit;
+        a.w.stats[4] += ck_units;
+        a.w.stats[5] += ck_draw;
+        a.w.stats[6] += ck_bar;
     }
 }
 
@@ -955,6 +1053,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
     bool have_spec = false;
     unsigned bar_target = 0;
     long long rounds = 0, units_done = 0, movers = 0;
+    long long redraws = 0;  // carried items drawn again in full (this thread's share)
     long long ck_commit = 0, ck_units = 0, ck_draw = 0, ck_bar = 0, ck0 = clock64(), ck1;
 
     while (true) {
@@ -1169,6 +1268,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                     continue;
                 }
             }
+            if (lane == 0 && nd == 2 && t < hi) ++redraws;
             for (int l = lane; l < L; l += 32) {
                 const double p = __ldcg(a.w.bufP + o + l);
                 pl[l] = p;
@@ -1198,6 +1298,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
         grid_sync(a.w.barrier, bar_target);
         CELDA_TICK(ck_bar);
     }
+    if (redraws) atomicAdd(reinterpret_cast<unsigned long long*>(a.w.stats + 7), (unsigned long long)redraws);
     if (blockIdx.x == 0) {
         for (int q = threadIdx.x; q < L * C; q += blockDim.x) a.tTab[q] = t_s[(q % L) * Cp + (q / L)];
         for (int q = threadIdx.x; q < L; q += blockDim.x) {
@@ -1208,11 +1309,13 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
             a.w.stats[0] += rounds;
             a.w.stats[1] += units_done;
             a.w.stats[2] += movers;
-            a.w.stats[3] += ck_commit;
-            a.w.stats[4] += ck_units;
-            a.w.stats[5] += ck_draw;
-            a.w.stats[6] += ck_bar;
         }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.w.stats[3] += ck_commit;
+        a.w.stats[4] += ck_units;
+        a.w.stats[5] += ck_draw;
+        a.w.stats[6] += ck_bar;
     }
 }
 
@@ -1285,6 +1388,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
     bool have_spec = false;
     unsigned bar_target = 0;
     long long rounds = 0, units_done = 0, movers = 0;
+    long long redraws = 0;  // carried items drawn again in full (this thread's share)
     long long ck_commit = 0, ck_units = 0, ck_draw = 0, ck_bar = 0, ck0 = clock64(), ck1;
 
     while (true) {
@@ -1455,6 +1559,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
                     continue;
                 }
             }
+            if (lane == 0 && nd == 2 && tt < hi) ++redraws;
             for (int l = lane; l < L; l += 32) {
                 const double p = __ldcg(a.w.bufP + o + l);
                 pl[l] = p;
@@ -1484,6 +1589,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
         grid_sync(a.w.barrier, bar_target);
         CELDA_TICK(ck_bar);
     }
+    if (redraws) atomicAdd(reinterpret_cast<unsigned long long*>(a.w.stats + 7), (unsigned long long)redraws);
     __syncthreads();  // thread 0's last commit (a mover in the final position) precedes the write-back
     if (blockIdx.x == 0) {
         for (int q = threadIdx.x; q < L; q += blockDim.x) {
@@ -1494,11 +1600,13 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
             a.w.stats[0] += rounds;
             a.w.stats[1] += units_done;
             a.w.stats[2] += movers;
-            a.w.stats[3] += ck_commit;
-            a.w.stats[4] += ck_units;
-            a.w.stats[5] += ck_draw;
-            a.w.stats[6] += ck_bar;
         }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        a.w.stats[3] += ck_commit;
+        a.w.stats[4] += ck_units;
+        a.w.stats[5] += ck_draw;
+        a.w.stats[6] += ck_bar;
     }
 }
 
@@ -1573,6 +1681,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_zc(ZCArgs a) {
     bool have_spec = false;
     unsigned bar_target = 0;
     long long rounds = 0, units_done = 0, movers = 0;
+    long long redraws = 0;  // carried items drawn again in full (this thread's share)
 
     while (true) {
         bool committed = false;
@@ -1755,6 +1864,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_zc(ZCArgs a) {
                     continue;
                 }
             }
+            if (lane == 0 && nd == 2 && tt < hi) ++redraws;
             for (int j = lane; j < K; j += 32) {
                 const double p = combine(j);
                 pl[j] = p;
@@ -1782,6 +1892,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_zc(ZCArgs a) {
         have_spec = true;
         grid_sync(a.w.barrier, bar_target);
     }
+    if (redraws) atomicAdd(reinterpret_cast<unsigned long long*>(a.w.stats + 7), (unsigned long long)redraws);
     __syncthreads();  // thread 0's last commit (a mover in the final position) precedes the write-back
     if (blockIdx.x == 0) {
         for (int q = threadIdx.x; q < K; q += blockDim.x) a.nCP[q] = nCP_s[q];

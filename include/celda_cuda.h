@@ -185,7 +185,8 @@ int celda_chain_timer_stop(celda_chain *h, float *ms);
  * 5 rowSumByGroup (decompose), 6 colSumByGroup (decompose). */
 int celda_chain_profile(celda_chain *h, int enable);
 int celda_chain_profile_get(celda_chain *h, int which, double *ms, long long *launches,
-                            long long *stats /* [7]: rounds, units, movers, CTA-0 clocks in commit / units / draw / barriers */);
+                            long long *stats /* [8]: rounds, units, movers, CTA-0 clocks in commit / units / draw / barriers,
+                                                  carried items drawn again in full */);
 
 #ifdef __cplusplus
 }
