@@ -1,3 +1,7 @@
+#!/usr/bin/env python
+"""Debug aid: which sampler paths the sweeps take and how long the general path's segments run (device clocks).
+Needs the instrumented build: nvcc ... -DCELDA_DEBUG_STATS -shared -o celda_b200/libcelda_cuda_dbg.so celda_cuda.cu
+(see celda_b200/csrc/Makefile for the flags); the product library carries no counters."""
 import ctypes as C, sys, os, numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import celda_b200._lib as L
