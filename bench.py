@@ -324,21 +324,26 @@ def main():
         out["roofline"] = {
             "bound": "fp64", "kernel": "k_sweep_z", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
             "frac": ach / peak if peak else None,
-            "traffic": (128.946944 + 20.384256) * 1e6 if default_cfg else None,
+            "traffic": (150.641920 + 75.385344) * 1e6 if default_cfg else None,
             "traffic_note": "bytes; algorithmic HBM bytes are 4*L*C (nTSByC) + 4*L*C (visiting-order copy, written and read) "
-                            "+ 8*K*C (probs) = 144 MB",
+                            "+ 8*K*C (probs) = 144 MB; the rest is the per-(cell, population) partial sums and the round's "
+                            "value tables spilling from L2",
             "note": "achieved = ALGORITHMIC flops (C*K*L + 2*C*K lgamma at 56 flop, the reference's work) / device time; "
                     "peak = DFMA rate measured live (2 flop/FMA; MEASURED_PEAKS.json has no FP64 entry).  In large rounds "
                     "the kernel serves most lgamma terms from shared-memory value tables (bit-identical values), so the "
-                    "FP64 pipe itself is only ~20 % busy (ncu) and the limit is issue / shared-memory latency",
+                    "FP64 pipe itself is only ~10 % busy (ncu) and the limit is issue / shared-memory and L2 latency; "
+                    "ms_per_launch includes the two small helper kernels that lay the counts out in visiting order",
             "ms_per_launch": z_ms}
         y_ms = py["ms"] / max(1, py["launches"])
         y_flop = FLOP_PER_LGAMMA * (float(nG) * a.L * a.K + 6.0 * nG * a.L)
         out["roofline_y"] = {"bound": "fp64", "kernel": "k_sweep_y", "achieved": y_flop / (y_ms * 1e-3) / 1e12, "peak": peak,
                              "unit": "TFLOP/s", "frac": y_flop / (y_ms * 1e-3) / 1e12 / peak if peak else None,
-                             "traffic": (3.136768 + 4.524800) * 1e6 if default_cfg else None, "ms_per_launch": y_ms,
-                             "note": "unfused bit-reproducible arithmetic: 0.5 of the FMA peak is the ceiling; ncu: fp64 "
-                                     "pipe 44 % busy; ~11 movers per sweep each cost a grid-wide round"}
+                             "traffic": (11.512064 + 4.040192) * 1e6 if default_cfg else None, "ms_per_launch": y_ms,
+                             "note": "unfused bit-reproducible arithmetic: 0.5 of the FMA peak is the ceiling for evaluated "
+                                     "terms; 3 of 4 columns read lgamma(k + beta) from a 32 MB table in L2 instead (same "
+                                     "bits), ncu: fp64 pipe 21 % busy, barrier stalls dominate: ~11 movers per sweep each "
+                                     "cost a grid-wide round whose length is one full draw (tens of microseconds of "
+                                     "dependent FP64)"}
         # ---- HBM-bound aggregation kernels: the full decomposition (set_state), timed separately from the step
         zc, yc = ch.get_state()
         ch.profile(True)
