@@ -1471,14 +1471,22 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
             const bool active = valid && l >= 0;
             const bool isCur = active && (l == cur);
             const int lsafe = (l >= 0) ? l : 0;
-            // module of lane `lane` inside the staged tile: patch tasks stage rows da, db in slots 0, 1
-            // cursor into the gene's twin row; the next entry (column, count) is fetched one step ahead so that its
-            // latency is hidden behind the columns in between
-            long long nz = valid ? a.rp[i] : 0;
+            // Cursor into the gene's twin row.  The warp keeps a window of 32 consecutive entries in registers (lane k
+            // holds entry wbase + k: column and count, one coalesced load) and the window after it already in flight;
+            // the next entry reaches every lane by a shuffle, so that a gene with counts in many adjacent columns
+            // does not pay a global-load latency per column (it would hold up the whole CTA at the tile barrier).
             const long long nzEnd = valid ? a.rp[i + 1] : 0;
-            const long long NONE = 1LL << 60;
-            long long nextcol = (nz < nzEnd) ? a.tcol[nz] : NONE;
-            int nextx = (nz < nzEnd) ? a.tx[nz] : 0;
+            long long wbase = valid ? a.rp[i] : 0;
+            const int NONE = 0x7fffffff;
+            int wc, wx, wc2, wx2, widx = 0;
+            {
+                const long long e0 = wbase + lane, e1 = e0 + 32;
+                wc = (e0 < nzEnd) ? __ldg(a.tcol + e0) : NONE;
+                wx = (e0 < nzEnd) ? __ldg(a.tx + e0) : 0;
+                wc2 = (e1 < nzEnd) ? __ldg(a.tcol + e1) : NONE;
+                wx2 = (e1 < nzEnd) ? __ldg(a.tx + e1) : 0;
+            }
+            int nextcol = __shfl_sync(0xffffffffu, wc, 0), nextx = __shfl_sync(0xffffffffu, wx, 0);
             double p = 0.0;
             for (long long c0 = 0; c0 < nM; c0 += YG_TILE) {
                 const int tc = (int)min((long long)YG_TILE, nM - c0);
@@ -1490,12 +1498,12 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
                     ttile[cc * 32 + lane] = (l >= 0) ? __ldcg(a.t + g) : 0;
                 }
                 __syncthreads();
-                if (active) {
+                if (valid) {  // warp-uniform: the whole warp follows one gene, inactive lanes add zeros
                     // runs of columns where the gene has no count: (p + cached) - cached, a tight loop; then the
-                    // column with a count (warp-uniform: all lanes of the warp follow the same gene)
+                    // column with a count
                     int cc = 0;
                     while (cc < tc) {
-                        const int stop = (nextcol - c0 < tc) ? (int)(nextcol - c0) : tc;
+                        const int stop = ((long long)nextcol - c0 < tc) ? (int)((long long)nextcol - c0) : tc;
 #pragma unroll 4
                         for (; cc < stop; ++cc) {
                             const double cached = tile[cc * 32 + lane];
@@ -1507,19 +1515,21 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
                             const int xv = nextx;
                             const double fresh =
                                 lg_tab(lgtab, T, (long long)ttile[cc * 32 + lane] + (isCur ? -xv : xv), a.beta);
-                            ++nz;
-                            nextcol = (nz < nzEnd) ? a.tcol[nz] : NONE;
-                            nextx = (nz < nzEnd) ? a.tx[nz] : 0;
+                            if (++widx == 32) {  // window used up: the one in flight takes over, the next is requested
+                                wbase += 32;
+                                widx = 0;
+                                wc = wc2;
+                                wx = wx2;
+                                const long long e1 = wbase + 32 + lane;
+                                wc2 = (e1 < nzEnd) ? __ldg(a.tcol + e1) : NONE;
+                                wx2 = (e1 < nzEnd) ? __ldg(a.tx + e1) : 0;
+                            }
+                            nextcol = __shfl_sync(0xffffffffu, wc, widx);
+                            nextx = __shfl_sync(0xffffffffu, wx, widx);
                             p += isCur ? cached : fresh;
                             p -= isCur ? fresh : cached;
                             ++cc;
                         }
-                    }
-                } else {
-                    // inactive lanes keep the cursor in step so the tests above stay warp-uniform
-                    while (nextcol < c0 + tc) {
-                        ++nz;
-                        nextcol = (nz < nzEnd) ? a.tcol[nz] : NONE;
                     }
                 }
             }
