@@ -1793,11 +1793,20 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_zc(ZCArgs a) {
             const bool active = valid && j >= 0;
             const int sgn = (active && j == zi) ? -1 : 1;
             const int jsafe = (j >= 0) ? j : 0;
-            int nz = valid ? a.cp[i] : 0;
+            // cursor into the cell's CSC column: a register window of 32 entries per warp, the next window in flight
+            // (see k_sweep_yg)
             const int nzEnd = valid ? a.cp[i + 1] : 0;
+            int wbase = valid ? a.cp[i] : 0;
             const int NONE = 0x7fffffff;
-            int nextrow = (nz < nzEnd) ? a.ci[nz] : NONE;
-            int nextx = (nz < nzEnd) ? a.cx[nz] : 0;
+            int wc, wx, wc2, wx2, widx = 0;
+            {
+                const int e0 = wbase + lane, e1 = e0 + 32;
+                wc = (e0 < nzEnd) ? __ldg(a.ci + e0) : NONE;
+                wx = (e0 < nzEnd) ? __ldg(a.cx + e0) : 0;
+                wc2 = (e1 < nzEnd) ? __ldg(a.ci + e1) : NONE;
+                wx2 = (e1 < nzEnd) ? __ldg(a.cx + e1) : 0;
+            }
+            int nextrow = __shfl_sync(0xffffffffu, wc, 0), nextx = __shfl_sync(0xffffffffu, wx, 0);
             double S = 0.0;
             for (int r0 = 0; r0 < R; r0 += YG_TILE) {
                 const int tc = min(YG_TILE, R - r0);
@@ -1808,24 +1817,27 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_zc(ZCArgs a) {
                     ntile[rr * 32 + lane] = (j >= 0) ? __ldcg(a.n + g) : 0;
                 }
                 __syncthreads();
-                if (active) {
+                if (valid) {  // warp-uniform: the whole warp follows one cell, inactive lanes add zeros
                     int rr = 0;
                     while (rr < tc) {
-                        const int stop = (nextrow - r0 < tc) ? nextrow - r0 : tc;
+                        const int stop = ((long long)nextrow - r0 < tc) ? nextrow - r0 : tc;
 #pragma unroll 4
                         for (; rr < stop; ++rr) S += tile[rr * 32 + lane];
                         if (rr < tc) {
                             S += lg_tab(lgtab, T, (long long)ntile[rr * 32 + lane] + sgn * nextx, a.beta);
-                            ++nz;
-                            nextrow = (nz < nzEnd) ? a.ci[nz] : NONE;
-                            nextx = (nz < nzEnd) ? a.cx[nz] : 0;
+                            if (++widx == 32) {
+                                wbase += 32;
+                                widx = 0;
+                                wc = wc2;
+                                wx = wx2;
+                                const int e1 = wbase + 32 + lane;
+                                wc2 = (e1 < nzEnd) ? __ldg(a.ci + e1) : NONE;
+                                wx2 = (e1 < nzEnd) ? __ldg(a.cx + e1) : 0;
+                            }
+                            nextrow = __shfl_sync(0xffffffffu, wc, widx);
+                            nextx = __shfl_sync(0xffffffffu, wx, widx);
                             ++rr;
                         }
-                    }
-                } else {
-                    while (nextrow < r0 + tc) {
-                        ++nz;
-                        nextrow = (nz < nzEnd) ? a.ci[nz] : NONE;
                     }
                 }
             }
