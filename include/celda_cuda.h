@@ -137,7 +137,8 @@ void celda_chain_destroy(celda_chain *h);
 /* .cCGDecomposeCounts / .cCDecomposeCounts / .cGDecomposeCounts from labels (z or y may be NULL per model). */
 int celda_chain_set_state(celda_chain *h, const int *z, const int *y);
 int celda_chain_get_state(celda_chain *h, int *z, int *y);
-/* Sweeps with injected order/uniforms (host pointers) ... */
+/* Sweeps with injected order/uniforms (host pointers).  sweep_y: celda_CG and celda_G handles (the latter on the raw
+ * counts, every cell scanned); sweep_z_gibbs: celda_CG and celda_C handles (the latter on the raw counts). */
 int celda_chain_sweep_y(celda_chain *h, const int *ix, const double *u, int doSample);
 int celda_chain_sweep_z_gibbs(celda_chain *h, const int *ix, const double *u, int doSample);
 /* EM z step (.cCCalcEMProbZ, R/celda_C.R:717-756) and one EM-mode iteration of the chain loop. */
@@ -153,7 +154,9 @@ int celda_chain_get_draws(celda_chain *h, int which, int *ix, double *u);
 /* Raw generator (known-answer tests): out[4 i ..] = philox4x32_10(counters[4 i ..], key[0..1]) as 32-bit words. */
 int celda_cuda_philox4x32(const int *counters, const int *key, int n, int *out);
 /* One iteration of the chain loop without split heuristics (R/celda_CG.R:543-602): y sweep, rowSumByGroupChange,
- * z sweep (Gibbs), colSumByGroupChange, log-likelihood.  All four of ix/u NULL => Philox mode. */
+ * z sweep (Gibbs), colSumByGroupChange, log-likelihood.  All four of ix/u NULL => Philox mode.
+ * On a celda_C handle: the Gibbs z sweep on the raw counts + .cCCalcLL (R/celda_C.R:427-470; ix_y/u_y ignored);
+ * on a celda_G handle: the y sweep on the raw counts + .cGCalcLL (R/celda_G.R:400-424; ix_z/u_z ignored). */
 int celda_chain_iterate(celda_chain *h, const int *ix_y, const double *u_y, const int *ix_z, const double *u_z,
                         double *ll);
 /* Pre-stage injected draws for n_iter iterations in HBM, then run them without host traffic. */
