@@ -401,8 +401,12 @@ class Chain:
         return ll.value
 
     def iterate(self, ix_y, u_y, ix_z, u_z):
-        """One iteration of R/celda_CG.R:543-602 (no split heuristics); returns the log-likelihood."""
+        """One iteration of R/celda_CG.R:543-602 (no split heuristics); returns the log-likelihood.  On a celda_C
+        handle pass (None, None, ix_z, u_z), on a celda_G handle (ix_y, u_y, None, None); all None = Philox."""
         ll = C.c_double(0)
+        # int32 / float64 arrays pass through untouched (pinned buffers stay pinned); anything else is converted
+        ix_y, ix_z = (None if v is None else _i(v) for v in (ix_y, ix_z))
+        u_y, u_z = (None if v is None else _d(v) for v in (u_y, u_z))
         check(lib().celda_chain_iterate(self._h, _pi(ix_y), _pd(u_y), _pi(ix_z), _pd(u_z), C.byref(ll)))
         return ll.value
 
