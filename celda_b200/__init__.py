@@ -337,6 +337,13 @@ class Chain:
                                        _pi(counts.i), _pd(counts.x), _pi(s), self.nS, self.K, self.L, alpha, beta,
                                        delta, gamma))
 
+    def reconfigure(self, K=None, L=None):
+        """Another (K, L) of a grid search on the same resident counts (R/celdaGridSearch.R:290-391)."""
+        K = self.K if K is None else int(K)
+        L = self.L if L is None else int(L)
+        check(lib().celda_chain_reconfigure(self._h, K, L))
+        self.K, self.L = (1 if self.model == MODEL_G else K), (1 if self.model == MODEL_C else L)
+
     def close(self):
         if self._h:
             lib().celda_chain_destroy(self._h)
@@ -469,5 +476,6 @@ class Chain:
             st = (C.c_longlong * 8)()
             check(lib().celda_chain_profile_get(self._h, w, C.byref(ms), C.byref(nl), st))
             out[n] = dict(ms=ms.value, launches=nl.value, rounds=st[0], units=st[1], movers=st[2],
-                          clk_commit=st[3], clk_units=st[4], clk_draw=st[5], clk_barrier=st[6], redraws=st[7])
+                          clk_commit=st[3], clk_units=st[4], clk_draw=st[5], clk_barrier=st[6],
+                          redraws=st[7] & ((1 << 40) - 1), discards=st[7] >> 40)
         return out

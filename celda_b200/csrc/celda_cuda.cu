@@ -83,9 +83,9 @@ struct SweepBufs {
         CELDA_TRY(spec.alloc(Wmax));
         CELDA_TRY(drawMx.alloc(Wmax));
         CELDA_TRY(drawNz.alloc((size_t)4 * Wmax));
-        CELDA_TRY(colsum.alloc(ncand));
-        CELDA_TRY(lgnCP.alloc(ncand));
-        CELDA_TRY(status.alloc(1));
+        CELDA_TRY(colsum.alloc((size_t)ncand + 4 * MCMAX));
+        CELDA_TRY(lgnCP.alloc((size_t)ncand + 4 * MCMAX));
+        CELDA_TRY(status.alloc(2));  // [0] sampler status of the sweeps, [1] visiting order is not a permutation
         CELDA_TRY(status.zero(st));
         CELDA_TRY(barrier.alloc(1));
         CELDA_TRY(stats.alloc(40));
@@ -128,7 +128,7 @@ struct celda_chain {
     DevBuf<int> ph_iota;
     DevBuf<unsigned char> ph_tmp;
     int last_draw_n[2] = {0, 0};  // for get_draws: y, z
-    DevBuf<int> emFlag;
+    DevBuf<int> emFlag, ordSeen;
     // staged draws
     int staged_iters = 0;
     DevBuf<int> st_ixy, st_ixz;
@@ -193,11 +193,29 @@ int chain_sync(celda_chain* h) {
 
 int sweep_status(int stv);
 
+// Status of the sweeps launched since the last check.  A failure is reported once: the words are cleared so that the
+// handle can be used again (after set_state -- the chain state behind a failed sweep is unspecified).
 int chain_check_status(celda_chain* h) {
-    int stv = 0;
-    CELDA_CUDA_OK(cudaMemcpyAsync(&stv, h->wb.status.p, sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    int stv[2] = {0, 0};
+    CELDA_CUDA_OK(cudaMemcpyAsync(stv, h->wb.status.p, sizeof(stv), cudaMemcpyDeviceToHost, h->st));
     CELDA_TRY(chain_sync(h));
-    return sweep_status(stv);
+    if (stv[0] || stv[1]) {
+        CELDA_TRY(h->wb.status.zero(h->st));
+        CELDA_TRY(chain_sync(h));
+    }
+    if (stv[1]) return fail("the visiting order must be a permutation of 1..n");
+    return sweep_status(stv[0]);
+}
+
+// Injected visiting order: copied to the device and checked there (every value in 1..n exactly once).  A bad order
+// raises status word 1, which makes the sweep kernels return at once; the error surfaces at the end-of-call check.
+int chain_upload_order(celda_chain* h, int* d_ix, const int* ix, long long n) {
+    CELDA_CUDA_OK(cudaMemcpyAsync(d_ix, ix, sizeof(int) * n, cudaMemcpyHostToDevice, h->st));
+    if (h->ordSeen.n < (size_t)n) CELDA_TRY(h->ordSeen.alloc((size_t)n));
+    CELDA_CUDA_OK(cudaMemsetAsync(h->ordSeen.p, 0, sizeof(int) * n, h->st));
+    k_validate_order<<<grid_for(n, 256, h->sms), 256, 0, h->st>>>(d_ix, n, h->ordSeen.p, h->wb.status.p + 1);
+    count_launch();
+    return 0;
 }
 
 // Cell-sharded mode: combine the shards' partial G x K and K x S tables with one all-reduce each (int32 sums are
@@ -254,6 +272,8 @@ int chain_decompose(celda_chain* h) {
     }
     if (h->model == CELDA_MODEL_CG) {  // nTSByCP = colSumByGroup(nTSByC, z, K); nCP = colSums(nTSByCP)
         CELDA_TRY(h->nTSByCP.zero(st));
+        if (sizeof(int) * h->L * h->K > 200 * 1024) return fail("L x K = %d x %d tables exceed the shared-memory budget", h->L, h->K);
+        CELDA_CUDA_OK(cudaFuncSetAttribute(k_colsum_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * h->L * h->K)));
         k_colsum_dense<<<std::min(sms * 2, std::max(1, h->nM / 64)), 512, sizeof(int) * h->L * h->K, st>>>(
             h->nTSByC.p, h->L, h->nM, h->z.p, h->K, h->nTSByCP.p);
         k_colsums_small<<<1, 256, 0, st>>>(h->nTSByCP.p, h->L, h->K, h->nCP.p);
@@ -354,24 +374,33 @@ void window_sizes(const SweepBufs& b, int sms, int threads, int ncand, int cap, 
     *full = (int)(std::max<long long>(1, cap / u) * u);
 }
 
+// Tentative commits per round of k_sweep_z / k_sweep_y (sweeps.cuh, "multi-commit rounds"); CELDA_CUDA_MC overrides
+// (1 reproduces the one-mover-per-round schedule).
+int sweep_mc() {
+    const char* v = getenv("CELDA_CUDA_MC");
+    const int m = v ? atoi(v) : MCMAX;
+    return std::max(1, std::min(m, MCMAX));
+}
+
 // cap: largest steady-state window.  Items behind a mover are patched and redrawn every round, so a sweep whose
 // items keep moving (genes of low count in the y sweep) wants a smaller window than one that is quiet.
 SweepWork make_work(SweepBufs& b, int sms, int threads, int ncand, int which, int cap) {
     int wfull, wunit;
     window_sizes(b, sms, threads, ncand, std::min(cap, b.Wmax), &wfull, &wunit);
     return SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.drawMx.p, b.drawNz.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
-                     b.stats.p + 8 * which, b.Wmax, wfull, wunit, b.Wmin, b.lgT};
+                     b.stats.p + 8 * which, b.Wmax, wfull, wunit, b.Wmin, b.lgT, sweep_mc()};
 }
 
 // a: data pointers and sizes filled by the caller; work space, window policy and launch geometry set here.
 int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     int threads = 1024;
-    if (z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32) > 220 * 1024) threads = 512;
+    const int MC = sweep_mc();
+    if (z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32, 0, MC) > 220 * 1024) threads = 512;
     a.w = make_work(b, sms, threads, a.K, which, window_cap("CELDA_CUDA_ZCAP", 32768));
     // value tables: the shared memory left over holds the heads; sized from this sweep's count distribution
     a.EsCap = 0;
     {
-        const size_t base = z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32);
+        const size_t base = z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32, 0, MC);
         const long long room = ((long long)200 * 1024 - (long long)base) / (long long)sizeof(double);  // ~28 KB stays L1
         if (room >= 8LL * a.R && a.nM >= 4096) {
             a.EsCap = (int)std::min<long long>(room, 1 << 20);
@@ -394,7 +423,7 @@ int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
             const size_t ptSmem = sizeof(int) * ((size_t)32 * (RC | 1) + RC);
             CELDA_CUDA_OK(cudaFuncSetAttribute(k_permute_transpose, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ptSmem));
             k_permute_transpose<<<(int)std::min<long long>((a.nM + 31) / 32, (long long)sms * 8), 256, ptSmem, st>>>(
-                a.counts, a.R, RC, a.nM, a.ix, b.ztXT.p, b.ztHist.p, a.z, a.nByC, b.ztZT.p, b.ztNT.p);
+                a.counts, a.R, RC, a.nM, a.ix, b.ztXT.p, b.ztHist.p, a.z, a.nByC, b.ztZT.p, b.ztNT.p, b.status.p);
             k_pick_rowV<<<1, 256, 0, st>>>(b.ztHist.p, a.R, a.EsCap, b.ztOffg.p, b.ztGrp.p, b.ztTmp.p);
             count_launch(2);
             a.offg = b.ztOffg.p;
@@ -421,7 +450,7 @@ int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
             a.w.Wunit = std::min(a.w.Wunit, a.w.Wfull);
         }
     }
-    const size_t smem = z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32, a.EsCap);
+    const size_t smem = z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32, a.EsCap, MC);
     if (smem > 220 * 1024) return fail("z sweep: K=%d x R=%d tables need %zu bytes of shared memory (> 220 KB)", a.K, a.R, smem);
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CELDA_CUDA_OK(cudaMemsetAsync(b.barrier.p, 0, sizeof(unsigned), st));
@@ -433,9 +462,10 @@ int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
 
 int run_sweep_y(YArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     int threads = 1024;
-    if (y_sweep_smem(a.L, a.ncol, b.lgT, threads / 32) > 220 * 1024) threads = 512;
+    const int MC = sweep_mc();
+    if (y_sweep_smem(a.L, a.ncol, b.lgT, threads / 32, MC) > 220 * 1024) threads = 512;
     a.w = make_work(b, sms, threads, a.L, which, window_cap("CELDA_CUDA_YCAP", 8192));
-    const size_t smem = y_sweep_smem(a.L, a.ncol, b.lgT, threads / 32);
+    const size_t smem = y_sweep_smem(a.L, a.ncol, b.lgT, threads / 32, MC);
     if (smem > 220 * 1024) return fail("y sweep: L=%d x K=%d tables need %zu bytes of shared memory (> 220 KB)", a.L, a.ncol, smem);
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CELDA_CUDA_OK(cudaMemsetAsync(b.barrier.p, 0, sizeof(unsigned), st));
@@ -458,7 +488,7 @@ int run_sweep_yg(YGArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     if (unit > cap) unit = cap / nwarp * nwarp;
     const long long full = std::max<long long>(1, cap / unit) * unit;
     a.w = SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.drawMx.p, b.drawNz.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
-                    b.stats.p + 8 * which, b.Wmax, (int)full, (int)unit, std::max(b.Wmin, nwarp), b.lgT};
+                    b.stats.p + 8 * which, b.Wmax, (int)full, (int)unit, std::max(b.Wmin, nwarp), b.lgT, 1};
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_yg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CELDA_CUDA_OK(cudaMemsetAsync(b.barrier.p, 0, sizeof(unsigned), st));
     void* args[] = {&a};
@@ -481,7 +511,7 @@ int run_sweep_zc(ZCArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     if (unit > cap) unit = cap / nwarp * nwarp;
     const long long full = std::max<long long>(1, cap / unit) * unit;
     a.w = SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.drawMx.p, b.drawNz.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
-                    b.stats.p + 8 * which, b.Wmax, (int)full, (int)unit, std::max(b.Wmin, nwarp), b.lgT};
+                    b.stats.p + 8 * which, b.Wmax, (int)full, (int)unit, std::max(b.Wmin, nwarp), b.lgT, 1};
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_zc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CELDA_CUDA_OK(cudaMemsetAsync(b.barrier.p, 0, sizeof(unsigned), st));
     void* args[] = {&a};
@@ -732,6 +762,43 @@ int validate_order(const int* ix, long long n, const char* what) {
         if (v < 1 || v > n || seen[v - 1]) return fail("%s must be a permutation of 1..%lld", what, n);
         seen[v - 1] = 1;
     }
+    return 0;
+}
+
+// Every buffer whose size depends on K or L (tables, probabilities, sweep work space).  Called at create and by
+// celda_chain_reconfigure: the CSC copy, its gene-major twin and the row / column totals are (K, L)-independent.
+int chain_alloc_tables(celda_chain* h) {
+    const int model = h->model, nG = h->nG, nM = h->nM;
+    cudaStream_t st = h->st;
+    if (model != CELDA_MODEL_C) {
+        CELDA_TRY(h->nTSByC.alloc((size_t)h->L * nM));
+        if (model == CELDA_MODEL_G) CELDA_TRY(h->lgt.alloc((size_t)h->L * nM));
+        CELDA_TRY(h->nByTS.alloc(h->L));
+        CELDA_TRY(h->nGByTS.alloc(h->L));
+        CELDA_TRY(h->probsY.alloc((size_t)h->L * nG));
+    }
+    if (model != CELDA_MODEL_G) {
+        CELDA_TRY(h->nGByCP.alloc((size_t)nG * h->K));
+        CELDA_TRY(h->mCPByS.alloc((size_t)h->K * h->nS));
+        CELDA_TRY(h->nCP.alloc(h->K));
+        CELDA_TRY(h->probsZ.alloc((size_t)h->K * nM));
+        if (h->comm) {
+            CELDA_TRY(h->nGByCP_loc.alloc((size_t)nG * h->K));
+            CELDA_TRY(h->mCPByS_loc.alloc((size_t)h->K * h->nS));
+        }
+    }
+    if (model == CELDA_MODEL_CG) CELDA_TRY(h->nTSByCP.alloc((size_t)h->L * h->K));
+    if (model == CELDA_MODEL_C) CELDA_TRY(h->lgt.alloc((size_t)nG * h->K));  // lgamma(nGByCP + beta), Gibbs z sweep
+    if (model == CELDA_MODEL_CG && h->lgG.n == 0) {
+        const long long TG = 1LL << 22;
+        CELDA_TRY(h->lgG.alloc((size_t)TG));
+        k_lgG_fill<<<grid_for(TG, 256, h->sms), 256, 0, st>>>(h->beta, TG, h->lgG.p);
+        count_launch();
+    }
+    CELDA_TRY(h->wb.alloc(std::max(h->K, h->L), st));
+    CELDA_TRY(h->phiBuf.alloc((size_t)std::max(nG, h->L) * h->K));
+    CELDA_TRY(h->thetaBuf.alloc((size_t)h->K * h->nS));
+    h->has_state = false;
     return 0;
 }
 
@@ -1417,7 +1484,9 @@ int celda_chain_create(celda_chain** out, int device, int model, int nG, int nM,
     if (nG < 1 || nM < 1) return fail("counts must have at least one row and one column");
     if (model != CELDA_MODEL_G && (K < 1 || K > nM)) return fail("'K' must be between 1 and the number of cells");
     if (model != CELDA_MODEL_C && (L < 1 || L > nG)) return fail("'L' must be between 1 and the number of features");
-    if (K > 32767 || L > 32767) return fail("K and L must be below 32768");
+    // the sampler keeps one bit per candidate and lane in a 32-bit word (warp_sample_ll): at most 1024 candidates
+    if (K > 1024 || L > 1024) return fail("K and L must not exceed 1024");
+    if (p[0] != 0) return fail("column pointers of 'counts' must start at 0");
     if (model != CELDA_MODEL_G) {
         if (!s) return fail("sample labels are required");
         CELDA_TRY(check_labels_host(s, nM, nS, "s", "nS"));
@@ -1515,34 +1584,13 @@ int celda_chain_create(celda_chain** out, int device, int model, int nG, int nM,
         CELDA_TRY(h->changed.alloc(nG));
         CELDA_TRY(h->nchanged.alloc(1));
         CELDA_CUDA_OK(cudaStreamSynchronize(st));
-        CELDA_TRY(h->nTSByC.alloc((size_t)h->L * nM));
-        if (model == CELDA_MODEL_G) CELDA_TRY(h->lgt.alloc((size_t)h->L * nM));
-        CELDA_TRY(h->nByTS.alloc(h->L));
-        CELDA_TRY(h->nGByTS.alloc(h->L));
-        CELDA_TRY(h->probsY.alloc((size_t)h->L * nG));
     }
-    if (model != CELDA_MODEL_G) {
-        CELDA_TRY(h->nGByCP.alloc((size_t)nG * h->K));
-        CELDA_TRY(h->mCPByS.alloc((size_t)h->K * h->nS));
-        CELDA_TRY(h->nCP.alloc(h->K));
-        CELDA_TRY(h->probsZ.alloc((size_t)h->K * nM));
-    }
-    if (model == CELDA_MODEL_CG) CELDA_TRY(h->nTSByCP.alloc((size_t)h->L * h->K));
-    if (model == CELDA_MODEL_C) CELDA_TRY(h->lgt.alloc((size_t)nG * h->K));  // lgamma(nGByCP + beta), Gibbs z sweep
-    if (model == CELDA_MODEL_CG) {
-        const long long TG = 1LL << 22;
-        CELDA_TRY(h->lgG.alloc((size_t)TG));
-        k_lgG_fill<<<grid_for(TG, 256, h->sms), 256, 0, st>>>(h->beta, TG, h->lgG.p);
-        count_launch();
-    }
-    CELDA_TRY(h->wb.alloc(std::max(h->K, h->L), st));
+    CELDA_TRY(chain_alloc_tables(h.get()));
     CELDA_TRY(h->ixy.alloc(nG));
     CELDA_TRY(h->uy.alloc(nG));
     CELDA_TRY(h->ixz.alloc(nM));
     CELDA_TRY(h->uz.alloc(nM));
     CELDA_TRY(h->llPartial.alloc(1024));
-    CELDA_TRY(h->phiBuf.alloc((size_t)std::max(nG, h->L) * h->K));
-    CELDA_TRY(h->thetaBuf.alloc((size_t)h->K * h->nS));
     CELDA_TRY(h->emFlag.alloc(1));
     CELDA_TRY(h->llOut.alloc(1));
     CELDA_CUDA_OK(cudaStreamSynchronize(st));
@@ -1552,6 +1600,23 @@ int celda_chain_create(celda_chain** out, int device, int model, int nG, int nM,
 }
 
 void celda_chain_destroy(celda_chain* h) { delete h; }
+
+// celdaGridSearch runs every (K, L, chain) combination on the same counts (R/celdaGridSearch.R:290-391): the resident
+// CSC copy, its gene-major twin and the totals are kept, only the (K, L)-sized tables are re-allocated.  The handle
+// needs set_state before the next sweep.
+int celda_chain_reconfigure(celda_chain* h, int K, int L) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    CELDA_TRY(chain_sync(h));
+    if (h->comm) return fail("reconfigure: not available on a cell-sharded chain");
+    if (h->model != CELDA_MODEL_G && (K < 1 || K > h->nM)) return fail("'K' must be between 1 and the number of cells");
+    if (h->model != CELDA_MODEL_C && (L < 1 || L > h->nG)) return fail("'L' must be between 1 and the number of features");
+    if (K > 1024 || L > 1024) return fail("K and L must not exceed 1024");
+    h->K = (h->model == CELDA_MODEL_G) ? 1 : K;
+    h->L = (h->model == CELDA_MODEL_C) ? 1 : L;
+    CELDA_TRY(chain_alloc_tables(h));
+    CELDA_CUDA_OK(cudaGetLastError());
+    return chain_sync(h);
+}
 
 int celda_chain_set_state(celda_chain* h, const int* z, const int* y) {
     CELDA_CUDA_OK(cudaSetDevice(h->device));
@@ -1585,8 +1650,7 @@ int celda_chain_get_state(celda_chain* h, int* z, int* y) {
 int celda_chain_sweep_y(celda_chain* h, const int* ix, const double* u, int doSample) {
     CELDA_CUDA_OK(cudaSetDevice(h->device));
     if (!h->has_state) return fail("set_state must be called first");
-    CELDA_TRY(validate_order(ix, h->nG, "ix"));
-    CELDA_CUDA_OK(cudaMemcpyAsync(h->ixy.p, ix, sizeof(int) * h->nG, cudaMemcpyHostToDevice, h->st));
+        CELDA_TRY(chain_upload_order(h, h->ixy.p, ix, h->nG));
     CELDA_CUDA_OK(cudaMemcpyAsync(h->uy.p, u, sizeof(double) * h->nG, cudaMemcpyHostToDevice, h->st));
     CELDA_TRY(chain_step_y(h, h->ixy.p, h->uy.p, doSample));
     return chain_check_status(h);
@@ -1595,8 +1659,7 @@ int celda_chain_sweep_y(celda_chain* h, const int* ix, const double* u, int doSa
 int celda_chain_sweep_z_gibbs(celda_chain* h, const int* ix, const double* u, int doSample) {
     CELDA_CUDA_OK(cudaSetDevice(h->device));
     if (!h->has_state) return fail("set_state must be called first");
-    CELDA_TRY(validate_order(ix, h->nM, "ix"));
-    CELDA_CUDA_OK(cudaMemcpyAsync(h->ixz.p, ix, sizeof(int) * h->nM, cudaMemcpyHostToDevice, h->st));
+        CELDA_TRY(chain_upload_order(h, h->ixz.p, ix, h->nM));
     CELDA_CUDA_OK(cudaMemcpyAsync(h->uz.p, u, sizeof(double) * h->nM, cudaMemcpyHostToDevice, h->st));
     CELDA_TRY(chain_step_z(h, h->ixz.p, h->uz.p, doSample));
     return chain_check_status(h);
@@ -1713,8 +1776,7 @@ int celda_chain_iterate(celda_chain* h, const int* ix_y, const double* u_y, cons
     cudaStream_t st = h->st;
     if (h->model == CELDA_MODEL_C) {  // .celda_C loop body, algorithm = "Gibbs" (R/celda_C.R:427-470): z sweep, log-likelihood
         if (ix_z && u_z) {
-            CELDA_TRY(validate_order(ix_z, h->nM, "ix_z"));
-            CELDA_CUDA_OK(cudaMemcpyAsync(h->ixz.p, ix_z, sizeof(int) * h->nM, cudaMemcpyHostToDevice, st));
+                        CELDA_TRY(chain_upload_order(h, h->ixz.p, ix_z, h->nM));
             CELDA_CUDA_OK(cudaMemcpyAsync(h->uz.p, u_z, sizeof(double) * h->nM, cudaMemcpyHostToDevice, st));
         } else {
             CELDA_TRY(chain_philox_draws(h, h->nM, h->ixz.p, h->uz.p));
@@ -1726,8 +1788,7 @@ int celda_chain_iterate(celda_chain* h, const int* ix_y, const double* u_y, cons
     }
     if (h->model == CELDA_MODEL_G) {  // .celda_G loop body (R/celda_G.R:400-424): y sweep, log-likelihood
         if (ix_y && u_y) {
-            CELDA_TRY(validate_order(ix_y, h->nG, "ix_y"));
-            CELDA_CUDA_OK(cudaMemcpyAsync(h->ixy.p, ix_y, sizeof(int) * h->nG, cudaMemcpyHostToDevice, st));
+                        CELDA_TRY(chain_upload_order(h, h->ixy.p, ix_y, h->nG));
             CELDA_CUDA_OK(cudaMemcpyAsync(h->uy.p, u_y, sizeof(double) * h->nG, cudaMemcpyHostToDevice, st));
         } else {
             CELDA_TRY(chain_philox_draws(h, h->nG, h->ixy.p, h->uy.p));
@@ -1742,11 +1803,9 @@ int celda_chain_iterate(celda_chain* h, const int* ix_y, const double* u_y, cons
         CELDA_TRY(chain_philox_draws(h, h->nM, h->ixz.p, h->uz.p));
     } else {
         if (!ix_y || !u_y || !ix_z || !u_z) return fail("iterate: pass all four of ix_y, u_y, ix_z, u_z or none (Philox)");
-        CELDA_TRY(validate_order(ix_y, h->nG, "ix_y"));
-        CELDA_TRY(validate_order(ix_z, h->nM, "ix_z"));
-        CELDA_CUDA_OK(cudaMemcpyAsync(h->ixy.p, ix_y, sizeof(int) * h->nG, cudaMemcpyHostToDevice, st));
+                        CELDA_TRY(chain_upload_order(h, h->ixy.p, ix_y, h->nG));
         CELDA_CUDA_OK(cudaMemcpyAsync(h->uy.p, u_y, sizeof(double) * h->nG, cudaMemcpyHostToDevice, st));
-        CELDA_CUDA_OK(cudaMemcpyAsync(h->ixz.p, ix_z, sizeof(int) * h->nM, cudaMemcpyHostToDevice, st));
+        CELDA_TRY(chain_upload_order(h, h->ixz.p, ix_z, h->nM));
         CELDA_CUDA_OK(cudaMemcpyAsync(h->uz.p, u_z, sizeof(double) * h->nM, cudaMemcpyHostToDevice, st));
     }
     CELDA_TRY(chain_step_y(h, h->ixy.p, h->uy.p, 1));
@@ -1771,8 +1830,7 @@ int celda_chain_iterate_em(celda_chain* h, const int* ix_y, const double* u_y, d
     if (h->model == CELDA_MODEL_G) return fail("iterate_em: celda_G has no cell populations");
     if (h->model == CELDA_MODEL_CG) {
         if (!ix_y || !u_y) return fail("iterate_em: injected order and uniforms are required for the y sweep");
-        CELDA_TRY(validate_order(ix_y, h->nG, "ix_y"));
-        CELDA_CUDA_OK(cudaMemcpyAsync(h->ixy.p, ix_y, sizeof(int) * h->nG, cudaMemcpyHostToDevice, h->st));
+                CELDA_TRY(chain_upload_order(h, h->ixy.p, ix_y, h->nG));
         CELDA_CUDA_OK(cudaMemcpyAsync(h->uy.p, u_y, sizeof(double) * h->nG, cudaMemcpyHostToDevice, h->st));
         CELDA_TRY(chain_step_y(h, h->ixy.p, h->uy.p, 1));
     }
@@ -1838,6 +1896,8 @@ int celda_chain_perplexity(celda_chain* h, double* perplexity) {
 int celda_chain_stage_draws(celda_chain* h, int n_iter, const int* ix_y, const double* u_y, const int* ix_z,
                             const double* u_z) {
     CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (h->model != CELDA_MODEL_CG) return fail("stage_draws: staged iterations run on a celda_CG chain");
+    if (n_iter < 1 || !ix_y || !u_y || !ix_z || !u_z) return fail("stage_draws: n_iter >= 1 and all four arrays are required");
     for (int it = 0; it < n_iter; ++it) {
         CELDA_TRY(validate_order(ix_y + (size_t)it * h->nG, h->nG, "ix_y"));
         CELDA_TRY(validate_order(ix_z + (size_t)it * h->nM, h->nM, "ix_z"));

@@ -234,4 +234,11 @@ __device__ __forceinline__ double dlgamma(double x) {
     return dlgamma_large(x);
 }
 
+// lg_delta[k] of the reference: c(NA, lgamma(seq(nG + L) * delta)) (R/celda_CG.R:429, R/celda_G.R:332): index 0 is NA,
+// so a module count of zero makes the probability vector NA ("NA in probability vector" from sample.int).
+__device__ __forceinline__ double dlgdelta(int k, double delta) {
+    if (k == 0) return __longlong_as_double(0x7ff8000000000000LL);
+    return dlgamma_hot((double)k * delta);
+}
+
 }  // namespace celda

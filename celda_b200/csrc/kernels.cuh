@@ -538,15 +538,15 @@ __global__ void k_cG_CalcGibbsProbY(int index0, const double* __restrict__ count
         if (i == cur) {
             p += dlgamma_hot((double)g + gamma);
             p -= dlgamma_hot((double)(g - 1) + gamma);
-            p += dlgamma_hot((double)g * delta);
-            p -= dlgamma_hot((double)(g - 1) * delta);
+            p += dlgdelta(g, delta);
+            p -= dlgdelta(g - 1, delta);
             p += dlgamma_hot(nbyTS[i] - nbyG[index0] + (double)(g - 1) * delta);
             p -= dlgamma_hot(nbyTS[i] + (double)g * delta);
         } else {
             p += dlgamma_hot((double)(g + 1) + gamma);
             p -= dlgamma_hot((double)g + gamma);
-            p += dlgamma_hot((double)(g + 1) * delta);
-            p -= dlgamma_hot((double)g * delta);
+            p += dlgdelta(g + 1, delta);
+            p -= dlgdelta(g, delta);
             p += dlgamma_hot(nbyTS[i] + (double)g * delta);
             p -= dlgamma_hot(nbyTS[i] + nbyG[index0] + (double)(g + 1) * delta);
         }
@@ -1124,6 +1124,14 @@ __global__ void k_colsum_twin(int nG, const long long* __restrict__ rp, const in
             out[(size_t)g * K + k] = sum;
         }
         __syncthreads();
+    }
+}
+
+// An injected visiting order must hold every value of 1..n exactly once (seen: n ints, zeroed): flag is raised otherwise.
+__global__ void k_validate_order(const int* __restrict__ ix, long long n, int* __restrict__ seen, int* __restrict__ flag) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int v = ix[t];
+        if (v < 1 || v > n || atomicExch(&seen[v - 1], 1) != 0) *flag = 1;
     }
 }
 

@@ -389,17 +389,18 @@ struct SweepWork {
     int* spec;          // [Wmax] ring: packed (old << 16 | new) for movers, -1 otherwise
     double* drawMx;     // [Wmax] ring: max log-probability of the item's last draw
     int* drawNz;        // [Wmax][4] ring: its positive entries (see warp_sample_ll)
-    double* colsum;     // [K]  (z sweep)
-    double* lgnCP;      // [K]  (z sweep)
+    double* colsum;     // [K + 4 MCMAX]  (z sweep) cached column sums: base columns, then two banks of commit slots
+    double* lgnCP;      // [K + 4 MCMAX]  (z sweep)
     unsigned* barrier;  // zeroed before launch
     int* status;        // 0 ok, else sampler error code
     long long* stats;   // [0] rounds, [1] units, [2] movers, [3..6] CTA-0 clocks in commit / units / draw / barriers,
-                        // [7] carried items drawn again in full (all CTAs)
+                        // [7] low 40 bits: carried items drawn again in full (all CTAs); high bits: discarded tentative commits
     int Wmax;           // ring capacity (items)
     int Wfull;          // steady-state window: units per round = a whole number of grid-wide lane passes
     int Wunit;          // items whose units fill one grid-wide lane pass
     int Wmin;
     int lgT;            // entries of the shared-memory lgamma(k + beta) table
+    int MC;             // tentative commits per round (k_sweep_z / k_sweep_y), 1..MCMAX
 };
 
 // A carried item after the commit (da, db): its draw is a function of e = exp(pl - max) and u alone, and only the
@@ -420,6 +421,99 @@ __device__ __forceinline__ bool draw_recorded_zero(const SweepWork& w, size_t sl
 }
 __device__ __forceinline__ bool draw_still_zero(double mx, double pa, double pb) {
     return dexp(pa - mx) == 0.0 && dexp(pb - mx) == 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------ multi-commit rounds
+// k_sweep_z / k_sweep_y commit SEVERAL movers per grid-wide round.  After the draws of a window, the first M movers
+// (visiting order) become *tentative* commits.  Commit i yields two new table columns ("slots" K + 2i, K + 2i + 1:
+// the old label's column without the item, the new label's column with it); the base columns stay untouched.  An item
+// with q tentative commits in front of it sees, for column j, the slot of the last of those q commits that touched j,
+// else the base column: exactly the table state a sequential sweep would show it if those commits are real.  Its
+// "stale" columns -- the ones touched by the q commits, plus the columns of commits that were discarded in the round
+// before (Dcarry) -- are re-evaluated against those slots and its draw is repeated (or proven unchanged).  An item
+// whose outcome differs from the one recorded in the ring is marked INVALID: every commit in front of the first
+// invalid item stands (all items before it, movers included, reproduced their outcome under exactly the commits in
+// front of them), every commit behind it is discarded, and its columns become Dcarry for the items still in the
+// window.  The first invalid item's new outcome was computed from standing commits only, so it is the true one; the
+// next round starts there.  With M = 1 this is the single-commit schedule; the arithmetic of every unit and every
+// draw is unchanged, so results stay bit-identical to the sequential sweep (scripts/proto_multicommit.py checks the
+// bookkeeping against a sequential sweep on random problems).
+constexpr int MCMAX = 16;           // tentative commits per round, upper bound (SweepWork::MC <= MCMAX)
+constexpr int SPEC_INV = 1 << 30;   // spec ring, movers: the last validation changed this item's outcome
+
+// spec ring encoding: -1 non-mover; (old << 16 | new) mover; invalid marks carry the 3-bit tag of the round that set
+// them (non-mover: -2 - tag; mover: | SPEC_INV | tag << 27), so a mark is honoured by the next round only.
+__device__ __forceinline__ int spec_mark(int v, int tag) { return v < 0 ? -2 - tag : (v | SPEC_INV | (tag << 27)); }
+__device__ __forceinline__ int spec_clean(int v) { return v < 0 ? -1 : (v & 0x03ffffff); }
+__device__ __forceinline__ bool spec_invalid(int v, int tag) {
+    return v < -1 ? (-2 - v) == tag : ((v & SPEC_INV) && ((v >> 27) & 7) == tag);
+}
+
+// Block-wide: smallest c in [0, nwin) whose ring slot carries an invalid mark of round `tag`, or -1.
+__device__ int block_first_invalid(const int* spec, long long pos, int Wmax, int nwin, int tag, int* s_first) {
+    if (threadIdx.x == 0) *s_first = 0x7fffffff;
+    __syncthreads();
+    int best = 0x7fffffff;
+    for (int c0 = threadIdx.x; c0 < nwin && best == 0x7fffffff; c0 += 4 * blockDim.x) {
+        int v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = c0 + k * blockDim.x;
+            v[k] = (c < nwin) ? __ldcg(spec + ((pos + c) & (long long)(Wmax - 1))) : -1;
+        }
+#pragma unroll
+        for (int k = 3; k >= 0; --k)
+            if (spec_invalid(v[k], tag)) best = c0 + k * blockDim.x;
+    }
+    for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best != 0x7fffffff) atomicMin(s_first, best);
+    __syncthreads();
+    const int f = *s_first;
+    __syncthreads();
+    return f == 0x7fffffff ? -1 : f;
+}
+
+// Block-wide ordered compaction: the first (visiting order) <= cap movers among the ring slots of [pos, pos + nwin).
+// out_t[k] = position, out_pk[k] = clean packed (old << 16 | new).  s_tmp: 34 ints.  Returns the number selected.
+__device__ int block_select_movers(const int* spec, long long pos, int Wmax, int nwin, int cap, long long* out_t, int* out_pk,
+                                   int* s_tmp) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    int total = 0;
+    for (int base = 0; base < nwin && total < cap; base += blockDim.x) {
+        const int c = base + threadIdx.x;
+        const int v = (c < nwin) ? __ldcg(spec + ((pos + c) & (long long)(Wmax - 1))) : -1;
+        const bool mover = v >= 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, mover);
+        if (lane == 0) s_tmp[warp] = __popc(bal);
+        __syncthreads();
+        if (warp == 0) {
+            const int cnt = (lane < nwarp) ? s_tmp[lane] : 0;
+            int inc = cnt;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int nb = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += nb;
+            }
+            s_tmp[lane] = inc - cnt;
+            if (lane == 31) s_tmp[32] = inc;
+        }
+        __syncthreads();
+        const int rank = total + s_tmp[warp] + __popc(bal & ((1u << lane) - 1u));
+        if (mover && rank < cap) {
+            out_t[rank] = pos + c;
+            out_pk[rank] = spec_clean(v);
+        }
+        total += s_tmp[32];
+        __syncthreads();
+    }
+    return min(total, cap);
+}
+
+// Tentative commits wanted per round: a round costs a fixed latency (two grid barriers, the scans, one draw) plus
+// patch work that grows with (window x commits); the window itself has to span the commits, so with g items between
+// movers the cost per mover is about F / M + c g (M + 4), smallest near M = sqrt(F / (c g)).
+__device__ __forceinline__ int mc_target(int gavg, int MC) {
+    const int m = (int)sqrtf(48000.0f / (float)max(gavg, 1));
+    return max(1, min(m, MC));
 }
 
 // ------------------------------------------------------------------------------------------------ z sweep
@@ -512,19 +606,36 @@ __device__ __forceinline__ double z_table_rows(const int* xp, long long nM, int 
 
 __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int R = a.R, K = a.K, nS = a.nS, T = a.w.lgT;
-    const int Rp = R | 1;  // odd stride: candidate-major rows, conflict-free across lanes of r
+    if (a.w.status[1]) return;  // the injected visiting order failed its check: nothing may be indexed through it
+    const int R = a.R, K = a.K, nS = a.nS, T = a.w.lgT, MC = a.w.MC;
+    const int KS = K + 2 * MC;  // column slots: K base columns + two per tentative commit
+    const int Rp = R | 1;       // odd stride: candidate-major rows, conflict-free across lanes of r
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int scratchD = max(R, 2 * K + (K + 1) / 2) + 2;
     double* lgtab = reinterpret_cast<double*>(smem_raw);
     double* scratch_all = lgtab + T;
-    long long* nCP_s = reinterpret_cast<long long*>(scratch_all + (size_t)nwarp * scratchD);
-    double* vt_s = reinterpret_cast<double*>(nCP_s + K);  // [EsCap] value table head of this CTA's candidate
-    int* n_s = reinterpret_cast<int*>(vt_s + a.EsCap);
-    int* m_s = n_s + (size_t)K * Rp;
-    int* offg_s = m_s + K * nS;     // [R + 1]
-    int* grp_s = offg_s + R + 1;    // [ZT_MAXGRP + 3]
-    int* s_misc = grp_s + ZT_MAXGRP + 3;  // [0] first mover
+    long long* nCP_s = reinterpret_cast<long long*>(scratch_all + (size_t)nwarp * scratchD);  // [KS]
+    long long* cm_t = nCP_s + KS;                                                             // [MCMAX] positions
+    double* vt_s = reinterpret_cast<double*>(cm_t + MCMAX);  // [EsCap] value table head of this CTA's candidate
+    int* n_s = reinterpret_cast<int*>(vt_s + a.EsCap);       // [KS][Rp]
+    int* m_s = n_s + (size_t)KS * Rp;
+    int* offg_s = m_s + K * nS;           // [R + 1]
+    int* grp_s = offg_s + R + 1;          // [ZT_MAXGRP + 3]
+    int* fin_s = grp_s + ZT_MAXGRP + 3;   // [K] slot of column j with every tentative commit applied
+    int* CL_s = fin_s + K;                // [K] stale-column list: Dcarry first, then the commits' columns in order
+    int* inCL_s = CL_s + K;               // [K]
+    int* dc_s = inCL_s + K;               // [K] Dcarry
+    int* cm_a = dc_s + K;                 // [MCMAX] each: old label, new label, sample, cell total, cell, source slots, packed
+    int* cm_b = cm_a + MCMAX;
+    int* cm_s = cm_b + MCMAX;
+    int* cm_N = cm_s + MCMAX;
+    int* cm_cell = cm_N + MCMAX;
+    int* cm_srcA = cm_cell + MCMAX;
+    int* cm_srcB = cm_srcA + MCMAX;
+    int* cm_pk = cm_srcB + MCMAX;
+    int* nq_s = cm_pk + MCMAX;            // [MCMAX + 1] stale columns of an item with q commits in front
+    int* seg_s = nq_s + MCMAX + 1;        // [MCMAX + 2] patch-unit offsets per segment
+    int* s_misc = seg_s + MCMAX + 2;      // [40]
     double* scr = scratch_all + (size_t)warp * scratchD;
     // Lane-per-unit rounds: a CTA tabulates, for the candidate j it is serving,
     // lgamma(n[r][j] + v + beta) over the counts v that occur in row r, one group of rows at a time (as many rows
@@ -540,100 +651,208 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
     const int gwarpT = warp * gridDim.x + blockIdx.x;
 
     for (int q = threadIdx.x; q < R * K; q += blockDim.x) n_s[(q / R) * Rp + (q % R)] = a.nTab[q];
-    for (int q = threadIdx.x; q < K; q += blockDim.x) nCP_s[q] = a.nCP[q];
+    for (int q = threadIdx.x; q < K; q += blockDim.x) {
+        nCP_s[q] = a.nCP[q];
+        fin_s[q] = q;
+    }
     for (int q = threadIdx.x; q < K * nS; q += blockDim.x) m_s[q] = a.mCPByS[q];
     for (int q = threadIdx.x; q < T; q += blockDim.x) lgtab[q] = dlgamma((double)q + a.beta);
     if (useTab) {
         for (int q = threadIdx.x; q <= R; q += blockDim.x) offg_s[q] = a.offg[q];
         for (int q = threadIdx.x; q < ZT_MAXGRP + 3; q += blockDim.x) grp_s[q] = a.grp[q];
     }
+    if (threadIdx.x <= MCMAX) nq_s[threadIdx.x] = 0;
+    if (threadIdx.x <= MCMAX + 1) seg_s[threadIdx.x] = 0;
     __syncthreads();
 
-    long long pos = 0, hi = 0;
-    int W = a.w.Wfull, nd = K, da = -1, db = -1, gavg = a.w.Wfull;  // nd == K: every column's cached sum is still to be computed
-    bool have_spec = false;
-    long long prev_end = 0;
+    long long pos = 0, hi = 0, prev_end = 0;
+    int W = a.w.Wfull, gavg = a.w.Wfull, M = 0, ndc = 0, mcAimd = MC, par = 0, tagPrev = 0;
+    bool have_spec = false, first = true;
     unsigned bar_target = 0;
-    long long rounds = 0, units_done = 0, movers = 0;
+    long long rounds = 0, units_done = 0, movers = 0, discards = 0;
     long long redraws = 0;  // carried items drawn again in full (this thread's share)
+    int cheapScore = 4, cheapTick = 0;
     long long ck_commit = 0, ck_units = 0, ck_draw = 0, ck_bar = 0, ck0 = clock64(), ck1;
 #define CELDA_TICK(acc) do { ck1 = clock64(); acc += ck1 - ck0; ck0 = ck1; } while (0)
 
+    // slot of column j for an item with q tentative commits in front of it
+    auto slot_of = [&](int q, int j) {
+        for (int i = q - 1; i >= 0; --i) {
+            if (cm_b[i] == j) return K + 2 * i + 1;
+            if (cm_a[i] == j) return K + 2 * i;
+        }
+        return j;
+    };
+    // the per-slot cached sums live in global memory (written by whichever warp evaluated them); the commit slots
+    // alternate between two banks so that a round never overwrites what the next round's first phase still reads
+    auto gslot = [&](int slot, int bank) { return slot < K ? slot : K + bank * 2 * MCMAX + (slot - K); };
+    auto window_for = [&](int g, int mc) -> int {
+        const long long target = (long long)g * (mc + 4);
+        if (target >= a.w.Wunit) return (int)min((target / a.w.Wunit) * a.w.Wunit, (long long)a.w.Wfull);
+        return (int)max((long long)a.w.Wmin, target);
+    };
+
     while (true) {
-        // ---- commit the first mover of the previous window (every CTA updates its own copy of the tables)
+        // ---- settle the previous round: which tentative commits stand, where the window restarts, the next commits
         if (have_spec) {
-            const int nwin = (int)(prev_end - pos);
-            const int first = block_first_mover(a.w.spec, pos, a.w.Wmax, nwin, s_misc);
-            if (first < 0) {
-                pos = prev_end;
-                hi = pos;
-                nd = 0;
-                gavg = min(2 * gavg + nwin, 1 << 24);
-                W = (2 * W <= a.w.Wunit) ? 2 * W : min(max(2 * W / a.w.Wunit, 1) * a.w.Wunit, a.w.Wfull);
-            } else {
-                const long long t = pos + first;
-                const long long i = a.ix[t] - 1;
-                const int packed = __ldcg(a.w.spec + ring_slot(pos + first, a.w.Wmax));
-                da = packed >> 16;
-                db = packed & 0xffff;
-                const int* x = a.counts + i * R;
-                for (int r = threadIdx.x; r < R; r += blockDim.x) {
-                    const int xv = x[r];
-                    n_s[da * Rp + r] -= xv;
-                    n_s[db * Rp + r] += xv;
+            const int nwinPrev = (int)(prev_end - pos);
+            const int f = block_first_invalid(a.w.spec, pos, a.w.Wmax, nwinPrev, tagPrev, s_misc);
+            const long long tf = pos + f;
+            int qf = M;
+            if (f >= 0) {
+                qf = 0;
+                for (int i = 0; i < M; ++i) qf += (cm_t[i] < tf);
+            }
+            // standing commits advance the base columns (in order: a later commit's slot supersedes an earlier one's)
+            for (int r = threadIdx.x; r < R; r += blockDim.x)
+                for (int i = 0; i < qf; ++i) {
+                    n_s[cm_a[i] * Rp + r] = n_s[(K + 2 * i) * Rp + r];
+                    n_s[cm_b[i] * Rp + r] = n_s[(K + 2 * i + 1) * Rp + r];
                 }
-                if (threadIdx.x == 0) {
-                    const int Ni = a.nByC[i], si = a.s[i] - 1;
-                    nCP_s[da] -= Ni;
-                    nCP_s[db] += Ni;
-                    m_s[si * K + da] -= 1;
-                    m_s[si * K + db] += 1;
-                    if (blockIdx.x == 0) a.z[i] = db + 1;
+            if (threadIdx.x == 0) {
+                for (int i = 0; i < qf; ++i) {
+                    const int ca = cm_a[i], cb = cm_b[i];
+                    nCP_s[ca] = nCP_s[K + 2 * i];
+                    nCP_s[cb] = nCP_s[K + 2 * i + 1];
+                    m_s[cm_s[i] * K + ca] -= 1;
+                    m_s[cm_s[i] * K + cb] += 1;
+                    if (blockIdx.x == 0) {
+                        a.z[cm_cell[i]] = cb + 1;
+                        a.w.colsum[ca] = __ldcg(a.w.colsum + gslot(K + 2 * i, par ^ 1));
+                        a.w.lgnCP[ca] = __ldcg(a.w.lgnCP + gslot(K + 2 * i, par ^ 1));
+                        a.w.colsum[cb] = __ldcg(a.w.colsum + gslot(K + 2 * i + 1, par ^ 1));
+                        a.w.lgnCP[cb] = __ldcg(a.w.lgnCP + gslot(K + 2 * i + 1, par ^ 1));
+                    }
                 }
-                ++movers;
-                // gavg: running estimate of the items between movers.  Under churn the window (and with it the
-                // patch + redraw work of every round) shrinks to a few gaps; results already computed beyond it
-                // are dropped and recomputed when the sweep gets there.
-                gavg = max(1, (3 * gavg + first + 1) / 4);
-                W = (4LL * gavg >= a.w.Wunit) ? (int)min((4LL * gavg / a.w.Wunit) * a.w.Wunit, (long long)a.w.Wfull)
-                                              : max(a.w.Wmin, 4 * gavg);
-                pos = t + 1;
-                hi = min(prev_end, pos + W);
-                nd = 2;
-                __syncthreads();
+                int nd_ = 0;  // Dcarry: the columns of the discarded commits
+                for (int i = qf; i < M; ++i)
+                    for (int side = 0; side < 2; ++side) {
+                        const int c = side ? cm_b[i] : cm_a[i];
+                        bool seen = false;
+                        for (int d = 0; d < nd_; ++d) seen |= (dc_s[d] == c);
+                        if (!seen) dc_s[nd_++] = c;
+                    }
+                s_misc[1] = nd_;
+            }
+            const long long oldpos = pos;
+            if (qf < M) pos = tf;  // no unselected mover can lie in front of a discarded selected one
+            else if (M > 0) pos = cm_t[M - 1] + 1;
+            __syncthreads();
+            ndc = s_misc[1];
+            movers += qf;
+            discards += M - qf;
+            if (M > 0) mcAimd = (qf == M) ? min(MC, 2 * mcAimd) : max(1, qf + 1);
+            if (qf > 0) gavg = max(1, (int)((3LL * gavg + max(1LL, (pos - oldpos) / qf)) / 4));
+            int mcCur = min(mcAimd, mc_target(gavg, MC));
+            W = window_for(gavg, mcCur);
+            hi = min(prev_end, pos + W);
+            M = block_select_movers(a.w.spec, pos, a.w.Wmax, (int)(hi - pos), mcCur, cm_t, cm_pk, s_misc + 2);
+            if (M == 0 && ndc == 0) {  // nothing moves and nothing is stale: the carried items are settled
+                gavg = (int)min(2LL * gavg + (hi - pos), (long long)(1 << 24));
+                pos = hi;
+                mcCur = min(mcAimd, mc_target(gavg, MC));
+                W = window_for(gavg, mcCur);
             }
         }
         if (pos >= a.nM) break;
+        // ---- this round's tentative commits: records, source slots, stale-column list, new column slots
+        if (threadIdx.x < M) {
+            const int i = threadIdx.x;
+            const int cell = a.ix[cm_t[i]] - 1, pk = cm_pk[i];
+            cm_cell[i] = cell;
+            cm_a[i] = pk >> 16;
+            cm_b[i] = pk & 0xffff;
+            cm_s[i] = a.s[cell] - 1;
+            cm_N[i] = a.nByC[cell];
+        }
+        for (int j = threadIdx.x; j < K; j += blockDim.x) inCL_s[j] = 0;
+        __syncthreads();
+        if (threadIdx.x < M) {
+            cm_srcA[threadIdx.x] = slot_of(threadIdx.x, cm_a[threadIdx.x]);
+            cm_srcB[threadIdx.x] = slot_of(threadIdx.x, cm_b[threadIdx.x]);
+        }
+        if (threadIdx.x == 32) {
+            int n = 0;
+            for (int d = 0; d < ndc; ++d) {
+                CL_s[n++] = dc_s[d];
+                inCL_s[dc_s[d]] = 1;
+            }
+            nq_s[0] = n;
+            for (int i = 0; i < M; ++i) {
+                if (!inCL_s[cm_a[i]]) {
+                    CL_s[n++] = cm_a[i];
+                    inCL_s[cm_a[i]] = 1;
+                }
+                if (!inCL_s[cm_b[i]]) {
+                    CL_s[n++] = cm_b[i];
+                    inCL_s[cm_b[i]] = 1;
+                }
+                nq_s[i + 1] = n;
+            }
+            // segment q = the carried items with exactly q commits in front: (m_{q-1}, m_q], the last one up to hi
+            long long prevLast = pos - 1;
+            seg_s[0] = 0;
+            for (int q = 0; q <= M; ++q) {
+                const long long last = (q < M) ? cm_t[q] : hi - 1;
+                const long long len = max(0LL, last - prevLast);
+                seg_s[q + 1] = seg_s[q] + (int)len * nq_s[q];
+                prevLast = max(prevLast, last);
+            }
+        }
+        __syncthreads();
+        for (int r = threadIdx.x; r < R; r += blockDim.x) {
+            for (int i = 0; i < M; ++i) {
+                const int xv = __ldg(a.counts + (size_t)cm_cell[i] * R + r);
+                n_s[(K + 2 * i) * Rp + r] = n_s[cm_srcA[i] * Rp + r] - xv;
+                n_s[(K + 2 * i + 1) * Rp + r] = n_s[cm_srcB[i] * Rp + r] + xv;
+            }
+        }
+        if (threadIdx.x == blockDim.x - 1)
+            for (int i = 0; i < M; ++i) {
+                nCP_s[K + 2 * i] = nCP_s[cm_srcA[i]] - cm_N[i];
+                nCP_s[K + 2 * i + 1] = nCP_s[cm_srcB[i]] + cm_N[i];
+            }
+        for (int j = threadIdx.x; j < K; j += blockDim.x) fin_s[j] = slot_of(M, j);
+        __syncthreads();
         CELDA_TICK(ck_commit);
-        // after a commit the window is topped up with fresh items only once it is less than half full: carried items
-        // cost two patch units and a check (draw_unchanged), fresh ones a full evaluation and draw, cheaper in batches
-        const bool topup = nd != 2 || (hi - pos) * 2 < W;
+        // after commits the window is topped up with fresh items only once it is less than half full: carried items
+        // cost a few patch units and a check, fresh ones a full evaluation and draw, cheaper in batches
+        const bool topup = first || (M == 0 && ndc == 0) || (hi - pos) * 2 < W;
         const long long end = topup ? max(hi, min(pos + (long long)W, a.nM)) : hi;
         const int nwin = (int)(end - pos);
-        const long long nPatch = (hi - pos) * (nd == K ? 0 : nd);  // nd == K only on the first round (hi == pos)
+        const int nColU = first ? K : 2 * M;     // cached column sums: every base column once, then the new slots
+        const long long nPatch = seg_s[M + 1];   // stale columns of the carried items
         const long long nFresh = (end - hi) * K;
-        const long long total = nd + nPatch + nFresh;
+        const long long total = nColU + nPatch + nFresh;
+        const int tag = (int)(rounds & 7);
         ++rounds;
         // ---- A1: units.  Large rounds: one LANE per unit (the lane evaluates and adds its unit's terms serially, no
         // staging, no single-lane phases).  Small rounds (churn): one WARP per unit for latency.  Both orders of
         // evaluation are the reference's, so the results are identical.
-        auto decode = [&](long long uidx, long long& t, int& j) {
+        // unit index -> (position t or -1 for a column sum, candidate j, column slot)
+        auto decode = [&](long long uidx, long long& t, int& j, int& slot) {
             t = -1;
-            if (uidx < nd) {
-                j = (nd == K) ? (int)uidx : (uidx == 0 ? da : db);
-            } else if (uidx < nd + nPatch) {
-                const long long q = uidx - nd;
-                t = pos + q / 2;
-                j = (q & 1) ? db : da;
+            if (uidx < nColU) {
+                slot = first ? (int)uidx : K + (int)uidx;
+                j = -1;
+            } else if (uidx < nColU + nPatch) {
+                int rel = (int)(uidx - nColU), q = 0;
+                while (rel >= seg_s[q + 1]) ++q;
+                rel -= seg_s[q];
+                const int wq = nq_s[q];
+                t = ((q == 0) ? pos : cm_t[q - 1] + 1) + rel / wq;
+                j = CL_s[rel % wq];
+                slot = slot_of(q, j);
             } else {
-                const long long q = uidx - nd - nPatch;
+                const long long q = uidx - nColU - nPatch;
                 t = hi + q / K;
                 j = (int)(q % K);
+                slot = fin_s[j];
             }
         };
         // one warp per unit: lanes evaluate the lgamma terms into shared memory, lane 0 adds them serially
-        auto warp_unit = [&](long long t, int j) {
-            const int* ncol = n_s + j * Rp;
+        auto warp_unit = [&](long long t, int j, int slot) {
+            const int* ncol = n_s + slot * Rp;
             if (t < 0) {
                 for (int r = lane; r < R; r += 32) scr[r] = lg_tab2(lgtab, T, a.lgG, a.TG, ncol[r], a.beta);
                 __syncwarp();
@@ -641,8 +860,8 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                     double S = 0.0;
 #pragma unroll 8
                     for (int r = 0; r < R; ++r) S += scr[r];  // loads run ahead of the serial adds
-                    a.w.colsum[j] = S;
-                    a.w.lgnCP[j] = dlgamma((double)nCP_s[j] + Rbeta);
+                    a.w.colsum[gslot(slot, par)] = S;
+                    a.w.lgnCP[gslot(slot, par)] = dlgamma((double)nCP_s[slot] + Rbeta);
                 }
                 __syncwarp();
             } else {
@@ -658,19 +877,50 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                     for (int r = 0; r < R; ++r) S += scr[r];  // loads run ahead of the serial adds
                     const size_t o = ring_slot(t, a.w.Wmax) * K + j;
                     a.w.bufP[o] = S;
-                    a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
+                    a.w.bufA[o] = dlgamma_hot((double)(nCP_s[slot] + (long long)sgn * a.nByC[i]) + Rbeta);
                 }
                 __syncwarp();
             }
         };
+        // one lane per unit, direct evaluation
+        auto lane_unit = [&](long long t, int j, int slot) {
+            const int* ncol = n_s + slot * Rp;
+            if (t < 0) {
+                double S = 0.0;
+                for (int r = 0; r < R; ++r) S += lg_tab2(lgtab, T, a.lgG, a.TG, ncol[r], a.beta);
+                a.w.colsum[gslot(slot, par)] = S;
+                a.w.lgnCP[gslot(slot, par)] = dlgamma((double)nCP_s[slot] + Rbeta);
+            } else {
+                const long long i = a.ix[t] - 1;
+                const int zi = a.z[i] - 1;
+                const int sgn = (j == zi) ? -1 : 1;
+                const int* x = a.counts + i * R;
+                double S = 0.0;
+#pragma unroll 2
+                for (int r = 0; r < R; ++r) S += lg_tab2(lgtab, T, a.lgG, a.TG, (long long)ncol[r] + sgn * __ldg(x + r), a.beta);
+                const size_t o = ring_slot(t, a.w.Wmax) * K + j;
+                a.w.bufP[o] = S;
+                a.w.bufA[o] = dlgamma_hot((double)(nCP_s[slot] + (long long)sgn * a.nByC[i]) + Rbeta);
+            }
+        };
         const bool bigRound = total >= (long long)tw * 16;
         if (bigRound && useTab) {
-            // (1) cached column sums and patch units: few, one warp each
-            for (long long uidx = gwarpT; uidx < nd + nPatch; uidx += tw) {
-                int j;
-                long long t;
-                decode(uidx, t, j);
-                warp_unit(t, j);
+            // (1) cached column sums and patch units: one warp each while they are few, else one lane each
+            const long long nSmall = nColU + nPatch;
+            if (nSmall < (long long)tw * 8) {
+                for (long long uidx = gwarpT; uidx < nSmall; uidx += tw) {
+                    int j, slot;
+                    long long t;
+                    decode(uidx, t, j, slot);
+                    warp_unit(t, j, slot);
+                }
+            } else {
+                for (long long uidx = (long long)gwarp * 32 + lane; uidx < nSmall; uidx += (long long)tw * 32) {
+                    int j, slot;
+                    long long t;
+                    decode(uidx, t, j, slot);
+                    lane_unit(t, j, slot);
+                }
             }
             const long long nFreshCells = end - hi;
             // (1b) this round's value tables, every entry once: vtg[j][e] = lgamma(n[r][j] + v + beta) for the e-th
@@ -686,7 +936,8 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                         const int mid = (lo + hiR) >> 1;
                         if (offg_s[mid] <= e) lo = mid; else hiR = mid;
                     }
-                    a.vtg[(size_t)j * a.vtStride + e] = lg_tab2(lgtab, T, a.lgG, a.TG, (long long)n_s[j * Rp + lo] + (e - offg_s[lo]), a.beta);
+                    a.vtg[(size_t)j * a.vtStride + e] =
+                        lg_tab2(lgtab, T, a.lgG, a.TG, (long long)n_s[fin_s[j] * Rp + lo] + (e - offg_s[lo]), a.beta);
                 }
                 grid_sync(a.w.barrier, bar_target);
             }
@@ -704,7 +955,8 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                     const long long segEnd = min(c1, (long long)(j + 1) * nchunk);
                     const long long chLo = cs - (long long)j * nchunk, chHi = segEnd - (long long)j * nchunk;
                     cs = segEnd;
-                    const int* ncol = n_s + j * Rp;
+                    const int* ncol = n_s + fin_s[j] * Rp;
+                    const long long nCPj = nCP_s[fin_s[j]];
                     for (int gI = 0; gI < ngrp; ++gI) {
                         const int r0 = grp_s[1 + gI], r1 = grp_s[2 + gI];
                         const int e0 = offg_s[r0], ne = offg_s[r1] - e0;
@@ -739,7 +991,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                                          : z_table_rows<true>(xp, a.nM, r0, r1, offg_s, e0, vt_s, ncol, lgtab, T, a.beta, S);
                             a.w.bufP[o] = S;
                             if (gI == ngrp - 1)
-                                a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)__ldg(a.nT + t)) + Rbeta);
+                                a.w.bufA[o] = dlgamma_hot((double)(nCPj + (long long)__ldg(a.nT + t)) + Rbeta);
                         }
                     }
                 }
@@ -747,57 +999,56 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
             // (3) each fresh cell against its own population (counts removed): direct evaluation, one warp each
             for (long long q = gwarpT; q < nFreshCells; q += tw) {
                 const long long t = hi + q;
-                warp_unit(t, a.z[a.ix[t] - 1] - 1);
+                const int zi = a.z[a.ix[t] - 1] - 1;
+                warp_unit(t, zi, fin_s[zi]);
             }
         } else if (bigRound) {
             for (long long uidx = (long long)gwarp * 32 + lane; uidx < total; uidx += (long long)tw * 32) {
-                int j;
+                int j, slot;
                 long long t;
-                decode(uidx, t, j);
-                const int* ncol = n_s + j * Rp;
-                if (t < 0) {
-                    double S = 0.0;
-                    for (int r = 0; r < R; ++r) S += lg_tab2(lgtab, T, a.lgG, a.TG, ncol[r], a.beta);
-                    a.w.colsum[j] = S;
-                    a.w.lgnCP[j] = dlgamma((double)nCP_s[j] + Rbeta);
-                } else {
-                    const long long i = a.ix[t] - 1;
-                    const int zi = a.z[i] - 1;
-                    const int sgn = (j == zi) ? -1 : 1;
-                    const int* x = a.counts + i * R;
-                    double S = 0.0;
-#pragma unroll 2
-                    for (int r = 0; r < R; ++r) S += lg_tab2(lgtab, T, a.lgG, a.TG, (long long)ncol[r] + sgn * __ldg(x + r), a.beta);
-                    const size_t o = ring_slot(t, a.w.Wmax) * K + j;
-                    a.w.bufP[o] = S;
-                    a.w.bufA[o] = dlgamma_hot((double)(nCP_s[j] + (long long)sgn * a.nByC[i]) + Rbeta);
-                }
+                decode(uidx, t, j, slot);
+                lane_unit(t, j, slot);
             }
         } else {
             for (long long uidx = gwarpT; uidx < total; uidx += tw) {
-                int j;
+                int j, slot;
                 long long t;
-                decode(uidx, t, j);
-                warp_unit(t, j);
+                decode(uidx, t, j, slot);
+                warp_unit(t, j, slot);
             }
         }
         units_done += total;
         CELDA_TICK(ck_units);
         grid_sync(a.w.barrier, bar_target);
         CELDA_TICK(ck_bar);
-        // ---- A2: combine in the reference's order, draw
+        // ---- A2: combine in the reference's order, draw / validate
         double* pl = scr;
         double* rr = scr + K;
         int* perm = reinterpret_cast<int*>(scr + 2 * K);
-        for (int c = gwarpT; c < nwin; c += tw) {
+        // carried items in front of the first tentative commit have nothing stale unless commits were discarded
+        const int cstart = (ndc > 0 || M == 0) ? 0 : (int)(cm_t[0] + 1 - pos);
+        for (int c = cstart + gwarpT; c < nwin; c += tw) {
             const long long t = pos + c;
+            const bool fresh = t >= hi;
+            int q = M;
+            if (!fresh) {
+                q = 0;
+                for (int i = 0; i < M; ++i) q += (cm_t[i] < t);
+            }
+            const int ncols = fresh ? K : nq_s[q];
+            if (ncols == 0) continue;
             const long long i = a.ix[t] - 1;
             const int zi = a.z[i] - 1, si = a.s[i] - 1;
             const size_t slot = ring_slot(t, a.w.Wmax), o = slot * K;
+            const int oldv = fresh ? -1 : __ldcg(a.w.spec + slot);
             auto combine = [&](int j) {
+                const int g = gslot(slot_of(q, j), par);
                 const double S = __ldcg(a.w.bufP + o + j), A = __ldcg(a.w.bufA + o + j);
-                const double cs = __ldcg(a.w.colsum + j), lc = __ldcg(a.w.lgnCP + j);
-                double p = dlog((double)(m_s[si * K + j] - (j == zi)) + a.alpha);
+                const double cs = __ldcg(a.w.colsum + g), lc = __ldcg(a.w.lgnCP + g);
+                int mm = m_s[si * K + j] - (j == zi);
+                for (int e = 0; e < q; ++e)
+                    if (cm_s[e] == si) mm += (cm_b[e] == j) - (cm_a[e] == j);
+                double p = dlog((double)mm + a.alpha);
                 if (j != zi) {
                     p = p + S;
                     p = p - A;
@@ -811,18 +1062,34 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                 }
                 return p;
             };
-            double mxOld;
-            if (a.doSample && nd == 2 && t < hi && gavg >= 32 && draw_recorded_zero(a.w, slot, da, db, mxOld)) {
-                const double pa = combine(da), pb = combine(db);
-                if (draw_still_zero(mxOld, pa, pb)) {  // carried over the commit (da, db) with an unchanged draw
-                    if (a.probs && lane == 0) {
-                        a.probs[i * K + da] = pa;
-                        a.probs[i * K + db] = pb;
+            // A carried item's draw is a function of e = exp(p - max) and u alone.  If every stale column had e == 0 at the
+            // item's last draw (none is among its recorded positive entries) and still has, the vector e is bit-identical
+            // and the recorded outcome stands.  Tried while it keeps succeeding (a failed test only adds latency).
+            if (!fresh && a.doSample && ncols <= 32 && (cheapScore > 0 || ((++cheapTick) & 15) == 0)) {
+                const int4 nz = __ldcg(reinterpret_cast<const int4*>(a.w.drawNz) + slot);
+                bool ok = nz.x != -2;
+                if (ok) {
+                    const double mxOld = __ldcg(a.w.drawMx + slot);
+                    const int cj = (lane < ncols) ? CL_s[lane] : -1;
+                    bool mine = true;
+                    double p = 0.0;
+                    if (cj >= 0) {
+                        mine = !(nz.x == cj || nz.y == cj || nz.z == cj || nz.w == cj);
+                        if (mine) {
+                            p = combine(cj);
+                            mine = dexp(p - mxOld) == 0.0;
+                        }
                     }
-                    continue;
+                    ok = __all_sync(0xffffffffu, mine);
+                    if (ok) {
+                        if (a.probs && cj >= 0) a.probs[i * K + cj] = p;
+                        if (lane == 0 && oldv != spec_clean(oldv)) a.w.spec[slot] = spec_clean(oldv);
+                    }
                 }
+                cheapScore = ok ? min(8, cheapScore + 1) : max(0, cheapScore - 1);
+                if (ok) continue;
             }
-            if (lane == 0 && nd == 2 && t < hi) ++redraws;
+            if (lane == 0 && !fresh) ++redraws;
             for (int j = lane; j < K; j += 32) {
                 const double p = combine(j);
                 pl[j] = p;
@@ -843,11 +1110,17 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                     reinterpret_cast<int4*>(a.w.drawNz)[slot] = nz;
                 }
             }
-            if (lane == 0) a.w.spec[slot] = (znew != zi) ? ((zi << 16) | znew) : -1;
+            if (lane == 0) {
+                const int newv = (znew != zi) ? ((zi << 16) | znew) : -1;
+                a.w.spec[slot] = (fresh || newv == spec_clean(oldv)) ? newv : spec_mark(newv, tag);
+            }
             __syncwarp();
         }
         prev_end = end;
         have_spec = true;
+        first = false;
+        tagPrev = tag;
+        par ^= 1;
         CELDA_TICK(ck_draw);
         grid_sync(a.w.barrier, bar_target);
         CELDA_TICK(ck_bar);
@@ -862,6 +1135,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
             a.w.stats[0] += rounds;
             a.w.stats[1] += units_done;
             a.w.stats[2] += movers;
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.w.stats + 7), (unsigned long long)discards << 40);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -872,11 +1146,12 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
     }
 }
 
-inline size_t z_sweep_smem(int R, int K, int nS, int T, int nwarp, int EsCap = 0) {
-    const int Rp = R | 1;
+inline size_t z_sweep_smem(int R, int K, int nS, int T, int nwarp, int EsCap = 0, int MC = MCMAX) {
+    const int Rp = R | 1, KS = K + 2 * MC;
     const size_t scratchD = (size_t)std::max(R, 2 * K + (K + 1) / 2) + 2;
-    return sizeof(double) * (T + nwarp * scratchD + EsCap) + sizeof(long long) * K +
-           sizeof(int) * ((size_t)K * Rp + K * nS + (R + 1) + ZT_MAXGRP + 3 + 4);
+    return sizeof(double) * (T + nwarp * scratchD + EsCap) + sizeof(long long) * (KS + MCMAX) +
+           sizeof(int) * ((size_t)KS * Rp + K * nS + (R + 1) + ZT_MAXGRP + 3 + 4 * (size_t)K + 8 * MCMAX + (MCMAX + 1) +
+                          (MCMAX + 2) + 40);
 }
 
 // xT[r][t] = counts[r, ix[t] - 1]: the count matrix in visiting order, transposed, so that lanes holding
@@ -886,8 +1161,9 @@ inline size_t z_sweep_smem(int R, int K, int nS, int T, int nwarp, int EsCap = 0
 __global__ void k_permute_transpose(const int* __restrict__ counts, int R, int RC, long long nM, const int* __restrict__ ix,
                                     int* __restrict__ xT, int* __restrict__ rowMax /* [R], zeroed */,
                                     const int* __restrict__ z, const int* __restrict__ nByC, int* __restrict__ zT,
-                                    int* __restrict__ nT) {
+                                    int* __restrict__ nT, const int* __restrict__ status) {
     extern __shared__ int pt_smem[];
+    if (status[1]) return;  // bad visiting order (see chain_upload_order)
     const int RCp = RC | 1;
     int* tile = pt_smem;             // [32][RCp]
     int* bmax = pt_smem + 32 * RCp;  // [RC]
@@ -997,18 +1273,34 @@ __global__ void k_lgG_fill(double beta, long long n, double* __restrict__ out) {
 
 __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int L = a.L, C = a.ncol, T = a.w.lgT;
+    if (a.w.status[1]) return;  // the injected visiting order failed its check: nothing may be indexed through it
+    const int L = a.L, C = a.ncol, T = a.w.lgT, MC = a.w.MC;
+    const int LS = L + 2 * MC;  // row slots: L base rows + two per tentative commit (see "multi-commit rounds")
     const int Cp = C | 1;
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int scratchD = max(2 * C + 8, 2 * L + (L + 1) / 2) + 2;
     double* lgtab = reinterpret_cast<double*>(smem_raw);
-    double* lgt_s = lgtab + T;                          // [L][Cp] lgamma(t + beta)
-    double* tail_s = lgt_s + (size_t)L * Cp;             // [L][7] module-only terms of the second loop
-    double* scratch_all = tail_s + (size_t)L * 7;
-    long long* T_s = reinterpret_cast<long long*>(scratch_all + (size_t)nwarp * scratchD);
-    int* t_s = reinterpret_cast<int*>(T_s + L);         // [L][Cp]
-    int* g_s = t_s + (size_t)L * Cp;
-    int* s_misc = g_s + L;
+    double* lgt_s = lgtab + T;                           // [LS][Cp] lgamma(t + beta)
+    double* tail_s = lgt_s + (size_t)LS * Cp;            // [LS][7] module-only terms of the second loop
+    double* scratch_all = tail_s + (size_t)LS * 7;
+    long long* T_s = reinterpret_cast<long long*>(scratch_all + (size_t)nwarp * scratchD);  // [LS]
+    long long* cm_t = T_s + LS;                          // [MCMAX] positions of the tentative commits
+    long long* cm_N = cm_t + MCMAX;                      // [MCMAX] their gene totals
+    int* t_s = reinterpret_cast<int*>(cm_N + MCMAX);     // [LS][Cp]
+    int* g_s = t_s + (size_t)LS * Cp;                    // [LS]
+    int* fin_s = g_s + LS;                               // [L] slot of row l with every tentative commit applied
+    int* CL_s = fin_s + L;                               // [L] stale-row list: Dcarry first, then the commits' rows in order
+    int* inCL_s = CL_s + L;                              // [L]
+    int* dc_s = inCL_s + L;                              // [L] Dcarry
+    int* cm_a = dc_s + L;                                // [MCMAX] each
+    int* cm_b = cm_a + MCMAX;
+    int* cm_gene = cm_b + MCMAX;
+    int* cm_srcA = cm_gene + MCMAX;
+    int* cm_srcB = cm_srcA + MCMAX;
+    int* cm_pk = cm_srcB + MCMAX;
+    int* nq_s = cm_pk + MCMAX;                           // [MCMAX + 1]
+    int* seg_s = nq_s + MCMAX + 1;                       // [MCMAX + 2]
+    int* s_misc = seg_s + MCMAX + 2;                     // [40]
     double* scr = scratch_all + (size_t)warp * scratchD;
     const int gwarp = blockIdx.x * nwarp + warp, tw = gridDim.x * nwarp;
     // warp-granular work goes round the CTAs first (item c -> CTA c mod grid), so a short list of items lands on
@@ -1020,16 +1312,19 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
     for (int q = threadIdx.x; q < L; q += blockDim.x) {
         T_s[q] = a.nByTS[q];
         g_s[q] = a.nGByTS[q];
+        fin_s[q] = q;
     }
+    if (threadIdx.x <= MCMAX) nq_s[threadIdx.x] = 0;
+    if (threadIdx.x <= MCMAX + 1) seg_s[threadIdx.x] = 0;
     __syncthreads();
     for (int q = threadIdx.x; q < L * C; q += blockDim.x) {
         const int l = q / C, c = q % C;
         lgt_s[l * Cp + c] = lg_tab2(lgtab, T, a.lgG, a.TG, t_s[l * Cp + c], a.beta);
     }
-    __syncthreads();
-    // Module-only terms of cG_CalcGibbsProbY's second loop (:230-246), cached per module and refreshed when a
-    // gene enters or leaves it: lgamma(g-1+gamma), (g+gamma), (g+1+gamma), ((g-1) delta), (g delta), ((g+1) delta),
-    // (T + g delta) -- the same expressions the per-unit code evaluated, so the values are identical.
+    // Module-only terms of cG_CalcGibbsProbY's second loop (:230-246), cached per row slot:
+    // lgamma(g-1+gamma), (g+gamma), (g+1+gamma), ((g-1) delta), (g delta), ((g+1) delta), (T + g delta) -- the same
+    // expressions the per-unit code evaluates, so the values are identical.  lg_delta[0] is NA in the reference
+    // (R/celda_CG.R:429): dlgdelta() returns NaN there and the draw reports "NA in probability vector".
     auto tail_fill = [&](int l, int k) {
         const int g = g_s[l];
         double v;
@@ -1037,107 +1332,209 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
             case 0: v = dlgamma_hot((double)(g - 1) + a.gamma); break;
             case 1: v = dlgamma_hot((double)g + a.gamma); break;
             case 2: v = dlgamma_hot((double)(g + 1) + a.gamma); break;
-            case 3: v = dlgamma_hot((double)(g - 1) * a.delta); break;
-            case 4: v = dlgamma_hot((double)g * a.delta); break;
-            case 5: v = dlgamma_hot((double)(g + 1) * a.delta); break;
+            case 3: v = dlgdelta(g - 1, a.delta); break;
+            case 4: v = dlgdelta(g, a.delta); break;
+            case 5: v = dlgdelta(g + 1, a.delta); break;
             default: v = dlgamma_hot((double)T_s[l] + (double)g * a.delta); break;
         }
         tail_s[l * 7 + k] = v;
     };
     for (int q = threadIdx.x; q < L * 7; q += blockDim.x) tail_fill(q / 7, q % 7);
-    bool tail_stale = false;
     __syncthreads();
 
     long long pos = 0, hi = 0, prev_end = 0;
-    int W = a.w.Wfull, nd = 0, da = -1, db = -1, gavg = a.w.Wfull;
-    bool have_spec = false;
+    int W = a.w.Wfull, gavg = a.w.Wfull, M = 0, ndc = 0, mcAimd = MC, tagPrev = 0;
+    bool have_spec = false, first = true;
     unsigned bar_target = 0;
-    long long rounds = 0, units_done = 0, movers = 0;
+    long long rounds = 0, units_done = 0, movers = 0, discards = 0;
     long long redraws = 0;  // carried items drawn again in full (this thread's share)
+    int cheapScore = 4, cheapTick = 0;
     long long ck_commit = 0, ck_units = 0, ck_draw = 0, ck_bar = 0, ck0 = clock64(), ck1;
 
+    // slot of row l for an item with q tentative commits in front of it
+    auto slot_of = [&](int q, int l) {
+        for (int i = q - 1; i >= 0; --i) {
+            if (cm_b[i] == l) return L + 2 * i + 1;
+            if (cm_a[i] == l) return L + 2 * i;
+        }
+        return l;
+    };
+    auto window_for = [&](int g, int mc) -> int {
+        const long long target = (long long)g * (mc + 4);
+        if (target >= a.w.Wunit) return (int)min((target / a.w.Wunit) * a.w.Wunit, (long long)a.w.Wfull);
+        return (int)max((long long)a.w.Wmin, target);
+    };
+
     while (true) {
+        // ---- settle the previous round: which tentative commits stand, where the window restarts, the next commits
         if (have_spec) {
-            const int nwin = (int)(prev_end - pos);
-            const int first = block_first_mover(a.w.spec, pos, a.w.Wmax, nwin, s_misc);
-            if (first < 0) {
-                pos = prev_end;
-                hi = pos;
-                nd = 0;
-                gavg = min(2 * gavg + nwin, 1 << 24);
-                W = (2 * W <= a.w.Wunit) ? 2 * W : min(max(2 * W / a.w.Wunit, 1) * a.w.Wunit, a.w.Wfull);
-            } else {
-                const long long t = pos + first;
-                const int i = a.ix[t] - 1;
-                const int packed = __ldcg(a.w.spec + ring_slot(pos + first, a.w.Wmax));
-                da = packed >> 16;
-                db = packed & 0xffff;
-                const int* x = a.counts + (size_t)i * C;
-                for (int c = threadIdx.x; c < C; c += blockDim.x) {
-                    const int xv = x[c];
-                    t_s[da * Cp + c] -= xv;
-                    t_s[db * Cp + c] += xv;
-                    lgt_s[da * Cp + c] = lg_tab2(lgtab, T, a.lgG, a.TG, t_s[da * Cp + c], a.beta);
-                    lgt_s[db * Cp + c] = lg_tab2(lgtab, T, a.lgG, a.TG, t_s[db * Cp + c], a.beta);
+            const int nwinPrev = (int)(prev_end - pos);
+            const int f = block_first_invalid(a.w.spec, pos, a.w.Wmax, nwinPrev, tagPrev, s_misc);
+            const long long tf = pos + f;
+            int qf = M;
+            if (f >= 0) {
+                qf = 0;
+                for (int i = 0; i < M; ++i) qf += (cm_t[i] < tf);
+            }
+            // standing commits advance the base rows (in order: a later commit's slot supersedes an earlier one's)
+            for (int c = threadIdx.x; c < C + 7; c += blockDim.x)
+                for (int i = 0; i < qf; ++i)
+                    for (int side = 0; side < 2; ++side) {
+                        const int dst = side ? cm_b[i] : cm_a[i], src = L + 2 * i + side;
+                        if (c < C) {
+                            t_s[dst * Cp + c] = t_s[src * Cp + c];
+                            lgt_s[dst * Cp + c] = lgt_s[src * Cp + c];
+                        } else {
+                            tail_s[dst * 7 + (c - C)] = tail_s[src * 7 + (c - C)];
+                        }
+                    }
+            if (threadIdx.x == blockDim.x - 1) {
+                for (int i = 0; i < qf; ++i) {
+                    const int ca = cm_a[i], cb = cm_b[i];
+                    g_s[ca] = g_s[L + 2 * i];
+                    g_s[cb] = g_s[L + 2 * i + 1];
+                    T_s[ca] = T_s[L + 2 * i];
+                    T_s[cb] = T_s[L + 2 * i + 1];
+                    if (blockIdx.x == 0) a.y[cm_gene[i]] = cb + 1;
                 }
-                if (threadIdx.x == 0) {
-                    const long long Ni = a.nByG[i];
-                    g_s[da] -= 1;
-                    g_s[db] += 1;
-                    T_s[da] -= Ni;
-                    T_s[db] += Ni;
-                    if (blockIdx.x == 0) a.y[i] = db + 1;
-                }
-                tail_stale = true;  // the cached module terms are refreshed lazily, before the next lane-per-unit round
-                ++movers;
-                // gavg: running estimate of the items between movers.  Under churn the window (and with it the
-                // patch + redraw work of every round) shrinks to a few gaps; results already computed beyond it
-                // are dropped and recomputed when the sweep gets there.
-                gavg = max(1, (3 * gavg + first + 1) / 4);
-                W = (4LL * gavg >= a.w.Wunit) ? (int)min((4LL * gavg / a.w.Wunit) * a.w.Wunit, (long long)a.w.Wfull)
-                                              : max(a.w.Wmin, 4 * gavg);
-                pos = t + 1;
-                hi = min(prev_end, pos + W);
-                nd = 2;
-                __syncthreads();
+                int nd_ = 0;  // Dcarry: the rows of the discarded commits
+                for (int i = qf; i < M; ++i)
+                    for (int side = 0; side < 2; ++side) {
+                        const int c = side ? cm_b[i] : cm_a[i];
+                        bool seen = false;
+                        for (int d = 0; d < nd_; ++d) seen |= (dc_s[d] == c);
+                        if (!seen) dc_s[nd_++] = c;
+                    }
+                s_misc[1] = nd_;
+            }
+            const long long oldpos = pos;
+            if (qf < M) pos = tf;  // no unselected mover can lie in front of a discarded selected one
+            else if (M > 0) pos = cm_t[M - 1] + 1;
+            __syncthreads();
+            ndc = s_misc[1];
+            movers += qf;
+            discards += M - qf;
+            if (M > 0) mcAimd = (qf == M) ? min(MC, 2 * mcAimd) : max(1, qf + 1);
+            if (qf > 0) gavg = max(1, (int)((3LL * gavg + max(1LL, (pos - oldpos) / qf)) / 4));
+            int mcCur = min(mcAimd, mc_target(gavg, MC));
+            W = window_for(gavg, mcCur);
+            hi = min(prev_end, pos + W);
+            M = block_select_movers(a.w.spec, pos, a.w.Wmax, (int)(hi - pos), mcCur, cm_t, cm_pk, s_misc + 2);
+            if (M == 0 && ndc == 0) {  // nothing moves and nothing is stale: the carried items are settled
+                gavg = (int)min(2LL * gavg + (hi - pos), (long long)(1 << 24));
+                pos = hi;
+                mcCur = min(mcAimd, mc_target(gavg, MC));
+                W = window_for(gavg, mcCur);
             }
         }
         if (pos >= a.nG) break;
+        // ---- this round's tentative commits: records, source slots, stale-row list, new row slots
+        if (threadIdx.x < M) {
+            const int i = threadIdx.x;
+            const int gene = a.ix[cm_t[i]] - 1, pk = cm_pk[i];
+            cm_gene[i] = gene;
+            cm_a[i] = pk >> 16;
+            cm_b[i] = pk & 0xffff;
+            cm_N[i] = a.nByG[gene];
+        }
+        for (int j = threadIdx.x; j < L; j += blockDim.x) inCL_s[j] = 0;
+        __syncthreads();
+        if (threadIdx.x < M) {
+            cm_srcA[threadIdx.x] = slot_of(threadIdx.x, cm_a[threadIdx.x]);
+            cm_srcB[threadIdx.x] = slot_of(threadIdx.x, cm_b[threadIdx.x]);
+        }
+        if (threadIdx.x == 32) {
+            int n = 0;
+            for (int d = 0; d < ndc; ++d) {
+                CL_s[n++] = dc_s[d];
+                inCL_s[dc_s[d]] = 1;
+            }
+            nq_s[0] = n;
+            for (int i = 0; i < M; ++i) {
+                if (!inCL_s[cm_a[i]]) {
+                    CL_s[n++] = cm_a[i];
+                    inCL_s[cm_a[i]] = 1;
+                }
+                if (!inCL_s[cm_b[i]]) {
+                    CL_s[n++] = cm_b[i];
+                    inCL_s[cm_b[i]] = 1;
+                }
+                nq_s[i + 1] = n;
+            }
+            long long prevLast = pos - 1;
+            seg_s[0] = 0;
+            for (int q = 0; q <= M; ++q) {
+                const long long last = (q < M) ? cm_t[q] : hi - 1;
+                const long long len = max(0LL, last - prevLast);
+                seg_s[q + 1] = seg_s[q] + (int)len * nq_s[q];
+                prevLast = max(prevLast, last);
+            }
+        }
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            for (int i = 0; i < M; ++i) {
+                const int xv = __ldg(a.counts + (size_t)cm_gene[i] * C + c);
+                t_s[(L + 2 * i) * Cp + c] = t_s[cm_srcA[i] * Cp + c] - xv;
+                t_s[(L + 2 * i + 1) * Cp + c] = t_s[cm_srcB[i] * Cp + c] + xv;
+            }
+        }
+        if (threadIdx.x == blockDim.x - 1)
+            for (int i = 0; i < M; ++i) {
+                g_s[L + 2 * i] = g_s[cm_srcA[i]] - 1;
+                g_s[L + 2 * i + 1] = g_s[cm_srcB[i]] + 1;
+                T_s[L + 2 * i] = T_s[cm_srcA[i]] - cm_N[i];
+                T_s[L + 2 * i + 1] = T_s[cm_srcB[i]] + cm_N[i];
+            }
+        for (int j = threadIdx.x; j < L; j += blockDim.x) fin_s[j] = slot_of(M, j);
+        __syncthreads();
+        for (int q = threadIdx.x; q < 2 * M * (C + 7); q += blockDim.x) {
+            const int sl = L + q / (C + 7), c = q % (C + 7);
+            if (c < C)
+                lgt_s[sl * Cp + c] = lg_tab2(lgtab, T, a.lgG, a.TG, t_s[sl * Cp + c], a.beta);
+            else
+                tail_fill(sl, c - C);
+        }
+        __syncthreads();
         CELDA_TICK(ck_commit);
-        // after a commit the window is topped up with fresh items only once it is less than half full: carried items
-        // cost two patch units and a check (draw_unchanged), fresh ones a full evaluation and draw, cheaper in batches
-        const bool topup = nd != 2 || (hi - pos) * 2 < W;
+        // after commits the window is topped up with fresh items only once it is less than half full: carried items
+        // cost a few patch units and a check, fresh ones a full evaluation and draw, cheaper in batches
+        const bool topup = first || (M == 0 && ndc == 0) || (hi - pos) * 2 < W;
         const long long end = topup ? max(hi, min(pos + (long long)W, (long long)a.nG)) : hi;
         const int nwin = (int)(end - pos);
-        const long long nPatch = (hi - pos) * nd;
+        const long long nPatch = seg_s[M + 1];
         const long long nFresh = (end - hi) * L;
         const long long total = nPatch + nFresh;
+        const int tag = (int)(rounds & 7);
         ++rounds;
-        if (total >= (long long)tw * 16) {
-            if (tail_stale) {
-                __syncthreads();
-                for (int q = threadIdx.x; q < L * 7; q += blockDim.x) tail_fill(q / 7, q % 7);
-                tail_stale = false;
-                __syncthreads();
+        // unit index -> (position t, module l, row slot)
+        auto decode = [&](long long uidx, long long& t, int& l, int& slot) {
+            if (uidx < nPatch) {
+                int rel = (int)uidx, q = 0;
+                while (rel >= seg_s[q + 1]) ++q;
+                rel -= seg_s[q];
+                const int wq = nq_s[q];
+                t = ((q == 0) ? pos : cm_t[q - 1] + 1) + rel / wq;
+                l = CL_s[rel % wq];
+                slot = slot_of(q, l);
+            } else {
+                const long long q = uidx - nPatch;
+                t = hi + q / L;
+                l = (int)(q % L);
+                slot = fin_s[l];
             }
+        };
+        if (total >= (long long)tw * 16) {
             // one lane per (gene, module) unit: the whole cG_CalcGibbsProbY term sequence in one thread
             for (long long uidx = (long long)gwarp * 32 + lane; uidx < total; uidx += (long long)tw * 32) {
                 long long t;
-                int l;
-                if (uidx < nPatch) {
-                    t = pos + uidx / 2;
-                    l = (uidx & 1) ? db : da;
-                } else {
-                    const long long q = uidx - nPatch;
-                    t = hi + q / L;
-                    l = (int)(q % L);
-                }
+                int l, slot;
+                decode(uidx, t, l, slot);
                 const int i = a.ix[t] - 1;
                 const int cur = a.y[i] - 1;
                 const bool isCur = (l == cur);
                 const int* x = a.counts + (size_t)i * C;
-                const int* trow = t_s + l * Cp;
-                const double* lrow = lgt_s + l * Cp;
+                const int* trow = t_s + slot * Cp;
+                const double* lrow = lgt_s + slot * Cp;
                 double p = 0.0;
                 const int sgn = isCur ? -1 : 1;
 #pragma unroll 2
@@ -1158,12 +1555,12 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                     p += isCur ? cached : fresh;
                     p -= isCur ? fresh : cached;
                 }
-                const int g = g_s[l];
-                const double Tl = (double)T_s[l], Ni = (double)a.nByG[i];
+                const int g = g_s[slot];
+                const double Tl = (double)T_s[slot], Ni = (double)a.nByG[i];
                 {
                     // second loop of cG_CalcGibbsProbY (:230-246); (g0, g1) = (g, g-1) for the current module else
                     // (g+1, g): five of the six terms depend on the module only and come from the cache
-                    const double* tl = tail_s + l * 7;
+                    const double* tl = tail_s + slot * 7;
                     const int g1 = isCur ? g - 1 : g, g0 = g1 + 1;
                     p += tl[isCur ? 1 : 2];
                     p -= tl[isCur ? 0 : 1];
@@ -1177,21 +1574,14 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
         } else {
             for (long long uidx = gwarpT; uidx < total; uidx += tw) {
                 long long t;
-                int l;
-                if (uidx < nPatch) {
-                    t = pos + uidx / 2;
-                    l = (uidx & 1) ? db : da;
-                } else {
-                    const long long q = uidx - nPatch;
-                    t = hi + q / L;
-                    l = (int)(q % L);
-                }
+                int l, slot;
+                decode(uidx, t, l, slot);
                 const int i = a.ix[t] - 1;
                 const int cur = a.y[i] - 1;
                 const bool isCur = (l == cur);
                 const int* x = a.counts + (size_t)i * C;
-                const int* trow = t_s + l * Cp;
-                const double* lrow = lgt_s + l * Cp;
+                const int* trow = t_s + slot * Cp;
+                const double* lrow = lgt_s + slot * Cp;
                 // first loop of cG_CalcGibbsProbY (:212-225): per column one fresh lgamma and one cached one
                 for (int c = lane; c < C; c += 32) {
                     const double cached = lrow[c];
@@ -1200,29 +1590,20 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                     scr[2 * c] = isCur ? cached : fresh;      // added
                     scr[2 * c + 1] = isCur ? fresh : cached;  // subtracted
                 }
-                // second loop (:230-246): six per-module terms, evaluated by six lanes
+                // second loop (:230-246): five module-only terms from the cache, the sixth evaluated
                 if (lane < 6) {
-                    const int g = g_s[l];
-                    const double Tl = (double)T_s[l], Ni = (double)a.nByG[i];
+                    const int g = g_s[slot];
+                    const double Tl = (double)T_s[slot], Ni = (double)a.nByG[i];
+                    const double* tl = tail_s + slot * 7;
+                    const int g1 = isCur ? g - 1 : g, g0 = g1 + 1;
                     double v;
-                    if (isCur) {
-                        switch (lane) {
-                            case 0: v = dlgamma((double)g + a.gamma); break;
-                            case 1: v = dlgamma((double)(g - 1) + a.gamma); break;
-                            case 2: v = dlgamma((double)g * a.delta); break;
-                            case 3: v = dlgamma((double)(g - 1) * a.delta); break;
-                            case 4: v = dlgamma(Tl - Ni + (double)(g - 1) * a.delta); break;
-                            default: v = dlgamma(Tl + (double)g * a.delta); break;
-                        }
-                    } else {
-                        switch (lane) {
-                            case 0: v = dlgamma((double)(g + 1) + a.gamma); break;
-                            case 1: v = dlgamma((double)g + a.gamma); break;
-                            case 2: v = dlgamma((double)(g + 1) * a.delta); break;
-                            case 3: v = dlgamma((double)g * a.delta); break;
-                            case 4: v = dlgamma(Tl + (double)g * a.delta); break;
-                            default: v = dlgamma(Tl + Ni + (double)(g + 1) * a.delta); break;
-                        }
+                    switch (lane) {
+                        case 0: v = tl[isCur ? 1 : 2]; break;
+                        case 1: v = tl[isCur ? 0 : 1]; break;
+                        case 2: v = tl[isCur ? 4 : 5]; break;
+                        case 3: v = tl[isCur ? 3 : 4]; break;
+                        case 4: v = isCur ? dlgamma_hot(Tl - Ni + (double)g1 * a.delta) : tl[6]; break;
+                        default: v = isCur ? tl[6] : dlgamma_hot(Tl + Ni + (double)g0 * a.delta); break;
                     }
                     scr[2 * C + lane] = v;
                 }
@@ -1252,23 +1633,48 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
         double* pl = scr;
         double* rr = scr + L;
         int* perm = reinterpret_cast<int*>(scr + 2 * L);
-        for (int c = gwarpT; c < nwin; c += tw) {
+        // carried items in front of the first tentative commit have nothing stale unless commits were discarded
+        const int cstart = (ndc > 0 || M == 0) ? 0 : (int)(cm_t[0] + 1 - pos);
+        for (int c = cstart + gwarpT; c < nwin; c += tw) {
             const long long t = pos + c;
+            const bool fresh = t >= hi;
+            int q = M;
+            if (!fresh) {
+                q = 0;
+                for (int i = 0; i < M; ++i) q += (cm_t[i] < t);
+            }
+            const int ncols = fresh ? L : nq_s[q];
+            if (ncols == 0) continue;
             const int i = a.ix[t] - 1;
             const int cur = a.y[i] - 1;
             const size_t slot = ring_slot(t, a.w.Wmax), o = slot * L;
-            double mxOld;
-            if (a.doSample && nd == 2 && t < hi && gavg >= 32 && draw_recorded_zero(a.w, slot, da, db, mxOld)) {
-                const double pa = __ldcg(a.w.bufP + o + da), pb = __ldcg(a.w.bufP + o + db);
-                if (draw_still_zero(mxOld, pa, pb)) {  // carried over the commit (da, db) with an unchanged draw
-                    if (a.probs && lane == 0) {
-                        a.probs[(size_t)i * L + da] = pa;
-                        a.probs[(size_t)i * L + db] = pb;
+            const int oldv = fresh ? -1 : __ldcg(a.w.spec + slot);
+            // see k_sweep_z: the recorded draw stands if every stale entry had exp(p - max) == 0 and still has
+            if (!fresh && a.doSample && ncols <= 32 && (cheapScore > 0 || ((++cheapTick) & 15) == 0)) {
+                const int4 nz = __ldcg(reinterpret_cast<const int4*>(a.w.drawNz) + slot);
+                bool ok = nz.x != -2;
+                if (ok) {
+                    const double mxOld = __ldcg(a.w.drawMx + slot);
+                    const int cj = (lane < ncols) ? CL_s[lane] : -1;
+                    bool mine = true;
+                    double p = 0.0;
+                    if (cj >= 0) {
+                        mine = !(nz.x == cj || nz.y == cj || nz.z == cj || nz.w == cj);
+                        if (mine) {
+                            p = __ldcg(a.w.bufP + o + cj);
+                            mine = dexp(p - mxOld) == 0.0;
+                        }
                     }
-                    continue;
+                    ok = __all_sync(0xffffffffu, mine);
+                    if (ok) {
+                        if (a.probs && cj >= 0) a.probs[(size_t)i * L + cj] = p;
+                        if (lane == 0 && oldv != spec_clean(oldv)) a.w.spec[slot] = spec_clean(oldv);
+                    }
                 }
+                cheapScore = ok ? min(8, cheapScore + 1) : max(0, cheapScore - 1);
+                if (ok) continue;
             }
-            if (lane == 0 && nd == 2 && t < hi) ++redraws;
+            if (lane == 0 && !fresh) ++redraws;
             for (int l = lane; l < L; l += 32) {
                 const double p = __ldcg(a.w.bufP + o + l);
                 pl[l] = p;
@@ -1289,11 +1695,16 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                     reinterpret_cast<int4*>(a.w.drawNz)[slot] = nz;
                 }
             }
-            if (lane == 0) a.w.spec[slot] = (ynew != cur) ? ((cur << 16) | ynew) : -1;
+            if (lane == 0) {
+                const int newv = (ynew != cur) ? ((cur << 16) | ynew) : -1;
+                a.w.spec[slot] = (fresh || newv == spec_clean(oldv)) ? newv : spec_mark(newv, tag);
+            }
             __syncwarp();
         }
         prev_end = end;
         have_spec = true;
+        first = false;
+        tagPrev = tag;
         CELDA_TICK(ck_draw);
         grid_sync(a.w.barrier, bar_target);
         CELDA_TICK(ck_bar);
@@ -1309,6 +1720,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
             a.w.stats[0] += rounds;
             a.w.stats[1] += units_done;
             a.w.stats[2] += movers;
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.w.stats + 7), (unsigned long long)discards << 40);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -1319,11 +1731,11 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
     }
 }
 
-inline size_t y_sweep_smem(int L, int C, int T, int nwarp) {
-    const int Cp = C | 1;
+inline size_t y_sweep_smem(int L, int C, int T, int nwarp, int MC = MCMAX) {
+    const int Cp = C | 1, LS = L + 2 * MC;
     const size_t scratchD = (size_t)std::max(2 * C + 8, 2 * L + (L + 1) / 2) + 2;
-    return sizeof(double) * (T + (size_t)L * Cp + (size_t)L * 7 + nwarp * scratchD) + sizeof(long long) * L +
-           sizeof(int) * ((size_t)L * Cp + L + 4);
+    return sizeof(double) * (T + (size_t)LS * Cp + (size_t)LS * 7 + nwarp * scratchD) + sizeof(long long) * (LS + 2 * MCMAX) +
+           sizeof(int) * ((size_t)LS * Cp + LS + 4 * (size_t)L + 6 * MCMAX + (MCMAX + 1) + (MCMAX + 2) + 40);
 }
 
 // ------------------------------------------------------------------------------------------------ y sweep, celda_G
@@ -1358,6 +1770,7 @@ constexpr int YG_TILE = 128;  // columns per staged tile
 
 __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (a.w.status[1]) return;  // the injected visiting order failed its check: nothing may be indexed through it
     const int L = a.L, T = a.w.lgT;
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int scratchD = 2 * L + (L + 1) / 2 + 2;
@@ -1539,8 +1952,8 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
                 const int g1 = isCur ? g - 1 : g, g0 = g1 + 1;
                 p += dlgamma_hot((double)g0 + a.gamma);
                 p -= dlgamma_hot((double)g1 + a.gamma);
-                p += dlgamma_hot((double)g0 * a.delta);
-                p -= dlgamma_hot((double)g1 * a.delta);
+                p += dlgdelta(g0, a.delta);
+                p -= dlgdelta(g1, a.delta);
                 p += dlgamma_hot(isCur ? Tl - Ni + (double)g1 * a.delta : Tl + (double)g1 * a.delta);
                 p -= dlgamma_hot(isCur ? Tl + (double)g0 * a.delta : Tl + Ni + (double)g0 * a.delta);
                 a.w.bufP[ring_slot(tgene, a.w.Wmax) * L + l] = p;
@@ -1665,6 +2078,7 @@ struct ZCArgs {
 
 __global__ void __launch_bounds__(1024, 1) k_sweep_zc(ZCArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (a.w.status[1]) return;  // the injected visiting order failed its check: nothing may be indexed through it
     const int K = a.K, nS = a.nS, T = a.w.lgT, R = a.nG;
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int scratchD = 2 * K + (K + 1) / 2 + 2;

@@ -134,6 +134,10 @@ int celda_chain_create(celda_chain **out, int device, int model, int nG, int nM,
                        const double *x, const int *s /* 1-based sample labels, NULL for celda_G */, int nS, int K,
                        int L, double alpha, double beta, double delta, double gamma);
 void celda_chain_destroy(celda_chain *h);
+/* celdaGridSearch runs every (K, L, chain) of paramsTest on the same counts (R/celdaGridSearch.R:290-391, one
+ * `counts` shared by all .celda_CG calls): keep the resident counts, re-size the (K, L)-dependent tables.  The handle
+ * needs celda_chain_set_state before the next sweep.  K, L <= 1024. */
+int celda_chain_reconfigure(celda_chain *h, int K, int L);
 /* .cCGDecomposeCounts / .cCDecomposeCounts / .cGDecomposeCounts from labels (z or y may be NULL per model). */
 int celda_chain_set_state(celda_chain *h, const int *z, const int *y);
 int celda_chain_get_state(celda_chain *h, int *z, int *y);

@@ -589,6 +589,8 @@ static inline double tab_or_eval(const double *tab, double idx, double shift, do
      * (R/celda_CG.R:428-429,543).  tab == NULL evaluates the entry directly: same value, no table. */
     long k = (long)idx;
     if (tab) return tab[k];
+    /* lgdelta <- c(NA, lgamma(seq(nG + L) * delta)): entry 0 is NA (R/celda_CG.R:429, R/celda_G.R:332) */
+    if (scale != 0 && k == 0) return NAN;
     return o_lgamma(scale != 0 ? (double)k * scale : (double)k + shift);
 }
 
