@@ -378,8 +378,8 @@ void window_sizes(const SweepBufs& b, int sms, int threads, int ncand, int cap, 
 // (1 reproduces the one-mover-per-round schedule).
 int sweep_mc() {
     const char* v = getenv("CELDA_CUDA_MC");
-    const int m = v ? atoi(v) : MCMAX;
-    return std::max(1, std::min(m, MCMAX));
+    const int m = v ? atoi(v) : MCMAX - 1;
+    return std::max(1, std::min(m, MCMAX - 1));
 }
 
 // cap: largest steady-state window.  Items behind a mover are patched and redrawn every round, so a sweep whose
@@ -394,14 +394,20 @@ SweepWork make_work(SweepBufs& b, int sms, int threads, int ncand, int which, in
 // a: data pointers and sizes filled by the caller; work space, window policy and launch geometry set here.
 int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     int threads = 1024;
-    const int MC = sweep_mc();
+    int MC = sweep_mc();  // fewer tentative commits per round when large tables leave no room for their column slots
+    while (MC > 1 && z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32, 0, MC) > 160 * 1024) MC /= 2;
     if (z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32, 0, MC) > 220 * 1024) threads = 512;
     a.w = make_work(b, sms, threads, a.K, which, window_cap("CELDA_CUDA_ZCAP", 32768));
+    a.w.MC = MC;
     // value tables: the shared memory left over holds the heads; sized from this sweep's count distribution
     a.EsCap = 0;
     {
-        const size_t base = z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32, 0, MC);
-        const long long room = ((long long)200 * 1024 - (long long)base) / (long long)sizeof(double);  // ~28 KB stays L1
+        // the table head shares its buffer with the commit slots beyond the second commit (z_sweep_vtcap)
+        const size_t base = z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32, 0, MC) -
+                            sizeof(double) * z_sweep_vtcap(a.R, a.K, 0, MC);
+        // shared-memory budget of the kernel in KB (the rest of the 228 KB stays L1); CELDA_CUDA_ZSMEM_KB overrides
+        const long long budget = (long long)window_cap("CELDA_CUDA_ZSMEM_KB", 207) * 1024;
+        const long long room = (budget - (long long)base) / (long long)sizeof(double);
         if (room >= 8LL * a.R && a.nM >= 4096) {
             a.EsCap = (int)std::min<long long>(room, 1 << 20);
             if (b.ztOffg.n < (size_t)a.R + 1) {
@@ -450,6 +456,7 @@ int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
             a.w.Wunit = std::min(a.w.Wunit, a.w.Wfull);
         }
     }
+    a.vtCap = (int)z_sweep_vtcap(a.R, a.K, a.EsCap, MC);
     const size_t smem = z_sweep_smem(a.R, a.K, a.nS, b.lgT, threads / 32, a.EsCap, MC);
     if (smem > 220 * 1024) return fail("z sweep: K=%d x R=%d tables need %zu bytes of shared memory (> 220 KB)", a.K, a.R, smem);
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_z, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -462,9 +469,11 @@ int run_sweep_z(ZArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
 
 int run_sweep_y(YArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     int threads = 1024;
-    const int MC = sweep_mc();
+    int MC = sweep_mc();  // fewer tentative commits per round when large tables leave no room for their row slots
+    while (MC > 1 && y_sweep_smem(a.L, a.ncol, b.lgT, threads / 32, MC) > 220 * 1024) MC /= 2;
     if (y_sweep_smem(a.L, a.ncol, b.lgT, threads / 32, MC) > 220 * 1024) threads = 512;
     a.w = make_work(b, sms, threads, a.L, which, window_cap("CELDA_CUDA_YCAP", 8192));
+    a.w.MC = MC;
     const size_t smem = y_sweep_smem(a.L, a.ncol, b.lgT, threads / 32, MC);
     if (smem > 220 * 1024) return fail("y sweep: L=%d x K=%d tables need %zu bytes of shared memory (> 220 KB)", a.L, a.ncol, smem);
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_y, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

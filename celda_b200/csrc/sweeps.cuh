@@ -303,11 +303,15 @@ __device__ int warp_sample_ll(double* pl, int n, double u, double* r, int* perm,
         for (int i = lane; i < n; i += 32) {
             const double ri = r[i];
             if (ri > 0.0) {
+                // entries are >= +0: their bit patterns order like the values, and integer compares leave the FP64 pipe alone
+                const long long bi = __double_as_longlong(ri);
+                const long long* rb = reinterpret_cast<const long long*>(r);
                 int gt = 0, eq = 0;
+#pragma unroll 4
                 for (int j = 0; j < n; ++j) {
-                    const double v = r[j];
-                    gt += (v > ri);
-                    eq += (v == ri);
+                    const long long v = rb[j];
+                    gt += (v > bi);
+                    eq += (v == bi);
                 }
                 tie |= (eq > 1);
                 hs[gt] = ri;
@@ -438,7 +442,7 @@ __device__ __forceinline__ bool draw_still_zero(double mx, double pa, double pb)
 // next round starts there.  With M = 1 this is the single-commit schedule; the arithmetic of every unit and every
 // draw is unchanged, so results stay bit-identical to the sequential sweep (scripts/proto_multicommit.py checks the
 // bookkeeping against a sequential sweep on random problems).
-constexpr int MCMAX = 16;           // tentative commits per round, upper bound (SweepWork::MC <= MCMAX)
+constexpr int MCMAX = 32;           // array bound of the commit records; SweepWork::MC <= MCMAX - 1 (one lane per commit + 1)
 constexpr int SPEC_INV = 1 << 30;   // spec ring, movers: the last validation changed this item's outcome
 
 // spec ring encoding: -1 non-mover; (old << 16 | new) mover; invalid marks carry the 3-bit tag of the round that set
@@ -449,11 +453,15 @@ __device__ __forceinline__ bool spec_invalid(int v, int tag) {
     return v < -1 ? (-2 - v) == tag : ((v & SPEC_INV) && ((v >> 27) & 7) == tag);
 }
 
-// Block-wide: smallest c in [0, nwin) whose ring slot carries an invalid mark of round `tag`, or -1.
-__device__ int block_first_invalid(const int* spec, long long pos, int Wmax, int nwin, int tag, int* s_first) {
-    if (threadIdx.x == 0) *s_first = 0x7fffffff;
+// Block-wide: smallest c in [0, nwin) whose ring slot carries an invalid mark of round `tag`, or -1; anyMover tells
+// whether the slots examined hold a mover at all (a quiet window needs no selection pass).  s_first: 2 ints.
+__device__ int block_first_invalid(const int* spec, long long pos, int Wmax, int nwin, int tag, int* s_first, bool& anyMover) {
+    if (threadIdx.x == 0) {
+        s_first[0] = 0x7fffffff;
+        s_first[1] = 0;
+    }
     __syncthreads();
-    int best = 0x7fffffff;
+    int best = 0x7fffffff, mv = 0;
     for (int c0 = threadIdx.x; c0 < nwin && best == 0x7fffffff; c0 += 4 * blockDim.x) {
         int v[4];
 #pragma unroll
@@ -462,47 +470,79 @@ __device__ int block_first_invalid(const int* spec, long long pos, int Wmax, int
             v[k] = (c < nwin) ? __ldcg(spec + ((pos + c) & (long long)(Wmax - 1))) : -1;
         }
 #pragma unroll
-        for (int k = 3; k >= 0; --k)
+        for (int k = 3; k >= 0; --k) {
             if (spec_invalid(v[k], tag)) best = c0 + k * blockDim.x;
+            mv |= (v[k] >= 0);
+        }
     }
     for (int o = 16; o; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if ((threadIdx.x & 31) == 0 && best != 0x7fffffff) atomicMin(s_first, best);
+    mv = __any_sync(0xffffffffu, mv);
+    if ((threadIdx.x & 31) == 0) {
+        if (best != 0x7fffffff) atomicMin(&s_first[0], best);
+        if (mv) s_first[1] = 1;
+    }
     __syncthreads();
-    const int f = *s_first;
+    const int f = s_first[0];
+    // a thread that stopped at an invalid item has not seen the rest of the window: assume movers there
+    anyMover = s_first[1] != 0 || f != 0x7fffffff;
     __syncthreads();
     return f == 0x7fffffff ? -1 : f;
 }
 
 // Block-wide ordered compaction: the first (visiting order) <= cap movers among the ring slots of [pos, pos + nwin).
-// out_t[k] = position, out_pk[k] = clean packed (old << 16 | new).  s_tmp: 34 ints.  Returns the number selected.
+// out_t[k] = position, out_pk[k] = clean packed (old << 16 | new).  s_tmp: 130 ints.  Returns the number selected.
+// Four chunks of blockDim items per pass (four loads in flight per thread, two barriers per pass).
 __device__ int block_select_movers(const int* spec, long long pos, int Wmax, int nwin, int cap, long long* out_t, int* out_pk,
                                    int* s_tmp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     int total = 0;
-    for (int base = 0; base < nwin && total < cap; base += blockDim.x) {
-        const int c = base + threadIdx.x;
-        const int v = (c < nwin) ? __ldcg(spec + ((pos + c) & (long long)(Wmax - 1))) : -1;
-        const bool mover = v >= 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, mover);
-        if (lane == 0) s_tmp[warp] = __popc(bal);
+    for (int base = 0; base < nwin && total < cap; base += 4 * blockDim.x) {
+        int v[4];
+        unsigned bal[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = base + k * blockDim.x + threadIdx.x;
+            v[k] = (c < nwin) ? __ldcg(spec + ((pos + c) & (long long)(Wmax - 1))) : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            bal[k] = __ballot_sync(0xffffffffu, v[k] >= 0);
+            if (lane == 0) s_tmp[k * 32 + warp] = __popc(bal[k]);
+        }
         __syncthreads();
-        if (warp == 0) {
-            const int cnt = (lane < nwarp) ? s_tmp[lane] : 0;
-            int inc = cnt;
+        if (warp == 0) {  // exclusive prefix over the 4 x nwarp counts in (chunk, warp) order: lane <-> 4 consecutive counts
+            int c4[4], sum = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = lane * 4 + q, k = idx / nwarp, w = idx - k * nwarp;
+                c4[q] = (idx < 4 * nwarp) ? s_tmp[k * 32 + w] : 0;
+                sum += c4[q];
+            }
+            int inc = sum;
             for (int o = 1; o < 32; o <<= 1) {
                 const int nb = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= o) inc += nb;
             }
-            s_tmp[lane] = inc - cnt;
-            if (lane == 31) s_tmp[32] = inc;
+            int run = inc - sum;
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int idx = lane * 4 + q, k = idx / nwarp, w = idx - k * nwarp;
+                if (idx < 4 * nwarp) s_tmp[k * 32 + w] = run;
+                run += c4[q];
+            }
+            if (lane == 31) s_tmp[128] = inc;
         }
         __syncthreads();
-        const int rank = total + s_tmp[warp] + __popc(bal & ((1u << lane) - 1u));
-        if (mover && rank < cap) {
-            out_t[rank] = pos + c;
-            out_pk[rank] = spec_clean(v);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int rank = total + s_tmp[k * 32 + warp] + __popc(bal[k] & ((1u << lane) - 1u));
+            if (v[k] >= 0 && rank < cap) {
+                out_t[rank] = pos + base + k * blockDim.x + threadIdx.x;
+                out_pk[rank] = spec_clean(v[k]);
+            }
         }
-        total += s_tmp[32];
+        total += s_tmp[128];
         __syncthreads();
     }
     return min(total, cap);
@@ -516,9 +556,141 @@ __device__ __forceinline__ int mc_target(int gavg, int MC) {
     return max(1, min(m, MC));
 }
 
+// Round bookkeeping done by ONE warp (lane <-> tentative commit) while the other warps copy table columns: the
+// Dcarry list of the discarded commits, the next tentative commits' records, their source slots, the stale-column
+// list CL with its per-commit prefix lengths nq, and the patch-unit segment offsets.  Everything here is a few
+// shared-memory words per lane with __syncwarp between steps; one __syncthreads publishes the result.
+struct CommitBank {
+    long long t[MCMAX];   // visiting position of the mover
+    long long N[MCMAX];   // its total count
+    int a[MCMAX], b[MCMAX], item[MCMAX], aux[MCMAX], srcA[MCMAX], srcB[MCMAX], pk[MCMAX];
+};
+
+// slot of candidate j for an item with q commits of bank cb in front of it (ncand base slots first)
+__device__ __forceinline__ int bank_slot_of(const CommitBank* cb, int ncand, int q, int j) {
+    for (int i = q - 1; i >= 0; --i) {
+        if (cb->b[i] == j) return ncand + 2 * i + 1;
+        if (cb->a[i] == j) return ncand + 2 * i;
+    }
+    return j;
+}
+
+// Warp-level ordered selection of the first <= cap movers of [pos, pos + nsel) (nsel <= a few thousand).
+__device__ __forceinline__ int warp_select_movers(const int* spec, long long pos, int Wmax, int nsel, int cap, CommitBank* nb,
+                                                  int lane) {
+    int Mn = 0;
+    for (int base = 0; base < nsel && Mn < cap; base += 256) {
+        int v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int c = base + k * 32 + lane;
+            v[k] = (c < nsel) ? __ldcg(spec + ((pos + c) & (long long)(Wmax - 1))) : -1;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const bool mover = v[k] >= 0;
+            const unsigned bal = __ballot_sync(0xffffffffu, mover);
+            const int rank = Mn + __popc(bal & ((1u << lane) - 1u));
+            if (mover && rank < cap) {
+                nb->t[rank] = pos + base + k * 32 + lane;
+                nb->pk[rank] = spec_clean(v[k]);
+            }
+            Mn += __popc(bal);
+        }
+    }
+    return min(Mn, cap);
+}
+
+// Dcarry of the commits [qf, M) of the old bank, in commit order without repeats; returns its length (all lanes).
+__device__ __forceinline__ int warp_build_dcarry(const CommitBank* ob, int qf, int M, int* dc_s, int lane) {
+    bool newA = false, newB = false;
+    int ca = -1, cb = -1;
+    if (lane >= qf && lane < M) {
+        ca = ob->a[lane];
+        cb = ob->b[lane];
+        newA = newB = true;
+        for (int k = qf; k < lane; ++k) {
+            const int ak = ob->a[k], bk = ob->b[k];
+            newA &= (ak != ca) & (bk != ca);
+            newB &= (ak != cb) & (bk != cb);
+        }
+    }
+    const int cnt = (int)newA + (int)newB;
+    int inc = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int nb = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += nb;
+    }
+    const int at = inc - cnt;
+    if (newA) dc_s[at] = ca;
+    if (newB) dc_s[at + (int)newA] = cb;
+    return __shfl_sync(0xffffffffu, inc, 31);
+}
+
+// Source slots, stale list CL (Dcarry first, then each commit's columns where new), nq, segment offsets.
+// The records a/b/t of the new bank are in place.  hiC = end of the carried items.
+__device__ __forceinline__ void warp_build_lists(CommitBank* nb, int ncand, int Mn, int ndc, const int* dc_s, int* CL_s, int* nq_s,
+                                                 int* seg_s, long long pos, long long hiC, int lane) {
+    bool newA = false, newB = false;
+    int ca = -1, cb = -1;
+    if (lane < Mn) {
+        ca = nb->a[lane];
+        cb = nb->b[lane];
+        nb->srcA[lane] = bank_slot_of(nb, ncand, lane, ca);
+        nb->srcB[lane] = bank_slot_of(nb, ncand, lane, cb);
+        newA = newB = true;
+        for (int d = 0; d < ndc; ++d) {
+            const int c = dc_s[d];
+            newA &= (c != ca);
+            newB &= (c != cb);
+        }
+        for (int k = 0; k < lane; ++k) {
+            const int ak = nb->a[k], bk = nb->b[k];
+            newA &= (ak != ca) & (bk != ca);
+            newB &= (ak != cb) & (bk != cb);
+        }
+    }
+    for (int d = lane; d < ndc; d += 32) CL_s[d] = dc_s[d];
+    const int cnt = (int)newA + (int)newB;
+    int inc = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    const int at = ndc + inc - cnt;
+    if (newA) CL_s[at] = ca;
+    if (newB) CL_s[at + (int)newA] = cb;
+    if (lane == 0) nq_s[0] = ndc;
+    if (lane < Mn) nq_s[lane + 1] = ndc + inc;
+    __syncwarp();
+    // segment q = the carried items with exactly q commits in front: (m_{q-1}, m_q], the last one up to hiC - 1
+    int units = 0;
+    if (lane <= Mn) {
+        const long long last = (lane < Mn) ? nb->t[lane] : hiC - 1;
+        const long long prevLast = (lane == 0) ? pos - 1 : nb->t[lane - 1];
+        units = (int)max(0LL, last - prevLast) * nq_s[lane];
+    }
+    int incU = units;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incU, o);
+        if (lane >= o) incU += v;
+    }
+    if (lane == 0) seg_s[0] = 0;
+    seg_s[lane + 1] = incU;  // lanes beyond Mn repeat the total: seg_s[Mn + 1] is what the kernels read
+    __syncwarp();
+}
+
+
 // ------------------------------------------------------------------------------------------------ z sweep
 // .cCCalcGibbsProbZ (R/celda_C.R:620-714) on a dense R x nM int32 count matrix (nTSByC in celda_CG).
 constexpr int ZT_MAXGRP = 30;  // row groups of the value tables
+
+// columns of the z sweep's table with memory of their own: the K base columns and the slots of the first two tentative
+// commits, rounded up so that the value-table buffer behind them stays 8-byte aligned (the row stride is odd)
+__host__ __device__ inline int z_sweep_kb(int K, int MC) {
+    const int kb = K + 2 * (MC < 2 ? MC : 2);
+    return kb + (kb & 1);
+}
 
 struct ZArgs {
     int R, K, nS;
@@ -540,6 +712,7 @@ struct ZArgs {
     const int* grp;     // [ZT_MAXGRP + 3]: grp[0] = number of row groups, then the group boundaries (rows); last entry = 1 when
                         // every row's table covers all its counts (no look-up can miss)
     int EsCap;          // shared-memory table capacity in entries; 0 disables the tables
+    int vtCap;          // doubles reserved for the table head / the commit slots beyond the second commit (z_sweep_vtcap)
     const int* xT;      // [R][nM]: xT[r][t] = counts[r, ix[t] - 1], the counts in visiting order, cell-minor
     const int* zT;      // [nM] zT[t] = z[ix[t] - 1] at the start of the sweep (a cell's label changes only at its own visit)
     const int* nT;      // [nM] nT[t] = nByC[ix[t] - 1]
@@ -608,34 +781,29 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     if (a.w.status[1]) return;  // the injected visiting order failed its check: nothing may be indexed through it
     const int R = a.R, K = a.K, nS = a.nS, T = a.w.lgT, MC = a.w.MC;
-    const int KS = K + 2 * MC;  // column slots: K base columns + two per tentative commit
+    // Column slots: K base columns + two per tentative commit.  The first KB columns have memory of their own; the
+    // slots beyond (commits 2, 3, ...) lie over the head of the value-table buffer vt_s, which only table rounds use --
+    // and a round that may become a table round selects at most two commits (see the window policy below).
+    const int KS = K + 2 * MC, KB = z_sweep_kb(K, MC);
     const int Rp = R | 1;       // odd stride: candidate-major rows, conflict-free across lanes of r
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int scratchD = max(R, 2 * K + (K + 1) / 2) + 2;
     double* lgtab = reinterpret_cast<double*>(smem_raw);
     double* scratch_all = lgtab + T;
     long long* nCP_s = reinterpret_cast<long long*>(scratch_all + (size_t)nwarp * scratchD);  // [KS]
-    long long* cm_t = nCP_s + KS;                                                             // [MCMAX] positions
-    double* vt_s = reinterpret_cast<double*>(cm_t + MCMAX);  // [EsCap] value table head of this CTA's candidate
-    int* n_s = reinterpret_cast<int*>(vt_s + a.EsCap);       // [KS][Rp]
-    int* m_s = n_s + (size_t)KS * Rp;
+    CommitBank* banks = reinterpret_cast<CommitBank*>(nCP_s + KS);  // [2] tentative commits of this round / the last
+    long long* st_s = reinterpret_cast<long long*>(banks + 2);  // [12] statistics and CTA-0 clocks (thread 0)
+    int* n_s = reinterpret_cast<int*>(st_s + 12);            // [KB][Rp] (+ the slots KB.. over vt_s); KB * Rp is even
+    double* vt_s = reinterpret_cast<double*>(n_s + (size_t)KB * Rp);  // [vtCap] value table head of this CTA's candidate
+    int* m_s = reinterpret_cast<int*>(vt_s + a.vtCap);
     int* offg_s = m_s + K * nS;           // [R + 1]
     int* grp_s = offg_s + R + 1;          // [ZT_MAXGRP + 3]
     int* fin_s = grp_s + ZT_MAXGRP + 3;   // [K] slot of column j with every tentative commit applied
     int* CL_s = fin_s + K;                // [K] stale-column list: Dcarry first, then the commits' columns in order
-    int* inCL_s = CL_s + K;               // [K]
-    int* dc_s = inCL_s + K;               // [K] Dcarry
-    int* cm_a = dc_s + K;                 // [MCMAX] each: old label, new label, sample, cell total, cell, source slots, packed
-    int* cm_b = cm_a + MCMAX;
-    int* cm_s = cm_b + MCMAX;
-    int* cm_N = cm_s + MCMAX;
-    int* cm_cell = cm_N + MCMAX;
-    int* cm_srcA = cm_cell + MCMAX;
-    int* cm_srcB = cm_srcA + MCMAX;
-    int* cm_pk = cm_srcB + MCMAX;
-    int* nq_s = cm_pk + MCMAX;            // [MCMAX + 1] stale columns of an item with q commits in front
+    int* dc_s = CL_s + K;                 // [K] Dcarry
+    int* nq_s = dc_s + K;                 // [MCMAX + 1] stale columns of an item with q commits in front
     int* seg_s = nq_s + MCMAX + 1;        // [MCMAX + 2] patch-unit offsets per segment
-    int* s_misc = seg_s + MCMAX + 2;      // [40]
+    int* s_misc = seg_s + MCMAX + 2;      // [144]
     double* scr = scratch_all + (size_t)warp * scratchD;
     // Lane-per-unit rounds: a CTA tabulates, for the candidate j it is serving,
     // lgamma(n[r][j] + v + beta) over the counts v that occur in row r, one group of rows at a time (as many rows
@@ -643,6 +811,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
     // lgamma evaluations; its partial sum waits in the ring buffer between row groups.  The tables hold exactly
     // the values lg_tab() returns, and a count beyond a row's table is evaluated directly.
     const bool useTab = a.EsCap > 0;
+    (void)KS;
 
     const double Rbeta = (double)R * a.beta;
     const int gwarp = blockIdx.x * nwarp + warp, tw = gridDim.x * nwarp;
@@ -663,26 +832,27 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
     }
     if (threadIdx.x <= MCMAX) nq_s[threadIdx.x] = 0;
     if (threadIdx.x <= MCMAX + 1) seg_s[threadIdx.x] = 0;
+    CommitBank* cb = banks;
     __syncthreads();
 
     long long pos = 0, hi = 0, prev_end = 0;
-    int W = a.w.Wfull, gavg = a.w.Wfull, M = 0, ndc = 0, mcAimd = MC, par = 0, tagPrev = 0;
+    int W = a.w.Wfull, gavg = a.w.Wfull, M = 0, mcAimd = MC, par = 0, tagPrev = 0;
     bool have_spec = false, first = true;
     unsigned bar_target = 0;
-    long long rounds = 0, units_done = 0, movers = 0, discards = 0;
-    long long redraws = 0;  // carried items drawn again in full (this thread's share)
+    int roundNo = 0;
     int cheapScore = 4, cheapTick = 0;
-    long long ck_commit = 0, ck_units = 0, ck_draw = 0, ck_bar = 0, ck0 = clock64(), ck1;
-#define CELDA_TICK(acc) do { ck1 = clock64(); acc += ck1 - ck0; ck0 = ck1; } while (0)
+    if (threadIdx.x < 12) st_s[threadIdx.x] = (threadIdx.x == 9) ? clock64() : 0;  // 0 rounds 1 units 2 movers 3 discards 4 redraws 5..8 clocks
+    __syncthreads();
+#define CELDA_TICKR(acc) do { ck1 = clock64(); acc += ck1 - ck0; ck0 = ck1; } while (0)
+#define CELDA_TICK(k) do { if (threadIdx.x == 0) { const long long c_ = clock64(); st_s[k] += c_ - st_s[9]; st_s[9] = c_; } } while (0)
+#ifdef CELDA_COMMIT_PROF
+#define CELDA_CSUB(k) do { const long long c_ = clock64(); csub[k] += c_ - csub0; csub0 = c_; } while (0)
+#define CELDA_CSUB_BEGIN() csub0 = clock64()
+#else
+#define CELDA_CSUB(k) do { } while (0)
+#define CELDA_CSUB_BEGIN() do { } while (0)
+#endif
 
-    // slot of column j for an item with q tentative commits in front of it
-    auto slot_of = [&](int q, int j) {
-        for (int i = q - 1; i >= 0; --i) {
-            if (cm_b[i] == j) return K + 2 * i + 1;
-            if (cm_a[i] == j) return K + 2 * i;
-        }
-        return j;
-    };
     // the per-slot cached sums live in global memory (written by whichever warp evaluated them); the commit slots
     // alternate between two banks so that a round never overwrites what the next round's first phase still reads
     auto gslot = [&](int slot, int bank) { return slot < K ? slot : K + bank * 2 * MCMAX + (slot - K); };
@@ -692,140 +862,138 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
         return (int)max((long long)a.w.Wmin, target);
     };
 
+    long long csub[6] = {0, 0, 0, 0, 0, 0}, csub0 = 0;
+    (void)csub; (void)csub0;
     while (true) {
         // ---- settle the previous round: which tentative commits stand, where the window restarts, the next commits
+        CELDA_CSUB_BEGIN();
+        CommitBank* ob = cb;              // the finished round's commits
+        cb = banks + par;                 // this round's
+        bool hasDc = false;
         if (have_spec) {
             const int nwinPrev = (int)(prev_end - pos);
-            const int f = block_first_invalid(a.w.spec, pos, a.w.Wmax, nwinPrev, tagPrev, s_misc);
+            bool anyMover;
+            const int f = block_first_invalid(a.w.spec, pos, a.w.Wmax, nwinPrev, tagPrev, s_misc, anyMover);
+            CELDA_CSUB(0);
             const long long tf = pos + f;
-            int qf = M;
+            const int Mold = M;
+            int qf = Mold;
             if (f >= 0) {
                 qf = 0;
-                for (int i = 0; i < M; ++i) qf += (cm_t[i] < tf);
+                for (int i = 0; i < Mold; ++i) qf += (ob->t[i] < tf);
             }
-            // standing commits advance the base columns (in order: a later commit's slot supersedes an earlier one's)
-            for (int r = threadIdx.x; r < R; r += blockDim.x)
-                for (int i = 0; i < qf; ++i) {
-                    n_s[cm_a[i] * Rp + r] = n_s[(K + 2 * i) * Rp + r];
-                    n_s[cm_b[i] * Rp + r] = n_s[(K + 2 * i + 1) * Rp + r];
-                }
-            if (threadIdx.x == 0) {
-                for (int i = 0; i < qf; ++i) {
-                    const int ca = cm_a[i], cb = cm_b[i];
-                    nCP_s[ca] = nCP_s[K + 2 * i];
-                    nCP_s[cb] = nCP_s[K + 2 * i + 1];
-                    m_s[cm_s[i] * K + ca] -= 1;
-                    m_s[cm_s[i] * K + cb] += 1;
-                    if (blockIdx.x == 0) {
-                        a.z[cm_cell[i]] = cb + 1;
-                        a.w.colsum[ca] = __ldcg(a.w.colsum + gslot(K + 2 * i, par ^ 1));
-                        a.w.lgnCP[ca] = __ldcg(a.w.lgnCP + gslot(K + 2 * i, par ^ 1));
-                        a.w.colsum[cb] = __ldcg(a.w.colsum + gslot(K + 2 * i + 1, par ^ 1));
-                        a.w.lgnCP[cb] = __ldcg(a.w.lgnCP + gslot(K + 2 * i + 1, par ^ 1));
-                    }
-                }
-                int nd_ = 0;  // Dcarry: the columns of the discarded commits
-                for (int i = qf; i < M; ++i)
-                    for (int side = 0; side < 2; ++side) {
-                        const int c = side ? cm_b[i] : cm_a[i];
-                        bool seen = false;
-                        for (int d = 0; d < nd_; ++d) seen |= (dc_s[d] == c);
-                        if (!seen) dc_s[nd_++] = c;
-                    }
-                s_misc[1] = nd_;
-            }
+            hasDc = qf < Mold;
             const long long oldpos = pos;
-            if (qf < M) pos = tf;  // no unselected mover can lie in front of a discarded selected one
-            else if (M > 0) pos = cm_t[M - 1] + 1;
-            __syncthreads();
-            ndc = s_misc[1];
-            movers += qf;
-            discards += M - qf;
-            if (M > 0) mcAimd = (qf == M) ? min(MC, 2 * mcAimd) : max(1, qf + 1);
+            if (qf < Mold) pos = tf;  // no unselected mover can lie in front of a discarded selected one
+            else if (Mold > 0) pos = ob->t[Mold - 1] + 1;
+            if (threadIdx.x == 0) {
+                st_s[2] += qf;
+                st_s[3] += Mold - qf;
+            }
+            if (Mold > 0) mcAimd = (qf == Mold) ? min(MC, 2 * mcAimd) : max(1, qf + 1);
             if (qf > 0) gavg = max(1, (int)((3LL * gavg + max(1LL, (pos - oldpos) / qf)) / 4));
             int mcCur = min(mcAimd, mc_target(gavg, MC));
             W = window_for(gavg, mcCur);
+            if (useTab && 2LL * W * K + 64 >= (long long)tw * 16) {
+                // this window could make a table round (total >= tw * 16), whose value tables lie over the commit slots
+                // beyond the second commit: take the most commits whose window keeps every round small, else two
+                const long long fit = ((long long)tw * 16 - 64) / (2LL * K * gavg) - 4;
+                mcCur = (fit >= 3) ? (int)min((long long)mcCur, fit) : min(mcCur, 2);
+                W = window_for(gavg, mcCur);
+            }
             hi = min(prev_end, pos + W);
-            M = block_select_movers(a.w.spec, pos, a.w.Wmax, (int)(hi - pos), mcCur, cm_t, cm_pk, s_misc + 2);
-            if (M == 0 && ndc == 0) {  // nothing moves and nothing is stale: the carried items are settled
+            const int nsel = (int)(hi - pos);
+            const bool wideSel = nsel > 1024;  // a large window is scanned by the whole block, a small one by warp 0
+            int Mwide = 0;
+            if (wideSel && anyMover) Mwide = block_select_movers(a.w.spec, pos, a.w.Wmax, nsel, mcCur, cb->t, cb->pk, s_misc + 2);
+            if (warp == 0) {
+                // one warp: Dcarry, the next commits and their records, source slots, stale list, segments
+                const int ndc = warp_build_dcarry(ob, qf, Mold, dc_s, lane);
+                const int Mn = wideSel ? Mwide : (anyMover ? warp_select_movers(a.w.spec, pos, a.w.Wmax, nsel, mcCur, cb, lane) : 0);
+                __syncwarp();
+                if (lane < Mn) {
+                    const int cell = a.ix[cb->t[lane]] - 1, pk = cb->pk[lane];
+                    cb->item[lane] = cell;
+                    cb->a[lane] = pk >> 16;
+                    cb->b[lane] = pk & 0xffff;
+                    cb->aux[lane] = a.s[cell] - 1;
+                    cb->N[lane] = a.nByC[cell];
+                }
+                __syncwarp();
+                warp_build_lists(cb, K, Mn, ndc, dc_s, CL_s, nq_s, seg_s, pos, hi, lane);
+                if (lane == 0) s_misc[140] = Mn;
+            } else {
+                // the other warps: standing commits advance the base columns (in order: a later commit's slot
+                // supersedes an earlier one's) and the per-column scalars
+                for (int r = threadIdx.x - 32; r < R; r += blockDim.x - 32)
+                    for (int i = 0; i < qf; ++i) {
+                        n_s[ob->a[i] * Rp + r] = n_s[(K + 2 * i) * Rp + r];
+                        n_s[ob->b[i] * Rp + r] = n_s[(K + 2 * i + 1) * Rp + r];
+                    }
+                for (int j = (int)blockDim.x - 1 - (int)threadIdx.x; j < K; j += blockDim.x - 32) {
+                    const int sl = bank_slot_of(ob, K, qf, j);
+                    if (sl != j) {
+                        nCP_s[j] = nCP_s[sl];
+                        if (blockIdx.x == 0) {
+                            a.w.colsum[j] = __ldcg(a.w.colsum + gslot(sl, par ^ 1));
+                            a.w.lgnCP[j] = __ldcg(a.w.lgnCP + gslot(sl, par ^ 1));
+                        }
+                    }
+                }
+                if (warp == 1 && lane < qf) {
+                    atomicAdd(&m_s[ob->aux[lane] * K + ob->a[lane]], -1);
+                    atomicAdd(&m_s[ob->aux[lane] * K + ob->b[lane]], 1);
+                    if (blockIdx.x == 0) a.z[ob->item[lane]] = ob->b[lane] + 1;
+                }
+            }
+            __syncthreads();
+            M = s_misc[140];
+            CELDA_CSUB(1);
+            if (M == 0 && !hasDc) {  // nothing moves and nothing is stale: the carried items are settled
                 gavg = (int)min(2LL * gavg + (hi - pos), (long long)(1 << 24));
                 pos = hi;
-                mcCur = min(mcAimd, mc_target(gavg, MC));
-                W = window_for(gavg, mcCur);
+                W = window_for(gavg, 1);
             }
         }
         if (pos >= a.nM) break;
-        // ---- this round's tentative commits: records, source slots, stale-column list, new column slots
-        if (threadIdx.x < M) {
-            const int i = threadIdx.x;
-            const int cell = a.ix[cm_t[i]] - 1, pk = cm_pk[i];
-            cm_cell[i] = cell;
-            cm_a[i] = pk >> 16;
-            cm_b[i] = pk & 0xffff;
-            cm_s[i] = a.s[cell] - 1;
-            cm_N[i] = a.nByC[cell];
-        }
-        for (int j = threadIdx.x; j < K; j += blockDim.x) inCL_s[j] = 0;
-        __syncthreads();
-        if (threadIdx.x < M) {
-            cm_srcA[threadIdx.x] = slot_of(threadIdx.x, cm_a[threadIdx.x]);
-            cm_srcB[threadIdx.x] = slot_of(threadIdx.x, cm_b[threadIdx.x]);
-        }
-        if (threadIdx.x == 32) {
-            int n = 0;
-            for (int d = 0; d < ndc; ++d) {
-                CL_s[n++] = dc_s[d];
-                inCL_s[dc_s[d]] = 1;
+        CELDA_CSUB(2);
+        // ---- this round's tentative commits: new column slots
+        {
+            // the movers' count columns, all loads in flight at once (staged in the warp scratch, idle here)
+            int* xs = reinterpret_cast<int*>(scratch_all);
+            for (int q = threadIdx.x; q < M * R; q += blockDim.x) {
+                const int i = q / R, r = q - i * R;
+                xs[q] = __ldg(a.counts + (size_t)cb->item[i] * R + r);
             }
-            nq_s[0] = n;
-            for (int i = 0; i < M; ++i) {
-                if (!inCL_s[cm_a[i]]) {
-                    CL_s[n++] = cm_a[i];
-                    inCL_s[cm_a[i]] = 1;
+            __syncthreads();
+            CELDA_CSUB(3);
+            for (int r = threadIdx.x; r < R; r += blockDim.x)
+                for (int i = 0; i < M; ++i) {
+                    const int xv = xs[i * R + r];
+                    n_s[(K + 2 * i) * Rp + r] = n_s[cb->srcA[i] * Rp + r] - xv;
+                    n_s[(K + 2 * i + 1) * Rp + r] = n_s[cb->srcB[i] * Rp + r] + xv;
                 }
-                if (!inCL_s[cm_b[i]]) {
-                    CL_s[n++] = cm_b[i];
-                    inCL_s[cm_b[i]] = 1;
-                }
-                nq_s[i + 1] = n;
-            }
-            // segment q = the carried items with exactly q commits in front: (m_{q-1}, m_q], the last one up to hi
-            long long prevLast = pos - 1;
-            seg_s[0] = 0;
-            for (int q = 0; q <= M; ++q) {
-                const long long last = (q < M) ? cm_t[q] : hi - 1;
-                const long long len = max(0LL, last - prevLast);
-                seg_s[q + 1] = seg_s[q] + (int)len * nq_s[q];
-                prevLast = max(prevLast, last);
-            }
-        }
-        __syncthreads();
-        for (int r = threadIdx.x; r < R; r += blockDim.x) {
-            for (int i = 0; i < M; ++i) {
-                const int xv = __ldg(a.counts + (size_t)cm_cell[i] * R + r);
-                n_s[(K + 2 * i) * Rp + r] = n_s[cm_srcA[i] * Rp + r] - xv;
-                n_s[(K + 2 * i + 1) * Rp + r] = n_s[cm_srcB[i] * Rp + r] + xv;
-            }
         }
         if (threadIdx.x == blockDim.x - 1)
             for (int i = 0; i < M; ++i) {
-                nCP_s[K + 2 * i] = nCP_s[cm_srcA[i]] - cm_N[i];
-                nCP_s[K + 2 * i + 1] = nCP_s[cm_srcB[i]] + cm_N[i];
+                nCP_s[K + 2 * i] = nCP_s[cb->srcA[i]] - cb->N[i];
+                nCP_s[K + 2 * i + 1] = nCP_s[cb->srcB[i]] + cb->N[i];
             }
-        for (int j = threadIdx.x; j < K; j += blockDim.x) fin_s[j] = slot_of(M, j);
+        for (int j = threadIdx.x; j < K; j += blockDim.x) fin_s[j] = bank_slot_of(cb, K, M, j);
         __syncthreads();
-        CELDA_TICK(ck_commit);
+        CELDA_CSUB(4);
+        CELDA_TICK(5);
         // after commits the window is topped up with fresh items only once it is less than half full: carried items
         // cost a few patch units and a check, fresh ones a full evaluation and draw, cheaper in batches
-        const bool topup = first || (M == 0 && ndc == 0) || (hi - pos) * 2 < W;
+        const bool topup = first || (M == 0 && !hasDc) || (hi - pos) * 2 < W;
         const long long end = topup ? max(hi, min(pos + (long long)W, a.nM)) : hi;
         const int nwin = (int)(end - pos);
         const int nColU = first ? K : 2 * M;     // cached column sums: every base column once, then the new slots
         const long long nPatch = seg_s[M + 1];   // stale columns of the carried items
         const long long nFresh = (end - hi) * K;
         const long long total = nColU + nPatch + nFresh;
-        const int tag = (int)(rounds & 7);
-        ++rounds;
+        const int tag = roundNo & 7;
+        ++roundNo;
         // ---- A1: units.  Large rounds: one LANE per unit (the lane evaluates and adds its unit's terms serially, no
         // staging, no single-lane phases).  Small rounds (churn): one WARP per unit for latency.  Both orders of
         // evaluation are the reference's, so the results are identical.
@@ -840,9 +1008,9 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                 while (rel >= seg_s[q + 1]) ++q;
                 rel -= seg_s[q];
                 const int wq = nq_s[q];
-                t = ((q == 0) ? pos : cm_t[q - 1] + 1) + rel / wq;
+                t = ((q == 0) ? pos : cb->t[q - 1] + 1) + rel / wq;
                 j = CL_s[rel % wq];
-                slot = slot_of(q, j);
+                slot = bank_slot_of(cb, K, q, j);
             } else {
                 const long long q = uidx - nColU - nPatch;
                 t = hi + q / K;
@@ -904,7 +1072,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
             }
         };
         const bool bigRound = total >= (long long)tw * 16;
-        if (bigRound && useTab) {
+        if (bigRound && useTab && M <= 2) {
             // (1) cached column sums and patch units: one warp each while they are few, else one lane each
             const long long nSmall = nColU + nPatch;
             if (nSmall < (long long)tw * 8) {
@@ -1017,23 +1185,26 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                 warp_unit(t, j, slot);
             }
         }
-        units_done += total;
-        CELDA_TICK(ck_units);
+        if (threadIdx.x == 0) {
+            st_s[0] += 1;
+            st_s[1] += total;
+        }
+        CELDA_TICK(6);
         grid_sync(a.w.barrier, bar_target);
-        CELDA_TICK(ck_bar);
+        CELDA_TICK(8);
         // ---- A2: combine in the reference's order, draw / validate
         double* pl = scr;
         double* rr = scr + K;
         int* perm = reinterpret_cast<int*>(scr + 2 * K);
         // carried items in front of the first tentative commit have nothing stale unless commits were discarded
-        const int cstart = (ndc > 0 || M == 0) ? 0 : (int)(cm_t[0] + 1 - pos);
+        const int cstart = (hasDc || M == 0) ? 0 : (int)(cb->t[0] + 1 - pos);
         for (int c = cstart + gwarpT; c < nwin; c += tw) {
             const long long t = pos + c;
             const bool fresh = t >= hi;
             int q = M;
             if (!fresh) {
                 q = 0;
-                for (int i = 0; i < M; ++i) q += (cm_t[i] < t);
+                for (int i = 0; i < M; ++i) q += (cb->t[i] < t);
             }
             const int ncols = fresh ? K : nq_s[q];
             if (ncols == 0) continue;
@@ -1042,12 +1213,12 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
             const size_t slot = ring_slot(t, a.w.Wmax), o = slot * K;
             const int oldv = fresh ? -1 : __ldcg(a.w.spec + slot);
             auto combine = [&](int j) {
-                const int g = gslot(slot_of(q, j), par);
+                const int g = gslot(bank_slot_of(cb, K, q, j), par);
                 const double S = __ldcg(a.w.bufP + o + j), A = __ldcg(a.w.bufA + o + j);
                 const double cs = __ldcg(a.w.colsum + g), lc = __ldcg(a.w.lgnCP + g);
                 int mm = m_s[si * K + j] - (j == zi);
                 for (int e = 0; e < q; ++e)
-                    if (cm_s[e] == si) mm += (cm_b[e] == j) - (cm_a[e] == j);
+                    if (cb->aux[e] == si) mm += (cb->b[e] == j) - (cb->a[e] == j);
                 double p = dlog((double)mm + a.alpha);
                 if (j != zi) {
                     p = p + S;
@@ -1089,7 +1260,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
                 cheapScore = ok ? min(8, cheapScore + 1) : max(0, cheapScore - 1);
                 if (ok) continue;
             }
-            if (lane == 0 && !fresh) ++redraws;
+            if (lane == 0 && !fresh) atomicAdd(reinterpret_cast<unsigned long long*>(st_s + 4), 1ull);
             for (int j = lane; j < K; j += 32) {
                 const double p = combine(j);
                 pl[j] = p;
@@ -1121,37 +1292,48 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_z(ZArgs a) {
         first = false;
         tagPrev = tag;
         par ^= 1;
-        CELDA_TICK(ck_draw);
+        CELDA_TICK(7);
         grid_sync(a.w.barrier, bar_target);
-        CELDA_TICK(ck_bar);
+        CELDA_TICK(8);
     }
-    if (redraws) atomicAdd(reinterpret_cast<unsigned long long*>(a.w.stats + 7), (unsigned long long)redraws);
-    // ---- write the tables back (CTA 0's copy; all copies are identical)
+    __syncthreads();
+    if (threadIdx.x == 0 && st_s[4]) atomicAdd(reinterpret_cast<unsigned long long*>(a.w.stats + 7), (unsigned long long)st_s[4]);
+    #ifdef CELDA_COMMIT_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int q = 0; q < 6; ++q) a.w.stats[8 + q] += csub[q];
+#endif
+// ---- write the tables back (CTA 0's copy; all copies are identical)
     if (blockIdx.x == 0) {
         for (int q = threadIdx.x; q < R * K; q += blockDim.x) a.nTab[q] = n_s[(q / R) * Rp + (q % R)];
         for (int q = threadIdx.x; q < K; q += blockDim.x) a.nCP[q] = nCP_s[q];
         for (int q = threadIdx.x; q < K * nS; q += blockDim.x) a.mCPByS[q] = m_s[q];
         if (threadIdx.x == 0) {
-            a.w.stats[0] += rounds;
-            a.w.stats[1] += units_done;
-            a.w.stats[2] += movers;
-            atomicAdd(reinterpret_cast<unsigned long long*>(a.w.stats + 7), (unsigned long long)discards << 40);
+            a.w.stats[0] += st_s[0];
+            a.w.stats[1] += st_s[1];
+            a.w.stats[2] += st_s[2];
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.w.stats + 7), (unsigned long long)st_s[3] << 40);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        a.w.stats[3] += ck_commit;
-        a.w.stats[4] += ck_units;
-        a.w.stats[5] += ck_draw;
-        a.w.stats[6] += ck_bar;
+        a.w.stats[3] += st_s[5];
+        a.w.stats[4] += st_s[6];
+        a.w.stats[5] += st_s[7];
+        a.w.stats[6] += st_s[8];
     }
 }
 
-inline size_t z_sweep_smem(int R, int K, int nS, int T, int nwarp, int EsCap = 0, int MC = MCMAX) {
-    const int Rp = R | 1, KS = K + 2 * MC;
+// vtCap: doubles of the buffer shared by the value-table head (EsCap entries) and the commit slots beyond column KB
+inline size_t z_sweep_vtcap(int R, int K, int EsCap, int MC) {
+    const int Rp = R | 1, KS = K + 2 * MC, KB = z_sweep_kb(K, MC);
+    const size_t ext = ((size_t)(KS - KB) * Rp * sizeof(int) + 7) / 8;
+    return std::max((size_t)EsCap, ext);
+}
+inline size_t z_sweep_smem(int R, int K, int nS, int T, int nwarp, int EsCap = 0, int MC = MCMAX - 1) {
+    const int Rp = R | 1, KS = K + 2 * MC, KB = z_sweep_kb(K, MC);
     const size_t scratchD = (size_t)std::max(R, 2 * K + (K + 1) / 2) + 2;
-    return sizeof(double) * (T + nwarp * scratchD + EsCap) + sizeof(long long) * (KS + MCMAX) +
-           sizeof(int) * ((size_t)KS * Rp + K * nS + (R + 1) + ZT_MAXGRP + 3 + 4 * (size_t)K + 8 * MCMAX + (MCMAX + 1) +
-                          (MCMAX + 2) + 40);
+    return sizeof(double) * (T + nwarp * scratchD + z_sweep_vtcap(R, K, EsCap, MC)) + sizeof(long long) * KS +
+           2 * sizeof(CommitBank) + 12 * sizeof(long long) +
+           sizeof(int) * ((size_t)KB * Rp + K * nS + (R + 1) + ZT_MAXGRP + 3 + 3 * (size_t)K + (MCMAX + 1) + (MCMAX + 2) + 144);
 }
 
 // xT[r][t] = counts[r, ix[t] - 1]: the count matrix in visiting order, transposed, so that lanes holding
@@ -1284,23 +1466,16 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
     double* tail_s = lgt_s + (size_t)LS * Cp;            // [LS][7] module-only terms of the second loop
     double* scratch_all = tail_s + (size_t)LS * 7;
     long long* T_s = reinterpret_cast<long long*>(scratch_all + (size_t)nwarp * scratchD);  // [LS]
-    long long* cm_t = T_s + LS;                          // [MCMAX] positions of the tentative commits
-    long long* cm_N = cm_t + MCMAX;                      // [MCMAX] their gene totals
-    int* t_s = reinterpret_cast<int*>(cm_N + MCMAX);     // [LS][Cp]
+    CommitBank* banks = reinterpret_cast<CommitBank*>(T_s + LS);  // [2] tentative commits of this round / the last
+    long long* st_s = reinterpret_cast<long long*>(banks + 2);  // [12] statistics and CTA-0 clocks (thread 0)
+    int* t_s = reinterpret_cast<int*>(st_s + 12);        // [LS][Cp]
     int* g_s = t_s + (size_t)LS * Cp;                    // [LS]
     int* fin_s = g_s + LS;                               // [L] slot of row l with every tentative commit applied
     int* CL_s = fin_s + L;                               // [L] stale-row list: Dcarry first, then the commits' rows in order
-    int* inCL_s = CL_s + L;                              // [L]
-    int* dc_s = inCL_s + L;                              // [L] Dcarry
-    int* cm_a = dc_s + L;                                // [MCMAX] each
-    int* cm_b = cm_a + MCMAX;
-    int* cm_gene = cm_b + MCMAX;
-    int* cm_srcA = cm_gene + MCMAX;
-    int* cm_srcB = cm_srcA + MCMAX;
-    int* cm_pk = cm_srcB + MCMAX;
-    int* nq_s = cm_pk + MCMAX;                           // [MCMAX + 1]
+    int* dc_s = CL_s + L;                                // [L] Dcarry
+    int* nq_s = dc_s + L;                                // [MCMAX + 1]
     int* seg_s = nq_s + MCMAX + 1;                       // [MCMAX + 2]
-    int* s_misc = seg_s + MCMAX + 2;                     // [40]
+    int* s_misc = seg_s + MCMAX + 2;                     // [144]
     double* scr = scratch_all + (size_t)warp * scratchD;
     const int gwarp = blockIdx.x * nwarp + warp, tw = gridDim.x * nwarp;
     // warp-granular work goes round the CTAs first (item c -> CTA c mod grid), so a short list of items lands on
@@ -1316,6 +1491,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
     }
     if (threadIdx.x <= MCMAX) nq_s[threadIdx.x] = 0;
     if (threadIdx.x <= MCMAX + 1) seg_s[threadIdx.x] = 0;
+    CommitBank* cb = banks;
     __syncthreads();
     for (int q = threadIdx.x; q < L * C; q += blockDim.x) {
         const int l = q / C, c = q % C;
@@ -1343,149 +1519,131 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
     __syncthreads();
 
     long long pos = 0, hi = 0, prev_end = 0;
-    int W = a.w.Wfull, gavg = a.w.Wfull, M = 0, ndc = 0, mcAimd = MC, tagPrev = 0;
+    int W = a.w.Wfull, gavg = a.w.Wfull, M = 0, mcAimd = MC, par = 0, tagPrev = 0;
     bool have_spec = false, first = true;
     unsigned bar_target = 0;
-    long long rounds = 0, units_done = 0, movers = 0, discards = 0;
-    long long redraws = 0;  // carried items drawn again in full (this thread's share)
+    int roundNo = 0;
     int cheapScore = 4, cheapTick = 0;
-    long long ck_commit = 0, ck_units = 0, ck_draw = 0, ck_bar = 0, ck0 = clock64(), ck1;
+    if (threadIdx.x < 12) st_s[threadIdx.x] = (threadIdx.x == 9) ? clock64() : 0;  // 0 rounds 1 units 2 movers 3 discards 4 redraws 5..8 clocks
+    __syncthreads();
 
-    // slot of row l for an item with q tentative commits in front of it
-    auto slot_of = [&](int q, int l) {
-        for (int i = q - 1; i >= 0; --i) {
-            if (cm_b[i] == l) return L + 2 * i + 1;
-            if (cm_a[i] == l) return L + 2 * i;
-        }
-        return l;
-    };
     auto window_for = [&](int g, int mc) -> int {
         const long long target = (long long)g * (mc + 4);
         if (target >= a.w.Wunit) return (int)min((target / a.w.Wunit) * a.w.Wunit, (long long)a.w.Wfull);
         return (int)max((long long)a.w.Wmin, target);
     };
 
+    long long csub[6] = {0, 0, 0, 0, 0, 0}, csub0 = 0;
+    (void)csub; (void)csub0;
     while (true) {
         // ---- settle the previous round: which tentative commits stand, where the window restarts, the next commits
+        CELDA_CSUB_BEGIN();
+        CommitBank* ob = cb;              // the finished round's commits
+        cb = banks + par;                 // this round's
+        bool hasDc = false;
         if (have_spec) {
             const int nwinPrev = (int)(prev_end - pos);
-            const int f = block_first_invalid(a.w.spec, pos, a.w.Wmax, nwinPrev, tagPrev, s_misc);
+            bool anyMover;
+            const int f = block_first_invalid(a.w.spec, pos, a.w.Wmax, nwinPrev, tagPrev, s_misc, anyMover);
+            CELDA_CSUB(0);
             const long long tf = pos + f;
-            int qf = M;
+            const int Mold = M;
+            int qf = Mold;
             if (f >= 0) {
                 qf = 0;
-                for (int i = 0; i < M; ++i) qf += (cm_t[i] < tf);
+                for (int i = 0; i < Mold; ++i) qf += (ob->t[i] < tf);
             }
-            // standing commits advance the base rows (in order: a later commit's slot supersedes an earlier one's)
-            for (int c = threadIdx.x; c < C + 7; c += blockDim.x)
-                for (int i = 0; i < qf; ++i)
-                    for (int side = 0; side < 2; ++side) {
-                        const int dst = side ? cm_b[i] : cm_a[i], src = L + 2 * i + side;
-                        if (c < C) {
-                            t_s[dst * Cp + c] = t_s[src * Cp + c];
-                            lgt_s[dst * Cp + c] = lgt_s[src * Cp + c];
-                        } else {
-                            tail_s[dst * 7 + (c - C)] = tail_s[src * 7 + (c - C)];
-                        }
-                    }
-            if (threadIdx.x == blockDim.x - 1) {
-                for (int i = 0; i < qf; ++i) {
-                    const int ca = cm_a[i], cb = cm_b[i];
-                    g_s[ca] = g_s[L + 2 * i];
-                    g_s[cb] = g_s[L + 2 * i + 1];
-                    T_s[ca] = T_s[L + 2 * i];
-                    T_s[cb] = T_s[L + 2 * i + 1];
-                    if (blockIdx.x == 0) a.y[cm_gene[i]] = cb + 1;
-                }
-                int nd_ = 0;  // Dcarry: the rows of the discarded commits
-                for (int i = qf; i < M; ++i)
-                    for (int side = 0; side < 2; ++side) {
-                        const int c = side ? cm_b[i] : cm_a[i];
-                        bool seen = false;
-                        for (int d = 0; d < nd_; ++d) seen |= (dc_s[d] == c);
-                        if (!seen) dc_s[nd_++] = c;
-                    }
-                s_misc[1] = nd_;
-            }
+            hasDc = qf < Mold;
             const long long oldpos = pos;
-            if (qf < M) pos = tf;  // no unselected mover can lie in front of a discarded selected one
-            else if (M > 0) pos = cm_t[M - 1] + 1;
-            __syncthreads();
-            ndc = s_misc[1];
-            movers += qf;
-            discards += M - qf;
-            if (M > 0) mcAimd = (qf == M) ? min(MC, 2 * mcAimd) : max(1, qf + 1);
+            if (qf < Mold) pos = tf;  // no unselected mover can lie in front of a discarded selected one
+            else if (Mold > 0) pos = ob->t[Mold - 1] + 1;
+            if (threadIdx.x == 0) {
+                st_s[2] += qf;
+                st_s[3] += Mold - qf;
+            }
+            if (Mold > 0) mcAimd = (qf == Mold) ? min(MC, 2 * mcAimd) : max(1, qf + 1);
             if (qf > 0) gavg = max(1, (int)((3LL * gavg + max(1LL, (pos - oldpos) / qf)) / 4));
-            int mcCur = min(mcAimd, mc_target(gavg, MC));
+            const int mcCur = min(mcAimd, mc_target(gavg, MC));
             W = window_for(gavg, mcCur);
             hi = min(prev_end, pos + W);
-            M = block_select_movers(a.w.spec, pos, a.w.Wmax, (int)(hi - pos), mcCur, cm_t, cm_pk, s_misc + 2);
-            if (M == 0 && ndc == 0) {  // nothing moves and nothing is stale: the carried items are settled
+            const int nsel = (int)(hi - pos);
+            const bool wideSel = nsel > 1024;  // a large window is scanned by the whole block, a small one by warp 0
+            int Mwide = 0;
+            if (wideSel && anyMover) Mwide = block_select_movers(a.w.spec, pos, a.w.Wmax, nsel, mcCur, cb->t, cb->pk, s_misc + 2);
+            if (warp == 0) {
+                // one warp: Dcarry, the next commits and their records, source slots, stale list, segments
+                const int ndc = warp_build_dcarry(ob, qf, Mold, dc_s, lane);
+                const int Mn = wideSel ? Mwide : (anyMover ? warp_select_movers(a.w.spec, pos, a.w.Wmax, nsel, mcCur, cb, lane) : 0);
+                __syncwarp();
+                if (lane < Mn) {
+                    const int gene = a.ix[cb->t[lane]] - 1, pk = cb->pk[lane];
+                    cb->item[lane] = gene;
+                    cb->a[lane] = pk >> 16;
+                    cb->b[lane] = pk & 0xffff;
+                    cb->N[lane] = a.nByG[gene];
+                }
+                __syncwarp();
+                warp_build_lists(cb, L, Mn, ndc, dc_s, CL_s, nq_s, seg_s, pos, hi, lane);
+                if (lane == 0) s_misc[140] = Mn;
+            } else {
+                // the other warps: standing commits advance the base rows (in order: a later commit's slot supersedes
+                // an earlier one's) and the per-row scalars
+                for (int c = threadIdx.x - 32; c < C + 7; c += blockDim.x - 32)
+                    for (int i = 0; i < qf; ++i)
+                        for (int side = 0; side < 2; ++side) {
+                            const int dst = side ? ob->b[i] : ob->a[i], src = L + 2 * i + side;
+                            if (c < C) {
+                                t_s[dst * Cp + c] = t_s[src * Cp + c];
+                                lgt_s[dst * Cp + c] = lgt_s[src * Cp + c];
+                            } else {
+                                tail_s[dst * 7 + (c - C)] = tail_s[src * 7 + (c - C)];
+                            }
+                        }
+                for (int j = (int)blockDim.x - 1 - (int)threadIdx.x; j < L; j += blockDim.x - 32) {
+                    const int sl = bank_slot_of(ob, L, qf, j);
+                    if (sl != j) {
+                        g_s[j] = g_s[sl];
+                        T_s[j] = T_s[sl];
+                    }
+                }
+                if (warp == 1 && lane < qf && blockIdx.x == 0) a.y[ob->item[lane]] = ob->b[lane] + 1;
+            }
+            __syncthreads();
+            M = s_misc[140];
+            CELDA_CSUB(1);
+            if (M == 0 && !hasDc) {  // nothing moves and nothing is stale: the carried items are settled
                 gavg = (int)min(2LL * gavg + (hi - pos), (long long)(1 << 24));
                 pos = hi;
-                mcCur = min(mcAimd, mc_target(gavg, MC));
-                W = window_for(gavg, mcCur);
+                W = window_for(gavg, min(mcAimd, mc_target(gavg, MC)));
             }
         }
         if (pos >= a.nG) break;
-        // ---- this round's tentative commits: records, source slots, stale-row list, new row slots
-        if (threadIdx.x < M) {
-            const int i = threadIdx.x;
-            const int gene = a.ix[cm_t[i]] - 1, pk = cm_pk[i];
-            cm_gene[i] = gene;
-            cm_a[i] = pk >> 16;
-            cm_b[i] = pk & 0xffff;
-            cm_N[i] = a.nByG[gene];
-        }
-        for (int j = threadIdx.x; j < L; j += blockDim.x) inCL_s[j] = 0;
-        __syncthreads();
-        if (threadIdx.x < M) {
-            cm_srcA[threadIdx.x] = slot_of(threadIdx.x, cm_a[threadIdx.x]);
-            cm_srcB[threadIdx.x] = slot_of(threadIdx.x, cm_b[threadIdx.x]);
-        }
-        if (threadIdx.x == 32) {
-            int n = 0;
-            for (int d = 0; d < ndc; ++d) {
-                CL_s[n++] = dc_s[d];
-                inCL_s[dc_s[d]] = 1;
+        CELDA_CSUB(2);
+        // ---- this round's tentative commits: new row slots
+        CELDA_CSUB(3);
+        {
+            // the movers' count rows, all loads in flight at once (staged in the warp scratch, idle here)
+            int* xs = reinterpret_cast<int*>(scratch_all);
+            for (int q = threadIdx.x; q < M * C; q += blockDim.x) {
+                const int i = q / C, c = q - i * C;
+                xs[q] = __ldg(a.counts + (size_t)cb->item[i] * C + c);
             }
-            nq_s[0] = n;
-            for (int i = 0; i < M; ++i) {
-                if (!inCL_s[cm_a[i]]) {
-                    CL_s[n++] = cm_a[i];
-                    inCL_s[cm_a[i]] = 1;
+            __syncthreads();
+            for (int c = threadIdx.x; c < C; c += blockDim.x)
+                for (int i = 0; i < M; ++i) {
+                    const int xv = xs[i * C + c];
+                    t_s[(L + 2 * i) * Cp + c] = t_s[cb->srcA[i] * Cp + c] - xv;
+                    t_s[(L + 2 * i + 1) * Cp + c] = t_s[cb->srcB[i] * Cp + c] + xv;
                 }
-                if (!inCL_s[cm_b[i]]) {
-                    CL_s[n++] = cm_b[i];
-                    inCL_s[cm_b[i]] = 1;
-                }
-                nq_s[i + 1] = n;
-            }
-            long long prevLast = pos - 1;
-            seg_s[0] = 0;
-            for (int q = 0; q <= M; ++q) {
-                const long long last = (q < M) ? cm_t[q] : hi - 1;
-                const long long len = max(0LL, last - prevLast);
-                seg_s[q + 1] = seg_s[q] + (int)len * nq_s[q];
-                prevLast = max(prevLast, last);
-            }
-        }
-        __syncthreads();
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
-            for (int i = 0; i < M; ++i) {
-                const int xv = __ldg(a.counts + (size_t)cm_gene[i] * C + c);
-                t_s[(L + 2 * i) * Cp + c] = t_s[cm_srcA[i] * Cp + c] - xv;
-                t_s[(L + 2 * i + 1) * Cp + c] = t_s[cm_srcB[i] * Cp + c] + xv;
-            }
         }
         if (threadIdx.x == blockDim.x - 1)
             for (int i = 0; i < M; ++i) {
-                g_s[L + 2 * i] = g_s[cm_srcA[i]] - 1;
-                g_s[L + 2 * i + 1] = g_s[cm_srcB[i]] + 1;
-                T_s[L + 2 * i] = T_s[cm_srcA[i]] - cm_N[i];
-                T_s[L + 2 * i + 1] = T_s[cm_srcB[i]] + cm_N[i];
+                g_s[L + 2 * i] = g_s[cb->srcA[i]] - 1;
+                g_s[L + 2 * i + 1] = g_s[cb->srcB[i]] + 1;
+                T_s[L + 2 * i] = T_s[cb->srcA[i]] - cb->N[i];
+                T_s[L + 2 * i + 1] = T_s[cb->srcB[i]] + cb->N[i];
             }
-        for (int j = threadIdx.x; j < L; j += blockDim.x) fin_s[j] = slot_of(M, j);
+        for (int j = threadIdx.x; j < L; j += blockDim.x) fin_s[j] = bank_slot_of(cb, L, M, j);
         __syncthreads();
         for (int q = threadIdx.x; q < 2 * M * (C + 7); q += blockDim.x) {
             const int sl = L + q / (C + 7), c = q % (C + 7);
@@ -1495,17 +1653,18 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                 tail_fill(sl, c - C);
         }
         __syncthreads();
-        CELDA_TICK(ck_commit);
+        CELDA_CSUB(4);
+        CELDA_TICK(5);
         // after commits the window is topped up with fresh items only once it is less than half full: carried items
         // cost a few patch units and a check, fresh ones a full evaluation and draw, cheaper in batches
-        const bool topup = first || (M == 0 && ndc == 0) || (hi - pos) * 2 < W;
+        const bool topup = first || (M == 0 && !hasDc) || (hi - pos) * 2 < W;
         const long long end = topup ? max(hi, min(pos + (long long)W, (long long)a.nG)) : hi;
         const int nwin = (int)(end - pos);
         const long long nPatch = seg_s[M + 1];
         const long long nFresh = (end - hi) * L;
         const long long total = nPatch + nFresh;
-        const int tag = (int)(rounds & 7);
-        ++rounds;
+        const int tag = roundNo & 7;
+        ++roundNo;
         // unit index -> (position t, module l, row slot)
         auto decode = [&](long long uidx, long long& t, int& l, int& slot) {
             if (uidx < nPatch) {
@@ -1513,9 +1672,9 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                 while (rel >= seg_s[q + 1]) ++q;
                 rel -= seg_s[q];
                 const int wq = nq_s[q];
-                t = ((q == 0) ? pos : cm_t[q - 1] + 1) + rel / wq;
+                t = ((q == 0) ? pos : cb->t[q - 1] + 1) + rel / wq;
                 l = CL_s[rel % wq];
-                slot = slot_of(q, l);
+                slot = bank_slot_of(cb, L, q, l);
             } else {
                 const long long q = uidx - nPatch;
                 t = hi + q / L;
@@ -1626,22 +1785,25 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                 __syncwarp();
             }
         }
-        units_done += total;
-        CELDA_TICK(ck_units);
+        if (threadIdx.x == 0) {
+            st_s[0] += 1;
+            st_s[1] += total;
+        }
+        CELDA_TICK(6);
         grid_sync(a.w.barrier, bar_target);
-        CELDA_TICK(ck_bar);
+        CELDA_TICK(8);
         double* pl = scr;
         double* rr = scr + L;
         int* perm = reinterpret_cast<int*>(scr + 2 * L);
         // carried items in front of the first tentative commit have nothing stale unless commits were discarded
-        const int cstart = (ndc > 0 || M == 0) ? 0 : (int)(cm_t[0] + 1 - pos);
+        const int cstart = (hasDc || M == 0) ? 0 : (int)(cb->t[0] + 1 - pos);
         for (int c = cstart + gwarpT; c < nwin; c += tw) {
             const long long t = pos + c;
             const bool fresh = t >= hi;
             int q = M;
             if (!fresh) {
                 q = 0;
-                for (int i = 0; i < M; ++i) q += (cm_t[i] < t);
+                for (int i = 0; i < M; ++i) q += (cb->t[i] < t);
             }
             const int ncols = fresh ? L : nq_s[q];
             if (ncols == 0) continue;
@@ -1674,7 +1836,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
                 cheapScore = ok ? min(8, cheapScore + 1) : max(0, cheapScore - 1);
                 if (ok) continue;
             }
-            if (lane == 0 && !fresh) ++redraws;
+            if (lane == 0 && !fresh) atomicAdd(reinterpret_cast<unsigned long long*>(st_s + 4), 1ull);
             for (int l = lane; l < L; l += 32) {
                 const double p = __ldcg(a.w.bufP + o + l);
                 pl[l] = p;
@@ -1705,11 +1867,17 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
         have_spec = true;
         first = false;
         tagPrev = tag;
-        CELDA_TICK(ck_draw);
+        par ^= 1;
+        CELDA_TICK(7);
         grid_sync(a.w.barrier, bar_target);
-        CELDA_TICK(ck_bar);
+        CELDA_TICK(8);
     }
-    if (redraws) atomicAdd(reinterpret_cast<unsigned long long*>(a.w.stats + 7), (unsigned long long)redraws);
+    __syncthreads();
+    if (threadIdx.x == 0 && st_s[4]) atomicAdd(reinterpret_cast<unsigned long long*>(a.w.stats + 7), (unsigned long long)st_s[4]);
+#ifdef CELDA_COMMIT_PROF
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int q = 0; q < 6; ++q) a.w.stats[8 + q] += csub[q];
+#endif
     if (blockIdx.x == 0) {
         for (int q = threadIdx.x; q < L * C; q += blockDim.x) a.tTab[q] = t_s[(q % L) * Cp + (q / L)];
         for (int q = threadIdx.x; q < L; q += blockDim.x) {
@@ -1717,25 +1885,25 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_y(YArgs a) {
             a.nGByTS[q] = g_s[q];
         }
         if (threadIdx.x == 0) {
-            a.w.stats[0] += rounds;
-            a.w.stats[1] += units_done;
-            a.w.stats[2] += movers;
-            atomicAdd(reinterpret_cast<unsigned long long*>(a.w.stats + 7), (unsigned long long)discards << 40);
+            a.w.stats[0] += st_s[0];
+            a.w.stats[1] += st_s[1];
+            a.w.stats[2] += st_s[2];
+            atomicAdd(reinterpret_cast<unsigned long long*>(a.w.stats + 7), (unsigned long long)st_s[3] << 40);
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        a.w.stats[3] += ck_commit;
-        a.w.stats[4] += ck_units;
-        a.w.stats[5] += ck_draw;
-        a.w.stats[6] += ck_bar;
+        a.w.stats[3] += st_s[5];
+        a.w.stats[4] += st_s[6];
+        a.w.stats[5] += st_s[7];
+        a.w.stats[6] += st_s[8];
     }
 }
 
-inline size_t y_sweep_smem(int L, int C, int T, int nwarp, int MC = MCMAX) {
+inline size_t y_sweep_smem(int L, int C, int T, int nwarp, int MC = MCMAX - 1) {
     const int Cp = C | 1, LS = L + 2 * MC;
     const size_t scratchD = (size_t)std::max(2 * C + 8, 2 * L + (L + 1) / 2) + 2;
-    return sizeof(double) * (T + (size_t)LS * Cp + (size_t)LS * 7 + nwarp * scratchD) + sizeof(long long) * (LS + 2 * MCMAX) +
-           sizeof(int) * ((size_t)LS * Cp + LS + 4 * (size_t)L + 6 * MCMAX + (MCMAX + 1) + (MCMAX + 2) + 40);
+    return sizeof(double) * (T + (size_t)LS * Cp + (size_t)LS * 7 + nwarp * scratchD) + sizeof(long long) * LS +
+           2 * sizeof(CommitBank) + 12 * sizeof(long long) + sizeof(int) * ((size_t)LS * Cp + LS + 3 * (size_t)L + (MCMAX + 1) + (MCMAX + 2) + 144);
 }
 
 // ------------------------------------------------------------------------------------------------ y sweep, celda_G
@@ -1853,7 +2021,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
         }
         if (pos >= a.nG) break;
         if (committed) grid_sync(a.w.barrier, bar_target);  // table rows a, b are visible before they are read
-        CELDA_TICK(ck_commit);
+        CELDA_TICKR(ck_commit);
         // after a commit the window is topped up with fresh items only once it is less than half full: carried items
         // cost two patch units and a check (draw_unchanged), fresh ones a full evaluation and draw, cheaper in batches
         const bool topup = nd != 2 || (hi - pos) * 2 < W;
@@ -1960,9 +2128,9 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
             }
         }
         units_done += ntask;
-        CELDA_TICK(ck_units);
+        CELDA_TICKR(ck_units);
         grid_sync(a.w.barrier, bar_target);
-        CELDA_TICK(ck_bar);
+        CELDA_TICKR(ck_bar);
         double* pl = scr;
         double* rr = scr + L;
         int* perm = reinterpret_cast<int*>(scr + 2 * L);
@@ -2008,9 +2176,9 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
         }
         prev_end = end;
         have_spec = true;
-        CELDA_TICK(ck_draw);
+        CELDA_TICKR(ck_draw);
         grid_sync(a.w.barrier, bar_target);
-        CELDA_TICK(ck_bar);
+        CELDA_TICKR(ck_bar);
     }
     if (redraws) atomicAdd(reinterpret_cast<unsigned long long*>(a.w.stats + 7), (unsigned long long)redraws);
     __syncthreads();  // thread 0's last commit (a mover in the final position) precedes the write-back
