@@ -77,22 +77,25 @@ __device__ __noinline__ void revsort_serial(double* a, int* ib, int n) {
 // >= +0 and adding +0.0 to a non-negative partial sum is the identity, so zeros are skipped: a chunk of 32 with few
 // positive entries is added through shuffles, a dense chunk by a serial loop over shared memory (broadcast reads).
 __device__ __forceinline__ double warp_ordered_sum_pos(const double* r, int n, int lane) {
+    // few positive entries overall: chunk by chunk through shuffles
+    int npos = 0;
+    for (int base = 0; base < n; base += 32) npos += __popc(__ballot_sync(0xffffffffu, base + lane < n && r[base + lane] > 0.0));
     double s = 0.0;
-    for (int base = 0; base < n; base += 32) {
-        const double v = (base + lane < n) ? r[base + lane] : 0.0;
-        unsigned m = __ballot_sync(0xffffffffu, v > 0.0);
-        if (__popc(m) <= 6) {
+    if (npos <= 12) {
+        for (int base = 0; base < n; base += 32) {
+            const double v = (base + lane < n) ? r[base + lane] : 0.0;
+            unsigned m = __ballot_sync(0xffffffffu, v > 0.0);
             while (m) {
                 const int b = __ffs(m) - 1;
                 m &= m - 1;
                 s += shfl_d(v, b);
             }
-        } else {
-            const int e = min(n, base + 32);
-#pragma unroll 4
-            for (int i = base; i < e; ++i) s += r[i];
         }
+        return s;
     }
+    // dense vector: one serial pass, loads (broadcast) running ahead of the dependent adds
+#pragma unroll 8
+    for (int i = 0; i < n; ++i) s += r[i];
     return s;
 }
 
@@ -170,6 +173,12 @@ __device__ int warp_sample_ll(double* pl, int n, double u, double* r, int* perm,
             P += __popc(m);
         }
         __syncwarp();
+        if (P == 1 && u <= 1.0) {  // a single positive entry: e = 1 exactly, q = 1 / 1 / 1, and u <= 1 selects it at the first position
+            const int res = perm[0];
+            __syncwarp();
+            CELDA_DBG_ADD(1);
+            return res;
+        }
         if (P >= 1 && P <= 32) {
             const int myIdx = (lane < P) ? perm[lane] : -1;
             const double myE = (lane < P) ? hs[lane] : 0.0;
@@ -298,26 +307,39 @@ __device__ int warp_sample_ll(double* pl, int n, double u, double* r, int* perm,
     if (!slow && result < 0) {
         CELDA_DBG_ADD(3);
         // Rank sort of the positive entries (hs aliases pl, which is no longer needed): position = number of larger
-        // values.  Any exact tie among positive entries leaves the order to heapsort => exact path.
+        // values.  Entries are >= +0, so their bit patterns order like the values and integer compares leave the FP64
+        // pipe alone.  A lane keeps up to five of its entries in registers and passes over the vector once per group.
+        // Any exact tie among positive entries leaves the order to heapsort => exact path.
         bool tie = false;
-        for (int i = lane; i < n; i += 32) {
-            const double ri = r[i];
-            if (ri > 0.0) {
-                // entries are >= +0: their bit patterns order like the values, and integer compares leave the FP64 pipe alone
-                const long long bi = __double_as_longlong(ri);
-                const long long* rb = reinterpret_cast<const long long*>(r);
-                int gt = 0, eq = 0;
-#pragma unroll 4
-                for (int j = 0; j < n; ++j) {
-                    const long long v = rb[j];
-                    gt += (v > bi);
-                    eq += (v == bi);
+        const long long* rb = reinterpret_cast<const long long*>(r);
+        for (int q = lane; q < n; q += 32) perm[q] = -1;
+        __syncwarp();
+        for (int i0 = lane; i0 < n; i0 += 160) {
+            long long b[5];
+            int gt[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const int idx = i0 + 32 * q;
+                b[q] = (idx < n) ? rb[idx] : 0;
+                gt[q] = 0;
+            }
+#pragma unroll 2
+            for (int j = 0; j < n; ++j) {
+                const long long v = rb[j];
+#pragma unroll
+                for (int q = 0; q < 5; ++q) gt[q] += (v > b[q]);
+            }
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+                const int idx = i0 + 32 * q;
+                if (idx < n && b[q] > 0) {
+                    hs[gt[q]] = __longlong_as_double(b[q]);
+                    perm[gt[q]] = idx;
                 }
-                tie |= (eq > 1);
-                hs[gt] = ri;
-                perm[gt] = i;
             }
         }
+        __syncwarp();
+        for (int q = lane; q < P; q += 32) tie |= (perm[q] < 0);  // equal entries share a position and leave a hole behind it
         __syncwarp();
         if (__any_sync(FULL, tie)) {
             slow = true;

@@ -63,27 +63,41 @@ def _run_chain(ch, algorithm, maxIter, stopIter, draws, rng, nG, nM, model):
     return dict(z=zBest, y=yBest, completeLogLik=np.asarray(ll), finalLogLik=llBest)
 
 
+def _celda_CG_chain(ch, c, K, L, seed, algorithm, maxIter, stopIter, zInitialize, yInitialize, zInit, yInit, draws):
+    """Chain number c (1-based) of .celda_CG on a resident handle already sized for (K, L) (R/celda_CG.R:432-790)."""
+    nG, nM = ch.nG, ch.nM
+    rng = np.random.Generator(np.random.PCG64(seed + c - 1))
+    z = initialize_cluster(K, nM, zInit if zInitialize == "predefined" else None, rng)
+    y = initialize_cluster(L, nG, yInit if yInitialize == "predefined" else None, rng)
+    ch.set_state(z, y)
+    ch.seed(seed, stream=c - 1)
+    return _run_chain(ch, algorithm, maxIter, stopIter, draws, rng, nG, nM, MODEL_CG)
+
+
 def celda_CG(counts, sampleLabel, K, L, alpha=1.0, beta=1.0, delta=1.0, gamma=1.0, algorithm="EM", stopIter=10,
              maxIter=200, seed=12345, nchains=3, zInitialize="random", yInitialize="random", zInit=None, yInit=None,
-             draws="philox", device=0):
+             draws="philox", device=0, chain=None):
     """celda_CG(x, sampleLabel, K, L, ...) (R/celda_CG.R:85-261) on a CSC count matrix, split heuristics off.
     Returns the per-chain results and `model`, built like the reference from the LAST chain (quirk Q1,
-    R/celda_CG.R:796-811)."""
+    R/celda_CG.R:796-811).  `chain`: a resident handle over the same counts and hyper-parameters to re-use
+    (celdaGridSearch); it is re-sized to (K, L) and left open."""
     if algorithm not in ("EM", "Gibbs"):
         raise ValueError("'algorithm' must be 'EM' or 'Gibbs'")
     chains = []
-    ch = Chain(counts, sampleLabel, K=K, L=L, alpha=alpha, beta=beta, delta=delta, gamma=gamma, model=MODEL_CG,
-               device=device)
+    if chain is None:
+        ch = Chain(counts, sampleLabel, K=K, L=L, alpha=alpha, beta=beta, delta=delta, gamma=gamma, model=MODEL_CG,
+                   device=device)
+    else:
+        ch = chain
+        if (ch.K, ch.L) != (int(K), int(L)):
+            ch.reconfigure(K, L)
     try:
         for c in range(1, nchains + 1):
-            rng = np.random.Generator(np.random.PCG64(seed + c - 1))
-            z = initialize_cluster(K, counts.ncol, zInit if zInitialize == "predefined" else None, rng)
-            y = initialize_cluster(L, counts.nrow, yInit if yInitialize == "predefined" else None, rng)
-            ch.set_state(z, y)
-            ch.seed(seed, stream=c - 1)
-            chains.append(_run_chain(ch, algorithm, maxIter, stopIter, draws, rng, counts.nrow, counts.ncol, MODEL_CG))
+            chains.append(_celda_CG_chain(ch, c, K, L, seed, algorithm, maxIter, stopIter, zInitialize, yInitialize,
+                                          zInit, yInit, draws))
     finally:
-        ch.close()
+        if chain is None:
+            ch.close()
     best = max(range(nchains), key=lambda i: chains[i]["finalLogLik"])
     return dict(chains=chains, model=chains[-1], bestChain=best + 1,
                 params=dict(K=K, L=L, alpha=alpha, beta=beta, delta=delta, gamma=gamma, algorithm=algorithm, seed=seed))
@@ -168,30 +182,62 @@ def partition_runs(runs, nranks, cost=lambda r: r.get("K", 1) * r.get("L", 1)):
     return out
 
 
+def run_order(runs, cost=lambda r: r.get("K", 1) * r.get("L", 1)):
+    """Longest-first order of the grid-search runs (indices into `runs`), the order a shared work queue hands them out."""
+    return sorted(range(len(runs)), key=lambda i: (-cost(runs[i]), i))
+
+
 def celdaGridSearch(counts, sampleLabel, paramsTest, maxIter=200, nchains=3, seed=12345, algorithm="Gibbs",
-                    rank=0, nranks=1, device=0, runner=None, gather=None, **fixed):
+                    rank=0, nranks=1, device=0, runner=None, gather=None, queue=None, **fixed):
     """celdaGridSearch(x, model = "celda_CG", paramsTest, nchains, ...) (R/celdaGridSearch.R:214-439): every
-    (chain, K, L) run is an independent single-chain celda_CG; runs are partitioned over `nranks` GPUs (this rank
-    executes its share), then gathered.  `runner(run, seed)` -> result dict can be injected (tests); `gather` is a
-    callable all-gathering picklable objects across ranks (torch.distributed.all_gather_object in bench/tests)."""
+    (chain, K, L) run is an independent single-chain celda_CG on the SAME counts (:290-391).  Each rank keeps one
+    resident chain handle (counts uploaded and gene-major twin built once) and re-sizes it per run
+    (celda_chain_reconfigure).  Work distribution over `nranks` GPUs: `queue` -- a callable returning the next
+    position (0-based, shared atomic counter, e.g. a torch.distributed store `add`) in the longest-first order, so a
+    GPU pulls the next run when it finishes one -- or, without a queue, the static longest-processing-time partition.
+    `runner(run, seed)` -> result dict can be injected (tests); `gather` all-gathers picklable objects across ranks."""
+    import time
     runs = expand_grid(paramsTest, nchains)
-    mine = partition_runs(runs, nranks)[rank]
+    resident = {"ch": None}
 
     def default_runner(run, sd):
+        if resident["ch"] is None:
+            hyper = {k: fixed[k] for k in ("alpha", "beta", "delta", "gamma") if k in fixed}
+            resident["ch"] = Chain(counts, sampleLabel, K=run["K"], L=run["L"], model=MODEL_CG, device=device, **hyper)
         res = celda_CG(counts, sampleLabel, run["K"], run["L"], maxIter=maxIter, nchains=1, seed=sd,
-                       algorithm=algorithm, device=device, **fixed)
+                       algorithm=algorithm, device=device, chain=resident["ch"], **fixed)
         return res["model"]
 
     runner = runner or default_runner
+    if queue is None:
+        mine = iter(partition_runs(runs, nranks)[rank])
+    else:
+        order = run_order(runs)
+
+        def pull():
+            while True:
+                k = queue()
+                if k >= len(order):
+                    return
+                yield runs[order[k]]
+
+        mine = pull()
     local = []
-    for run in mine:
-        sd = chain_seed(seed, run["index"], nchains)
-        res = runner(run, sd)
-        local.append(dict(index=run["index"], chain=run["chain"], K=run.get("K"), L=run.get("L"), seed=sd,
-                          logLikelihood=float(res["finalLogLik"]), result=res))
+    try:
+        for run in mine:
+            sd = chain_seed(seed, run["index"], nchains)
+            t0 = time.perf_counter()
+            res = runner(run, sd)
+            local.append(dict(index=run["index"], chain=run["chain"], K=run.get("K"), L=run.get("L"), seed=sd,
+                              logLikelihood=float(res["finalLogLik"]), seconds=time.perf_counter() - t0, rank=rank,
+                              result=res))
+    finally:
+        if resident["ch"] is not None:
+            resident["ch"].close()
     everything = [local] if gather is None else gather(local)
     flat = sorted((r for part in everything for r in part), key=lambda r: r["index"])
-    return dict(runParams=[{k: r[k] for k in ("index", "chain", "K", "L", "seed", "logLikelihood")} for r in flat],
+    return dict(runParams=[{k: r[k] for k in ("index", "chain", "K", "L", "seed", "logLikelihood", "seconds", "rank")}
+                           for r in flat],
                 resList=[r["result"] for r in flat])
 
 
