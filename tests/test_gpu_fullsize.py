@@ -81,3 +81,86 @@ def test_full_size_prefix_parity_and_invariants(oracle, big):
     assert (z1 != z0).sum() > 500 and (y1 != y0).sum() > 100  # the sweeps did move labels
     for c in (ch, fresh, again):
         c.close()
+
+
+@pytest.mark.timeout(1200)
+def test_full_size_whole_sweeps_bit_exact(oracle, big):
+    """One FULL y sweep and one FULL z sweep at configs[1] against the oracle: every label, every table and both
+    probability matrices, array_equal (R/celda_CG.R:543-585)."""
+    d, z0, y0 = big
+    K, L, nG, nM = 30, 150, d["nG"], d["nM"]
+    A = cb.CSC(nG, nM, d["p"], d["i"], d["x"])
+    O = (nG, nM, d["p"], d["i"], d["x"])
+    rng = np.random.default_rng(23)
+    ixy, uy = rng.permutation(nG).astype(np.int32) + 1, rng.random(nG)
+    ixz, uz = rng.permutation(nM).astype(np.int32) + 1, rng.random(nM)
+    ch = cb.Chain(A, d["s"], K=K, L=L)
+    ch.set_state(z0, y0)
+    p = oracle.cCGDecomposeCounts(O, d["s"], z0, y0, K, L)
+    t0 = ch.tables()
+    for k in ("mCPByS", "nTSByC", "nTSByCP", "nGByCP", "nCP", "nByTS", "nGByTS", "nByC", "nByG"):
+        assert np.array_equal(t0[k], p[k]), k
+    # ---- y sweep
+    ch.sweep_y(ixy, uy)
+    _, y1 = ch.get_state()
+    _, py = ch.probs()
+    oy = oracle.cGCalcGibbsProbY(p["nGByCP"], p["nTSByCP"], p["nByTS"], p["nGByTS"], p["nByG"], y0, L, nG, 1.0, 1.0, 1.0,
+                                 ixy, uy)
+    assert np.array_equal(y1, oy["y"]), int((y1 != oy["y"]).sum())
+    assert np.array_equal(py, oy["probs"])
+    t1 = ch.tables()
+    assert np.array_equal(t1["nTSByCP"], oy["nTSByC"]) and np.array_equal(t1["nByTS"], oy["nByTS"])
+    assert np.array_equal(t1["nGByTS"], oy["nGByTS"])
+    nTSByC = oracle.rowSumByGroupChangeSparse(O, p["nTSByC"], oy["y"], y0, L)
+    assert np.array_equal(t1["nTSByC"], nTSByC)
+    # ---- z sweep
+    ch.sweep_z_gibbs(ixz, uz)
+    z1, _ = ch.get_state()
+    pz, _ = ch.probs()
+    oz = oracle.cCCalcGibbsProbZ(nTSByC, p["mCPByS"], oy["nTSByC"], p["nByC"], p["nCP"], z0, d["s"], K, L, nM, 1.0, 1.0,
+                                 ixz, uz)
+    assert np.array_equal(z1, oz["z"]), int((z1 != oz["z"]).sum())
+    assert np.array_equal(pz, oz["probs"])
+    t2 = ch.tables()
+    assert np.array_equal(t2["nTSByCP"], oz["nGByCP"]) and np.array_equal(t2["mCPByS"], oz["mCPByS"])
+    assert np.array_equal(t2["nCP"], oz["nCP"])
+    nGByCP = oracle.colSumByGroupChangeSparse(O, p["nGByCP"], oz["z"], z0, K)
+    assert np.array_equal(t2["nGByCP"], nGByCP)
+    assert (z1 != z0).sum() > 1000 and (y1 != y0).sum() > 200
+    ch.close()
+
+
+def test_commits_per_round_do_not_change_results(gold_cg):
+    """The number of tentative commits per round (CELDA_CUDA_MC) is a schedule, not a result: 1 (one mover per round),
+    4 and the default give identical labels, tables and probabilities from a churning start."""
+    import os
+    counts, s, K, L = gold_cg["counts"], gold_cg["s"], 5, 10
+    nG, nM = counts.shape
+    rng = np.random.default_rng(91)
+    z = rng.integers(1, K + 1, nM).astype(np.int32)
+    y = rng.integers(1, L + 1, nG).astype(np.int32)
+    draws = [(rng.permutation(nG).astype(np.int32) + 1, rng.random(nG), rng.permutation(nM).astype(np.int32) + 1,
+              rng.random(nM)) for _ in range(3)]
+    res = []
+    old = os.environ.get("CELDA_CUDA_MC")
+    try:
+        for mc in ("1", "4", None):
+            if mc is None:
+                os.environ.pop("CELDA_CUDA_MC", None)
+            else:
+                os.environ["CELDA_CUDA_MC"] = mc
+            ch = cb.Chain(cb.CSC.from_dense(counts), s, K=K, L=L)
+            ch.set_state(z, y)
+            lls = [ch.iterate(*dr) for dr in draws]
+            res.append((ch.get_state(), ch.probs(), ch.tables(), lls))
+            ch.close()
+    finally:
+        if old is None:
+            os.environ.pop("CELDA_CUDA_MC", None)
+        else:
+            os.environ["CELDA_CUDA_MC"] = old
+    for r in res[1:]:
+        assert np.array_equal(r[0][0], res[0][0][0]) and np.array_equal(r[0][1], res[0][0][1])
+        assert np.array_equal(r[1][0], res[0][1][0]) and np.array_equal(r[1][1], res[0][1][1])
+        assert all(np.array_equal(r[2][k], res[0][2][k]) for k in r[2])
+        assert r[3] == res[0][3]
