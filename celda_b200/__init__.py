@@ -439,6 +439,25 @@ class Chain:
         check(lib().celda_chain_perplexity(self._h, C.byref(v)))
         return v.value
 
+    def perplexity_new(self, newCounts):
+        """perplexity(x, celdaMod, newCounts = ...) (R/perplexity.R:233-325): `newCounts` is a CSC of the same shape."""
+        if (newCounts.nrow, newCounts.ncol) != (self.nG, self.nM):
+            raise ValueError("newCounts should have the same number of rows and columns as counts")
+        v = C.c_double(0)
+        check(lib().celda_chain_perplexity_new(self._h, _pi(newCounts.p), _pi(newCounts.i), _pd(newCounts.x), C.byref(v)))
+        return v.value
+
+    def perplexity_resampled(self, seed=12345, numResample=5, return_counts=False):
+        """.resamplePerplexity(doResampling = TRUE) for this model (R/perplexity.R:449-476): `numResample` multinomial
+        resamples of the counts (.resampleCountMatrix, :764-775; device Philox) and the perplexity of each."""
+        out = np.zeros(int(numResample))
+        check(lib().celda_chain_perplexity_resampled(self._h, int(seed), int(numResample), _pd(out)))
+        if not return_counts:
+            return out
+        x = np.zeros(self.counts.nnz, np.int32)
+        check(lib().celda_chain_get_resampled(self._h, _pi(x)))
+        return out, x
+
     def tables(self):
         """The sufficient statistics as R holds them (.cCGDecomposeCounts, R/celda_CG.R:902-934)."""
         K, L, nG, nM, nS = self.K, self.L, self.nG, self.nM, self.nS

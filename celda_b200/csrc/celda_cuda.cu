@@ -128,7 +128,7 @@ struct celda_chain {
     DevBuf<int> ph_iota;
     DevBuf<unsigned char> ph_tmp;
     int last_draw_n[2] = {0, 0};  // for get_draws: y, z
-    DevBuf<int> emFlag, ordSeen;
+    DevBuf<int> emFlag, ordSeen, resCum, resX;  // resX / resCum: multinomial resample of the counts (perplexity)
     // staged draws
     int staged_iters = 0;
     DevBuf<int> st_ixy, st_ixz;
@@ -690,14 +690,16 @@ int chain_step_z_em(celda_chain* h, int doSample) {
     const int threads = 256, nwarp = threads / 32;
     const int grid = (int)std::min<long long>(((long long)h->nM + nwarp - 1) / nwarp, (long long)h->sms * 32);
     if (isC && K <= 64 && (long long)h->nM >= 4096) {
-        // large celda_C problems: phi streamed through shared memory in gene tiles shared by a block of cells
-        const int GT = std::min(R, (int)(200 * 1024 / (sizeof(double) * K)));
-        const size_t smem = sizeof(double) * (size_t)GT * K;
-        CELDA_CUDA_OK(cudaFuncSetAttribute(k_em_probs_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // large celda_C problems: phi streamed through shared memory in gene tiles (TMA bulk copies, double-buffered)
+        // shared by a block of cells
+        const int GT = std::min((R + 1) & ~1, (int)(200 * 1024 / (sizeof(double) * K)) & ~1);  // even: 16-byte aligned tiles
+        if (GT > 65536) return fail("EM step: gene tile of %d rows exceeds the packed row field", GT);
+        const size_t smem = 128 + sizeof(double) * ((size_t)GT * K + 2);
+        CELDA_CUDA_OK(cudaFuncSetAttribute(k_em_probs_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const long long cpb = 32LL * EM_CPW;
         const int tgrid = (int)std::min<long long>((h->nM + cpb - 1) / cpb, (long long)h->sms);
-        k_em_probs_tiled<<<tgrid, 1024, smem, st>>>(R, h->nM, K, GT, h->cp.p, h->ci.p, h->cx.p, h->phiBuf.p, h->thetaBuf.p,
-                                                   h->s.p, h->probsZ.p, doSample ? h->z.p : nullptr);
+        k_em_probs_tma<<<tgrid, 1024, smem, st>>>(R, h->nM, K, GT, h->cp.p, h->ci.p, h->cx.p, h->phiBuf.p, h->thetaBuf.p,
+                                                 h->s.p, h->probsZ.p, doSample ? h->z.p : nullptr);
     } else if (isC)
         k_em_probs<true><<<grid, threads, 0, st>>>(R, h->nM, K, h->cp.p, h->ci.p, h->cx.p, h->phiBuf.p, h->thetaBuf.p, h->s.p,
                                                   h->probsZ.p, doSample ? h->z.p : nullptr);
@@ -805,7 +807,7 @@ int chain_alloc_tables(celda_chain* h) {
         count_launch();
     }
     CELDA_TRY(h->wb.alloc(std::max(h->K, h->L), st));
-    CELDA_TRY(h->phiBuf.alloc((size_t)std::max(nG, h->L) * h->K));
+    CELDA_TRY(h->phiBuf.alloc((size_t)std::max(nG, h->L) * h->K + 2));  // + slack for 16-byte bulk copies
     CELDA_TRY(h->thetaBuf.alloc((size_t)h->K * h->nS));
     h->has_state = false;
     return 0;
@@ -1851,8 +1853,12 @@ int celda_chain_iterate_em(celda_chain* h, const int* ix_y, const double* u_y, d
 }
 
 // perplexity(x) on the model's own counts (R/perplexity.R:233-325, newCounts = NULL).
-int celda_chain_perplexity(celda_chain* h, double* perplexity) {
-    CELDA_CUDA_OK(cudaSetDevice(h->device));
+}  // extern "C"
+namespace {
+
+// perplexity of the chain's model on a count matrix with the chain's dimensions (R/perplexity.R:233-325): the chain's
+// own counts, another matrix (newCounts) or a resample.  colTot: the column totals of that matrix.
+int chain_perplexity_on(celda_chain* h, const int* dp, const int* di, const int* dx, const int* colTot, double* perplexity) {
     if (!h->has_state) return fail("set_state must be called first");
     cudaStream_t st = h->st;
     const int sms = h->sms, K = h->K, L = h->L, nG = h->nG;
@@ -1869,8 +1875,8 @@ int celda_chain_perplexity(celda_chain* h, double* perplexity) {
         count_launch();
     }
     if (h->model == CELDA_MODEL_G) {
-        k_perp_cells_G<<<grid, threads, 0, st>>>(h->nM, L, h->cp.p, h->ci.p, h->cx.p, h->nTSByC.p, h->y.p, h->nByG.p, psiDen.p,
-                                                h->beta, h->delta, percell.p);
+        k_perp_cells_G<<<grid, threads, 0, st>>>(h->nM, L, dp, di, dx, h->nTSByC.p, h->y.p, h->nByG.p, psiDen.p, h->beta,
+                                                h->delta, percell.p);
         count_launch();
     } else {
         if (K > 256) return fail("perplexity: K must be <= 256");
@@ -1883,11 +1889,11 @@ int celda_chain_perplexity(celda_chain* h, double* perplexity) {
                                                                        h->nTSByCP.p, h->nGByCP.p, colDen.p, h->beta,
                                                                        h->delta, M.p);
         k_perp_theta<<<(h->nS + 63) / 64, 64, 0, st>>>(h->mCPByS.p, K, h->nS, h->alpha, theta.p);
-        k_perp_cells<<<grid, threads, 0, st>>>(h->nM, K, h->cp.p, h->ci.p, h->cx.p, M.p, theta.p, h->s.p, percell.p);
+        k_perp_cells<<<grid, threads, 0, st>>>(h->nM, K, dp, di, dx, M.p, theta.p, h->s.p, percell.p);
         count_launch(4);
     }
     k_sum_array<<<NB, 256, 0, st>>>(percell.p, h->nM, partial.p);
-    k_perp_final<<<1, 256, 0, st>>>(partial.p, NB, h->nByC.p, h->nM, out.p);
+    k_perp_final<<<1, 256, 0, st>>>(partial.p, NB, colTot, h->nM, out.p);
     count_launch(2);
     CELDA_CUDA_OK(cudaGetLastError());
     if (h->comm) {  // shards: all-reduce (logPx, total counts); the sum order differs from one GPU: 1e-9, not bit-exact
@@ -1899,6 +1905,80 @@ int celda_chain_perplexity(celda_chain* h, double* perplexity) {
         return 0;
     }
     CELDA_CUDA_OK(cudaMemcpyAsync(perplexity, out.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    return chain_sync(h);
+}
+
+}  // namespace
+extern "C" {
+
+int celda_chain_perplexity(celda_chain* h, double* perplexity) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    return chain_perplexity_on(h, h->cp.p, h->ci.p, h->cx.p, h->nByC.p, perplexity);
+}
+
+// perplexity(x, celdaMod, newCounts = ...) (R/perplexity.R:233-325): the model of the chain evaluated on another count
+// matrix of the same dimensions (any sparsity pattern).
+int celda_chain_perplexity_new(celda_chain* h, const int* p, const int* i, const double* x, double* perplexity) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (!p || !i || !x) return fail("perplexity_new: the new count matrix is required");
+    if (p[0] != 0) return fail("column pointers of 'newCounts' must start at 0");
+    for (int c = 0; c < h->nM; ++c)
+        if (p[c + 1] < p[c]) return fail("column pointers of 'newCounts' must be non-decreasing");
+    const long long Z = p[h->nM];
+    for (long long t = 0; t < Z; ++t)
+        if (i[t] < 0 || i[t] >= h->nG) return fail("row index out of range in 'newCounts'");
+    cudaStream_t st = h->st;
+    DevBuf<int> dp, di, dxi, flag, tot, ones, tmp;
+    DevBuf<double> dx;
+    CELDA_TRY(dp.upload(p, (size_t)h->nM + 1, st));
+    CELDA_TRY(di.upload(i, (size_t)Z, st));
+    CELDA_TRY(dx.upload(x, (size_t)Z, st));
+    CELDA_TRY(dxi.alloc((size_t)Z));
+    CELDA_TRY(flag.alloc(1));
+    CELDA_TRY(flag.zero(st));
+    k_narrow<<<grid_for(Z, 256, h->sms), 256, 0, st>>>(dx.p, Z, dxi.p, flag.p);
+    int f = 0;
+    CELDA_CUDA_OK(cudaMemcpyAsync(&f, flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CELDA_CUDA_OK(cudaStreamSynchronize(st));
+    if (f) return fail("newCounts must be integer-valued and below 2^31 (found a non-integer entry)");
+    CELDA_TRY(tot.alloc(h->nM));
+    CELDA_TRY(ones.alloc(h->nG));
+    CELDA_TRY(tmp.alloc(h->nM));
+    k_fill_int<<<grid_for(h->nG, 256, h->sms), 256, 0, st>>>(ones.p, h->nG, 1);
+    k_rowsum_csc<int><<<std::min((h->nM + 7) / 8, h->sms * 8), 256, sizeof(int) * 8, st>>>(h->nM, dp.p, di.p, dxi.p, ones.p, 1,
+                                                                                        tmp.p, tot.p);
+    count_launch(3);
+    return chain_perplexity_on(h, dp.p, di.p, dxi.p, tot.p, perplexity);
+}
+
+// .resamplePerplexity(doResampling = TRUE) (R/perplexity.R:449-476) for the chain's model: n multinomial resamples of
+// the counts (.resampleCountMatrix, :764-775) drawn on the device with Philox (key = seed), perplexity on each.  The
+// resample shares the counts' (p, i) pattern and column totals.
+int celda_chain_perplexity_resampled(celda_chain* h, unsigned long long seed, int n_resample, double* perplexity) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (n_resample < 1) return fail("The 'numResample' parameter needs to be an integer greater than 0.");
+    cudaStream_t st = h->st;
+    if (h->resCum.n < (size_t)h->Z) {
+        CELDA_TRY(h->resCum.alloc((size_t)h->Z));
+        CELDA_TRY(h->resX.alloc((size_t)h->Z));
+    }
+    const int threads = 256, nwarp = threads / 32;
+    const int grid = (int)std::min<long long>(((long long)h->nM + nwarp - 1) / nwarp, (long long)h->sms * 16);
+    for (int j = 0; j < n_resample; ++j) {
+        k_resample_prefix<<<grid, threads, 0, st>>>(h->nM, h->cp.p, h->cx.p, h->resCum.p, h->resX.p);
+        k_resample_draw<<<grid, threads, 0, st>>>(h->nM, h->cp.p, h->resCum.p, (unsigned)seed, (unsigned)(seed >> 32), (unsigned)j,
+                                                 h->resX.p);
+        count_launch(2);
+        CELDA_TRY(chain_perplexity_on(h, h->cp.p, h->ci.p, h->resX.p, h->nByC.p, perplexity + j));
+    }
+    return 0;
+}
+
+// The resampled values of the last celda_chain_perplexity_resampled call, aligned with the stored entries of the counts.
+int celda_chain_get_resampled(celda_chain* h, int* x) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (h->resX.n < (size_t)h->Z) return fail("get_resampled: no resample has been drawn");
+    CELDA_TRY(h->resX.download(x, (size_t)h->Z, h->st));
     return chain_sync(h);
 }
 

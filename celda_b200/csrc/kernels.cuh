@@ -880,7 +880,7 @@ __global__ void k_perp_final(const double* __restrict__ partial, int np, const i
     __syncthreads();
     unsigned long long t = 0;
     for (long long c = threadIdx.x; c < nM; c += blockDim.x) t += (unsigned long long)nByC[c];
-    atomicAdd(&tot, t);
+    atomicAdd(&tot, t);  // nByC: the column totals of the matrix the per-cell terms were computed on
     __syncthreads();
     if (threadIdx.x == 0) {
         double logPx = 0.0;
@@ -1124,6 +1124,215 @@ __global__ void k_colsum_twin(int nG, const long long* __restrict__ rp, const in
             out[(size_t)g * K + k] = sum;
         }
         __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ TMA helpers (sm_100a)
+// One-dimensional bulk copies global -> shared (cp.async.bulk, SASS UBLKCP) completing on an mbarrier.
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_addr(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// .countsTimesProbs + which.max (R/celda_C.R:717-756, 967-977) for large celda_C problems.  Same arithmetic as
+// k_em_probs<true> (the stored entries of a column are added in storage order, product and sum unfused).  The kernel is
+// bound by the shared-memory / shuffle pipe: every stored entry needs its K phi values (K * 8 bytes of shared-memory
+// traffic, 128 bytes per clock and SM) plus the broadcast of (row, count) to the 32 lanes.  So: phi is streamed through
+// shared memory in gene tiles by one TMA bulk copy per tile (mbarrier completion), lane l holds populations 2l and
+// 2l + 1 and reads them with ONE 16-byte load, and (row - tile start, count) travel in ONE 32-bit shuffle (16 bits each;
+// a chunk with a count >= 65536 takes two).  A warp owns EM_CPW cells, one after the other.
+__global__ void __launch_bounds__(1024, 1)
+k_em_probs_tma(int R, long long nM, int K, int GT, const int* __restrict__ p, const int* __restrict__ ri,
+               const int* __restrict__ xv, const double* __restrict__ phi, const double* __restrict__ theta,
+               const int* __restrict__ s, double* __restrict__ probs, int* __restrict__ znew) {
+    extern __shared__ __align__(128) unsigned char em_smem[];
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(em_smem);
+    double* tile = reinterpret_cast<double*>(em_smem + 128);  // [GT][K]
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long cpb = (long long)nwarp * EM_CPW;  // cells per block pass
+    const int k0 = 2 * lane, k1 = 2 * lane + 1;       // K <= 64
+    const bool pair = k1 < K, single = k0 < K && !pair;
+    const bool vec = (K & 1) == 0;  // rows are 16-byte aligned only for even K
+    const unsigned rowBytes = (unsigned)K * 8u, tileLane = smem_addr(tile) + (pair ? (unsigned)k0 * 8u : 0u);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        mbar_init_fence();
+    }
+    __syncthreads();
+    unsigned phase = 0;
+    for (long long blk = blockIdx.x; blk * cpb < nM; blk += gridDim.x) {
+        long long cell[EM_CPW];
+        int cur[EM_CPW], end[EM_CPW];
+        double acc0[EM_CPW], acc1[EM_CPW];
+#pragma unroll
+        for (int j = 0; j < EM_CPW; ++j) {
+            cell[j] = blk * cpb + (long long)warp * EM_CPW + j;
+            const bool ok = cell[j] < nM;
+            cur[j] = ok ? p[cell[j]] : 0;
+            end[j] = ok ? p[cell[j] + 1] : 0;
+            acc0[j] = 0.0;
+            acc1[j] = 0.0;
+        }
+        for (int g0 = 0; g0 < R; g0 += GT) {
+            const int g1 = min(R, g0 + GT);
+            __syncthreads();  // the previous tile is no longer read
+            if (threadIdx.x == 0) {
+                // bulk copies move multiples of 16 bytes: GT is even, an odd last tile of odd K reads 8 bytes of slack
+                const unsigned bytes = (unsigned)(((size_t)(g1 - g0) * K * sizeof(double) + 15) & ~(size_t)15);
+                mbar_arrive_expect_tx(bar, bytes);
+                bulk_copy_g2s(tile, phi + (size_t)g0 * K, bytes, bar);
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+#pragma unroll
+            for (int j = 0; j < EM_CPW; ++j) {
+                while (cur[j] < end[j]) {
+                    const int cnt = min(32, end[j] - cur[j]);
+                    const int myr = (lane < cnt) ? ri[cur[j] + lane] : 0x7fffffff;
+                    const int myxi = (lane < cnt) ? xv[cur[j] + lane] : 0;
+                    const int inTile = __popc(__ballot_sync(0xffffffffu, myr < g1));  // rows ascend: a prefix
+                    const bool wide = __any_sync(0xffffffffu, lane < inTile && (unsigned)myxi >= 65536u);
+                    double a0 = acc0[j], a1 = acc1[j];
+                    if (!wide && vec) {
+                        // branch-free body: every lane loads 16 bytes (lanes beyond K / 2 re-read the row's first pair and
+                        // accumulate into registers nobody reads), 32-bit shared-memory addressing
+                        const unsigned pk = ((unsigned)(myr - g0) << 16) | (unsigned)myxi;
+#pragma unroll 4
+                        for (int u = 0; u < inTile; ++u) {
+                            const unsigned q = __shfl_sync(0xffffffffu, pk, u);
+                            const double x = (double)(int)(q & 0xffffu);
+                            const double2 v = lds_f64x2(tileLane + (q >> 16) * rowBytes);
+                            a0 += v.x * x;
+                            a1 += v.y * x;
+                        }
+                    } else {
+                        for (int u = 0; u < inTile; ++u) {
+                            const int r = __shfl_sync(0xffffffffu, myr, u) - g0;
+                            const double x = (double)__shfl_sync(0xffffffffu, myxi, u);
+                            const double* row = tile + (size_t)r * K;
+                            if (k0 < K) a0 += row[k0] * x;
+                            if (k1 < K) a1 += row[k1] * x;
+                        }
+                    }
+                    acc0[j] = a0;
+                    acc1[j] = a1;
+                    cur[j] += inTile;
+                    if (inTile < cnt || inTile == 0) break;  // the rest of the column belongs to later tiles
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < EM_CPW; ++j) {
+            if (cell[j] >= nM) continue;
+            const long long c = cell[j];
+            const double* th = theta + (size_t)(s[c] - 1) * K;
+            double bv = -__longlong_as_double(0x7ff0000000000000LL);
+            int bi = 0x7fffffff;
+            if (k0 < K) {
+                const double v = acc0[j] + th[k0];
+                if (probs) probs[c * K + k0] = v;
+                bv = v;
+                bi = k0;
+            }
+            if (k1 < K) {
+                const double v = acc1[j] + th[k1];
+                if (probs) probs[c * K + k1] = v;
+                if (v > bv) {  // which.max: the lowest index wins a tie
+                    bv = v;
+                    bi = k1;
+                }
+            }
+            for (int o = 16; o; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi < bi)) {
+                    bv = ov;
+                    bi = oi;
+                }
+            }
+            if (znew && lane == 0) znew[c] = (bi == 0x7fffffff ? 0 : bi) + 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ resampled counts
+// .resampleCountMatrix (R/perplexity.R:764-775): every cell's counts are redrawn as rmultinom(1, size = colSum,
+// prob = column / colSum), i.e. colSum categorical draws over the column's stored entries.  The resample keeps the
+// matrix's (p, i) pattern; only the values change (possibly to 0).  One warp per cell: inclusive prefix sums of the
+// column in `cum`, then draw t of cell c takes the Philox4x32-10 block (counter = (t / 4, cell, resample, 0x5253),
+// key = seed), scales 32 bits to [0, colSum) and finds its entry by binary search.  R's own generator cannot be
+// replayed on the device, so this path is pinned statistically.
+__global__ void k_resample_prefix(long long nM, const int* __restrict__ p, const int* __restrict__ xv, int* __restrict__ cum,
+                                  int* __restrict__ xres) {
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long long c = blockIdx.x * (long long)nwarp + warp; c < nM; c += (long long)gridDim.x * nwarp) {
+        const int b = p[c], e = p[c + 1];
+        int run = 0;
+        for (int t0 = b; t0 < e; t0 += 32) {
+            const int t = t0 + lane;
+            int v = (t < e) ? xv[t] : 0;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int nb = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += nb;
+            }
+            if (t < e) {
+                cum[t] = run + v;
+                xres[t] = 0;
+            }
+            run += __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+}
+
+__global__ void k_resample_draw(long long nM, const int* __restrict__ p, const int* __restrict__ cum, unsigned k0, unsigned k1,
+                                unsigned resample, int* __restrict__ xres) {
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (long long c = blockIdx.x * (long long)nwarp + warp; c < nM; c += (long long)gridDim.x * nwarp) {
+        const int b = p[c], e = p[c + 1];
+        if (e == b) continue;
+        const unsigned N = (unsigned)cum[e - 1];
+        for (unsigned t4 = lane; 4ull * t4 < N; t4 += 32) {  // one Philox block = four draws
+            const Philox4 r = philox4x32_10(t4, (unsigned)c, resample, 0x5253u, k0, k1);
+            const unsigned w[4] = {r.x[0], r.x[1], r.x[2], r.x[3]};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (4ull * t4 + q >= N) break;
+                const unsigned target = (unsigned)(((unsigned long long)w[q] * N) >> 32);  // uniform on [0, N)
+                int lo = b, hi = e - 1;  // first entry with cum > target
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if ((unsigned)cum[mid] > target) hi = mid; else lo = mid + 1;
+                }
+                atomicAdd(&xres[lo], 1);
+            }
+        }
     }
 }
 

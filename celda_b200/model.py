@@ -271,6 +271,19 @@ def clusterProbability(chain, log=False):
     return out
 
 
+def resamplePerplexity(chain, doResampling=False, numResample=5, seed=12345):
+    """.resamplePerplexity for one model (R/perplexity.R:449-498): the default (doResampling = FALSE) is the
+    perplexity on the counts themselves (one column); with resampling, `numResample` columns from multinomial
+    resamples of the counts.  Returns (perplexities, their mean) like the celdaList's perplexity row and
+    runParams$mean_perplexity."""
+    if not isinstance(doResampling, bool):
+        raise ValueError("The 'doResampling' parameter needs to be logical (TRUE/FALSE).")
+    if doResampling and (not isinstance(numResample, (int, np.integer)) or numResample < 1):
+        raise ValueError("The 'numResample' parameter needs to be an integer greater than 0.")
+    perp = chain.perplexity_resampled(seed, numResample) if doResampling else np.array([chain.perplexity()])
+    return perp, float(perp.mean())
+
+
 def factorizeMatrix(chain, type=("counts", "proportion", "posterior")):
     """.factorizeMatrixCG (R/factorizeMatrix.R:193-299) from the chain's device-resident tables: counts /
     proportions / posterior of sample (K x S), cellPopulation (L x K), cell (L x C), module (G x L),

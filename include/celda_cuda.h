@@ -171,6 +171,15 @@ int celda_chain_loglik(celda_chain *h, double *ll);
 /* perplexity(x) of the current state on the model's own counts: .perplexityCelda_CG / _C / _G
  * (R/perplexity.R:233-325) over the posterior factors of R/factorizeMatrix.R:280-296. */
 int celda_chain_perplexity(celda_chain *h, double *perplexity);
+/* perplexity(x, celdaMod, newCounts) (R/perplexity.R:233-325): the chain's model evaluated on another count matrix of
+ * the same dimensions (dgCMatrix slots p, i, x; any sparsity pattern). */
+int celda_chain_perplexity_new(celda_chain *h, const int *p, const int *i, const double *x, double *perplexity);
+/* .resamplePerplexity(doResampling = TRUE) (R/perplexity.R:449-476) + .resampleCountMatrix (:764-775) for the chain's
+ * model: n_resample multinomial resamples of the counts, drawn on the device with Philox4x32-10 (key = seed), and the
+ * perplexity of each; perplexity: [n_resample]. */
+int celda_chain_perplexity_resampled(celda_chain *h, unsigned long long seed, int n_resample, double *perplexity);
+/* The values of the last resample, aligned with the stored entries of the chain's counts (x: [nnz]). */
+int celda_chain_get_resampled(celda_chain *h, int *x);
 /* Tables as R holds them (double, column-major); any pointer may be NULL. */
 int celda_chain_get_tables(celda_chain *h, int *mCPByS, double *nTSByC, double *nTSByCP, double *nGByCP, double *nCP,
                            double *nByC, double *nByG, double *nByTS, int *nGByTS);

@@ -54,3 +54,49 @@ def test_celda_G_chain_ll_and_perplexity(oracle, gold_g):
     want = oracle.perplexity_G(O, p["nTSByC"], p["nByG"], y, 10, 1.0, 1.0)
     assert abs(ch.perplexity() - want) <= 1e-9 * want
     ch.close()
+
+
+def test_perplexity_on_new_counts_and_resampling(oracle, gold_cg, gold_grid):
+    """perplexity(newCounts = ...) (R/perplexity.R:233-325) and .resamplePerplexity(doResampling = TRUE)
+    (:449-476, .resampleCountMatrix :764-775) for a celda_CG model."""
+    from celda_b200 import model
+    counts = gold_cg["counts"]
+    A, O = cb.CSC.from_dense(counts), dense_to_csc(counts)
+    m = [i for i in range(9) if gold_grid["K"][i] == 5 and gold_grid["L"][i] == 10][0]
+    z, y, s = gold_grid["z"][m], gold_grid["y"][m], gold_grid["s"]
+    ch = cb.Chain(A, s, K=5, L=10)
+    ch.set_state(z, y)
+    p = oracle.cCGDecomposeCounts(O, s, z, y, 5, 10)
+    # (1) another matrix with its own sparsity pattern
+    rng = np.random.default_rng(8)
+    other = rng.poisson(counts * 0.7 + 0.05).astype(np.int64)
+    other[0, other.sum(0) == 0] = 1
+    want = oracle.perplexity_CG(dense_to_csc(other), p["mCPByS"], p["nTSByCP"], p["nByG"], y, 5, 10, s, 1.0, 1.0, 1.0)
+    got = ch.perplexity_new(cb.CSC.from_dense(other))
+    assert abs(got - want) <= 1e-9 * want
+    assert abs(ch.perplexity_new(A) - ch.perplexity()) <= 1e-12 * got
+    # (2) resamples: column totals and support preserved, values follow the column proportions; the oracle reproduces
+    # the perplexity of the very matrix the device drew
+    perp, x = ch.perplexity_resampled(seed=2024, numResample=3, return_counts=True)
+    assert perp.shape == (3,) and len(set(perp.tolist())) == 3
+    res = np.zeros_like(counts)
+    cols = np.repeat(np.arange(A.ncol), np.diff(A.p))
+    res[A.i, cols] = x
+    assert np.array_equal(res.sum(0), counts.sum(0)) and (res[counts == 0] == 0).all() and (x >= 0).all()
+    want = oracle.perplexity_CG(dense_to_csc(res), p["mCPByS"], p["nTSByCP"], p["nByG"], y, 5, 10, s, 1.0, 1.0, 1.0)
+    assert abs(perp[2] - want) <= 1e-9 * want
+    big = counts >= 30  # z-scores of resampled entries against Binomial(colSum, prop): unit variance, no bias
+    N = np.broadcast_to(counts.sum(0), counts.shape)[big].astype(float)
+    pr = counts[big] / N
+    zs = (res[big] - counts[big]) / np.sqrt(N * pr * (1 - pr))
+    assert abs(zs.mean()) < 0.05 and 0.9 < zs.std() < 1.1
+    # (3) the stored perplexities of the reference's grid search came from resampled counts: 45.20-45.29 for K=5, L=10
+    perp5 = ch.perplexity_resampled(seed=7, numResample=5)
+    assert 45.0 < perp5.mean() < 45.5
+    same = ch.perplexity_resampled(seed=7, numResample=5)
+    assert np.array_equal(perp5, same)  # counter-based generator: reproducible
+    pr2, mean2 = model.resamplePerplexity(ch, doResampling=True, numResample=5, seed=7)
+    assert np.array_equal(pr2, perp5) and abs(mean2 - perp5.mean()) < 1e-12
+    pr1, mean1 = model.resamplePerplexity(ch)
+    assert pr1.shape == (1,) and pr1[0] == ch.perplexity() == mean1
+    ch.close()
