@@ -6,7 +6,8 @@ collective on the data path.
 Randomness: `draws="philox"` uses the device generator seeded with (seed, chain); `draws=callable` injects
 (ix_y, u_y, ix_z, u_z) per iteration, which is how a run is reproduced seed for seed from R.
 Label initialisation: "predefined" (zInit / yInit) follows the reference exactly; "random" restates
-.initializeCluster (R/initialize_clusters.R:1-57) with numpy's generator (R's RNG stream is not available).
+.initializeCluster (R/initialize_clusters.R:1-57) and "split" (the reference default) .initializeSplitZ / Y
+(celda_b200/split.py) with numpy's generator (R's RNG stream is not available).
 """
 import itertools
 
@@ -32,6 +33,16 @@ def initialize_cluster(N, length, initial=None, rng=None):
         ix = np.flatnonzero(z == top)
         z[rng.choice(ix)] = i
     return z
+
+
+def best_chain(lls):
+    """Index of the chain to return: the first one with the highest final log-likelihood
+    (`result$finalLogLik > bestResult$finalLogLik`, R/celda_C.R:577-589).  Chains that converge to the same partition
+    have the same log-likelihood up to the rounding of the reduction, so values within 1e-10 relative count as equal:
+    the earliest of them is returned whatever the summation order."""
+    top = max(lls)
+    tol = 1e-10 * abs(top)
+    return next(i for i, v in enumerate(lls) if v >= top - tol)
 
 
 def _run_chain(ch, algorithm, maxIter, stopIter, draws, rng, nG, nM, model):
@@ -67,15 +78,24 @@ def _celda_CG_chain(ch, c, K, L, seed, algorithm, maxIter, stopIter, zInitialize
     """Chain number c (1-based) of .celda_CG on a resident handle already sized for (K, L) (R/celda_CG.R:432-790)."""
     nG, nM = ch.nG, ch.nM
     rng = np.random.Generator(np.random.PCG64(seed + c - 1))
-    z = initialize_cluster(K, nM, zInit if zInitialize == "predefined" else None, rng)
-    y = initialize_cluster(L, nG, yInit if yInitialize == "predefined" else None, rng)
+    a, b, d, g = ch.hyper
+    if zInitialize == "split":  # the reference default (R/celda_CG.R:463-469)
+        from . import split
+        z = split.initializeSplitZ(ch.counts, K, alpha=a, beta=b, rng=rng)
+    else:
+        z = initialize_cluster(K, nM, zInit if zInitialize == "predefined" else None, rng)
+    if yInitialize == "split":  # R/celda_CG.R:487-493
+        from . import split
+        y = split.initializeSplitY(ch.counts, L, beta=b, delta=d, gamma=g, rng=rng)
+    else:
+        y = initialize_cluster(L, nG, yInit if yInitialize == "predefined" else None, rng)
     ch.set_state(z, y)
     ch.seed(seed, stream=c - 1)
     return _run_chain(ch, algorithm, maxIter, stopIter, draws, rng, nG, nM, MODEL_CG)
 
 
 def celda_CG(counts, sampleLabel, K, L, alpha=1.0, beta=1.0, delta=1.0, gamma=1.0, algorithm="EM", stopIter=10,
-             maxIter=200, seed=12345, nchains=3, zInitialize="random", yInitialize="random", zInit=None, yInit=None,
+             maxIter=200, seed=12345, nchains=3, zInitialize="split", yInitialize="split", zInit=None, yInit=None,
              draws="philox", device=0, chain=None):
     """celda_CG(x, sampleLabel, K, L, ...) (R/celda_CG.R:85-261) on a CSC count matrix, split heuristics off.
     Returns the per-chain results and `model`, built like the reference from the LAST chain (quirk Q1,
@@ -98,13 +118,13 @@ def celda_CG(counts, sampleLabel, K, L, alpha=1.0, beta=1.0, delta=1.0, gamma=1.
     finally:
         if chain is None:
             ch.close()
-    best = max(range(nchains), key=lambda i: chains[i]["finalLogLik"])
+    best = best_chain([c["finalLogLik"] for c in chains])
     return dict(chains=chains, model=chains[-1], bestChain=best + 1,
                 params=dict(K=K, L=L, alpha=alpha, beta=beta, delta=delta, gamma=gamma, algorithm=algorithm, seed=seed))
 
 
 def celda_C(counts, sampleLabel, K, alpha=1.0, beta=1.0, algorithm="EM", stopIter=10, maxIter=200, seed=12345,
-            nchains=3, zInitialize="random", zInit=None, device=0):
+            nchains=3, zInitialize="split", zInit=None, device=0):
     """celda_C (R/celda_C.R:306-616), algorithm = "EM" (forces stopIter <- 1, :351-353) or "Gibbs" (the z sweep on
     the raw counts, :427-440).  The best chain is returned (R/celda_C.R:577-589 does this correctly)."""
     if algorithm not in ("EM", "Gibbs"):
@@ -116,33 +136,41 @@ def celda_C(counts, sampleLabel, K, alpha=1.0, beta=1.0, algorithm="EM", stopIte
     try:
         for c in range(1, nchains + 1):
             rng = np.random.Generator(np.random.PCG64(seed + c - 1))
-            z = initialize_cluster(K, counts.ncol, zInit if zInitialize == "predefined" else None, rng)
+            if zInitialize == "split":
+                from . import split
+                z = split.initializeSplitZ(counts, K, alpha=alpha, beta=beta, rng=rng)
+            else:
+                z = initialize_cluster(K, counts.ncol, zInit if zInitialize == "predefined" else None, rng)
             ch.set_state(z=z)
             ch.seed(seed, stream=c - 1)
             chains.append(_run_chain(ch, algorithm, maxIter, stopIter, "philox", rng, counts.nrow, counts.ncol, MODEL_C))
     finally:
         ch.close()
-    best = max(range(nchains), key=lambda i: chains[i]["finalLogLik"])
+    best = best_chain([c["finalLogLik"] for c in chains])
     return dict(chains=chains, model=chains[best], bestChain=best + 1,
                 params=dict(K=K, alpha=alpha, beta=beta, algorithm=algorithm, seed=seed))
 
 
 def celda_G(counts, L, beta=1.0, delta=1.0, gamma=1.0, stopIter=10, maxIter=200, seed=12345, nchains=3,
-            yInitialize="random", yInit=None, device=0):
+            yInitialize="split", yInit=None, device=0, draws="philox"):
     """celda_G (R/celda_G.R:268-520): Gibbs y sweeps on the raw counts, split heuristics off; best chain returned
-    (R/celda_G.R:483-494)."""
+    (R/celda_G.R:483-494).  `draws`: "philox" or a callable (it, rng, nG, nM) -> (ix_y, u_y, None, None)."""
     chains = []
     ch = Chain(counts, None, L=L, beta=beta, delta=delta, gamma=gamma, model=MODEL_G, device=device)
     try:
         for c in range(1, nchains + 1):
             rng = np.random.Generator(np.random.PCG64(seed + c - 1))
-            y = initialize_cluster(L, counts.nrow, yInit if yInitialize == "predefined" else None, rng)
+            if yInitialize == "split":
+                from . import split
+                y = split.initializeSplitY(counts, L, beta=beta, delta=delta, gamma=gamma, rng=rng)
+            else:
+                y = initialize_cluster(L, counts.nrow, yInit if yInitialize == "predefined" else None, rng)
             ch.set_state(y=y)
             ch.seed(seed, stream=c - 1)
-            chains.append(_run_chain(ch, "Gibbs", maxIter, stopIter, "philox", rng, counts.nrow, counts.ncol, MODEL_G))
+            chains.append(_run_chain(ch, "Gibbs", maxIter, stopIter, draws, rng, counts.nrow, counts.ncol, MODEL_G))
     finally:
         ch.close()
-    best = max(range(nchains), key=lambda i: chains[i]["finalLogLik"])
+    best = best_chain([c["finalLogLik"] for c in chains])
     return dict(chains=chains, model=chains[best], bestChain=best + 1,
                 params=dict(L=L, beta=beta, delta=delta, gamma=gamma, seed=seed))
 

@@ -19,7 +19,7 @@ g = dict(np.load(os.path.join(ROOT, "tests", "golden", "celdaCG.npz")))
 A = cb.CSC.from_dense(g["counts"])
 cb.Chain(A, g["s"], K=5, L=10).close()  # context + kernels warm
 t0 = time.perf_counter()
-res = model.celda_CG(A, g["s"], K=5, L=10, algorithm="Gibbs", maxIter=200, stopIter=10, nchains=3, seed=12345)
+res = model.celda_CG(A, g["s"], K=5, L=10, algorithm="Gibbs", maxIter=200, stopIter=10, nchains=3, seed=12345)  # default "split" initialisation
 wall = time.perf_counter() - t0
 iters = [len(c["completeLogLik"]) - 1 for c in res["chains"]]
 best = max(c["finalLogLik"] for c in res["chains"])

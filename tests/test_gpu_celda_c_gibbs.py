@@ -114,7 +114,7 @@ def test_model_drivers_celda_C_gibbs_and_celda_G(oracle, gold_c, gold_g):
     from celda_b200 import model
     counts, s, K = gold_c["counts"], gold_c["s_mod"], 10
     A, O = cb.CSC.from_dense(counts), dense_to_csc(counts)
-    res = model.celda_C(A, s, K, algorithm="Gibbs", maxIter=12, nchains=2, seed=7)
+    res = model.celda_C(A, s, K, algorithm="Gibbs", maxIter=12, nchains=2, seed=7, zInitialize="random")
     m = res["model"]
     p = oracle.cCDecomposeCounts(O, s, m["z"], K)
     want = oracle.cCCalcLL(p["mCPByS"], p["nGByCP"], K, p["nS"], p["nG"], 1.0, 1.0)
@@ -124,7 +124,7 @@ def test_model_drivers_celda_C_gibbs_and_celda_G(oracle, gold_c, gold_g):
 
     counts, L = gold_g["counts"], 10
     A, O = cb.CSC.from_dense(counts), dense_to_csc(counts)
-    res = model.celda_G(A, L, maxIter=8, nchains=2, seed=7)
+    res = model.celda_G(A, L, maxIter=8, nchains=2, seed=7, yInitialize="random")
     m = res["model"]
     p = oracle.cGDecomposeCounts(O, m["y"], L)
     want = oracle.cGCalcLL(p["nTSByC"], p["nByTS"], p["nByG"], p["nGByTS"], counts.shape[1], counts.shape[0], L,
