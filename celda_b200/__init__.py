@@ -325,6 +325,7 @@ class Chain:
                  model=MODEL_CG, device=0):
         self._h = C.c_void_p()
         self.counts, self.model, self.K, self.L = counts, model, int(K), int(L)
+        self.device = int(device)
         self.nG, self.nM = counts.nrow, counts.ncol
         self.hyper = (float(alpha), float(beta), float(delta), float(gamma))
         s = None

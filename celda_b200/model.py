@@ -74,30 +74,40 @@ def _run_chain(ch, algorithm, maxIter, stopIter, draws, rng, nG, nM, model):
     return dict(z=zBest, y=yBest, completeLogLik=np.asarray(ll), finalLogLik=llBest)
 
 
-def _celda_CG_chain(ch, c, K, L, seed, algorithm, maxIter, stopIter, zInitialize, yInitialize, zInit, yInit, draws):
+def _celda_CG_chain(ch, c, K, L, seed, algorithm, maxIter, stopIter, zInitialize, yInitialize, zInit, yInit, draws,
+                    splitOnIter=-1, splitOnLast=False):
     """Chain number c (1-based) of .celda_CG on a resident handle already sized for (K, L) (R/celda_CG.R:432-790)."""
     nG, nM = ch.nG, ch.nM
     rng = np.random.Generator(np.random.PCG64(seed + c - 1))
     a, b, d, g = ch.hyper
     if zInitialize == "split":  # the reference default (R/celda_CG.R:463-469)
         from . import split
-        z = split.initializeSplitZ(ch.counts, K, alpha=a, beta=b, rng=rng)
+        z = split.initializeSplitZ(ch.counts, K, alpha=a, beta=b, rng=rng, backend=split.DeviceBackend(ch.device))
     else:
         z = initialize_cluster(K, nM, zInit if zInitialize == "predefined" else None, rng)
     if yInitialize == "split":  # R/celda_CG.R:487-493
         from . import split
-        y = split.initializeSplitY(ch.counts, L, beta=b, delta=d, gamma=g, rng=rng)
+        y = split.initializeSplitY(ch.counts, L, beta=b, delta=d, gamma=g, rng=rng,
+                                   backend=split.DeviceBackend(ch.device))
     else:
         y = initialize_cluster(L, nG, yInit if yInitialize == "predefined" else None, rng)
     ch.set_state(z, y)
     ch.seed(seed, stream=c - 1)
+    if splitOnIter > 0 or splitOnLast:  # the split / merge heuristic of R/celda_CG.R:604-716
+        from . import split
+        dr = (lambda it, r, G, M: (None, None, None, None)) if draws == "philox" else draws
+        return split.run_chain_CG_with_splits(split.DeviceOpsCG(ch, algorithm), ch.counts, K, L, dr, rng,
+                                              split.DeviceBackend(ch.device), maxIter=maxIter, stopIter=stopIter,
+                                              splitOnIter=splitOnIter, splitOnLast=splitOnLast)
     return _run_chain(ch, algorithm, maxIter, stopIter, draws, rng, nG, nM, MODEL_CG)
 
 
 def celda_CG(counts, sampleLabel, K, L, alpha=1.0, beta=1.0, delta=1.0, gamma=1.0, algorithm="EM", stopIter=10,
              maxIter=200, seed=12345, nchains=3, zInitialize="split", yInitialize="split", zInit=None, yInit=None,
-             draws="philox", device=0, chain=None):
-    """celda_CG(x, sampleLabel, K, L, ...) (R/celda_CG.R:85-261) on a CSC count matrix, split heuristics off.
+             draws="philox", device=0, chain=None, splitOnIter=10, splitOnLast=True):
+    """celda_CG(x, sampleLabel, K, L, ...) (R/celda_CG.R:85-261) on a CSC count matrix, with the reference's defaults:
+    'split' initialisation and the split / merge heuristic every `splitOnIter` iterations and at a stall
+    (celda_b200/split.py); splitOnIter = -1 and splitOnLast = False switch the heuristic off.
     Returns the per-chain results and `model`, built like the reference from the LAST chain (quirk Q1,
     R/celda_CG.R:796-811).  `chain`: a resident handle over the same counts and hyper-parameters to re-use
     (celdaGridSearch); it is re-sized to (K, L) and left open."""
@@ -114,7 +124,7 @@ def celda_CG(counts, sampleLabel, K, L, alpha=1.0, beta=1.0, delta=1.0, gamma=1.
     try:
         for c in range(1, nchains + 1):
             chains.append(_celda_CG_chain(ch, c, K, L, seed, algorithm, maxIter, stopIter, zInitialize, yInitialize,
-                                          zInit, yInit, draws))
+                                          zInit, yInit, draws, splitOnIter, splitOnLast))
     finally:
         if chain is None:
             ch.close()
@@ -124,7 +134,7 @@ def celda_CG(counts, sampleLabel, K, L, alpha=1.0, beta=1.0, delta=1.0, gamma=1.
 
 
 def celda_C(counts, sampleLabel, K, alpha=1.0, beta=1.0, algorithm="EM", stopIter=10, maxIter=200, seed=12345,
-            nchains=3, zInitialize="split", zInit=None, device=0):
+            nchains=3, zInitialize="split", zInit=None, device=0, splitOnIter=10, splitOnLast=True):
     """celda_C (R/celda_C.R:306-616), algorithm = "EM" (forces stopIter <- 1, :351-353) or "Gibbs" (the z sweep on
     the raw counts, :427-440).  The best chain is returned (R/celda_C.R:577-589 does this correctly)."""
     if algorithm not in ("EM", "Gibbs"):
@@ -138,11 +148,18 @@ def celda_C(counts, sampleLabel, K, alpha=1.0, beta=1.0, algorithm="EM", stopIte
             rng = np.random.Generator(np.random.PCG64(seed + c - 1))
             if zInitialize == "split":
                 from . import split
-                z = split.initializeSplitZ(counts, K, alpha=alpha, beta=beta, rng=rng)
+                z = split.initializeSplitZ(counts, K, alpha=alpha, beta=beta, rng=rng, backend=split.DeviceBackend(device))
             else:
                 z = initialize_cluster(K, counts.ncol, zInit if zInitialize == "predefined" else None, rng)
             ch.set_state(z=z)
             ch.seed(seed, stream=c - 1)
+            if splitOnIter > 0 or splitOnLast:  # .cCSplitZ steps (R/celda_C.R:459-508)
+                from . import split
+                chains.append(split.run_chain_one_axis_with_splits(
+                    split.DeviceOpsC(ch, algorithm), counts, K, "z", lambda it, r, G, M: (None, None, None, None), rng,
+                    split.DeviceBackend(device), maxIter=maxIter, stopIter=stopIter, splitOnIter=splitOnIter,
+                    splitOnLast=splitOnLast))
+                continue
             chains.append(_run_chain(ch, algorithm, maxIter, stopIter, "philox", rng, counts.nrow, counts.ncol, MODEL_C))
     finally:
         ch.close()
@@ -152,7 +169,7 @@ def celda_C(counts, sampleLabel, K, alpha=1.0, beta=1.0, algorithm="EM", stopIte
 
 
 def celda_G(counts, L, beta=1.0, delta=1.0, gamma=1.0, stopIter=10, maxIter=200, seed=12345, nchains=3,
-            yInitialize="split", yInit=None, device=0, draws="philox"):
+            yInitialize="split", yInit=None, device=0, draws="philox", splitOnIter=10, splitOnLast=True):
     """celda_G (R/celda_G.R:268-520): Gibbs y sweeps on the raw counts, split heuristics off; best chain returned
     (R/celda_G.R:483-494).  `draws`: "philox" or a callable (it, rng, nG, nM) -> (ix_y, u_y, None, None)."""
     chains = []
@@ -162,11 +179,19 @@ def celda_G(counts, L, beta=1.0, delta=1.0, gamma=1.0, stopIter=10, maxIter=200,
             rng = np.random.Generator(np.random.PCG64(seed + c - 1))
             if yInitialize == "split":
                 from . import split
-                y = split.initializeSplitY(counts, L, beta=beta, delta=delta, gamma=gamma, rng=rng)
+                y = split.initializeSplitY(counts, L, beta=beta, delta=delta, gamma=gamma, rng=rng,
+                                           backend=split.DeviceBackend(device))
             else:
                 y = initialize_cluster(L, counts.nrow, yInit if yInitialize == "predefined" else None, rng)
             ch.set_state(y=y)
             ch.seed(seed, stream=c - 1)
+            if splitOnIter > 0 or splitOnLast:  # .cGSplitY steps (R/celda_G.R:437-470)
+                from . import split
+                dr = (lambda it, r, G, M: (None, None, None, None)) if draws == "philox" else draws
+                chains.append(split.run_chain_one_axis_with_splits(
+                    split.DeviceOpsG(ch), counts, L, "y", dr, rng, split.DeviceBackend(device), maxIter=maxIter,
+                    stopIter=stopIter, splitOnIter=splitOnIter, splitOnLast=splitOnLast))
+                continue
             chains.append(_run_chain(ch, "Gibbs", maxIter, stopIter, draws, rng, counts.nrow, counts.ncol, MODEL_G))
     finally:
         ch.close()

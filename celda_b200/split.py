@@ -70,19 +70,21 @@ class DeviceBackend:
     """The operations of the split initialisation on libcelda_cuda (no CPU fallback)."""
 
     def __init__(self, device=0):
+        from . import set_device
         self.device = device
+        set_device(device)  # the stateless entry points (colSumByGroup) run on the library's current device
 
     def celda_C_labels(self, counts, K, alpha, beta, maxIter, seed):
         """.celda_C(counts, K, maxIter, zInitialize = "random", algorithm = "EM", nchains = 3): best chain's z."""
         s = np.ones(counts.ncol, dtype=np.int32)
         res = _model.celda_C(counts, s, K, alpha=alpha, beta=beta, algorithm="EM", maxIter=maxIter, seed=seed, nchains=3,
-                             zInitialize="random", device=self.device)
+                             zInitialize="random", device=self.device, splitOnIter=-1, splitOnLast=False)
         return res["model"]["z"]
 
     def celda_G_labels(self, counts, L, beta, delta, gamma, maxIter, seed):
         """.celda_G(counts, L, maxIter, yInitialize = "random", nchains = 3): best chain's y (injected Gibbs draws)."""
         res = _model.celda_G(counts, L, beta=beta, delta=delta, gamma=gamma, maxIter=maxIter, seed=seed, nchains=3,
-                             yInitialize="random", device=self.device, draws=_draws_G)
+                             yInitialize="random", device=self.device, draws=_draws_G, splitOnIter=-1, splitOnLast=False)
         return res["model"]["y"]
 
     def session_C(self, counts, alpha, beta):
@@ -266,3 +268,277 @@ def initializeSplitY(counts, L, LSubcluster=None, tempK=100, beta=1.0, delta=1.0
             ses.close()
     assert overallY.size == nG
     return overallY
+
+
+# ================================================================== split / merge heuristic (R/split_clusters.R)
+def _order_decreasing(ll, n):
+    """utils::head(order(ll, decreasing = TRUE, na.last = NA), n) with NA = -inf: indices (0-based) by decreasing value,
+    the lower index first among values within 1e-10 relative (equal up to the rounding of the reduction)."""
+    ll = np.array(ll, dtype=np.float64, copy=True)
+    out = []
+    while len(out) < n and np.isfinite(ll).any():
+        k = _first_max(np.where(np.isfinite(ll), ll, -np.inf))
+        out.append(k)
+        ll[k] = -np.inf
+    return out
+
+
+def _split_heuristic(lab, N, min_size, sub_split, second, ll_of, max_try):
+    """The body shared by .cCSplitZ, .cCGSplitZ, .cCGSplitY and .cGSplitY (R/split_clusters.R:2-763): every cluster with
+    at least `min_size` members is split in two by a short sub-chain (`sub_split(i)` -> 1/2 labels of its members);
+    the clusters whose members, moved to their second-best cluster, cost the least log-likelihood are candidates for
+    removal; for each candidate i and each splittable j != i the proposal "dissolve i, split j, give j's second half
+    the label i" is scored by the log-likelihood, and the best proposal (or the current labels) is returned."""
+    ta = np.bincount(lab, minlength=N + 1)[1:]
+    to_split = np.flatnonzero(ta >= min_size) + 1
+    non_empty = np.flatnonzero(ta > 0) + 1
+    if to_split.size == 0:
+        return lab, "Cluster sizes too small. No additional splitting was performed."
+    clust = {int(i): np.asarray(sub_split(int(i)), dtype=np.int32) for i in to_split}
+    cands, lls = [lab], [ll_of(lab)]
+    ll_shuffle = np.full(N, -np.inf)
+    for i in non_empty:
+        new = lab.copy()
+        ix = lab == i
+        new[ix] = second[ix]
+        ll_shuffle[i - 1] = ll_of(new)
+    pairs = [None]
+    for i0 in _order_decreasing(ll_shuffle, max_try):
+        i = i0 + 1
+        for j in to_split:
+            if j == i:
+                continue
+            new = lab.copy()
+            move = lab == i
+            new[move] = second[move]
+            sp = lab == j
+            new[sp] = np.where(clust[int(j)] == 1, j, i)
+            cands.append(new)
+            lls.append(ll_of(new))
+            pairs.append((i, int(j)))
+    sel = _first_max(np.asarray(lls))
+    if sel == 0:
+        return lab, "No additional splitting was performed."
+    return cands[sel], "Cluster %d was reassigned and cluster %d was split in two." % pairs[sel]
+
+
+def _sub_seed(rng):
+    return int(rng.integers(1, 2**31 - 4))
+
+
+def cCSplitZ(counts, z, K, zProb, ll_of, rng, backend, maxClustersToTry=10, minCell=3):
+    """.cCSplitZ (R/split_clusters.R:2-150).  zProb: [K, nM] log-probabilities of the last z update; ll_of(z) -> .cCCalcLL."""
+    second = _second_best(zProb, z)
+    return _split_heuristic(
+        z, K, minCell, lambda i: backend.celda_C_labels(csc_columns(counts, z == i), 2, 1.0, 1.0, 5, _sub_seed(rng)),
+        second, ll_of, int(maxClustersToTry))
+
+
+def cCGSplitZ(counts, z, K, zProb, ll_of, rng, backend, maxClustersToTry=10, minCell=3):
+    """.cCGSplitZ (R/split_clusters.R:154-347): as .cCSplitZ, scored with .cCGCalcLL at fixed y."""
+    return cCSplitZ(counts, z, K, zProb, ll_of, rng, backend, maxClustersToTry, minCell)
+
+
+def cCGSplitY(counts, y, z, K, L, yProb, ll_of, rng, backend, maxClustersToTry=10, KSubclusters=10, minCell=3):
+    """.cCGSplitY (R/split_clusters.R:350-588): the cells are first reduced to at most KSubclusters pseudo-cells per
+    population (celda_C sub-chains), the module splits are found by celda_G on those pseudo-cells."""
+    zTa = np.bincount(z, minlength=K + 1)[1:]
+    tempZ = np.zeros(z.size, dtype=np.int32)
+    top = 0
+    for i in np.flatnonzero(zTa > 0) + 1:
+        ix = z == i
+        if zTa[i - 1] <= KSubclusters:
+            tempZ[ix] = np.arange(top + 1, top + zTa[i - 1] + 1)
+        else:
+            tempZ[ix] = backend.celda_C_labels(csc_columns(counts, ix), KSubclusters, 1.0, 1.0, 5, _sub_seed(rng)) + top
+        top = int(tempZ.max())
+    pseudo = np.asarray(backend.colSumByGroup(counts, tempZ, top))  # G x top, dense
+    second = _second_best(yProb, y)
+
+    def sub(i):
+        rows = CSC.from_dense(pseudo[y == i, :])
+        return backend.celda_G_labels(rows, 2, 1.0, 1.0, 1.0, 5, _sub_seed(rng))
+
+    return _split_heuristic(y, L, minCell, sub, second, ll_of, int(maxClustersToTry))
+
+
+def cGSplitY(counts, y, L, yProb, ll_of, rng, backend, minFeature=3, maxClustersToTry=10):
+    """.cGSplitY (R/split_clusters.R:592-763)."""
+    second = _second_best(yProb, y)
+
+    def sub(i):
+        return backend.celda_G_labels(csc_rows(counts, y == i), 2, 1.0, 1.0, 1.0, 5, _sub_seed(rng))
+
+    return _split_heuristic(y, L, minFeature, sub, second, ll_of, int(maxClustersToTry))
+
+
+# ------------------------------------------------------------------ chain loop with the split steps
+class DeviceOpsCG:
+    """The chain operations the loop needs, on a resident celda_CG handle."""
+
+    def __init__(self, ch, algorithm="Gibbs"):
+        self.ch, self.algorithm = ch, algorithm
+
+    def ll(self):
+        return self.ch.loglik()
+
+    def iterate(self, ixy, uy, ixz, uz):
+        if self.algorithm == "Gibbs":
+            return self.ch.iterate(ixy, uy, ixz, uz)  # all None = device Philox draws
+        if ixy is None:
+            self.ch.sweep_y_philox()
+            self.ch.sweep_z_em()
+            return self.ch.loglik()
+        return self.ch.iterate_em(ixy, uy)
+
+    def state(self):
+        return self.ch.get_state()
+
+    def set_state(self, z, y):
+        self.ch.set_state(z, y)
+
+    def probs(self):
+        return self.ch.probs()
+
+    def ll_alt(self, z, y):
+        """Log-likelihood of other labels; the chain is left at them (the caller sets the final state)."""
+        self.ch.set_state(z, y)
+        return self.ch.loglik()
+
+
+def run_chain_CG_with_splits(ops, counts, K, L, draws, rng, backend, maxIter=200, stopIter=10, splitOnIter=10,
+                             splitOnLast=True):
+    """The while loop of .celda_CG (R/celda_CG.R:536-755) with the split steps: Gibbs y sweep, z sweep, log-likelihood,
+    module split (.cCGSplitY) and population split (.cCGSplitZ) every `splitOnIter` iterations or at a stall, the
+    best-so-far bookkeeping and the stopping rule.  draws(it, rng, nG, nM) supplies the visiting orders and uniforms."""
+    nG, nM = counts.nrow, counts.ncol
+    ll = [ops.ll()]
+    zBest, yBest = ops.state()
+    llBest = ll[0]
+    it, noImp, doCell, doGene = 1, 0, True, True
+    messages = []
+    while it <= maxIter and noImp <= stopIter:
+        temp = ops.iterate(*draws(it, rng, nG, nM))
+        z, y = ops.state()
+        pz, py = ops.probs()
+        dirty = False
+        if L > 2 and it != maxIter and ((noImp == stopIter and not all(temp >= v for v in ll) and splitOnLast) or
+                                        (splitOnIter > 0 and it % splitOnIter == 0 and doGene)):
+            newY, msg = cCGSplitY(counts, y, z, K, L, py, lambda yy: ops.ll_alt(z, yy), rng, backend,
+                                  maxClustersToTry=max(L / 2, 10), minCell=3)
+            messages.append((it, "y", msg))
+            if not np.array_equal(newY, y):
+                noImp, doGene = 1, True
+            else:
+                doGene = False
+            y, dirty = newY, True
+        if K > 2 and it != maxIter and ((noImp == stopIter and not all(temp > v for v in ll) and splitOnLast) or
+                                        (splitOnIter > 0 and it % splitOnIter == 0 and doCell)):
+            newZ, msg = cCGSplitZ(counts, z, K, pz, lambda zz: ops.ll_alt(zz, y), rng, backend, maxClustersToTry=K,
+                                  minCell=3)
+            messages.append((it, "z", msg))
+            if not np.array_equal(newZ, z):
+                noImp, doCell = 0, True
+            else:
+                doCell = False
+            z, dirty = newZ, True
+        if dirty:
+            ops.set_state(z, y)
+        temp = ops.ll()
+        if all(temp > v for v in ll) or it == 1:
+            zBest, yBest, llBest, noImp = z.copy(), y.copy(), temp, 1
+        else:
+            noImp += 1
+        ll.append(temp)
+        it += 1
+    return dict(z=zBest, y=yBest, completeLogLik=np.asarray(ll), finalLogLik=llBest, messages=messages)
+
+
+class DeviceOpsC:
+    """Chain operations of the celda_C loop on a resident handle (algorithm "EM" or "Gibbs")."""
+
+    def __init__(self, ch, algorithm="EM"):
+        self.ch, self.algorithm = ch, algorithm
+
+    def ll(self):
+        return self.ch.loglik()
+
+    def iterate(self, ixy, uy, ixz, uz):
+        if self.algorithm == "EM":
+            return self.ch.iterate_em()
+        return self.ch.iterate(None, None, ixz, uz)  # ixz None = device Philox draws
+
+    def state(self):
+        return self.ch.get_state()[0]
+
+    def set_state(self, z):
+        self.ch.set_state(z=z)
+
+    def probs(self):
+        return self.ch.probs()[0]
+
+    def ll_alt(self, z):
+        self.ch.set_state(z=z)
+        return self.ch.loglik()
+
+
+class DeviceOpsG:
+    """Chain operations of the celda_G loop on a resident handle."""
+
+    def __init__(self, ch):
+        self.ch = ch
+
+    def ll(self):
+        return self.ch.loglik()
+
+    def iterate(self, ixy, uy, ixz, uz):
+        return self.ch.iterate(ixy, uy, None, None)
+
+    def state(self):
+        return self.ch.get_state()[1]
+
+    def set_state(self, y):
+        self.ch.set_state(y=y)
+
+    def probs(self):
+        return self.ch.probs()[1]
+
+    def ll_alt(self, y):
+        self.ch.set_state(y=y)
+        return self.ch.loglik()
+
+
+def run_chain_one_axis_with_splits(ops, counts, N, axis, draws, rng, backend, maxIter=200, stopIter=10, splitOnIter=10,
+                                   splitOnLast=True):
+    """The while loops of .celda_C (axis = "z", R/celda_C.R:412-543, .cCSplitZ) and .celda_G (axis = "y",
+    R/celda_G.R:384-517, .cGSplitY) with their split step."""
+    nG, nM = counts.nrow, counts.ncol
+    ll = [ops.ll()]
+    best, llBest = ops.state(), ll[0]
+    it, noImp, doSplit = 1, 0, True
+    messages = []
+    while it <= maxIter and noImp <= stopIter:
+        temp = ops.iterate(*draws(it, rng, nG, nM))
+        lab = ops.state()
+        if N > 2 and it != maxIter and ((noImp == stopIter and not all(temp >= v for v in ll) and splitOnLast) or
+                                        (splitOnIter > 0 and it % splitOnIter == 0 and doSplit)):
+            if axis == "z":
+                new, msg = cCSplitZ(counts, lab, N, ops.probs(), ops.ll_alt, rng, backend, maxClustersToTry=N, minCell=3)
+            else:
+                new, msg = cGSplitY(counts, lab, N, ops.probs(), ops.ll_alt, rng, backend, minFeature=3,
+                                    maxClustersToTry=max(N / 2, 10))
+            messages.append((it, axis, msg))
+            if not np.array_equal(new, lab):
+                noImp, doSplit = (0 if axis == "z" else 1), True
+            else:
+                doSplit = False
+            lab = new
+            ops.set_state(lab)
+        temp = ops.ll()
+        if all(temp > v for v in ll) or it == 1:
+            best, llBest, noImp = lab.copy(), temp, 1
+        else:
+            noImp += 1
+        ll.append(temp)
+        it += 1
+    return dict(**{axis: best}, completeLogLik=np.asarray(ll), finalLogLik=llBest, messages=messages)

@@ -117,3 +117,47 @@ class _SesG:
 
     def close(self):
         pass
+
+
+class OracleOpsCG:
+    """The chain operations of celda_b200.split.run_chain_CG_with_splits on the CPU oracle (celda_CG, Gibbs)."""
+
+    def __init__(self, oracle, counts, s, K, L, z, y, hyper=(1.0, 1.0, 1.0, 1.0)):
+        self.o, self.O, self.s, self.K, self.L, self.h = oracle, _csc(counts), np.asarray(s, np.int32), K, L, hyper
+        self.nG, self.nM = counts.nrow, counts.ncol
+        self.set_state(z, y)
+
+    def set_state(self, z, y):
+        self.z, self.y = np.asarray(z, np.int32).copy(), np.asarray(y, np.int32).copy()
+        self.p = self.o.cCGDecomposeCounts(self.O, self.s, self.z, self.y, self.K, self.L)
+        self.pz = self.py = None
+
+    def _ll(self, p):
+        a, b, d, g = self.h
+        return self.o.cCGCalcLL(self.K, self.L, p["mCPByS"], p["nTSByCP"], p["nByG"], p["nByTS"], p["nGByTS"], p["nS"],
+                                self.nG, a, b, d, g)
+
+    def ll(self):
+        return self._ll(self.p)
+
+    def ll_alt(self, z, y):
+        self.set_state(z, y)
+        return self.ll()
+
+    def state(self):
+        return self.z.copy(), self.y.copy()
+
+    def probs(self):
+        return self.pz, self.py
+
+    def iterate(self, ixy, uy, ixz, uz):
+        o, p, (a, b, d, g) = self.o, self.p, self.h
+        oy = o.cGCalcGibbsProbY(p["nGByCP"], p["nTSByCP"], p["nByTS"], p["nGByTS"], p["nByG"], self.y, self.L, self.nG, b,
+                                d, g, ixy, uy)
+        nTSByC = o.rowSumByGroupChangeSparse(self.O, p["nTSByC"].copy(order="F"), oy["y"], self.y, self.L)
+        oz = o.cCCalcGibbsProbZ(nTSByC, p["mCPByS"], oy["nTSByC"], p["nByC"], p["nCP"], self.z, self.s, self.K, self.L,
+                                self.nM, a, b, ixz, uz)
+        py, pz = oy["probs"], oz["probs"]
+        self.set_state(oz["z"], oy["y"])
+        self.pz, self.py = pz, py
+        return self.ll()
