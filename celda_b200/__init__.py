@@ -434,6 +434,14 @@ class Chain:
         check(lib().celda_chain_loglik(self._h, C.byref(ll)))
         return ll.value
 
+    def loglik_alt(self, z=None, y=None):
+        """.cCGCalcLL with one label vector replaced (celda_CG), the chain's state untouched (split heuristics)."""
+        z = None if z is None else _i(z)
+        y = None if y is None else _i(y)
+        ll = C.c_double(0)
+        check(lib().celda_chain_loglik_alt(self._h, _pi(z), _pi(y), C.byref(ll)))
+        return ll.value
+
     def perplexity(self):
         """perplexity(x) on the model's own counts (R/perplexity.R:233-325)."""
         v = C.c_double(0)

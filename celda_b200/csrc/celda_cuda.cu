@@ -128,6 +128,8 @@ struct celda_chain {
     DevBuf<int> ph_iota;
     DevBuf<unsigned char> ph_tmp;
     int last_draw_n[2] = {0, 0};  // for get_draws: y, z
+    DevBuf<int> altLab, altT, altM, altG;  // celda_chain_loglik_alt: candidate labels and their small tables
+    DevBuf<long long> altTS;
     DevBuf<int> emFlag, ordSeen, resCum, resX;  // resX / resCum: multinomial resample of the counts (perplexity)
     // staged draws
     int staged_iters = 0;
@@ -141,6 +143,7 @@ struct celda_chain {
 
     ~celda_chain() {
         cudaSetDevice(device);
+        if (st) cudaStreamSynchronize(st);  // the buffers go back to the cache (DevCache): no kernel may still use them
         for (auto& pe : pending) {
             cudaEventDestroy(pe.second.first);
             cudaEventDestroy(pe.second.second);
@@ -1910,6 +1913,59 @@ int chain_perplexity_on(celda_chain* h, const int* dp, const int* di, const int*
 
 }  // namespace
 extern "C" {
+
+// Log-likelihood of the chain's model under OTHER labels, the chain left untouched: what the split heuristics and the
+// cluster-removal loops of the 'split' initialisation evaluate hundreds of times per call (.cCGSplitZ / .cCGSplitY
+// R/split_clusters.R:236-330,483-560; .initializeSplit* R/initialize_clusters.R:150-216).  Exactly one of z_alt, y_alt
+// replaces the chain's labels.  celda_CG needs no pass over the counts: other z -> nTSByCP = colSumByGroup(nTSByC, z),
+// mCPByS = table(z, s); other y -> nTSByCP = rowSumByGroup(nGByCP, y), nByTS, nGByTS from nByG.
+int celda_chain_loglik_alt(celda_chain* h, const int* z_alt, const int* y_alt, double* ll) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (!h->has_state) return fail("set_state must be called first");
+    if ((z_alt != nullptr) == (y_alt != nullptr)) return fail("loglik_alt: pass exactly one of z_alt, y_alt");
+    if (h->model != CELDA_MODEL_CG) return fail("loglik_alt: celda_CG chains only (use set_state + loglik)");
+    if (h->comm) return fail("loglik_alt: not available on a cell-sharded chain");
+    cudaStream_t st = h->st;
+    const int K = h->K, L = h->L, nG = h->nG, nM = h->nM;
+    const int n = z_alt ? nM : nG, top = z_alt ? K : L;
+    for (int q = 0; q < n; ++q)
+        if ((z_alt ? z_alt[q] : y_alt[q]) < 1 || (z_alt ? z_alt[q] : y_alt[q]) > top)
+            return fail(z_alt ? "Assigned value of cell cluster greater than the total number of cell clusters!"
+                              : "Assigned value of feature module greater than the total number of feature modules!");
+    if (h->altLab.n < (size_t)std::max(nG, nM)) CELDA_TRY(h->altLab.alloc((size_t)std::max(nG, nM)));
+    if (h->altT.n < (size_t)L * K) CELDA_TRY(h->altT.alloc((size_t)L * K));
+    if (h->altM.n < (size_t)K * h->nS) CELDA_TRY(h->altM.alloc((size_t)K * h->nS));
+    if (h->altG.n < (size_t)L) {
+        CELDA_TRY(h->altG.alloc((size_t)L));
+        CELDA_TRY(h->altTS.alloc((size_t)L));
+    }
+    CELDA_CUDA_OK(cudaMemcpyAsync(h->altLab.p, z_alt ? z_alt : y_alt, sizeof(int) * n, cudaMemcpyHostToDevice, st));
+    CELDA_CUDA_OK(cudaMemsetAsync(h->altT.p, 0, sizeof(int) * (size_t)L * K, st));
+    LLIn in{h->model, K, L, h->nS, nG, nM, h->mCPByS.p, h->altT.p, h->nGByCP.p, h->nTSByC.p, h->nGByTS.p, h->nByG.p,
+            h->nByTS.p, h->alpha, h->beta, h->delta, h->gamma};
+    if (z_alt) {
+        if (sizeof(int) * L * K > 200 * 1024) return fail("L x K = %d x %d tables exceed the shared-memory budget", L, K);
+        CELDA_CUDA_OK(cudaFuncSetAttribute(k_colsum_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(int) * L * K)));
+        k_colsum_dense<<<std::min(h->sms * 2, std::max(1, nM / 64)), 512, sizeof(int) * L * K, st>>>(h->nTSByC.p, L, nM,
+                                                                                                  h->altLab.p, K, h->altT.p);
+        CELDA_CUDA_OK(cudaMemsetAsync(h->altM.p, 0, sizeof(int) * (size_t)K * h->nS, st));
+        k_table_zs<<<grid_for(nM, 256, h->sms), 256, 0, st>>>(h->altLab.p, h->s.p, nM, K, h->altM.p);
+        count_launch(2);
+        in.mCPByS = h->altM.p;
+    } else {
+        k_rowsum_genemajor<<<grid_for((long long)nG * K, 256, h->sms), 256, 0, st>>>(h->nGByCP.p, nG, K, h->altLab.p, L, h->altT.p);
+        CELDA_CUDA_OK(cudaMemsetAsync(h->altTS.p, 0, sizeof(long long) * L, st));
+        k_fill_int<<<1, 256, 0, st>>>(h->altG.p, L, 1);
+        k_module_totals<<<grid_for(nG, 256, h->sms), 256, 0, st>>>(h->altLab.p, h->nByG.p, nG,
+                                                                  (unsigned long long*)h->altTS.p, h->altG.p);
+        count_launch(3);
+        in.nByTS = h->altTS.p;
+        in.nGByTS = h->altG.p;
+    }
+    CELDA_TRY(run_loglik(in, h->llPartial.p, h->llOut.p, st));
+    CELDA_CUDA_OK(cudaMemcpyAsync(ll, h->llOut.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    return chain_sync(h);
+}
 
 int celda_chain_perplexity(celda_chain* h, double* perplexity) {
     CELDA_CUDA_OK(cudaSetDevice(h->device));

@@ -1336,6 +1336,18 @@ __global__ void k_resample_draw(long long nM, const int* __restrict__ p, const i
     }
 }
 
+// nTSByCP (L x K column-major) of other module labels from the gene-major nGByCP: .cGReDecomposeCounts applied to
+// nGByCP as .cCGSplitY does (R/split_clusters.R:483-486).  out pre-zeroed.
+__global__ void k_rowsum_genemajor(const int* __restrict__ nGByCP, int nG, int K, const int* __restrict__ y, int L,
+                                   int* __restrict__ out) {
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < (long long)nG * K;
+         q += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(q / K), k = (int)(q - (long long)g * K);
+        const int v = nGByCP[q];
+        if (v) atomicAdd(&out[(size_t)k * L + (y[g] - 1)], v);
+    }
+}
+
 // An injected visiting order must hold every value of 1..n exactly once (seen: n ints, zeroed): flag is raised otherwise.
 __global__ void k_validate_order(const int* __restrict__ ix, long long n, int* __restrict__ seen, int* __restrict__ flag) {
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {

@@ -16,17 +16,42 @@ from . import CSC, MODEL_C, MODEL_G, Chain
 from . import model as _model
 
 
+# seconds spent per kind of operation (diagnostics: scripts/run_default_pipeline.py prints them)
+TIMES = {}
+
+
+def _timed(kind):
+    import functools
+    import time
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrap(*a, **k):
+            t0 = time.perf_counter()
+            try:
+                return fn(*a, **k)
+            finally:
+                TIMES[kind] = TIMES.get(kind, 0.0) + time.perf_counter() - t0
+                TIMES[kind + "_calls"] = TIMES.get(kind + "_calls", 0) + 1
+        return wrap
+    return deco
+
+
 # ------------------------------------------------------------------ small helpers on the CSC container
+@_timed("csc_columns")
 def csc_columns(counts, keep):
-    """counts[, keep, drop = FALSE] for a boolean mask."""
-    keep = np.asarray(keep, dtype=bool)
-    lens = np.diff(counts.p)[keep]
-    p = np.zeros(int(keep.sum()) + 1, dtype=np.int64)
+    """counts[, keep, drop = FALSE] for a boolean mask (touches only the selected columns' entries)."""
+    cols = np.flatnonzero(np.asarray(keep, dtype=bool))
+    starts = counts.p[cols].astype(np.int64)
+    lens = counts.p[cols + 1].astype(np.int64) - starts
+    p = np.zeros(cols.size + 1, dtype=np.int64)
     np.cumsum(lens, out=p[1:])
-    entry = np.repeat(keep, np.diff(counts.p))
-    return CSC(counts.nrow, int(keep.sum()), p.astype(np.int32), counts.i[entry], counts.x[entry])
+    # positions of the selected entries: for column k the run starts[k] .. starts[k] + lens[k] - 1
+    idx = np.arange(p[-1], dtype=np.int64) + np.repeat(starts - p[:-1], lens)
+    return CSC(counts.nrow, cols.size, p.astype(np.int32), counts.i[idx], counts.x[idx])
 
 
+@_timed("csc_rows")
 def csc_rows(counts, keep, drop_empty_columns=False):
     """counts[keep, , drop = FALSE]; optionally also the columns whose sum over the kept rows is 0."""
     keep = np.asarray(keep, dtype=bool)
@@ -74,6 +99,7 @@ class DeviceBackend:
         self.device = device
         set_device(device)  # the stateless entry points (colSumByGroup) run on the library's current device
 
+    @_timed("sub_celda_C")
     def celda_C_labels(self, counts, K, alpha, beta, maxIter, seed):
         """.celda_C(counts, K, maxIter, zInitialize = "random", algorithm = "EM", nchains = 3): best chain's z."""
         s = np.ones(counts.ncol, dtype=np.int32)
@@ -81,6 +107,7 @@ class DeviceBackend:
                              zInitialize="random", device=self.device, splitOnIter=-1, splitOnLast=False)
         return res["model"]["z"]
 
+    @_timed("sub_celda_G")
     def celda_G_labels(self, counts, L, beta, delta, gamma, maxIter, seed):
         """.celda_G(counts, L, maxIter, yInitialize = "random", nchains = 3): best chain's y (injected Gibbs draws)."""
         res = _model.celda_G(counts, L, beta=beta, delta=delta, gamma=gamma, maxIter=maxIter, seed=seed, nchains=3,
@@ -93,6 +120,7 @@ class DeviceBackend:
     def session_G(self, counts, beta, delta, gamma):
         return _SessionG(counts, beta, delta, gamma, self.device)
 
+    @_timed("colSumByGroup")
     def colSumByGroup(self, counts, z, K):
         from . import colSumByGroupSparse
         return colSumByGroupSparse(counts, z, K)
@@ -400,10 +428,14 @@ class DeviceOpsCG:
     def probs(self):
         return self.ch.probs()
 
-    def ll_alt(self, z, y):
-        """Log-likelihood of other labels; the chain is left at them (the caller sets the final state)."""
-        self.ch.set_state(z, y)
-        return self.ch.loglik()
+    @_timed("ll_alt_z")
+    def ll_alt_z(self, z):
+        """.cCGCalcLL with other population labels, the chain's modules and state unchanged (celda_chain_loglik_alt)."""
+        return self.ch.loglik_alt(z=z)
+
+    @_timed("ll_alt_y")
+    def ll_alt_y(self, y):
+        return self.ch.loglik_alt(y=y)
 
 
 def run_chain_CG_with_splits(ops, counts, K, L, draws, rng, backend, maxIter=200, stopIter=10, splitOnIter=10,
@@ -421,29 +453,27 @@ def run_chain_CG_with_splits(ops, counts, K, L, draws, rng, backend, maxIter=200
         temp = ops.iterate(*draws(it, rng, nG, nM))
         z, y = ops.state()
         pz, py = ops.probs()
-        dirty = False
         if L > 2 and it != maxIter and ((noImp == stopIter and not all(temp >= v for v in ll) and splitOnLast) or
                                         (splitOnIter > 0 and it % splitOnIter == 0 and doGene)):
-            newY, msg = cCGSplitY(counts, y, z, K, L, py, lambda yy: ops.ll_alt(z, yy), rng, backend,
-                                  maxClustersToTry=max(L / 2, 10), minCell=3)
+            newY, msg = cCGSplitY(counts, y, z, K, L, py, ops.ll_alt_y, rng, backend, maxClustersToTry=max(L / 2, 10),
+                                  minCell=3)
             messages.append((it, "y", msg))
             if not np.array_equal(newY, y):
                 noImp, doGene = 1, True
+                y = newY
+                ops.set_state(z, y)  # nTSByC <- rowSumByGroup(counts, y) etc. (R/celda_CG.R:654-659)
             else:
                 doGene = False
-            y, dirty = newY, True
         if K > 2 and it != maxIter and ((noImp == stopIter and not all(temp > v for v in ll) and splitOnLast) or
                                         (splitOnIter > 0 and it % splitOnIter == 0 and doCell)):
-            newZ, msg = cCGSplitZ(counts, z, K, pz, lambda zz: ops.ll_alt(zz, y), rng, backend, maxClustersToTry=K,
-                                  minCell=3)
+            newZ, msg = cCGSplitZ(counts, z, K, pz, ops.ll_alt_z, rng, backend, maxClustersToTry=K, minCell=3)
             messages.append((it, "z", msg))
             if not np.array_equal(newZ, z):
                 noImp, doCell = 0, True
+                z = newZ
+                ops.set_state(z, y)
             else:
                 doCell = False
-            z, dirty = newZ, True
-        if dirty:
-            ops.set_state(z, y)
         temp = ops.ll()
         if all(temp > v for v in ll) or it == 1:
             zBest, yBest, llBest, noImp = z.copy(), y.copy(), temp, 1

@@ -168,6 +168,10 @@ int celda_chain_stage_draws(celda_chain *h, int n_iter, const int *ix_y, const d
                             const double *u_z);
 int celda_chain_iterate_staged(celda_chain *h, int iter, double *ll);
 int celda_chain_loglik(celda_chain *h, double *ll);
+/* .cCGCalcLL of the chain's model with ONE label vector replaced (exactly one of z_alt, y_alt non-NULL), chain state
+ * untouched: the candidate evaluations of .cCGSplitZ / .cCGSplitY (R/split_clusters.R:236-330, 483-560), which
+ * re-aggregate nTSByC by z resp. nGByCP by y (.cCReDecomposeCounts / .cGReDecomposeCounts) and never touch the counts. */
+int celda_chain_loglik_alt(celda_chain *h, const int *z_alt, const int *y_alt, double *ll);
 /* perplexity(x) of the current state on the model's own counts: .perplexityCelda_CG / _C / _G
  * (R/perplexity.R:233-325) over the posterior factors of R/factorizeMatrix.R:280-296. */
 int celda_chain_perplexity(celda_chain *h, double *perplexity);

@@ -125,12 +125,13 @@ class OracleOpsCG:
     def __init__(self, oracle, counts, s, K, L, z, y, hyper=(1.0, 1.0, 1.0, 1.0)):
         self.o, self.O, self.s, self.K, self.L, self.h = oracle, _csc(counts), np.asarray(s, np.int32), K, L, hyper
         self.nG, self.nM = counts.nrow, counts.ncol
+        self.pz = self.py = None
         self.set_state(z, y)
 
     def set_state(self, z, y):
         self.z, self.y = np.asarray(z, np.int32).copy(), np.asarray(y, np.int32).copy()
         self.p = self.o.cCGDecomposeCounts(self.O, self.s, self.z, self.y, self.K, self.L)
-        self.pz = self.py = None
+        # the probabilities of the last sweeps survive a label change (zProb = t(nextZ$probs), R/celda_CG.R:674-694)
 
     def _ll(self, p):
         a, b, d, g = self.h
@@ -140,9 +141,11 @@ class OracleOpsCG:
     def ll(self):
         return self._ll(self.p)
 
-    def ll_alt(self, z, y):
-        self.set_state(z, y)
-        return self.ll()
+    def ll_alt_z(self, z):
+        return self._ll(self.o.cCGDecomposeCounts(self.O, self.s, np.asarray(z, np.int32), self.y, self.K, self.L))
+
+    def ll_alt_y(self, y):
+        return self._ll(self.o.cCGDecomposeCounts(self.O, self.s, self.z, np.asarray(y, np.int32), self.K, self.L))
 
     def state(self):
         return self.z.copy(), self.y.copy()
