@@ -276,7 +276,10 @@ def run_regimes(cb, csc, d, a, device):
             rows.append({"ms": ms, "logLik": ll, "y_movers": pr["sweep_y"]["movers"], "z_movers": pr["sweep_z"]["movers"],
                          "y_rounds": pr["sweep_y"]["rounds"], "z_rounds": pr["sweep_z"]["rounds"],
                          "y_ms": pr["sweep_y"]["ms"], "z_ms": pr["sweep_z"]["ms"],
-                         "discarded_commits": pr["sweep_y"]["discards"] + pr["sweep_z"]["discards"]})
+                         "discarded_commits": pr["sweep_y"]["discards"] + pr["sweep_z"]["discards"],
+                         "carried_redraws": pr["sweep_y"]["redraws"] + pr["sweep_z"]["redraws"],
+                         "cta0_mclk": {k: {q: pr[k]["clk_" + q] / 1e6 for q in ("commit", "units", "draw", "barrier")}
+                                       for k in ("sweep_y", "sweep_z")}})
         ch.close()
         if name == "truth10":
             out["truth10_first_iteration_ms"] = rows[0]["ms"]
@@ -593,7 +596,7 @@ def rooflines(cb, ch, a, d, prof, clk, default_cfg):
     bytes_alg = {"rowSumByGroup": 8 * Z + 4 * (nM + 1) + 4 * nG + 4.0 * a.L * nM,
                  "colSumByGroup": 8 * Z + 4 * (nM + 1) + 4 * nM + 4.0 * nG * a.K}
     out["roofline_aggregation"] = {}
-    for kname, kern in (("rowSumByGroup", "k_rowsum_csc<int>"), ("colSumByGroup", "k_colsum_twin")):
+    for kname, kern in (("rowSumByGroup", "k_rowsum_csc_v4"), ("colSumByGroup", "k_colsum_twin_v4")):
         ms1 = agg[kname]["ms"] / max(1, agg[kname]["launches"])
         out["roofline_aggregation"][kname] = {
             "bound": "hbm", "kernel": kern, "achieved": bytes_alg[kname] / (ms1 * 1e-3) / 1e9, "peak": hbm,

@@ -231,6 +231,8 @@ int chain_reduce_tables(celda_chain* h) {
     return 0;
 }
 
+unsigned env_u32(const char* env, unsigned dflt);
+
 // ---- decompose (R/celda_CG.R:902-934, R/celda_C.R:800-822, R/celda_G.R:712-733)
 int chain_decompose(celda_chain* h) {
     cudaStream_t st = h->st;
@@ -239,8 +241,20 @@ int chain_decompose(celda_chain* h) {
         const int threads = 256, nwarp = threads / 32;
         {
             ProfScope ps(h, 5);
-            k_rowsum_csc<int><<<std::min((h->nM + nwarp - 1) / nwarp, sms * 8), threads, sizeof(int) * nwarp * h->L, st>>>(
-                h->nM, h->cp.p, h->ci.p, h->cx.p, h->y.p, h->L, h->nTSByC.p, nullptr);
+            // labels packed into shared memory + 16-byte loads when they fit (k_rowsum_csc_v4), else the generic kernel
+            const int t4 = 512, w4 = t4 / 32;
+            const size_t smem4 = sizeof(int) * (size_t)w4 * h->L + 2 * (size_t)h->nG;
+            if (h->L <= 65535 && smem4 <= 100 * 1024 && env_u32("CELDA_CUDA_AGG_V1", 0) != 1) {
+                CELDA_CUDA_OK(cudaFuncSetAttribute(k_rowsum_csc_v4, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem4));
+                k_rowsum_csc_v4<<<std::min((h->nM + w4 - 1) / w4, sms * 2), t4, smem4, st>>>(h->nM, h->nG, h->cp.p, h->ci.p, h->cx.p,
+                                                                                          h->y.p, h->L, h->nTSByC.p);
+            } else {
+                const size_t smem1 = sizeof(int) * nwarp * h->L;
+                if (smem1 > 200 * 1024) return fail("rowSumByGroup: L=%d needs %zu bytes of shared memory", h->L, smem1);
+                CELDA_CUDA_OK(cudaFuncSetAttribute(k_rowsum_csc<int>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+                k_rowsum_csc<int><<<std::min((h->nM + nwarp - 1) / nwarp, sms * 8), threads, smem1, st>>>(
+                    h->nM, h->cp.p, h->ci.p, h->cx.p, h->y.p, h->L, h->nTSByC.p, nullptr);
+            }
         }
         count_launch();
         if (h->model == CELDA_MODEL_G) {
@@ -260,8 +274,23 @@ int chain_decompose(celda_chain* h) {
         DevBuf<int>& mm = h->comm ? h->mCPByS_loc : h->mCPByS;
         if (h->tcol.n) {  // gene-major twin available (celda_CG): no global atomics
             ProfScope ps(h, 6);
-            k_colsum_twin<<<std::min(h->nG, sms * 8), 256, sizeof(int) * 8 * h->K, st>>>(h->nG, h->trp.p, h->tcol.p, h->tx.p,
-                                                                                       h->z.p, h->K, ng.p);
+            const size_t smem4 = sizeof(int) * 8 * CS_REP * (size_t)h->K;
+            const size_t smem5 = sizeof(int) * 32 * CS_REP * (size_t)h->K + (size_t)h->nM;
+            const unsigned aggv = env_u32("CELDA_CUDA_AGG_V1", 0);  // measurement aid: 1 = generic kernels, 4 = v4 colsum
+            if (h->K <= 256 && smem5 <= 200 * 1024 && h->nG >= 1024 && !aggv) {
+                // labels as bytes in shared memory, one warp per gene handed out through a counter
+                CELDA_TRY(h->nchanged.zero(st));
+                CELDA_CUDA_OK(cudaFuncSetAttribute(k_colsum_twin_v5, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem5));
+                k_colsum_twin_v5<<<sms, 1024, smem5, st>>>(h->nG, h->nM, h->trp.p, h->tcol.p, h->tx.p, h->z.p, h->K, ng.p,
+                                                           h->nchanged.p);
+            } else if (smem4 <= 48 * 1024 && aggv != 1) {
+                k_colsum_twin_v4<<<std::min(h->nG, sms * 8), 256, smem4, st>>>(h->nG, h->trp.p, h->tcol.p, h->tx.p, h->z.p, h->K, ng.p);
+            } else {
+                const size_t smem1 = sizeof(int) * 8 * h->K;
+                if (smem1 > 200 * 1024) return fail("colSumByGroup: K=%d needs %zu bytes of shared memory", h->K, smem1);
+                CELDA_CUDA_OK(cudaFuncSetAttribute(k_colsum_twin, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+                k_colsum_twin<<<std::min(h->nG, sms * 8), 256, smem1, st>>>(h->nG, h->trp.p, h->tcol.p, h->tx.p, h->z.p, h->K, ng.p);
+            }
         } else {
             CELDA_TRY(ng.zero(st));
             ProfScope ps(h, 6);
@@ -488,19 +517,18 @@ int run_sweep_y(YArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
 }
 
 int run_sweep_yg(YGArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
-    int threads = 1024;
-    if (yg_sweep_smem(a.L, b.lgT, threads / 32) > 220 * 1024) threads = 512;
+    int threads = YG_THREADS;
     if (yg_sweep_smem(a.L, b.lgT, threads / 32) > 220 * 1024) threads = 256;
     const size_t smem = yg_sweep_smem(a.L, b.lgT, threads / 32);
     if (smem > 220 * 1024) return fail("celda_G y sweep: L=%d needs %zu bytes of shared memory (> 220 KB)", a.L, smem);
-    // window: whole waves of (gene group) x (module chunk) tasks over the grid
-    const int nwarp = threads / 32, nchunk = (a.L + 31) / 32;
-    long long unit = std::max<long long>(nwarp, (long long)nwarp * sms / nchunk / nwarp * nwarp);
+    // window: whole waves of (gene group) x (module chunk) tasks over the grid; a task takes YG_R genes per warp
+    const int GB = threads / 32 * YG_R, nchunk = (a.L + 31) / 32;
+    long long unit = (long long)GB * std::max(1, sms / nchunk);
     const long long cap = std::min<long long>(b.Wmax, 8192);
-    if (unit > cap) unit = cap / nwarp * nwarp;
+    if (unit > cap) unit = std::max<long long>(1, cap / GB) * GB;
     const long long full = std::max<long long>(1, cap / unit) * unit;
     a.w = SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.drawMx.p, b.drawNz.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
-                    b.stats.p + 8 * which, b.Wmax, (int)full, (int)unit, std::max(b.Wmin, nwarp), b.lgT, 1};
+                    b.stats.p + 8 * which, b.Wmax, (int)full, (int)unit, std::max(b.Wmin, threads / 32), b.lgT, 1};
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_yg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CELDA_CUDA_OK(cudaMemsetAsync(b.barrier.p, 0, sizeof(unsigned), st));
     void* args[] = {&a};

@@ -112,6 +112,60 @@ __global__ void k_rowsum_csc(int nc, const int* __restrict__ p, const int* __res
     }
 }
 
+// rowSumByGroup for the chain handle (int32 counts): the same result as k_rowsum_csc<int>, shaped for HBM bandwidth.
+// The per-entry label look-up group[row] is the expensive part of the generic kernel (a 32-way gather through L1 per
+// warp instruction), so the labels are first packed to 16 bits in SHARED memory (nG * 2 bytes, shared by the CTA's
+// warps) where a gather costs a few bank conflicts; indices and values are read with 16-byte loads (the column's
+// unaligned head and tail with scalar loads), four vectors in flight per lane.  Requires L <= 65535 and
+// 2 * nG + 4 * nwarp * L bytes of shared memory; the launcher falls back to k_rowsum_csc otherwise.
+__global__ void __launch_bounds__(512) k_rowsum_csc_v4(int nc, int nG, const int* __restrict__ p, const int* __restrict__ ri,
+                                                       const int* __restrict__ xv, const int* __restrict__ group, int L,
+                                                       int* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* acc = reinterpret_cast<int*>(rs_smem) + warp * L;
+    unsigned short* lab = reinterpret_cast<unsigned short*>(rs_smem + sizeof(int) * (size_t)nwarp * L);
+    for (int g = threadIdx.x; g < nG; g += blockDim.x) lab[g] = (unsigned short)(group[g] - 1);
+    __syncthreads();
+    for (int c = blockIdx.x * nwarp + warp; c < nc; c += gridDim.x * nwarp) {
+        for (int l = lane; l < L; l += 32) acc[l] = 0;
+        __syncwarp();
+        const int b = p[c], e = p[c + 1];
+        const int b4 = min(e, (b + 3) & ~3), e4 = max(b4, e & ~3);  // [b4, e4) is 16-byte aligned in both arrays
+        if (b + lane < b4) atomicAdd(&acc[lab[ri[b + lane]]], xv[b + lane]);
+        if (e4 + lane < e) atomicAdd(&acc[lab[ri[e4 + lane]]], xv[e4 + lane]);
+        const int4* r4 = reinterpret_cast<const int4*>(ri + b4);
+        const int4* x4 = reinterpret_cast<const int4*>(xv + b4);
+        const int n4 = (e4 - b4) >> 2;
+        int t = lane;
+        for (; t + 96 < n4; t += 128) {  // four index and four value vectors in flight per lane
+            int4 r[4], v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                r[q] = __ldg(r4 + t + 32 * q);
+                v[q] = __ldg(x4 + t + 32 * q);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                atomicAdd(&acc[lab[r[q].x]], v[q].x);
+                atomicAdd(&acc[lab[r[q].y]], v[q].y);
+                atomicAdd(&acc[lab[r[q].z]], v[q].z);
+                atomicAdd(&acc[lab[r[q].w]], v[q].w);
+            }
+        }
+        for (; t < n4; t += 32) {
+            const int4 r = __ldg(r4 + t), v = __ldg(x4 + t);
+            atomicAdd(&acc[lab[r.x]], v.x);
+            atomicAdd(&acc[lab[r.y]], v.y);
+            atomicAdd(&acc[lab[r.z]], v.z);
+            atomicAdd(&acc[lab[r.w]], v.w);
+        }
+        __syncwarp();
+        for (int l = lane; l < L; l += 32) out[(size_t)c * L + l] = acc[l];
+        __syncwarp();
+    }
+}
+
 // colSumByGroup (src/matrixSumsSparse.cpp:9-38): out gene-major [nr][K] (pre-zeroed), integer atomics into L2.
 template <typename T>
 __global__ void k_colsum_csc(int nc, const int* __restrict__ p, const int* __restrict__ ri, const T* __restrict__ xv,
@@ -1127,6 +1181,123 @@ __global__ void k_colsum_twin(int nG, const long long* __restrict__ rp, const in
     }
 }
 
+// colSumByGroup over the gene-major twin with 16-byte loads and lane-replicated accumulators: a gene's entries all
+// fall into K counters, so plain per-warp counters serialise on same-address conflicts; here each warp keeps CS_REP
+// copies of the K counters (copy = lane % CS_REP) and the block folds them once per gene.  out: gene-major [nG][K].
+constexpr int CS_REP = 8;
+__global__ void __launch_bounds__(256) k_colsum_twin_v4(int nG, const long long* __restrict__ rp, const int* __restrict__ tcol,
+                                                        const int* __restrict__ tx, const int* __restrict__ group, int K,
+                                                        int* __restrict__ out) {
+    extern __shared__ int acc_tw4[];  // [nwarp][CS_REP][K]
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* acc = acc_tw4 + (warp * CS_REP + (lane & (CS_REP - 1))) * K - 1;  // labels are 1-based
+    const int nacc = nwarp * CS_REP * K;
+    for (int g = blockIdx.x; g < nG; g += gridDim.x) {
+        for (int k = threadIdx.x; k < nacc; k += blockDim.x) acc_tw4[k] = 0;
+        __syncthreads();
+        const long long b = rp[g], e = rp[g + 1];
+        const long long b4 = min(e, (b + 3) & ~3LL), e4 = max(b4, e & ~3LL);
+        if (b + threadIdx.x < b4) atomicAdd(&acc[group[tcol[b + threadIdx.x]]], tx[b + threadIdx.x]);
+        if (e4 + threadIdx.x < e) atomicAdd(&acc[group[tcol[e4 + threadIdx.x]]], tx[e4 + threadIdx.x]);
+        const int4* c4 = reinterpret_cast<const int4*>(tcol + b4);
+        const int4* x4 = reinterpret_cast<const int4*>(tx + b4);
+        const long long n4 = (e4 - b4) >> 2, step = blockDim.x;
+        long long t = threadIdx.x;
+        for (; t + step < n4; t += 2 * step) {
+            const int4 c0 = __ldg(c4 + t), c1 = __ldg(c4 + t + step), v0 = __ldg(x4 + t), v1 = __ldg(x4 + t + step);
+            const int g0 = group[c0.x], g1 = group[c0.y], g2 = group[c0.z], g3 = group[c0.w];
+            const int g4 = group[c1.x], g5 = group[c1.y], g6 = group[c1.z], g7 = group[c1.w];
+            atomicAdd(&acc[g0], v0.x);
+            atomicAdd(&acc[g1], v0.y);
+            atomicAdd(&acc[g2], v0.z);
+            atomicAdd(&acc[g3], v0.w);
+            atomicAdd(&acc[g4], v1.x);
+            atomicAdd(&acc[g5], v1.y);
+            atomicAdd(&acc[g6], v1.z);
+            atomicAdd(&acc[g7], v1.w);
+        }
+        for (; t < n4; t += step) {
+            const int4 c0 = __ldg(c4 + t), v0 = __ldg(x4 + t);
+            atomicAdd(&acc[group[c0.x]], v0.x);
+            atomicAdd(&acc[group[c0.y]], v0.y);
+            atomicAdd(&acc[group[c0.z]], v0.z);
+            atomicAdd(&acc[group[c0.w]], v0.w);
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < K; k += blockDim.x) {
+            int sum = 0;
+            for (int w = 0; w < nwarp * CS_REP; ++w) sum += acc_tw4[w * K + k];
+            out[(size_t)g * K + k] = sum;
+        }
+        __syncthreads();
+    }
+}
+
+// colSumByGroup over the gene-major twin, one WARP per gene (genes handed out through an atomic counter), with the
+// cell labels packed to bytes in SHARED memory: the per-entry look-up group[column] is what holds k_colsum_twin_v4
+// back (ncu: L1 at 80 %, DRAM at 60 %), a byte gather in shared memory costs a few bank conflicts instead.
+// Requires K <= 256 and nM + 4 * nwarp * CS_REP * K bytes of shared memory.  out: gene-major [nG][K].
+__global__ void __launch_bounds__(1024, 1) k_colsum_twin_v5(int nG, int nM, const long long* __restrict__ rp,
+                                                            const int* __restrict__ tcol, const int* __restrict__ tx,
+                                                            const int* __restrict__ group, int K, int* __restrict__ out,
+                                                            int* __restrict__ next /* zeroed */) {
+    extern __shared__ __align__(16) unsigned char cs5_smem[];
+    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* accw = reinterpret_cast<int*>(cs5_smem) + warp * CS_REP * K;    // [CS_REP][K] of this warp
+    int* acc = accw + (lane & (CS_REP - 1)) * K;
+    unsigned char* lab = cs5_smem + sizeof(int) * (size_t)nwarp * CS_REP * K;  // [nM] 0-based labels
+    for (int c = threadIdx.x; c < nM; c += blockDim.x) lab[c] = (unsigned char)(group[c] - 1);
+    for (int k = lane; k < CS_REP * K; k += 32) accw[k] = 0;
+    __syncthreads();
+    while (true) {
+        int g = 0;
+        if (lane == 0) g = atomicAdd(next, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= nG) break;
+        const long long b = rp[g], e = rp[g + 1];
+        const long long b4 = min(e, (b + 3) & ~3LL), e4 = max(b4, e & ~3LL);
+        if (b + lane < b4) atomicAdd(&acc[lab[tcol[b + lane]]], tx[b + lane]);
+        if (e4 + lane < e) atomicAdd(&acc[lab[tcol[e4 + lane]]], tx[e4 + lane]);
+        const int4* c4 = reinterpret_cast<const int4*>(tcol + b4);
+        const int4* x4 = reinterpret_cast<const int4*>(tx + b4);
+        const long long n4 = (e4 - b4) >> 2;
+        long long t = lane;
+        for (; t + 96 < n4; t += 128) {  // four column and four value vectors in flight per lane
+            int4 c[4], v[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                c[q] = __ldg(c4 + t + 32 * q);
+                v[q] = __ldg(x4 + t + 32 * q);
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                atomicAdd(&acc[lab[c[q].x]], v[q].x);
+                atomicAdd(&acc[lab[c[q].y]], v[q].y);
+                atomicAdd(&acc[lab[c[q].z]], v[q].z);
+                atomicAdd(&acc[lab[c[q].w]], v[q].w);
+            }
+        }
+        for (; t < n4; t += 32) {
+            const int4 c = __ldg(c4 + t), v = __ldg(x4 + t);
+            atomicAdd(&acc[lab[c.x]], v.x);
+            atomicAdd(&acc[lab[c.y]], v.y);
+            atomicAdd(&acc[lab[c.z]], v.z);
+            atomicAdd(&acc[lab[c.w]], v.w);
+        }
+        __syncwarp();
+        for (int k = lane; k < K; k += 32) {
+            int sum = 0;
+#pragma unroll
+            for (int w = 0; w < CS_REP; ++w) {
+                sum += accw[w * K + k];
+                accw[w * K + k] = 0;
+            }
+            out[(size_t)g * K + k] = sum;
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ TMA helpers (sm_100a)
 // One-dimensional bulk copies global -> shared (cp.async.bulk, SASS UBLKCP) completing on an mbarrier.
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -1142,9 +1313,29 @@ __device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsign
                  "l"(src), "r"(bytes), "r"(smem_addr(bar))
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
+}
+// generic-proxy writes (this thread's, and those made visible to it) are ordered before its later async-proxy accesses
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ double2 lds_f64x2(unsigned addr) {
     double2 v;
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ unsigned opaque_u32(unsigned x) {
+    unsigned y;
+    asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__device__ __forceinline__ int lds_s32(unsigned addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned lds_u8(unsigned addr) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
@@ -1227,10 +1418,16 @@ k_em_probs_tma(int R, long long nM, int K, int GT, const int* __restrict__ p, co
 #pragma unroll 4
                         for (int u = 0; u < inTile; ++u) {
                             const unsigned q = __shfl_sync(0xffffffffu, pk, u);
-                            const double x = (double)(int)(q & 0xffffu);
                             const double2 v = lds_f64x2(tileLane + (q >> 16) * rowBytes);
-                            a0 += v.x * x;
-                            a1 += v.y * x;
+                            const unsigned xi = q & 0xffffu;
+                            if (xi == 1u) {  // warp-uniform; phi * 1.0 is phi exactly, so the product is skipped (most counts are 1)
+                                a0 += v.x;
+                                a1 += v.y;
+                            } else {
+                                const double x = (double)(int)xi;
+                                a0 += v.x * x;
+                                a1 += v.y * x;
+                            }
                         }
                     } else {
                         for (int u = 0; u < inTile; ++u) {

@@ -1932,10 +1932,19 @@ inline size_t y_sweep_smem(int L, int C, int T, int nwarp, int MC = MCMAX - 1) {
 // .cGCalcGibbsProbY on the RAW counts (R/celda_G.R:401-415, 602-660): every gene's row is scanned over ALL cells
 // against nTSByC (L x nM), zero counts included -- cG_CalcGibbsProbY adds and subtracts the same table entry for
 // them (src/cG_calcGibbsProbY.cpp:218-222), which is not a floating-point no-op, so bit parity needs the full
-// column scan.  Layout: nTSByC (t) and its cached lgamma (lgt) stay in HBM; one CTA task = (one gene per warp of the
-// CTA, consecutive in the window) x (32 consecutive modules): warp <-> gene, lane <-> module.  The lgt tile of a column range is staged
-// in shared memory once and shared by the 32 genes, each warp walks it in column order with its gene's
-// gene-major twin row as a cursor (a warp-uniform test), evaluating a fresh lgamma only where the count is > 0.
+// column scan: 2 dependent FP64 adds per (gene, module, cell).  The kernel is laid out for the FP64 pipe:
+//   * nTSByC (t) and its cached lgamma (lgt) stay in HBM / L2.  A CTA task = (YG_R genes per warp of the CTA) x
+//     (32 consecutive modules): lane <-> module, and every lane carries YG_R independent accumulation chains, one
+//     per gene of its warp, so one shared-memory read of the cached value feeds 2 * YG_R adds and the chains hide
+//     each other's latency.
+//   * The (t, lgt) tile of YG_TC columns x 32 modules is brought in by TMA bulk copies (cp.async.bulk, one 256-byte
+//     and one 128-byte row per column) into a ring of YG_NBUF buffers, each completing on its own mbarrier; the warp
+//     that is last to finish a buffer refills it, so there is no CTA-wide barrier inside a task.
+//   * Where a gene has a count the term is a fresh lgamma: per tile each warp turns the next entries of its genes'
+//     gene-major twin rows (a 32-entry register window per gene, refilled ahead of use) into a 64-bit column mask
+//     and a list of counts in shared memory; the column loop runs tight over the columns no gene of the warp
+//     touches and takes the warp-uniform branch only at the masks' set bits.
+// Patch units after a commit (da, db) use the same code with lanes 0 and 1 bound to the two modules.
 struct YGArgs {
     int nG, L;
     long long nM;
@@ -1956,33 +1965,72 @@ struct YGArgs {
     SweepWork w;
 };
 
-constexpr int YG_TILE = 128;  // columns per staged tile
+// the table-miss path of the column loop as a call: eight inlined copies would not fit the instruction cache
+__device__ __noinline__ double dlgamma_hot_call(double x) { return dlgamma_hot(x); }
 
-__global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+constexpr int YG_TC = 64;    // columns per staged tile: one 64-bit event mask per gene and tile
+constexpr int YG_R = 8;      // genes per warp = accumulation chains per lane
+constexpr int YG_THREADS = 512;  // 16 warps: 128 registers per thread for the chains, masks and cursors
+constexpr int YG_NBUF = 3;   // tile buffers in flight
+
+struct YGCursor {  // per (warp, gene slot): where the gene's twin row starts, its length, the window's first entry
+    long long rb;
+    int n, e;
+};
+
+// bytes of the unit-phase work area (tiles, count lists, cursors); it shares its memory with the draw phase's scratch
+__host__ __device__ inline size_t yg_unit_bytes(int nwarp) {
+    return (size_t)YG_NBUF * YG_TC * 32 * (sizeof(double) + sizeof(int)) + (size_t)nwarp * YG_R * YG_TC * sizeof(int) +
+           (size_t)nwarp * YG_R * sizeof(YGCursor) + (size_t)nwarp * YG_TC;
+}
+__host__ __device__ inline size_t yg_fixed_bytes(int L, int T) {  // tables that live for the whole kernel, padded to 128
+    const size_t b = sizeof(double) * T + sizeof(long long) * L + sizeof(unsigned long long) * YG_NBUF +
+                     sizeof(int) * (L + YG_NBUF + 8);
+    return (b + 127) & ~(size_t)127;
+}
+
+__global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
+    extern __shared__ __align__(128) unsigned char yg_smem[];
     if (a.w.status[1]) return;  // the injected visiting order failed its check: nothing may be indexed through it
     const int L = a.L, T = a.w.lgT;
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int scratchD = 2 * L + (L + 1) / 2 + 2;
-    double* lgtab = reinterpret_cast<double*>(smem_raw);
-    double* tile = lgtab + T;                             // [YG_TILE][32] lgamma(t + beta)
-    double* scratch_all = tile + YG_TILE * 32;
-    long long* T_s = reinterpret_cast<long long*>(scratch_all + (size_t)nwarp * scratchD);
-    int* g_s = reinterpret_cast<int*>(T_s + L);
-    int* ttile = g_s + L;                                 // [YG_TILE][32] t
-    int* s_misc = ttile + YG_TILE * 32;
-    double* scr = scratch_all + (size_t)warp * scratchD;
-    const int gwarp = blockIdx.x * nwarp + warp, tw = gridDim.x * nwarp;
+    const unsigned FULL = 0xffffffffu;
+    double* lgtab = reinterpret_cast<double*>(yg_smem);
+    long long* T_s = reinterpret_cast<long long*>(lgtab + T);
+    unsigned long long* fullb = reinterpret_cast<unsigned long long*>(T_s + L);  // [YG_NBUF] tile landed
+    int* g_s = reinterpret_cast<int*>(fullb + YG_NBUF);
+    int* cnt_s = g_s + L;            // [YG_NBUF] warps done with the buffer
+    int* s_misc = cnt_s + YG_NBUF;   // [8]
+    unsigned char* region = yg_smem + yg_fixed_bytes(L, T);
+    // draw phase view of the region
+    double* scr = reinterpret_cast<double*>(region) + (size_t)warp * scratchD;
+    // unit phase view
+    double* tile = reinterpret_cast<double*>(region);                          // [YG_NBUF][YG_TC][32] lgamma(t + beta)
+    int* ttile = reinterpret_cast<int*>(tile + YG_NBUF * YG_TC * 32);          // [YG_NBUF][YG_TC][32] t
+    int* xw = ttile + YG_NBUF * YG_TC * 32 + (size_t)warp * YG_R * YG_TC;      // [YG_R][YG_TC] this warp's counts in the tile
+    YGCursor* cst = reinterpret_cast<YGCursor*>(ttile + YG_NBUF * YG_TC * 32 + (size_t)nwarp * YG_R * YG_TC) + warp * YG_R;
+    unsigned char* gm = reinterpret_cast<unsigned char*>(cst - warp * YG_R + nwarp * YG_R) + warp * YG_TC;  // [YG_TC] gene-slot set per column
+    const int tw = gridDim.x * nwarp;
     // warp-granular work goes round the CTAs first (item c -> CTA c mod grid), so a short list of items lands on
     // many SMs with one warp each instead of filling a few SMs
     const int gwarpT = warp * gridDim.x + blockIdx.x;
     const long long nM = a.nM;
     const int nchunk = (L + 31) / 32;
+    const long long ntile = (nM + YG_TC - 1) / YG_TC;
+    const bool tmaOk = (L & 3) == 0;  // 16-byte alignment of every (column, 32-module chunk) row of t and lgt
 
     for (int q = threadIdx.x; q < T; q += blockDim.x) lgtab[q] = dlgamma((double)q + a.beta);
     for (int q = threadIdx.x; q < L; q += blockDim.x) {
         T_s[q] = a.nByTS[q];
         g_s[q] = a.nGByTS[q];
+    }
+    if (threadIdx.x == 0) {
+        for (int b = 0; b < YG_NBUF; ++b) {
+            mbar_init(fullb + b, 1);
+            cnt_s[b] = 0;
+        }
+        mbar_init_fence();
     }
     __syncthreads();
 
@@ -1990,6 +2038,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
     int W = a.w.Wfull, nd = 0, da = -1, db = -1, gavg = a.w.Wfull;
     bool have_spec = false;
     unsigned bar_target = 0;
+    unsigned phaseBits = 0;  // bit b: parity of the next completion of fullb[b]
     long long rounds = 0, units_done = 0, movers = 0;
     long long redraws = 0;  // carried items drawn again in full (this thread's share)
     long long ck_commit = 0, ck_units = 0, ck_draw = 0, ck_bar = 0, ck0 = clock64(), ck1;
@@ -2049,104 +2098,286 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
         const bool topup = nd != 2 || (hi - pos) * 2 < W;
         const long long end = topup ? max(hi, min(pos + (long long)W, (long long)a.nG)) : hi;
         const int nwin = (int)(end - pos);
-        // ---- tasks: patch = (32 carried genes) x {da, db}; fresh = (32 new genes) x (32-module chunk)
-        const long long nPatchGrp = (nd == 2) ? (hi - pos + nwarp - 1) / nwarp : 0;
-        const long long nFreshGrp = (end - hi + nwarp - 1) / nwarp;
+        // ---- tasks: patch = (carried genes) x {da, db}; fresh = (new genes) x (32-module chunk).  A task takes NR genes
+        // per warp; NR is the largest of 8, 4, 2, 1 that still spreads the round over the whole grid (a round lasts as
+        // long as its longest task, and a task's time grows with NR).
+        auto pick_nr = [&](long long genes, int chunks) -> int {
+            int best = 1;
+            long long bestCost = 0x7fffffffffffffffLL;
+            for (int nr = YG_R; nr >= 1; nr >>= 1) {  // round time ~ waves x (fixed cost per tile + cost per gene slot)
+                const long long tasks = ((genes + (long long)nwarp * nr - 1) / ((long long)nwarp * nr)) * chunks;
+                const long long cost = ((tasks + gridDim.x - 1) / gridDim.x) * (3 + nr);
+                if (cost < bestCost) {
+                    bestCost = cost;
+                    best = nr;
+                }
+            }
+            return best;
+        };
+        const int nrP = (nd == 2) ? pick_nr(hi - pos, 1) : 1, nrF = pick_nr(end - hi, nchunk);
+        const int GBp = nwarp * nrP, GBf = nwarp * nrF;
+        const long long nPatchGrp = (nd == 2) ? (hi - pos + GBp - 1) / GBp : 0;
+        const long long nFreshGrp = (end - hi + GBf - 1) / GBf;
         const long long ntask = nPatchGrp + nFreshGrp * nchunk;
         ++rounds;
-        for (long long task = blockIdx.x; task < ntask; task += gridDim.x) {
-            long long tgene;   // visiting position of this warp's gene
-            int l;             // this lane's module, -1 = inactive lane
-            bool valid;
-            if (task < nPatchGrp) {
-                tgene = pos + task * nwarp + warp;
-                valid = tgene < hi;
+        // One task.  NR genes per warp: slot r <-> visiting position gstart + r * nwarp + warp.
+        auto run_task = [&](auto nr_tag, long long task) {
+            constexpr int NR = decltype(nr_tag)::value;
+            long long gstart, glimit;  // visiting positions [gstart, glimit) of this task's genes (at most nwarp * NR)
+            int l, l0 = 0, nl = 2;     // this lane's module (-1 = inactive lane); chunk start and width
+            const bool patch = task < nPatchGrp;
+            if (patch) {
+                gstart = pos + task * (nwarp * NR);
+                glimit = hi;
                 l = (lane == 0) ? da : (lane == 1 ? db : -1);
             } else {
                 const long long q = task - nPatchGrp;
-                tgene = hi + (q / nchunk) * nwarp + warp;
-                valid = tgene < end;
-                l = (int)(q % nchunk) * 32 + lane;
-                if (l >= L) l = -1;
+                gstart = hi + (q / nchunk) * (nwarp * NR);
+                glimit = end;
+                l0 = (int)(q % nchunk) * 32;
+                nl = min(32, L - l0);
+                l = (lane < nl) ? l0 + lane : -1;
             }
-            const int i = valid ? a.ix[tgene] - 1 : 0;
-            const int cur = valid ? a.y[i] - 1 : -1;
-            const bool active = valid && l >= 0;
-            const bool isCur = active && (l == cur);
-            const int lsafe = (l >= 0) ? l : 0;
-            // Cursor into the gene's twin row.  The warp keeps a window of 32 consecutive entries in registers (lane k
-            // holds entry wbase + k: column and count, one coalesced load) and the window after it already in flight;
-            // the next entry reaches every lane by a shuffle, so that a gene with counts in many adjacent columns
-            // does not pay a global-load latency per column (it would hold up the whole CTA at the tile barrier).
-            const long long nzEnd = valid ? a.rp[i + 1] : 0;
-            long long wbase = valid ? a.rp[i] : 0;
+            const bool active = l >= 0;
+            const bool useTma = tmaOk && !patch;
+            int pc[NR], px[NR], wq[NR];
+            unsigned curMask = 0;  // bit r: this lane's module is gene r's current module
+            double p[NR];
             const int NONE = 0x7fffffff;
-            int wc, wx, wc2, wx2, widx = 0;
-            {
-                const long long e0 = wbase + lane, e1 = e0 + 32;
-                wc = (e0 < nzEnd) ? __ldg(a.tcol + e0) : NONE;
-                wx = (e0 < nzEnd) ? __ldg(a.tx + e0) : 0;
-                wc2 = (e1 < nzEnd) ? __ldg(a.tcol + e1) : NONE;
-                wx2 = (e1 < nzEnd) ? __ldg(a.tx + e1) : 0;
+#pragma unroll
+            for (int r = 0; r < NR; ++r) {
+                const long long tg = gstart + (long long)r * nwarp + warp;
+                const bool valid = tg < glimit;
+                const int gi = valid ? a.ix[tg] - 1 : 0;
+                const long long rb = valid ? a.rp[gi] : 0;
+                const int n = valid ? (int)(a.rp[gi + 1] - rb) : 0;
+                if (lane == 0) cst[r] = YGCursor{rb, n, 0};
+                if (valid && active && a.y[gi] - 1 == l) curMask |= 1u << r;
+                pc[r] = (lane < n) ? __ldg(a.tcol + rb + lane) : NONE;
+                px[r] = (lane < n) ? __ldg(a.tx + rb + lane) : 0;
+                wq[r] = 0;
+                p[r] = 0.0;
             }
-            int nextcol = __shfl_sync(0xffffffffu, wc, 0), nextx = __shfl_sync(0xffffffffu, wx, 0);
-            double p = 0.0;
-            for (long long c0 = 0; c0 < nM; c0 += YG_TILE) {
-                const int tc = (int)min((long long)YG_TILE, nM - c0);
-                __syncthreads();
-                // stage t and lgt of columns [c0, c0 + tc) for this task's 32 modules: warp w loads columns w, w + nwarp, ...
-                for (int cc = warp; cc < tc; cc += nwarp) {
-                    const size_t g = (size_t)(c0 + cc) * L + lsafe;
-                    tile[cc * 32 + lane] = (l >= 0) ? __ldcg(a.lgt + g) : 0.0;
-                    ttile[cc * 32 + lane] = (l >= 0) ? __ldcg(a.t + g) : 0;
-                }
-                __syncthreads();
-                if (valid) {  // warp-uniform: the whole warp follows one gene, inactive lanes add zeros
-                    // runs of columns where the gene has no count: (p + cached) - cached, a tight loop; then the
-                    // column with a count
-                    int cc = 0;
-                    while (cc < tc) {
-                        const int stop = ((long long)nextcol - c0 < tc) ? (int)((long long)nextcol - c0) : tc;
-#pragma unroll 4
-                        for (; cc < stop; ++cc) {
-                            const double cached = tile[cc * 32 + lane];
-                            p += cached;
-                            p -= cached;
+            // one warp loads tile n into buffer b: TMA bulk copies for a module chunk, plain loads for the two patch rows
+            auto issue_tile = [&](long long n, int b) {
+                const long long c0 = n * YG_TC;
+                const int tc = (int)min((long long)YG_TC, nM - c0);
+                double* dt = tile + (size_t)b * YG_TC * 32;
+                int* di = ttile + (size_t)b * YG_TC * 32;
+                if (useTma) {
+                    if (lane == 0) mbar_arrive_expect_tx(fullb + b, (unsigned)(tc * nl * 12));
+                    __syncwarp();
+                    fence_proxy_async();  // rows written by the commit phase (generic proxy) are read by the copy engine
+                    for (int cc = lane; cc < tc; cc += 32) {
+                        const size_t g = (size_t)(c0 + cc) * L + l0;
+                        bulk_copy_g2s(dt + cc * 32, a.lgt + g, (unsigned)nl * 8u, fullb + b);
+                        bulk_copy_g2s(di + cc * 32, a.t + g, (unsigned)nl * 4u, fullb + b);
+                    }
+                } else {
+                    if (patch) {
+                        for (int cc = lane; cc < tc; cc += 32) {
+                            const size_t g = (size_t)(c0 + cc) * L;
+                            dt[cc * 32] = __ldcg(a.lgt + g + da);
+                            dt[cc * 32 + 1] = __ldcg(a.lgt + g + db);
+                            di[cc * 32] = __ldcg(a.t + g + da);
+                            di[cc * 32 + 1] = __ldcg(a.t + g + db);
                         }
-                        if (cc < tc) {
-                            const double cached = tile[cc * 32 + lane];
-                            const int xv = nextx;
-                            const double fresh =
-                                lg_tab(lgtab, T, (long long)ttile[cc * 32 + lane] + (isCur ? -xv : xv), a.beta);
-                            if (++widx == 32) {  // window used up: the one in flight takes over, the next is requested
-                                wbase += 32;
-                                widx = 0;
-                                wc = wc2;
-                                wx = wx2;
-                                const long long e1 = wbase + 32 + lane;
-                                wc2 = (e1 < nzEnd) ? __ldg(a.tcol + e1) : NONE;
-                                wx2 = (e1 < nzEnd) ? __ldg(a.tx + e1) : 0;
+                    } else {
+                        for (int cc0 = 0; cc0 < tc; cc0 += 8) {  // eight columns in flight
+                            double v[8];
+                            int tv[8];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const bool ok = active && cc0 + k < tc;
+                                const size_t g = (size_t)(c0 + cc0 + k) * L + (active ? l : 0);
+                                v[k] = ok ? __ldcg(a.lgt + g) : 0.0;
+                                tv[k] = ok ? __ldcg(a.t + g) : 0;
                             }
-                            nextcol = __shfl_sync(0xffffffffu, wc, widx);
-                            nextx = __shfl_sync(0xffffffffu, wx, widx);
-                            p += isCur ? cached : fresh;
-                            p -= isCur ? fresh : cached;
-                            ++cc;
+#pragma unroll
+                            for (int k = 0; k < 8; ++k)
+                                if (cc0 + k < tc) {
+                                    dt[(cc0 + k) * 32 + lane] = v[k];
+                                    di[(cc0 + k) * 32 + lane] = tv[k];
+                                }
                         }
                     }
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(fullb + b);
+                }
+            };
+            // the term of a column where gene r has the count xv: a fresh lgamma against the cached one
+            auto special = [&](double& pr, bool ic, int xv, int tv, double cached) {
+                const int arg = active ? tv + (ic ? -xv : xv) : 0;
+                const double fresh = (arg < T) ? lgtab[arg] : dlgamma_hot_call((double)arg + a.beta);
+                pr += ic ? cached : fresh;
+                pr -= ic ? fresh : cached;
+            };
+            // opaque copies: the compiler keeps them in registers instead of re-deriving them at every event
+            const unsigned ttBase = opaque_u32(smem_addr(ttile + lane)), gmA = opaque_u32(smem_addr(gm)),
+                           xwA = opaque_u32(smem_addr(xw));
+            __syncthreads();  // every warp is done with the previous task's buffers (and the draw phase's scratch)
+            if (warp < YG_NBUF && warp < ntile) issue_tile(warp, warp);
+            for (long long n = 0; n < ntile; ++n) {
+                const int b = (int)(n % YG_NBUF);
+                const long long c0 = n * YG_TC;
+                const int tc = (int)min((long long)YG_TC, nM - c0);
+                const long long lim = c0 + tc;
+                // ---- this tile's events: per gene the columns where it has a count (a 64-bit mask), the counts stored
+                // by (column, gene slot); then per column the set of gene slots with a count there (one byte)
+                unsigned long long ev = 0;
+                unsigned g0 = 0, g1 = 0;  // gene-slot sets of columns lane and lane + 32
+#pragma unroll
+                for (int r = 0; r < NR; ++r) {
+                    bool valid = lane >= wq[r] && (long long)pc[r] < lim;
+                    int rel = valid ? (int)(pc[r] - c0) : 0;
+                    unsigned lo = __reduce_or_sync(FULL, (valid && rel < 32) ? 1u << rel : 0u);
+                    unsigned hiw = __reduce_or_sync(FULL, (valid && rel >= 32) ? 1u << (rel - 32) : 0u);
+                    int cnt = __popc(__ballot_sync(FULL, valid));
+                    if (valid) xw[rel * NR + r] = px[r];
+                    wq[r] += cnt;
+                    if (wq[r] == 32) {  // window used up: the tile may hold more of this gene's entries
+                        YGCursor c = cst[r];
+                        do {
+                            c.e += 32;
+                            const int ee = c.e + lane;
+                            pc[r] = (ee < c.n) ? __ldg(a.tcol + c.rb + ee) : NONE;
+                            px[r] = (ee < c.n) ? __ldg(a.tx + c.rb + ee) : 0;
+                            valid = (long long)pc[r] < lim;
+                            rel = valid ? (int)(pc[r] - c0) : 0;
+                            lo |= __reduce_or_sync(FULL, (valid && rel < 32) ? 1u << rel : 0u);
+                            hiw |= __reduce_or_sync(FULL, (valid && rel >= 32) ? 1u << (rel - 32) : 0u);
+                            cnt = __popc(__ballot_sync(FULL, valid));
+                            if (valid) xw[rel * NR + r] = px[r];
+                        } while (cnt == 32);
+                        wq[r] = cnt;
+                        if (lane == 0) cst[r].e = c.e;
+                    }
+                    if (wq[r] >= 16) {  // slide the window to the first unused entry; the loads land during the column loop
+                        YGCursor c = cst[r];
+                        c.e += wq[r];
+                        const int ee = c.e + lane;
+                        pc[r] = (ee < c.n) ? __ldg(a.tcol + c.rb + ee) : NONE;
+                        px[r] = (ee < c.n) ? __ldg(a.tx + c.rb + ee) : 0;
+                        wq[r] = 0;
+                        if (lane == 0) cst[r].e = c.e;
+                    }
+                    ev |= ((unsigned long long)hiw << 32) | lo;
+                    g0 |= ((lo >> lane) & 1u) << r;
+                    g1 |= ((hiw >> lane) & 1u) << r;
+                }
+                gm[lane] = (unsigned char)g0;
+                gm[lane + 32] = (unsigned char)g1;
+                __syncwarp();
+                mbar_wait(fullb + b, (phaseBits >> b) & 1u);
+                phaseBits ^= 1u << b;
+                // ---- the column loop
+                {
+                    const double* tl = tile + (size_t)b * YG_TC * 32 + lane;
+                    const unsigned ttA = ttBase + (unsigned)b * (YG_TC * 32 * 4);
+                    int cc = 0;
+                    while (true) {
+                        const int stop = ev ? (__ffsll((long long)ev) - 1) : tc;
+#pragma unroll 4
+                        for (; cc < stop; ++cc) {  // no gene of this warp has a count here: (p + cached) - cached
+                            const double cached = tl[cc * 32];
+#pragma unroll
+                            for (int r = 0; r < NR; ++r) p[r] += cached;
+#pragma unroll
+                            for (int r = 0; r < NR; ++r) p[r] -= cached;
+                        }
+                        if (cc >= tc) break;
+                        ev &= ev - 1;
+                        // 32-bit shared-memory addressing (ld.shared on register operands) keeps the compiler from
+                        // re-deriving the warp's base pointers at every event
+                        const double cached = tl[cc * 32];
+                        const int tv = active ? lds_s32(ttA + (unsigned)cc * 128u) : 0;
+                        const unsigned g = lds_u8(gmA + (unsigned)cc);  // warp-uniform
+                        const unsigned xcA = xwA + (unsigned)(cc * NR) * 4u;
+                        if ((g & (g - 1)) == 0) {             // one gene of the warp has a count in this column (the usual case)
+                            const int rs = __ffs(g) - 1;
+                            const int xv = lds_s32(xcA + (unsigned)rs * 4u);
+                            const bool ic = (curMask >> rs) & 1u;
+                            switch (rs) {
+#define CELDA_YG_CASE(R_)                                                        \
+    case R_:                                                                     \
+        if (R_ < NR) {                                                           \
+            _Pragma("unroll") for (int r = 0; r < NR; ++r)                       \
+                if (r != R_) p[r] += cached;                                     \
+            _Pragma("unroll") for (int r = 0; r < NR; ++r)                       \
+                if (r != R_) p[r] -= cached;                                     \
+            special(p[R_ < NR ? R_ : 0], ic, xv, tv, cached);                    \
+        }                                                                        \
+        break;
+                                CELDA_YG_CASE(0)
+                                CELDA_YG_CASE(1)
+                                CELDA_YG_CASE(2)
+                                CELDA_YG_CASE(3)
+                                CELDA_YG_CASE(4)
+                                CELDA_YG_CASE(5)
+                                CELDA_YG_CASE(6)
+                                CELDA_YG_CASE(7)
+#undef CELDA_YG_CASE
+                                default: break;
+                            }
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < NR; ++r) {
+                                if (g & (1u << r)) {  // warp-uniform
+                                    special(p[r], (curMask >> r) & 1u, lds_s32(xcA + (unsigned)r * 4u), tv, cached);
+                                } else {
+                                    p[r] += cached;
+                                    p[r] -= cached;
+                                }
+                            }
+                        }
+                        ++cc;
+                    }
+                }
+                // ---- buffer b is free once every warp has passed; the last one refills it
+                __syncwarp();
+                int last = 0;
+                if (lane == 0) {
+                    __threadfence_block();
+                    last = atomicAdd(cnt_s + b, 1) == nwarp - 1;
+                    if (last) cnt_s[b] = 0;
+                }
+                last = __shfl_sync(FULL, last, 0);
+                if (last && n + YG_NBUF < ntile) issue_tile(n + YG_NBUF, b);
+            }
+            // the per-candidate scalar terms; a rolled loop (the chain values pass through the warp's count list, which
+            // is idle now) keeps 6 x NR inlined lgamma evaluations out of the instruction stream
+            double* pw = reinterpret_cast<double*>(xw);  // [NR][32] doubles fit the count list's YG_TC x YG_R ints
+            __syncwarp();
+#pragma unroll
+            for (int r = 0; r < NR; ++r) pw[r * 32 + lane] = p[r];
+#pragma unroll 1
+            for (int r = 0; r < NR; ++r) {
+                const long long tg = gstart + (long long)r * nwarp + warp;
+                if (active && tg < glimit) {
+                    const int gi = a.ix[tg] - 1;
+                    const bool isCur = (curMask >> r) & 1u;
+                    const int g = g_s[l];
+                    const double Tl = (double)T_s[l], Ni = (double)a.nByG[gi];
+                    const int g1 = isCur ? g - 1 : g, g0 = g1 + 1;
+                    double pp = pw[r * 32 + lane];
+                    pp += dlgamma_hot((double)g0 + a.gamma);
+                    pp -= dlgamma_hot((double)g1 + a.gamma);
+                    pp += dlgdelta(g0, a.delta);
+                    pp -= dlgdelta(g1, a.delta);
+                    pp += dlgamma_hot(isCur ? Tl - Ni + (double)g1 * a.delta : Tl + (double)g1 * a.delta);
+                    pp -= dlgamma_hot(isCur ? Tl + (double)g0 * a.delta : Tl + Ni + (double)g0 * a.delta);
+                    a.w.bufP[ring_slot(tg, a.w.Wmax) * L + l] = pp;
                 }
             }
-            if (active) {
-                const int g = g_s[l];
-                const double Tl = (double)T_s[l], Ni = (double)a.nByG[i];
-                const int g1 = isCur ? g - 1 : g, g0 = g1 + 1;
-                p += dlgamma_hot((double)g0 + a.gamma);
-                p -= dlgamma_hot((double)g1 + a.gamma);
-                p += dlgdelta(g0, a.delta);
-                p -= dlgdelta(g1, a.delta);
-                p += dlgamma_hot(isCur ? Tl - Ni + (double)g1 * a.delta : Tl + (double)g1 * a.delta);
-                p -= dlgamma_hot(isCur ? Tl + (double)g0 * a.delta : Tl + Ni + (double)g0 * a.delta);
-                a.w.bufP[ring_slot(tgene, a.w.Wmax) * L + l] = p;
+            __syncwarp();
+        };
+        for (long long task = blockIdx.x; task < ntask; task += gridDim.x) {
+            switch (task < nPatchGrp ? nrP : nrF) {
+                case 8: run_task(std::integral_constant<int, 8>{}, task); break;
+                case 4: run_task(std::integral_constant<int, 4>{}, task); break;
+                case 2: run_task(std::integral_constant<int, 2>{}, task); break;
+                default: run_task(std::integral_constant<int, 1>{}, task); break;
             }
         }
         units_done += ntask;
@@ -2225,8 +2456,7 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_yg(YGArgs a) {
 
 inline size_t yg_sweep_smem(int L, int T, int nwarp) {
     const size_t scratchD = (size_t)2 * L + (L + 1) / 2 + 2;
-    return sizeof(double) * (T + YG_TILE * 32 + nwarp * scratchD) + sizeof(long long) * L +
-           sizeof(int) * (L + YG_TILE * 32 + 4);
+    return yg_fixed_bytes(L, T) + std::max(sizeof(double) * nwarp * scratchD, yg_unit_bytes(nwarp));
 }
 
 // lgt = lgamma(t + beta) for the whole L x nM table (at set_state; the sweep keeps it current afterwards)
@@ -2245,6 +2475,8 @@ __global__ void k_lgt_fill(const int* __restrict__ t, long long n, double beta, 
 // x (32 populations, one per lane); the cached-lgamma tile of 128 genes is staged in shared memory once for the
 // CTA's cells; each warp walks it in gene order with the cell's CSC column as a cursor, adding the cached value
 // where the cell has no count and a fresh lgamma where it has one.
+constexpr int YG_TILE = 128;  // genes per staged tile of k_sweep_zc
+
 struct ZCArgs {
     int nG, K, nS;
     long long nM;
