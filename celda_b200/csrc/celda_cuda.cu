@@ -643,6 +643,7 @@ int chain_step_y(celda_chain* h, const int* d_ix, const double* d_u, int doSampl
         a.u = d_u;
         a.doSample = doSample;
         a.probs = h->probsY.p;
+        a.noTma = (int)env_u32("CELDA_CUDA_YG_NOTMA", 0);
         return run_sweep_yg(a, h->wb, h->sms, 0, h->st);
     }
     CELDA_CUDA_OK(cudaMemcpyAsync(h->yprev.p, h->y.p, sizeof(int) * h->nG, cudaMemcpyDeviceToDevice, h->st));

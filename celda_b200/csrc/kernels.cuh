@@ -1371,7 +1371,9 @@ k_em_probs_tma(int R, long long nM, int K, int GT, const int* __restrict__ p, co
     const int k0 = 2 * lane, k1 = 2 * lane + 1;       // K <= 64
     const bool pair = k1 < K, single = k0 < K && !pair;
     const bool vec = (K & 1) == 0;  // rows are 16-byte aligned only for even K
-    const unsigned rowBytes = (unsigned)K * 8u, tileLane = smem_addr(tile) + (pair ? (unsigned)k0 * 8u : 0u);
+    // lanes beyond K / 2 re-read the row's LAST pair: the same address as the lane before them in their quarter-warp (a
+    // broadcast), where the row's first pair would sit in the same banks at another address (one more wavefront per entry)
+    const unsigned rowBytes = (unsigned)K * 8u, tileLane = smem_addr(tile) + (pair ? (unsigned)k0 : (unsigned)max(K - 2, 0)) * 8u;
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         mbar_init_fence();
@@ -1412,7 +1414,7 @@ k_em_probs_tma(int R, long long nM, int K, int GT, const int* __restrict__ p, co
                     const bool wide = __any_sync(0xffffffffu, lane < inTile && (unsigned)myxi >= 65536u);
                     double a0 = acc0[j], a1 = acc1[j];
                     if (!wide && vec) {
-                        // branch-free body: every lane loads 16 bytes (lanes beyond K / 2 re-read the row's first pair and
+                        // branch-free body: every lane loads 16 bytes (lanes beyond K / 2 re-read the row's last pair and
                         // accumulate into registers nobody reads), 32-bit shared-memory addressing
                         const unsigned pk = ((unsigned)(myr - g0) << 16) | (unsigned)myxi;
 #pragma unroll 4

@@ -249,7 +249,38 @@ __device__ int warp_sample_ll(double* pl, int n, double u, double* r, int* perm,
     }
     __syncwarp();
     CELDA_DBG_SEG(4);
-    if (nc > 200) return -1;
+    if (nc > 200) {
+        // sample.int switches to Walker's alias method when more than 200 categories are likely (R random.c,
+        // walker_ProbSampleReplace): alias tables built serially from q = n p, then ONE uniform picks a cell and either
+        // its own category or its alias.  Rare (K or L > 200 with a diffuse vector): one lane, hs (the log-probabilities,
+        // no longer needed) holds the small/large work list, perm the aliases.
+        int res = 0;
+        __syncwarp();
+        if (lane == 0) {
+            int* HL = reinterpret_cast<int*>(hs);
+            int H = -1, Lp = n;
+            for (int i = 0; i < n; ++i) {
+                r[i] = r[i] * (double)n;
+                perm[i] = i;  // an entry that is never given an alias keeps itself (R leaves it unset; reachable only through rounding)
+                if (r[i] < 1.0) HL[++H] = i; else HL[--Lp] = i;
+            }
+            if (H >= 0 && Lp < n) {
+                for (int k = 0; k < n - 1; ++k) {
+                    const int i = HL[k], j = HL[Lp];
+                    perm[i] = j;
+                    r[j] += r[i] - 1.0;
+                    if (r[j] < 1.0) ++Lp;
+                    if (Lp >= n) break;
+                }
+            }
+            const double rU = u * (double)n;
+            const int k = min((int)rU, n - 1);
+            res = (rU < r[k] + (double)k) ? k : perm[k];
+        }
+        res = __shfl_sync(FULL, res, 0);
+        __syncwarp();
+        return res;
+    }
     if (n == 1) return 0;
     // Scan the values in descending order (the order revsort produces is unique up to ties).  Peaked
     // distributions end within a few warp arg-max steps; a diffuse one (more than 16 positive entries) switches to a rank sort after two.
@@ -1962,6 +1993,7 @@ struct YGArgs {
     const double* u;
     int doSample;
     double* probs;         // L x nG or null
+    int noTma;             // measurement aid (CELDA_CUDA_YG_NOTMA): stage the tiles with plain loads
     SweepWork w;
 };
 
@@ -2018,7 +2050,7 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
     const long long nM = a.nM;
     const int nchunk = (L + 31) / 32;
     const long long ntile = (nM + YG_TC - 1) / YG_TC;
-    const bool tmaOk = (L & 3) == 0;  // 16-byte alignment of every (column, 32-module chunk) row of t and lgt
+    const bool tmaOk = (L & 3) == 0 && !a.noTma;  // 16-byte alignment of every (column, 32-module chunk) row of t and lgt
 
     for (int q = threadIdx.x; q < T; q += blockDim.x) lgtab[q] = dlgamma((double)q + a.beta);
     for (int q = threadIdx.x; q < L; q += blockDim.x) {
@@ -2042,6 +2074,10 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
     long long rounds = 0, units_done = 0, movers = 0;
     long long redraws = 0;  // carried items drawn again in full (this thread's share)
     long long ck_commit = 0, ck_units = 0, ck_draw = 0, ck_bar = 0, ck0 = clock64(), ck1;
+    long long sg[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, sg0 = 0;  // unit-phase segments of this warp, patch tasks then fresh tasks:
+                                                                       // build, wait, columns, hand-over, refill, tiles
+    int sgk = 0;
+#define CELDA_YG_SEG(k) do { const long long c_ = clock64(); sg[sgk + k] += c_ - sg0; sg0 = c_; } while (0)
 
     while (true) {
         bool committed = false;
@@ -2218,6 +2254,9 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                            xwA = opaque_u32(smem_addr(xw));
             __syncthreads();  // every warp is done with the previous task's buffers (and the draw phase's scratch)
             if (warp < YG_NBUF && warp < ntile) issue_tile(warp, warp);
+            sg0 = clock64();
+            sgk = patch ? 0 : 6;
+            sg[sgk + 5] += ntile;
             for (long long n = 0; n < ntile; ++n) {
                 const int b = (int)(n % YG_NBUF);
                 const long long c0 = n * YG_TC;
@@ -2269,8 +2308,10 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                 gm[lane] = (unsigned char)g0;
                 gm[lane + 32] = (unsigned char)g1;
                 __syncwarp();
+                CELDA_YG_SEG(0);
                 mbar_wait(fullb + b, (phaseBits >> b) & 1u);
                 phaseBits ^= 1u << b;
+                CELDA_YG_SEG(1);
                 // ---- the column loop
                 {
                     const double* tl = tile + (size_t)b * YG_TC * 32 + lane;
@@ -2336,6 +2377,7 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                 }
                 // ---- buffer b is free once every warp has passed; the last one refills it
                 __syncwarp();
+                CELDA_YG_SEG(2);
                 int last = 0;
                 if (lane == 0) {
                     __threadfence_block();
@@ -2343,7 +2385,11 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                     if (last) cnt_s[b] = 0;
                 }
                 last = __shfl_sync(FULL, last, 0);
-                if (last && n + YG_NBUF < ntile) issue_tile(n + YG_NBUF, b);
+                CELDA_YG_SEG(3);
+                if (last && n + YG_NBUF < ntile) {
+                    issue_tile(n + YG_NBUF, b);
+                    CELDA_YG_SEG(4);
+                }
             }
             // the per-candidate scalar terms; a rolled loop (the chain values pass through the warp's count list, which
             // is idle now) keeps 6 x NR inlined lgamma evaluations out of the instruction stream
@@ -2452,6 +2498,12 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
         a.w.stats[5] += ck_draw;
         a.w.stats[6] += ck_bar;
     }
+    // unit-phase segment clocks of CTA 0's first and last warp (profile slots 2 and 3, unused by a celda_G chain)
+    if (blockIdx.x == 0 && lane == 0 && warp == 0)
+        for (int q = 0; q < 6; ++q) {
+            a.w.stats[16 + q] += sg[q];
+            a.w.stats[24 + q] += sg[6 + q];
+        }
 }
 
 inline size_t yg_sweep_smem(int L, int T, int nwarp) {

@@ -402,7 +402,7 @@ static void o_revsort(double *a, int *ib, int n)
 
 /* .sampleLl (R/celda_functions.R:1-11) with the uniform INJECTED:
  * exp(ll - max) ; / sum ; sample.int(n, 1, TRUE, prob) = FixupProb (renormalise by a plain-double sum of
- * the positive entries) ; Walker alias if > 200 entries have n*p > 0.1 (not restated: returns -1) ;
+ * the positive entries) ; Walker alias if > 200 entries have n*p > 0.1 ;
  * ProbSampleReplace (revsort descending, cumulative sum, first j < n-1 with u <= cum[j]).
  * Returns the 1-based label.  *margin (optional) = min_j |u - cum[j]| over the scanned prefix. */
 int o_sample_ll(const double *ll, int n, double u, double *work_p, int *work_perm, double *margin)
@@ -424,7 +424,37 @@ int o_sample_ll(const double *ll, int n, double u, double *work_p, int *work_per
     for (int i = 0; i < n; i++) work_p[i] /= s2;
     int nc = 0;
     for (int i = 0; i < n; i++) if (n * work_p[i] > 0.1) nc++;
-    if (nc > 200) return -1; /* Walker alias branch: not restated */
+    if (nc > 200) {
+        /* Walker's alias method (R random.c walker_ProbSampleReplace, restated): q = n p; entries with q < 1 are listed
+         * from the left of HL, the others from the right; each small entry takes the current large one as its alias,
+         * which gives up 1 - q of its mass; q[i] += i; one uniform rU = u n picks cell k = floor(rU) and returns k if
+         * rU < q[k], else its alias. */
+        int *HL = work_perm, H = -1, Lp = n;
+        int *al = (int *)malloc(sizeof(int) * (size_t)n);
+        if (!al) return -4;
+        for (int i = 0; i < n; i++) {
+            work_p[i] = work_p[i] * n;
+            if (work_p[i] < 1.) HL[++H] = i; else HL[--Lp] = i;
+        }
+        for (int i = 0; i < n; i++) al[i] = i;
+        if (H >= 0 && Lp < n) {
+            for (int k = 0; k < n - 1; k++) {
+                int i = HL[k], j = HL[Lp];
+                al[i] = j;
+                work_p[j] += work_p[i] - 1;
+                if (work_p[j] < 1.) Lp++;
+                if (Lp >= n) break;
+            }
+        }
+        for (int i = 0; i < n; i++) work_p[i] += i;
+        double rU = u * n;
+        int k = (int)rU;
+        if (k > n - 1) k = n - 1;
+        int ans = (rU < work_p[k]) ? k + 1 : al[k] + 1;
+        free(al);
+        if (margin) *margin = fabs(rU - work_p[k]) / n;
+        return ans;
+    }
     for (int i = 0; i < n; i++) work_perm[i] = i + 1;
     o_revsort(work_p, work_perm, n);
     for (int i = 1; i < n; i++) work_p[i] += work_p[i - 1];

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--K", type=int, default=50, help="cell populations used only to shape the synthetic counts")
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--flip", type=float, default=0.1, help="fraction of the true module labels re-drawn for the start state")
     a = ap.parse_args()
     import celda_b200 as cb
     from bench_support import simulate_cells_cg
@@ -31,7 +32,7 @@ def main():
     nG = d["nG"]
     rng = np.random.Generator(np.random.PCG64(4))
     y = d["y"].copy()
-    flip = rng.random(nG) < 0.1
+    flip = rng.random(nG) < a.flip
     y[flip] = rng.integers(1, a.L + 1, int(flip.sum()))
     t0 = time.time()
     ch = cb.Chain(counts, None, L=a.L, model=cb.MODEL_G)
@@ -59,6 +60,11 @@ def main():
         "tasks_per_sweep": prof["sweep_y"]["units"] / a.steps,
         "reference_work": {"table_lookups_per_sweep": 2.0 * nG * d["nM"] * a.L, "fresh_lgamma_per_sweep": Z * a.L},
         "dadd_rate_tflops": 2.0 * nG * d["nM"] * a.L / (sweep_ms * 1e-3) / 1e12,
+        "unit_phase_cta0_warp0_clk_per_tile": {
+            kind: dict({q: prof[w][f] / max(1, prof[w]["clk_draw"]) for q, f in (
+                ("build", "rounds"), ("wait_tile", "units"), ("columns", "movers"), ("hand_over", "clk_commit"),
+                ("refill", "clk_units"))}, tiles=prof[w]["clk_draw"] / a.steps)
+            for kind, w in (("patch_tasks", "sweep_z"), ("fresh_tasks", "colSumByGroupChange"))},
         "logLik_first_last": [lls[0], lls[-1]], "gen_s": gen_s, "setup_s": setup_s}))
     ch.close()
 

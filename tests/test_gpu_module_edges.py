@@ -81,3 +81,42 @@ def test_lgdelta_entry_zero_is_NA(oracle, gold_cg):
     ix, u = rng.permutation(nG).astype(np.int32) + 1, rng.random(nG)
     with pytest.raises(cb.CeldaCudaError, match="NA in probability vector"):
         cb.cGCalcGibbsProbY(p["nGByCP"], p["nTSByCP"], p["nByTS"], bare, p["nByG"], y, L, nG, 1.0, 1.0, 1.0, ix, u)
+
+
+def test_walker_alias_draws_more_than_200_likely_modules(oracle):
+    """L = 240 modules and very low counts: nearly every gene's module vector has > 200 entries with L * p > 0.1, so
+    sample.int draws through Walker's alias tables (R/celda_functions.R:1-11 -> sample.int).  Labels, tables and
+    probabilities stay bit-identical to the oracle, in the celda_CG form and on the raw counts (celda_G)."""
+    rng = np.random.default_rng(17)
+    G, C, K, L = 720, 48, 3, 240
+    counts = rng.poisson(0.4, (G, C)).astype(np.int32)
+    counts[counts.sum(1) == 0, 0] = 1
+    counts[0, counts.sum(0) == 0] = 1
+    s = np.ones(C, dtype=np.int32)
+    z = rng.integers(1, K + 1, C).astype(np.int32)
+    y = (rng.permutation(G) % L + 1).astype(np.int32)
+    A, O = cb.CSC.from_dense(counts), dense_to_csc(counts)
+    # celda_CG form
+    ch = cb.Chain(A, s, K=K, L=L)
+    ch.set_state(z, y)
+    p = oracle.cCGDecomposeCounts(O, s, z, y, K, L)
+    ix, u = rng.permutation(G).astype(np.int32) + 1, rng.random(G)
+    ref = oracle.cGCalcGibbsProbY(p["nGByCP"], p["nTSByCP"], p["nByTS"], p["nGByTS"], p["nByG"], y, L, G, 1.0, 1.0, 1.0, ix, u)
+    ch.sweep_y(ix, u)
+    _, yg = ch.get_state()
+    _, py = ch.probs()
+    q = np.exp(py - py.max(axis=0))
+    q /= q.sum(axis=0)
+    assert ((L * q > 0.1).sum(axis=0) > 200).mean() > 0.5     # the Walker branch is the common case here
+    assert np.array_equal(yg, ref["y"]) and np.array_equal(py, ref["probs"])
+    ch.close()
+    # celda_G form
+    ch = cb.Chain(A, None, L=L, model=cb.MODEL_G)
+    ch.set_state(y=y)
+    pg = oracle.cGDecomposeCounts(O, y, L)
+    refg = oracle.cGCalcGibbsProbY(counts.astype(np.float64), pg["nTSByC"], pg["nByTS"], pg["nGByTS"], pg["nByG"], y, L, G,
+                                   1.0, 1.0, 1.0, ix, u)
+    ch.sweep_y(ix, u)
+    _, yg = ch.get_state()
+    assert np.array_equal(yg, refg["y"]) and np.array_equal(ch.probs()[1], refg["probs"])
+    ch.close()

@@ -277,3 +277,51 @@ def test_em_step(oracle, gold_c):
     want = phi.T @ counts + theta[:, s - 1]
     assert np.allclose(a["probs"], want, rtol=1e-11)
     assert np.array_equal(a["z"], want.argmax(0) + 1)
+
+
+def test_walker_alias_branch_of_sample_int(oracle):
+    """More than 200 likely categories: sample.int takes Walker's alias method (R random.c walker_ProbSampleReplace).
+    The restatement must (1) return a category whose alias cell contains u * n, checked against an independent numpy
+    construction of the tables, and (2) sample every category with its probability (exact: cell masses sum to p)."""
+    rng = np.random.default_rng(3)
+    n = 260
+    ll = np.log(rng.dirichlet(np.full(n, 40.0)))           # diffuse: n * p > 0.1 for every category
+    p = np.exp(ll - ll.max())
+    p = p / p.sum()
+    p = p / p[p > 0].sum()
+    assert (n * p > 0.1).sum() > 200
+
+    def tables(p):
+        q = p * n
+        HL, a = np.empty(n, dtype=np.int64), np.arange(n)
+        H, Lp = -1, n
+        for i in range(n):
+            if q[i] < 1.0:
+                H += 1
+                HL[H] = i
+            else:
+                Lp -= 1
+                HL[Lp] = i
+        if H >= 0 and Lp < n:
+            for k in range(n - 1):
+                i, j = HL[k], HL[Lp]
+                a[i] = j
+                q[j] += q[i] - 1
+                if q[j] < 1.0:
+                    Lp += 1
+                if Lp >= n:
+                    break
+        return q, a
+
+    q, a = tables(p.copy())
+    mass = np.zeros(n)                                      # probability of each category under the alias tables
+    for k in range(n):
+        mass[k] += min(q[k], 1.0) / n
+        mass[a[k]] += max(1.0 - q[k], 0.0) / n
+    assert np.allclose(mass, p, atol=1e-12)
+    for u in np.concatenate([rng.random(400), [1e-300, 0.5, 1 - 1e-16]]):
+        got, _ = oracle.sampleLl(ll, u)
+        rU = u * n
+        k = min(int(rU), n - 1)
+        want = (k if rU < q[k] + k else a[k]) + 1
+        assert got == want
