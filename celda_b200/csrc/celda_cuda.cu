@@ -518,17 +518,24 @@ int run_sweep_y(YArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
 
 int run_sweep_yg(YGArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     int threads = YG_THREADS;
-    if (yg_sweep_smem(a.L, b.lgT, threads / 32) > 220 * 1024) threads = 256;
-    const size_t smem = yg_sweep_smem(a.L, b.lgT, threads / 32);
-    if (smem > 220 * 1024) return fail("celda_G y sweep: L=%d needs %zu bytes of shared memory (> 220 KB)", a.L, smem);
-    // window: whole waves of (gene group) x (module chunk) tasks over the grid; a task takes YG_R genes per warp
-    const int GB = threads / 32 * YG_R, nchunk = (a.L + 31) / 32;
-    long long unit = (long long)GB * std::max(1, sms / nchunk);
-    const long long cap = std::min<long long>(b.Wmax, 8192);
-    if (unit > cap) unit = std::max<long long>(1, cap / GB) * GB;
+    const size_t budget = 220 * 1024;
+    // the draw phase's scratch (per warp) and the unit phase's tile ring share the same memory
+    while (threads > 128 && yg_sweep_smem(a.L, b.lgT, threads / 32, 4) > budget) threads /= 2;
+    if (yg_sweep_smem(a.L, b.lgT, threads / 32, 4) > budget)
+        return fail("celda_G y sweep: L=%d needs %zu bytes of shared memory (> 220 KB)", a.L, yg_sweep_smem(a.L, b.lgT, threads / 32, 4));
+    // columns per tile: as many as the budget allows (a multiple of 4, at most 64)
+    int TC = 64;
+    while (TC > 4 && yg_sweep_smem(a.L, b.lgT, threads / 32, TC) > budget) TC -= 4;
+    a.TC = TC;
+    const size_t smem = yg_sweep_smem(a.L, b.lgT, threads / 32, TC);
+    // window: whole waves of (gene group) x (module group) tasks over the grid; a task takes one gene per warp
+    const int nwarp = threads / 32, ngroup = (a.L + 32 * YG_MAXMC - 1) / (32 * YG_MAXMC);
+    long long unit = (long long)nwarp * std::max(1, sms / ngroup);
+    const long long cap = std::min<long long>(b.Wmax, 3 * unit);
+    if (unit > cap) unit = std::max<long long>(1, cap / nwarp) * nwarp;
     const long long full = std::max<long long>(1, cap / unit) * unit;
     a.w = SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.drawMx.p, b.drawNz.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
-                    b.stats.p + 8 * which, b.Wmax, (int)full, (int)unit, std::max(b.Wmin, threads / 32), b.lgT, 1};
+                    b.stats.p + 8 * which, b.Wmax, (int)full, (int)unit, std::max(b.Wmin, nwarp), b.lgT, 1};
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_yg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CELDA_CUDA_OK(cudaMemsetAsync(b.barrier.p, 0, sizeof(unsigned), st));
     void* args[] = {&a};

@@ -1963,19 +1963,18 @@ inline size_t y_sweep_smem(int L, int C, int T, int nwarp, int MC = MCMAX - 1) {
 // .cGCalcGibbsProbY on the RAW counts (R/celda_G.R:401-415, 602-660): every gene's row is scanned over ALL cells
 // against nTSByC (L x nM), zero counts included -- cG_CalcGibbsProbY adds and subtracts the same table entry for
 // them (src/cG_calcGibbsProbY.cpp:218-222), which is not a floating-point no-op, so bit parity needs the full
-// column scan: 2 dependent FP64 adds per (gene, module, cell).  The kernel is laid out for the FP64 pipe:
-//   * nTSByC (t) and its cached lgamma (lgt) stay in HBM / L2.  A CTA task = (YG_R genes per warp of the CTA) x
-//     (32 consecutive modules): lane <-> module, and every lane carries YG_R independent accumulation chains, one
-//     per gene of its warp, so one shared-memory read of the cached value feeds 2 * YG_R adds and the chains hide
-//     each other's latency.
-//   * The (t, lgt) tile of YG_TC columns x 32 modules is brought in by TMA bulk copies (cp.async.bulk, one 256-byte
-//     and one 128-byte row per column) into a ring of YG_NBUF buffers, each completing on its own mbarrier; the warp
-//     that is last to finish a buffer refills it, so there is no CTA-wide barrier inside a task.
-//   * Where a gene has a count the term is a fresh lgamma: per tile each warp turns the next entries of its genes'
-//     gene-major twin rows (a 32-entry register window per gene, refilled ahead of use) into a 64-bit column mask
-//     and a list of counts in shared memory; the column loop runs tight over the columns no gene of the warp
-//     touches and takes the warp-uniform branch only at the masks' set bits.
-// Patch units after a commit (da, db) use the same code with lanes 0 and 1 bound to the two modules.
+// column scan: 2 dependent FP64 adds per (gene, module, cell).  Layout:
+//   * nTSByC (t) and its cached lgamma (lgt) stay in HBM / L2.  A CTA task = (one gene per warp) x (a group of up to
+//     8 x 32 modules): lane l of the warp carries one accumulation chain per 32-module chunk (modules l, l + 32, ...),
+//     i.e. up to 8 independent chains per lane that hide each other's FP64 latency, and every chain of the warp
+//     belongs to the SAME gene, so the columns where the gene has a count are a warp-uniform event (a cursor over
+//     the gene's gene-major twin row: a 32-entry register window, the next window already in flight).
+//   * Columns are contiguous in memory (L entries each), so the (t, lgt) tile of TC columns is ONE contiguous slab
+//     per array: two TMA bulk copies (cp.async.bulk) per tile into a ring of YG_NBUF buffers, each completing on its
+//     own mbarrier; the warp that is last to finish a buffer refills it -- no CTA-wide barrier inside a task.
+//   * Measured bound: shared-memory bandwidth (one 8-byte read per 2 FP64 adds), see DESIGN.md.
+// Patch units after a commit (da, db): the same code with one chain, lanes 0 and 1 bound to the two modules and a
+// tile of just those two rows.
 struct YGArgs {
     int nG, L;
     long long nM;
@@ -1994,37 +1993,33 @@ struct YGArgs {
     int doSample;
     double* probs;         // L x nG or null
     int noTma;             // measurement aid (CELDA_CUDA_YG_NOTMA): stage the tiles with plain loads
+    int TC;                // columns per tile (a multiple of 4; set by the launcher from the shared-memory budget)
     SweepWork w;
 };
 
-// the table-miss path of the column loop as a call: eight inlined copies would not fit the instruction cache
+// the table-miss path of the column loop as a call: inlined copies would not fit the instruction cache
 __device__ __noinline__ double dlgamma_hot_call(double x) { return dlgamma_hot(x); }
 
-constexpr int YG_TC = 64;    // columns per staged tile: one 64-bit event mask per gene and tile
-constexpr int YG_R = 8;      // genes per warp = accumulation chains per lane
-constexpr int YG_THREADS = 512;  // 16 warps: 128 registers per thread for the chains, masks and cursors
-constexpr int YG_NBUF = 3;   // tile buffers in flight
+constexpr int YG_THREADS = 512;   // 16 genes per task; 128 registers per thread for up to 8 chains with their operands in flight
+constexpr int YG_NBUF = 3;        // tile buffers in flight
+constexpr int YG_MAXMC = 8;       // 32-module chunks per task (chains per lane)
 
-struct YGCursor {  // per (warp, gene slot): where the gene's twin row starts, its length, the window's first entry
-    long long rb;
-    int n, e;
-};
-
-// bytes of the unit-phase work area (tiles, count lists, cursors); it shares its memory with the draw phase's scratch
-__host__ __device__ inline size_t yg_unit_bytes(int nwarp) {
-    return (size_t)YG_NBUF * YG_TC * 32 * (sizeof(double) + sizeof(int)) + (size_t)nwarp * YG_R * YG_TC * sizeof(int) +
-           (size_t)nwarp * YG_R * sizeof(YGCursor) + (size_t)nwarp * YG_TC;
+__host__ __device__ inline int yg_group_modules(int L) { return L < 32 * YG_MAXMC ? L : 32 * YG_MAXMC; }
+// bytes of the tile ring: TC columns x (modules of a group) x (8 + 4) bytes per buffer
+__host__ __device__ inline size_t yg_unit_bytes(int L, int TC) {
+    // + 256: the idle chains of a row's last 32-module chunk read up to 31 entries past the last row
+    return (size_t)YG_NBUF * TC * yg_group_modules(L) * (sizeof(double) + sizeof(int)) + 256;
 }
 __host__ __device__ inline size_t yg_fixed_bytes(int L, int T) {  // tables that live for the whole kernel, padded to 128
     const size_t b = sizeof(double) * T + sizeof(long long) * L + sizeof(unsigned long long) * YG_NBUF +
-                     sizeof(int) * (L + YG_NBUF + 8);
+                     sizeof(int) * (L + YG_NBUF + 8 + 65);
     return (b + 127) & ~(size_t)127;
 }
 
 __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
     extern __shared__ __align__(128) unsigned char yg_smem[];
     if (a.w.status[1]) return;  // the injected visiting order failed its check: nothing may be indexed through it
-    const int L = a.L, T = a.w.lgT;
+    const int L = a.L, T = a.w.lgT, TC = a.TC;
     const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int scratchD = 2 * L + (L + 1) / 2 + 2;
     const unsigned FULL = 0xffffffffu;
@@ -2034,23 +2029,21 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
     int* g_s = reinterpret_cast<int*>(fullb + YG_NBUF);
     int* cnt_s = g_s + L;            // [YG_NBUF] warps done with the buffer
     int* s_misc = cnt_s + YG_NBUF;   // [8]
+    int* hist_s = s_misc + 8;        // [65] density buckets of the per-round gene order
     unsigned char* region = yg_smem + yg_fixed_bytes(L, T);
     // draw phase view of the region
     double* scr = reinterpret_cast<double*>(region) + (size_t)warp * scratchD;
-    // unit phase view
-    double* tile = reinterpret_cast<double*>(region);                          // [YG_NBUF][YG_TC][32] lgamma(t + beta)
-    int* ttile = reinterpret_cast<int*>(tile + YG_NBUF * YG_TC * 32);          // [YG_NBUF][YG_TC][32] t
-    int* xw = ttile + YG_NBUF * YG_TC * 32 + (size_t)warp * YG_R * YG_TC;      // [YG_R][YG_TC] this warp's counts in the tile
-    YGCursor* cst = reinterpret_cast<YGCursor*>(ttile + YG_NBUF * YG_TC * 32 + (size_t)nwarp * YG_R * YG_TC) + warp * YG_R;
-    unsigned char* gm = reinterpret_cast<unsigned char*>(cst - warp * YG_R + nwarp * YG_R) + warp * YG_TC;  // [YG_TC] gene-slot set per column
+    // unit phase view: the tile ring, per buffer TC x GM doubles then (after all buffers) TC x GM ints
+    const int GM = yg_group_modules(L);                         // modules per task group (= L unless L > 256)
+    double* tile = reinterpret_cast<double*>(region);           // [YG_NBUF][TC][GM] lgamma(t + beta)
+    int* ttile = reinterpret_cast<int*>(tile + (size_t)YG_NBUF * TC * GM);  // [YG_NBUF][TC][GM] t
     const int tw = gridDim.x * nwarp;
     // warp-granular work goes round the CTAs first (item c -> CTA c mod grid), so a short list of items lands on
     // many SMs with one warp each instead of filling a few SMs
     const int gwarpT = warp * gridDim.x + blockIdx.x;
     const long long nM = a.nM;
-    const int nchunk = (L + 31) / 32;
-    const long long ntile = (nM + YG_TC - 1) / YG_TC;
-    const bool tmaOk = (L & 3) == 0 && !a.noTma;  // 16-byte alignment of every (column, 32-module chunk) row of t and lgt
+    const int ngroup = (L + GM - 1) / GM;
+    const long long ntile = (nM + TC - 1) / TC;
 
     for (int q = threadIdx.x; q < T; q += blockDim.x) lgtab[q] = dlgamma((double)q + a.beta);
     for (int q = threadIdx.x; q < L; q += blockDim.x) {
@@ -2074,10 +2067,6 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
     long long rounds = 0, units_done = 0, movers = 0;
     long long redraws = 0;  // carried items drawn again in full (this thread's share)
     long long ck_commit = 0, ck_units = 0, ck_draw = 0, ck_bar = 0, ck0 = clock64(), ck1;
-    long long sg[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, sg0 = 0;  // unit-phase segments of this warp, patch tasks then fresh tasks:
-                                                                       // build, wait, columns, hand-over, refill, tiles
-    int sgk = 0;
-#define CELDA_YG_SEG(k) do { const long long c_ = clock64(); sg[sgk + k] += c_ - sg0; sg0 = c_; } while (0)
 
     while (true) {
         bool committed = false;
@@ -2127,114 +2116,143 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
             }
         }
         if (pos >= a.nG) break;
-        if (committed) grid_sync(a.w.barrier, bar_target);  // table rows a, b are visible before they are read
-        CELDA_TICKR(ck_commit);
         // after a commit the window is topped up with fresh items only once it is less than half full: carried items
         // cost two patch units and a check (draw_unchanged), fresh ones a full evaluation and draw, cheaper in batches
         const bool topup = nd != 2 || (hi - pos) * 2 < W;
         const long long end = topup ? max(hi, min(pos + (long long)W, (long long)a.nG)) : hi;
         const int nwin = (int)(end - pos);
-        // ---- tasks: patch = (carried genes) x {da, db}; fresh = (new genes) x (32-module chunk).  A task takes NR genes
-        // per warp; NR is the largest of 8, 4, 2, 1 that still spreads the round over the whole grid (a round lasts as
-        // long as its longest task, and a task's time grows with NR).
-        auto pick_nr = [&](long long genes, int chunks) -> int {
-            int best = 1;
-            long long bestCost = 0x7fffffffffffffffLL;
-            for (int nr = YG_R; nr >= 1; nr >>= 1) {  // round time ~ waves x (fixed cost per tile + cost per gene slot)
-                const long long tasks = ((genes + (long long)nwarp * nr - 1) / ((long long)nwarp * nr)) * chunks;
-                const long long cost = ((tasks + gridDim.x - 1) / gridDim.x) * (3 + nr);
-                if (cost < bestCost) {
-                    bestCost = cost;
-                    best = nr;
+        // A gene's cost grows with its number of stored entries (a column with a count costs several times a column
+        // without), and the warps of a task advance tile by tile together: CTA 0 orders the carried and the fresh genes
+        // by density (64 buckets, densest first), so that a task's warps carry similar genes and the longest tasks
+        // start first.  Which warp evaluates a gene does not change the arithmetic.
+        int* permP = reinterpret_cast<int*>(a.w.bufA);  // [Wmax] slot -> carried gene (offset from pos)
+        int* permF = permP + a.w.Wmax;                  // [Wmax] slot -> fresh gene (offset from hi)
+        if (blockIdx.x == 0) {
+            for (int part = 0; part < 2; ++part) {
+                const long long lo = part ? hi : pos;
+                const int n = (int)(part ? end - hi : ((nd == 2) ? hi - pos : 0));
+                int* perm = part ? permF : permP;
+                if (n == 0) continue;
+                __syncthreads();
+                for (int q = threadIdx.x; q < 65; q += blockDim.x) hist_s[q] = 0;
+                __syncthreads();
+                for (int q = threadIdx.x; q < n; q += blockDim.x) {
+                    const int g = a.ix[lo + q] - 1;
+                    const long long nz = a.rp[g + 1] - a.rp[g];
+                    atomicAdd(&hist_s[63 - (int)min(63LL, nz * 64 / (nM + 1))], 1);
+                }
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    int run = 0;
+                    for (int q = 0; q < 64; ++q) {
+                        const int c = hist_s[q];
+                        hist_s[q] = run;
+                        run += c;
+                    }
+                }
+                __syncthreads();
+                for (int q = threadIdx.x; q < n; q += blockDim.x) {
+                    const int g = a.ix[lo + q] - 1;
+                    const long long nz = a.rp[g + 1] - a.rp[g];
+                    perm[atomicAdd(&hist_s[63 - (int)min(63LL, nz * 64 / (nM + 1))], 1)] = q;
                 }
             }
-            return best;
-        };
-        const int nrP = (nd == 2) ? pick_nr(hi - pos, 1) : 1, nrF = pick_nr(end - hi, nchunk);
-        const int GBp = nwarp * nrP, GBf = nwarp * nrF;
-        const long long nPatchGrp = (nd == 2) ? (hi - pos + GBp - 1) / GBp : 0;
-        const long long nFreshGrp = (end - hi + GBf - 1) / GBf;
-        const long long ntask = nPatchGrp + nFreshGrp * nchunk;
+        }
+        grid_sync(a.w.barrier, bar_target);  // the order, and after a commit table rows a, b, are visible before they are read
+        CELDA_TICKR(ck_commit);
+        // ---- tasks: patch = (nwarp carried genes) x {da, db}; fresh = (nwarp new genes) x (module group)
+        const long long nPatchGrp = (nd == 2) ? (hi - pos + nwarp - 1) / nwarp : 0;
+        const long long nFreshGrp = (end - hi + nwarp - 1) / nwarp;
+        const long long ntask = nPatchGrp + nFreshGrp * ngroup;
         ++rounds;
-        // One task.  NR genes per warp: slot r <-> visiting position gstart + r * nwarp + warp.
-        auto run_task = [&](auto nr_tag, long long task) {
-            constexpr int NR = decltype(nr_tag)::value;
-            long long gstart, glimit;  // visiting positions [gstart, glimit) of this task's genes (at most nwarp * NR)
-            int l, l0 = 0, nl = 2;     // this lane's module (-1 = inactive lane); chunk start and width
+        // One task with MC chains per lane.
+        auto run_task = [&](auto mc_tag, long long task) {
+            constexpr int MC = decltype(mc_tag)::value;
             const bool patch = task < nPatchGrp;
+            long long tg;      // visiting position of this warp's gene
+            bool valid;
+            int l0 = 0, gm = 2, stride = 2;   // first module, modules and row stride of the task's tile
             if (patch) {
-                gstart = pos + task * (nwarp * NR);
-                glimit = hi;
-                l = (lane == 0) ? da : (lane == 1 ? db : -1);
+                const long long slot = task * nwarp + warp;
+                valid = slot < hi - pos;
+                tg = pos + (valid ? __ldcg(permP + slot) : 0);
             } else {
                 const long long q = task - nPatchGrp;
-                gstart = hi + (q / nchunk) * (nwarp * NR);
-                glimit = end;
-                l0 = (int)(q % nchunk) * 32;
-                nl = min(32, L - l0);
-                l = (lane < nl) ? l0 + lane : -1;
+                const long long slot = (q / ngroup) * nwarp + warp;
+                valid = slot < end - hi;
+                tg = hi + (valid ? __ldcg(permF + slot) : 0);
+                l0 = (int)(q % ngroup) * GM;
+                gm = min(GM, L - l0);
+                stride = gm;
             }
-            const bool active = l >= 0;
-            const bool useTma = tmaOk && !patch;
-            int pc[NR], px[NR], wq[NR];
-            unsigned curMask = 0;  // bit r: this lane's module is gene r's current module
-            double p[NR];
-            const int NONE = 0x7fffffff;
+            // chain m of this lane <-> module lm[m] (patch: lanes 0 and 1 <-> da, db), -1 = idle
+            const int gi = valid ? a.ix[tg] - 1 : 0;
+            const int cur = valid ? a.y[gi] - 1 : -1;
+            unsigned actMask = 0, curMask = 0;
 #pragma unroll
-            for (int r = 0; r < NR; ++r) {
-                const long long tg = gstart + (long long)r * nwarp + warp;
-                const bool valid = tg < glimit;
-                const int gi = valid ? a.ix[tg] - 1 : 0;
-                const long long rb = valid ? a.rp[gi] : 0;
-                const int n = valid ? (int)(a.rp[gi + 1] - rb) : 0;
-                if (lane == 0) cst[r] = YGCursor{rb, n, 0};
-                if (valid && active && a.y[gi] - 1 == l) curMask |= 1u << r;
-                pc[r] = (lane < n) ? __ldg(a.tcol + rb + lane) : NONE;
-                px[r] = (lane < n) ? __ldg(a.tx + rb + lane) : 0;
-                wq[r] = 0;
-                p[r] = 0.0;
+            for (int m = 0; m < MC; ++m) {
+                const int l = patch ? (lane == 0 ? da : (lane == 1 ? db : -1)) : ((m * 32 + lane < gm) ? l0 + m * 32 + lane : -1);
+                if (l >= 0 && valid) actMask |= 1u << m;
+                if (l >= 0 && l == cur) curMask |= 1u << m;
             }
-            // one warp loads tile n into buffer b: TMA bulk copies for a module chunk, plain loads for the two patch rows
+            const int laneOff = patch ? min(lane, 1) : lane;  // this lane's entry within a tile row (+ 32 m)
+            const bool useTma = !patch && !a.noTma && gm == L;
+            // cursor over the gene's twin row: lane k holds entry wbase + k, the following window already in flight
+            const long long rb = valid ? a.rp[gi] : 0;
+            const int nEnt = valid ? (int)(a.rp[gi + 1] - rb) : 0;
+            const int NONE = 0x7fffffff;
+            int wbase = 0, widx = 0;
+            int wc = (lane < nEnt) ? __ldg(a.tcol + rb + lane) : NONE, wx = (lane < nEnt) ? __ldg(a.tx + rb + lane) : 0;
+            int wc2 = (32 + lane < nEnt) ? __ldg(a.tcol + rb + 32 + lane) : NONE, wx2 = (32 + lane < nEnt) ? __ldg(a.tx + rb + 32 + lane) : 0;
+            int nextcol = __shfl_sync(FULL, wc, 0), nextx = __shfl_sync(FULL, wx, 0);
+            double p[MC];
+#pragma unroll
+            for (int m = 0; m < MC; ++m) p[m] = 0.0;
+            // one warp loads tile n into buffer b
             auto issue_tile = [&](long long n, int b) {
-                const long long c0 = n * YG_TC;
-                const int tc = (int)min((long long)YG_TC, nM - c0);
-                double* dt = tile + (size_t)b * YG_TC * 32;
-                int* di = ttile + (size_t)b * YG_TC * 32;
-                if (useTma) {
-                    if (lane == 0) mbar_arrive_expect_tx(fullb + b, (unsigned)(tc * nl * 12));
-                    __syncwarp();
-                    fence_proxy_async();  // rows written by the commit phase (generic proxy) are read by the copy engine
-                    for (int cc = lane; cc < tc; cc += 32) {
-                        const size_t g = (size_t)(c0 + cc) * L + l0;
-                        bulk_copy_g2s(dt + cc * 32, a.lgt + g, (unsigned)nl * 8u, fullb + b);
-                        bulk_copy_g2s(di + cc * 32, a.t + g, (unsigned)nl * 4u, fullb + b);
+                const long long c0 = n * TC;
+                const int tc = (int)min((long long)TC, nM - c0);
+                double* dt = tile + (size_t)b * TC * GM;
+                int* di = ttile + (size_t)b * TC * GM;
+                const unsigned bytes8 = (unsigned)tc * (unsigned)L * 8u, bytes4 = (unsigned)tc * (unsigned)L * 4u;
+                if (useTma && (bytes4 & 15u) == 0) {
+                    // the tile's columns are one contiguous slab of each array: two bulk copies
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(fullb + b, bytes8 + bytes4);
+                        fence_proxy_async();  // rows written by the commit phase (generic proxy) are read by the copy engine
+                        bulk_copy_g2s(dt, a.lgt + (size_t)c0 * L, bytes8, fullb + b);
+                        bulk_copy_g2s(di, a.t + (size_t)c0 * L, bytes4, fullb + b);
                     }
+                    __syncwarp();
                 } else {
                     if (patch) {
                         for (int cc = lane; cc < tc; cc += 32) {
                             const size_t g = (size_t)(c0 + cc) * L;
-                            dt[cc * 32] = __ldcg(a.lgt + g + da);
-                            dt[cc * 32 + 1] = __ldcg(a.lgt + g + db);
-                            di[cc * 32] = __ldcg(a.t + g + da);
-                            di[cc * 32 + 1] = __ldcg(a.t + g + db);
+                            dt[cc * 2] = __ldcg(a.lgt + g + da);
+                            dt[cc * 2 + 1] = __ldcg(a.lgt + g + db);
+                            di[cc * 2] = __ldcg(a.t + g + da);
+                            di[cc * 2 + 1] = __ldcg(a.t + g + db);
                         }
                     } else {
-                        for (int cc0 = 0; cc0 < tc; cc0 += 8) {  // eight columns in flight
+                        const int tot = tc * gm;  // entry q <-> (column q / gm, module l0 + q % gm)
+                        for (int q0 = lane; q0 < tot; q0 += 256) {  // eight loads in flight per lane
                             double v[8];
                             int tv[8];
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
-                                const bool ok = active && cc0 + k < tc;
-                                const size_t g = (size_t)(c0 + cc0 + k) * L + (active ? l : 0);
-                                v[k] = ok ? __ldcg(a.lgt + g) : 0.0;
-                                tv[k] = ok ? __ldcg(a.t + g) : 0;
+                                const int q = q0 + 32 * k;
+                                const size_t g = (size_t)(c0 + q / gm) * L + l0 + q % gm;
+                                v[k] = (q < tot) ? __ldcg(a.lgt + g) : 0.0;
+                                tv[k] = (q < tot) ? __ldcg(a.t + g) : 0;
                             }
 #pragma unroll
-                            for (int k = 0; k < 8; ++k)
-                                if (cc0 + k < tc) {
-                                    dt[(cc0 + k) * 32 + lane] = v[k];
-                                    di[(cc0 + k) * 32 + lane] = tv[k];
+                            for (int k = 0; k < 8; ++k) {
+                                const int q = q0 + 32 * k;
+                                if (q < tot) {
+                                    dt[q] = v[k];
+                                    di[q] = tv[k];
                                 }
+                            }
                         }
                     }
                     __threadfence_block();
@@ -2242,142 +2260,63 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                     if (lane == 0) mbar_arrive(fullb + b);
                 }
             };
-            // the term of a column where gene r has the count xv: a fresh lgamma against the cached one
-            auto special = [&](double& pr, bool ic, int xv, int tv, double cached) {
-                const int arg = active ? tv + (ic ? -xv : xv) : 0;
-                const double fresh = (arg < T) ? lgtab[arg] : dlgamma_hot_call((double)arg + a.beta);
-                pr += ic ? cached : fresh;
-                pr -= ic ? fresh : cached;
-            };
-            // opaque copies: the compiler keeps them in registers instead of re-deriving them at every event
-            const unsigned ttBase = opaque_u32(smem_addr(ttile + lane)), gmA = opaque_u32(smem_addr(gm)),
-                           xwA = opaque_u32(smem_addr(xw));
             __syncthreads();  // every warp is done with the previous task's buffers (and the draw phase's scratch)
             if (warp < YG_NBUF && warp < ntile) issue_tile(warp, warp);
-            sg0 = clock64();
-            sgk = patch ? 0 : 6;
-            sg[sgk + 5] += ntile;
             for (long long n = 0; n < ntile; ++n) {
                 const int b = (int)(n % YG_NBUF);
-                const long long c0 = n * YG_TC;
-                const int tc = (int)min((long long)YG_TC, nM - c0);
-                const long long lim = c0 + tc;
-                // ---- this tile's events: per gene the columns where it has a count (a 64-bit mask), the counts stored
-                // by (column, gene slot); then per column the set of gene slots with a count there (one byte)
-                unsigned long long ev = 0;
-                unsigned g0 = 0, g1 = 0;  // gene-slot sets of columns lane and lane + 32
-#pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    bool valid = lane >= wq[r] && (long long)pc[r] < lim;
-                    int rel = valid ? (int)(pc[r] - c0) : 0;
-                    unsigned lo = __reduce_or_sync(FULL, (valid && rel < 32) ? 1u << rel : 0u);
-                    unsigned hiw = __reduce_or_sync(FULL, (valid && rel >= 32) ? 1u << (rel - 32) : 0u);
-                    int cnt = __popc(__ballot_sync(FULL, valid));
-                    if (valid) xw[rel * NR + r] = px[r];
-                    wq[r] += cnt;
-                    if (wq[r] == 32) {  // window used up: the tile may hold more of this gene's entries
-                        YGCursor c = cst[r];
-                        do {
-                            c.e += 32;
-                            const int ee = c.e + lane;
-                            pc[r] = (ee < c.n) ? __ldg(a.tcol + c.rb + ee) : NONE;
-                            px[r] = (ee < c.n) ? __ldg(a.tx + c.rb + ee) : 0;
-                            valid = (long long)pc[r] < lim;
-                            rel = valid ? (int)(pc[r] - c0) : 0;
-                            lo |= __reduce_or_sync(FULL, (valid && rel < 32) ? 1u << rel : 0u);
-                            hiw |= __reduce_or_sync(FULL, (valid && rel >= 32) ? 1u << (rel - 32) : 0u);
-                            cnt = __popc(__ballot_sync(FULL, valid));
-                            if (valid) xw[rel * NR + r] = px[r];
-                        } while (cnt == 32);
-                        wq[r] = cnt;
-                        if (lane == 0) cst[r].e = c.e;
-                    }
-                    if (wq[r] >= 16) {  // slide the window to the first unused entry; the loads land during the column loop
-                        YGCursor c = cst[r];
-                        c.e += wq[r];
-                        const int ee = c.e + lane;
-                        pc[r] = (ee < c.n) ? __ldg(a.tcol + c.rb + ee) : NONE;
-                        px[r] = (ee < c.n) ? __ldg(a.tx + c.rb + ee) : 0;
-                        wq[r] = 0;
-                        if (lane == 0) cst[r].e = c.e;
-                    }
-                    ev |= ((unsigned long long)hiw << 32) | lo;
-                    g0 |= ((lo >> lane) & 1u) << r;
-                    g1 |= ((hiw >> lane) & 1u) << r;
-                }
-                gm[lane] = (unsigned char)g0;
-                gm[lane + 32] = (unsigned char)g1;
-                __syncwarp();
-                CELDA_YG_SEG(0);
+                const long long c0 = n * TC;
+                const int tc = (int)min((long long)TC, nM - c0);
                 mbar_wait(fullb + b, (phaseBits >> b) & 1u);
                 phaseBits ^= 1u << b;
-                CELDA_YG_SEG(1);
-                // ---- the column loop
-                {
-                    const double* tl = tile + (size_t)b * YG_TC * 32 + lane;
-                    const unsigned ttA = ttBase + (unsigned)b * (YG_TC * 32 * 4);
-                    int cc = 0;
-                    while (true) {
-                        const int stop = ev ? (__ffsll((long long)ev) - 1) : tc;
-#pragma unroll 4
-                        for (; cc < stop; ++cc) {  // no gene of this warp has a count here: (p + cached) - cached
-                            const double cached = tl[cc * 32];
+                const double* tl = tile + (size_t)b * TC * GM + laneOff;
+                const int* tt = ttile + (size_t)b * TC * GM + laneOff;
+                int cc = valid ? 0 : tc;  // a warp without a gene only keeps the buffer hand-over going
+                while (cc < tc) {
+                    // columns where the gene has no count: (p + cached) - cached, a tight loop over the chains
+                    const long long rel = (long long)nextcol - c0;
+                    const int stop = rel < tc ? (int)rel : tc;
+#pragma unroll(MC <= 4 ? 2 : 1)
+                    for (; cc < stop; ++cc) {
+                        double cached[MC];
 #pragma unroll
-                            for (int r = 0; r < NR; ++r) p[r] += cached;
+                        for (int m = 0; m < MC; ++m) cached[m] = tl[cc * stride + 32 * m];
 #pragma unroll
-                            for (int r = 0; r < NR; ++r) p[r] -= cached;
+                        for (int m = 0; m < MC; ++m) p[m] += cached[m];
+#pragma unroll
+                        for (int m = 0; m < MC; ++m) p[m] -= cached[m];
+                    }
+                    if (cc < tc) {  // the column with a count: a fresh lgamma against the cached one
+                        const int xv = nextx;
+                        double cached[MC], fresh[MC];
+#pragma unroll
+                        for (int m = 0; m < MC; ++m) {
+                            const bool act = (actMask >> m) & 1u, ic = (curMask >> m) & 1u;
+                            cached[m] = tl[cc * stride + 32 * m];
+                            const int arg = act ? tt[cc * stride + 32 * m] + (ic ? -xv : xv) : 0;
+                            fresh[m] = (arg < T) ? lgtab[arg] : dlgamma_hot_call((double)arg + a.beta);
                         }
-                        if (cc >= tc) break;
-                        ev &= ev - 1;
-                        // 32-bit shared-memory addressing (ld.shared on register operands) keeps the compiler from
-                        // re-deriving the warp's base pointers at every event
-                        const double cached = tl[cc * 32];
-                        const int tv = active ? lds_s32(ttA + (unsigned)cc * 128u) : 0;
-                        const unsigned g = lds_u8(gmA + (unsigned)cc);  // warp-uniform
-                        const unsigned xcA = xwA + (unsigned)(cc * NR) * 4u;
-                        if ((g & (g - 1)) == 0) {             // one gene of the warp has a count in this column (the usual case)
-                            const int rs = __ffs(g) - 1;
-                            const int xv = lds_s32(xcA + (unsigned)rs * 4u);
-                            const bool ic = (curMask >> rs) & 1u;
-                            switch (rs) {
-#define CELDA_YG_CASE(R_)                                                        \
-    case R_:                                                                     \
-        if (R_ < NR) {                                                           \
-            _Pragma("unroll") for (int r = 0; r < NR; ++r)                       \
-                if (r != R_) p[r] += cached;                                     \
-            _Pragma("unroll") for (int r = 0; r < NR; ++r)                       \
-                if (r != R_) p[r] -= cached;                                     \
-            special(p[R_ < NR ? R_ : 0], ic, xv, tv, cached);                    \
-        }                                                                        \
-        break;
-                                CELDA_YG_CASE(0)
-                                CELDA_YG_CASE(1)
-                                CELDA_YG_CASE(2)
-                                CELDA_YG_CASE(3)
-                                CELDA_YG_CASE(4)
-                                CELDA_YG_CASE(5)
-                                CELDA_YG_CASE(6)
-                                CELDA_YG_CASE(7)
-#undef CELDA_YG_CASE
-                                default: break;
-                            }
-                        } else {
+                        if (++widx == 32) {  // window used up: the one in flight takes over, the next is requested
+                            wbase += 32;
+                            widx = 0;
+                            wc = wc2;
+                            wx = wx2;
+                            const int e1 = wbase + 32 + lane;
+                            wc2 = (e1 < nEnt) ? __ldg(a.tcol + rb + e1) : NONE;
+                            wx2 = (e1 < nEnt) ? __ldg(a.tx + rb + e1) : 0;
+                        }
+                        nextcol = __shfl_sync(FULL, wc, widx);
+                        nextx = __shfl_sync(FULL, wx, widx);
 #pragma unroll
-                            for (int r = 0; r < NR; ++r) {
-                                if (g & (1u << r)) {  // warp-uniform
-                                    special(p[r], (curMask >> r) & 1u, lds_s32(xcA + (unsigned)r * 4u), tv, cached);
-                                } else {
-                                    p[r] += cached;
-                                    p[r] -= cached;
-                                }
-                            }
+                        for (int m = 0; m < MC; ++m) {
+                            const bool ic = (curMask >> m) & 1u;
+                            p[m] += ic ? cached[m] : fresh[m];
+                            p[m] -= ic ? fresh[m] : cached[m];
                         }
                         ++cc;
                     }
                 }
                 // ---- buffer b is free once every warp has passed; the last one refills it
                 __syncwarp();
-                CELDA_YG_SEG(2);
                 int last = 0;
                 if (lane == 0) {
                     __threadfence_block();
@@ -2385,45 +2324,40 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                     if (last) cnt_s[b] = 0;
                 }
                 last = __shfl_sync(FULL, last, 0);
-                CELDA_YG_SEG(3);
-                if (last && n + YG_NBUF < ntile) {
-                    issue_tile(n + YG_NBUF, b);
-                    CELDA_YG_SEG(4);
-                }
+                if (last && n + YG_NBUF < ntile) issue_tile(n + YG_NBUF, b);
             }
-            // the per-candidate scalar terms; a rolled loop (the chain values pass through the warp's count list, which
-            // is idle now) keeps 6 x NR inlined lgamma evaluations out of the instruction stream
-            double* pw = reinterpret_cast<double*>(xw);  // [NR][32] doubles fit the count list's YG_TC x YG_R ints
-            __syncwarp();
+            // the per-candidate scalar terms of cG_CalcGibbsProbY's second loop
 #pragma unroll
-            for (int r = 0; r < NR; ++r) pw[r * 32 + lane] = p[r];
-#pragma unroll 1
-            for (int r = 0; r < NR; ++r) {
-                const long long tg = gstart + (long long)r * nwarp + warp;
-                if (active && tg < glimit) {
-                    const int gi = a.ix[tg] - 1;
-                    const bool isCur = (curMask >> r) & 1u;
+            for (int m = 0; m < MC; ++m) {
+                if ((actMask >> m) & 1u) {
+                    const int l = patch ? (lane == 0 ? da : db) : l0 + m * 32 + lane;
+                    const bool isCur = (curMask >> m) & 1u;
                     const int g = g_s[l];
                     const double Tl = (double)T_s[l], Ni = (double)a.nByG[gi];
                     const int g1 = isCur ? g - 1 : g, g0 = g1 + 1;
-                    double pp = pw[r * 32 + lane];
-                    pp += dlgamma_hot((double)g0 + a.gamma);
-                    pp -= dlgamma_hot((double)g1 + a.gamma);
-                    pp += dlgdelta(g0, a.delta);
-                    pp -= dlgdelta(g1, a.delta);
-                    pp += dlgamma_hot(isCur ? Tl - Ni + (double)g1 * a.delta : Tl + (double)g1 * a.delta);
-                    pp -= dlgamma_hot(isCur ? Tl + (double)g0 * a.delta : Tl + Ni + (double)g0 * a.delta);
+                    double pp = p[m];
+                    pp += dlgamma_hot_call((double)g0 + a.gamma);
+                    pp -= dlgamma_hot_call((double)g1 + a.gamma);
+                    pp += (g0 == 0) ? dlgdelta(0, a.delta) : dlgamma_hot_call((double)g0 * a.delta);
+                    pp -= (g1 == 0) ? dlgdelta(0, a.delta) : dlgamma_hot_call((double)g1 * a.delta);
+                    pp += dlgamma_hot_call(isCur ? Tl - Ni + (double)g1 * a.delta : Tl + (double)g1 * a.delta);
+                    pp -= dlgamma_hot_call(isCur ? Tl + (double)g0 * a.delta : Tl + Ni + (double)g0 * a.delta);
                     a.w.bufP[ring_slot(tg, a.w.Wmax) * L + l] = pp;
                 }
             }
-            __syncwarp();
         };
         for (long long task = blockIdx.x; task < ntask; task += gridDim.x) {
-            switch (task < nPatchGrp ? nrP : nrF) {
-                case 8: run_task(std::integral_constant<int, 8>{}, task); break;
-                case 4: run_task(std::integral_constant<int, 4>{}, task); break;
+            const int q = (int)((task - nPatchGrp) % ngroup);
+            const int mc = task < nPatchGrp ? 1 : (min(GM, L - q * GM) + 31) / 32;
+            switch (mc) {
+                case 1: run_task(std::integral_constant<int, 1>{}, task); break;
                 case 2: run_task(std::integral_constant<int, 2>{}, task); break;
-                default: run_task(std::integral_constant<int, 1>{}, task); break;
+                case 3: run_task(std::integral_constant<int, 3>{}, task); break;
+                case 4: run_task(std::integral_constant<int, 4>{}, task); break;
+                case 5: run_task(std::integral_constant<int, 5>{}, task); break;
+                case 6: run_task(std::integral_constant<int, 6>{}, task); break;
+                case 7: run_task(std::integral_constant<int, 7>{}, task); break;
+                default: run_task(std::integral_constant<int, 8>{}, task); break;
             }
         }
         units_done += ntask;
@@ -2499,16 +2433,11 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
         a.w.stats[6] += ck_bar;
     }
     // unit-phase segment clocks of CTA 0's first and last warp (profile slots 2 and 3, unused by a celda_G chain)
-    if (blockIdx.x == 0 && lane == 0 && warp == 0)
-        for (int q = 0; q < 6; ++q) {
-            a.w.stats[16 + q] += sg[q];
-            a.w.stats[24 + q] += sg[6 + q];
-        }
 }
 
-inline size_t yg_sweep_smem(int L, int T, int nwarp) {
+inline size_t yg_sweep_smem(int L, int T, int nwarp, int TC) {
     const size_t scratchD = (size_t)2 * L + (L + 1) / 2 + 2;
-    return yg_fixed_bytes(L, T) + std::max(sizeof(double) * nwarp * scratchD, yg_unit_bytes(nwarp));
+    return yg_fixed_bytes(L, T) + std::max(sizeof(double) * nwarp * scratchD, yg_unit_bytes(L, TC));
 }
 
 // lgt = lgamma(t + beta) for the whole L x nM table (at set_state; the sweep keeps it current afterwards)

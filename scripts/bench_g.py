@@ -60,11 +60,6 @@ def main():
         "tasks_per_sweep": prof["sweep_y"]["units"] / a.steps,
         "reference_work": {"table_lookups_per_sweep": 2.0 * nG * d["nM"] * a.L, "fresh_lgamma_per_sweep": Z * a.L},
         "dadd_rate_tflops": 2.0 * nG * d["nM"] * a.L / (sweep_ms * 1e-3) / 1e12,
-        "unit_phase_cta0_warp0_clk_per_tile": {
-            kind: dict({q: prof[w][f] / max(1, prof[w]["clk_draw"]) for q, f in (
-                ("build", "rounds"), ("wait_tile", "units"), ("columns", "movers"), ("hand_over", "clk_commit"),
-                ("refill", "clk_units"))}, tiles=prof[w]["clk_draw"] / a.steps)
-            for kind, w in (("patch_tasks", "sweep_z"), ("fresh_tasks", "colSumByGroupChange"))},
         "logLik_first_last": [lls[0], lls[-1]], "gen_s": gen_s, "setup_s": setup_s}))
     ch.close()
 
