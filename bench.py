@@ -596,7 +596,7 @@ def rooflines(cb, ch, a, d, prof, clk, default_cfg):
     bytes_alg = {"rowSumByGroup": 8 * Z + 4 * (nM + 1) + 4 * nG + 4.0 * a.L * nM,
                  "colSumByGroup": 8 * Z + 4 * (nM + 1) + 4 * nM + 4.0 * nG * a.K}
     out["roofline_aggregation"] = {}
-    for kname, kern in (("rowSumByGroup", "k_rowsum_csc_v4"), ("colSumByGroup", "k_colsum_twin_v4")):
+    for kname, kern in (("rowSumByGroup", "k_rowsum_csc_v4"), ("colSumByGroup", "k_colsum_twin_v5")):
         ms1 = agg[kname]["ms"] / max(1, agg[kname]["launches"])
         out["roofline_aggregation"][kname] = {
             "bound": "hbm", "kernel": kern, "achieved": bytes_alg[kname] / (ms1 * 1e-3) / 1e9, "peak": hbm,

@@ -531,7 +531,7 @@ int run_sweep_yg(YGArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     // window: whole waves of (gene group) x (module group) tasks over the grid; a task takes one gene per warp
     const int nwarp = threads / 32, ngroup = (a.L + 32 * YG_MAXMC - 1) / (32 * YG_MAXMC);
     long long unit = (long long)nwarp * std::max(1, sms / ngroup);
-    const long long cap = std::min<long long>(b.Wmax, 3 * unit);
+    const long long cap = std::min<long long>(b.Wmax, ((a.flags & 8) ? 2 : 3) * unit);
     if (unit > cap) unit = std::max<long long>(1, cap / nwarp) * nwarp;
     const long long full = std::max<long long>(1, cap / unit) * unit;
     a.w = SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.drawMx.p, b.drawNz.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
@@ -651,6 +651,7 @@ int chain_step_y(celda_chain* h, const int* d_ix, const double* d_u, int doSampl
         a.doSample = doSample;
         a.probs = h->probsY.p;
         a.noTma = (int)env_u32("CELDA_CUDA_YG_NOTMA", 0);
+        a.flags = (int)env_u32("CELDA_CUDA_YG_FLAGS", 3);
         return run_sweep_yg(a, h->wb, h->sms, 0, h->st);
     }
     CELDA_CUDA_OK(cudaMemcpyAsync(h->yprev.p, h->y.p, sizeof(int) * h->nG, cudaMemcpyDeviceToDevice, h->st));

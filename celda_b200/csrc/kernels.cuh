@@ -1328,6 +1328,21 @@ __device__ __forceinline__ unsigned opaque_u32(unsigned x) {
     asm volatile("mov.u32 %0, %1;" : "=r"(y) : "r"(x));
     return y;
 }
+// non-blocking variant: polls with test_wait instead of the (possibly suspending) try_wait
+__device__ __forceinline__ void mbar_wait_poll(unsigned long long* bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}"
+            : "=r"(done)
+            : "r"(smem_addr(bar)), "r"(parity)
+            : "memory");
+    }
+}
 __device__ __forceinline__ int lds_s32(unsigned addr) {
     int v;
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");

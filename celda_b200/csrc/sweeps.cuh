@@ -1993,6 +1993,7 @@ struct YGArgs {
     int doSample;
     double* probs;         // L x nG or null
     int noTma;             // measurement aid (CELDA_CUDA_YG_NOTMA): stage the tiles with plain loads
+    int flags;             // policy switches (CELDA_CUDA_YG_FLAGS): 1 wave-sized top-ups, 2 wide patch tiles, 4 several genes per patch warp
     int TC;                // columns per tile (a multiple of 4; set by the launcher from the shared-memory budget)
     SweepWork w;
 };
@@ -2002,13 +2003,14 @@ __device__ __noinline__ double dlgamma_hot_call(double x) { return dlgamma_hot(x
 
 constexpr int YG_THREADS = 512;   // 16 genes per task; 128 registers per thread for up to 8 chains with their operands in flight
 constexpr int YG_NBUF = 3;        // tile buffers in flight
-constexpr int YG_MAXMC = 8;       // 32-module chunks per task (chains per lane)
+constexpr int YG_MAXMC = 7;       // 32-module chunks per task (chains per lane); 8 would spill at 128 registers
+constexpr int YG_NGP = 4;         // most genes per warp in a patch task
 
 __host__ __device__ inline int yg_group_modules(int L) { return L < 32 * YG_MAXMC ? L : 32 * YG_MAXMC; }
 // bytes of the tile ring: TC columns x (modules of a group) x (8 + 4) bytes per buffer
 __host__ __device__ inline size_t yg_unit_bytes(int L, int TC) {
-    // + 256: the idle chains of a row's last 32-module chunk read up to 31 entries past the last row
-    return (size_t)YG_NBUF * TC * yg_group_modules(L) * (sizeof(double) + sizeof(int)) + 256;
+    // + 1024: idle chains (the chunk count is rounded up to 1, 2, 4 or 7) read up to 95 entries past the last row
+    return (size_t)YG_NBUF * TC * yg_group_modules(L) * (sizeof(double) + sizeof(int)) + 1024;
 }
 __host__ __device__ inline size_t yg_fixed_bytes(int L, int T) {  // tables that live for the whole kernel, padded to 128
     const size_t b = sizeof(double) * T + sizeof(long long) * L + sizeof(unsigned long long) * YG_NBUF +
@@ -2044,6 +2046,7 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
     const long long nM = a.nM;
     const int ngroup = (L + GM - 1) / GM;
     const long long ntile = (nM + TC - 1) / TC;
+    const int TCp = (a.flags & 2) ? max(4, min(1024, (TC * GM / 2) & ~3)) : TC;  // columns per patch tile (two rows) in the same buffers
 
     for (int q = threadIdx.x; q < T; q += blockDim.x) lgtab[q] = dlgamma((double)q + a.beta);
     for (int q = threadIdx.x; q < L; q += blockDim.x) {
@@ -2118,8 +2121,10 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
         if (pos >= a.nG) break;
         // after a commit the window is topped up with fresh items only once it is less than half full: carried items
         // cost two patch units and a check (draw_unchanged), fresh ones a full evaluation and draw, cheaper in batches
+        // ... and in batches of at least one grid-wide wave of tasks: a fresh task lasts several patch tasks, a round with
+        // a handful of them leaves the grid idle
         const bool topup = nd != 2 || (hi - pos) * 2 < W;
-        const long long end = topup ? max(hi, min(pos + (long long)W, (long long)a.nG)) : hi;
+        const long long end = topup ? max(hi, min(max(pos + (long long)W, hi + ((a.flags & 1) ? (long long)a.w.Wunit : 0LL)), (long long)a.nG)) : hi;
         const int nwin = (int)(end - pos);
         // A gene's cost grows with its number of stored entries (a column with a count costs several times a column
         // without), and the warps of a task advance tile by tile together: CTA 0 orders the carried and the fresh genes
@@ -2160,58 +2165,99 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
         }
         grid_sync(a.w.barrier, bar_target);  // the order, and after a commit table rows a, b, are visible before they are read
         CELDA_TICKR(ck_commit);
-        // ---- tasks: patch = (nwarp carried genes) x {da, db}; fresh = (nwarp new genes) x (module group)
-        const long long nPatchGrp = (nd == 2) ? (hi - pos + nwarp - 1) / nwarp : 0;
-        const long long nFreshGrp = (end - hi + nwarp - 1) / nwarp;
+        // ---- tasks: patch = (carried genes) x {da, db}; fresh = (new genes) x (module group).  A patch warp takes
+        // YG_NGP genes (two chains each -- the round is bound by the latency of one chain, more genes per warp are free), a
+        // fresh warp one gene (up to 8 chains).  Warp slot s of a part with n genes in S slots gets the genes s, s + S, ...
+        // of the density order: dense genes are spread over the warps.
+        const long long nP = (nd == 2) ? hi - pos : 0, nF = end - hi;
+        int ngP = 1;  // the fewest genes per warp that fit the carried genes into one grid-wide wave of patch tasks
+        while (false && ngP < YG_NGP && (nP + (long long)nwarp * ngP - 1) / ((long long)nwarp * ngP) > (long long)gridDim.x) ngP *= 2;
+        const long long slotsP = (nP + ngP - 1) / ngP, slotsF = nF;
+        const long long nPatchGrp = (slotsP + nwarp - 1) / nwarp;
+        const long long nFreshGrp = (slotsF + nwarp - 1) / nwarp;
         const long long ntask = nPatchGrp + nFreshGrp * ngroup;
         ++rounds;
-        // One task with MC chains per lane.
-        auto run_task = [&](auto mc_tag, long long task) {
+        // One task with MC chains per lane and gene, NG genes per warp.
+        auto run_task = [&](auto mc_tag, auto ng_tag, long long task) {
             constexpr int MC = decltype(mc_tag)::value;
+            constexpr int NG = decltype(ng_tag)::value;
             const bool patch = task < nPatchGrp;
-            long long tg;      // visiting position of this warp's gene
-            bool valid;
+            // a patch tile holds two entries per column, so it spans many more columns in the same buffer: the chain of a
+            // patch unit is short per column and a tile has to outlast the latency of its refill
+            const int TCt = patch ? TCp : TC;
+            const long long ntileT = (nM + TCt - 1) / TCt;
             int l0 = 0, gm = 2, stride = 2;   // first module, modules and row stride of the task's tile
+            long long slot, nPart, nSlots, lo;
+            const int* perm;
             if (patch) {
-                const long long slot = task * nwarp + warp;
-                valid = slot < hi - pos;
-                tg = pos + (valid ? __ldcg(permP + slot) : 0);
+                slot = task * nwarp + warp;
+                nPart = nP;
+                nSlots = slotsP;
+                lo = pos;
+                perm = permP;
             } else {
                 const long long q = task - nPatchGrp;
-                const long long slot = (q / ngroup) * nwarp + warp;
-                valid = slot < end - hi;
-                tg = hi + (valid ? __ldcg(permF + slot) : 0);
+                slot = (q / ngroup) * nwarp + warp;
+                nPart = nF;
+                nSlots = slotsF;
+                lo = hi;
+                perm = permF;
                 l0 = (int)(q % ngroup) * GM;
                 gm = min(GM, L - l0);
                 stride = gm;
             }
-            // chain m of this lane <-> module lm[m] (patch: lanes 0 and 1 <-> da, db), -1 = idle
-            const int gi = valid ? a.ix[tg] - 1 : 0;
-            const int cur = valid ? a.y[gi] - 1 : -1;
-            unsigned actMask = 0, curMask = 0;
+            // this warp's genes: order positions slot, slot + nSlots, ...
+            long long tg[NG];
+            int gi[NG], cur[NG];
+            unsigned validMask = 0;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                const long long o = slot + g * nSlots;
+                const bool v = slot < nSlots && o < nPart;
+                tg[g] = lo + (v ? __ldcg(perm + o) : 0);
+                gi[g] = v ? a.ix[tg[g]] - 1 : 0;
+                cur[g] = v ? a.y[gi[g]] - 1 : -1;
+                if (v) validMask |= 1u << g;
+            }
+            // chain m of this lane <-> module (patch: lanes 0 and 1 <-> da, db), idle if outside the group
+            unsigned actMask = 0, curMask[NG];
+#pragma unroll
+            for (int g = 0; g < NG; ++g) curMask[g] = 0;
 #pragma unroll
             for (int m = 0; m < MC; ++m) {
                 const int l = patch ? (lane == 0 ? da : (lane == 1 ? db : -1)) : ((m * 32 + lane < gm) ? l0 + m * 32 + lane : -1);
-                if (l >= 0 && valid) actMask |= 1u << m;
-                if (l >= 0 && l == cur) curMask |= 1u << m;
+                if (l >= 0) actMask |= 1u << m;
+#pragma unroll
+                for (int g = 0; g < NG; ++g)
+                    if (l >= 0 && l == cur[g]) curMask[g] |= 1u << m;
             }
             const int laneOff = patch ? min(lane, 1) : lane;  // this lane's entry within a tile row (+ 32 m)
             const bool useTma = !patch && !a.noTma && gm == L;
-            // cursor over the gene's twin row: lane k holds entry wbase + k, the following window already in flight
-            const long long rb = valid ? a.rp[gi] : 0;
-            const int nEnt = valid ? (int)(a.rp[gi + 1] - rb) : 0;
+            // cursors over the genes' twin rows: lane k holds entry wbase + k, the following window already in flight
             const int NONE = 0x7fffffff;
-            int wbase = 0, widx = 0;
-            int wc = (lane < nEnt) ? __ldg(a.tcol + rb + lane) : NONE, wx = (lane < nEnt) ? __ldg(a.tx + rb + lane) : 0;
-            int wc2 = (32 + lane < nEnt) ? __ldg(a.tcol + rb + 32 + lane) : NONE, wx2 = (32 + lane < nEnt) ? __ldg(a.tx + rb + 32 + lane) : 0;
-            int nextcol = __shfl_sync(FULL, wc, 0), nextx = __shfl_sync(FULL, wx, 0);
-            double p[MC];
+            long long rb[NG];
+            int nEnt[NG], wbase[NG], widx[NG], wc[NG], wx[NG], wc2[NG], wx2[NG], nextcol[NG], nextx[NG];
+            double p[NG][MC];
 #pragma unroll
-            for (int m = 0; m < MC; ++m) p[m] = 0.0;
+            for (int g = 0; g < NG; ++g) {
+                const bool v = (validMask >> g) & 1u;
+                rb[g] = v ? a.rp[gi[g]] : 0;
+                nEnt[g] = v ? (int)(a.rp[gi[g] + 1] - rb[g]) : 0;
+                wbase[g] = 0;
+                widx[g] = 0;
+                wc[g] = (lane < nEnt[g]) ? __ldg(a.tcol + rb[g] + lane) : NONE;
+                wx[g] = (lane < nEnt[g]) ? __ldg(a.tx + rb[g] + lane) : 0;
+                wc2[g] = (32 + lane < nEnt[g]) ? __ldg(a.tcol + rb[g] + 32 + lane) : NONE;
+                wx2[g] = (32 + lane < nEnt[g]) ? __ldg(a.tx + rb[g] + 32 + lane) : 0;
+                nextcol[g] = __shfl_sync(FULL, wc[g], 0);
+                nextx[g] = __shfl_sync(FULL, wx[g], 0);
+#pragma unroll
+                for (int m = 0; m < MC; ++m) p[g][m] = 0.0;
+            }
             // one warp loads tile n into buffer b
             auto issue_tile = [&](long long n, int b) {
-                const long long c0 = n * TC;
-                const int tc = (int)min((long long)TC, nM - c0);
+                const long long c0 = n * TCt;
+                const int tc = (int)min((long long)TCt, nM - c0);
                 double* dt = tile + (size_t)b * TC * GM;
                 int* di = ttile + (size_t)b * TC * GM;
                 const unsigned bytes8 = (unsigned)tc * (unsigned)L * 8u, bytes4 = (unsigned)tc * (unsigned)L * 4u;
@@ -2226,12 +2272,28 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                     __syncwarp();
                 } else {
                     if (patch) {
-                        for (int cc = lane; cc < tc; cc += 32) {
-                            const size_t g = (size_t)(c0 + cc) * L;
-                            dt[cc * 2] = __ldcg(a.lgt + g + da);
-                            dt[cc * 2 + 1] = __ldcg(a.lgt + g + db);
-                            di[cc * 2] = __ldcg(a.t + g + da);
-                            di[cc * 2 + 1] = __ldcg(a.t + g + db);
+                        for (int cc0 = lane; cc0 < tc; cc0 += 128) {  // sixteen loads in flight per lane
+                            double va[4], vb[4];
+                            int ta[4], tb[4];
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int cc = cc0 + 32 * k;
+                                const size_t g = (size_t)(c0 + min(cc, tc - 1)) * L;
+                                va[k] = __ldcg(a.lgt + g + da);
+                                vb[k] = __ldcg(a.lgt + g + db);
+                                ta[k] = __ldcg(a.t + g + da);
+                                tb[k] = __ldcg(a.t + g + db);
+                            }
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int cc = cc0 + 32 * k;
+                                if (cc < tc) {
+                                    dt[cc * 2] = va[k];
+                                    dt[cc * 2 + 1] = vb[k];
+                                    di[cc * 2] = ta[k];
+                                    di[cc * 2 + 1] = tb[k];
+                                }
+                            }
                         }
                     } else {
                         const int tot = tc * gm;  // entry q <-> (column q / gm, module l0 + q % gm)
@@ -2261,56 +2323,79 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                 }
             };
             __syncthreads();  // every warp is done with the previous task's buffers (and the draw phase's scratch)
-            if (warp < YG_NBUF && warp < ntile) issue_tile(warp, warp);
-            for (long long n = 0; n < ntile; ++n) {
+            if (warp < YG_NBUF && warp < ntileT) issue_tile(warp, warp);
+            for (long long n = 0; n < ntileT; ++n) {
                 const int b = (int)(n % YG_NBUF);
-                const long long c0 = n * TC;
-                const int tc = (int)min((long long)TC, nM - c0);
-                mbar_wait(fullb + b, (phaseBits >> b) & 1u);
+                const long long c0 = n * TCt;
+                const int tc = (int)min((long long)TCt, nM - c0);
+                if (a.flags & 16) mbar_wait_poll(fullb + b, (phaseBits >> b) & 1u);
+                else mbar_wait(fullb + b, (phaseBits >> b) & 1u);
                 phaseBits ^= 1u << b;
                 const double* tl = tile + (size_t)b * TC * GM + laneOff;
                 const int* tt = ttile + (size_t)b * TC * GM + laneOff;
-                int cc = valid ? 0 : tc;  // a warp without a gene only keeps the buffer hand-over going
+                int cc = validMask ? 0 : tc;  // a warp without a gene only keeps the buffer hand-over going
                 while (cc < tc) {
-                    // columns where the gene has no count: (p + cached) - cached, a tight loop over the chains
-                    const long long rel = (long long)nextcol - c0;
+                    // columns where neither gene has a count: (p + cached) - cached, a tight loop over the chains
+                    int nc = nextcol[0];
+#pragma unroll
+                    for (int g = 1; g < NG; ++g) nc = min(nc, nextcol[g]);
+                    const long long rel = (long long)nc - c0;
                     const int stop = rel < tc ? (int)rel : tc;
-#pragma unroll(MC <= 4 ? 2 : 1)
+#pragma unroll(MC <= 2 ? 2 : 1)
                     for (; cc < stop; ++cc) {
                         double cached[MC];
 #pragma unroll
                         for (int m = 0; m < MC; ++m) cached[m] = tl[cc * stride + 32 * m];
 #pragma unroll
-                        for (int m = 0; m < MC; ++m) p[m] += cached[m];
+                        for (int g = 0; g < NG; ++g) {
 #pragma unroll
-                        for (int m = 0; m < MC; ++m) p[m] -= cached[m];
+                            for (int m = 0; m < MC; ++m) p[g][m] += cached[m];
+                        }
+#pragma unroll
+                        for (int g = 0; g < NG; ++g) {
+#pragma unroll
+                            for (int m = 0; m < MC; ++m) p[g][m] -= cached[m];
+                        }
                     }
-                    if (cc < tc) {  // the column with a count: a fresh lgamma against the cached one
-                        const int xv = nextx;
-                        double cached[MC], fresh[MC];
+                    if (cc < tc) {  // a column where a gene of the warp has a count: a fresh lgamma against the cached one
+                        double cached[MC];
 #pragma unroll
-                        for (int m = 0; m < MC; ++m) {
-                            const bool act = (actMask >> m) & 1u, ic = (curMask >> m) & 1u;
-                            cached[m] = tl[cc * stride + 32 * m];
-                            const int arg = act ? tt[cc * stride + 32 * m] + (ic ? -xv : xv) : 0;
-                            fresh[m] = (arg < T) ? lgtab[arg] : dlgamma_hot_call((double)arg + a.beta);
-                        }
-                        if (++widx == 32) {  // window used up: the one in flight takes over, the next is requested
-                            wbase += 32;
-                            widx = 0;
-                            wc = wc2;
-                            wx = wx2;
-                            const int e1 = wbase + 32 + lane;
-                            wc2 = (e1 < nEnt) ? __ldg(a.tcol + rb + e1) : NONE;
-                            wx2 = (e1 < nEnt) ? __ldg(a.tx + rb + e1) : 0;
-                        }
-                        nextcol = __shfl_sync(FULL, wc, widx);
-                        nextx = __shfl_sync(FULL, wx, widx);
+                        for (int m = 0; m < MC; ++m) cached[m] = tl[cc * stride + 32 * m];
 #pragma unroll
-                        for (int m = 0; m < MC; ++m) {
-                            const bool ic = (curMask >> m) & 1u;
-                            p[m] += ic ? cached[m] : fresh[m];
-                            p[m] -= ic ? fresh[m] : cached[m];
+                        for (int g = 0; g < NG; ++g) {
+                            if ((long long)nextcol[g] - c0 == cc) {  // warp-uniform
+                                const int xv = nextx[g];
+                                double fresh[MC];
+#pragma unroll
+                                for (int m = 0; m < MC; ++m) {
+                                    const bool act = (actMask >> m) & 1u, ic = (curMask[g] >> m) & 1u;
+                                    const int arg = act ? tt[cc * stride + 32 * m] + (ic ? -xv : xv) : 0;
+                                    fresh[m] = (arg < T) ? lgtab[arg] : dlgamma_hot_call((double)arg + a.beta);
+                                }
+                                if (++widx[g] == 32) {  // window used up: the one in flight takes over, the next is requested
+                                    wbase[g] += 32;
+                                    widx[g] = 0;
+                                    wc[g] = wc2[g];
+                                    wx[g] = wx2[g];
+                                    const int e1 = wbase[g] + 32 + lane;
+                                    wc2[g] = (e1 < nEnt[g]) ? __ldg(a.tcol + rb[g] + e1) : NONE;
+                                    wx2[g] = (e1 < nEnt[g]) ? __ldg(a.tx + rb[g] + e1) : 0;
+                                }
+                                nextcol[g] = __shfl_sync(FULL, wc[g], widx[g]);
+                                nextx[g] = __shfl_sync(FULL, wx[g], widx[g]);
+#pragma unroll
+                                for (int m = 0; m < MC; ++m) {
+                                    const bool ic = (curMask[g] >> m) & 1u;
+                                    p[g][m] += ic ? cached[m] : fresh[m];
+                                    p[g][m] -= ic ? fresh[m] : cached[m];
+                                }
+                            } else {
+#pragma unroll
+                                for (int m = 0; m < MC; ++m) {
+                                    p[g][m] += cached[m];
+                                    p[g][m] -= cached[m];
+                                }
+                            }
                         }
                         ++cc;
                     }
@@ -2324,41 +2409,42 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                     if (last) cnt_s[b] = 0;
                 }
                 last = __shfl_sync(FULL, last, 0);
-                if (last && n + YG_NBUF < ntile) issue_tile(n + YG_NBUF, b);
+                if (last && n + YG_NBUF < ntileT) issue_tile(n + YG_NBUF, b);
             }
             // the per-candidate scalar terms of cG_CalcGibbsProbY's second loop
 #pragma unroll
-            for (int m = 0; m < MC; ++m) {
-                if ((actMask >> m) & 1u) {
-                    const int l = patch ? (lane == 0 ? da : db) : l0 + m * 32 + lane;
-                    const bool isCur = (curMask >> m) & 1u;
-                    const int g = g_s[l];
-                    const double Tl = (double)T_s[l], Ni = (double)a.nByG[gi];
-                    const int g1 = isCur ? g - 1 : g, g0 = g1 + 1;
-                    double pp = p[m];
-                    pp += dlgamma_hot_call((double)g0 + a.gamma);
-                    pp -= dlgamma_hot_call((double)g1 + a.gamma);
-                    pp += (g0 == 0) ? dlgdelta(0, a.delta) : dlgamma_hot_call((double)g0 * a.delta);
-                    pp -= (g1 == 0) ? dlgdelta(0, a.delta) : dlgamma_hot_call((double)g1 * a.delta);
-                    pp += dlgamma_hot_call(isCur ? Tl - Ni + (double)g1 * a.delta : Tl + (double)g1 * a.delta);
-                    pp -= dlgamma_hot_call(isCur ? Tl + (double)g0 * a.delta : Tl + Ni + (double)g0 * a.delta);
-                    a.w.bufP[ring_slot(tg, a.w.Wmax) * L + l] = pp;
+            for (int g = 0; g < NG; ++g) {
+                if (!((validMask >> g) & 1u)) continue;
+#pragma unroll
+                for (int m = 0; m < MC; ++m) {
+                    if ((actMask >> m) & 1u) {
+                        const int l = patch ? (lane == 0 ? da : db) : l0 + m * 32 + lane;
+                        const bool isCur = (curMask[g] >> m) & 1u;
+                        const int gt = g_s[l];
+                        const double Tl = (double)T_s[l], Ni = (double)a.nByG[gi[g]];
+                        const int g1 = isCur ? gt - 1 : gt, g0 = g1 + 1;
+                        double pp = p[g][m];
+                        pp += dlgamma_hot_call((double)g0 + a.gamma);
+                        pp -= dlgamma_hot_call((double)g1 + a.gamma);
+                        pp += (g0 == 0) ? dlgdelta(0, a.delta) : dlgamma_hot_call((double)g0 * a.delta);
+                        pp -= (g1 == 0) ? dlgdelta(0, a.delta) : dlgamma_hot_call((double)g1 * a.delta);
+                        pp += dlgamma_hot_call(isCur ? Tl - Ni + (double)g1 * a.delta : Tl + (double)g1 * a.delta);
+                        pp -= dlgamma_hot_call(isCur ? Tl + (double)g0 * a.delta : Tl + Ni + (double)g0 * a.delta);
+                        a.w.bufP[ring_slot(tg[g], a.w.Wmax) * L + l] = pp;
+                    }
                 }
             }
         };
         for (long long task = blockIdx.x; task < ntask; task += gridDim.x) {
             const int q = (int)((task - nPatchGrp) % ngroup);
-            const int mc = task < nPatchGrp ? 1 : (min(GM, L - q * GM) + 31) / 32;
-            switch (mc) {
-                case 1: run_task(std::integral_constant<int, 1>{}, task); break;
-                case 2: run_task(std::integral_constant<int, 2>{}, task); break;
-                case 3: run_task(std::integral_constant<int, 3>{}, task); break;
-                case 4: run_task(std::integral_constant<int, 4>{}, task); break;
-                case 5: run_task(std::integral_constant<int, 5>{}, task); break;
-                case 6: run_task(std::integral_constant<int, 6>{}, task); break;
-                case 7: run_task(std::integral_constant<int, 7>{}, task); break;
-                default: run_task(std::integral_constant<int, 8>{}, task); break;
-            }
+            const int mc = task < nPatchGrp ? 0 : (min(GM, L - q * GM) + 31) / 32;
+            using one = std::integral_constant<int, 1>;
+            // chains per lane: 1, 2, 4 or 7 (a group's chunk count rounded up; idle chains cost adds, no results)
+            if (mc == 0) run_task(one{}, one{}, task);
+            else if (mc == 1) run_task(one{}, one{}, task);
+            else if (mc == 2) run_task(std::integral_constant<int, 2>{}, one{}, task);
+            else if (mc <= 4) run_task(std::integral_constant<int, 4>{}, one{}, task);
+            else run_task(std::integral_constant<int, 7>{}, one{}, task);
         }
         units_done += ntask;
         CELDA_TICKR(ck_units);
