@@ -492,6 +492,17 @@ class Chain:
         check(lib().celda_chain_timer_stop(self._h, C.byref(ms)))
         return ms.value
 
+    def set_scan_mode(self, mode):
+        """celda_G y sweep: 0 = exact full-column scan (default), 1 = only the cells where the gene has a count (opt-in)."""
+        check(lib().celda_chain_set_scan_mode(self._h, int(mode)))
+
+    def scan_margin(self):
+        """(smallest margin / bound over the draws of the last mode-1 sweep, number of draws whose margin does not exceed
+        their bound); no such draw proves that the sweep's labels equal the exact scan's (include/celda_cuda.h)."""
+        m = (C.c_double * 2)()
+        check(lib().celda_chain_scan_margin(self._h, m))
+        return float(m[0]), int(m[1])
+
     def profile(self, enable=True):
         check(lib().celda_chain_profile(self._h, int(enable)))
 

@@ -40,6 +40,8 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     int load() {
         if (so) return 0;
@@ -50,7 +52,9 @@ struct NcclApi {
         CommDestroy = (decltype(CommDestroy))dlsym(so, "ncclCommDestroy");
         AllReduce = (decltype(AllReduce))dlsym(so, "ncclAllReduce");
         GetErrorString = (decltype(GetErrorString))dlsym(so, "ncclGetErrorString");
-        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !GetErrorString)
+        GroupStart = (decltype(GroupStart))dlsym(so, "ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))dlsym(so, "ncclGroupEnd");
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllReduce || !GetErrorString || !GroupStart || !GroupEnd)
             return fail("libnccl.so.2 lacks an expected symbol");
         return 0;
     }
@@ -119,6 +123,9 @@ struct celda_chain {
     DevBuf<double> llPartial, llOut;
     DevBuf<double> phiBuf, thetaBuf;  // EM step
     DevBuf<double> lgt;               // celda_G: lgamma(nTSByC + beta), maintained by the y sweep
+    int scanMode = 0;                 // celda_G: 0 exact full-column scan, 1 count columns only (celda_chain_set_scan_mode)
+    DevBuf<unsigned long long> marginBuf;  // [3] bits of: min margin, max |probs|, max |lgt| of the last mode-1 sweep
+    bool marginValid = false;
     DevBuf<double> lgG;               // celda_CG: lgamma(k + beta), k < 2^22, read through L2 by the y sweep
     // Philox mode
     unsigned long long ph_seed = 0, ph_stream = 0;
@@ -225,9 +232,12 @@ int chain_upload_order(celda_chain* h, int* d_ix, const int* ix, long long n) {
 // exact and order-independent, so every rank ends up with the bit-identical global tables).
 int chain_reduce_tables(celda_chain* h) {
     if (!h->comm) return 0;
+    // one NCCL group: the G x K and the K x S table are reduced by a single fused launch
+    CELDA_NCCL_OK(g_nccl.GroupStart());
     CELDA_NCCL_OK(g_nccl.AllReduce(h->nGByCP_loc.p, h->nGByCP.p, (size_t)h->nG * h->K, ncclInt32, ncclSum, h->comm->comm, h->st));
     CELDA_NCCL_OK(g_nccl.AllReduce(h->mCPByS_loc.p, h->mCPByS.p, (size_t)h->K * h->nS, ncclInt32, ncclSum, h->comm->comm, h->st));
-    count_launch(2);
+    CELDA_NCCL_OK(g_nccl.GroupEnd());
+    count_launch(1);
     return 0;
 }
 
@@ -651,8 +661,26 @@ int chain_step_y(celda_chain* h, const int* d_ix, const double* d_u, int doSampl
         a.doSample = doSample;
         a.probs = h->probsY.p;
         a.noTma = (int)env_u32("CELDA_CUDA_YG_NOTMA", 0);
-        a.flags = (int)env_u32("CELDA_CUDA_YG_FLAGS", 3);
-        return run_sweep_yg(a, h->wb, h->sms, 0, h->st);
+        a.flags = (int)env_u32("CELDA_CUDA_YG_FLAGS", 3) | (h->scanMode ? 32 : 0);
+        CELDA_TRY(run_sweep_yg(a, h->wb, h->sms, 0, h->st));
+        h->marginValid = false;
+        if (h->scanMode && doSample) {  // the report of scan mode 1 (see celda_chain_scan_margin)
+            if (!h->marginBuf.n) CELDA_TRY(h->marginBuf.alloc(3));
+            const unsigned long long init[3] = {0x7ff0000000000000ULL, 0ULL, 0ULL};
+            CELDA_CUDA_OK(cudaMemcpyAsync(h->marginBuf.p, init, sizeof(init), cudaMemcpyHostToDevice, h->st));
+            std::vector<long long> tot((size_t)h->L);
+            CELDA_CUDA_OK(cudaMemcpyAsync(tot.data(), h->nByTS.p, sizeof(long long) * h->L, cudaMemcpyDeviceToHost, h->st));
+            CELDA_CUDA_OK(cudaStreamSynchronize(h->st));  // `init` and `tot` live on this stack frame
+            double ntot = 0;
+            for (long long v : tot) ntot += (double)v;
+            k_max_abs<<<h->sms * 8, 256, 0, h->st>>>(h->lgt.p, (long long)h->L * h->nM, h->marginBuf.p + 2);
+            k_yg_margin<<<h->sms * 4, 256, 0, h->st>>>(h->nG, h->L, (long long)h->nM, h->probsY.p, h->y.p, d_ix, d_u, h->nByG.p,
+                                                      std::log(ntot + h->beta + 1.0), h->marginBuf.p + 2, h->marginBuf.p);
+            count_launch(2);
+            CELDA_CUDA_OK(cudaGetLastError());
+            h->marginValid = true;
+        }
+        return 0;
     }
     CELDA_CUDA_OK(cudaMemcpyAsync(h->yprev.p, h->y.p, sizeof(int) * h->nG, cudaMemcpyDeviceToDevice, h->st));
     CELDA_TRY(launch_sweep_y(h, d_ix, d_u, doSample, 0));
@@ -1758,6 +1786,27 @@ int celda_chain_attach_comm(celda_chain* h, celda_comm* comm) {
     CELDA_TRY(h->mCPByS_loc.alloc((size_t)h->K * h->nS));
     h->comm = comm;
     h->has_state = false;
+    return 0;
+}
+
+int celda_chain_set_scan_mode(celda_chain* h, int mode) {
+    if (h->model != CELDA_MODEL_G) return fail("scan mode: only the celda_G y sweep scans the raw counts");
+    if (mode != 0 && mode != 1) return fail("scan mode must be 0 (exact) or 1 (count columns only)");
+    h->scanMode = mode;
+    h->marginValid = false;
+    return 0;
+}
+
+int celda_chain_scan_margin(celda_chain* h, double* margin) {
+    CELDA_CUDA_OK(cudaSetDevice(h->device));
+    if (!h->marginValid) return fail("scan margin: no sweep in scan mode 1 (with doSample) since the mode was set");
+    unsigned long long bits[3];
+    CELDA_TRY(chain_sync(h));
+    CELDA_CUDA_OK(cudaMemcpy(bits, h->marginBuf.p, sizeof(bits), cudaMemcpyDeviceToHost));
+    double ratio;
+    memcpy(&ratio, bits, sizeof(ratio));
+    margin[0] = ratio;
+    margin[1] = (double)bits[1];
     return 0;
 }
 

@@ -1261,28 +1261,31 @@ __global__ void __launch_bounds__(1024, 1) k_colsum_twin_v5(int nG, int nM, cons
         const int4* c4 = reinterpret_cast<const int4*>(tcol + b4);
         const int4* x4 = reinterpret_cast<const int4*>(tx + b4);
         const long long n4 = (e4 - b4) >> 2;
+        // software pipeline: the next two column / value vectors are in flight while the current two are accumulated
         long long t = lane;
-        for (; t + 96 < n4; t += 128) {  // four column and four value vectors in flight per lane
-            int4 c[4], v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                c[q] = __ldg(c4 + t + 32 * q);
-                v[q] = __ldg(x4 + t + 32 * q);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                atomicAdd(&acc[lab[c[q].x]], v[q].x);
-                atomicAdd(&acc[lab[c[q].y]], v[q].y);
-                atomicAdd(&acc[lab[c[q].z]], v[q].z);
-                atomicAdd(&acc[lab[c[q].w]], v[q].w);
-            }
-        }
-        for (; t < n4; t += 32) {
-            const int4 c = __ldg(c4 + t), v = __ldg(x4 + t);
-            atomicAdd(&acc[lab[c.x]], v.x);
-            atomicAdd(&acc[lab[c.y]], v.y);
-            atomicAdd(&acc[lab[c.z]], v.z);
-            atomicAdd(&acc[lab[c.w]], v.w);
+        int4 c0, c1, v0, v1;
+        const int4 zero4 = make_int4(0, 0, 0, 0);
+        c0 = (t < n4) ? __ldg(c4 + t) : zero4;
+        v0 = (t < n4) ? __ldg(x4 + t) : zero4;
+        c1 = (t + 32 < n4) ? __ldg(c4 + t + 32) : zero4;
+        v1 = (t + 32 < n4) ? __ldg(x4 + t + 32) : zero4;
+        for (; t < n4; t += 64) {
+            const long long tn = t + 64;
+            const int4 nc0 = (tn < n4) ? __ldg(c4 + tn) : zero4, nv0 = (tn < n4) ? __ldg(x4 + tn) : zero4;
+            const int4 nc1 = (tn + 32 < n4) ? __ldg(c4 + tn + 32) : zero4, nv1 = (tn + 32 < n4) ? __ldg(x4 + tn + 32) : zero4;
+            // a vector beyond the row carries zero counts at column 0: adding 0 is harmless
+            atomicAdd(&acc[lab[c0.x]], v0.x);
+            atomicAdd(&acc[lab[c0.y]], v0.y);
+            atomicAdd(&acc[lab[c0.z]], v0.z);
+            atomicAdd(&acc[lab[c0.w]], v0.w);
+            atomicAdd(&acc[lab[c1.x]], v1.x);
+            atomicAdd(&acc[lab[c1.y]], v1.y);
+            atomicAdd(&acc[lab[c1.z]], v1.z);
+            atomicAdd(&acc[lab[c1.w]], v1.w);
+            c0 = nc0;
+            v0 = nv0;
+            c1 = nc1;
+            v1 = nv1;
         }
         __syncwarp();
         for (int k = lane; k < K; k += 32) {

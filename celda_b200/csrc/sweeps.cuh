@@ -1993,7 +1993,7 @@ struct YGArgs {
     int doSample;
     double* probs;         // L x nG or null
     int noTma;             // measurement aid (CELDA_CUDA_YG_NOTMA): stage the tiles with plain loads
-    int flags;             // policy switches (CELDA_CUDA_YG_FLAGS): 1 wave-sized top-ups, 2 wide patch tiles, 4 several genes per patch warp
+    int flags;             // policy switches (CELDA_CUDA_YG_FLAGS): 1 wave-sized top-ups, 2 wide patch tiles; 32 = scan mode 1
     int TC;                // columns per tile (a multiple of 4; set by the launcher from the shared-memory budget)
     SweepWork w;
 };
@@ -2341,6 +2341,7 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                     for (int g = 1; g < NG; ++g) nc = min(nc, nextcol[g]);
                     const long long rel = (long long)nc - c0;
                     const int stop = rel < tc ? (int)rel : tc;
+                    if (a.flags & 32) cc = stop;  // opt-in scan mode 1: the count-free columns are skipped (celda_chain_set_scan_mode)
 #pragma unroll(MC <= 2 ? 2 : 1)
                     for (; cc < stop; ++cc) {
                         double cached[MC];
@@ -2524,6 +2525,71 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
 inline size_t yg_sweep_smem(int L, int T, int nwarp, int TC) {
     const size_t scratchD = (size_t)2 * L + (L + 1) / 2 + 2;
     return yg_fixed_bytes(L, T) + std::max(sizeof(double) * nwarp * scratchD, yg_unit_bytes(L, TC));
+}
+
+// Scan mode 1 of the celda_G sweep, the report: per draw of the last sweep, the distance m between its uniform and the
+// nearest boundary of its cumulative distribution (the sampler's descending order) against a bound b on how far the
+// skipped operations can move that boundary.  A skipped pair p <- fl(fl(p + a) - a) moves p by at most
+// 2^-53 (|p + a| + |p|); along a chain |p| stays below N_g log(ntot + beta + 1) (N_g the gene's total count: every term
+// lgamma(t + x + beta) - lgamma(t + beta) is at most x log(t + x + beta)), |a| below amax = max |lgt|; nM pairs at most;
+// a change of d in every log-probability moves a boundary by less than 2 d: b = 4 nM 2^-53 (2 N_g log(..) + amax).
+// out[0]: min over the draws of m / b (bits of a non-negative double, atomicMin), out[1]: draws with m <= b (a count).
+// One warp per gene; plain exp / sums (a report, not part of the chain's arithmetic).
+__global__ void k_yg_margin(int nG, int L, long long nM, const double* __restrict__ probs, const int* __restrict__ y,
+                            const int* __restrict__ ix, const double* __restrict__ u, const long long* __restrict__ nByG,
+                            double logTot, const unsigned long long* __restrict__ amaxBits, unsigned long long* __restrict__ out) {
+    const int lane = threadIdx.x & 31, gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const double amax = __longlong_as_double((long long)*amaxBits);
+    for (int t = gw; t < nG; t += nw) {
+        const int i = ix[t] - 1, sel = y[i] - 1;
+        const double* p = probs + (size_t)i * L;
+        double mx = -1e308;
+        for (int l = lane; l < L; l += 32) mx = fmax(mx, p[l]);
+        for (int o = 16; o; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        double s = 0.0;
+        for (int l = lane; l < L; l += 32) s += exp(p[l] - mx);
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const double qsel = exp(p[sel] - mx) / s;
+        double lower = 0.0;
+        int ties = 0, likely = 0, above = 0;
+        for (int l = lane; l < L; l += 32) {
+            const double q = exp(p[l] - mx) / s;
+            if (q > qsel) {
+                lower += q;
+                ++above;
+            }
+            ties += (l != sel && q == qsel);
+            likely += ((double)L * q > 0.1);
+        }
+        for (int o = 16; o; o >>= 1) {
+            lower += __shfl_xor_sync(0xffffffffu, lower, o);
+            ties += __shfl_xor_sync(0xffffffffu, ties, o);
+            likely += __shfl_xor_sync(0xffffffffu, likely, o);
+            above += __shfl_xor_sync(0xffffffffu, above, o);
+        }
+        if (lane == 0) {
+            const double uu = u[t];
+            double m;
+            if (ties || likely > 200 || !(s > 0.0)) m = 0.0;  // exact ties and the Walker alias branch are not analysed
+            else {
+                const double up = lower + qsel - uu, dn = uu - lower;
+                // the first sorted position has no boundary below it, the last one (everything else above it) none above
+                m = (above == 0) ? up : ((above == L - 1) ? dn : fmin(up, dn));
+                m = fmax(m, 0.0);
+            }
+            const double b = 4.0 * (double)nM * 1.1102230246251565e-16 * (2.0 * (double)nByG[i] * logTot + amax);
+            atomicMin(out, (unsigned long long)__double_as_longlong(m / b));
+            if (!(m > b)) atomicAdd(out + 1, 1ull);
+        }
+    }
+}
+
+// max |v| over an array of doubles (bits, atomicMax)
+__global__ void k_max_abs(const double* __restrict__ v, long long n, unsigned long long* __restrict__ out) {
+    double m = 0.0;
+    for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < n; q += (long long)gridDim.x * blockDim.x) m = fmax(m, fabs(v[q]));
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
 }
 
 // lgt = lgamma(t + beta) for the whole L x nM table (at set_state; the sweep keeps it current afterwards)

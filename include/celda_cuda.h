@@ -197,6 +197,19 @@ int celda_comm_create(celda_comm **out, const char *id128, int nranks, int rank,
 void celda_comm_destroy(celda_comm *c);
 int celda_chain_attach_comm(celda_chain *h, celda_comm *comm);
 
+/* celda_G y sweep (celda_chain_sweep_y / iterate on a celda_G handle): how a gene's row is scanned.
+ * mode 0 (default): every cell, exactly like cG_CalcGibbsProbY (src/cG_calcGibbsProbY.cpp:212-225), which adds and
+ *   subtracts the same table entry for the cells where the gene has no count -- bit-identical probabilities.
+ * mode 1 (opt-in): only the cells where the gene has a count.  The skipped pairs change a log-probability by a few
+ *   units of rounding at most, so the draws agree with mode 0 unless a uniform falls within that distance of a
+ *   boundary of its cumulative distribution.  celda_chain_scan_margin reports, for the last sweep: per draw, the
+ *   distance m between its uniform and the nearest boundary and a bound b on how far the skipped operations can move
+ *   that boundary (b = 4 nM 2^-53 (2 N_g log(total count) + max |lgamma table entry|), N_g the gene's total count);
+ *   margin[0] = the smallest m / b over the sweep's draws (0 for a draw on the Walker alias branch or with an exact
+ *   tie), margin[1] = the number of draws with m <= b.  margin[1] == 0 proves that every label of the sweep is the one
+ *   the exact scan draws; the bound is a worst case (it grows with nM), so large matrices leave draws unproven. */
+int celda_chain_set_scan_mode(celda_chain *h, int mode);
+int celda_chain_scan_margin(celda_chain *h, double *margin /* [2] */);
 /* CUDA-event timing on the chain's stream (bench.py): start, then stop returns elapsed ms. */
 int celda_chain_timer_start(celda_chain *h);
 int celda_chain_timer_stop(celda_chain *h, float *ms);

@@ -84,3 +84,56 @@ def test_celda_G_sweep_sparse_midsize_two_chunks(oracle):
     _, y2 = ch.get_state()
     assert np.array_equal(y2, y)
     ch.close()
+
+
+def test_celda_G_scan_mode_count_columns_only():
+    """Opt-in scan mode 1 (celda_chain_set_scan_mode): the columns where a gene has no count are skipped.  The
+    probabilities differ from the exact scan by rounding only, and whenever the reported margin exceeds the reported
+    bound the labels are those of the exact scan."""
+    rng = np.random.default_rng(21)
+    G, C, L = 200, 1500, 40
+    y_true = rng.integers(1, L + 1, G)
+    y_true[:L] = np.arange(1, L + 1)
+    counts = np.zeros((G, C), dtype=np.int32)
+    for c in range(C):
+        mod = rng.multinomial(rng.integers(40, 160), rng.dirichlet(np.ones(L) * 0.3))
+        for l in np.flatnonzero(mod):
+            idx = np.flatnonzero(y_true == l + 1)
+            counts[idx, c] += rng.multinomial(mod[l], np.ones(idx.size) / idx.size).astype(np.int32)
+    counts[counts.sum(1) == 0, 0] = 1
+    counts[0, counts.sum(0) == 0] = 1
+    y = y_true.astype(np.int32).copy()
+    flip = rng.random(G) < 0.3
+    y[flip] = rng.integers(1, L + 1, int(flip.sum()))
+    A = cb.CSC.from_dense(counts)
+    exact, fast = cb.Chain(A, None, L=L, model=cb.MODEL_G), cb.Chain(A, None, L=L, model=cb.MODEL_G)
+    exact.set_state(y=y)
+    fast.set_state(y=y)
+    fast.set_scan_mode(1)
+    with pytest.raises(cb.CeldaCudaError):
+        fast.scan_margin()  # no sweep yet
+    for it in range(3):
+        ix, u = rng.permutation(G).astype(np.int32) + 1, rng.random(G)
+        le, lf = exact.iterate(ix, u, None, None), fast.iterate(ix, u, None, None)
+        ratio, unproven = fast.scan_margin()
+        assert ratio >= 0.0 and unproven >= 0
+        pe, pf = exact.probs()[1], fast.probs()[1]
+        assert np.max(np.abs(pe - pf)) <= 1e-9  # the skipped pairs move a log-probability by rounding only
+        if unproven == 0:
+            assert ratio > 1.0
+            assert np.array_equal(exact.get_state()[1], fast.get_state()[1])
+            assert abs(le - lf) <= 1e-12 * abs(le)
+        else:  # a draw too close to call: continue both chains from the exact labels
+            fast.set_state(y=exact.get_state()[1])
+    assert unproven == 0  # on this problem the margins are orders of magnitude above the bounds
+    fast.set_scan_mode(0)   # back to the exact scan: bit-identical again
+    ix, u = rng.permutation(G).astype(np.int32) + 1, rng.random(G)
+    exact.iterate(ix, u, None, None)
+    fast.iterate(ix, u, None, None)
+    assert np.array_equal(exact.probs()[1], fast.probs()[1])
+    cg = cb.Chain(A, np.ones(C, np.int32), K=2, L=L)
+    with pytest.raises(cb.CeldaCudaError):
+        cg.set_scan_mode(1)  # only the celda_G sweep scans raw counts
+    cg.close()
+    exact.close()
+    fast.close()
