@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--no-legs", action="store_true", help="skip the em_sharded / grid_search legs under torchrun")
     ap.add_argument("--em-cells", type=int, default=1000000)
     ap.add_argument("--grid-cells", type=int, default=50000)
+    ap.add_argument("--g-cells", type=int, default=500000, help="cells of the configs[3] celda_G leg (N = 1 only)")
     ap.add_argument("--grid-iters", type=int, default=8)
     return ap.parse_args()
 
@@ -423,6 +424,36 @@ def leg_grid_search(cb, a, rank, world, local, dist, torch):
                     "scaling run reports it as wall_s); log-likelihoods are independent of N (checksum)"}
 
 
+def leg_celda_g(cb, a, device, sm_mhz):
+    """configs[3]: celda_G module-only y sweep on the raw counts, 20k genes x 500k cells, L = 200 (one GPU: a Gibbs chain
+    does not shard).  Two sweeps from the generator's labels, exact full-column scan; the roofline is the sweep's own
+    bound, shared-memory wavefronts (one 8-byte read of the cached lgamma per two dependent adds)."""
+    from bench_support import simulate_cells_cg
+    d = simulate_cells_cg(12345, 10, a.g_cells // 10, a.genes, 50, 200, (500, 3000))
+    counts = cb.CSC(d["nG"], d["nM"], d["p"], d["i"], d["x"])
+    L = 200
+    ch = cb.Chain(counts, None, L=L, model=cb.MODEL_G, device=device)
+    ch.set_state(y=d["y"].copy())
+    ch.seed(12345)
+    ch.profile(True)
+    ch.timer_start()
+    lls = [ch.iterate(None, None, None, None) for _ in range(2)]
+    ms = ch.timer_stop() / 2
+    pr = ch.profile_get()["sweep_y"]
+    ch.close()
+    nchunk = (L + 31) // 32
+    wavefronts = 2.0 * nchunk * d["nG"] * d["nM"]          # one 256-byte warp read per (gene, 32-module chunk, cell)
+    peak = 148 * (sm_mhz or 1965.0) * 1e6                   # one wavefront per clock and SM
+    return {"workload": "configs[3]: celda_G y sweep, %d genes x %d cells, L=%d, nnz=%d, Philox draws, exact full-column scan"
+                        % (d["nG"], d["nM"], L, int(d["x"].size)),
+            "ms_per_sweep": ms, "iter_per_s": 1e3 / ms, "movers_per_sweep": pr["movers"] / 2, "rounds_per_sweep": pr["rounds"] / 2,
+            "dependent_adds_per_s": 2.0 * d["nG"] * d["nM"] * L / (ms * 1e-3),
+            "roofline": {"bound": "shared", "achieved": wavefronts / (ms * 1e-3) / 1e9, "peak": peak / 1e9, "unit": "Gwavefront/s",
+                         "frac": wavefronts / (ms * 1e-3) / peak,
+                         "note": "algorithmic wavefronts of the count-free columns only; a mover adds a pass over all cells"},
+            "logLik_last": lls[-1]}
+
+
 def main():
     a = parse()
     if a.impl == "reference":
@@ -531,6 +562,8 @@ def main():
         gs = leg_grid_search(cb, a, rank, world, local, dist, torch)
         if rank == 0:
             out["em_sharded"], out["grid_search"] = em, gs
+        if world == 1:
+            out["celda_g"] = leg_celda_g(cb, a, local, (out.get("clocks") or {}).get("sm_mhz"))
     if rank == 0:
         print(json.dumps(out))
     if dist is not None:

@@ -247,6 +247,50 @@ SEXP _celda_cuda_chain_perplexity(SEXP p) {
     return Rf_ScalarReal(v);
 }
 
+/* celdaGridSearch (R/celdaGridSearch.R:290-391): the next (K, L) run on the same resident counts */
+SEXP _celda_cuda_chain_reconfigure(SEXP p, SEXP K, SEXP L) {
+    CHECK(celda_chain_reconfigure((celda_chain *)R_ExternalPtrAddr(p), Rf_asInteger(K), Rf_asInteger(L)));
+    return R_NilValue;
+}
+
+/* split heuristics (R/split_clusters.R): log-likelihood of alternative labels, chain state untouched; NULL keeps a side */
+SEXP _celda_cuda_chain_loglik_alt(SEXP p, SEXP z, SEXP y) {
+    double ll = 0;
+    CHECK(celda_chain_loglik_alt((celda_chain *)R_ExternalPtrAddr(p), Rf_isNull(z) ? NULL : INTEGER(z),
+                                 Rf_isNull(y) ? NULL : INTEGER(y), &ll));
+    return Rf_ScalarReal(ll);
+}
+
+/* perplexity(x, newCounts = ...) (R/perplexity.R:233-325): newCounts as a dgCMatrix */
+SEXP _celda_cuda_chain_perplexity_new(SEXP p, SEXP counts) {
+    double v = 0;
+    CHECK(celda_chain_perplexity_new((celda_chain *)R_ExternalPtrAddr(p), INTEGER(slot(counts, "p")),
+                                     INTEGER(slot(counts, "i")), REAL(slot(counts, "x")), &v));
+    return Rf_ScalarReal(v);
+}
+
+/* resamplePerplexity(doResampling = TRUE) (R/perplexity.R:449-498, 764-775): numResample perplexities */
+SEXP _celda_cuda_chain_perplexity_resampled(SEXP p, SEXP seed, SEXP n) {
+    int k = Rf_asInteger(n);
+    SEXP ans = PROTECT(Rf_allocVector(REALSXP, k));
+    CHECK(celda_chain_perplexity_resampled((celda_chain *)R_ExternalPtrAddr(p), (unsigned long long)Rf_asReal(seed), k, REAL(ans)));
+    UNPROTECT(1);
+    return ans;
+}
+
+/* celda_G: opt-in scan of the count columns only, and its per-sweep report (include/celda_cuda.h) */
+SEXP _celda_cuda_chain_set_scan_mode(SEXP p, SEXP mode) {
+    CHECK(celda_chain_set_scan_mode((celda_chain *)R_ExternalPtrAddr(p), Rf_asInteger(mode)));
+    return R_NilValue;
+}
+
+SEXP _celda_cuda_chain_scan_margin(SEXP p) {
+    SEXP ans = PROTECT(Rf_allocVector(REALSXP, 2));
+    CHECK(celda_chain_scan_margin((celda_chain *)R_ExternalPtrAddr(p), REAL(ans)));
+    UNPROTECT(1);
+    return ans;
+}
+
 static const R_CallMethodDef CudaEntries[] = {
     {"_celda_cuda_colSumByGroupSparse", (DL_FUNC)&_celda_cuda_colSumByGroupSparse, 3},
     {"_celda_cuda_rowSumByGroupSparse", (DL_FUNC)&_celda_cuda_rowSumByGroupSparse, 3},
@@ -274,6 +318,12 @@ static const R_CallMethodDef CudaEntries[] = {
     {"_celda_cuda_chain_get_state", (DL_FUNC)&_celda_cuda_chain_get_state, 3},
     {"_celda_cuda_chain_loglik", (DL_FUNC)&_celda_cuda_chain_loglik, 1},
     {"_celda_cuda_chain_perplexity", (DL_FUNC)&_celda_cuda_chain_perplexity, 1},
+    {"_celda_cuda_chain_reconfigure", (DL_FUNC)&_celda_cuda_chain_reconfigure, 3},
+    {"_celda_cuda_chain_loglik_alt", (DL_FUNC)&_celda_cuda_chain_loglik_alt, 3},
+    {"_celda_cuda_chain_perplexity_new", (DL_FUNC)&_celda_cuda_chain_perplexity_new, 2},
+    {"_celda_cuda_chain_perplexity_resampled", (DL_FUNC)&_celda_cuda_chain_perplexity_resampled, 3},
+    {"_celda_cuda_chain_set_scan_mode", (DL_FUNC)&_celda_cuda_chain_set_scan_mode, 2},
+    {"_celda_cuda_chain_scan_margin", (DL_FUNC)&_celda_cuda_chain_scan_margin, 1},
     {NULL, NULL, 0}};
 
 /* called from R_init_celda (src/RcppExports.cpp:339-342) next to the Rcpp-generated table */
