@@ -1993,7 +1993,8 @@ struct YGArgs {
     int doSample;
     double* probs;         // L x nG or null
     int noTma;             // measurement aid (CELDA_CUDA_YG_NOTMA): stage the tiles with plain loads
-    int flags;             // policy switches (CELDA_CUDA_YG_FLAGS): 1 wave-sized top-ups, 2 wide patch tiles; 32 = scan mode 1
+    int flags;             // policy switches (CELDA_CUDA_YG_FLAGS): 1 wave-sized top-ups, 2 wide patch tiles, 16 poll the tile
+                           // barrier with test_wait; 32 = scan mode 1 (set by the library)
     int TC;                // columns per tile (a multiple of 4; set by the launcher from the shared-memory budget)
     SweepWork w;
 };
@@ -2002,9 +2003,8 @@ struct YGArgs {
 __device__ __noinline__ double dlgamma_hot_call(double x) { return dlgamma_hot(x); }
 
 constexpr int YG_THREADS = 512;   // 16 genes per task; 128 registers per thread for up to 8 chains with their operands in flight
-constexpr int YG_NBUF = 3;        // tile buffers in flight
+constexpr int YG_NBUF = 3;        // tile buffers in flight (two buffers with 1.5x wider tiles measure the same)
 constexpr int YG_MAXMC = 7;       // 32-module chunks per task (chains per lane); 8 would spill at 128 registers
-constexpr int YG_NGP = 4;         // most genes per warp in a patch task
 
 __host__ __device__ inline int yg_group_modules(int L) { return L < 32 * YG_MAXMC ? L : 32 * YG_MAXMC; }
 // bytes of the tile ring: TC columns x (modules of a group) x (8 + 4) bytes per buffer
@@ -2165,22 +2165,19 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
         }
         grid_sync(a.w.barrier, bar_target);  // the order, and after a commit table rows a, b, are visible before they are read
         CELDA_TICKR(ck_commit);
-        // ---- tasks: patch = (carried genes) x {da, db}; fresh = (new genes) x (module group).  A patch warp takes
-        // YG_NGP genes (two chains each -- the round is bound by the latency of one chain, more genes per warp are free), a
-        // fresh warp one gene (up to 8 chains).  Warp slot s of a part with n genes in S slots gets the genes s, s + S, ...
-        // of the density order: dense genes are spread over the warps.
+        // ---- tasks: patch = (nwarp carried genes) x {da, db}; fresh = (nwarp new genes) x (module group); one gene per
+        // warp, warp slot s of a part <-> gene s of the part's density order
         const long long nP = (nd == 2) ? hi - pos : 0, nF = end - hi;
-        int ngP = 1;  // the fewest genes per warp that fit the carried genes into one grid-wide wave of patch tasks
-        while (false && ngP < YG_NGP && (nP + (long long)nwarp * ngP - 1) / ((long long)nwarp * ngP) > (long long)gridDim.x) ngP *= 2;
-        const long long slotsP = (nP + ngP - 1) / ngP, slotsF = nF;
+        const long long slotsP = nP, slotsF = nF;
         const long long nPatchGrp = (slotsP + nwarp - 1) / nwarp;
         const long long nFreshGrp = (slotsF + nwarp - 1) / nwarp;
         const long long ntask = nPatchGrp + nFreshGrp * ngroup;
         ++rounds;
-        // One task with MC chains per lane and gene, NG genes per warp.
-        auto run_task = [&](auto mc_tag, auto ng_tag, long long task) {
+        // One task with MC chains per lane.  (NG: genes per warp.  Two genes per warp -- a dense one paired with a sparse
+        // one -- were measured and are slower: 128 registers do not hold 14 chains and their operands)
+        auto run_task = [&](auto mc_tag, long long task) {
             constexpr int MC = decltype(mc_tag)::value;
-            constexpr int NG = decltype(ng_tag)::value;
+            constexpr int NG = 1;
             const bool patch = task < nPatchGrp;
             // a patch tile holds two entries per column, so it spans many more columns in the same buffer: the chain of a
             // patch unit is short per column and a tile has to outlast the latency of its refill
@@ -2262,7 +2259,8 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                 int* di = ttile + (size_t)b * TC * GM;
                 const unsigned bytes8 = (unsigned)tc * (unsigned)L * 8u, bytes4 = (unsigned)tc * (unsigned)L * 4u;
                 if (useTma && (bytes4 & 15u) == 0) {
-                    // the tile's columns are one contiguous slab of each array: two bulk copies
+                    // the tile's columns are one contiguous slab of each array: two bulk copies (one pair of copies per
+                    // column issued by as many lanes measured 10 % slower)
                     if (lane == 0) {
                         mbar_arrive_expect_tx(fullb + b, bytes8 + bytes4);
                         fence_proxy_async();  // rows written by the commit phase (generic proxy) are read by the copy engine
@@ -2441,11 +2439,10 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
             const int mc = task < nPatchGrp ? 0 : (min(GM, L - q * GM) + 31) / 32;
             using one = std::integral_constant<int, 1>;
             // chains per lane: 1, 2, 4 or 7 (a group's chunk count rounded up; idle chains cost adds, no results)
-            if (mc == 0) run_task(one{}, one{}, task);
-            else if (mc == 1) run_task(one{}, one{}, task);
-            else if (mc == 2) run_task(std::integral_constant<int, 2>{}, one{}, task);
-            else if (mc <= 4) run_task(std::integral_constant<int, 4>{}, one{}, task);
-            else run_task(std::integral_constant<int, 7>{}, one{}, task);
+            if (mc <= 1) run_task(one{}, task);  // mc == 0: a patch task
+            else if (mc == 2) run_task(std::integral_constant<int, 2>{}, task);
+            else if (mc <= 4) run_task(std::integral_constant<int, 4>{}, task);
+            else run_task(std::integral_constant<int, 7>{}, task);
         }
         units_done += ntask;
         CELDA_TICKR(ck_units);
