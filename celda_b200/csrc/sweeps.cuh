@@ -2168,16 +2168,19 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
         // ---- tasks: patch = (nwarp carried genes) x {da, db}; fresh = (nwarp new genes) x (module group); one gene per
         // warp, warp slot s of a part <-> gene s of the part's density order
         const long long nP = (nd == 2) ? hi - pos : 0, nF = end - hi;
-        const long long slotsP = nP, slotsF = nF;
+        // (a second gene per patch warp, to save the second wave of patch tasks at c4, measured 17 % slower)
+        const int ngP = 1;
+        const long long slotsP = (nP + ngP - 1) / ngP, slotsF = nF;
         const long long nPatchGrp = (slotsP + nwarp - 1) / nwarp;
         const long long nFreshGrp = (slotsF + nwarp - 1) / nwarp;
         const long long ntask = nPatchGrp + nFreshGrp * ngroup;
         ++rounds;
-        // One task with MC chains per lane.  (NG: genes per warp.  Two genes per warp -- a dense one paired with a sparse
-        // one -- were measured and are slower: 128 registers do not hold 14 chains and their operands)
-        auto run_task = [&](auto mc_tag, long long task) {
+        // One task with MC chains per lane and gene, NG genes per warp.  (Two genes per warp in FRESH tasks -- a dense one
+        // paired with a sparse one -- were measured and are slower: 128 registers do not hold 14 chains and their
+        // operands)
+        auto run_task = [&](auto mc_tag, auto ng_tag, long long task) {
             constexpr int MC = decltype(mc_tag)::value;
-            constexpr int NG = 1;
+            constexpr int NG = decltype(ng_tag)::value;
             const bool patch = task < nPatchGrp;
             // a patch tile holds two entries per column, so it spans many more columns in the same buffer: the chain of a
             // patch unit is short per column and a tile has to outlast the latency of its refill
@@ -2439,10 +2442,10 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
             const int mc = task < nPatchGrp ? 0 : (min(GM, L - q * GM) + 31) / 32;
             using one = std::integral_constant<int, 1>;
             // chains per lane: 1, 2, 4 or 7 (a group's chunk count rounded up; idle chains cost adds, no results)
-            if (mc <= 1) run_task(one{}, task);  // mc == 0: a patch task
-            else if (mc == 2) run_task(std::integral_constant<int, 2>{}, task);
-            else if (mc <= 4) run_task(std::integral_constant<int, 4>{}, task);
-            else run_task(std::integral_constant<int, 7>{}, task);
+            if (mc <= 1) run_task(one{}, one{}, task);  // mc == 0: a patch task
+            else if (mc == 2) run_task(std::integral_constant<int, 2>{}, one{}, task);
+            else if (mc <= 4) run_task(std::integral_constant<int, 4>{}, one{}, task);
+            else run_task(std::integral_constant<int, 7>{}, one{}, task);
         }
         units_done += ntask;
         CELDA_TICKR(ck_units);
