@@ -1346,6 +1346,11 @@ __device__ __forceinline__ void mbar_wait_poll(unsigned long long* bar, unsigned
             : "memory");
     }
 }
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
 __device__ __forceinline__ int lds_s32(unsigned addr) {
     int v;
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");

@@ -2181,6 +2181,7 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
         auto run_task = [&](auto mc_tag, auto ng_tag, long long task) {
             constexpr int MC = decltype(mc_tag)::value;
             constexpr int NG = decltype(ng_tag)::value;
+            static_assert(NG == 1, "the column loop is written for one gene per warp");
             const bool patch = task < nPatchGrp;
             // a patch tile holds two entries per column, so it spans many more columns in the same buffer: the chain of a
             // patch unit is short per column and a tile has to outlast the latency of its refill
@@ -2232,6 +2233,19 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                     if (l >= 0 && l == cur[g]) curMask[g] |= 1u << m;
             }
             const int laneOff = patch ? min(lane, 1) : lane;  // this lane's entry within a tile row (+ 32 m)
+            // where the gene's current module sits among this task's chains: chunk mstar (warp-uniform), lane lstar
+            int mstar = -1, lstar = -1;
+            if (patch) {
+                if (cur[0] == da || cur[0] == db) {
+                    mstar = 0;
+                    lstar = (cur[0] == da) ? 0 : 1;
+                }
+            } else if (cur[0] >= l0 && cur[0] < l0 + gm) {
+                mstar = (cur[0] - l0) >> 5;
+                lstar = (cur[0] - l0) & 31;
+            }
+            const unsigned lgA = opaque_u32(smem_addr(lgtab));
+            const unsigned tileA = opaque_u32(smem_addr(tile + laneOff)), ttileA = opaque_u32(smem_addr(ttile + laneOff));
             const bool useTma = !patch && !a.noTma && gm == L;
             // cursors over the genes' twin rows: lane k holds entry wbase + k, the following window already in flight
             const int NONE = 0x7fffffff;
@@ -2333,7 +2347,7 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                 else mbar_wait(fullb + b, (phaseBits >> b) & 1u);
                 phaseBits ^= 1u << b;
                 const double* tl = tile + (size_t)b * TC * GM + laneOff;
-                const int* tt = ttile + (size_t)b * TC * GM + laneOff;
+                const unsigned tlA = tileA + (unsigned)b * (unsigned)(TC * GM) * 8u, ttA = ttileA + (unsigned)b * (unsigned)(TC * GM) * 4u;
                 int cc = validMask ? 0 : tc;  // a warp without a gene only keeps the buffer hand-over going
                 while (cc < tc) {
                     // columns where neither gene has a count: (p + cached) - cached, a tight loop over the chains
@@ -2359,44 +2373,52 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                             for (int m = 0; m < MC; ++m) p[g][m] -= cached[m];
                         }
                     }
-                    if (cc < tc) {  // a column where a gene of the warp has a count: a fresh lgamma against the cached one
-                        double cached[MC];
+                    if (cc < tc) {  // a column where the gene has a count: a fresh lgamma against the cached one
+                        // Shared-memory loads on 32-bit register addresses with immediate offsets (the compiler otherwise
+                        // re-derives the tile and table bases for every chain: 350 instructions per such column, ncu).
+                        const unsigned rowA = opaque_u32(tlA + (unsigned)(cc * stride) * 8u),
+                                       rowT = opaque_u32(ttA + (unsigned)(cc * stride) * 4u);
+                        const int xv = nextx[0], xneg = -xv;
+                        double cached[MC], fresh[MC];
+                        int arg[MC];
+                        unsigned over = 0;  // some chain's argument lies beyond the shared-memory table (rare)
 #pragma unroll
-                        for (int m = 0; m < MC; ++m) cached[m] = tl[cc * stride + 32 * m];
+                        for (int m = 0; m < MC; ++m) cached[m] = lds_f64(rowA + 256u * m);
 #pragma unroll
-                        for (int g = 0; g < NG; ++g) {
-                            if ((long long)nextcol[g] - c0 == cc) {  // warp-uniform
-                                const int xv = nextx[g];
-                                double fresh[MC];
+                        for (int m = 0; m < MC; ++m) {
+                            // only one chain of one lane is the gene's current module (curMask; counts removed: - x)
+                            arg[m] = lds_s32(rowT + 128u * m) + (((curMask[0] >> m) & 1u) ? xneg : xv);
+                            if (!((actMask >> m) & 1u)) arg[m] = 0;
+                            over |= (unsigned)(arg[m] >= T);
+                        }
+                        if (!__any_sync(FULL, over)) {
 #pragma unroll
-                                for (int m = 0; m < MC; ++m) {
-                                    const bool act = (actMask >> m) & 1u, ic = (curMask[g] >> m) & 1u;
-                                    const int arg = act ? tt[cc * stride + 32 * m] + (ic ? -xv : xv) : 0;
-                                    fresh[m] = (arg < T) ? lgtab[arg] : dlgamma_hot_call((double)arg + a.beta);
-                                }
-                                if (++widx[g] == 32) {  // window used up: the one in flight takes over, the next is requested
-                                    wbase[g] += 32;
-                                    widx[g] = 0;
-                                    wc[g] = wc2[g];
-                                    wx[g] = wx2[g];
-                                    const int e1 = wbase[g] + 32 + lane;
-                                    wc2[g] = (e1 < nEnt[g]) ? __ldg(a.tcol + rb[g] + e1) : NONE;
-                                    wx2[g] = (e1 < nEnt[g]) ? __ldg(a.tx + rb[g] + e1) : 0;
-                                }
-                                nextcol[g] = __shfl_sync(FULL, wc[g], widx[g]);
-                                nextx[g] = __shfl_sync(FULL, wx[g], widx[g]);
+                            for (int m = 0; m < MC; ++m) fresh[m] = lds_f64(lgA + (unsigned)arg[m] * 8u);
+                        } else {
 #pragma unroll
-                                for (int m = 0; m < MC; ++m) {
-                                    const bool ic = (curMask[g] >> m) & 1u;
-                                    p[g][m] += ic ? cached[m] : fresh[m];
-                                    p[g][m] -= ic ? fresh[m] : cached[m];
-                                }
+                            for (int m = 0; m < MC; ++m)
+                                fresh[m] = (arg[m] < T) ? lgtab[arg[m]] : dlgamma_hot_call((double)arg[m] + a.beta);
+                        }
+                        if (++widx[0] == 32) {  // window used up: the one in flight takes over, the next is requested
+                            wbase[0] += 32;
+                            widx[0] = 0;
+                            wc[0] = wc2[0];
+                            wx[0] = wx2[0];
+                            const int e1 = wbase[0] + 32 + lane;
+                            wc2[0] = (e1 < nEnt[0]) ? __ldg(a.tcol + rb[0] + e1) : NONE;
+                            wx2[0] = (e1 < nEnt[0]) ? __ldg(a.tx + rb[0] + e1) : 0;
+                        }
+                        nextcol[0] = __shfl_sync(FULL, wc[0], widx[0]);
+                        nextx[0] = __shfl_sync(FULL, wx[0], widx[0]);
+#pragma unroll
+                        for (int m = 0; m < MC; ++m) {
+                            if (m == mstar) {  // warp-uniform: the chunk that holds the current module
+                                const bool ic = lane == lstar;
+                                p[0][m] += ic ? cached[m] : fresh[m];
+                                p[0][m] -= ic ? fresh[m] : cached[m];
                             } else {
-#pragma unroll
-                                for (int m = 0; m < MC; ++m) {
-                                    p[g][m] += cached[m];
-                                    p[g][m] -= cached[m];
-                                }
+                                p[0][m] += fresh[m];
+                                p[0][m] -= cached[m];
                             }
                         }
                         ++cc;
