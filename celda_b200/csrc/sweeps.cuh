@@ -2815,7 +2815,11 @@ __global__ void __launch_bounds__(1024, 1) k_sweep_zc(ZCArgs a) {
 #pragma unroll 4
                         for (; rr < stop; ++rr) S += tile[rr * 32 + lane];
                         if (rr < tc) {
-                            S += lg_tab(lgtab, T, (long long)ntile[rr * 32 + lane] + sgn * nextx, a.beta);
+                            // one warp vote for the rare argument beyond the shared-memory table instead of a divergent
+                            // inlined lgamma per lane (see k_sweep_yg)
+                            const int karg = ntile[rr * 32 + lane] + sgn * nextx;
+                            if (!__any_sync(0xffffffffu, karg >= T)) S += lgtab[karg];
+                            else S += (karg < T) ? lgtab[karg] : dlgamma_hot_call((double)karg + a.beta);
                             if (++widx == 32) {
                                 wbase += 32;
                                 widx = 0;
