@@ -91,7 +91,7 @@ struct SweepBufs {
         CELDA_TRY(lgnCP.alloc((size_t)ncand + 4 * MCMAX));
         CELDA_TRY(status.alloc(2));  // [0] sampler status of the sweeps, [1] visiting order is not a permutation
         CELDA_TRY(status.zero(st));
-        CELDA_TRY(barrier.alloc(1));
+        CELDA_TRY(barrier.alloc(4));  // [0] grid barrier, [1] task counter of the celda_G sweep
         CELDA_TRY(stats.alloc(40));
         CELDA_TRY(stats.zero(st));
         return 0;
@@ -547,7 +547,7 @@ int run_sweep_yg(YGArgs a, SweepBufs& b, int sms, int which, cudaStream_t st) {
     a.w = SweepWork{b.bufP.p, b.bufA.p, b.spec.p, b.drawMx.p, b.drawNz.p, b.colsum.p, b.lgnCP.p, b.barrier.p, b.status.p,
                     b.stats.p + 8 * which, b.Wmax, (int)full, (int)unit, std::max(b.Wmin, nwarp), b.lgT, 1};
     CELDA_CUDA_OK(cudaFuncSetAttribute(k_sweep_yg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CELDA_CUDA_OK(cudaMemsetAsync(b.barrier.p, 0, sizeof(unsigned), st));
+    CELDA_CUDA_OK(cudaMemsetAsync(b.barrier.p, 0, 4 * sizeof(unsigned), st));
     void* args[] = {&a};
     CELDA_CUDA_OK(cudaLaunchCooperativeKernel((void*)k_sweep_yg, dim3(sms), dim3(threads), args, smem, st));
     count_launch();

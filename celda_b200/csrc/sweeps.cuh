@@ -2163,6 +2163,7 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                 }
             }
         }
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.w.barrier[1] = 0;  // this round's task counter
         grid_sync(a.w.barrier, bar_target);  // the order, and after a commit table rows a, b, are visible before they are read
         CELDA_TICKR(ck_commit);
         // ---- tasks: patch = (nwarp carried genes) x {da, db}; fresh = (nwarp new genes) x (module group); one gene per
@@ -2173,7 +2174,7 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
         const long long slotsP = (nP + ngP - 1) / ngP, slotsF = nF;
         const long long nPatchGrp = (slotsP + nwarp - 1) / nwarp;
         const long long nFreshGrp = (slotsF + nwarp - 1) / nwarp;
-        const long long ntask = nPatchGrp + nFreshGrp * ngroup;
+        const long long nFreshTasks = nFreshGrp * ngroup, ntask = nFreshTasks + nPatchGrp;
         ++rounds;
         // One task with MC chains per lane and gene, NG genes per warp.  (Two genes per warp in FRESH tasks -- a dense one
         // paired with a sparse one -- were measured and are slower: 128 registers do not hold 14 chains and their
@@ -2182,7 +2183,7 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
             constexpr int MC = decltype(mc_tag)::value;
             constexpr int NG = decltype(ng_tag)::value;
             static_assert(NG == 1, "the column loop is written for one gene per warp");
-            const bool patch = task < nPatchGrp;
+            const bool patch = task >= nFreshTasks;  // fresh tasks (up to 7 chains) are handed out before patch tasks (one chain)
             // a patch tile holds two entries per column, so it spans many more columns in the same buffer: the chain of a
             // patch unit is short per column and a tile has to outlast the latency of its refill
             const int TCt = patch ? TCp : TC;
@@ -2191,13 +2192,13 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
             long long slot, nPart, nSlots, lo;
             const int* perm;
             if (patch) {
-                slot = task * nwarp + warp;
+                slot = (task - nFreshTasks) * nwarp + warp;
                 nPart = nP;
                 nSlots = slotsP;
                 lo = pos;
                 perm = permP;
             } else {
-                const long long q = task - nPatchGrp;
+                const long long q = task;
                 slot = (q / ngroup) * nwarp + warp;
                 nPart = nF;
                 nSlots = slotsF;
@@ -2357,7 +2358,7 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                     const long long rel = (long long)nc - c0;
                     const int stop = rel < tc ? (int)rel : tc;
                     if (a.flags & 32) cc = stop;  // opt-in scan mode 1: the count-free columns are skipped (celda_chain_set_scan_mode)
-#pragma unroll(MC <= 2 ? 2 : 1)
+#pragma unroll 2
                     for (; cc < stop; ++cc) {
                         double cached[MC];
 #pragma unroll
@@ -2459,9 +2460,16 @@ __global__ void __launch_bounds__(YG_THREADS, 1) k_sweep_yg(YGArgs a) {
                 }
             }
         };
-        for (long long task = blockIdx.x; task < ntask; task += gridDim.x) {
-            const int q = (int)((task - nPatchGrp) % ngroup);
-            const int mc = task < nPatchGrp ? 0 : (min(GM, L - q * GM) + 31) / 32;
+        // Tasks are handed out through a counter, heaviest first (fresh before patch, densest genes first): a round lasts
+        // as long as its busiest CTA, and a fixed round-robin gave CTA 0 the heaviest task of every wave.
+        while (true) {
+            __syncthreads();
+            if (threadIdx.x == 0) s_misc[0] = (int)atomicAdd(a.w.barrier + 1, 1u);
+            __syncthreads();
+            const long long task = s_misc[0];
+            if (task >= ntask) break;
+            const int q = (int)(task % ngroup);
+            const int mc = task >= nFreshTasks ? 0 : (min(GM, L - q * GM) + 31) / 32;
             using one = std::integral_constant<int, 1>;
             // chains per lane: 1, 2, 4 or 7 (a group's chunk count rounded up; idle chains cost adds, no results)
             if (mc <= 1) run_task(one{}, one{}, task);  // mc == 0: a patch task
