@@ -1056,92 +1056,8 @@ __global__ void k_rowsum_change_twin(const int* __restrict__ list, const int* __
 namespace celda {
 
 // ---------------------------------------------------------------------------------------------- EM z step, tiled
-// Same arithmetic as k_em_probs<true> (stored entries of a column added in storage order, unfused), but phi is
-// streamed through shared memory in gene tiles and shared by the CTA's block of cells, so the G x K table is read
-// from L2 once per (CTA, cell block) instead of once per stored entry.  A warp owns EM_CPW cells (accumulators in
-// registers) and walks each cell's column with a cursor: rows are ascending, so the entries of a gene tile are a
-// contiguous run.
+// cells per warp of the tiled EM kernel (accumulators in registers, one cell after the other)
 constexpr int EM_CPW = 4;
-
-__global__ void __launch_bounds__(1024, 1)
-k_em_probs_tiled(int R, long long nM, int K, int GT, const int* __restrict__ p, const int* __restrict__ ri,
-                 const int* __restrict__ xv, const double* __restrict__ phi, const double* __restrict__ theta,
-                 const int* __restrict__ s, double* __restrict__ probs, int* __restrict__ znew) {
-    extern __shared__ __align__(16) unsigned char em_smem[];
-    double* tile = reinterpret_cast<double*>(em_smem);  // [GT][K]
-    const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long cpb = (long long)nwarp * EM_CPW;     // cells per block pass
-    const bool two = K > 32;                             // K <= 64 here: lane owns k = lane and lane + 32
-    for (long long blk = blockIdx.x; blk * cpb < nM; blk += gridDim.x) {
-        long long cell[EM_CPW];
-        int cur[EM_CPW], end[EM_CPW];
-        double acc0[EM_CPW], acc1[EM_CPW];
-#pragma unroll
-        for (int j = 0; j < EM_CPW; ++j) {
-            cell[j] = blk * cpb + (long long)warp * EM_CPW + j;
-            const bool ok = cell[j] < nM;
-            cur[j] = ok ? p[cell[j]] : 0;
-            end[j] = ok ? p[cell[j] + 1] : 0;
-            acc0[j] = 0.0;
-            acc1[j] = 0.0;
-        }
-        for (int g0 = 0; g0 < R; g0 += GT) {
-            const int g1 = min(R, g0 + GT);
-            __syncthreads();
-            for (long long q = threadIdx.x; q < (long long)(g1 - g0) * K; q += blockDim.x) tile[q] = phi[(size_t)g0 * K + q];
-            __syncthreads();
-#pragma unroll
-            for (int j = 0; j < EM_CPW; ++j) {
-                while (cur[j] < end[j]) {
-                    const int cnt = min(32, end[j] - cur[j]);
-                    const int myr = (lane < cnt) ? ri[cur[j] + lane] : 0x7fffffff;
-                    const double myx = (lane < cnt) ? (double)xv[cur[j] + lane] : 0.0;
-                    const int inTile = __popc(__ballot_sync(0xffffffffu, myr < g1));  // rows ascend: a prefix
-                    for (int u = 0; u < inTile; ++u) {
-                        const int r = __shfl_sync(0xffffffffu, myr, u) - g0;
-                        const double x = __shfl_sync(0xffffffffu, myx, u);
-                        const double* row = tile + (size_t)r * K;
-                        if (lane < K) acc0[j] += row[lane] * x;
-                        if (two && lane + 32 < K) acc1[j] += row[lane + 32] * x;
-                    }
-                    cur[j] += inTile;
-                    if (inTile < cnt || inTile == 0) break;  // the rest of the column belongs to later tiles
-                }
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < EM_CPW; ++j) {
-            if (cell[j] >= nM) continue;
-            const long long c = cell[j];
-            const double* th = theta + (size_t)(s[c] - 1) * K;
-            double bv = -__longlong_as_double(0x7ff0000000000000LL);
-            int bi = 0x7fffffff;
-            if (lane < K) {
-                const double v = acc0[j] + th[lane];
-                if (probs) probs[c * K + lane] = v;
-                bv = v;
-                bi = lane;
-            }
-            if (two && lane + 32 < K) {
-                const double v = acc1[j] + th[lane + 32];
-                if (probs) probs[c * K + lane + 32] = v;
-                if (v > bv) {
-                    bv = v;
-                    bi = lane + 32;
-                }
-            }
-            for (int o = 16; o; o >>= 1) {
-                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                if (ov > bv || (ov == bv && oi < bi)) {
-                    bv = ov;
-                    bi = oi;
-                }
-            }
-            if (znew && lane == 0) znew[c] = (bi == 0x7fffffff ? 0 : bi) + 1;
-        }
-    }
-}
 
 }  // namespace celda
 
@@ -1354,11 +1270,6 @@ __device__ __forceinline__ double lds_f64(unsigned addr) {
 __device__ __forceinline__ int lds_s32(unsigned addr) {
     int v;
     asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned lds_u8(unsigned addr) {
-    unsigned v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
     return v;
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
