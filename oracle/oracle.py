@@ -39,9 +39,10 @@ class OracleError(RuntimeError):
 
 
 class Oracle:
-    def __init__(self, long_double=False):
+    def __init__(self, long_double=False, lib_path=None):
+        """lib_path: another build of celda_oracle.c (the sanitizer build, oracle/Makefile target `asan`)."""
         build()
-        self.lib = C.CDLL(os.path.join(_HERE, "libcelda_oracle_ld.so" if long_double else "libcelda_oracle.so"))
+        self.lib = C.CDLL(lib_path or os.path.join(_HERE, "libcelda_oracle_ld.so" if long_double else "libcelda_oracle.so"))
         L = self.lib
         L.o_last_error.restype = C.c_char_p
         for n in ("o_log_vec", "o_exp_vec", "o_lgamma_vec"):
