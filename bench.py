@@ -420,6 +420,7 @@ def leg_grid_search(cb, a, rank, world, local, dist, torch):
             "runs": len(rp), "wall_s": wall, "sum_of_run_seconds": serial, "speedup_vs_serial": serial / wall,
             "runs_per_rank": per_rank, "chains_per_s": len(rp) / wall,
             "logLikelihood_checksum": float(np.sum([r["logLikelihood"] for r in rp])),
+            "failed_runs": int(sum(1 for r in rp if r.get("error"))),
             "note": "sum_of_run_seconds is what one GPU spends on the same runs one after the other (the N=1 line of the "
                     "scaling run reports it as wall_s); log-likelihoods are independent of N (checksum)"}
 

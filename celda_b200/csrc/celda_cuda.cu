@@ -8,6 +8,7 @@
 #include <cub/device/device_radix_sort.cuh>
 #include <dlfcn.h>
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX v3: ranges are no-ops unless a profiler injects itself
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -168,6 +169,10 @@ struct ProfScope {
     int which;
     cudaEvent_t a = nullptr, b = nullptr;
     ProfScope(celda_chain* h_, int w) : h(h_), which(w) {
+        static const char* const names[] = {"celda:sweep_y", "celda:rowSumByGroupChange", "celda:sweep_z",
+                                            "celda:colSumByGroupChange", "celda:logLik", "celda:rowSumByGroup",
+                                            "celda:colSumByGroup"};
+        nvtxRangePushA(names[w >= 0 && w < 7 ? w : 0]);  // the chain's phases as NVTX ranges (nsys / ncu --nvtx)
         if (h->profile) {
             cudaEventCreate(&a);
             cudaEventCreate(&b);
@@ -179,6 +184,7 @@ struct ProfScope {
             cudaEventRecord(b, h->st);
             h->pending.push_back({which, {a, b}});
         }
+        nvtxRangePop();
     }
 };
 

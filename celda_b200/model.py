@@ -241,14 +241,16 @@ def run_order(runs, cost=lambda r: r.get("K", 1) * r.get("L", 1)):
 
 
 def celdaGridSearch(counts, sampleLabel, paramsTest, maxIter=200, nchains=3, seed=12345, algorithm="Gibbs",
-                    rank=0, nranks=1, device=0, runner=None, gather=None, queue=None, **fixed):
+                    rank=0, nranks=1, device=0, runner=None, gather=None, queue=None, isolate_failures=True, **fixed):
     """celdaGridSearch(x, model = "celda_CG", paramsTest, nchains, ...) (R/celdaGridSearch.R:214-439): every
     (chain, K, L) run is an independent single-chain celda_CG on the SAME counts (:290-391).  Each rank keeps one
     resident chain handle (counts uploaded and gene-major twin built once) and re-sizes it per run
     (celda_chain_reconfigure).  Work distribution over `nranks` GPUs: `queue` -- a callable returning the next
     position (0-based, shared atomic counter, e.g. a torch.distributed store `add`) in the longest-first order, so a
     GPU pulls the next run when it finishes one -- or, without a queue, the static longest-processing-time partition.
-    `runner(run, seed)` -> result dict can be injected (tests); `gather` all-gathers picklable objects across ranks."""
+    `runner(run, seed)` -> result dict can be injected (tests); `gather` all-gathers picklable objects across ranks.
+    A run that raises is reported in its runParams row (`error`, logLikelihood = NaN) and the remaining runs go on with a
+    fresh resident chain (`isolate_failures=False` re-raises, like a failed PSOCK worker fails the reference's search)."""
     import time
     runs = expand_grid(paramsTest, nchains)
     resident = {"ch": None}
@@ -280,16 +282,24 @@ def celdaGridSearch(counts, sampleLabel, paramsTest, maxIter=200, nchains=3, see
         for run in mine:
             sd = chain_seed(seed, run["index"], nchains)
             t0 = time.perf_counter()
-            res = runner(run, sd)
+            try:
+                res, err = runner(run, sd), None
+            except Exception as e:  # one failed run does not take the grid down: it is reported, the others go on
+                if not isolate_failures:
+                    raise
+                res, err = None, "%s: %s" % (type(e).__name__, e)
+                if resident["ch"] is not None:  # the chain state behind a failed sweep is unspecified: start afresh
+                    resident["ch"].close()
+                    resident["ch"] = None
             local.append(dict(index=run["index"], chain=run["chain"], K=run.get("K"), L=run.get("L"), seed=sd,
-                              logLikelihood=float(res["finalLogLik"]), seconds=time.perf_counter() - t0, rank=rank,
-                              result=res))
+                              logLikelihood=float(res["finalLogLik"]) if res is not None else float("nan"),
+                              seconds=time.perf_counter() - t0, rank=rank, result=res, error=err))
     finally:
         if resident["ch"] is not None:
             resident["ch"].close()
     everything = [local] if gather is None else gather(local)
     flat = sorted((r for part in everything for r in part), key=lambda r: r["index"])
-    return dict(runParams=[{k: r[k] for k in ("index", "chain", "K", "L", "seed", "logLikelihood", "seconds", "rank")}
+    return dict(runParams=[{k: r[k] for k in ("index", "chain", "K", "L", "seed", "logLikelihood", "seconds", "rank", "error")}
                            for r in flat],
                 resList=[r["result"] for r in flat])
 

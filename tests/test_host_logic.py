@@ -98,3 +98,26 @@ def test_world_size_2_gloo_paths():
                        timeout=280)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("WORKER_OK") == 2, r.stdout[-2000:]
+
+
+def test_grid_search_isolates_a_failed_run():
+    """One run that raises is reported in its row and the other runs still complete (failure isolation)."""
+    import math
+
+    from celda_b200 import model
+
+    def runner(run, seed):
+        if run["K"] == 3 and run["chain"] == 2:
+            raise RuntimeError("sampler failed")
+        return dict(finalLogLik=-float(run["K"] * 10 + run["L"]), z=None, y=None)
+
+    res = model.celdaGridSearch(None, None, dict(K=[2, 3], L=[4]), nchains=2, runner=runner)
+    rows = res["runParams"]
+    assert [r["index"] for r in rows] == [1, 2, 3, 4]
+    bad = [r for r in rows if r["error"]]
+    assert len(bad) == 1 and bad[0]["K"] == 3 and bad[0]["chain"] == 2 and math.isnan(bad[0]["logLikelihood"])
+    assert "sampler failed" in bad[0]["error"] and res["resList"][bad[0]["index"] - 1] is None
+    assert all(r["error"] is None and r["logLikelihood"] == -(r["K"] * 10 + r["L"]) for r in rows if r is not bad[0])
+    import pytest
+    with pytest.raises(RuntimeError):
+        model.celdaGridSearch(None, None, dict(K=[2, 3], L=[4]), nchains=2, runner=runner, isolate_failures=False)
