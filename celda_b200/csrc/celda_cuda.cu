@@ -1401,6 +1401,67 @@ int celda_cCCalcGibbsProbZ(const double* counts, int* mCPByS, int nS, double* nG
     CELDA_TRY(du.upload(u, (size_t)nM));
     if (probs) CELDA_TRY(dprobs.alloc((size_t)K * nM));
     CELDA_TRY(wb.alloc(K, 0));
+    if (z_sweep_smem(nG, K, nS, wb.lgT, 16, 0, 1) > 220 * 1024) {
+        // celda_C shapes (counts = the raw G x C matrix, R/celda_C.R:427-440): the G x K table does not fit shared memory,
+        // so the sweep runs on the raw-count kernel (k_sweep_zc) over a CSC copy of the dense argument; same arithmetic
+        // (the reference sums all G genes per candidate, zeros included)
+        std::vector<int> hp((size_t)nM + 1, 0), hi, hx;
+        for (long long c = 0; c < nM; ++c) {
+            for (int g = 0; g < nG; ++g) {
+                const double v = counts[(size_t)c * nG + g];
+                if (v != 0.0) {
+                    hi.push_back(g);
+                    hx.push_back((int)v);
+                }
+            }
+            if (hi.size() > 0x7fffffffULL) return fail("cCCalcGibbsProbZ: more than 2^31 - 1 stored counts");
+            hp[(size_t)c + 1] = (int)hi.size();
+        }
+        DevBuf<int> dp_, di_, dx_, dng;
+        DevBuf<double> dlg;
+        CELDA_TRY(dp_.upload(hp.data(), hp.size()));
+        CELDA_TRY(di_.upload(hi.data(), std::max<size_t>(hi.size(), 1)));
+        CELDA_TRY(dx_.upload(hx.data(), std::max<size_t>(hx.size(), 1)));
+        CELDA_TRY(dng.alloc((size_t)nG * K));
+        CELDA_TRY(dlg.alloc((size_t)nG * K));
+        k_transpose_convert<int, int><<<grid_for((long long)nG * K, 256, sms), 256>>>(dn.p, nG, K, dng.p, false);
+        k_lgt_fill<<<grid_for((long long)nG * K, 256, sms), 256>>>(dng.p, (long long)nG * K, beta, dlg.p);
+        count_launch(2);
+        ZCArgs c{};
+        c.nG = nG;
+        c.K = K;
+        c.nS = nS;
+        c.nM = nM;
+        c.cp = dp_.p;
+        c.ci = di_.p;
+        c.cx = dx_.p;
+        c.nByC = dbc.p;
+        c.s = ds.p;
+        c.z = dz.p;
+        c.n = dng.p;
+        c.lgn = dlg.p;
+        c.nCP = dcp.p;
+        c.mCPByS = dm.p;
+        c.alpha = alpha;
+        c.beta = beta;
+        c.ix = dix.p;
+        c.u = du.p;
+        c.doSample = doSample;
+        c.probs = probs ? dprobs.p : nullptr;
+        CELDA_TRY(run_sweep_zc(c, wb, sms, 0, 0));
+        k_transpose_convert<int, int><<<grid_for((long long)nG * K, 256, sms), 256>>>(dng.p, nG, K, dn.p, true);
+        count_launch();
+        int stv = 0;
+        CELDA_CUDA_OK(cudaMemcpy(&stv, wb.status.p, sizeof(int), cudaMemcpyDeviceToHost));
+        CELDA_TRY(sweep_status(stv));
+        CELDA_TRY(dz.download(z, (size_t)nM));
+        CELDA_TRY(dm.download(mCPByS, (size_t)K * nS));
+        CELDA_TRY(down_d<int>(dn.p, (size_t)nG * K, nGByCP));
+        CELDA_TRY(down_d<long long>(dcp.p, K, nCP));
+        if (probs) CELDA_TRY(dprobs.download(probs, (size_t)K * nM));
+        CELDA_CUDA_OK(cudaDeviceSynchronize());
+        return 0;
+    }
     ZArgs a{};
     a.R = nG;
     a.K = K;

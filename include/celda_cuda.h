@@ -105,8 +105,9 @@ int celda_cGCalcLL(const double *nTSByC, const double *nByTS, const double *nByG
 /* ---- a8/a9/a10 at sweep granularity, R-closure signatures ------------------------------------
  * replaces .cCCalcGibbsProbZ(counts, mCPByS, nGByCP, nByC, nCP, z, s, K, nG, nM, alpha, beta, doSample)
  *                                                                 R/celda_C.R:620-714
- * counts: dense nG x nM (nTSByC in celda_CG).  ix/u: injected visiting order (1-based) and uniforms
- * (SURVEY.md App. C).  mCPByS, nGByCP, nCP, z are updated in place; probs (K x nM) may be NULL. */
+ * counts: dense nG x nM (nTSByC in celda_CG; the raw count matrix in celda_C -- when its nG x K table does not fit
+ * shared memory the sweep runs on the raw-count kernel over a CSC copy, same results).  ix/u: injected visiting order
+ * (1-based) and uniforms.  mCPByS, nGByCP, nCP, z are updated in place; probs (K x nM) may be NULL. */
 int celda_cCCalcGibbsProbZ(const double *counts, int *mCPByS, int nS, double *nGByCP, const double *nByC, double *nCP,
                            int *z, const int *s, int K, int nG, long long nM, double alpha, double beta, int doSample,
                            const int *ix, const double *u, double *probs);

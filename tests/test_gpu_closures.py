@@ -75,3 +75,27 @@ def test_closure_signature_em(oracle, gold_c):
     with pytest.raises(cb.CeldaCudaError, match="Division by 0"):
         cb.cCCalcEMProbZ(counts.astype(np.float64), p["mCPByS"] * 0, p["nGByCP"], p["nByC"], p["nCP"], z, s, K, p["nG"],
                          p["nM"], 0.0, 1.0)
+
+
+def test_closure_z_sweep_celda_C_shape_beyond_shared_memory(oracle):
+    """.cCCalcGibbsProbZ with counts = a raw G x C matrix whose G x K table does not fit shared memory (G = 2600 at
+    K = 30, R/celda_C.R:427-440): the stateless call runs on the raw-count kernel; labels, tables and probabilities
+    equal the oracle's dense evaluation bit for bit."""
+    rng = np.random.default_rng(44)
+    G, C, K, S = 2600, 120, 30, 2
+    counts = rng.poisson(0.15, (G, C)).astype(np.int32)
+    counts[counts.sum(1) == 0, 0] = 1
+    counts[0, counts.sum(0) == 0] = 1
+    s = (np.arange(C) % S + 1).astype(np.int32)
+    z = (rng.permutation(C) % K + 1).astype(np.int32)
+    p = oracle.cCDecomposeCounts(dense_to_csc(counts), s, z, K)
+    ix, u = rng.permutation(C).astype(np.int32) + 1, rng.random(C)
+    dense = counts.astype(np.float64)
+    for do_sample in (True, False):
+        got = cb.cCCalcGibbsProbZ(dense, p["mCPByS"], p["nGByCP"], p["nByC"], p["nCP"], z, s, K, G, C, 1.0, 1.0, ix, u,
+                                  doSample=do_sample)
+        ref = oracle.cCCalcGibbsProbZ(dense, p["mCPByS"], p["nGByCP"], p["nByC"], p["nCP"], z, s, K, G, C, 1.0, 1.0, ix, u,
+                                      doSample=do_sample)
+        for k in ("mCPByS", "nGByCP", "nCP", "z", "probs"):
+            assert np.array_equal(got[k], ref[k]), (do_sample, k)
+    assert (ref["z"] == z).all() and (got["z"] == z).all()  # the last pass did not sample
