@@ -1,7 +1,9 @@
 /*
  * celda_cuda_shim.c -- the .Call shims a celda maintainer adds to celda/src/ to bind libcelda_cuda
- * (include/celda_cuda.h).  NOT compiled in this repository: R.h / Rinternals.h are not present in the build
- * image; the same C ABI is exercised through ctypes by celda_b200/ and the test-suite.
+ * (include/celda_cuda.h).  R.h / Rinternals.h are not present in the build image, so this
+ * file is compiled (-Wall -Wextra -Werror) and driven through `.Call` against a miniature of the R C API,
+ * tests/r_stub/ (tests/test_r_shim.py); the same C ABI is exercised through ctypes by celda_b200/ and the rest of
+ * the test-suite.
  *
  * Conventions: every shim unpacks R objects into plain pointers, calls the C ABI, and raises an R error with
  * celda_cuda_last_error() only AFTER the call has returned (the library has released its temporaries by then).

@@ -1,0 +1,62 @@
+/* Miniature stand-in for R's C API: just enough of Rinternals.h to compile and run r/celda_cuda_shim.c without an
+ * R installation (tests/test_r_shim.py).  Test infrastructure, not part of the product: the semantics follow
+ * "Writing R Extensions" for the handful of entry points the shim uses; objects live in an arena that
+ * rstub_reset() frees.  A real build uses R's own headers. */
+#ifndef RSTUB_RINTERNALS_H
+#define RSTUB_RINTERNALS_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rstub_sexp *SEXP;
+typedef ptrdiff_t R_xlen_t;
+typedef unsigned int SEXPTYPE;
+typedef enum { FALSE = 0, TRUE } Rboolean;
+
+#define NILSXP 0
+#define SYMSXP 1
+#define INTSXP 13
+#define REALSXP 14
+#define VECSXP 19
+#define EXTPTRSXP 22
+#define S4SXP 25
+
+extern SEXP R_NilValue;
+
+int *INTEGER(SEXP x);
+double *REAL(SEXP x);
+R_xlen_t XLENGTH(SEXP x);
+SEXP SET_VECTOR_ELT(SEXP x, R_xlen_t i, SEXP v);
+SEXP VECTOR_ELT(SEXP x, R_xlen_t i);
+
+SEXP Rf_allocVector(SEXPTYPE type, R_xlen_t n);
+SEXP Rf_allocMatrix(SEXPTYPE type, int nrow, int ncol);
+SEXP Rf_coerceVector(SEXP x, SEXPTYPE type);
+SEXP Rf_ScalarReal(double v);
+SEXP Rf_install(const char *name);
+SEXP R_do_slot(SEXP obj, SEXP name);
+int Rf_asInteger(SEXP x);
+double Rf_asReal(SEXP x);
+int Rf_nrows(SEXP x);
+int Rf_ncols(SEXP x);
+int Rf_nlevels(SEXP x);
+Rboolean Rf_isFactor(SEXP x);
+Rboolean Rf_isNull(SEXP x);
+void Rf_error(const char *fmt, ...) __attribute__((noreturn, format(printf, 1, 2)));
+
+SEXP Rf_protect(SEXP x);
+void Rf_unprotect(int n);
+#define PROTECT(x) Rf_protect(x)
+#define UNPROTECT(n) Rf_unprotect(n)
+
+typedef void (*R_CFinalizer_t)(SEXP);
+SEXP R_MakeExternalPtr(void *p, SEXP tag, SEXP prot);
+void *R_ExternalPtrAddr(SEXP s);
+void R_ClearExternalPtr(SEXP s);
+void R_RegisterCFinalizerEx(SEXP s, R_CFinalizer_t fun, Rboolean onexit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

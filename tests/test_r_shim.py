@@ -1,0 +1,267 @@
+"""r/celda_cuda_shim.c -- the .Call binding INTEGRATION.md asks a celda maintainer to add -- compiled and driven
+without an R installation: tests/r_stub/ is a miniature of the R C API (vectors with dim / levels / S4 slots,
+external pointers with finalizers, Rf_error as a non-local exit, the R_registerRoutines table and an arity-checking
+.Call).  The CPU tests cover what needs no device: the shim compiles against include/celda_cuda.h, links against
+libcelda_cuda.so, registers every routine with the arity its definition has, and turns the library's status +
+celda_cuda_last_error() into an R error.  The gpu tests run the testthat vectors of the reference
+(tests/testthat/test-matrixSums.R:5-76) and one celda_CG chain iteration through `.Call`, against the CPU oracle."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SHIM = os.path.join(ROOT, "r", "celda_cuda_shim.c")
+STUB = os.path.join(ROOT, "tests", "r_stub")
+
+INTSXP, REALSXP, VECSXP, EXTPTRSXP = 13, 14, 19, 22
+
+
+class RStub:
+    """`.Call` over the stub runtime; numpy arrays in, numpy arrays out (column-major like R)."""
+
+    def __init__(self, so):
+        L = self.L = C.CDLL(so)
+        vp = C.c_void_p
+        for name, res, args in [
+            ("rstub_nil", vp, []), ("rstub_int", vp, [C.c_ssize_t, vp]), ("rstub_real", vp, [C.c_ssize_t, vp]),
+            ("rstub_set_dim", None, [vp, C.c_int, C.c_int]), ("rstub_set_levels", None, [vp, C.c_int]),
+            ("rstub_s4", vp, []), ("rstub_set_slot", None, [vp, C.c_char_p, vp]), ("rstub_type", C.c_int, [vp]),
+            ("rstub_length", C.c_longlong, [vp]), ("rstub_data", vp, [vp]), ("rstub_nrow", C.c_int, [vp]),
+            ("rstub_ncol", C.c_int, [vp]), ("rstub_vector_elt", vp, [vp, C.c_longlong]),
+            ("rstub_protect_balance", C.c_int, []), ("rstub_n_routines", C.c_int, []),
+            ("rstub_routine_name", C.c_char_p, [C.c_int]), ("rstub_routine_nargs", C.c_int, [C.c_int]),
+            ("rstub_call", vp, [C.c_char_p, C.c_int, C.POINTER(vp), C.c_char_p, C.c_int]), ("rstub_reset", C.c_int, []),
+            ("celda_cuda_register", None, [vp]),
+        ]:
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        L.celda_cuda_register(None)
+
+    # ---- R objects
+    def integer(self, v, dim=None, levels=None):
+        a = np.ascontiguousarray(np.asarray(v, dtype=np.int32).ravel(order="F"))
+        s = self.L.rstub_int(a.size, a.ctypes.data)
+        if dim is not None:
+            self.L.rstub_set_dim(s, *dim)
+        if levels is not None:
+            self.L.rstub_set_levels(s, levels)
+        return s
+
+    def numeric(self, v, dim=None):
+        a = np.ascontiguousarray(np.asarray(v, dtype=np.float64).ravel(order="F"))
+        s = self.L.rstub_real(a.size, a.ctypes.data)
+        if dim is not None:
+            self.L.rstub_set_dim(s, *dim)
+        return s
+
+    def matrix(self, m):
+        m = np.asarray(m)
+        return (self.integer if m.dtype.kind == "i" else self.numeric)(m, dim=m.shape)
+
+    def factor(self, codes, nlevels):
+        return self.integer(codes, levels=nlevels)
+
+    def dgCMatrix(self, dense):
+        """The Matrix package's column-compressed S4 object: slots Dim, p, i (0-based), x (double)."""
+        dense = np.asarray(dense)
+        p, i, x = [0], [], []
+        for c in range(dense.shape[1]):
+            nz = np.nonzero(dense[:, c])[0]
+            i += nz.tolist()
+            x += dense[nz, c].tolist()
+            p.append(len(i))
+        s = self.L.rstub_s4()
+        for name, v in (("Dim", self.integer(dense.shape)), ("p", self.integer(p)), ("i", self.integer(i)),
+                        ("x", self.numeric(x))):
+            self.L.rstub_set_slot(s, name.encode(), v)
+        return s
+
+    @property
+    def NULL(self):
+        return self.L.rstub_nil()
+
+    def value(self, s):
+        t, n = self.L.rstub_type(s), self.L.rstub_length(s)
+        if t == VECSXP:
+            return [self.value(self.L.rstub_vector_elt(s, k)) for k in range(n)]
+        if t not in (INTSXP, REALSXP):
+            return s  # NULL, external pointer
+        ct = C.c_int if t == INTSXP else C.c_double
+        a = np.ctypeslib.as_array(C.cast(self.L.rstub_data(s), C.POINTER(ct)), shape=(max(n, 1),))[:n].copy()
+        nr, nc = self.L.rstub_nrow(s), self.L.rstub_ncol(s)
+        return a.reshape((nr, nc), order="F") if nr * nc == n and nc != 1 else a
+
+    # ---- .Call
+    def call(self, name, *args, raw=False):
+        arr = (C.c_void_p * max(len(args), 1))(*args)
+        err = C.create_string_buffer(1024)
+        out = self.L.rstub_call(name.encode(), len(args), arr, err, len(err))
+        if not out:
+            raise RuntimeError(err.value.decode())
+        assert self.L.rstub_protect_balance() == 0, f"{name}: PROTECT / UNPROTECT imbalance"
+        return out if raw else self.value(out)
+
+    def routines(self):
+        return {self.L.rstub_routine_name(k).decode(): self.L.rstub_routine_nargs(k)
+                for k in range(self.L.rstub_n_routines())}
+
+
+@pytest.fixture(scope="module")
+def R(tmp_path_factory):
+    from celda_b200 import _lib
+    so_dir = os.path.dirname(_lib.build())
+    out = str(tmp_path_factory.mktemp("rshim") / "celda_shim_test.so")
+    cmd = ["gcc", "-O1", "-g", "-Wall", "-Wextra", "-Werror", "-Wno-cast-function-type", "-shared", "-fPIC",
+           "-I" + os.path.join(STUB, "include"), "-I" + os.path.join(ROOT, "include"), "-o", out, SHIM,
+           os.path.join(STUB, "rstub.c"), "-L" + so_dir, "-l:libcelda_cuda.so", "-Wl,-rpath," + so_dir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    stub = RStub(out)
+    yield stub
+    stub.L.rstub_reset()
+
+
+def _shim_definitions():
+    src = re.sub(r"/\*.*?\*/", "", open(SHIM).read(), flags=re.S)
+    return {m.group(1): len([a for a in m.group(2).split(",") if a.strip()])
+            for m in re.finditer(r"^SEXP\s+(_\w+)\s*\(([^)]*)\)\s*\{", src, flags=re.M)}
+
+
+def test_shim_compiles_and_registers_every_routine(R):
+    """-Wall -Wextra -Werror against include/celda_cuda.h, and the R_CallMethodDef table agrees with the definitions."""
+    defs, table = _shim_definitions(), R.routines()
+    assert len(defs) >= 30
+    assert table == defs  # same names, and numArgs equals each definition's parameter count
+    # the dense natives keep the .Call names of the reference (NAMESPACE useDynLib / src/RcppExports.cpp:308-337)
+    for name in ("_rowSumByGroup", "_colSumByGroup", "_rowSumByGroupChange", "_colSumByGroupChange", "_perplexityG",
+                 "_rowSumByGroup_numeric", "_colSumByGroup_numeric", "_rowSumByGroupChange_numeric",
+                 "_colSumByGroupChange_numeric"):
+        assert name in table
+
+
+def test_shim_binds_only_declared_entry_points():
+    from celda_b200 import _lib
+    used = set(re.findall(r"\b(celda_\w+)\s*\(", open(SHIM).read())) - {"celda_cuda_register"}
+    decl = set(_lib.declared_functions())
+    assert used and used <= decl, used - decl
+
+
+def test_call_checks_arity_and_name(R):
+    with pytest.raises(RuntimeError, match="Incorrect number of arguments"):
+        R.call("_rowSumByGroup", R.NULL)
+    with pytest.raises(RuntimeError, match="not available for .Call"):
+        R.call("_celda_cuda_no_such_routine")
+
+
+def test_library_status_becomes_an_R_error_without_a_device(R):
+    """Argument validation precedes any CUDA call, so the error path of CHECK() runs on a CPU-only box:
+    the messages are the reference's (src/matrixSums.c:13-22, 151-172)."""
+    mat = np.asfortranarray(np.tile(np.arange(1, 6), 20).reshape(10, 10, order="F").astype(np.int32))
+    lab = np.repeat([1, 2], 5)
+    with pytest.raises(RuntimeError, match="must be a factor"):
+        R.call("_rowSumByGroup", R.matrix(mat), R.integer(lab))  # an integer vector, not a factor
+    with pytest.raises(RuntimeError, match="must match the number of rows"):
+        R.call("_rowSumByGroup", R.matrix(mat), R.factor(lab[:9], 2))
+    with pytest.raises(RuntimeError, match="must match the number of columns"):
+        R.call("_colSumByGroup_numeric", R.matrix(mat.astype(np.float64)), R.factor(lab[:9], 2))
+    with pytest.raises(RuntimeError, match="must not be NA"):
+        na = lab.copy()
+        na[3] = np.iinfo(np.int32).min
+        R.call("_rowSumByGroup", R.matrix(mat), R.factor(na, 2))
+    with pytest.raises(RuntimeError, match='no slot of name "Dim"'):
+        R.call("_celda_cuda_colSumByGroupSparse", R.matrix(mat), R.integer(lab), R.integer([2]))
+    with pytest.raises(RuntimeError, match="wrong SEXP type"):
+        R.call("_celda_cuda_chain_loglik", R.integer([1]))  # not an external pointer
+
+
+# ------------------------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["int", "numeric"])
+def test_matrixSums_known_answers_through_dotCall(R, kind):
+    """tests/testthat/test-matrixSums.R:5-76 the way R would run it: `.Call` on matrices and factors."""
+    dtype, sfx = (np.int32, "") if kind == "int" else (np.float64, "_numeric")
+    mat = np.tile(np.arange(1, 6), 20).reshape(10, 10, order="F").astype(dtype)
+    lab, lab2 = np.repeat([1, 2], 5), np.array([1, 2] * 5)
+    want_r = np.stack([mat[lab == g].sum(0) for g in (1, 2)])
+    want_c = np.stack([mat[:, lab == g].sum(1) for g in (1, 2)], axis=1)
+    got_r = R.call("_rowSumByGroup" + sfx, R.matrix(mat), R.factor(lab, 2))
+    got_c = R.call("_colSumByGroup" + sfx, R.matrix(mat), R.factor(lab, 2))
+    assert got_r.dtype == dtype and np.array_equal(got_r, want_r) and np.array_equal(got_c, want_c)
+    px = R.matrix(want_r)
+    out = R.call("_rowSumByGroupChange" + sfx, R.matrix(mat), px, R.factor(lab2, 2), R.factor(lab, 2), raw=True)
+    assert out == px  # modified in place and returned, like the reference (src/matrixSums.c:136-142)
+    assert np.array_equal(R.value(px), np.stack([mat[lab2 == g].sum(0) for g in (1, 2)]))
+    px = R.matrix(want_c)
+    R.call("_colSumByGroupChange" + sfx, R.matrix(mat), px, R.factor(lab2, 2), R.factor(lab, 2))
+    assert np.array_equal(R.value(px), np.stack([mat[:, lab2 == g].sum(1) for g in (1, 2)], axis=1))
+
+
+@pytest.mark.gpu
+def test_sparse_aggregation_and_natives_through_dotCall(R, oracle, gold_cg):
+    from oracle.oracle import dense_to_csc
+    counts = gold_cg["counts"]
+    nG, nM = counts.shape
+    rng = np.random.default_rng(3)
+    z, z2 = rng.integers(1, 6, nM), rng.integers(1, 6, nM)
+    y, y2 = rng.integers(1, 11, nG), rng.integers(1, 11, nG)
+    O, A = dense_to_csc(counts), R.dgCMatrix(counts)
+    cs = R.call("_celda_cuda_colSumByGroupSparse", A, R.integer(z), R.integer([5]))
+    rs = R.call("_celda_cuda_rowSumByGroupSparse", A, R.integer(y), R.integer([10]))
+    assert np.array_equal(cs, oracle.colSumByGroupSparse(O, z.astype(np.int32), 5))
+    assert np.array_equal(rs, oracle.rowSumByGroupSparse(O, y.astype(np.int32), 10))
+    px = R.matrix(cs)
+    R.call("_celda_cuda_colSumByGroupChangeSparse", A, px, R.integer(z2), R.integer(z), R.integer([5]))
+    assert np.array_equal(R.value(px), oracle.colSumByGroupSparse(O, z2.astype(np.int32), 5))
+    px = R.matrix(rs)
+    R.call("_celda_cuda_rowSumByGroupChangeSparse", A, px, R.integer(y2), R.integer(y), R.integer([10]))
+    assert np.array_equal(R.value(px), oracle.rowSumByGroupSparse(O, y2.astype(np.int32), 10))
+    # eigenMatMultInt(A, B) = t(A) %*% B (src/eigenMatMultInt.cpp:11-20), fastNormPropLog (src/matrixNorm.cpp:36-52)
+    a, b = rng.random((40, 6)), rng.integers(0, 9, (40, 7)).astype(np.int32)
+    assert np.allclose(R.call("_celda_cuda_eigenMatMultInt", R.matrix(a), R.matrix(b)), a.T @ b, rtol=1e-13)
+    m = rng.integers(0, 50, (12, 9)).astype(np.float64)
+    want = np.log((m + 0.5) / (m + 0.5).sum(0))
+    assert np.allclose(R.call("_celda_cuda_fastNormPropLog", R.matrix(m), R.numeric([0.5])), want, rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_chain_iteration_through_dotCall_matches_oracle(R, oracle, gold_cg):
+    """create -> set_state -> iterate -> get_state / loglik / perplexity on an external pointer, one celda_CG Gibbs
+    iteration (R/celda_CG.R:543-602) with injected draws; labels bit-exact, logLik 1e-9; the finalizer frees it."""
+    from oracle.oracle import dense_to_csc
+    counts, s, K, L = gold_cg["counts"], gold_cg["s"], 5, 10
+    nG, nM = counts.shape
+    rng = np.random.default_rng(0)
+    z, y = rng.integers(1, K + 1, nM).astype(np.int32), rng.integers(1, L + 1, nG).astype(np.int32)
+    ixy, uy = rng.permutation(nG).astype(np.int32) + 1, rng.random(nG)
+    ixz, uz = rng.permutation(nM).astype(np.int32) + 1, rng.random(nM)
+    h = R.call("_celda_cuda_chain_create", R.integer([0]), R.dgCMatrix(counts), R.integer(s),
+               R.integer([int(s.max())]), R.integer([K]), R.integer([L]), R.numeric([1, 1, 1, 1]), R.integer([0]),
+               raw=True)
+    assert R.L.rstub_type(h) == EXTPTRSXP
+    R.call("_celda_cuda_chain_set_state", h, R.integer(z), R.integer(y))
+    ll = R.call("_celda_cuda_chain_iterate", h, R.integer(ixy), R.numeric(uy), R.integer(ixz), R.numeric(uz))[0]
+    zg, yg = R.call("_celda_cuda_chain_get_state", h, R.integer([nM]), R.integer([nG]))
+    O = dense_to_csc(counts)
+    p = oracle.cCGDecomposeCounts(O, s, z, y, K, L)
+    oy = oracle.cGCalcGibbsProbY(p["nGByCP"], p["nTSByCP"], p["nByTS"], p["nGByTS"], p["nByG"], y, L, nG, 1.0, 1.0,
+                                 1.0, ixy, uy)
+    nTSByC = oracle.rowSumByGroupChangeSparse(O, p["nTSByC"].copy(order="F"), oy["y"], y, L)
+    oz = oracle.cCCalcGibbsProbZ(nTSByC, p["mCPByS"], oy["nTSByC"], p["nByC"], p["nCP"], z, s, K, L, nM, 1.0, 1.0,
+                                 ixz, uz)
+    ref = oracle.cCGCalcLL(K, L, oz["mCPByS"], oz["nGByCP"], p["nByG"], oy["nByTS"], oy["nGByTS"], p["nS"], nG, 1.0,
+                           1.0, 1.0, 1.0)
+    assert np.array_equal(zg, oz["z"]) and np.array_equal(yg, oy["y"])
+    assert abs(ll - ref) <= 1e-9 * abs(ref)
+    assert abs(R.call("_celda_cuda_chain_loglik", h)[0] - ref) <= 1e-9 * abs(ref)
+    assert R.call("_celda_cuda_chain_perplexity", h)[0] > 1.0
+    # an R-level error from inside the library (labels out of range) leaves the handle usable
+    with pytest.raises(RuntimeError):
+        R.call("_celda_cuda_chain_set_state", h, R.integer(np.full(nM, K + 1)), R.integer(y))
+    R.call("_celda_cuda_chain_set_state", h, R.integer(zg), R.integer(yg))
+    assert abs(R.call("_celda_cuda_chain_loglik", h)[0] - ref) <= 1e-9 * abs(ref)
+    assert R.L.rstub_reset() == 1  # gc: the external pointer's finalizer ran celda_chain_destroy
+    R.L.celda_cuda_register(None)
