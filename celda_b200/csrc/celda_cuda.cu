@@ -106,6 +106,11 @@ struct celda_chain {
     double alpha = 1, beta = 1, delta = 1, gamma = 1;
     cudaStream_t st = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // celda_chain_iterate (celda_CG, injected draws): the z sweep's order and uniforms are copied on a second stream
+    // while the y sweep runs; the iteration's results come back through one pinned block
+    cudaStream_t stCopy = nullptr;
+    cudaEvent_t evCopyGo = nullptr, evCopyDone = nullptr;
+    double* hostRes = nullptr;  // pinned: [0] log-likelihood, [1] the two status words
     bool has_state = false;
     DevBuf<int> cp, ci, cx, s, z, y, zprev, yprev;
     // gene-major twin of the counts (rows sorted by column), built on the device at create for celda_CG / celda_G
@@ -138,7 +143,7 @@ struct celda_chain {
     int last_draw_n[2] = {0, 0};  // for get_draws: y, z
     DevBuf<int> altLab, altT, altM, altG;  // celda_chain_loglik_alt: candidate labels and their small tables
     DevBuf<long long> altTS;
-    DevBuf<int> emFlag, ordSeen, resCum, resX;  // resX / resCum: multinomial resample of the counts (perplexity)
+    DevBuf<int> emFlag, ordSeen, ordSeenZ, resCum, resX;  // resX / resCum: multinomial resample of the counts (perplexity)
     // staged draws
     int staged_iters = 0;
     DevBuf<int> st_ixy, st_ixz;
@@ -158,6 +163,13 @@ struct celda_chain {
         }
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (stCopy) {
+            cudaStreamSynchronize(stCopy);
+            cudaStreamDestroy(stCopy);
+        }
+        if (evCopyGo) cudaEventDestroy(evCopyGo);
+        if (evCopyDone) cudaEventDestroy(evCopyDone);
+        if (hostRes) cudaFreeHost(hostRes);
         if (st) cudaStreamDestroy(st);
     }
 };
@@ -232,6 +244,48 @@ int chain_upload_order(celda_chain* h, int* d_ix, const int* ix, long long n) {
     k_validate_order<<<grid_for(n, 256, h->sms), 256, 0, h->st>>>(d_ix, n, h->ordSeen.p, h->wb.status.p + 1);
     count_launch();
     return 0;
+}
+
+// The z sweep's injected draws of a celda_CG iteration (12 bytes per cell), issued after the y sweep has been launched:
+// the copies run on the copy engine behind the y sweep instead of in front of it.  The copy stream starts behind
+// everything already queued on the chain's stream (evCopyGo) and the chain's stream resumes behind it (evCopyDone).
+int chain_copy_stream(celda_chain* h) {
+    if (h->stCopy) return 0;
+    CELDA_CUDA_OK(cudaEventCreateWithFlags(&h->evCopyGo, cudaEventDisableTiming));
+    CELDA_CUDA_OK(cudaEventCreateWithFlags(&h->evCopyDone, cudaEventDisableTiming));
+    CELDA_CUDA_OK(cudaStreamCreateWithFlags(&h->stCopy, cudaStreamNonBlocking));
+    return 0;
+}
+
+int chain_upload_z_draws_behind(celda_chain* h, const int* ix_z, const double* u_z) {
+    const long long n = h->nM;
+    if (h->ordSeenZ.n < (size_t)n) CELDA_TRY(h->ordSeenZ.alloc((size_t)n));
+    CELDA_CUDA_OK(cudaStreamWaitEvent(h->stCopy, h->evCopyGo, 0));
+    CELDA_CUDA_OK(cudaMemcpyAsync(h->ixz.p, ix_z, sizeof(int) * n, cudaMemcpyHostToDevice, h->stCopy));
+    CELDA_CUDA_OK(cudaMemcpyAsync(h->uz.p, u_z, sizeof(double) * n, cudaMemcpyHostToDevice, h->stCopy));
+    CELDA_CUDA_OK(cudaMemsetAsync(h->ordSeenZ.p, 0, sizeof(int) * n, h->stCopy));
+    k_validate_order<<<grid_for(n, 256, h->sms), 256, 0, h->stCopy>>>(h->ixz.p, n, h->ordSeenZ.p, h->wb.status.p + 1);
+    count_launch();
+    CELDA_CUDA_OK(cudaEventRecord(h->evCopyDone, h->stCopy));
+    CELDA_CUDA_OK(cudaStreamWaitEvent(h->st, h->evCopyDone, 0));
+    return 0;
+}
+
+// End of an iteration: log-likelihood and status words through one pinned block and one synchronisation.
+int chain_finish_iteration(celda_chain* h, double* ll) {
+    if (!h->hostRes) CELDA_CUDA_OK(cudaMallocHost(&h->hostRes, 2 * sizeof(double)));
+    int* stv = reinterpret_cast<int*>(h->hostRes + 1);
+    CELDA_CUDA_OK(cudaMemcpyAsync(h->hostRes, h->llOut.p, sizeof(double), cudaMemcpyDeviceToHost, h->st));
+    CELDA_CUDA_OK(cudaMemcpyAsync(stv, h->wb.status.p, 2 * sizeof(int), cudaMemcpyDeviceToHost, h->st));
+    CELDA_TRY(chain_sync(h));
+    *ll = h->hostRes[0];
+    const int s0 = stv[0], s1 = stv[1];
+    if (s0 || s1) {
+        CELDA_TRY(h->wb.status.zero(h->st));
+        CELDA_TRY(chain_sync(h));
+    }
+    if (s1) return fail("the visiting order must be a permutation of 1..n");
+    return sweep_status(s0);
 }
 
 // Cell-sharded mode: combine the shards' partial G x K and K x S tables with one all-reduce each (int32 sums are
@@ -1796,7 +1850,7 @@ int celda_chain_get_state(celda_chain* h, int* z, int* y) {
 int celda_chain_sweep_y(celda_chain* h, const int* ix, const double* u, int doSample) {
     CELDA_CUDA_OK(cudaSetDevice(h->device));
     if (!h->has_state) return fail("set_state must be called first");
-        CELDA_TRY(chain_upload_order(h, h->ixy.p, ix, h->nG));
+    CELDA_TRY(chain_upload_order(h, h->ixy.p, ix, h->nG));
     CELDA_CUDA_OK(cudaMemcpyAsync(h->uy.p, u, sizeof(double) * h->nG, cudaMemcpyHostToDevice, h->st));
     CELDA_TRY(chain_step_y(h, h->ixy.p, h->uy.p, doSample));
     return chain_check_status(h);
@@ -1805,7 +1859,7 @@ int celda_chain_sweep_y(celda_chain* h, const int* ix, const double* u, int doSa
 int celda_chain_sweep_z_gibbs(celda_chain* h, const int* ix, const double* u, int doSample) {
     CELDA_CUDA_OK(cudaSetDevice(h->device));
     if (!h->has_state) return fail("set_state must be called first");
-        CELDA_TRY(chain_upload_order(h, h->ixz.p, ix, h->nM));
+    CELDA_TRY(chain_upload_order(h, h->ixz.p, ix, h->nM));
     CELDA_CUDA_OK(cudaMemcpyAsync(h->uz.p, u, sizeof(double) * h->nM, cudaMemcpyHostToDevice, h->st));
     CELDA_TRY(chain_step_z(h, h->ixz.p, h->uz.p, doSample));
     return chain_check_status(h);
@@ -1943,7 +1997,7 @@ int celda_chain_iterate(celda_chain* h, const int* ix_y, const double* u_y, cons
     cudaStream_t st = h->st;
     if (h->model == CELDA_MODEL_C) {  // .celda_C loop body, algorithm = "Gibbs" (R/celda_C.R:427-470): z sweep, log-likelihood
         if (ix_z && u_z) {
-                        CELDA_TRY(chain_upload_order(h, h->ixz.p, ix_z, h->nM));
+            CELDA_TRY(chain_upload_order(h, h->ixz.p, ix_z, h->nM));
             CELDA_CUDA_OK(cudaMemcpyAsync(h->uz.p, u_z, sizeof(double) * h->nM, cudaMemcpyHostToDevice, st));
         } else {
             CELDA_TRY(chain_philox_draws(h, h->nM, h->ixz.p, h->uz.p));
@@ -1955,7 +2009,7 @@ int celda_chain_iterate(celda_chain* h, const int* ix_y, const double* u_y, cons
     }
     if (h->model == CELDA_MODEL_G) {  // .celda_G loop body (R/celda_G.R:400-424): y sweep, log-likelihood
         if (ix_y && u_y) {
-                        CELDA_TRY(chain_upload_order(h, h->ixy.p, ix_y, h->nG));
+            CELDA_TRY(chain_upload_order(h, h->ixy.p, ix_y, h->nG));
             CELDA_CUDA_OK(cudaMemcpyAsync(h->uy.p, u_y, sizeof(double) * h->nG, cudaMemcpyHostToDevice, st));
         } else {
             CELDA_TRY(chain_philox_draws(h, h->nG, h->ixy.p, h->uy.p));
@@ -1970,16 +2024,16 @@ int celda_chain_iterate(celda_chain* h, const int* ix_y, const double* u_y, cons
         CELDA_TRY(chain_philox_draws(h, h->nM, h->ixz.p, h->uz.p));
     } else {
         if (!ix_y || !u_y || !ix_z || !u_z) return fail("iterate: pass all four of ix_y, u_y, ix_z, u_z or none (Philox)");
-                        CELDA_TRY(chain_upload_order(h, h->ixy.p, ix_y, h->nG));
+        CELDA_TRY(chain_upload_order(h, h->ixy.p, ix_y, h->nG));
         CELDA_CUDA_OK(cudaMemcpyAsync(h->uy.p, u_y, sizeof(double) * h->nG, cudaMemcpyHostToDevice, st));
-        CELDA_TRY(chain_upload_order(h, h->ixz.p, ix_z, h->nM));
-        CELDA_CUDA_OK(cudaMemcpyAsync(h->uz.p, u_z, sizeof(double) * h->nM, cudaMemcpyHostToDevice, st));
+        CELDA_TRY(chain_copy_stream(h));
+        CELDA_CUDA_OK(cudaEventRecord(h->evCopyGo, st));  // ixz / uz are free once everything queued so far has run
     }
     CELDA_TRY(chain_step_y(h, h->ixy.p, h->uy.p, 1));
+    if (ix_z) CELDA_TRY(chain_upload_z_draws_behind(h, ix_z, u_z));
     CELDA_TRY(chain_step_z(h, h->ixz.p, h->uz.p, 1));
     CELDA_TRY(chain_loglik_async(h));
-    CELDA_CUDA_OK(cudaMemcpyAsync(ll, h->llOut.p, sizeof(double), cudaMemcpyDeviceToHost, st));
-    return chain_check_status(h);
+    return chain_finish_iteration(h, ll);
 }
 
 int celda_chain_sweep_z_em(celda_chain* h, int doSample) {
@@ -1997,7 +2051,7 @@ int celda_chain_iterate_em(celda_chain* h, const int* ix_y, const double* u_y, d
     if (h->model == CELDA_MODEL_G) return fail("iterate_em: celda_G has no cell populations");
     if (h->model == CELDA_MODEL_CG) {
         if (!ix_y || !u_y) return fail("iterate_em: injected order and uniforms are required for the y sweep");
-                CELDA_TRY(chain_upload_order(h, h->ixy.p, ix_y, h->nG));
+        CELDA_TRY(chain_upload_order(h, h->ixy.p, ix_y, h->nG));
         CELDA_CUDA_OK(cudaMemcpyAsync(h->uy.p, u_y, sizeof(double) * h->nG, cudaMemcpyHostToDevice, h->st));
         CELDA_TRY(chain_step_y(h, h->ixy.p, h->uy.p, 1));
     }
