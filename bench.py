@@ -529,13 +529,38 @@ def main():
     e2e = world * K / (ms_e2e / 1e3)
     h2d = 12 * (nG + nM)
 
+    # ------------------------------------------------------------ leg 3: the production generator (device Philox)
+    # same chain, no injected draws: the visiting orders (a key sort per sweep) and the uniforms are made on the device
+    ph_err, ms_ph = None, float("nan")
+    try:
+        ch.seed(12345 + rank, 0)
+        for it in range(W):
+            ch.iterate_philox()
+    except Exception as e:  # reported in the line, never fatal for the headline legs
+        ph_err = str(e)
+    barrier()
+    l0 = cb.launch_count()
+    ch.timer_start()
+    try:
+        for it in range(K):
+            if ph_err is None:
+                ch.iterate_philox()
+    except Exception as e:
+        ph_err = str(e)
+    ms_ph = max_over_ranks(ch.timer_stop())
+    philox = ({"error": ph_err} if ph_err else
+              {"ms_per_step": ms_ph / K, "iter_per_s": world * K / (ms_ph / 1e3),
+               "launches_per_step": (cb.launch_count() - l0) / K,
+               "note": "celda_chain_iterate with NULL draws: Philox4x32-10 keys + uniforms and the key sort that turns "
+                       "them into visiting orders run on the device inside the timed region; 8 B D2H per step"})
+
     out = {"metric": "celda_CG_gibbs_iterations_per_sec", "value": value, "unit": "iter/s", "n_gpus": world,
            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_of(a, d),
            "cells_iters_per_sec": value * nM, "clocks": clk, "gpu_launches": int(launches),
            "e2e": {"value": e2e, "unit": "iter/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                    "ms_per_step": ms_e2e / K},
-           "logLik_first_last": [lls[0], lls[-1]]}
+           "logLik_first_last": [lls[0], lls[-1]], "philox_mode": philox}
     if rank == 0:
         default_cfg = (a.cells, a.genes, a.K, a.L, a.start) == (100000, 20000, 30, 150, "truth10")
         out.update(rooflines(cb, ch, a, d, prof, clk, default_cfg))
