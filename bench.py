@@ -530,7 +530,8 @@ def main():
     h2d = 12 * (nG + nM)
 
     # ------------------------------------------------------------ leg 3: the production generator (device Philox)
-    # same chain, no injected draws: the visiting orders (a key sort per sweep) and the uniforms are made on the device
+    # same chain, no injected draws: the visiting orders (a keyed permutation, philox.cuh) and the uniforms are made
+    # on the device, one kernel per sweep
     ph_err, ms_ph = None, float("nan")
     try:
         ch.seed(12345 + rank, 0)
@@ -551,8 +552,8 @@ def main():
     philox = ({"error": ph_err} if ph_err else
               {"ms_per_step": ms_ph / K, "iter_per_s": world * K / (ms_ph / 1e3),
                "launches_per_step": (cb.launch_count() - l0) / K,
-               "note": "celda_chain_iterate with NULL draws: Philox4x32-10 keys + uniforms and the key sort that turns "
-                       "them into visiting orders run on the device inside the timed region; 8 B D2H per step"})
+               "note": "celda_chain_iterate with NULL draws: the visiting orders (keyed Feistel permutation over Philox4x32-10, no "
+                       "sort) and the uniforms are computed on the device inside the timed region; 8 B D2H per step"})
 
     out = {"metric": "celda_CG_gibbs_iterations_per_sec", "value": value, "unit": "iter/s", "n_gpus": world,
            "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak",

@@ -137,9 +137,6 @@ struct celda_chain {
     unsigned long long ph_seed = 0, ph_stream = 0;
     unsigned ph_sweep = 0;
     bool ph_seeded = false;
-    DevBuf<unsigned long long> ph_keys, ph_keys_out;
-    DevBuf<int> ph_iota;
-    DevBuf<unsigned char> ph_tmp;
     int last_draw_n[2] = {0, 0};  // for get_draws: y, z
     DevBuf<int> altLab, altT, altM, altG;  // celda_chain_loglik_alt: candidate labels and their small tables
     DevBuf<long long> altTS;
@@ -874,22 +871,10 @@ int chain_check_em_flag(celda_chain* h) {
 // the device into the chain's ix / u staging buffers.
 int chain_philox_draws(celda_chain* h, long long n, int* d_ix, double* d_u) {
     if (!h->ph_seeded) return fail("philox mode: call celda_chain_seed first");
-    cudaStream_t st = h->st;
-    if (h->ph_keys.n < (size_t)n) {
-        CELDA_TRY(h->ph_keys.alloc((size_t)n));
-        CELDA_TRY(h->ph_keys_out.alloc((size_t)n));
-        CELDA_TRY(h->ph_iota.alloc((size_t)n));
-    }
-    k_philox_draws<<<grid_for(n, 256, h->sms), 256, 0, st>>>(n, (unsigned)h->ph_seed, (unsigned)(h->ph_seed >> 32), h->ph_sweep,
-                                                             (unsigned)h->ph_stream, h->ph_keys.p, h->ph_iota.p, d_u);
+    k_philox_draws<<<grid_for(n, 256, h->sms), 256, 0, h->st>>>(n, philox_order_bits((unsigned long long)n), (unsigned)h->ph_seed,
+                                                                (unsigned)(h->ph_seed >> 32), h->ph_sweep,
+                                                                (unsigned)h->ph_stream, d_ix, d_u);
     count_launch();
-    size_t bytes = 0;
-    CELDA_CUDA_OK(cub::DeviceRadixSort::SortPairs(nullptr, bytes, h->ph_keys.p, h->ph_keys_out.p, h->ph_iota.p, d_ix, (int)n, 0,
-                                                  64, st));
-    if (h->ph_tmp.n < bytes) CELDA_TRY(h->ph_tmp.alloc(bytes));
-    CELDA_CUDA_OK(cub::DeviceRadixSort::SortPairs(h->ph_tmp.p, bytes, h->ph_keys.p, h->ph_keys_out.p, h->ph_iota.p, d_ix, (int)n,
-                                                  0, 64, st));
-    count_launch(8);  // radix sort passes
     h->ph_sweep += 1;
     return 0;
 }

@@ -4,6 +4,7 @@
 // for bit and is order-independent (atomics are safe).
 #pragma once
 #include "celda_math.cuh"
+#include "philox.cuh"
 
 namespace celda {
 
@@ -950,25 +951,6 @@ __global__ void k_perp_final(const double* __restrict__ partial, int np, const i
 namespace celda {
 
 // ---------------------------------------------------------------------------------------------- Philox4x32-10
-// Counter-based generator (Salmon et al., SC'11).  Used for the production ("philox") mode of the sweeps; the
-// injection mode takes order and uniforms from the host instead.
-struct Philox4 {
-    unsigned x[4];
-};
-__host__ __device__ inline Philox4 philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
-                                                 unsigned k1) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const unsigned long long p0 = 0xD2511F53ull * c0, p1 = 0xCD9E8D57ull * c2;
-        const unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0, n1 = (unsigned)p1;
-        const unsigned n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1, n3 = (unsigned)p0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    return Philox4{{c0, c1, c2, c3}};
-}
-
 __global__ void k_philox_raw(const unsigned* __restrict__ ctr, const unsigned* __restrict__ key, int n,
                              unsigned* __restrict__ out) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -977,19 +959,12 @@ __global__ void k_philox_raw(const unsigned* __restrict__ ctr, const unsigned* _
     }
 }
 
-// Draws of one sweep: counter = (item lo, item hi, sweep id, 2 * stream + purpose); purpose 0 -> 64-bit sort key of
-// item i (the visiting order is the argsort of the keys), purpose 1 -> the uniform of the t-th visited item,
-// u = (52 random bits + 1/2) * 2^-52 in (0, 1), exactly representable.
-__global__ void k_philox_draws(long long n, unsigned k0, unsigned k1, unsigned sweep, unsigned stream,
-                               unsigned long long* __restrict__ keys, int* __restrict__ iota, double* __restrict__ u) {
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const unsigned lo = (unsigned)i, hi = (unsigned)(i >> 32);
-        const Philox4 a = philox4x32_10(lo, hi, sweep, 2u * stream, k0, k1);
-        keys[i] = ((unsigned long long)a.x[0] << 32) | a.x[1];
-        iota[i] = (int)i + 1;
-        const Philox4 b = philox4x32_10(lo, hi, sweep, 2u * stream + 1u, k0, k1);
-        const unsigned long long bits = (((unsigned long long)b.x[0] << 32) | b.x[1]) >> 12;
-        u[i] = ((double)bits + 0.5) * 2.220446049250313e-16;
+// Draws of one sweep in Philox mode (philox.cuh): ix[t] = the t-th visited item (1-based), u[t] = its uniform.
+__global__ void k_philox_draws(long long n, unsigned bits, unsigned k0, unsigned k1, unsigned sweep, unsigned stream,
+                               int* __restrict__ ix, double* __restrict__ u) {
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        ix[t] = (int)philox_order((unsigned long long)t, (unsigned long long)n, bits, k0, k1, sweep, stream) + 1;
+        u[t] = philox_uniform((unsigned long long)t, k0, k1, sweep, stream);
     }
 }
 

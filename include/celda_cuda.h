@@ -150,7 +150,8 @@ int celda_chain_sweep_z_gibbs(celda_chain *h, const int *ix, const double *u, in
 int celda_chain_sweep_z_em(celda_chain *h, int doSample);
 int celda_chain_iterate_em(celda_chain *h, const int *ix_y, const double *u_y, double *ll);
 /* ... or with the device Philox4x32-10 generator (key = seed; counter = item, sweep number, stream): the visiting
- * order is the argsort of per-item 64-bit keys, one uniform in (0,1) per visited item.  get_draws returns the order
+ * order is a keyed pseudo-random permutation computed item by item (a Feistel network over Philox with cycle walking,
+ * celda_b200/csrc/philox.cuh: no sort), one uniform in (0,1) per visited item.  get_draws returns the order
  * and uniforms the last sweep consumed (which = 0 y, 1 z), so a Philox run can be replayed in injection mode. */
 int celda_chain_seed(celda_chain *h, unsigned long long seed, unsigned long long stream);
 int celda_chain_sweep_y_philox(celda_chain *h, int doSample);
