@@ -21,6 +21,25 @@
 static SEXP slot(SEXP x, const char *n) { return R_do_slot(x, Rf_install(n)); }
 static int nlev(SEXP f) { return Rf_isFactor(f) ? Rf_nlevels(f) : -1; } /* -1 == "not a factor" in the C ABI */
 
+/* a modifiable copy of x as `type`, attributes (dim) kept: the closures below return updated copies, R arguments are
+ * never modified.  The caller PROTECTs the result. */
+static SEXP fresh(SEXP x, SEXPTYPE type) {
+    SEXP y = PROTECT(Rf_coerceVector(x, type));
+    if (y == x) y = Rf_duplicate(x);
+    UNPROTECT(1);
+    return y;
+}
+static SEXP named_list(int n, const char *const *names, SEXP *vals) {
+    SEXP out = PROTECT(Rf_allocVector(VECSXP, n)), nm = PROTECT(Rf_allocVector(STRSXP, n));
+    for (int k = 0; k < n; ++k) {
+        SET_VECTOR_ELT(out, k, vals[k]);
+        SET_STRING_ELT(nm, k, Rf_mkChar(names[k]));
+    }
+    Rf_setAttrib(out, R_NamesSymbol, nm);
+    UNPROTECT(2);
+    return out;
+}
+
 /* ---- src/matrixSumsSparse.cpp ---------------------------------------------------------------- */
 SEXP _celda_cuda_colSumByGroupSparse(SEXP counts, SEXP group, SEXP K) {
     int *dim = INTEGER(slot(counts, "Dim")), k = Rf_asInteger(K);
@@ -163,6 +182,67 @@ SEXP _celda_cuda_cG_CalcGibbsProbY(SEXP index, SEXP counts, SEXP nTSbyC, SEXP nb
     return probs;
 }
 
+/* ---- the sweeps at closure granularity (R/celda_C.R:620-756, R/celda_G.R:602-660) ---------------
+ * Same arguments and the same named list as the R closures; the draws the closure would take from R's generator are
+ * passed in: ix = sample(seq_len(n)), u = runif(n), drawn by the caller under its with_seed.
+ * `counts` is the dense matrix the closure indexes (nTSByC / nGByCP in celda_CG, as.matrix(counts) in celda_C / G). */
+SEXP _celda_cuda_cCCalcGibbsProbZ(SEXP counts, SEXP mCPByS, SEXP nGByCP, SEXP nByC, SEXP nCP, SEXP z, SEXP s, SEXP K,
+                                  SEXP nG, SEXP nM, SEXP alpha, SEXP beta, SEXP doSample, SEXP ix, SEXP u) {
+    int k = Rf_asInteger(K), nm = Rf_asInteger(nM);
+    SEXP cnt = PROTECT(Rf_coerceVector(counts, REALSXP)), byc = PROTECT(Rf_coerceVector(nByC, REALSXP));
+    SEXP ss = PROTECT(Rf_coerceVector(s, INTSXP)), ord = PROTECT(Rf_coerceVector(ix, INTSXP));
+    SEXP m = PROTECT(fresh(mCPByS, INTSXP)), n = PROTECT(fresh(nGByCP, REALSXP)), cp = PROTECT(fresh(nCP, REALSXP));
+    SEXP zz = PROTECT(fresh(z, INTSXP)), probs = PROTECT(Rf_allocMatrix(REALSXP, k, nm));
+    int rc = celda_cCCalcGibbsProbZ(REAL(cnt), INTEGER(m), Rf_ncols(m), REAL(n), REAL(byc), REAL(cp), INTEGER(zz),
+                                    INTEGER(ss), k, Rf_asInteger(nG), nm, Rf_asReal(alpha), Rf_asReal(beta),
+                                    Rf_asLogical(doSample), INTEGER(ord), REAL(u), REAL(probs));
+    static const char *const names[] = {"mCPByS", "nGByCP", "nCP", "z", "probs"};
+    SEXP vals[] = {m, n, cp, zz, probs};
+    SEXP out = named_list(5, names, vals);
+    UNPROTECT(9);
+    CHECK(rc);
+    return out;
+}
+
+SEXP _celda_cuda_cGCalcGibbsProbY(SEXP counts, SEXP nTSByC, SEXP nByTS, SEXP nGByTS, SEXP nByG, SEXP y, SEXP L, SEXP nG,
+                                  SEXP beta, SEXP delta, SEXP gamma, SEXP doSample, SEXP ix, SEXP u) {
+    int l = Rf_asInteger(L), ng = Rf_asInteger(nG);
+    SEXP cnt = PROTECT(Rf_coerceVector(counts, REALSXP)), byg = PROTECT(Rf_coerceVector(nByG, REALSXP));
+    SEXP ord = PROTECT(Rf_coerceVector(ix, INTSXP));
+    SEXP t = PROTECT(fresh(nTSByC, REALSXP)), ts = PROTECT(fresh(nByTS, REALSXP)), gt = PROTECT(fresh(nGByTS, INTSXP));
+    SEXP yy = PROTECT(fresh(y, INTSXP)), probs = PROTECT(Rf_allocMatrix(REALSXP, l, ng));
+    int rc = celda_cGCalcGibbsProbY(REAL(cnt), Rf_ncols(cnt), REAL(t), REAL(ts), INTEGER(gt), REAL(byg), INTEGER(yy), l, ng,
+                                    Rf_asReal(beta), Rf_asReal(delta), Rf_asReal(gamma), Rf_asLogical(doSample),
+                                    INTEGER(ord), REAL(u), REAL(probs));
+    static const char *const names[] = {"nTSByC", "nGByTS", "nByTS", "y", "probs"};
+    SEXP vals[] = {t, gt, ts, yy, probs};
+    SEXP out = named_list(5, names, vals);
+    UNPROTECT(8);
+    CHECK(rc);
+    return out;
+}
+
+/* .cCCalcEMProbZ: counts as a dgCMatrix (S4) or a dense matrix; nByC is not needed by the EM step (kept for the signature) */
+SEXP _celda_cuda_cCCalcEMProbZ(SEXP counts, SEXP mCPByS, SEXP nGByCP, SEXP nByC, SEXP nCP, SEXP z, SEXP s, SEXP K, SEXP nG,
+                               SEXP nM, SEXP alpha, SEXP beta, SEXP doSample) {
+    (void)nByC;
+    int k = Rf_asInteger(K), nm = Rf_asInteger(nM), sparse = IS_S4_OBJECT(counts);
+    SEXP cnt = PROTECT(sparse ? slot(counts, "x") : Rf_coerceVector(counts, REALSXP));
+    SEXP ss = PROTECT(Rf_coerceVector(s, INTSXP));
+    SEXP m = PROTECT(fresh(mCPByS, INTSXP)), n = PROTECT(fresh(nGByCP, REALSXP)), cp = PROTECT(fresh(nCP, REALSXP));
+    SEXP zz = PROTECT(fresh(z, INTSXP)), probs = PROTECT(Rf_allocMatrix(REALSXP, k, nm));
+    int rc = celda_cCCalcEMProbZ(Rf_asInteger(nG), nm, sparse ? INTEGER(slot(counts, "p")) : NULL,
+                                 sparse ? INTEGER(slot(counts, "i")) : NULL, REAL(cnt), INTEGER(m), Rf_ncols(m), REAL(n),
+                                 REAL(cp), INTEGER(zz), INTEGER(ss), k, Rf_asReal(alpha), Rf_asReal(beta),
+                                 Rf_asLogical(doSample), REAL(probs));
+    static const char *const names[] = {"mCPByS", "nGByCP", "nCP", "z", "probs"};
+    SEXP vals[] = {m, n, cp, zz, probs};
+    SEXP out = named_list(5, names, vals);
+    UNPROTECT(7);
+    CHECK(rc);
+    return out;
+}
+
 /* ---- log-likelihoods (R closures .cCGCalcLL / .cCCalcLL / .cGCalcLL) --------------------------- */
 SEXP _celda_cuda_cCGCalcLL(SEXP K, SEXP L, SEXP mCPByS, SEXP nTSByCP, SEXP nByG, SEXP nByTS, SEXP nGByTS, SEXP nS,
                            SEXP hyper /* alpha, beta, delta, gamma */) {
@@ -171,6 +251,32 @@ SEXP _celda_cuda_cCGCalcLL(SEXP K, SEXP L, SEXP mCPByS, SEXP nTSByCP, SEXP nByG,
     int rc = celda_cCGCalcLL(Rf_asInteger(K), Rf_asInteger(L), INTEGER(mCPByS), REAL(nTSByCP), REAL(nByG),
                              (int)XLENGTH(nByG), REAL(nByTS), INTEGER(g), Rf_asInteger(nS), h[0], h[1], h[2], h[3], &ll);
     UNPROTECT(1);
+    CHECK(rc);
+    return Rf_ScalarReal(ll);
+}
+
+/* .cCCalcLL(mCPByS, nGByCP, s, z, K, nS, nG, alpha, beta) R/celda_C.R:760-788 (s and z are unused by the formula) */
+SEXP _celda_cuda_cCCalcLL(SEXP mCPByS, SEXP nGByCP, SEXP s, SEXP z, SEXP K, SEXP nS, SEXP nG, SEXP alpha, SEXP beta) {
+    (void)s;
+    (void)z;
+    double ll = 0;
+    SEXP m = PROTECT(Rf_coerceVector(mCPByS, INTSXP)), n = PROTECT(Rf_coerceVector(nGByCP, REALSXP));
+    int rc = celda_cCCalcLL(INTEGER(m), REAL(n), Rf_asInteger(K), Rf_asInteger(nS), Rf_asInteger(nG), Rf_asReal(alpha),
+                            Rf_asReal(beta), &ll);
+    UNPROTECT(2);
+    CHECK(rc);
+    return Rf_ScalarReal(ll);
+}
+
+/* .cGCalcLL(nTSByC, nByTS, nByG, nGByTS, nM, nG, L, beta, delta, gamma) R/celda_G.R:664-702 */
+SEXP _celda_cuda_cGCalcLL(SEXP nTSByC, SEXP nByTS, SEXP nByG, SEXP nGByTS, SEXP nM, SEXP nG, SEXP L, SEXP beta, SEXP delta,
+                          SEXP gamma) {
+    double ll = 0;
+    SEXP t = PROTECT(Rf_coerceVector(nTSByC, REALSXP)), ts = PROTECT(Rf_coerceVector(nByTS, REALSXP));
+    SEXP g = PROTECT(Rf_coerceVector(nByG, REALSXP)), gt = PROTECT(Rf_coerceVector(nGByTS, INTSXP));
+    int rc = celda_cGCalcLL(REAL(t), REAL(ts), REAL(g), Rf_asInteger(nG), INTEGER(gt), (long long)Rf_asReal(nM),
+                            Rf_asInteger(L), Rf_asReal(beta), Rf_asReal(delta), Rf_asReal(gamma), &ll);
+    UNPROTECT(4);
     CHECK(rc);
     return Rf_ScalarReal(ll);
 }
@@ -293,6 +399,69 @@ SEXP _celda_cuda_chain_scan_margin(SEXP p) {
     return ans;
 }
 
+/* single sweeps on the handle: .cGCalcGibbsProbY / .cCCalcGibbsProbZ / .cCCalcEMProbZ with the tables resident;
+ * doSample = FALSE leaves the labels alone and only fills the probabilities (clusterProbability, the second-best
+ * labels of the 'split' initialisation) */
+SEXP _celda_cuda_chain_sweep_y(SEXP p, SEXP ix, SEXP u, SEXP doSample) {
+    CHECK(celda_chain_sweep_y(chain_of(p), INTEGER(ix), REAL(u), Rf_asLogical(doSample)));
+    return R_NilValue;
+}
+SEXP _celda_cuda_chain_sweep_z_gibbs(SEXP p, SEXP ix, SEXP u, SEXP doSample) {
+    CHECK(celda_chain_sweep_z_gibbs(chain_of(p), INTEGER(ix), REAL(u), Rf_asLogical(doSample)));
+    return R_NilValue;
+}
+SEXP _celda_cuda_chain_sweep_z_em(SEXP p, SEXP doSample) {
+    CHECK(celda_chain_sweep_z_em(chain_of(p), Rf_asLogical(doSample)));
+    return R_NilValue;
+}
+
+/* list(z = K x nM, y = L x nG) of the last sweeps' probabilities; a dimension of 0 skips that side (celda_C / celda_G) */
+SEXP _celda_cuda_chain_get_probs(SEXP p, SEXP K, SEXP nM, SEXP L, SEXP nG) {
+    int k = Rf_asInteger(K), nm = Rf_asInteger(nM), l = Rf_asInteger(L), ng = Rf_asInteger(nG);
+    SEXP pz = PROTECT(Rf_allocMatrix(REALSXP, k, nm)), py = PROTECT(Rf_allocMatrix(REALSXP, l, ng));
+    int rc = celda_chain_get_probs(chain_of(p), (k && nm) ? REAL(pz) : NULL, (l && ng) ? REAL(py) : NULL);
+    static const char *const names[] = {"z", "y"};
+    SEXP vals[] = {pz, py};
+    SEXP out = named_list(2, names, vals);
+    UNPROTECT(2);
+    CHECK(rc);
+    return out;
+}
+
+/* the count tables of the handle as .cCGDecomposeCounts / .cCDecomposeCounts / .cGDecomposeCounts return them
+ * (R/celda_CG.R:902-934); dimensions that do not apply to the handle's model are passed as 0 and come back empty */
+SEXP _celda_cuda_chain_get_tables(SEXP p, SEXP nG, SEXP nM, SEXP nS, SEXP K, SEXP L) {
+    int ng = Rf_asInteger(nG), nm = Rf_asInteger(nM), ns = Rf_asInteger(nS), k = Rf_asInteger(K), l = Rf_asInteger(L);
+    SEXP v[9];
+    v[0] = PROTECT(Rf_allocMatrix(INTSXP, k, ns));   /* mCPByS  */
+    v[1] = PROTECT(Rf_allocMatrix(REALSXP, l, nm));  /* nTSByC  */
+    v[2] = PROTECT(Rf_allocMatrix(REALSXP, l, k));   /* nTSByCP */
+    v[3] = PROTECT(Rf_allocMatrix(REALSXP, ng, k));  /* nGByCP  */
+    v[4] = PROTECT(Rf_allocVector(REALSXP, k));      /* nCP     */
+    v[5] = PROTECT(Rf_allocVector(REALSXP, nm));     /* nByC    */
+    v[6] = PROTECT(Rf_allocVector(REALSXP, ng));     /* nByG    */
+    v[7] = PROTECT(Rf_allocVector(REALSXP, l));      /* nByTS   */
+    v[8] = PROTECT(Rf_allocVector(INTSXP, l));       /* nGByTS  */
+    int rc = celda_chain_get_tables(chain_of(p), INTEGER(v[0]), REAL(v[1]), REAL(v[2]), REAL(v[3]), REAL(v[4]), REAL(v[5]),
+                                    REAL(v[6]), REAL(v[7]), INTEGER(v[8]));
+    static const char *const names[] = {"mCPByS", "nTSByC", "nTSByCP", "nGByCP", "nCP", "nByC", "nByG", "nByTS", "nGByTS"};
+    SEXP out = named_list(9, names, v);
+    UNPROTECT(9);
+    CHECK(rc);
+    return out;
+}
+
+/* which GPU the stateless entry points use; celdaGridSearch workers call it once with their share of the devices */
+SEXP _celda_cuda_set_device(SEXP device) {
+    CHECK(celda_cuda_set_device(Rf_asInteger(device)));
+    return R_NilValue;
+}
+SEXP _celda_cuda_device_count(void) {
+    int n = 0;
+    CHECK(celda_cuda_device_count(&n));
+    return Rf_ScalarInteger(n);
+}
+
 static const R_CallMethodDef CudaEntries[] = {
     {"_celda_cuda_colSumByGroupSparse", (DL_FUNC)&_celda_cuda_colSumByGroupSparse, 3},
     {"_celda_cuda_rowSumByGroupSparse", (DL_FUNC)&_celda_cuda_rowSumByGroupSparse, 3},
@@ -326,6 +495,18 @@ static const R_CallMethodDef CudaEntries[] = {
     {"_celda_cuda_chain_perplexity_resampled", (DL_FUNC)&_celda_cuda_chain_perplexity_resampled, 3},
     {"_celda_cuda_chain_set_scan_mode", (DL_FUNC)&_celda_cuda_chain_set_scan_mode, 2},
     {"_celda_cuda_chain_scan_margin", (DL_FUNC)&_celda_cuda_chain_scan_margin, 1},
+    {"_celda_cuda_cCCalcGibbsProbZ", (DL_FUNC)&_celda_cuda_cCCalcGibbsProbZ, 15},
+    {"_celda_cuda_cGCalcGibbsProbY", (DL_FUNC)&_celda_cuda_cGCalcGibbsProbY, 14},
+    {"_celda_cuda_cCCalcEMProbZ", (DL_FUNC)&_celda_cuda_cCCalcEMProbZ, 13},
+    {"_celda_cuda_cCCalcLL", (DL_FUNC)&_celda_cuda_cCCalcLL, 9},
+    {"_celda_cuda_cGCalcLL", (DL_FUNC)&_celda_cuda_cGCalcLL, 10},
+    {"_celda_cuda_chain_sweep_y", (DL_FUNC)&_celda_cuda_chain_sweep_y, 4},
+    {"_celda_cuda_chain_sweep_z_gibbs", (DL_FUNC)&_celda_cuda_chain_sweep_z_gibbs, 4},
+    {"_celda_cuda_chain_sweep_z_em", (DL_FUNC)&_celda_cuda_chain_sweep_z_em, 2},
+    {"_celda_cuda_chain_get_probs", (DL_FUNC)&_celda_cuda_chain_get_probs, 5},
+    {"_celda_cuda_chain_get_tables", (DL_FUNC)&_celda_cuda_chain_get_tables, 6},
+    {"_celda_cuda_set_device", (DL_FUNC)&_celda_cuda_set_device, 1},
+    {"_celda_cuda_device_count", (DL_FUNC)&_celda_cuda_device_count, 0},
     {NULL, NULL, 0}};
 
 /* called from R_init_celda (src/RcppExports.cpp:339-342) next to the Rcpp-generated table */

@@ -16,24 +16,41 @@ typedef enum { FALSE = 0, TRUE } Rboolean;
 
 #define NILSXP 0
 #define SYMSXP 1
+#define CHARSXP 9
+#define LGLSXP 10
 #define INTSXP 13
 #define REALSXP 14
+#define STRSXP 16
 #define VECSXP 19
 #define EXTPTRSXP 22
 #define S4SXP 25
 
 extern SEXP R_NilValue;
+extern SEXP R_NamesSymbol;
 
 int *INTEGER(SEXP x);
 double *REAL(SEXP x);
 R_xlen_t XLENGTH(SEXP x);
 SEXP SET_VECTOR_ELT(SEXP x, R_xlen_t i, SEXP v);
 SEXP VECTOR_ELT(SEXP x, R_xlen_t i);
+void SET_STRING_ELT(SEXP x, R_xlen_t i, SEXP v);
+SEXP STRING_ELT(SEXP x, R_xlen_t i);
+const char *R_CHAR(SEXP x);
+#define CHAR(x) R_CHAR(x)
+int *LOGICAL(SEXP x);
 
 SEXP Rf_allocVector(SEXPTYPE type, R_xlen_t n);
 SEXP Rf_allocMatrix(SEXPTYPE type, int nrow, int ncol);
 SEXP Rf_coerceVector(SEXP x, SEXPTYPE type);
 SEXP Rf_ScalarReal(double v);
+SEXP Rf_ScalarInteger(int v);
+SEXP Rf_mkChar(const char *s);
+SEXP Rf_duplicate(SEXP x);
+SEXP Rf_setAttrib(SEXP x, SEXP name, SEXP value);
+SEXP Rf_getAttrib(SEXP x, SEXP name);
+int Rf_asLogical(SEXP x);
+Rboolean Rf_isMatrix(SEXP x);
+int IS_S4_OBJECT(SEXP x);
 SEXP Rf_install(const char *name);
 SEXP R_do_slot(SEXP obj, SEXP name);
 int Rf_asInteger(SEXP x);

@@ -26,12 +26,15 @@ struct rstub_sexp {
     int nlevels;         /* >= 0: an R factor with that many levels */
     char sym[32];        /* SYMSXP */
     struct rstub_slot *slots;
+    SEXP names;          /* the "names" attribute (a STRSXP) */
     R_CFinalizer_t fin;
     struct rstub_sexp *next_alloc;
 };
 
-static struct rstub_sexp nil_value = {NILSXP, 0, NULL, 0, 0, 0, -1, "", NULL, NULL, NULL};
+static struct rstub_sexp nil_value = {NILSXP, 0, NULL, 0, 0, 0, -1, "", NULL, NULL, NULL, NULL};
+static struct rstub_sexp names_symbol = {SYMSXP, 0, NULL, 0, 0, 0, -1, "names", NULL, NULL, NULL, NULL};
 SEXP R_NilValue = &nil_value;
+SEXP R_NamesSymbol = &names_symbol;
 
 static struct rstub_sexp *arena = NULL;
 static int protect_depth = 0, protect_max = 0, protect_underflow = 0;
@@ -69,12 +72,13 @@ SEXP VECTOR_ELT(SEXP x, R_xlen_t i) {
 }
 
 SEXP Rf_allocVector(SEXPTYPE type, R_xlen_t n) {
-    size_t w = type == INTSXP ? sizeof(int) : type == REALSXP ? sizeof(double) : type == VECSXP ? sizeof(SEXP) : 0;
+    size_t w = (type == INTSXP || type == LGLSXP) ? sizeof(int) : type == REALSXP ? sizeof(double)
+               : (type == VECSXP || type == STRSXP) ? sizeof(SEXP) : 0;
     if (!w || n < 0) Rf_error("allocVector: unsupported type %u or negative length", type);
     SEXP s = node(type);
     s->length = n;
     s->data = calloc((size_t)n + 1, w);
-    if (type == VECSXP)
+    if (type == VECSXP || type == STRSXP)
         for (R_xlen_t i = 0; i < n; ++i) ((SEXP *)s->data)[i] = R_NilValue;
     return s;
 }
@@ -91,11 +95,13 @@ SEXP Rf_coerceVector(SEXP x, SEXPTYPE type) {
     if (x->type == REALSXP && type == INTSXP) {
         SEXP s = Rf_allocVector(INTSXP, x->length);
         for (R_xlen_t i = 0; i < x->length; ++i) ((int *)s->data)[i] = (int)((double *)x->data)[i];
+        s->has_dim = x->has_dim, s->nrow = x->nrow, s->ncol = x->ncol; /* attributes are kept */
         return s;
     }
-    if (x->type == INTSXP && type == REALSXP) {
+    if ((x->type == INTSXP || x->type == LGLSXP) && type == REALSXP) {
         SEXP s = Rf_allocVector(REALSXP, x->length);
         for (R_xlen_t i = 0; i < x->length; ++i) ((double *)s->data)[i] = (double)((int *)x->data)[i];
+        s->has_dim = x->has_dim, s->nrow = x->nrow, s->ncol = x->ncol;
         return s;
     }
     Rf_error("coerceVector: unsupported conversion %u -> %u", x->type, type);
@@ -105,6 +111,58 @@ SEXP Rf_ScalarReal(double v) {
     ((double *)s->data)[0] = v;
     return s;
 }
+SEXP Rf_ScalarInteger(int v) {
+    SEXP s = Rf_allocVector(INTSXP, 1);
+    ((int *)s->data)[0] = v;
+    return s;
+}
+SEXP Rf_mkChar(const char *str) {
+    SEXP s = node(CHARSXP);
+    s->length = (R_xlen_t)strlen(str);
+    s->data = malloc(strlen(str) + 1);
+    strcpy((char *)s->data, str);
+    return s;
+}
+const char *R_CHAR(SEXP x) { need(x, CHARSXP, "CHAR()"); return (const char *)x->data; }
+void SET_STRING_ELT(SEXP x, R_xlen_t i, SEXP v) {
+    need(x, STRSXP, "SET_STRING_ELT()");
+    need(v, CHARSXP, "SET_STRING_ELT() value");
+    if (i < 0 || i >= x->length) Rf_error("SET_STRING_ELT(): index out of range");
+    ((SEXP *)x->data)[i] = v;
+}
+SEXP STRING_ELT(SEXP x, R_xlen_t i) {
+    need(x, STRSXP, "STRING_ELT()");
+    if (i < 0 || i >= x->length) Rf_error("STRING_ELT(): index out of range");
+    return ((SEXP *)x->data)[i];
+}
+int *LOGICAL(SEXP x) { need(x, LGLSXP, "LOGICAL()"); return (int *)x->data; }
+SEXP Rf_duplicate(SEXP x) {
+    if (x->type != INTSXP && x->type != REALSXP && x->type != LGLSXP) Rf_error("duplicate: unsupported type %u", x->type);
+    SEXP s = Rf_allocVector(x->type, x->length);
+    memcpy(s->data, x->data, (size_t)x->length * (x->type == REALSXP ? sizeof(double) : sizeof(int)));
+    s->has_dim = x->has_dim, s->nrow = x->nrow, s->ncol = x->ncol, s->nlevels = x->nlevels;
+    return s;
+}
+SEXP Rf_setAttrib(SEXP x, SEXP name, SEXP value) {
+    need(name, SYMSXP, "setAttrib()");
+    if (strcmp(name->sym, "names")) Rf_error("setAttrib: only \"names\" is supported");
+    need(value, STRSXP, "setAttrib(names)");
+    if (value->length != x->length) Rf_error("'names' attribute must be the same length as the vector");
+    x->names = value;
+    return value;
+}
+SEXP Rf_getAttrib(SEXP x, SEXP name) {
+    need(name, SYMSXP, "getAttrib()");
+    return (!strcmp(name->sym, "names") && x->names) ? x->names : R_NilValue;
+}
+int Rf_asLogical(SEXP x) {
+    if (x->length < 1) Rf_error("asLogical: zero-length argument");
+    if (x->type == LGLSXP || x->type == INTSXP) return ((int *)x->data)[0] != 0;
+    if (x->type == REALSXP) return ((double *)x->data)[0] != 0.0;
+    Rf_error("asLogical: unsupported type %u", x->type);
+}
+Rboolean Rf_isMatrix(SEXP x) { return x->has_dim ? TRUE : FALSE; }
+int IS_S4_OBJECT(SEXP x) { return x->type == S4SXP; }
 SEXP Rf_install(const char *name) {
     SEXP s = node(SYMSXP);
     snprintf(s->sym, sizeof(s->sym), "%s", name);
@@ -118,7 +176,7 @@ SEXP R_do_slot(SEXP obj, SEXP name) {
 }
 int Rf_asInteger(SEXP x) {
     if (x->length < 1) Rf_error("asInteger: zero-length argument");
-    if (x->type == INTSXP) return ((int *)x->data)[0];
+    if (x->type == INTSXP || x->type == LGLSXP) return ((int *)x->data)[0];
     if (x->type == REALSXP) return (int)((double *)x->data)[0];
     Rf_error("asInteger: unsupported type %u", x->type);
 }
@@ -194,6 +252,12 @@ SEXP rstub_real(R_xlen_t n, const double *v) {
     if (n) memcpy(s->data, v, sizeof(double) * (size_t)n);
     return s;
 }
+SEXP rstub_logical(int v) {
+    SEXP s = Rf_allocVector(LGLSXP, 1);
+    ((int *)s->data)[0] = v;
+    return s;
+}
+const char *rstub_name(SEXP x, long long i) { return x->names ? R_CHAR(((SEXP *)x->names->data)[i]) : ""; }
 void rstub_set_dim(SEXP x, int nrow, int ncol) { x->has_dim = 1; x->nrow = nrow; x->ncol = ncol; }
 void rstub_set_levels(SEXP x, int nlevels) { x->nlevels = nlevels; }
 SEXP rstub_s4(void) { return node(S4SXP); }
@@ -226,9 +290,17 @@ typedef SEXP (*F2)(SEXP, SEXP);
 typedef SEXP (*F3)(SEXP, SEXP, SEXP);
 typedef SEXP (*F4)(SEXP, SEXP, SEXP, SEXP);
 typedef SEXP (*F5)(SEXP, SEXP, SEXP, SEXP, SEXP);
+typedef SEXP (*F6)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+typedef SEXP (*F7)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 typedef SEXP (*F8)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 typedef SEXP (*F9)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+typedef SEXP (*F10)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+typedef SEXP (*F11)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 typedef SEXP (*F12)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+typedef SEXP (*F13)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+typedef SEXP (*F14)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+typedef SEXP (*F15)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
+typedef SEXP (*F16)(SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP, SEXP);
 
 /* .Call(name, ...): looks the routine up in the registered table, checks the arity like R does, runs it under a
  * setjmp that Rf_error returns to.  NULL + message in `err` on an R error. */
@@ -258,9 +330,17 @@ SEXP rstub_call(const char *name, int nargs, SEXP *a, char *err, int errlen) {
         case 3: out = ((F3)f)(a[0], a[1], a[2]); break;
         case 4: out = ((F4)f)(a[0], a[1], a[2], a[3]); break;
         case 5: out = ((F5)f)(a[0], a[1], a[2], a[3], a[4]); break;
+        case 6: out = ((F6)f)(a[0], a[1], a[2], a[3], a[4], a[5]); break;
+        case 7: out = ((F7)f)(a[0], a[1], a[2], a[3], a[4], a[5], a[6]); break;
         case 8: out = ((F8)f)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]); break;
         case 9: out = ((F9)f)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8]); break;
+        case 10: out = ((F10)f)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9]); break;
+        case 11: out = ((F11)f)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10]); break;
         case 12: out = ((F12)f)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11]); break;
+        case 13: out = ((F13)f)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12]); break;
+        case 14: out = ((F14)f)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13]); break;
+        case 15: out = ((F15)f)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14]); break;
+        case 16: out = ((F16)f)(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13], a[14], a[15]); break;
         default: snprintf(err, errlen, "rstub_call: arity %d not wired", nargs); break;
         }
         if (out && protect_depth != depth) {

@@ -35,7 +35,8 @@ class RStub:
             ("rstub_protect_balance", C.c_int, []), ("rstub_n_routines", C.c_int, []),
             ("rstub_routine_name", C.c_char_p, [C.c_int]), ("rstub_routine_nargs", C.c_int, [C.c_int]),
             ("rstub_call", vp, [C.c_char_p, C.c_int, C.POINTER(vp), C.c_char_p, C.c_int]), ("rstub_reset", C.c_int, []),
-            ("celda_cuda_register", None, [vp]),
+            ("celda_cuda_register", None, [vp]), ("rstub_logical", vp, [C.c_int]),
+            ("rstub_name", C.c_char_p, [vp, C.c_longlong]),
         ]:
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
@@ -80,6 +81,9 @@ class RStub:
             self.L.rstub_set_slot(s, name.encode(), v)
         return s
 
+    def logical(self, v):
+        return self.L.rstub_logical(int(bool(v)))
+
     @property
     def NULL(self):
         return self.L.rstub_nil()
@@ -87,7 +91,9 @@ class RStub:
     def value(self, s):
         t, n = self.L.rstub_type(s), self.L.rstub_length(s)
         if t == VECSXP:
-            return [self.value(self.L.rstub_vector_elt(s, k)) for k in range(n)]
+            vals = [self.value(self.L.rstub_vector_elt(s, k)) for k in range(n)]
+            names = [self.L.rstub_name(s, k).decode() for k in range(n)]
+            return dict(zip(names, vals)) if all(names) else vals
         if t not in (INTSXP, REALSXP):
             return s  # NULL, external pointer
         ct = C.c_int if t == INTSXP else C.c_double
@@ -110,31 +116,54 @@ class RStub:
                 for k in range(self.L.rstub_n_routines())}
 
 
-@pytest.fixture(scope="module")
-def R(tmp_path_factory):
+def _build_shim(tmpdir, mock=False):
+    """The shim + the R API miniature as one shared object on top of libcelda_cuda.so; with mock=True the closure-level
+    entry points resolve to tests/r_stub/mock_celda_cuda.c (the CPU oracle) linked in front of the product library."""
     from celda_b200 import _lib
     so_dir = os.path.dirname(_lib.build())
-    out = str(tmp_path_factory.mktemp("rshim") / "celda_shim_test.so")
-    cmd = ["gcc", "-O1", "-g", "-Wall", "-Wextra", "-Werror", "-Wno-cast-function-type", "-shared", "-fPIC",
-           "-I" + os.path.join(STUB, "include"), "-I" + os.path.join(ROOT, "include"), "-o", out, SHIM,
-           os.path.join(STUB, "rstub.c"), "-L" + so_dir, "-l:libcelda_cuda.so", "-Wl,-rpath," + so_dir]
-    r = subprocess.run(cmd, capture_output=True, text=True)
+    warn = ["-O1", "-g", "-Wall", "-Wextra", "-Werror", "-Wno-cast-function-type", "-shared", "-fPIC"]
+    libs = ["-L" + so_dir, "-l:libcelda_cuda.so", "-Wl,-rpath," + so_dir]
+    if mock:
+        odir = os.path.join(ROOT, "oracle")
+        subprocess.check_call(["make", "-s", "-C", odir, "all"])
+        mock_so = os.path.join(tmpdir, "libmock_celda_cuda.so")
+        r = subprocess.run(["gcc"] + warn + ["-I" + os.path.join(ROOT, "include"), "-o", mock_so,
+                            os.path.join(STUB, "mock_celda_cuda.c"), "-L" + odir, "-l:libcelda_oracle.so",
+                            "-Wl,-rpath," + odir], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        libs = ["-L" + tmpdir, "-l:libmock_celda_cuda.so", "-Wl,-rpath," + tmpdir] + libs
+    out = os.path.join(tmpdir, "celda_shim_test.so")
+    r = subprocess.run(["gcc"] + warn + ["-I" + os.path.join(STUB, "include"), "-I" + os.path.join(ROOT, "include"), "-o", out,
+                        SHIM, os.path.join(STUB, "rstub.c")] + libs, capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    stub = RStub(out)
+    return RStub(out)
+
+
+@pytest.fixture(scope="module")
+def R(tmp_path_factory):
+    stub = _build_shim(str(tmp_path_factory.mktemp("rshim")))
+    yield stub
+    stub.L.rstub_reset()
+
+
+@pytest.fixture(scope="module")
+def Rmock(tmp_path_factory):
+    stub = _build_shim(str(tmp_path_factory.mktemp("rshim_mock")), mock=True)
+    stub.L.mock_celda_cuda_calls.restype = C.c_int
     yield stub
     stub.L.rstub_reset()
 
 
 def _shim_definitions():
     src = re.sub(r"/\*.*?\*/", "", open(SHIM).read(), flags=re.S)
-    return {m.group(1): len([a for a in m.group(2).split(",") if a.strip()])
+    return {m.group(1): len([a for a in m.group(2).split(",") if a.strip() not in ("", "void")])
             for m in re.finditer(r"^SEXP\s+(_\w+)\s*\(([^)]*)\)\s*\{", src, flags=re.M)}
 
 
 def test_shim_compiles_and_registers_every_routine(R):
     """-Wall -Wextra -Werror against include/celda_cuda.h, and the R_CallMethodDef table agrees with the definitions."""
     defs, table = _shim_definitions(), R.routines()
-    assert len(defs) >= 30
+    assert len(defs) >= 44
     assert table == defs  # same names, and numArgs equals each definition's parameter count
     # the dense natives keep the .Call names of the reference (NAMESPACE useDynLib / src/RcppExports.cpp:308-337)
     for name in ("_rowSumByGroup", "_colSumByGroup", "_rowSumByGroupChange", "_colSumByGroupChange", "_perplexityG",
@@ -176,6 +205,103 @@ def test_library_status_becomes_an_R_error_without_a_device(R):
         R.call("_celda_cuda_colSumByGroupSparse", R.matrix(mat), R.integer(lab), R.integer([2]))
     with pytest.raises(RuntimeError, match="wrong SEXP type"):
         R.call("_celda_cuda_chain_loglik", R.integer([1]))  # not an external pointer
+
+
+# ---------------------------------------------------------- closures through .Call, answered by the CPU oracle (mock)
+def _same(got, want, names):
+    assert list(got) == names  # the reference's list, in the reference's order
+    for k in names:
+        assert np.array_equal(got[k], want[k]), k
+
+
+def test_gibbs_closures_through_dotCall_marshal_like_the_reference(Rmock, oracle, gold_cg):
+    """.cCCalcGibbsProbZ / .cGCalcGibbsProbY as celda_CG calls them (R/celda_CG.R:566-585, 544-563): same arguments, same
+    named list, arguments left untouched.  The library side is the mock (CPU oracle), so this pins the shim only."""
+    from oracle.oracle import dense_to_csc
+    counts, s, K, L = gold_cg["counts"], gold_cg["s"], 5, 10
+    nG, nM = counts.shape
+    rng = np.random.default_rng(11)
+    z, y = rng.integers(1, K + 1, nM).astype(np.int32), rng.integers(1, L + 1, nG).astype(np.int32)
+    p = oracle.cCGDecomposeCounts(dense_to_csc(counts), s, z, y, K, L)
+    ix, u = rng.permutation(nM).astype(np.int32) + 1, rng.random(nM)
+    n0 = Rmock.L.mock_celda_cuda_calls()
+    for doSample in (True, False):
+        want = oracle.cCCalcGibbsProbZ(p["nTSByC"], p["mCPByS"], p["nTSByCP"], p["nByC"], p["nCP"], z, s, K, L, nM, 1.0,
+                                       0.7, ix, u, doSample=doSample)
+        args = [Rmock.matrix(p["nTSByC"]), Rmock.matrix(p["mCPByS"]), Rmock.matrix(p["nTSByCP"]), Rmock.numeric(p["nByC"]),
+                Rmock.numeric(p["nCP"]), Rmock.integer(z), Rmock.integer(s), Rmock.integer([K]), Rmock.integer([L]),
+                Rmock.integer([nM]), Rmock.numeric([1.0]), Rmock.numeric([0.7]), Rmock.logical(doSample),
+                Rmock.integer(ix), Rmock.numeric(u)]
+        got = Rmock.call("_celda_cuda_cCCalcGibbsProbZ", *args)
+        _same(got, want, ["mCPByS", "nGByCP", "nCP", "z", "probs"])
+        assert got["probs"].shape == (K, nM) and got["mCPByS"].dtype == np.int32
+        assert (got["z"] != z).any() == doSample
+        # R semantics: the caller's objects are not modified
+        assert np.array_equal(Rmock.value(args[1]), p["mCPByS"]) and np.array_equal(Rmock.value(args[5]), z)
+        assert np.array_equal(Rmock.value(args[2]), p["nTSByCP"]) and np.array_equal(Rmock.value(args[4]), p["nCP"])
+    # integer-typed tables (colSumByGroup of an integer matrix) are accepted and coerced
+    got = Rmock.call("_celda_cuda_cCCalcGibbsProbZ", args[0], args[1], Rmock.matrix(p["nTSByCP"].astype(np.int32)),
+                     Rmock.integer(p["nByC"]), Rmock.integer(p["nCP"]), *args[5:12], Rmock.logical(True), *args[13:])
+    want = oracle.cCCalcGibbsProbZ(p["nTSByC"], p["mCPByS"], p["nTSByCP"], p["nByC"], p["nCP"], z, s, K, L, nM, 1.0, 0.7, ix, u)
+    _same(got, want, ["mCPByS", "nGByCP", "nCP", "z", "probs"])
+
+    ixy, uy = rng.permutation(nG).astype(np.int32) + 1, rng.random(nG)
+    want = oracle.cGCalcGibbsProbY(p["nGByCP"], p["nTSByCP"], p["nByTS"], p["nGByTS"], p["nByG"], y, L, nG, 0.9, 1.1, 1.3,
+                                   ixy, uy)
+    args = [Rmock.matrix(p["nGByCP"]), Rmock.matrix(p["nTSByCP"]), Rmock.numeric(p["nByTS"]), Rmock.numeric(p["nGByTS"]),
+            Rmock.numeric(p["nByG"]), Rmock.integer(y), Rmock.integer([L]), Rmock.integer([nG]), Rmock.numeric([0.9]),
+            Rmock.numeric([1.1]), Rmock.numeric([1.3]), Rmock.logical(True), Rmock.integer(ixy), Rmock.numeric(uy)]
+    got = Rmock.call("_celda_cuda_cGCalcGibbsProbY", *args)
+    _same(got, want, ["nTSByC", "nGByTS", "nByTS", "y", "probs"])
+    assert got["probs"].shape == (L, nG) and got["nGByTS"].dtype == np.int32 and (got["y"] != y).any()
+    assert np.array_equal(Rmock.value(args[1]), p["nTSByCP"]) and np.array_equal(Rmock.value(args[5]), y)
+    assert Rmock.L.mock_celda_cuda_calls() == n0 + 4  # the closure entry points resolved to the mock, not the GPU library
+
+
+def test_em_closure_and_loglik_shims_marshal_like_the_reference(Rmock, oracle, gold_c, gold_g):
+    from oracle.oracle import dense_to_csc
+    counts, s, K = gold_c["counts"], gold_c["s_mod"], 10
+    nG, nM = counts.shape
+    z = np.random.default_rng(4).integers(1, K + 1, nM).astype(np.int32)
+    O = dense_to_csc(counts)
+    p = oracle.cCDecomposeCounts(O, s, z, K)
+    tail = [Rmock.integer(z), Rmock.integer(s), Rmock.integer([K]), Rmock.integer([nG]), Rmock.integer([nM]),
+            Rmock.numeric([1.0]), Rmock.numeric([1.0]), Rmock.logical(True)]
+    head = [Rmock.matrix(p["mCPByS"]), Rmock.matrix(p["nGByCP"]), Rmock.numeric(p["nByC"]), Rmock.numeric(p["nCP"])]
+    want = oracle.cCCalcEMProbZ(O, p["mCPByS"], p["nGByCP"], p["nByC"], p["nCP"], z, s, K, nG, nM, 1.0, 1.0)
+    for cnt in (Rmock.dgCMatrix(counts), Rmock.matrix(counts.astype(np.float64)), Rmock.matrix(counts.astype(np.int32))):
+        got = Rmock.call("_celda_cuda_cCCalcEMProbZ", cnt, *head, *tail)
+        assert list(got) == ["mCPByS", "nGByCP", "nCP", "z", "probs"]
+        for k in ("mCPByS", "nGByCP", "nCP", "z"):
+            assert np.array_equal(got[k], want[k]), k
+        assert np.allclose(got["probs"], want["probs"], rtol=1e-12)  # sparse and dense products add in different orders
+    assert np.array_equal(Rmock.value(tail[0]), z)
+    ll = Rmock.call("_celda_cuda_cCCalcLL", head[0], head[1], tail[1], tail[0], Rmock.integer([K]),
+                    Rmock.integer([p["nS"]]), Rmock.integer([nG]), Rmock.numeric([1.0]), Rmock.numeric([1.0]))[0]
+    assert ll == oracle.cCCalcLL(p["mCPByS"], p["nGByCP"], K, p["nS"], nG, 1.0, 1.0)
+
+    counts, L = gold_g["counts"], 10
+    nG, nM = counts.shape
+    y = np.random.default_rng(5).integers(1, L + 1, nG).astype(np.int32)
+    q = oracle.cGDecomposeCounts(dense_to_csc(counts), y, L)
+    ll = Rmock.call("_celda_cuda_cGCalcLL", Rmock.matrix(q["nTSByC"]), Rmock.numeric(q["nByTS"]), Rmock.numeric(q["nByG"]),
+                    Rmock.numeric(q["nGByTS"]), Rmock.integer([nM]), Rmock.integer([nG]), Rmock.integer([L]),
+                    Rmock.numeric([1.0]), Rmock.numeric([1.0]), Rmock.numeric([1.0]))[0]
+    assert ll == oracle.cGCalcLL(q["nTSByC"], q["nByTS"], q["nByG"], q["nGByTS"], nM, nG, L, 1.0, 1.0, 1.0)
+
+
+def test_closure_errors_surface_as_R_errors(Rmock, oracle, gold_cg):
+    """A status from the library (here: the oracle's own argument check) becomes an R error after the PROTECT stack is
+    balanced."""
+    counts, s = gold_cg["counts"], gold_cg["s"]
+    nG, nM = counts.shape
+    bad = [Rmock.matrix(np.zeros((3, nM))), Rmock.matrix(np.zeros((2, int(s.max())), np.int32)), Rmock.matrix(np.zeros((3, 2))),
+           Rmock.numeric(np.zeros(nM)), Rmock.numeric(np.zeros(2)), Rmock.integer(np.full(nM, 7)), Rmock.integer(s),
+           Rmock.integer([2]), Rmock.integer([3]), Rmock.integer([nM]), Rmock.numeric([1.0]), Rmock.numeric([1.0]),
+           Rmock.logical(True), Rmock.integer(np.arange(1, nM + 1)), Rmock.numeric(np.full(nM, 0.5))]
+    with pytest.raises(RuntimeError):
+        Rmock.call("_celda_cuda_cCCalcGibbsProbZ", *bad)  # z = 7 with K = 2
+    assert Rmock.L.rstub_protect_balance() == 0
 
 
 # ------------------------------------------------------------------------------------------------------- GPU
