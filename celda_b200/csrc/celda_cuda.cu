@@ -867,8 +867,8 @@ int chain_check_em_flag(celda_chain* h) {
     return 0;
 }
 
-// Philox mode: visiting order (argsort of per-item 64-bit keys) and one uniform per visited item, generated on
-// the device into the chain's ix / u staging buffers.
+// Philox mode: visiting order (philox_order, a keyed permutation evaluated item by item: philox.cuh) and one uniform
+// per visited item, generated by one kernel into the chain's ix / u staging buffers.
 int chain_philox_draws(celda_chain* h, long long n, int* d_ix, double* d_u) {
     if (!h->ph_seeded) return fail("philox mode: call celda_chain_seed first");
     k_philox_draws<<<grid_for(n, 256, h->sms), 256, 0, h->st>>>(n, philox_order_bits((unsigned long long)n), (unsigned)h->ph_seed,
