@@ -160,3 +160,34 @@ def test_celda_C_default_pipeline_reaches_the_reference_fit(oracle, obackend, go
     ref = float(gold_c["finalLogLik"])  # celdaCMod
     assert abs(r["finalLogLik"] - ref) <= 1e-12 * abs(ref)
     assert same_partition(r["z"], gold_c["z"])
+
+
+def test_grid_of_default_pipelines_reaches_or_beats_the_reference_grid(oracle, obackend, host_order, gold_cg, gold_grid):
+    """The reference's stored celdaGridSearch result on celdaCGSim (celdaCGGridSearchRes: K = 4..6 x L = 9..11, one
+    model each): for every (K, L) the better of two default-pipeline chains (seeds 12345 and 5, device-generator draws)
+    is at least as likely as the reference's model, and for the six points with K <= 5 it IS the reference's model
+    (same log-likelihood to 1e-12)."""
+    from split_oracle_backend import OracleOpsCG
+    counts, s = cb.CSC.from_dense(gold_cg["counts"]), gold_cg["s"]
+
+    def chain(K, L, seed):
+        rng = np.random.Generator(np.random.PCG64(seed))
+        z = split.initializeSplitZ(counts, K, alpha=1.0, beta=1.0, rng=rng, backend=obackend)
+        y = split.initializeSplitY(counts, L, beta=1.0, delta=1.0, gamma=1.0, rng=rng, backend=obackend)
+
+        def draws(it, rng_, nG, nM):
+            iy, uy = host_order(nG, seed=seed, sweep=2 * (it - 1), stream=0, uniforms=True)
+            iz, uz = host_order(nM, seed=seed, sweep=2 * (it - 1) + 1, stream=0, uniforms=True)
+            return iy[0], uy[0], iz[0], uz[0]
+
+        return split.run_chain_CG_with_splits(OracleOpsCG(oracle, counts, s, K, L, z, y), counts, K, L, draws, rng,
+                                              obackend, maxIter=50, stopIter=10, splitOnIter=10, splitOnLast=True)
+
+    exact = 0
+    for K, L, ref in zip(gold_grid["K"], gold_grid["L"], gold_grid["finalLogLik"]):
+        best = max(chain(int(K), int(L), seed)["finalLogLik"] for seed in (12345, 5))
+        assert best >= ref - 1e-9 * abs(ref), (K, L, best, ref)
+        same = abs(best - ref) <= 1e-12 * abs(ref)
+        exact += same
+        assert same or K == 6, (K, L, best, ref)
+    assert exact == 6
