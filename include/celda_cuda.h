@@ -130,7 +130,11 @@ int celda_cCCalcEMProbZ(int nG, long long nM, const int *p, const int *i, const 
 typedef struct celda_chain celda_chain;
 enum { CELDA_MODEL_CG = 0, CELDA_MODEL_C = 1, CELDA_MODEL_G = 2 };
 
-/* Upload the count matrix (integrality-checked, narrowed to int32) and build its gene-major twin. */
+/* Upload the count matrix (integrality-checked, narrowed to int32) and build its gene-major twin.
+ * Range: the per-entry tables (nTSByC, nGByCP, nTSByCP, nByC) are int32 on the device, the totals (nCP, nByG, nByTS)
+ * int64: a cell's total count and every (gene or module, population) total must stay below 2^31 -- the matrix total
+ * may exceed it (configs[2]: 5.5e9 counts over 50 populations).  The reference's dgCMatrix path holds these tables
+ * as doubles; its integer-matrix path has the same 2^31 bound (R integer overflow). */
 int celda_chain_create(celda_chain **out, int device, int model, int nG, int nM, const int *p, const int *i,
                        const double *x, const int *s /* 1-based sample labels, NULL for celda_G */, int nS, int K,
                        int L, double alpha, double beta, double delta, double gamma);
