@@ -73,6 +73,23 @@ void *R_ExternalPtrAddr(SEXP s);
 void R_ClearExternalPtr(SEXP s);
 void R_RegisterCFinalizerEx(SEXP s, R_CFinalizer_t fun, Rboolean onexit);
 
+int Rf_length(SEXP x);
+#define LENGTH(x) Rf_length(x)
+extern int R_NaInt;
+#define NA_INTEGER R_NaInt
+
+/* R's short names (Rinternals.h without R_NO_REMAP): what the reference's own C sources use */
+#ifndef R_NO_REMAP
+#define error(...) Rf_error(__VA_ARGS__)
+#define allocMatrix(t, r, c) Rf_allocMatrix(t, r, c)
+#define allocVector(t, n) Rf_allocVector(t, n)
+#define isFactor(x) Rf_isFactor(x)
+#define nlevels(x) Rf_nlevels(x)
+#define nrows(x) Rf_nrows(x)
+#define ncols(x) Rf_ncols(x)
+#define length(x) Rf_length(x)
+#endif
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,6 +35,7 @@ static struct rstub_sexp nil_value = {NILSXP, 0, NULL, 0, 0, 0, -1, "", NULL, NU
 static struct rstub_sexp names_symbol = {SYMSXP, 0, NULL, 0, 0, 0, -1, "names", NULL, NULL, NULL, NULL};
 SEXP R_NilValue = &nil_value;
 SEXP R_NamesSymbol = &names_symbol;
+int R_NaInt = (-2147483647 - 1);
 
 static struct rstub_sexp *arena = NULL;
 static int protect_depth = 0, protect_max = 0, protect_underflow = 0;
@@ -186,6 +187,7 @@ double Rf_asReal(SEXP x) {
     if (x->type == INTSXP) return (double)((int *)x->data)[0];
     Rf_error("asReal: unsupported type %u", x->type);
 }
+int Rf_length(SEXP x) { return (int)x->length; }
 int Rf_nrows(SEXP x) { return x->has_dim ? x->nrow : (int)x->length; }
 int Rf_ncols(SEXP x) { return x->has_dim ? x->ncol : 1; }
 int Rf_nlevels(SEXP x) { return x->nlevels < 0 ? 0 : x->nlevels; }
@@ -353,6 +355,22 @@ SEXP rstub_call(const char *name, int nargs, SEXP *a, char *err, int errlen) {
         out = NULL;
     }
     err_jmp = outer;
+    return out;
+}
+
+/* the same for a routine given by address (a library that does not register its routines) */
+static R_CallMethodDef one_routine[2];
+SEXP rstub_call_ptr(void *fn, int nargs, SEXP *a, char *err, int errlen) {
+    const R_CallMethodDef *saved = routines;
+    union { void *p; DL_FUNC f; } cv; /* data pointer -> function pointer */
+    cv.p = fn;
+    one_routine[0].name = "<by address>";
+    one_routine[0].fun = cv.f;
+    one_routine[0].numArgs = nargs;
+    one_routine[1].name = NULL;
+    routines = one_routine;
+    SEXP out = rstub_call("<by address>", nargs, a, err, errlen);
+    routines = saved;
     return out;
 }
 

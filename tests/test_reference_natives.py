@@ -1,0 +1,146 @@
+"""The oracle against the REFERENCE'S OWN compiled C natives.  oracle/_ref/libcelda_ref_natives.so is
+/root/reference/src/matrixSums.c + src/perplexity.c compiled in place (oracle/Makefile target `ref`, run by
+__graft_entry__.build() where /root/reference exists) against the R C-API miniature of tests/r_stub; the built file
+travels to the GPU box.  Every dense aggregation native (int and numeric, plain and *Change) and _perplexityG is driven
+through `.Call`-style calls on random matrices, ragged shapes, wrapping integers and the error cases, and must agree
+with the oracle's restatement bit for bit (values) and word for word (messages).  The CUDA entry points are compared
+with the oracle in tests/test_gpu_natives.py, so this closes the chain reference C -> oracle -> device."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from test_r_shim import RStub
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libcelda_ref_natives.so")
+
+pytestmark = pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref not built (needs /root/reference at build time)")
+
+
+class RefNatives(RStub):
+    """The reference natives are plain exported functions (celda registers them through Rcpp's table, which is not part
+    of these two files): call them by address."""
+
+    def __init__(self, so):
+        L = self.L = C.CDLL(so)
+        vp = C.c_void_p
+        for name, res, args in [
+            ("rstub_nil", vp, []), ("rstub_int", vp, [C.c_ssize_t, vp]), ("rstub_real", vp, [C.c_ssize_t, vp]),
+            ("rstub_set_dim", None, [vp, C.c_int, C.c_int]), ("rstub_set_levels", None, [vp, C.c_int]),
+            ("rstub_type", C.c_int, [vp]), ("rstub_length", C.c_longlong, [vp]), ("rstub_data", vp, [vp]),
+            ("rstub_nrow", C.c_int, [vp]), ("rstub_ncol", C.c_int, [vp]), ("rstub_vector_elt", vp, [vp, C.c_longlong]),
+            ("rstub_name", C.c_char_p, [vp, C.c_longlong]), ("rstub_protect_balance", C.c_int, []),
+            ("rstub_call_ptr", vp, [vp, C.c_int, C.POINTER(vp), C.c_char_p, C.c_int]), ("rstub_reset", C.c_int, []),
+        ]:
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+
+    def call(self, name, *args, raw=False):
+        fn = C.cast(getattr(self.L, name), C.c_void_p)
+        arr = (C.c_void_p * max(len(args), 1))(*args)
+        err = C.create_string_buffer(1024)
+        out = self.L.rstub_call_ptr(fn, len(args), arr, err, len(err))
+        if not out:
+            raise RuntimeError(err.value.decode())
+        return out if raw else self.value(out)
+
+
+@pytest.fixture(scope="module")
+def ref():
+    r = RefNatives(REF_SO)
+    yield r
+    r.L.rstub_reset()
+
+
+def _mat(rng, kind, nr, nc):
+    if kind == "int":
+        return rng.integers(0, 50, (nr, nc)).astype(np.int32)
+    return rng.random((nr, nc)) * 10 - 3
+
+
+@pytest.mark.parametrize("kind", ["int", "numeric"])
+@pytest.mark.parametrize("nr,nc,nl", [(10, 10, 2), (37, 5, 7), (1, 9, 3), (64, 1, 4), (23, 41, 23)])
+def test_dense_aggregation_natives_equal_the_oracle(ref, oracle, kind, nr, nc, nl):
+    sfx = "" if kind == "int" else "_numeric"
+    rng = np.random.default_rng(nr * 1000 + nc)
+    x = _mat(rng, kind, nr, nc)
+    gr, gr2 = rng.integers(1, nl + 1, nr), rng.integers(1, nl + 1, nr)
+    gc, gc2 = rng.integers(1, nl + 1, nc), rng.integers(1, nl + 1, nc)
+    got = ref.call("_rowSumByGroup" + sfx, ref.matrix(x), ref.factor(gr, nl))
+    want = oracle.rowSumByGroup(x, gr, nl)
+    assert got.dtype == want.dtype and np.array_equal(np.asarray(got).reshape(want.shape, order="F"), want)
+    got = ref.call("_colSumByGroup" + sfx, ref.matrix(x), ref.factor(gc, nl))
+    want_c = oracle.colSumByGroup(x, gc, nl)
+    assert np.array_equal(np.asarray(got).reshape(want_c.shape, order="F"), want_c)
+    # the incremental variants update px in place and return it (src/matrixSums.c:136-142)
+    px = ref.matrix(want)
+    out = ref.call("_rowSumByGroupChange" + sfx, ref.matrix(x), px, ref.factor(gr2, nl), ref.factor(gr, nl), raw=True)
+    assert out == px
+    po = oracle.rowSumByGroupChange(x, want.copy(order="F"), gr2, gr, nl)
+    assert np.array_equal(np.asarray(ref.value(px)).reshape(po.shape, order="F"), po)
+    px = ref.matrix(want_c)
+    ref.call("_colSumByGroupChange" + sfx, ref.matrix(x), px, ref.factor(gc2, nl), ref.factor(gc, nl))
+    po = oracle.colSumByGroupChange(x, want_c.copy(order="F"), gc2, gc, nl)
+    assert np.array_equal(np.asarray(ref.value(px)).reshape(po.shape, order="F"), po)
+
+
+def test_integer_sums_wrap_like_the_reference(ref, oracle):
+    big = np.full((4, 3), 2 ** 30, dtype=np.int32)
+    g = np.array([1, 1, 1, 1])
+    got = ref.call("_rowSumByGroup", ref.matrix(big), ref.factor(g, 1))
+    assert np.array_equal(np.asarray(got).ravel(), oracle.rowSumByGroup(big, g, 1).ravel())  # 4 * 2^30 wraps to 0
+
+
+@pytest.mark.parametrize("kind", ["int", "numeric"])
+def test_error_messages_equal_the_reference(ref, oracle, kind):
+    sfx = "" if kind == "int" else "_numeric"
+    rng = np.random.default_rng(1)
+    x = _mat(rng, kind, 6, 4)
+    gr, gc = np.array([1, 2, 1, 2, 1, 2]), np.array([1, 2, 2, 1])
+    na = gr.copy()
+    na[2] = np.iinfo(np.int32).min
+    px_r, px_c = oracle.rowSumByGroup(x, gr, 2), oracle.colSumByGroup(x, gc, 2)
+    cases = [
+        ("_rowSumByGroup", (x, ("v", gr)), lambda: oracle.rowSumByGroup(x, gr, -1)),                   # not a factor
+        ("_rowSumByGroup", (x, ("f", gr[:5], 2)), lambda: oracle.rowSumByGroup(x, gr[:5], 2)),         # length
+        ("_colSumByGroup", (x, ("f", gc[:3], 2)), lambda: oracle.colSumByGroup(x, gc[:3], 2)),
+        ("_rowSumByGroupChange", (x, px_r, ("f", gr, 2), ("f", gr, 3)),
+         lambda: oracle.rowSumByGroupChange(x, px_r.copy(order="F"), gr, gr, 2, 3)),                   # levels differ
+        ("_colSumByGroupChange", (x, px_r, ("f", gc, 2), ("f", gc, 2)),
+         lambda: oracle.colSumByGroupChange(x, px_r.copy(order="F"), gc, gc, 2)),                      # px shape
+        ("_rowSumByGroupChange", (x, px_r, ("f", na, 2), ("f", gr, 2)),
+         lambda: oracle.rowSumByGroupChange(x, px_r.copy(order="F"), na, gr, 2)),                      # NA label
+    ]
+    if kind == "int":  # the numeric natives do not check NA in the plain sums (src/matrixSums.c:198-278)
+        cases.append(("_rowSumByGroup", (x, ("f", na, 2)), lambda: oracle.rowSumByGroup(x, na, 2)))
+    for name, args, ofn in cases:
+        rargs = []
+        for a in args:
+            if isinstance(a, tuple):
+                rargs.append(ref.integer(a[1]) if a[0] == "v" else ref.factor(a[1], a[2]))
+            else:
+                rargs.append(ref.matrix(a))
+        with pytest.raises(RuntimeError) as e_ref:
+            ref.call(name + sfx, *rargs)
+        with pytest.raises(Exception) as e_or:
+            ofn()
+        assert str(e_ref.value) == str(e_or.value), name
+
+
+def test_perplexityG_equals_the_oracle(ref, oracle):
+    rng = np.random.default_rng(9)
+    nr, nc, nl = 30, 12, 5
+    x = rng.integers(0, 20, (nr, nc)).astype(np.int32)
+    group = rng.integers(1, nl + 1, nr)
+    phi = rng.random((nl, nc)) + 0.01
+    psi = rng.random((nr, nl)) + 0.01
+    got = ref.call("_perplexityG", ref.matrix(x), ref.matrix(phi), ref.matrix(psi), ref.factor(group, nl))[0]
+    want = oracle.perplexityG_dense(x, phi, psi, group, nl)
+    assert got == want or abs(got - want) <= 1e-13 * abs(want)  # the native calls libm's log, the oracle its own
+    with pytest.raises(RuntimeError) as e_ref:
+        ref.call("_perplexityG", ref.matrix(x), ref.matrix(phi[:, :5]), ref.matrix(psi), ref.factor(group, nl))
+    with pytest.raises(Exception) as e_or:
+        oracle.perplexityG_dense(x, phi[:, :5], psi, group, nl)
+    assert str(e_ref.value) == str(e_or.value)
