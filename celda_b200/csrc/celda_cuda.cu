@@ -1009,7 +1009,8 @@ struct CscDev {
 int celda_colSumByGroupSparse(int nrow, int ncol, const int* p, const int* i, const double* x, const int* group,
                               long long ngroup, int K, double* out) {
     if (ncol != ngroup) return fail("Length of 'group' must be equal to the number of columns in 'counts'.");
-    CELDA_TRY(check_labels_host(group, ngroup, K, "group", "K"));
+    for (long long c = 0; c < ngroup; ++c)  // src/matrixSumsSparse.cpp:21: this one message of the file has no full stop
+        if (group[c] < 1 || group[c] > K) return fail("The entries in 'group' need to be between 1 and 'K'");
     if (K > ncol) return fail("'K' cannot be bigger than the number of columns in 'counts'.");
     CELDA_CUDA_OK(cudaSetDevice(g_device));
     const int sms = num_sms(g_device);

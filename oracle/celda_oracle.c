@@ -227,7 +227,8 @@ int o_colSumByGroupSparse(int nr, int nc, const int *p, const int *ri, const dou
                           long ngroup, int K, double *out)
 {
     if (nc != ngroup) FAIL("Length of 'group' must be equal to the number of columns in 'counts'.");
-    if (check_labels(group, ngroup, K, "group", "K")) return 1;
+    for (long i = 0; i < ngroup; i++) /* :21 -- this one message of the file has no full stop */
+        if (group[i] < 1 || group[i] > K) FAIL("The entries in 'group' need to be between 1 and 'K'");
     if (K > nc) FAIL("'K' cannot be bigger than the number of columns in 'counts'.");
     memset(out, 0, sizeof(double) * (size_t)nr * K);
     for (int j = 0; j < nc; ++j)

@@ -144,3 +144,113 @@ def test_perplexityG_equals_the_oracle(ref, oracle):
     with pytest.raises(Exception) as e_or:
         oracle.perplexityG_dense(x, phi[:, :5], psi, group, nl)
     assert str(e_ref.value) == str(e_or.value)
+
+
+# ------------------------------------------------------------------ src/matrixSumsSparse.cpp (rows a2-a5, sparse)
+SPARSE_SO = os.path.join(ROOT, "oracle", "_ref", "libcelda_ref_sparse.so")
+
+
+@pytest.fixture(scope="module")
+def refsp():
+    if not os.path.exists(SPARSE_SO):
+        pytest.skip("oracle/_ref/libcelda_ref_sparse.so not built")
+    L = C.CDLL(SPARSE_SO)
+    L.ref_last_error.restype = C.c_char_p
+    return L
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+class _RefSparse:
+    def __init__(self, L):
+        self.L = L
+
+    def _chk(self, rc):
+        if rc:
+            raise RuntimeError(self.L.ref_last_error().decode())
+
+    def sum(self, which, O, group, n):
+        nr, nc, p, i, x = O
+        group = np.ascontiguousarray(group, np.int32)
+        out = np.zeros((nr, n) if which == "col" else (n, nc), order="F")
+        fn = getattr(self.L, f"ref_{which}SumByGroupSparse")
+        self._chk(fn(nr, nc, _ip(p), _ip(i), _dp(x), _ip(group), C.c_long(group.size), n, _dp(out)))
+        return out
+
+    def change(self, which, O, px, group, pgroup, n):
+        nr, nc, p, i, x = O
+        group, pgroup = np.ascontiguousarray(group, np.int32), np.ascontiguousarray(pgroup, np.int32)
+        fn = getattr(self.L, f"ref_{which}SumByGroupChangeSparse")
+        self._chk(fn(nr, nc, _ip(p), _ip(i), _dp(x), _dp(px), px.shape[0], px.shape[1], _ip(group), C.c_long(group.size),
+                     _ip(pgroup), C.c_long(pgroup.size), n))
+        return px
+
+
+@pytest.mark.parametrize("nr,nc,K,L,density", [(100, 425, 5, 10, 0.3), (57, 33, 4, 6, 0.05), (8, 300, 7, 8, 0.9),
+                                                (40, 40, 1, 1, 0.2)])
+def test_sparse_aggregation_natives_equal_the_oracle(refsp, oracle, nr, nc, K, L, density):
+    """The reference's compiled colSumByGroupSparse / rowSumByGroupSparse / *ChangeSparse against the restatement:
+    identical doubles on random sparse counts with empty columns and rows, px updated in place."""
+    from oracle.oracle import dense_to_csc
+    rng = np.random.default_rng(nr + nc)
+    dense = rng.integers(1, 30, (nr, nc)) * (rng.random((nr, nc)) < density)
+    dense[:, rng.integers(0, nc, 3)] = 0   # empty columns
+    dense[rng.integers(0, nr, 2), :] = 0   # empty rows
+    O = dense_to_csc(dense)
+    ref = _RefSparse(refsp)
+    z, z2 = rng.integers(1, K + 1, nc).astype(np.int32), rng.integers(1, K + 1, nc).astype(np.int32)
+    y, y2 = rng.integers(1, L + 1, nr).astype(np.int32), rng.integers(1, L + 1, nr).astype(np.int32)
+    cs, rs = ref.sum("col", O, z, K), ref.sum("row", O, y, L)
+    assert np.array_equal(cs, oracle.colSumByGroupSparse(O, z, K))
+    assert np.array_equal(rs, oracle.rowSumByGroupSparse(O, y, L))
+    assert np.array_equal(cs, np.stack([dense[:, z == k].sum(1) for k in range(1, K + 1)], axis=1))
+    a, b = cs.copy(order="F"), cs.copy(order="F")
+    assert ref.change("col", O, a, z2, z, K) is a
+    assert np.array_equal(a, oracle.colSumByGroupChangeSparse(O, b, z2, z, K))
+    assert np.array_equal(a, ref.sum("col", O, z2, K))
+    a, b = rs.copy(order="F"), rs.copy(order="F")
+    ref.change("row", O, a, y2, y, L)
+    assert np.array_equal(a, oracle.rowSumByGroupChangeSparse(O, b, y2, y, L))
+    assert np.array_equal(a, ref.sum("row", O, y2, L))
+
+
+def test_sparse_aggregation_error_messages_equal_the_reference(refsp, oracle):
+    from oracle.oracle import dense_to_csc
+    rng = np.random.default_rng(3)
+    dense = rng.integers(0, 5, (12, 9))
+    O = dense_to_csc(dense)
+    ref = _RefSparse(refsp)
+    z, y = rng.integers(1, 4, 9).astype(np.int32), rng.integers(1, 5, 12).astype(np.int32)
+    px_c, px_r = oracle.colSumByGroupSparse(O, z, 3), oracle.rowSumByGroupSparse(O, y, 4)
+    bad_z, bad_y = z.copy(), y.copy()
+    bad_z[0], bad_y[0] = 4, 0
+    cases = [
+        (lambda o: o.colSumByGroupSparse(O, z[:8], 3), lambda: ref.sum("col", O, z[:8], 3)),           # length
+        (lambda o: o.rowSumByGroupSparse(O, y[:11], 4), lambda: ref.sum("row", O, y[:11], 4)),
+        (lambda o: o.colSumByGroupSparse(O, bad_z, 3), lambda: ref.sum("col", O, bad_z, 3)),           # label range
+        (lambda o: o.rowSumByGroupSparse(O, bad_y, 4), lambda: ref.sum("row", O, bad_y, 4)),
+        (lambda o: o.colSumByGroupSparse(O, np.ones(9, np.int32), 10), lambda: ref.sum("col", O, np.ones(9, np.int32), 10)),
+        (lambda o: o.rowSumByGroupSparse(O, np.ones(12, np.int32), 13), lambda: ref.sum("row", O, np.ones(12, np.int32), 13)),
+        (lambda o: o.colSumByGroupChangeSparse(O, px_c.copy(order="F"), z, z[:8], 3),
+         lambda: ref.change("col", O, px_c.copy(order="F"), z, z[:8], 3)),                             # group vs pgroup
+        (lambda o: o.colSumByGroupChangeSparse(O, px_c.copy(order="F"), z, bad_z, 3),
+         lambda: ref.change("col", O, px_c.copy(order="F"), z, bad_z, 3)),                             # pgroup range
+        (lambda o: o.rowSumByGroupChangeSparse(O, px_r.copy(order="F"), bad_y, y, 4),
+         lambda: ref.change("row", O, px_r.copy(order="F"), bad_y, y, 4)),
+        (lambda o: o.colSumByGroupChangeSparse(O, px_c[:11].copy(order="F"), z, z, 3),
+         lambda: ref.change("col", O, px_c[:11].copy(order="F"), z, z, 3)),                            # px shape
+        (lambda o: o.rowSumByGroupChangeSparse(O, px_r[:, :8].copy(order="F"), y, y, 4),
+         lambda: ref.change("row", O, px_r[:, :8].copy(order="F"), y, y, 4)),
+    ]
+    for k, (ofn, rfn) in enumerate(cases):
+        with pytest.raises(RuntimeError) as e_ref:
+            rfn()
+        with pytest.raises(Exception) as e_or:
+            ofn(oracle)
+        assert str(e_ref.value) == str(e_or.value), (k, str(e_ref.value), str(e_or.value))
