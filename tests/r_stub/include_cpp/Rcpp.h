@@ -40,6 +40,13 @@ class Vector {
     long n_ = 0;
 };
 
+namespace internal {
+struct NamedPlaceHolder {};
+}  // namespace internal
+static const internal::NamedPlaceHolder _ = internal::NamedPlaceHolder();
+template <typename T>
+class RowView;
+
 template <typename T>
 class Matrix {
   public:
@@ -58,12 +65,78 @@ class Matrix {
     const T& operator[](long i) const { return p_[i]; }
     T* begin() { return p_; }
     const T* begin() const { return p_; }
+    RowView<T> operator()(long i, const internal::NamedPlaceHolder&) const;  // m(i, _)
 
   private:
     std::shared_ptr<std::vector<T>> own_;
     T* p_ = nullptr;
     int nr_ = 0, nc_ = 0;
 };
+
+// ---- the little sugar src/cG_calcGibbsProbY.cpp's cross-check variant (cG_calcGibbsProbY_Simple) is written in: row
+// views `m(i, _)`, eager element-wise +, -, *, lgamma and a left-to-right sum.  The production native of that file
+// (cG_CalcGibbsProbY) uses none of it -- only indexing and the C library's scalar lgamma.
+template <typename T>
+class RowView {
+  public:
+    RowView(T* first, long stride, long n) : p_(first), stride_(stride), n_(n) {}
+    long size() const { return n_; }
+    T operator[](long j) const { return p_[(size_t)j * stride_]; }
+    RowView& operator=(const Vector<T>& v) {
+        for (long j = 0; j < n_; ++j) p_[(size_t)j * stride_] = v[j];
+        return *this;
+    }
+
+  private:
+    T* p_;
+    long stride_, n_;
+};
+template <typename T>
+inline RowView<T> Matrix<T>::operator()(long i, const internal::NamedPlaceHolder&) const {
+    return RowView<T>(const_cast<T*>(p_) + i, nr_, nc_);
+}
+template <typename T>
+inline Vector<T> operator-(const RowView<T>& a, const RowView<T>& b) {
+    Vector<T> r(a.size());
+    for (long j = 0; j < a.size(); ++j) r[j] = a[j] - b[j];
+    return r;
+}
+template <typename T>
+inline Vector<T> operator+(const RowView<T>& a, const RowView<T>& b) {
+    Vector<T> r(a.size());
+    for (long j = 0; j < a.size(); ++j) r[j] = a[j] + b[j];
+    return r;
+}
+inline Vector<double> operator+(const Vector<int>& a, double s) {
+    Vector<double> r(a.size());
+    for (long j = 0; j < a.size(); ++j) r[j] = a[j] + s;
+    return r;
+}
+inline Vector<double> operator*(const Vector<int>& a, double s) {
+    Vector<double> r(a.size());
+    for (long j = 0; j < a.size(); ++j) r[j] = a[j] * s;
+    return r;
+}
+inline Vector<double> operator+(const Vector<int>& a, const Vector<double>& b) {
+    Vector<double> r(a.size());
+    for (long j = 0; j < a.size(); ++j) r[j] = a[j] + b[j];
+    return r;
+}
+inline Vector<double> operator+(const Matrix<int>& a, double s) {
+    Vector<double> r(a.size());
+    for (long j = 0; j < a.size(); ++j) r[j] = a[j] + s;
+    return r;
+}
+inline Vector<double> lgamma(const Vector<double>& a) {
+    Vector<double> r(a.size());
+    for (long j = 0; j < a.size(); ++j) r[j] = ::lgamma(a[j]);
+    return r;
+}
+inline double sum(const Vector<double>& a) {
+    double t = 0;
+    for (long j = 0; j < a.size(); ++j) t += a[j];
+    return t;
+}
 
 typedef Vector<int> IntegerVector;
 typedef Vector<double> NumericVector;

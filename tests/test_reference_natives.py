@@ -147,13 +147,13 @@ def test_perplexityG_equals_the_oracle(ref, oracle):
 
 
 # ------------------------------------------------------------------ src/matrixSumsSparse.cpp (rows a2-a5, sparse)
-SPARSE_SO = os.path.join(ROOT, "oracle", "_ref", "libcelda_ref_sparse.so")
+SPARSE_SO = os.path.join(ROOT, "oracle", "_ref", "libcelda_ref_cpp.so")
 
 
 @pytest.fixture(scope="module")
 def refsp():
     if not os.path.exists(SPARSE_SO):
-        pytest.skip("oracle/_ref/libcelda_ref_sparse.so not built")
+        pytest.skip("oracle/_ref/libcelda_ref_cpp.so not built")
     L = C.CDLL(SPARSE_SO)
     L.ref_last_error.restype = C.c_char_p
     return L
@@ -254,3 +254,90 @@ def test_sparse_aggregation_error_messages_equal_the_reference(refsp, oracle):
         with pytest.raises(Exception) as e_or:
             ofn(oracle)
         assert str(e_ref.value) == str(e_or.value), (k, str(e_ref.value), str(e_or.value))
+
+
+# ------------------------------------------------------------------ src/cG_calcGibbsProbY.cpp (row a10: the y kernel)
+def _y_state(oracle, gold_g, L, seed):
+    from oracle.oracle import dense_to_csc
+    counts = gold_g["counts"]
+    nG, nM = counts.shape
+    y = np.random.default_rng(seed).integers(1, L + 1, nG).astype(np.int32)
+    p = oracle.cGDecomposeCounts(dense_to_csc(counts), y, L)
+    return counts, y, p
+
+
+def _tables(oracle, p, nG, L, beta, gamma, delta):
+    """lgbeta / lggamma / lgdelta as .celda_G builds them (R/celda_G.R:380-383), by the oracle's lgamma."""
+    top = int(p["nTSByC"].sum(0).max())
+    lgb = oracle.lgamma(np.arange(0, top + 1) + beta)
+    lgg = oracle.lgamma(np.arange(0, nG + L + 1) + gamma)
+    lgd = np.concatenate([[np.nan], oracle.lgamma(np.arange(1, nG + L + 1) * delta)])
+    return lgb, lgg, lgd
+
+
+@pytest.mark.parametrize("L,hyper", [(10, (1.0, 1.0, 1.0)), (4, (0.5, 2.0, 1.5))])
+def test_y_kernel_native_equals_the_oracle(refsp, oracle, gold_g, L, hyper):
+    """The reference's compiled cG_CalcGibbsProbY against the restatement, gene by gene on a random celda_G state.  The
+    native takes lgamma of the two nByTS terms per module from the C library while the oracle (and the device) evaluate
+    R's lgammafn (which is what builds the tables in R): each entry is a difference of lgamma values near 1e5, so the
+    vectors agree to a few units in the last place OF THOSE TERMS (4 ulp allowed, 2-3 measured), not of the result --
+    which is why DESIGN.md section 3 fixes one arithmetic for oracle and device.  Same first maximum and the same
+    sampled module for the same uniform."""
+    beta, gamma, delta = hyper
+    counts, y, p = _y_state(oracle, gold_g, L, 17)
+    nG, nM = counts.shape
+    lgb, lgg, lgd = _tables(oracle, p, nG, L, beta, gamma, delta)
+    t, ts, gt, g = np.asfortranarray(p["nTSByC"], dtype=np.float64), p["nByTS"].astype(np.float64), \
+        p["nGByTS"].astype(np.int32), p["nByG"].astype(np.float64)
+    rng = np.random.default_rng(1)
+    ulp_top = float(np.spacing(oracle.lgamma(np.array([ts.max() + g.max() + (nG + 1) * delta]))[0]))  # the largest term
+    genes = rng.choice(nG, 40, replace=False) + 1
+    for index in genes:
+        row = np.ascontiguousarray(counts[index - 1], dtype=np.float64)
+        got = np.zeros(L)
+        rc = refsp.ref_cG_CalcGibbsProbY(int(index), _dp(row), nM, _dp(t), _dp(ts), _ip(gt), _dp(g), _ip(y), L, nG, _dp(lgb),
+                                         C.c_long(lgb.size), _dp(lgg), C.c_long(lgg.size), _dp(lgd), C.c_long(lgd.size),
+                                         C.c_double(delta), _dp(got))
+        assert rc == 0, refsp.ref_last_error()
+        want = oracle.cG_CalcGibbsProbY(int(index), row, t, ts, gt, g, y, L, beta, gamma, delta, lgb, lgg, lgd)
+        both_nan = np.isnan(got) & np.isnan(want)  # lg_delta[0] is NA: a gene alone in its module (R aborts there)
+        assert (np.isnan(got) == np.isnan(want)).all()
+        assert np.abs(got[~both_nan] - want[~both_nan]).max(initial=0.0) <= 4 * ulp_top  # measured: 2-3 ulp of that term
+        if not both_nan.any():
+            assert int(np.argmax(got)) == int(np.argmax(want))
+            u = float(rng.random())
+            assert oracle.sampleLl(got, u)[0] == oracle.sampleLl(want, u)[0]
+
+
+def test_reference_cross_check_variants_agree_with_its_production_kernel(refsp, oracle, gold_g):
+    """The reference ships three more forms of the kernel 'as a sanity check when modifying the faster function'
+    (src/cG_calcGibbsProbY.cpp:4-6).  Run here for the same purpose: _fastRow and _ori reproduce the production
+    vector, _Simple (full expression per candidate) reproduces it up to its constant -- and so does the oracle."""
+    L, (beta, gamma, delta) = 6, (1.0, 1.0, 1.0)
+    counts, y, p = _y_state(oracle, gold_g, L, 23)
+    nG, nM = counts.shape
+    lgb, lgg, lgd = _tables(oracle, p, nG, L, beta, gamma, delta)
+    ci = np.asfortranarray(counts, dtype=np.int32)
+    ti, tsi, gti, gi = np.asfortranarray(p["nTSByC"], dtype=np.int32), p["nByTS"].astype(np.int32), \
+        p["nGByTS"].astype(np.int32), p["nByG"].astype(np.int32)
+    t, ts, g = ti.astype(np.float64, order="F"), tsi.astype(np.float64), gi.astype(np.float64)
+    for index in (1, 7, 50, nG):
+        row = np.ascontiguousarray(counts[index - 1], dtype=np.float64)
+        want = oracle.cG_CalcGibbsProbY(index, row, t, ts, gti, g, y, L, beta, gamma, delta, lgb, lgg, lgd)
+        for which in (0, 1):
+            got = np.zeros(L)
+            rc = refsp.ref_cG_CalcGibbsProbY_int(which, index, _ip(ci), nM, _ip(ti), _ip(tsi), _ip(gti), _ip(gi), _ip(y), L, nG,
+                                                 _dp(lgb), C.c_long(lgb.size), _dp(lgg), C.c_long(lgg.size), _dp(lgd),
+                                                 C.c_long(lgd.size), C.c_double(delta), _dp(got))
+            assert rc == 0
+            if which == 0:
+                assert np.allclose(got, want, rtol=1e-12, atol=0)
+            else:  # _ori sums every module's terms for every candidate: equal up to a constant
+                assert np.allclose(got - got[0], want - want[0], rtol=0, atol=1e-7 * np.abs(got).max())
+        simple = np.zeros(L)
+        before = (ti.copy(), tsi.copy(), gti.copy())
+        rc = refsp.ref_cG_calcGibbsProbY_Simple(_ip(ci), nM, _ip(gti), _ip(ti), _ip(tsi), _ip(gi), _ip(y), L, nG, index,
+                                                C.c_double(gamma), C.c_double(beta), C.c_double(delta), _dp(simple))
+        assert rc == 0
+        assert all(np.array_equal(a, b) for a, b in zip(before, (ti, tsi, gti)))  # it restores the tables it edits
+        assert np.allclose(simple - simple[0], want - want[0], rtol=0, atol=1e-7 * np.abs(simple).max())
