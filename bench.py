@@ -243,6 +243,7 @@ def run_reference(a):
             per_step.append(full)
     sec = float(np.mean(per_step))
     value = chains / sec
+    natives = reference_natives(d, a, z, y, tables)
     print(json.dumps({
         "impl": "reference", "metric": "celda_CG_gibbs_iterations_per_sec", "value": value, "unit": "iter/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
@@ -250,7 +251,41 @@ def run_reference(a):
         "cells_iters_per_sec": value * d["nM"],
         "cpu_baseline": {"value": value, "unit": "iter/s", "cores": chains, "kind": "port", "sample": desc,
                          "extrapolated": extrap},
+        "reference_natives": natives,
         "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def reference_natives(d, a, z, y, tables):
+    """The reference's OWN compiled sparse aggregation natives (oracle/_ref/libcelda_ref_cpp.so = src/matrixSumsSparse.cpp
+    built unmodified, oracle/Makefile target `ref`) on the full workload: seconds per call on one host core, and whether
+    their tables equal the port's.  None when the library was not built (no /root/reference at build time)."""
+    import ctypes as C
+    so = os.path.join(ROOT, "oracle", "_ref", "libcelda_ref_cpp.so")
+    if not os.path.exists(so):
+        return None
+    try:
+        L = C.CDLL(so)
+        ip, dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+        pp, ii, xx = (np.ascontiguousarray(d["p"], np.int32), np.ascontiguousarray(d["i"], np.int32),
+                      np.ascontiguousarray(d["x"], np.float64))
+        zz, yy = np.ascontiguousarray(z, np.int32), np.ascontiguousarray(y, np.int32)
+        nG, nM = int(d["nG"]), int(d["nM"])
+        rs, cs = np.zeros((a.L, nM), order="F"), np.zeros((nG, a.K), order="F")
+        t0 = time.perf_counter()
+        rc1 = L.ref_rowSumByGroupSparse(nG, nM, pp.ctypes.data_as(ip), ii.ctypes.data_as(ip), xx.ctypes.data_as(dp),
+                                        yy.ctypes.data_as(ip), C.c_long(nG), a.L, rs.ctypes.data_as(dp))
+        t1 = time.perf_counter()
+        rc2 = L.ref_colSumByGroupSparse(nG, nM, pp.ctypes.data_as(ip), ii.ctypes.data_as(ip), xx.ctypes.data_as(dp),
+                                        zz.ctypes.data_as(ip), C.c_long(nM), a.K, cs.ctypes.data_as(dp))
+        t2 = time.perf_counter()
+        if rc1 or rc2:
+            return {"error": "status %d / %d" % (rc1, rc2)}
+        return {"kind": "reference", "what": "src/matrixSumsSparse.cpp compiled unmodified (oracle/_ref), one core, full workload",
+                "rowSumByGroupSparse_s": t1 - t0, "colSumByGroupSparse_s": t2 - t1,
+                "GB_per_s": [8.0 * xx.size / 1e9 / (t1 - t0), 8.0 * xx.size / 1e9 / (t2 - t1)],
+                "tables_equal_port": bool(np.array_equal(rs, tables["nTSByC"]) and np.array_equal(cs, tables["nGByCP"]))}
+    except Exception as e:  # a reported extra, never fatal for the arm
+        return {"error": str(e)}
 
 
 def run_regimes(cb, csc, d, a, device):
