@@ -280,7 +280,32 @@ def reference_natives(d, a, z, y, tables):
         t2 = time.perf_counter()
         if rc1 or rc2:
             return {"error": "status %d / %d" % (rc1, rc2)}
-        return {"kind": "reference", "what": "src/matrixSumsSparse.cpp compiled unmodified (oracle/_ref), one core, full workload",
+        # the y sweep's native part as the reference runs it (R/celda_G.R:602-660): the lgamma tables are rebuilt by every
+        # call of the closure, then one call of the compiled cG_CalcGibbsProbY per gene (labels not updated here)
+        from oracle.oracle import Oracle
+        o = Oracle()
+        t3 = time.perf_counter()
+        lgb = o.lgamma(np.arange(0, int(tables["nCP"].max()) + 1, dtype=np.float64) + 1.0)
+        lgg = o.lgamma(np.arange(0, nG + a.L + 1, dtype=np.float64) + 1.0)
+        lgd = np.concatenate([[np.nan], o.lgamma(np.arange(1, nG + a.L + 1, dtype=np.float64) * 1.0)])
+        t4 = time.perf_counter()
+        cnt = np.ascontiguousarray(tables["nGByCP"], np.float64)  # row g = counts[g, ] as R passes it
+        tt = np.asfortranarray(tables["nTSByCP"], np.float64)
+        ts, gt = np.ascontiguousarray(tables["nByTS"], np.float64), np.ascontiguousarray(tables["nGByTS"], np.int32)
+        bg, probs = np.ascontiguousarray(tables["nByG"], np.float64), np.zeros(a.L)
+        f = L.ref_cG_CalcGibbsProbY
+        fixed = (tt.ctypes.data_as(dp), ts.ctypes.data_as(dp), gt.ctypes.data_as(ip), bg.ctypes.data_as(dp),
+                 yy.ctypes.data_as(ip), a.L, nG, lgb.ctypes.data_as(dp), C.c_long(lgb.size), lgg.ctypes.data_as(dp),
+                 C.c_long(lgg.size), lgd.ctypes.data_as(dp), C.c_long(lgd.size), C.c_double(1.0), probs.ctypes.data_as(dp))
+        base, stride = cnt.ctypes.data, cnt.strides[0]
+        t5 = time.perf_counter()
+        for g in range(nG):
+            f(g + 1, C.cast(base + g * stride, dp), a.K, *fixed)
+        t6 = time.perf_counter()
+        return {"kind": "reference", "what": "src/matrixSumsSparse.cpp and src/cG_calcGibbsProbY.cpp compiled unmodified (oracle/_ref), one core, full workload",
+                "y_sweep_native_part_s": {"lgamma_tables": t4 - t3, "cG_CalcGibbsProbY_calls": t6 - t5, "genes": nG,
+                                          "note": "tables by the port's lgammafn; the R loop, sampling and table updates "
+                                                  "around the calls are not included"},
                 "rowSumByGroupSparse_s": t1 - t0, "colSumByGroupSparse_s": t2 - t1,
                 "GB_per_s": [8.0 * xx.size / 1e9 / (t1 - t0), 8.0 * xx.size / 1e9 / (t2 - t1)],
                 "tables_equal_port": bool(np.array_equal(rs, tables["nTSByC"]) and np.array_equal(cs, tables["nGByCP"]))}
