@@ -62,6 +62,14 @@ def test_order_is_a_permutation_for_every_n(order, n):
     assert np.array_equal(np.sort(ix), np.arange(1, n + 1, dtype=np.int32))
 
 
+def test_order_is_a_permutation_for_all_small_n(order):
+    """Every n up to 2100 (all the small bit widths and their boundaries), three sweeps each."""
+    for n in range(1, 2101):
+        ix = order(n, seed=n, sweep=n % 7, stream=n % 3, nsweep=3)
+        want = np.arange(1, n + 1, dtype=np.int32)
+        assert all(np.array_equal(np.sort(row), want) for row in ix), n
+
+
 def test_order_depends_on_seed_sweep_and_stream_only(order):
     n = 5000
     base = order(n, seed=7, sweep=3, stream=1)[0]
