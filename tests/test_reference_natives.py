@@ -341,3 +341,81 @@ def test_reference_cross_check_variants_agree_with_its_production_kernel(refsp, 
         assert rc == 0
         assert all(np.array_equal(a, b) for a, b in zip(before, (ti, tsi, gti)))  # it restores the tables it edits
         assert np.allclose(simple - simple[0], want - want[0], rtol=0, atol=1e-7 * np.abs(simple).max())
+
+
+# ------------------------------------------------------------------ the product's error contract, on the CPU
+def test_library_error_messages_equal_the_reference_natives(ref, refsp, gold_cg):
+    """libcelda_cuda validates its arguments on the host before the first CUDA call, so its error contract can be held
+    against the reference's compiled natives without a device: for every precondition the reference checks (lengths,
+    label range, K / L against the matrix, px shape, factor-ness, NA labels) the library returns the SAME message."""
+    import celda_b200 as cb
+    from oracle.oracle import dense_to_csc
+    rng = np.random.default_rng(3)
+    dense = rng.integers(0, 5, (12, 9))
+    O = dense_to_csc(dense)
+    A = cb.CSC.from_dense(dense)
+    rs = _RefSparse(refsp)
+    z, y = rng.integers(1, 4, 9).astype(np.int32), rng.integers(1, 5, 12).astype(np.int32)
+    bad_z, bad_y = z.copy(), y.copy()
+    bad_z[0], bad_y[0] = 4, 0
+    pc, pr = np.zeros((12, 3), order="F"), np.zeros((4, 9), order="F")
+    sparse_cases = [
+        (lambda: cb.colSumByGroupSparse(A, z[:8], 3), lambda: rs.sum("col", O, z[:8], 3)),
+        (lambda: cb.rowSumByGroupSparse(A, y[:11], 4), lambda: rs.sum("row", O, y[:11], 4)),
+        (lambda: cb.colSumByGroupSparse(A, bad_z, 3), lambda: rs.sum("col", O, bad_z, 3)),
+        (lambda: cb.rowSumByGroupSparse(A, bad_y, 4), lambda: rs.sum("row", O, bad_y, 4)),
+        (lambda: cb.colSumByGroupSparse(A, np.ones(9, np.int32), 10), lambda: rs.sum("col", O, np.ones(9, np.int32), 10)),
+        (lambda: cb.rowSumByGroupSparse(A, np.ones(12, np.int32), 13), lambda: rs.sum("row", O, np.ones(12, np.int32), 13)),
+        (lambda: cb.colSumByGroupChangeSparse(A, pc.copy(order="F"), z, z[:8], 3),
+         lambda: rs.change("col", O, pc.copy(order="F"), z, z[:8], 3)),
+        (lambda: cb.colSumByGroupChangeSparse(A, pc.copy(order="F"), z, bad_z, 3),
+         lambda: rs.change("col", O, pc.copy(order="F"), z, bad_z, 3)),
+        (lambda: cb.rowSumByGroupChangeSparse(A, pr.copy(order="F"), bad_y, y, 4),
+         lambda: rs.change("row", O, pr.copy(order="F"), bad_y, y, 4)),
+        (lambda: cb.colSumByGroupChangeSparse(A, pc[:11].copy(order="F"), z, z, 3),
+         lambda: rs.change("col", O, pc[:11].copy(order="F"), z, z, 3)),
+        (lambda: cb.rowSumByGroupChangeSparse(A, pr[:, :8].copy(order="F"), y, y, 4),
+         lambda: rs.change("row", O, pr[:, :8].copy(order="F"), y, y, 4)),
+    ]
+    for k, (ours, theirs) in enumerate(sparse_cases):
+        with pytest.raises(cb.CeldaCudaError) as e_ours:
+            ours()
+        with pytest.raises(RuntimeError) as e_ref:
+            theirs()
+        assert str(e_ours.value) == str(e_ref.value), (k, str(e_ours.value), str(e_ref.value))
+
+    # dense natives (src/matrixSums.c): factor-ness, lengths, levels, px shape, NA
+    for dtype, sfx in ((np.int32, ""), (np.float64, "_numeric")):
+        x = np.asfortranarray(rng.integers(0, 9, (6, 4)).astype(dtype))
+        gr, gc = np.array([1, 2, 1, 2, 1, 2], np.int32), np.array([1, 2, 2, 1], np.int32)
+        na = gr.copy()
+        na[2] = np.iinfo(np.int32).min
+        px_r, px_c = np.zeros((2, 4), dtype, order="F"), np.zeros((6, 2), dtype, order="F")
+        dense_cases = [
+            (lambda: cb.rowSumByGroup_dense(x, gr, -1), ("_rowSumByGroup", [x, ("v", gr)])),
+            (lambda: cb.colSumByGroup_dense(x, gc, -1), ("_colSumByGroup", [x, ("v", gc)])),
+            (lambda: cb.rowSumByGroup_dense(x, gr[:5], 2), ("_rowSumByGroup", [x, ("f", gr[:5], 2)])),
+            (lambda: cb.colSumByGroup_dense(x, gc[:3], 2), ("_colSumByGroup", [x, ("f", gc[:3], 2)])),
+            (lambda: cb.rowSumByGroupChange_dense(x, px_r.copy(order="F"), gr, gr, 2, 3),
+             ("_rowSumByGroupChange", [x, px_r, ("f", gr, 2), ("f", gr, 3)])),
+            (lambda: cb.colSumByGroupChange_dense(x, px_r.copy(order="F"), gc, gc, 2),
+             ("_colSumByGroupChange", [x, px_r, ("f", gc, 2), ("f", gc, 2)])),
+            (lambda: cb.rowSumByGroupChange_dense(x, px_c.copy(order="F"), gr, gr, 2),
+             ("_rowSumByGroupChange", [x, px_c, ("f", gr, 2), ("f", gr, 2)])),
+            (lambda: cb.rowSumByGroupChange_dense(x, px_r.copy(order="F"), gr[:5], gr, 2),
+             ("_rowSumByGroupChange", [x, px_r, ("f", gr[:5], 2), ("f", gr, 2)])),
+            (lambda: cb.rowSumByGroupChange_dense(x, px_r.copy(order="F"), na, gr, 2),
+             ("_rowSumByGroupChange", [x, px_r, ("f", na, 2), ("f", gr, 2)])),
+            (lambda: cb.colSumByGroupChange_dense(x, px_c.copy(order="F"), gc, gc[:3], 2),
+             ("_colSumByGroupChange", [x, px_c, ("f", gc, 2), ("f", gc[:3], 2)])),
+        ]
+        if dtype == np.int32:
+            dense_cases.append((lambda: cb.rowSumByGroup_dense(x, na, 2), ("_rowSumByGroup", [x, ("f", na, 2)])))
+        for k, (ours, (name, args)) in enumerate(dense_cases):
+            rargs = [(ref.integer(a[1]) if a[0] == "v" else ref.factor(a[1], a[2])) if isinstance(a, tuple) else ref.matrix(a)
+                     for a in args]
+            with pytest.raises(cb.CeldaCudaError) as e_ours:
+                ours()
+            with pytest.raises(RuntimeError) as e_ref:
+                ref.call(name + sfx, *rargs)
+            assert str(e_ours.value) == str(e_ref.value), (sfx, k, name, str(e_ours.value), str(e_ref.value))
