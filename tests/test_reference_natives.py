@@ -419,3 +419,20 @@ def test_library_error_messages_equal_the_reference_natives(ref, refsp, gold_cg)
             with pytest.raises(RuntimeError) as e_ref:
                 ref.call(name + sfx, *rargs)
             assert str(e_ours.value) == str(e_ref.value), (sfx, k, name, str(e_ours.value), str(e_ref.value))
+
+    # _perplexityG (src/perplexity.c:13-43).  The reference's label check is `< 0 || > nrow(x)` and would index out of
+    # bounds for 0 or for a label above the number of levels; the library rejects those too (same message).
+    nr, nc, nl = 8, 5, 3
+    x = rng.integers(0, 9, (nr, nc)).astype(np.int32)
+    phi, psi, grp = rng.random((nl, nc)) + 0.1, rng.random((nr, nl)) + 0.1, rng.integers(1, nl + 1, nr).astype(np.int32)
+    na = grp.copy()
+    na[1] = np.iinfo(np.int32).min
+    for k, (xx, ph, ps, g, lev) in enumerate([(x, phi, psi, grp, -1), (x, phi, psi, grp[:7], nl), (x, phi[:, :4], psi, grp, nl),
+                                              (x, phi[:2], psi, grp, nl), (x, phi, psi[:7], grp, nl),
+                                              (x, phi, psi[:, :2], grp, nl), (x, phi, psi, na, nl)]):
+        with pytest.raises(cb.CeldaCudaError) as e_ours:
+            cb.perplexityG(xx, ph, ps, g, lev)
+        with pytest.raises(RuntimeError) as e_ref:
+            ref.call("_perplexityG", ref.matrix(xx), ref.matrix(np.asfortranarray(ph)), ref.matrix(np.asfortranarray(ps)),
+                     ref.integer(g) if lev < 0 else ref.factor(g, lev))
+        assert str(e_ours.value) == str(e_ref.value), (k, str(e_ours.value), str(e_ref.value))
