@@ -8,9 +8,16 @@
  *
  * Each function cites the reference file:line it follows (paths relative to /root/reference).
  *
- * PARITY PIN: the reference cannot be compiled or run in the build container (no R, Rcpp,
- * Eigen, R.h -- SURVEY.md section 8c), so this oracle is pinned against the reference's own
- * fixtures instead: tests/test_oracle_golden.py checks the three log-likelihood functions
+ * PARITY PIN (1), the reference's own natives: there is no R, Rcpp or Eigen in the build container, but
+ * the reference's native sources compile UNMODIFIED against miniatures of the R C API and of the Rcpp /
+ * Eigen containers (tests/r_stub, my own code): `make ref` builds oracle/_ref/ from
+ * /root/reference/src/{matrixSums.c, perplexity.c, matrixSumsSparse.cpp, cG_calcGibbsProbY.cpp}, and
+ * tests/test_reference_natives.py holds this file against them -- the twelve aggregation natives and
+ * _perplexityG bit for bit and message for message, the y kernel cG_CalcGibbsProbY to 2-3 ulp of its
+ * largest lgamma term (libm lgamma there, R's lgammafn here) with identical argmax and draws.
+ * PARITY PIN (2), the R closures (z sweep, EM step, log-likelihoods, decompositions, sampler) need an R
+ * interpreter and cannot run here; they are pinned against the reference's own
+ * fixtures: tests/test_oracle_golden.py checks the three log-likelihood functions
  * against data/celda{CG,C,G}Mod.rda finalLogLik (bit-identical or <= 4e-16 relative), the 9
  * grid-search models of data/celdaCGGridSearchRes.rda, the aggregation known answers of
  * tests/testthat/test-matrixSums.R, and the Delta-probs == Delta-LL identity that ties the
