@@ -28,6 +28,10 @@ void order_host(long long n, unsigned long long seed, unsigned sweep0, unsigned 
                                                                    (unsigned)(seed >> 32), sweep0 + s, stream);
         }
 }
+void philox_host(const unsigned* ctr, const unsigned* key, unsigned* out) {
+    const celda::Philox4 r = celda::philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+    for (int q = 0; q < 4; ++q) out[q] = r.x[q];
+}
 }
 """
 
@@ -42,17 +46,37 @@ def build_host_order(tmpdir):
     L.order_host.restype = None
     L.order_host.argtypes = [C.c_longlong, C.c_ulonglong, C.c_uint, C.c_uint, C.c_int, C.c_void_p, C.c_void_p]
 
+    L.philox_host.restype = None
+    L.philox_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+
+    def philox(ctr, key):
+        c, k, out = np.asarray(ctr, np.uint32), np.asarray(key, np.uint32), np.zeros(4, np.uint32)
+        L.philox_host(c.ctypes.data, k.ctypes.data, out.ctypes.data)
+        return out.tolist()
+
     def order(n, seed=12345, sweep=0, stream=0, nsweep=1, uniforms=False):
         out = np.zeros((nsweep, n), dtype=np.int32)
         u = np.zeros((nsweep, n)) if uniforms else None
         L.order_host(n, seed, sweep, stream, nsweep, out.ctypes.data, u.ctypes.data if uniforms else None)
         return (out, u) if uniforms else out
+    order.philox = philox
     return order
 
 
 @pytest.fixture(scope="module")
 def order(tmp_path_factory):
     return build_host_order(str(tmp_path_factory.mktemp("philox_order")))
+
+
+def test_generator_known_answers_on_the_host_build(order):
+    """Random123's kat_vectors for philox4x32-10 on the host build of the header the device compiles
+    (tests/test_gpu_philox.py checks the same vectors on the GPU)."""
+    kat = [([0, 0, 0, 0], [0, 0], [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])]
+    for ctr, key, want in kat:
+        assert order.philox(ctr, key) == want
 
 
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 31, 32, 33, 63, 64, 65, 83, 100, 127, 128, 129, 1000, 4097, 19999, 100000,
