@@ -435,7 +435,7 @@ def leg_grid_search(cb, a, rank, world, local, dist, torch):
     from celda_b200 import model
     dd = simulate_cells_cg(12345, 10, a.grid_cells // 10, a.genes, 30, 150, (1000, 10000))
     counts = cb.CSC(dd["nG"], dd["nM"], dd["p"], dd["i"], dd["x"])
-    params = {"K": [10, 20, 30, 40, 50], "L": [50, 100, 150, 200]}
+    params = {"K": [5, 10, 15, 20, 25, 30, 35, 40, 45, 50], "L": [50, 100, 150, 200]}  # x 3 chains = 120 runs
     counter = [0]
     if world > 1:
         store = dist.distributed_c10d._get_default_store()
