@@ -122,6 +122,8 @@ def _build_shim(tmpdir, mock=False):
     from celda_b200 import _lib
     so_dir = os.path.dirname(_lib.build())
     warn = ["-O1", "-g", "-Wall", "-Wextra", "-Werror", "-Wno-cast-function-type", "-shared", "-fPIC"]
+    if os.environ.get("CELDA_SHIM_SANITIZE") == "1":  # test_shim_and_stub_clean_under_asan_and_ubsan re-runs this file so
+        warn += ["-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer"]
     libs = ["-L" + so_dir, "-l:libcelda_cuda.so", "-Wl,-rpath," + so_dir]
     if mock:
         odir = os.path.join(ROOT, "oracle")
@@ -302,6 +304,26 @@ def test_closure_errors_surface_as_R_errors(Rmock, oracle, gold_cg):
     with pytest.raises(RuntimeError):
         Rmock.call("_celda_cuda_cCCalcGibbsProbZ", *bad)  # z = 7 with K = 2
     assert Rmock.L.rstub_protect_balance() == 0
+
+
+def test_shim_and_stub_clean_under_asan_and_ubsan():
+    """The CPU tests of this file once more in a subprocess with the shim, the R API miniature and the mock built with
+    AddressSanitizer + UndefinedBehaviorSanitizer (libasan preloaded): the marshalling of the closures (copies, dims,
+    named lists), the PROTECT bookkeeping and the error exits touch no memory they do not own."""
+    import sys
+    if os.environ.get("CELDA_SHIM_SANITIZE") == "1":
+        pytest.skip("already inside the sanitizer run")
+    try:
+        asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True, check=True).stdout.strip()
+    except Exception:
+        asan = ""
+    if not (os.path.isabs(asan) and os.path.exists(asan)):
+        pytest.skip("gcc's libasan is not available")
+    env = dict(os.environ, LD_PRELOAD=asan, CELDA_SHIM_SANITIZE="1", ASAN_OPTIONS="detect_leaks=0:abort_on_error=1",
+               UBSAN_OPTIONS="halt_on_error=1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "not gpu",
+                        "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, timeout=600, cwd=ROOT)
+    assert r.returncode == 0 and " passed" in r.stdout, (r.stdout[-3000:], r.stderr[-3000:])
 
 
 # ------------------------------------------------------------------------------------------------------- GPU
