@@ -14,7 +14,8 @@ import pytest
 from test_r_shim import RStub
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REF_SO = os.path.join(ROOT, "oracle", "_ref", "libcelda_ref_natives.so")
+REF_DIR = os.environ.get("CELDA_REF_DIR") or os.path.join(ROOT, "oracle", "_ref")  # a sanitizer build, see the last test
+REF_SO = os.path.join(REF_DIR, "libcelda_ref_natives.so")
 
 pytestmark = pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref not built (needs /root/reference at build time)")
 
@@ -147,7 +148,7 @@ def test_perplexityG_equals_the_oracle(ref, oracle):
 
 
 # ------------------------------------------------------------------ src/matrixSumsSparse.cpp (rows a2-a5, sparse)
-SPARSE_SO = os.path.join(ROOT, "oracle", "_ref", "libcelda_ref_cpp.so")
+SPARSE_SO = os.path.join(REF_DIR, "libcelda_ref_cpp.so")
 
 
 @pytest.fixture(scope="module")
@@ -436,3 +437,37 @@ def test_library_error_messages_equal_the_reference_natives(ref, refsp, gold_cg)
             ref.call("_perplexityG", ref.matrix(xx), ref.matrix(np.asfortranarray(ph)), ref.matrix(np.asfortranarray(ps)),
                      ref.integer(g) if lev < 0 else ref.factor(g, lev))
         assert str(e_ours.value) == str(e_ref.value), (k, str(e_ours.value), str(e_ref.value))
+
+
+def test_reference_natives_and_miniatures_clean_under_asan_and_ubsan(tmp_path):
+    """This file once more in a subprocess against a second build of oracle/_ref with AddressSanitizer +
+    UndefinedBehaviorSanitizer (`make -C oracle ref REFDIR=... SAN=...`, libasan preloaded): the R / Rcpp / Eigen
+    miniatures hand the reference's code exactly the memory it indexes, and the reference's natives themselves run clean
+    on these inputs."""
+    import subprocess
+    import sys
+    if os.environ.get("CELDA_REF_DIR"):
+        pytest.skip("already inside the sanitizer run")
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("needs the reference sources to build the instrumented copy")
+    try:
+        asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True, check=True).stdout.strip()
+    except Exception:
+        asan = ""
+    if not (os.path.isabs(asan) and os.path.exists(asan)):
+        pytest.skip("gcc's libasan is not available")
+    san = "-g -fsanitize=address,undefined -fno-sanitize-recover=undefined -fno-omit-frame-pointer"
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "ref", "CC=gcc", "CXX=g++", f"REFDIR={tmp_path}",
+                           f"SAN={san}"])
+    # libstdc++ is preloaded next to libasan: python itself does not link it, and ASan resolves __cxa_throw when it starts
+    # (the reference's stop() is a C++ exception thrown inside a dlopen'ed library)
+    stdcpp = subprocess.run(["g++", "-print-file-name=libstdc++.so.6"], capture_output=True, text=True).stdout.strip()
+    env = dict(os.environ, LD_PRELOAD=f"{asan} {stdcpp}".strip(), CELDA_REF_DIR=str(tmp_path),
+               ASAN_OPTIONS="detect_leaks=0:abort_on_error=1", UBSAN_OPTIONS="halt_on_error=1")
+    # the wrap test is left out: there UBSan stops at the reference's own `ans[...] += x[...]` on int
+    # (src/matrixSums.c:42, signed overflow is undefined in C; it wraps on every build we know, which is what the
+    # oracle and the device reproduce) -- the one finding, and it is the reference's
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-x", "-m", "not gpu",
+                        "-k", "not wrap", "-p", "no:cacheprovider"], capture_output=True, text=True, env=env, timeout=600,
+                       cwd=ROOT)
+    assert r.returncode == 0 and " passed" in r.stdout, (r.stdout[-3000:], r.stderr[-3000:])
