@@ -174,6 +174,25 @@ def test_shim_compiles_and_registers_every_routine(R):
         assert name in table
 
 
+def test_registered_names_and_arities_match_the_reference_table(R):
+    """Against the reference's own registration table (src/RcppExports.cpp:308-337): the nine plain-C natives keep their
+    `.Call` names and arities, the Rcpp exports on the path map `_celda_<name>` -> `_celda_cuda_<name>` with the same
+    arity (cG_CalcGibbsProbY takes beta / gamma where the reference takes the three lgamma tables: 12 for 13)."""
+    path = "/root/reference/src/RcppExports.cpp"
+    if not os.path.exists(path):
+        pytest.skip("the reference is not present on this box")
+    ref = {m.group(1): int(m.group(2)) for m in re.finditer(r'\{"(_\w+)",\s*\(DL_FUNC\)\s*&\w+,\s*(\d+)\}', open(path).read())}
+    mine = R.routines()
+    plain = [n for n in ref if not n.startswith("_celda_")]
+    assert len(plain) == 9
+    for n in plain:
+        assert mine[n] == ref[n], n
+    for n in ("colSumByGroupSparse", "rowSumByGroupSparse", "colSumByGroupChangeSparse", "rowSumByGroupChangeSparse",
+              "eigenMatMultInt", "eigenMatMultNumeric", "fastNormPropLog"):
+        assert mine["_celda_cuda_" + n] == ref["_celda_" + n], n
+    assert mine["_celda_cuda_cG_CalcGibbsProbY"] == ref["_celda_cG_CalcGibbsProbY"] - 1
+
+
 def test_shim_binds_only_declared_entry_points():
     from celda_b200 import _lib
     used = set(re.findall(r"\b(celda_\w+)\s*\(", open(SHIM).read())) - {"celda_cuda_register"}
