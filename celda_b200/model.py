@@ -241,7 +241,8 @@ def run_order(runs, cost=lambda r: r.get("K", 1) * r.get("L", 1)):
 
 
 def celdaGridSearch(counts, sampleLabel, paramsTest, maxIter=200, nchains=3, seed=12345, algorithm="Gibbs",
-                    rank=0, nranks=1, device=0, runner=None, gather=None, queue=None, isolate_failures=True, **fixed):
+                    rank=0, nranks=1, device=0, runner=None, gather=None, queue=None, isolate_failures=True,
+                    bestOnly=False, **fixed):
     """celdaGridSearch(x, model = "celda_CG", paramsTest, nchains, ...) (R/celdaGridSearch.R:214-439): every
     (chain, K, L) run is an independent single-chain celda_CG on the SAME counts (:290-391).  Each rank keeps one
     resident chain handle (counts uploaded and gene-major twin built once) and re-sizes it per run
@@ -250,7 +251,9 @@ def celdaGridSearch(counts, sampleLabel, paramsTest, maxIter=200, nchains=3, see
     GPU pulls the next run when it finishes one -- or, without a queue, the static longest-processing-time partition.
     `runner(run, seed)` -> result dict can be injected (tests); `gather` all-gathers picklable objects across ranks.
     A run that raises is reported in its runParams row (`error`, logLikelihood = NaN) and the remaining runs go on with a
-    fresh resident chain (`isolate_failures=False` re-raises, like a failed PSOCK worker fails the reference's search)."""
+    fresh resident chain (`isolate_failures=False` re-raises, like a failed PSOCK worker fails the reference's search).
+    `bestOnly=True` (the reference's default, R/celdaGridSearch.R:419-425) keeps the best chain of every parameter
+    combination (selectBestModel); the default here returns every run, which is what the benchmark legs count."""
     import time
     runs = expand_grid(paramsTest, nchains)
     resident = {"ch": None}
@@ -299,9 +302,55 @@ def celdaGridSearch(counts, sampleLabel, paramsTest, maxIter=200, nchains=3, see
             resident["ch"].close()
     everything = [local] if gather is None else gather(local)
     flat = sorted((r for part in everything for r in part), key=lambda r: r["index"])
-    return dict(runParams=[{k: r[k] for k in ("index", "chain", "K", "L", "seed", "logLikelihood", "seconds", "rank", "error")}
-                           for r in flat],
-                resList=[r["result"] for r in flat])
+    out = dict(runParams=[{k: r[k] for k in ("index", "chain", "K", "L", "seed", "logLikelihood", "seconds", "rank", "error")}
+                          for r in flat],
+               resList=[r["result"] for r in flat])
+    return selectBestModel(out, asList=True) if bestOnly else out
+
+
+_NOT_PARAMS = ("index", "chain", "logLikelihood", "mean_perplexity", "seed", "seconds", "rank", "error")
+
+
+def subsetCeldaList(res, params):
+    """subsetCeldaList(x, params) (R/celdaGridSearch.R:546-581) on a celdaGridSearch result: keep the runs whose
+    runParams match every entry of `params` (a value or a list of values per column); a single match returns that
+    model, otherwise a result of the same shape."""
+    rp = res["runParams"]
+    cols = set().union(*(r.keys() for r in rp)) if rp else set()
+    bad = [k for k in params if k not in cols]
+    if bad:
+        raise ValueError("The following elements in 'params' are not columns in runParams (x) " + ",".join(bad))
+    keep = list(range(len(rp)))
+    for k, want in params.items():
+        want = set(np.atleast_1d(want).tolist())
+        keep = [i for i in keep if rp[i][k] in want]
+        if not keep:
+            raise ValueError("No runs matched the criteria given in 'params'. Check 'runParams(x)' for complete list of "
+                             "parameters used to generate 'x'.")
+    if len(keep) == 1:
+        return res["resList"][keep[0]]
+    return dict(runParams=[rp[i] for i in keep], resList=[res["resList"][i] for i in keep])
+
+
+def selectBestModel(res, asList=False):
+    """selectBestModel(x, asList) (R/celdaGridSearch.R:668-687): for every combination of the tested parameters the
+    chain with the highest log-likelihood (`which.max`: the first one on ties, failed runs (NaN) never win), groups in
+    the order they first appear.  One combination and asList = False returns the model itself.  This is what
+    celdaGridSearch(bestOnly = TRUE), the reference's default, returns."""
+    rp = res["runParams"]
+    groups = {}
+    for i, r in enumerate(rp):
+        key = tuple((k, r[k]) for k in r if k not in _NOT_PARAMS)
+        ll = r["logLikelihood"]
+        cur = groups.get(key)
+        if cur is None:
+            groups[key] = i
+        elif not np.isnan(ll) and (np.isnan(rp[cur]["logLikelihood"]) or ll > rp[cur]["logLikelihood"]):
+            groups[key] = i
+    ix = list(groups.values())
+    if len(ix) == 1 and not asList:
+        return res["resList"][ix[0]]
+    return dict(runParams=[rp[i] for i in ix], resList=[res["resList"][i] for i in ix])
 
 
 # ------------------------------------------------------------------ cold callers of the hot path (SURVEY.md 8f N3, N4)

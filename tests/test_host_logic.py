@@ -121,3 +121,25 @@ def test_grid_search_isolates_a_failed_run():
     import pytest
     with pytest.raises(RuntimeError):
         model.celdaGridSearch(None, None, dict(K=[2, 3], L=[4]), nchains=2, runner=runner, isolate_failures=False)
+
+
+def test_selectBestModel_and_subsetCeldaList():
+    """R/celdaGridSearch.R:546-581, 668-687 on a celdaGridSearch-shaped result."""
+    from celda_b200 import model
+    runs = model.expand_grid({"K": [4, 5], "L": [9, 10]}, nchains=3)
+    lls = [-5.0, -3.0, -3.0, float("nan"), -7.0, -6.5, -1.0, -2.0, float("nan"), float("nan"), float("nan"), -9.0]
+    rp = [dict(index=r["index"], chain=r["chain"], K=r["K"], L=r["L"], seed=12345 + r["index"] - 1, logLikelihood=ll,
+               seconds=0.1, rank=0, error=None) for r, ll in zip(runs, lls)]
+    res = dict(runParams=rp, resList=[{"id": r["index"]} for r in rp])
+    best = model.selectBestModel(res, asList=True)
+    assert [(r["K"], r["L"], r["chain"]) for r in best["runParams"]] == [(4, 9, 2), (5, 9, 3), (4, 10, 1), (5, 10, 3)]
+    assert [m["id"] for m in best["resList"]] == [r["index"] for r in best["runParams"]]
+    one = model.subsetCeldaList(best, {"K": 5, "L": 10})
+    assert one == {"id": 12}                                  # a single match returns the model
+    sub = model.subsetCeldaList(res, {"K": [4], "chain": [1, 2]})
+    assert [r["index"] for r in sub["runParams"]] == [1, 2, 7, 8] and len(sub["resList"]) == 4
+    assert model.selectBestModel(model.subsetCeldaList(res, {"K": 4, "L": 9})) == {"id": 2}
+    with pytest.raises(ValueError, match="not columns in runParams"):
+        model.subsetCeldaList(res, {"Q": 1})
+    with pytest.raises(ValueError, match="No runs matched"):
+        model.subsetCeldaList(res, {"K": 6})
