@@ -238,6 +238,14 @@ def _same(got, want, names):
 def test_gibbs_closures_through_dotCall_marshal_like_the_reference(Rmock, oracle, gold_cg):
     """.cCCalcGibbsProbZ / .cGCalcGibbsProbY as celda_CG calls them (R/celda_CG.R:566-585, 544-563): same arguments, same
     named list, arguments left untouched.  The library side is the mock (CPU oracle), so this pins the shim only."""
+    n0 = Rmock.L.mock_celda_cuda_calls()
+    gibbs_closures_roundtrip(Rmock, oracle, gold_cg)
+    assert Rmock.L.mock_celda_cuda_calls() == n0 + 4  # the closure entry points resolved to the mock, not the GPU library
+
+
+def gibbs_closures_roundtrip(Rmock, oracle, gold_cg):
+    """Both Gibbs closures through `.Call` against the oracle called directly (shared with the GPU run of
+    tests/test_zz_gpu_r_shim_closures.py, where the library behind the shim is the real one)."""
     from oracle.oracle import dense_to_csc
     counts, s, K, L = gold_cg["counts"], gold_cg["s"], 5, 10
     nG, nM = counts.shape
@@ -245,7 +253,6 @@ def test_gibbs_closures_through_dotCall_marshal_like_the_reference(Rmock, oracle
     z, y = rng.integers(1, K + 1, nM).astype(np.int32), rng.integers(1, L + 1, nG).astype(np.int32)
     p = oracle.cCGDecomposeCounts(dense_to_csc(counts), s, z, y, K, L)
     ix, u = rng.permutation(nM).astype(np.int32) + 1, rng.random(nM)
-    n0 = Rmock.L.mock_celda_cuda_calls()
     for doSample in (True, False):
         want = oracle.cCCalcGibbsProbZ(p["nTSByC"], p["mCPByS"], p["nTSByCP"], p["nByC"], p["nCP"], z, s, K, L, nM, 1.0,
                                        0.7, ix, u, doSample=doSample)
@@ -276,7 +283,6 @@ def test_gibbs_closures_through_dotCall_marshal_like_the_reference(Rmock, oracle
     _same(got, want, ["nTSByC", "nGByTS", "nByTS", "y", "probs"])
     assert got["probs"].shape == (L, nG) and got["nGByTS"].dtype == np.int32 and (got["y"] != y).any()
     assert np.array_equal(Rmock.value(args[1]), p["nTSByCP"]) and np.array_equal(Rmock.value(args[5]), y)
-    assert Rmock.L.mock_celda_cuda_calls() == n0 + 4  # the closure entry points resolved to the mock, not the GPU library
 
 
 def test_em_closure_and_loglik_shims_marshal_like_the_reference(Rmock, oracle, gold_c, gold_g):
