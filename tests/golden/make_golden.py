@@ -55,7 +55,8 @@ def _sample_codes(sim_label, n):
     return np.asarray([levels.index(v) + 1 for v in labels], dtype=np.int32)
 
 
-def main():
+def main(outdir=HERE):
+    """Writes the four .npz files into `outdir` (the committed ones live next to this script)."""
     out = {}
     # ---- celda_CG
     sim = read_rda(f"{REF}/celdaCGSim.rda")["celdaCGSim"]
@@ -73,7 +74,7 @@ def main():
         completeLogLik=_vec(mod.attr["completeLogLik"], np.float64),
         **{f"param_{k}": np.float64(v) for k, v in _params(mod).items()},
     )
-    np.savez_compressed(f"{HERE}/celdaCG.npz", **cg)
+    np.savez_compressed(f"{outdir}/celdaCG.npz", **cg)
     out["celdaCG"] = cg
     # ---- celda_C
     sim = read_rda(f"{REF}/celdaCSim.rda")["celdaCSim"]
@@ -89,7 +90,7 @@ def main():
         completeLogLik=_vec(mod.attr["completeLogLik"], np.float64),
         **{f"param_{k}": np.float64(v) for k, v in _params(mod).items()},
     )
-    np.savez_compressed(f"{HERE}/celdaC.npz", **c)
+    np.savez_compressed(f"{outdir}/celdaC.npz", **c)
     out["celdaC"] = c
     # ---- celda_G
     sim = read_rda(f"{REF}/celdaGSim.rda")["celdaGSim"]
@@ -102,7 +103,7 @@ def main():
         completeLogLik=_vec(mod.attr["completeLogLik"], np.float64),
         **{f"param_{k}": np.float64(v) for k, v in _params(mod).items()},
     )
-    np.savez_compressed(f"{HERE}/celdaG.npz", **g)
+    np.savez_compressed(f"{outdir}/celdaG.npz", **g)
     out["celdaG"] = g
     # ---- grid search: 9 models on the celdaCGSim counts
     gs = read_rda(f"{REF}/celdaCGGridSearchRes.rda")["celdaCGGridSearchRes"]
@@ -125,7 +126,7 @@ def main():
         runParams_logLikelihood=cols["logLikelihood"], perplexity=_matrix(perp, np.float64),
         s=_factor_codes(res[0].attr["sampleLabel"])[0],
     )
-    np.savez_compressed(f"{HERE}/celdaCGGrid.npz", **grid)
+    np.savez_compressed(f"{outdir}/celdaCGGrid.npz", **grid)
     out["grid"] = grid
     for k, v in out.items():
         print(k, {n: (a.shape if hasattr(a, "shape") and a.shape else a) for n, a in v.items()})

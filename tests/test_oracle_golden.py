@@ -325,3 +325,22 @@ def test_walker_alias_branch_of_sample_int(oracle):
         k = min(int(rU), n - 1)
         want = (k if rU < q[k] + k else a[k]) + 1
         assert got == want
+
+
+def test_committed_fixtures_equal_a_fresh_extraction_from_the_reference(tmp_path):
+    """tests/golden/*.npz are what tests/golden/make_golden.py extracts from /root/reference/data/*.rda today (skipped on
+    a box without the reference): the fixtures the parity tests stand on were not edited by hand."""
+    import importlib.util
+    import os
+    if not os.path.isdir("/root/reference/data"):
+        pytest.skip("the reference is not present on this box")
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    mg.main(str(tmp_path))
+    for name in ("celdaCG", "celdaC", "celdaG", "celdaCGGrid"):
+        fresh, kept = np.load(tmp_path / f"{name}.npz"), np.load(os.path.join(here, f"{name}.npz"))
+        assert sorted(fresh.files) == sorted(kept.files), name
+        for k in fresh.files:
+            assert np.array_equal(fresh[k], kept[k]), (name, k)
